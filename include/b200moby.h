@@ -1,0 +1,182 @@
+/*
+ * b200moby.h -- C ABI of the B200-native time-stepping contact hot path.
+ *
+ * This is the drop-in boundary for the one path this repository accelerates
+ * (SURVEY.md section 8): narrowphase -> forward dynamics + semi-implicit Euler
+ * -> Delassus / LCP assembly -> lcp_fast / Lemke pivoting -> impulse
+ * application, run as a batch of independent simulation instances ("envs").
+ *
+ * Moby itself has no C ABI (its seams are C++ virtuals); each
+ * entry point below names the reference interface it replaces (file:line under
+ * the Moby tree).  Conventions:
+ *   - plain pointers and sizes only; no C++/torch types; no exceptions cross
+ *     the boundary; every call returns a b200moby_status;
+ *   - one handle per GPU, not thread-safe per handle;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - "_dev" pointers are device pointers on the handle's GPU, everything
+ *     else is host memory;
+ *   - all arithmetic is IEEE FP64, indices are int32;
+ *   - per-env arrays are structure-of-arrays across envs: element k of env e
+ *     lives at [k * n_envs + e]  (written [k][env] below);
+ *   - dense LCP matrices are column-major, one contiguous n*n block per
+ *     problem: M[b*n*n + c*n + r].
+ */
+#ifndef B200MOBY_H
+#define B200MOBY_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MOBY_ABI_VERSION 1
+
+typedef enum {
+  B200MOBY_OK = 0,
+  B200MOBY_ERR_INVALID = 1,      /* bad argument */
+  B200MOBY_ERR_CUDA = 2,         /* CUDA runtime error (see b200moby_last_error) */
+  B200MOBY_ERR_UNSUPPORTED = 3,  /* scene needs a feature outside the hot path */
+  B200MOBY_ERR_NO_DEVICE = 4     /* no sm_100 device: there is no CPU fallback */
+} b200moby_status;
+
+/* Per-LCP solver status words (written by the kernels; never abort a batch).
+ * They mirror the bool / exception cascade of LCP.cpp:212-487. */
+enum {
+  B200MOBY_LCP_OK = 0,            /* solved, no regularisation */
+  B200MOBY_LCP_TRIVIAL = 1,       /* q >= -zero_tol: z = 0 (LCP.cpp:578-584, :89-95) */
+  B200MOBY_LCP_RAY = 2,           /* Lemke ray termination (LCP.cpp:892-903) */
+  B200MOBY_LCP_MAXITER = 3,       /* iteration cap (LCP.cpp:548, :107) */
+  B200MOBY_LCP_SINGULAR = 4,      /* exact zero pivot in the basis solve (LCP.cpp:122, :840) */
+  B200MOBY_LCP_EMPTY_RATIO = 5,   /* "zero tolerance too low" (LCP.cpp:946-958) */
+  B200MOBY_LCP_UNVERIFIED = 6,    /* regularised wrapper: no lambda passed the checks */
+  B200MOBY_LCP_REGULARIZED = 16   /* OK after regularisation: 16 + attempt index (0-based) */
+};
+
+/* Shapes the narrowphase handles. */
+enum { B200MOBY_SHAPE_NONE = 0, B200MOBY_SHAPE_SPHERE = 1, B200MOBY_SHAPE_BOX = 2, B200MOBY_SHAPE_PLANE = 3 };
+
+/* Impact models (ImpactConstraintHandler.cpp:122-146). */
+enum {
+  B200MOBY_MODEL_QP = 0,   /* default build: QP-as-LCP, ImpactConstraintHandlerQP.cpp:94-263 */
+  B200MOBY_MODEL_AP = 1    /* -DUSE_AP_MODEL: Anitescu-Potra LCP, ImpactConstraintHandlerLCP.cpp:94-370 */
+};
+
+#define B200MOBY_MAX_BODIES 16
+
+/*
+ * Batch scene descriptor: `n_bodies` rigid bodies per env (static ones
+ * included), one collision geometry per body located at the body frame
+ * (primitive pose = identity), `n_envs` independent copies whose parameters may
+ * differ per env.  Replaces the object graph XMLReader::read builds
+ * (XMLReader.cpp:60-132) for the scenes in BASELINE.json.
+ *
+ * All arrays are host pointers, copied at create time.
+ */
+typedef struct {
+  int n_envs;
+  int n_bodies;
+  /* [body][env] */
+  const int*    shape;      /* B200MOBY_SHAPE_* */
+  const int*    enabled;    /* RigidBody enabled= (0: static) */
+  const double* mass;       /* kg; ignored for disabled bodies */
+  /* [body][3][env] */
+  const double* dims;       /* box: xlen,ylen,zlen; sphere: radius,-,-; plane: -,-,- (plane is y=0 of the body frame, BoxPrimitive.cpp:358, PlanePrimitive.cpp:477) */
+  const double* inertia;    /* principal body-frame inertia (InertiaFromPrimitive) */
+  /* contact parameters, [body_i*n_bodies + body_j][env] for i<j (ContactParameters.cpp:97-136) */
+  const double* mu_coulomb;
+  const double* mu_viscous;
+  const double* epsilon;
+  const double* compliance;
+  const int*    NK;         /* friction-cone-edges (>=4, even); 0 = pair disabled (<DisabledPair>) */
+  double gravity[3];            /* GravityForce accel= (GravityForce.cpp:32-68) */
+  double contact_dist_thresh;   /* ConstraintSimulator.cpp:56, default 1e-6 */
+  double min_step_size;         /* TimeSteppingSimulator.cpp:48, default sqrt(eps) */
+  int    impact_model;          /* B200MOBY_MODEL_* */
+  int    stabilization_max_iterations; /* must be 0 this round */
+} b200moby_scene_desc;
+
+typedef struct b200moby_sim* b200moby_handle;
+
+/* Device-side counters, summed over envs (SURVEY.md section 5 "Metrics"). */
+typedef struct {
+  long long env_steps;        /* TimeSteppingSimulator::step calls x envs */
+  long long mini_steps;       /* do_mini_step calls (TimeSteppingSimulator.cpp:114) */
+  long long lcp_solves;       /* impact problems handed to the LCP solver */
+  long long lcp_fast_calls;   /* lcp_fast invocations, regularised retries included */
+  long long lemke_calls;      /* lcp_lemke invocations, regularised retries included */
+  long long pivots;           /* total pivots / iterations */
+  long long lcp_failures;     /* LCPSolverException equivalents (ImpactConstraintHandlerQP.cpp:224) */
+  long long impact_tol_events;/* ImpactToleranceException equivalents (ImpactConstraintHandler.cpp:153-167) */
+  long long contacts;         /* contact constraints generated */
+  long long max_lcp_n;        /* largest LCP dimension seen */
+} b200moby_counters;
+
+const char* b200moby_last_error(void);
+int b200moby_abi_version(void);
+/* Number of visible sm_100 devices (0 => every compute call returns NO_DEVICE). */
+int b200moby_device_count(void);
+
+/* ---- simulator: replaces TimeSteppingSimulator::step (TimeSteppingSimulator.cpp:52-111) ---- */
+b200moby_status b200moby_create(const b200moby_scene_desc* desc, int device, b200moby_handle* out);
+b200moby_status b200moby_destroy(b200moby_handle h);
+/* q: [body][7][env] = x y z qx qy qz qw (Euler coordinates, regress.cpp:78-95);
+ * v: [body][6][env] = linear, angular velocity at the COM in a global-aligned frame. Host buffers. */
+b200moby_status b200moby_set_state(b200moby_handle h, const double* q, const double* v);
+b200moby_status b200moby_get_state(b200moby_handle h, double* q, double* v);
+/* Same with device buffers (no host round trip). */
+b200moby_status b200moby_set_state_dev(b200moby_handle h, const double* q_dev, const double* v_dev, void* stream);
+b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q_dev, double* v_dev, void* stream);
+/* n_steps x step(dt) for every env; asynchronous on `stream`. */
+b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* stream);
+b200moby_status b200moby_get_counters(b200moby_handle h, b200moby_counters* out);
+b200moby_status b200moby_reset_counters(b200moby_handle h);
+/* Simulated time per env, [env] host buffer (Simulator::current_time). */
+b200moby_status b200moby_get_time(b200moby_handle h, double* t);
+/* Debug tap: LCP of the last impact solve of each env. MM_dev: [env][nmax*nmax] column-major with
+ * leading dimension n[env]; any pointer may be NULL. */
+b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int zcap);
+
+/* ---- batched solvers: replace LCP::lcp_lemke / lcp_fast and wrappers (LCP.h:21-27) ----
+ * M_dev [batch][n*n] column-major, q_dev [batch][n], z_dev [batch][n] (in: warm start for lcp_fast, out: solution),
+ * status_dev [batch], pivots_dev [batch] (may be NULL), pivot_log_dev [batch][log_cap] (may be NULL):
+ *   Lemke logs the leaving basis position per pivot, lcp_fast logs (moved index | 0x40000000 if moved to basic).
+ * piv_tol / zero_tol <= 0 select the reference defaults (LCP.cpp:570-571, :761, :57-58). */
+b200moby_status b200moby_lcp_lemke_batched(int batch, int n, const double* M_dev, const double* q_dev, double* z_dev,
+                                           double piv_tol, double zero_tol, int* status_dev, int* pivots_dev,
+                                           int* pivot_log_dev, int log_cap, void* stream);
+b200moby_status b200moby_lcp_fast_batched(int batch, int n, const double* M_dev, const double* q_dev, double* z_dev,
+                                          int warm_start, double zero_tol, int* status_dev, int* pivots_dev,
+                                          int* pivot_log_dev, int log_cap, void* stream);
+/* Regularised wrappers (LCP.cpp:212-350, :353-487): lambda = 10^rf for rf = min_exp; rf < max_exp; rf += step_exp. */
+b200moby_status b200moby_lcp_lemke_regularized_batched(int batch, int n, const double* M_dev, const double* q_dev,
+                                                       double* z_dev, int min_exp, int step_exp, int max_exp,
+                                                       double piv_tol, double zero_tol, int* status_dev,
+                                                       int* pivots_dev, void* stream);
+b200moby_status b200moby_lcp_fast_regularized_batched(int batch, int n, const double* M_dev, const double* q_dev,
+                                                      double* z_dev, int warm_start, int min_exp, int step_exp,
+                                                      int max_exp, double zero_tol, int* status_dev, int* pivots_dev,
+                                                      void* stream);
+/* Host-buffer convenience forms: H2D, solve, D2H, synchronise (the call a Moby LCP object would make). */
+b200moby_status b200moby_lcp_lemke_host(int batch, int n, const double* M, const double* q, double* z, double piv_tol,
+                                        double zero_tol, int* status, int* pivots, int device);
+b200moby_status b200moby_lcp_fast_host(int batch, int n, const double* M, const double* q, double* z, int warm_start,
+                                       double zero_tol, int* status, int* pivots, int device);
+
+/* ---- stage kernels, exposed for parity tests and for callers that keep Moby's own step loop ---- */
+/* Forward dynamics + velocity half of semi-implicit Euler for free rigid bodies
+ * (Simulator.cpp:319-350,482-602; TimeSteppingSimulator.cpp:181-192). q_dev [body][7][env], v_dev [body][6][env] in/out. */
+b200moby_status b200moby_fwd_dyn_batched(b200moby_handle h, const double* q_dev, double* v_dev, double dt, void* stream);
+/* Narrowphase for every body pair (CCD.inl:3-82 and leaves). Outputs, per env, up to `cap` contacts:
+ * count_dev [env]; point/normal/tan1/tan2 [cap][3][env]; pair_dev [cap][env] = body1*n_bodies+body2; dist_dev [cap][env]. */
+b200moby_status b200moby_find_contacts_batched(b200moby_handle h, const double* q_dev, const double* v_dev, int cap, int* count_dev,
+                                               double* point_dev, double* normal_dev, double* tan1_dev,
+                                               double* tan2_dev, int* pair_dev, double* dist_dev, void* stream);
+/* Delassus / LCP assembly for the contacts found at (q,v): writes MM [env][nmax*nmax] (column-major, ld = n[env]),
+ * qq [env][nmax], n_dev [env] (ImpactConstraintHandler.cpp:1898-2166 + ImpactConstraintHandlerQP.cpp:271-497
+ * or ImpactConstraintHandlerLCP.cpp:94-310). Only the first island of each env is assembled. */
+b200moby_status b200moby_delassus_batched(b200moby_handle h, const double* q_dev, const double* v_dev, int nmax,
+                                          double* MM_dev, double* qq_dev, int* n_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MOBY_H */

@@ -1,0 +1,210 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked into the product library.
+// extern "C" surface so tests / bench.py's cpu_baseline leg can drive the CPU oracle through ctypes.
+// It consumes the same plain-C batch descriptor as the product (include/b200moby.h is a data-format
+// header only) so one synthetic scene feeds both sides.
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "../include/b200moby.h"
+#include "oracle_lcp.h"
+#include "oracle_sim.h"
+
+using namespace oracle;
+
+extern "C" {
+
+// ---- LCP solvers.  M column-major n*n.  z: in (warm start when warm!=0) / out.  log may be NULL. Returns 1 on success.
+int oracle_lcp_lemke(int n, const double* M, const double* q, double* z, double piv_tol, double zero_tol, int tie,
+                     int* pivots, int* status, int* log, int log_cap, int* log_len) {
+  LCP lcp; lcp.tie = (TieRule)tie; lcp.keep_log = (log != nullptr);
+  Vec zz(n, 0.0);
+  bool ok = lcp.lcp_lemke(n, M, q, zz, piv_tol, zero_tol);
+  for (int i = 0; i < n; i++) z[i] = (i < (int)zz.size()) ? zz[i] : 0.0;
+  if (pivots) *pivots = (int)lcp.pivots;
+  if (status) *status = lcp.status;
+  if (log) { int m = std::min<int>(log_cap, (int)lcp.log.size()); for (int i = 0; i < m; i++) log[i] = lcp.log[i]; }
+  if (log_len) *log_len = (int)lcp.log.size();
+  return ok ? 1 : 0;
+}
+
+int oracle_lcp_fast(int n, const double* M, const double* q, double* z, int warm, double zero_tol, int tie, int* pivots,
+                    int* status, int* log, int log_cap, int* log_len) {
+  LCP lcp; lcp.tie = (TieRule)tie; lcp.keep_log = (log != nullptr);
+  Vec zz;
+  if (warm) zz.assign(z, z + n);
+  bool ok = lcp.lcp_fast(n, M, q, zz, zero_tol);
+  if (ok) for (int i = 0; i < n; i++) z[i] = zz[i];
+  if (pivots) *pivots = (int)lcp.pivots;
+  if (status) *status = lcp.status;
+  if (log) { int m = std::min<int>(log_cap, (int)lcp.log.size()); for (int i = 0; i < m; i++) log[i] = lcp.log[i]; }
+  if (log_len) *log_len = (int)lcp.log.size();
+  return ok ? 1 : 0;
+}
+
+int oracle_lcp_fast_regularized(int n, const double* M, const double* q, double* z, int warm, int min_exp, int step_exp,
+                                int max_exp, double zero_tol, int tie, int* pivots, int* status) {
+  LCP lcp; lcp.tie = (TieRule)tie;
+  Vec zz;
+  if (warm) zz.assign(z, z + n);
+  bool ok = lcp.lcp_fast_regularized(n, M, q, zz, min_exp, (unsigned)step_exp, max_exp, -1.0, zero_tol);
+  if (zz.size() == (size_t)n) for (int i = 0; i < n; i++) z[i] = zz[i];
+  if (pivots) *pivots = (int)lcp.pivots;
+  if (status) *status = lcp.status;
+  return ok ? 1 : 0;
+}
+
+int oracle_lcp_lemke_regularized(int n, const double* M, const double* q, double* z, int min_exp, int step_exp, int max_exp,
+                                 double piv_tol, double zero_tol, int tie, int* pivots, int* status) {
+  LCP lcp; lcp.tie = (TieRule)tie;
+  Vec zz(n, 0.0);
+  bool ok = lcp.lcp_lemke_regularized(n, M, q, zz, min_exp, (unsigned)step_exp, max_exp, piv_tol, zero_tol);
+  for (int i = 0; i < n; i++) z[i] = (ok && i < (int)zz.size()) ? zz[i] : 0.0;
+  if (pivots) *pivots = (int)lcp.pivots;
+  if (status) *status = lcp.status;
+  return ok ? 1 : 0;
+}
+
+// ---- simulator ----
+struct OracleSim { Sim sim; };
+
+static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
+  const int nb = d->n_bodies, ne = d->n_envs;
+  S.init(nb);
+  for (int b = 0; b < nb; b++) {
+    Body& B = S.bodies[b];
+    B.shape = d->shape[(size_t)b * ne + e];
+    B.enabled = d->enabled[(size_t)b * ne + e] != 0;
+    B.mass = d->mass[(size_t)b * ne + e];
+    for (int k = 0; k < 3; k++) {
+      B.dims[k] = d->dims[((size_t)b * 3 + k) * ne + e];
+      B.J[k] = d->inertia[((size_t)b * 3 + k) * ne + e];
+    }
+  }
+  for (int i = 0; i < nb; i++)
+    for (int j = i + 1; j < nb; j++) {
+      ContactParams& c = S.cparams[(size_t)i * nb + j];
+      const size_t o = ((size_t)i * nb + j) * ne + e;
+      c.mu_c = d->mu_coulomb[o]; c.mu_v = d->mu_viscous[o]; c.eps = d->epsilon[o]; c.compliance = d->compliance[o]; c.NK = d->NK[o];
+    }
+  S.gravity = V3(d->gravity[0], d->gravity[1], d->gravity[2]);
+  S.contact_dist_thresh = d->contact_dist_thresh;
+  S.min_step_size = d->min_step_size;
+  S.model = d->impact_model;
+}
+
+void* oracle_sim_create(const b200moby_scene_desc* d, int env, int tie) {
+  OracleSim* o = new OracleSim;
+  fill_from_desc(o->sim, d, env);
+  o->sim.lcp.tie = (TieRule)tie;
+  return o;
+}
+void oracle_sim_destroy(void* h) { delete (OracleSim*)h; }
+
+// q: [body][7], v: [body][6] (AoS for one env)
+static void set_state(Sim& S, const double* q, const double* v) {
+  for (size_t b = 0; b < S.bodies.size(); b++) {
+    Body& B = S.bodies[b];
+    B.x = V3(q[b * 7 + 0], q[b * 7 + 1], q[b * 7 + 2]);
+    double nrm = 0; for (int k = 0; k < 4; k++) nrm += q[b * 7 + 3 + k] * q[b * 7 + 3 + k];
+    nrm = std::sqrt(nrm);
+    for (int k = 0; k < 4; k++) B.quat[k] = q[b * 7 + 3 + k] / nrm;
+    S.update_pose(B);
+    B.vl = V3(v[b * 6 + 0], v[b * 6 + 1], v[b * 6 + 2]);
+    B.va = V3(v[b * 6 + 3], v[b * 6 + 4], v[b * 6 + 5]);
+  }
+}
+void oracle_sim_set_state(void* h, const double* q, const double* v) { set_state(((OracleSim*)h)->sim, q, v); }
+static void get_state(Sim& S, double* q, double* v) {
+  for (size_t b = 0; b < S.bodies.size(); b++) {
+    const Body& B = S.bodies[b];
+    q[b * 7 + 0] = B.x.x; q[b * 7 + 1] = B.x.y; q[b * 7 + 2] = B.x.z;
+    for (int k = 0; k < 4; k++) q[b * 7 + 3 + k] = B.quat[k];
+    v[b * 6 + 0] = B.vl.x; v[b * 6 + 1] = B.vl.y; v[b * 6 + 2] = B.vl.z;
+    v[b * 6 + 3] = B.va.x; v[b * 6 + 4] = B.va.y; v[b * 6 + 5] = B.va.z;
+  }
+}
+void oracle_sim_get_state(void* h, double* q, double* v) { get_state(((OracleSim*)h)->sim, q, v); }
+void oracle_sim_step(void* h, double dt, int n_steps) {
+  Sim& S = ((OracleSim*)h)->sim;
+  for (int i = 0; i < n_steps; i++) S.step(dt);
+}
+double oracle_sim_time(void* h) { return ((OracleSim*)h)->sim.current_time; }
+void oracle_sim_counters(void* h, b200moby_counters* c) {
+  const Counters& k = ((OracleSim*)h)->sim.cnt;
+  c->env_steps = k.env_steps; c->mini_steps = k.mini_steps; c->lcp_solves = k.lcp_solves; c->lcp_fast_calls = k.lcp_fast_calls;
+  c->lemke_calls = k.lemke_calls; c->pivots = k.pivots; c->lcp_failures = k.lcp_failures; c->impact_tol_events = k.impact_tol_events;
+  c->contacts = k.contacts; c->max_lcp_n = k.max_lcp_n;
+}
+// LCP of the most recent impact solve: returns n; copies min(n*n, cap) etc.
+int oracle_sim_last_lcp(void* h, double* MM, double* qq, double* z, int ncap) {
+  Sim& S = ((OracleSim*)h)->sim;
+  const int n = S.last_n;
+  if (n <= ncap) {
+    if (MM) std::memcpy(MM, S.last_MM.data(), sizeof(double) * (size_t)n * n);
+    if (qq) std::memcpy(qq, S.last_qq.data(), sizeof(double) * n);
+    if (z) std::memcpy(z, S.last_z.data(), sizeof(double) * n);
+  }
+  return n;
+}
+// contacts of the most recent mini-step: point, normal, tan1, tan2 as [cap][3]; pair = b1*nb+b2; returns count
+int oracle_sim_last_contacts(void* h, int cap, double* point, double* normal, double* tan1, double* tan2, int* pair, double* dist) {
+  Sim& S = ((OracleSim*)h)->sim;
+  const int nb = (int)S.bodies.size();
+  const int m = (int)S.last_contacts.size();
+  for (int i = 0; i < m && i < cap; i++) {
+    const Contact& c = S.last_contacts[i];
+    for (int k = 0; k < 3; k++) { point[i * 3 + k] = c.p[k]; normal[i * 3 + k] = c.n[k]; tan1[i * 3 + k] = c.t1[k]; tan2[i * 3 + k] = c.t2[k]; }
+    pair[i] = c.b1 * nb + c.b2; dist[i] = c.dist;
+  }
+  return m;
+}
+// Contacts + first-island LCP at the current state without stepping (assembly parity): returns n (0 if no impact)
+int oracle_sim_assemble(void* h, double* MM, double* qq, int ncap, int* n_contacts) {
+  Sim& S = ((OracleSim*)h)->sim;
+  std::vector<std::pair<int, int> > pairs; std::vector<PairDist> pd; std::vector<Contact> cons;
+  S.broad_phase(pairs); S.calc_pairwise_distances(pairs, pd); S.find_unilateral_constraints(pd, cons);
+  if (n_contacts) *n_contacts = (int)cons.size();
+  if (cons.empty()) return 0;
+  std::vector<Contact*> cp; std::vector<int> ib;
+  for (auto& c : cons) { cp.push_back(&c); ib.push_back(c.b1); ib.push_back(c.b2); }
+  int n; Vec M, q;
+  S.assemble_island_lcp(cp, ib, n, M, q);
+  if (n <= ncap) { std::memcpy(MM, M.data(), sizeof(double) * (size_t)n * n); std::memcpy(qq, q.data(), sizeof(double) * n); }
+  return n;
+}
+
+// Batch driver for tests / the CPU baseline: steps envs [e0,e1) of the descriptor `n_steps` times with `threads`
+// host threads.  q,v use the product's SoA layout ([body][7][env], [body][6][env]) and are updated in place.
+void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e0, int e1, double dt, int n_steps, int tie,
+                       int threads, b200moby_counters* total) {
+  const int nb = d->n_bodies, ne = d->n_envs;
+  if (threads < 1) threads = 1;
+  std::vector<Counters> cs(threads);
+  auto work = [&](int t) {
+    std::vector<double> qa(nb * 7), va(nb * 6);
+    for (int e = e0 + t; e < e1; e += threads) {
+      Sim S; fill_from_desc(S, d, e); S.lcp.tie = (TieRule)tie;
+      for (int b = 0; b < nb; b++) { for (int k = 0; k < 7; k++) qa[b * 7 + k] = q[((size_t)b * 7 + k) * ne + e]; for (int k = 0; k < 6; k++) va[b * 6 + k] = v[((size_t)b * 6 + k) * ne + e]; }
+      set_state(S, qa.data(), va.data());
+      for (int i = 0; i < n_steps; i++) S.step(dt);
+      get_state(S, qa.data(), va.data());
+      for (int b = 0; b < nb; b++) { for (int k = 0; k < 7; k++) q[((size_t)b * 7 + k) * ne + e] = qa[b * 7 + k]; for (int k = 0; k < 6; k++) v[((size_t)b * 6 + k) * ne + e] = va[b * 6 + k]; }
+      Counters& c = cs[t]; const Counters& k = S.cnt;
+      c.env_steps += k.env_steps; c.mini_steps += k.mini_steps; c.lcp_solves += k.lcp_solves; c.lcp_fast_calls += k.lcp_fast_calls;
+      c.lemke_calls += k.lemke_calls; c.pivots += k.pivots; c.lcp_failures += k.lcp_failures; c.impact_tol_events += k.impact_tol_events;
+      c.contacts += k.contacts; c.max_lcp_n = std::max(c.max_lcp_n, k.max_lcp_n);
+    }
+  };
+  if (threads == 1) work(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+  if (total) {
+    std::memset(total, 0, sizeof(*total));
+    for (auto& c : cs) {
+      total->env_steps += c.env_steps; total->mini_steps += c.mini_steps; total->lcp_solves += c.lcp_solves; total->lcp_fast_calls += c.lcp_fast_calls;
+      total->lemke_calls += c.lemke_calls; total->pivots += c.pivots; total->lcp_failures += c.lcp_failures; total->impact_tol_events += c.impact_tol_events;
+      total->contacts += c.contacts; total->max_lcp_n = std::max(total->max_lcp_n, c.max_lcp_n);
+    }
+  }
+}
+
+}  // extern "C"
