@@ -1,0 +1,382 @@
+// Group-cooperative LCP solvers: Lemke complementary pivoting on an on-chip tableau and the
+// principal-pivoting `lcp_fast`, each with the reference's regularised wrapper.
+//
+// Behavioural contract = Moby src/LCP.cpp (lcp_fast :41-196, rand_min :199-209 with the documented
+// lowest-index tie rule, wrappers :212-487, lcp_lemke :545-1003): same tolerances, same entering /
+// leaving rules, same iteration caps, same failure cascade.  What is different is how the numbers are
+// produced: the reference re-factorises the n x n basis with LU for every Lemke pivot (O(n^3) per
+// pivot); here the tableau B^-1 [N | q] lives in shared memory and a pivot is one rank-one update
+// (2 n (n+2) flops) done by all threads of the group.
+#pragma once
+#include "common.cuh"
+
+namespace b2m {
+
+enum {
+  LCP_OK = 0, LCP_TRIVIAL = 1, LCP_RAY = 2, LCP_MAXITER = 3, LCP_SINGULAR = 4, LCP_EMPTY_RATIO = 5,
+  LCP_UNVERIFIED = 6, LCP_REGULARIZED = 16
+};
+
+// element (r,c) of M + lambda I
+__device__ __forceinline__ double m_at(const double* M, int ldm, int r, int c, double lambda) {
+  double v = M[(size_t)c * ldm + r];
+  return (r == c) ? v + lambda : v;
+}
+
+// MatrixNd::norm_inf() of M + lambda I: largest |entry|
+template <class G>
+__device__ double norm_inf(const G& g, int n, const double* M, int ldm, double lambda) {
+  double m = 0.0;
+  for (int e = g.tid; e < n * n; e += G::size) {
+    const int c = e / n, r = e - c * n;
+    m = fmax(m, fabs(m_at(M, ldm, r, c, lambda)));
+  }
+  return g.max(m);
+}
+
+// LCP::rand_min with the lowest-index tie rule: first minimum, then the lowest index i with v[i] < v[min] + tol.
+template <class G>
+__device__ int rand_min(const G& g, const double* v, int m, double tol) {
+  double key = B2M_INF; int idx = 0x7fffffff;
+  for (int i = g.tid; i < m; i += G::size) { const double x = v[i]; if (x < key) { key = x; idx = i; } }
+  g.min_key_idx(key, idx);
+  const double thr = key + tol;
+  int cand = 0x7fffffff;
+  for (int i = g.tid; i < idx; i += G::size) if (v[i] < thr) { cand = i; break; }
+  cand = g.min(cand);
+  return cand < idx ? cand : idx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lemke.  Work memory: T  n*(n+2) doubles (column-major, ld n: slots 0..n nonbasic columns, column n+1 = x),
+//                      dvec n, rvec n+2 doubles; where 2n+1, bas n ints.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t lemke_work_doubles(int n) { return (size_t)n * (n + 2) + n + (n + 2); }
+__host__ __device__ inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
+
+template <class G>
+__device__ int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
+                           double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
+                           int* log, int log_cap, int* log_len) {
+  double* T = wd;
+  double* dvec = T + (size_t)n * (n + 2);
+  double* rvec = dvec + n;
+  int* where = wi;            // variable id -> nonbasic slot (>= 0) or -(row+1) when basic
+  int* bas = wi + 2 * n + 1;  // row -> variable id
+  double* xcol = T + (size_t)n * (n + 1);
+  const int t = 2 * n;
+  const int MAXITER = min(1000, 50 * n);                                   // LCP.cpp:548
+  int nlog = 0, piv = 0, status = LCP_OK;
+
+  const double nrm = norm_inf(g, n, M, ldm, lambda);
+  if (zero_tol <= 0.0) zero_tol = B2M_EPS * nrm * n;                       // :570-571
+  const double PIV_TOL = (piv_tol > 0.0) ? piv_tol : B2M_EPS * n * fmax(1.0, nrm);   // :761
+  // trivial solution (:578-584)
+  double mq = B2M_INF;
+  for (int i = g.tid; i < n; i += G::size) mq = fmin(mq, q[i]);
+  mq = g.min(mq);
+  for (int i = g.tid; i < n; i += G::size) z[i] = 0.0;
+  if (mq > -zero_tol) { if (pivots_out) *pivots_out = 0; if (log_len) *log_len = 0; g.sync(); return LCP_TRIVIAL; }
+  if (!(mq < 0.0)) { if (pivots_out) *pivots_out = 0; if (log_len) *log_len = 0; g.sync(); return LCP_OK; }   // :737-758
+
+  // initial tableau: B = -I  =>  B^-1 M[:,j] = -M[:,j];  cover column B^-1 u = -u with u_i = [q_i < 0]   (:696-698,776-785)
+  for (int e = g.tid; e < n * n; e += G::size) { const int c = e / n, r = e - c * n; T[e] = -m_at(M, ldm, r, c, lambda); }
+  for (int i = g.tid; i < n; i += G::size) {
+    const double qi = q[i];
+    T[(size_t)n * n + i] = (qi < 0.0) ? -1.0 : 0.0;
+    xcol[i] = qi;
+    where[i] = i; where[n + i] = -(i + 1); bas[i] = n + i;
+  }
+  if (g.tid == 0) where[t] = n;
+  g.sync();
+
+  // first leaving row: first minimum of x (:764-771); entering: the artificial variable
+  int r; { double key = B2M_INF; int idx = 0x7fffffff;
+    for (int i = g.tid; i < n; i += G::size) { const double x = xcol[i]; if (x < key) { key = x; idx = i; } }
+    g.min_key_idx(key, idx); r = idx; }
+  int s = n;           // entering slot
+  int entering = t;
+  bool first = true;   // the first pass pivots the artificial variable in (LCP.cpp:776-785); `piv` counts the pivots after it
+  for (;;) {
+    // entering column
+    for (int i = g.tid; i < n; i += G::size) dvec[i] = T[(size_t)s * n + i];
+    g.sync();
+    if (!first) {
+      // ratio test (:886-975)
+      double theta = B2M_INF; bool anycand = false;
+      for (int i = g.tid; i < n; i += G::size) { const double d = dvec[i]; if (d > PIV_TOL) { anycand = true; theta = fmin(theta, (xcol[i] + zero_tol) / d); } }
+      if (!g.any(anycand)) { status = LCP_RAY; break; }
+      theta = g.min(theta);
+      int lo = 0x7fffffff;
+      const int trow = -(where[t] + 1);
+      bool tpass = false;
+      for (int i = g.tid; i < n; i += G::size) {
+        const double d = dvec[i];
+        if (d > PIV_TOL && xcol[i] / d <= theta) { if (i < lo) lo = i; if (i == trow) tpass = true; }
+      }
+      lo = g.min(lo);
+      if (lo == 0x7fffffff) { status = LCP_EMPTY_RATIO; break; }
+      r = g.any(tpass) ? trow : lo;
+    }
+    const int leaving = bas[r];
+    const double p = dvec[r];
+    g.sync();                                   // everyone has read bas/where/dvec[r] before they change
+    // pivot row, scaled; the leaving variable's column (a unit vector while basic) replaces slot s
+    for (int c = g.tid; c < n + 2; c += G::size) rvec[c] = (c == s) ? 1.0 / p : T[(size_t)c * n + r] / p;
+    for (int i = g.tid; i < n; i += G::size) T[(size_t)s * n + i] = 0.0;
+    if (g.tid == 0) {
+      if (log && nlog < log_cap) log[nlog] = leaving;
+      where[entering] = -(r + 1); where[leaving] = s; bas[r] = entering;
+    }
+    nlog++;
+    g.sync();
+    // rank-one update of the whole tableau (x included)
+    {
+      int i = g.tid % n, c = g.tid / n;
+      const int total = n * (n + 2);
+      for (int e = g.tid; e < total; e += G::size) {
+        T[e] = (i == r) ? rvec[c] : fma(-dvec[i], rvec[c], T[e]);
+        i += G::size; while (i >= n) { i -= n; c++; }
+      }
+    }
+    g.sync();
+    if (!first) piv++;
+    first = false;
+    if (leaving == t) break;                                               // :800-822 solved
+    if (piv >= MAXITER) { status = LCP_MAXITER; break; }                   // :789
+    entering = (leaving < n) ? n + leaving : leaving - n;                  // :823-833 complement
+    s = where[entering];
+  }
+  if (status == LCP_OK) {
+    for (int i = g.tid; i < n; i += G::size) { const int b = bas[i]; if (b < n) z[b] = xcol[i]; }
+  }
+  if (pivots_out) *pivots_out = piv;
+  if (log_len) *log_len = nlog;
+  g.sync();
+  return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lcp_fast.  Work memory: A n*n, zz n, w n doubles; nonbas n, bas n ints (+2 ints of scalars).
+// The sub-system solve follows the oracle's LU order operation for operation (partial pivoting on the
+// first maximum, reciprocal multipliers, fma updates, column-oriented back substitution) so results are
+// bit-identical to the CPU checker.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t fast_work_doubles(int n) { return (size_t)n * n + 2 * (size_t)n; }
+__host__ __device__ inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2; }
+
+// solves A x = b (A k x k column-major ld k, destroyed; b <- x).  Returns false on an exactly zero pivot.
+template <class G>
+__device__ bool lu_solve(const G& g, int k, double* A, double* b) {
+  for (int j = 0; j < k; j++) {
+    double key = 1.0; int p = 0x7fffffff;                       // lexicographic min of (-|a|, i) == first maximum
+    for (int i = j + g.tid; i < k; i += G::size) { const double v = -fabs(A[(size_t)j * k + i]); if (v < key) { key = v; p = i; } }
+    g.min_key_idx(key, p);
+    if (key == 0.0 || p == 0x7fffffff) return false;
+    if (p != j) {
+      for (int c = g.tid; c < k; c += G::size) { const double tmp = A[(size_t)c * k + j]; A[(size_t)c * k + j] = A[(size_t)c * k + p]; A[(size_t)c * k + p] = tmp; }
+      if (g.tid == 0) { const double tmp = b[j]; b[j] = b[p]; b[p] = tmp; }
+    }
+    g.sync();
+    const double rinv = 1.0 / A[(size_t)j * k + j];
+    const double bj = b[j];
+    for (int i = j + 1 + g.tid; i < k; i += G::size) {
+      const double l = A[(size_t)j * k + i] * rinv;
+      A[(size_t)j * k + i] = l;
+      for (int c = j + 1; c < k; c++) A[(size_t)c * k + i] = fma(-l, A[(size_t)c * k + j], A[(size_t)c * k + i]);
+      b[i] = fma(-l, bj, b[i]);
+    }
+    g.sync();
+  }
+  for (int c = k - 1; c >= 0; c--) {
+    const double xc = b[c] / A[(size_t)c * k + c];
+    g.sync();
+    if (g.tid == 0) b[c] = xc;
+    for (int i = g.tid; i < c; i += G::size) b[i] = fma(-A[(size_t)c * k + i], xc, b[i]);
+    g.sync();
+  }
+  return true;
+}
+
+__device__ inline void list_erase(int* L, int& m, int pos) { for (int i = pos; i + 1 < m; i++) L[i] = L[i + 1]; m--; }
+__device__ inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while (i > 0 && L[i - 1] > v) { L[i] = L[i - 1]; i--; } L[i] = v; m++; }
+
+template <class G>
+__device__ int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
+                              bool warm, double* z, double* wd, int* wi, int* pivots_out, int* log, int log_cap,
+                              int* log_len) {
+  double* A = wd;
+  double* zz = A + (size_t)n * n;
+  double* w = zz + n;
+  int* nonbas = wi;
+  int* bas = wi + n;
+  int* cnt = wi + 2 * n;      // cnt[0] = |nonbas|, cnt[1] = |bas|
+  int nlog = 0;
+  if (zero_tol < 0.0) zero_tol = n * norm_inf(g, n, M, ldm, lambda) * B2M_EPS;      // LCP.cpp:57-58
+  if (warm) {                                                                        // :65-85
+    if (g.tid == 0) {
+      int k = 0, nb = 0;
+      for (int i = 0; i < n; i++) { if (fabs(z[i]) < zero_tol) bas[nb++] = i; else nonbas[k++] = i; }
+      cnt[0] = k; cnt[1] = nb;
+    }
+  } else {                                                                           // :86-103
+    double key = B2M_INF; int idx = 0x7fffffff;
+    for (int i = g.tid; i < n; i += G::size) { const double x = q[i]; if (x < key) { key = x; idx = i; } }
+    g.min_key_idx(key, idx);
+    if (key > -zero_tol) {
+      for (int i = g.tid; i < n; i += G::size) z[i] = 0.0;
+      if (pivots_out) *pivots_out = 0; if (log_len) *log_len = 0;
+      g.sync();
+      return LCP_TRIVIAL;
+    }
+    if (g.tid == 0) { nonbas[0] = idx; int nb = 0; for (int i = 0; i < n; i++) if (i != idx) bas[nb++] = i; cnt[0] = 1; cnt[1] = nb; }
+  }
+  g.sync();
+  const int MAX_PIV = 2 * n;                                                         // :107
+  int piv = 0, status = LCP_MAXITER;
+  for (piv = 0; piv < MAX_PIV; piv++) {
+    const int k = cnt[0], nb = cnt[1];
+    for (int e = g.tid; e < k * k; e += G::size) { const int c = e / k, r = e - c * k; A[e] = m_at(M, ldm, nonbas[r], nonbas[c], lambda); }   // :111
+    for (int i = g.tid; i < k; i += G::size) zz[i] = -q[nonbas[i]];                  // :113-115
+    g.sync();
+    if (!lu_solve(g, k, A, zz)) { status = LCP_SINGULAR; break; }                    // :118-126
+    for (int i = g.tid; i < nb; i += G::size) {                                      // :129
+      const int bi = bas[i];
+      double sacc = 0.0;
+      for (int c = 0; c < k; c++) sacc = fma(M[(size_t)nonbas[c] * ldm + bi], zz[c], sacc);
+      w[i] = sacc + q[bi];
+    }
+    g.sync();
+    const int minw = (nb > 0) ? rand_min(g, w, nb, zero_tol) : -1;                   // :130
+    if (minw < 0 || w[minw] > -zero_tol) {                                           // :135
+      const int minz = (k > 0) ? rand_min(g, zz, k, zero_tol) : -1;                  // :138
+      if (minz >= 0 && zz[minz] < -zero_tol) {                                       // :141-150
+        g.sync();
+        if (g.tid == 0) {
+          int kk = k, nbb = nb; const int idx = nonbas[minz];
+          list_erase(nonbas, kk, minz); list_insert_sorted(bas, nbb, idx);
+          cnt[0] = kk; cnt[1] = nbb;
+          if (log && nlog < log_cap) log[nlog] = idx | 0x40000000;
+        }
+        nlog++;
+      } else {                                                                       // :151-162
+        g.sync();
+        for (int i = g.tid; i < n; i += G::size) z[i] = 0.0;
+        g.sync();
+        for (int j = g.tid; j < k; j += G::size) z[nonbas[j]] = zz[j];
+        status = LCP_OK;
+        break;
+      }
+    } else {                                                                         // :164-189
+      const int minz = (k > 0) ? rand_min(g, zz, k, zero_tol) : -1;                  // :176 (old ordering)
+      const bool second = (minz >= 0 && zz[minz] < -zero_tol);
+      g.sync();
+      if (g.tid == 0) {
+        int kk = k, nbb = nb; const int idx = bas[minw];
+        list_erase(bas, nbb, minw); list_insert_sorted(nonbas, kk, idx);
+        if (log && nlog < log_cap) log[nlog] = idx;
+        if (second) {                                                                // :179-188 (position in the NEW list)
+          const int idx2 = nonbas[minz];
+          list_erase(nonbas, kk, minz); list_insert_sorted(bas, nbb, idx2);
+          if (log && nlog + 1 < log_cap) log[nlog + 1] = idx2 | 0x40000000;
+        }
+        cnt[0] = kk; cnt[1] = nbb;
+      }
+      nlog += second ? 2 : 1;
+    }
+    g.sync();
+  }
+  if (pivots_out) *pivots_out = piv;
+  if (log_len) *log_len = nlog;
+  g.sync();
+  return status;
+}
+
+// Solution checks of the regularised wrappers (LCP.cpp:240-256 with >=, :303-319 with >); w is scratch (n).
+template <class G>
+__device__ bool lcp_verify(const G& g, int n, const double* M, int ldm, const double* q, double lambda, const double* z,
+                           double ZERO_TOL, bool strict, double* w) {
+  double mz = B2M_INF, mw = B2M_INF, mn = B2M_INF, mx = -B2M_INF;
+  for (int i = g.tid; i < n; i += G::size) {
+    double sacc = 0.0;
+    for (int c = 0; c < n; c++) sacc = fma(m_at(M, ldm, i, c, lambda), z[c], sacc);
+    const double wi = sacc + q[i];
+    const double pr = z[i] * wi;
+    mz = fmin(mz, z[i]); mw = fmin(mw, wi); mn = fmin(mn, pr); mx = fmax(mx, pr);
+  }
+  mz = g.min(mz); mw = g.min(mw); mn = g.min(mn); mx = g.max(mx);
+  const bool lo_ok = strict ? (mz > -ZERO_TOL && mw > -ZERO_TOL && mn > -ZERO_TOL) : (mz >= -ZERO_TOL && mw >= -ZERO_TOL && mn >= -ZERO_TOL);
+  return lo_ok && (mx < ZERO_TOL);
+}
+
+__device__ __forceinline__ double pow10i(int e) { return pow(10.0, (double)e); }
+
+// lcp_fast_regularized (LCP.cpp:212-350).  stats[0] += lcp_fast calls, stats[1] += pivots (thread 0 only, may be NULL).
+template <class G>
+__device__ int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, const double* q, double zero_tol, bool warm,
+                                    int min_exp, int step_exp, int max_exp, double* z, double* wd, int* wi,
+                                    int* pivots_out, long long* stats) {
+  if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
+  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :228
+  double* wv = wd + (size_t)n * n + n;   // the solver's w vector doubles as verification scratch
+  int total = 0, piv = 0;
+  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr);
+  bool zvalid = warm || st == LCP_OK || st == LCP_TRIVIAL;   // z.size()==n in the reference (LCP.cpp:65): warm start of the retries
+  total += piv;
+  if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+  if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, wv)) {
+    if (pivots_out) *pivots_out = piv;   // reference leaves `pivots` at the last solve's count here (:252-255)
+    return st;
+  }
+  int attempt = 0;
+  for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :281-340
+    const double lambda = pow10i(rf);
+    g.sync();
+    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr);
+    zvalid = zvalid || st == LCP_OK || st == LCP_TRIVIAL;
+    total += piv;
+    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+    if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, lambda, z, ZERO_TOL, true, wv)) {
+      if (pivots_out) *pivots_out = total;
+      return LCP_REGULARIZED + attempt;
+    }
+  }
+  if (pivots_out) *pivots_out = total;
+  return LCP_UNVERIFIED;
+}
+
+// lcp_lemke_regularized (LCP.cpp:353-487).
+template <class G>
+__device__ int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, const double* q, double piv_tol,
+                                     double zero_tol, int min_exp, int step_exp, int max_exp, double* z, double* wd,
+                                     int* wi, int* pivots_out, long long* stats) {
+  if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
+  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :369
+  double* wv = wd + (size_t)n * (n + 2);   // dvec doubles as verification scratch
+  int total = 0, piv = 0;
+  int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr);
+  total += piv;
+  if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+  if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, wv)) {
+    if (pivots_out) *pivots_out = piv;
+    return st;
+  }
+  int attempt = 0;
+  for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :419-477
+    const double lambda = pow10i(rf);
+    g.sync();
+    st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr);
+    total += piv;
+    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+    if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, lambda, z, ZERO_TOL, true, wv)) {
+      if (pivots_out) *pivots_out = total;
+      return LCP_REGULARIZED + attempt;
+    }
+  }
+  if (pivots_out) *pivots_out = total;
+  for (int i = g.tid; i < n; i += G::size) z[i] = 0.0;
+  g.sync();
+  return LCP_UNVERIFIED;
+}
+
+}  // namespace b2m

@@ -1,0 +1,218 @@
+// Batched LCP kernels + their C ABI (include/b200moby.h): replaces LCP::lcp_lemke / lcp_fast and the
+// regularised wrappers (Moby include/Moby/LCP.h:21-27) for batches of independent dense problems.
+//
+// Mapping: one warp per LCP while the solver's working set fits the SM's shared memory (n <= ~160: the
+// Lemke tableau is n (n+2) doubles), otherwise one 256-thread block per LCP with the working set in a
+// per-block global scratch that stays L2-resident.  Grids are persistent (148 SMs x resident blocks) and
+// stride over the batch.
+#include <cstdio>
+#include <cstring>
+#include "../../include/b200moby.h"
+#include "host_util.h"
+#include "lcp_device.cuh"
+
+using namespace b2m;
+
+namespace {
+
+enum Mode { MODE_LEMKE = 0, MODE_FAST = 1, MODE_LEMKE_REG = 2, MODE_FAST_REG = 3 };
+
+struct LcpArgs {
+  int batch, n, mode;
+  const double* M; const double* q; double* z;
+  double piv_tol, zero_tol;
+  int warm, min_exp, step_exp, max_exp;
+  int* status; int* pivots; int* log; int log_cap;
+  double* scratch_d; int* scratch_i;       // block-per-LCP only
+  size_t scratch_d_stride, scratch_i_stride;
+};
+
+__host__ __device__ inline size_t work_doubles(int mode, int n) {
+  const size_t a = lemke_work_doubles(n), b = fast_work_doubles(n);
+  if (mode == MODE_LEMKE || mode == MODE_LEMKE_REG) return a;
+  return b;
+}
+__host__ __device__ inline size_t work_ints(int mode, int n) {
+  return (mode == MODE_LEMKE || mode == MODE_LEMKE_REG) ? lemke_work_ints(n) : fast_work_ints(n);
+}
+// per-problem staging: M (n*n), q (n), z (n) for the lcp_fast family (random gathers into M); Lemke reads M once.
+__host__ __device__ inline size_t stage_doubles(int mode, int n) {
+  return (mode == MODE_FAST || mode == MODE_FAST_REG) ? (size_t)n * n + 2 * (size_t)n : 2 * (size_t)n;
+}
+
+template <class G>
+__device__ void solve_one(const G& g, const LcpArgs& a, int b, double* sm_d, int* sm_i) {
+  const int n = a.n;
+  const double* Mg = a.M + (size_t)b * n * n;
+  const double* qg = a.q + (size_t)b * n;
+  double* zg = a.z + (size_t)b * n;
+  int st, piv = 0, nlog = 0;
+  int* logp = a.log ? a.log + (size_t)b * a.log_cap : nullptr;
+  if (a.mode == MODE_FAST || a.mode == MODE_FAST_REG) {
+    double* Ms = sm_d; double* qs = Ms + (size_t)n * n; double* zs = qs + n; double* wd = zs + n;
+    for (int e = g.tid; e < n * n; e += G::size) Ms[e] = Mg[e];
+    for (int i = g.tid; i < n; i += G::size) { qs[i] = qg[i]; zs[i] = a.warm ? zg[i] : 0.0; }
+    g.sync();
+    if (a.mode == MODE_FAST) st = lcp_fast_solve(g, n, Ms, n, qs, 0.0, a.zero_tol, a.warm != 0, zs, wd, sm_i, &piv, logp, a.log_cap, &nlog);
+    else st = lcp_fast_regularized(g, n, Ms, n, qs, a.zero_tol, a.warm != 0, a.min_exp, a.step_exp, a.max_exp, zs, wd, sm_i, &piv, nullptr);
+    g.sync();
+    const bool ok = (st == LCP_OK || st == LCP_TRIVIAL || st >= LCP_REGULARIZED);
+    if (ok) for (int i = g.tid; i < n; i += G::size) zg[i] = zs[i];      // on failure z is left as given (LCP.cpp:118-126,192-195)
+  } else {
+    double* qs = sm_d; double* zs = qs + n; double* wd = zs + n;
+    for (int i = g.tid; i < n; i += G::size) qs[i] = qg[i];
+    g.sync();
+    if (a.mode == MODE_LEMKE) st = lemke_solve(g, n, Mg, n, qs, 0.0, a.piv_tol, a.zero_tol, zs, wd, sm_i, &piv, logp, a.log_cap, &nlog);
+    else st = lcp_lemke_regularized(g, n, Mg, n, qs, a.piv_tol, a.zero_tol, a.min_exp, a.step_exp, a.max_exp, zs, wd, sm_i, &piv, nullptr);
+    g.sync();
+    for (int i = g.tid; i < n; i += G::size) zg[i] = zs[i];
+  }
+  if (g.tid == 0) {
+    a.status[b] = st;
+    if (a.pivots) a.pivots[b] = piv;
+    if (logp && nlog < a.log_cap) logp[nlog] = -1;     // terminator
+  }
+  g.sync();
+}
+
+// one warp per LCP, working set in shared memory
+__global__ void __launch_bounds__(256) lcp_warp_kernel(LcpArgs a, int warps_per_block, size_t warp_d, size_t warp_i) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int w = threadIdx.x >> 5;
+  double* sm_d = (double*)smem + (size_t)w * warp_d;
+  int* sm_i = (int*)((double*)smem + (size_t)warps_per_block * warp_d) + (size_t)w * warp_i;
+  WarpGroup g(nullptr);
+  for (int b = blockIdx.x * warps_per_block + w; b < a.batch; b += gridDim.x * warps_per_block) solve_one(g, a, b, sm_d, sm_i);
+}
+
+// one block per LCP, working set in global scratch (L2-resident), reductions through shared memory
+__global__ void __launch_bounds__(256) lcp_block_kernel(LcpArgs a) {
+  __shared__ double red[4 * 8 + 4];
+  BlockGroup<256> g(red);
+  double* wd = a.scratch_d + (size_t)blockIdx.x * a.scratch_d_stride;
+  int* wi = a.scratch_i + (size_t)blockIdx.x * a.scratch_i_stride;
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) solve_one(g, a, b, wd, wi);
+}
+
+b200moby_status launch(LcpArgs a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (a.batch < 0 || a.n < 0 || (a.batch > 0 && a.n > 0 && (!a.M || !a.q || !a.z || !a.status))) return b2m_fail(B200MOBY_ERR_INVALID, "null pointer or negative size");
+  if (a.batch == 0 || a.n == 0) return B200MOBY_OK;
+  int dev = 0, sms = 0;
+  B2M_CUDA(cudaGetDevice(&dev));
+  B2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t wd = stage_doubles(a.mode, a.n) + work_doubles(a.mode, a.n);
+  const size_t wi = (work_ints(a.mode, a.n) + 3) & ~(size_t)3;
+  const size_t per_warp = wd * sizeof(double) + wi * sizeof(int);
+  const size_t MAXS = 227 * 1024;
+  if (per_warp <= MAXS) {
+    int wpb = (int)std::min<size_t>(8, MAXS / per_warp);
+    // do not launch blocks wider than the batch needs
+    while (wpb > 1 && (size_t)(wpb - 1) * sms >= (size_t)a.batch) wpb--;
+    const size_t shmem = per_warp * wpb;
+    B2M_CUDA(cudaFuncSetAttribute(lcp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
+    int per_sm = 1;
+    B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcp_warp_kernel, wpb * 32, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const int need = (a.batch + wpb - 1) / wpb;
+    const int grid = std::min(need, sms * per_sm);
+    lcp_warp_kernel<<<grid, wpb * 32, shmem, stream>>>(a, wpb, wd, wi);
+    B2M_CUDA(cudaGetLastError());
+  } else {
+    const int grid = std::min(a.batch, sms * 2);
+    a.scratch_d_stride = (wd + 1) & ~(size_t)1;
+    a.scratch_i_stride = wi;
+    B2M_CUDA(cudaMallocAsync((void**)&a.scratch_d, a.scratch_d_stride * grid * sizeof(double), stream));
+    B2M_CUDA(cudaMallocAsync((void**)&a.scratch_i, a.scratch_i_stride * grid * sizeof(int), stream));
+    lcp_block_kernel<<<grid, 256, 0, stream>>>(a);
+    B2M_CUDA(cudaGetLastError());
+    B2M_CUDA(cudaFreeAsync(a.scratch_d, stream));
+    B2M_CUDA(cudaFreeAsync(a.scratch_i, stream));
+  }
+  return B200MOBY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+b200moby_status b200moby_lcp_lemke_batched(int batch, int n, const double* M, const double* q, double* z, double piv_tol,
+                                           double zero_tol, int* status, int* pivots, int* log, int log_cap, void* stream) {
+  if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  LcpArgs a; memset(&a, 0, sizeof(a));
+  a.batch = batch; a.n = n; a.mode = MODE_LEMKE; a.M = M; a.q = q; a.z = z; a.piv_tol = piv_tol; a.zero_tol = zero_tol;
+  a.status = status; a.pivots = pivots; a.log = log; a.log_cap = log_cap;
+  return launch(a, stream);
+}
+
+b200moby_status b200moby_lcp_fast_batched(int batch, int n, const double* M, const double* q, double* z, int warm,
+                                          double zero_tol, int* status, int* pivots, int* log, int log_cap, void* stream) {
+  if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  LcpArgs a; memset(&a, 0, sizeof(a));
+  a.batch = batch; a.n = n; a.mode = MODE_FAST; a.M = M; a.q = q; a.z = z; a.zero_tol = zero_tol; a.warm = warm;
+  a.status = status; a.pivots = pivots; a.log = log; a.log_cap = log_cap;
+  return launch(a, stream);
+}
+
+b200moby_status b200moby_lcp_lemke_regularized_batched(int batch, int n, const double* M, const double* q, double* z,
+                                                       int min_exp, int step_exp, int max_exp, double piv_tol,
+                                                       double zero_tol, int* status, int* pivots, void* stream) {
+  if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  if (step_exp <= 0) return b2m_fail(B200MOBY_ERR_INVALID, "step_exp must be positive");
+  LcpArgs a; memset(&a, 0, sizeof(a));
+  a.batch = batch; a.n = n; a.mode = MODE_LEMKE_REG; a.M = M; a.q = q; a.z = z; a.piv_tol = piv_tol; a.zero_tol = zero_tol;
+  a.min_exp = min_exp; a.step_exp = step_exp; a.max_exp = max_exp; a.status = status; a.pivots = pivots;
+  return launch(a, stream);
+}
+
+b200moby_status b200moby_lcp_fast_regularized_batched(int batch, int n, const double* M, const double* q, double* z, int warm,
+                                                      int min_exp, int step_exp, int max_exp, double zero_tol,
+                                                      int* status, int* pivots, void* stream) {
+  if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  if (step_exp <= 0) return b2m_fail(B200MOBY_ERR_INVALID, "step_exp must be positive");
+  LcpArgs a; memset(&a, 0, sizeof(a));
+  a.batch = batch; a.n = n; a.mode = MODE_FAST_REG; a.M = M; a.q = q; a.z = z; a.zero_tol = zero_tol; a.warm = warm;
+  a.min_exp = min_exp; a.step_exp = step_exp; a.max_exp = max_exp; a.status = status; a.pivots = pivots;
+  return launch(a, stream);
+}
+
+static b200moby_status host_form(int mode, int batch, int n, const double* M, const double* q, double* z, int warm,
+                                 double piv_tol, double zero_tol, int* status, int* pivots, int device) {
+  if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  if (batch <= 0 || n <= 0) return B200MOBY_OK;
+  B2M_CUDA(cudaSetDevice(device));
+  double *dM = nullptr, *dq = nullptr, *dz = nullptr; int *dst = nullptr, *dpv = nullptr;
+  const size_t nM = (size_t)batch * n * n, nv = (size_t)batch * n;
+  cudaStream_t s; B2M_CUDA(cudaStreamCreate(&s));
+  B2M_CUDA(cudaMallocAsync((void**)&dM, nM * sizeof(double), s));
+  B2M_CUDA(cudaMallocAsync((void**)&dq, nv * sizeof(double), s));
+  B2M_CUDA(cudaMallocAsync((void**)&dz, nv * sizeof(double), s));
+  B2M_CUDA(cudaMallocAsync((void**)&dst, batch * sizeof(int), s));
+  B2M_CUDA(cudaMallocAsync((void**)&dpv, batch * sizeof(int), s));
+  B2M_CUDA(cudaMemcpyAsync(dM, M, nM * sizeof(double), cudaMemcpyHostToDevice, s));
+  B2M_CUDA(cudaMemcpyAsync(dq, q, nv * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (warm) B2M_CUDA(cudaMemcpyAsync(dz, z, nv * sizeof(double), cudaMemcpyHostToDevice, s));
+  b200moby_status r = (mode == MODE_LEMKE)
+      ? b200moby_lcp_lemke_batched(batch, n, dM, dq, dz, piv_tol, zero_tol, dst, dpv, nullptr, 0, s)
+      : b200moby_lcp_fast_batched(batch, n, dM, dq, dz, warm, zero_tol, dst, dpv, nullptr, 0, s);
+  if (r == B200MOBY_OK) {
+    B2M_CUDA(cudaMemcpyAsync(z, dz, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (status) B2M_CUDA(cudaMemcpyAsync(status, dst, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (pivots) B2M_CUDA(cudaMemcpyAsync(pivots, dpv, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  cudaFreeAsync(dM, s); cudaFreeAsync(dq, s); cudaFreeAsync(dz, s); cudaFreeAsync(dst, s); cudaFreeAsync(dpv, s);
+  B2M_CUDA(cudaStreamSynchronize(s));
+  cudaStreamDestroy(s);
+  return r;
+}
+
+b200moby_status b200moby_lcp_lemke_host(int batch, int n, const double* M, const double* q, double* z, double piv_tol,
+                                        double zero_tol, int* status, int* pivots, int device) {
+  return host_form(MODE_LEMKE, batch, n, M, q, z, 0, piv_tol, zero_tol, status, pivots, device);
+}
+b200moby_status b200moby_lcp_fast_host(int batch, int n, const double* M, const double* q, double* z, int warm,
+                                       double zero_tol, int* status, int* pivots, int device) {
+  return host_form(MODE_FAST, batch, n, M, q, z, warm, -1.0, zero_tol, status, pivots, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""GPU parity tests of the batched LCP kernels against the CPU oracle (through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+
+from lcp_problems import lcp_residuals, random_batch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _log_list(row):
+    row = list(row)
+    return row[:row.index(-1)] if -1 in row else row
+
+
+@pytest.mark.parametrize("n,batch", [(1, 8), (3, 64), (8, 256), (24, 128), (40, 128), (96, 48), (200, 6)])
+def test_lemke_matches_oracle(torch_cuda, oracle, n, batch):
+    """Tableau Lemke vs the oracle's LU-per-pivot Lemke: same leaving-variable sequence on tie-free well-conditioned
+    problems, z within 1e-9 relative."""
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    M, q = random_batch(batch, n, seed=1000 + n)
+    cap = 50 * n + 8
+    z, st, piv, log = LCP(log_cap=cap).lcp_lemke(_dev(torch, M), _dev(torch, q))
+    z, st, piv, log = z.cpu().numpy(), st.cpu().numpy(), piv.cpu().numpy(), log.cpu().numpy()
+    same_seq = 0
+    for b in range(batch):
+        ok, zo, info = oracle.lcp_lemke(M[b], q[b], log_cap=cap)
+        assert ok and st[b] in (0, 1), (b, st[b], info)
+        scale = max(1.0, np.abs(zo).max())
+        assert np.allclose(z[b], zo, rtol=0, atol=1e-9 * scale), (b, np.abs(z[b] - zo).max())
+        if _log_list(log[b]) == list(info["log"]) and piv[b] == info["pivots"]:
+            same_seq += 1
+    assert same_seq == batch, f"pivot sequences identical on {same_seq}/{batch}"
+
+
+@pytest.mark.parametrize("n,batch", [(1, 8), (3, 64), (8, 256), (24, 128), (40, 128), (96, 48), (200, 6)])
+def test_fast_matches_oracle_bitwise(torch_cuda, oracle, n, batch):
+    """lcp_fast follows the oracle's arithmetic order: identical index sequences and bit-identical z."""
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    M, q = random_batch(batch, n, seed=2000 + n)
+    cap = 4 * n + 8
+    z, st, piv, log = LCP(log_cap=cap).lcp_fast(_dev(torch, M), _dev(torch, q))
+    z, st, piv, log = z.cpu().numpy(), st.cpu().numpy(), piv.cpu().numpy(), log.cpu().numpy()
+    for b in range(batch):
+        ok, zo, info = oracle.lcp_fast(M[b], q[b], log_cap=cap)
+        assert ok == (st[b] in (0, 1)), (b, st[b], info)
+        assert piv[b] == info["pivots"] and _log_list(log[b]) == list(info["log"]), b
+        if ok:
+            assert np.array_equal(z[b], zo), (b, np.abs(z[b] - zo).max())
+
+
+def test_fast_warm_start(torch_cuda, oracle):
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    M, q = random_batch(64, 32, seed=77)
+    rng = np.random.default_rng(3)
+    z0 = np.where(rng.random((64, 32)) < 0.3, rng.random((64, 32)), 0.0)      # arbitrary (stale) warm start, rule H1
+    z, st, piv, _ = LCP().lcp_fast(_dev(torch, M), _dev(torch, q), z0=_dev(torch, z0))
+    z, st, piv = z.cpu().numpy(), st.cpu().numpy(), piv.cpu().numpy()
+    for b in range(64):
+        ok, zo, info = oracle.lcp_fast(M[b], q[b], z0=z0[b])
+        assert ok == (st[b] in (0, 1)) and piv[b] == info["pivots"]
+        assert np.array_equal(z[b], zo)
+
+
+def test_regularized_wrappers(torch_cuda, oracle):
+    """Includes rank-deficient problems with a zero diagonal block (the [[H,-A'],[A,0]] shape of the QP-as-LCP)."""
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    rng = np.random.default_rng(9)
+    Ms, qs = [], []
+    for _ in range(64):
+        m, k = 6, 4
+        J = rng.standard_normal((m, 3))
+        H = J @ J.T                                   # rank 3 < 6
+        A = np.abs(rng.standard_normal((k, m)))
+        MM = np.block([[H, -A.T], [A, np.zeros((k, k))]])
+        Ms.append(MM)
+        qs.append(np.concatenate([rng.standard_normal(m), np.abs(rng.standard_normal(k))]))
+    M, q = np.stack(Ms), np.stack(qs)
+    lcp = LCP()
+    zf, sf, pf = lcp.lcp_fast_regularized(_dev(torch, M), _dev(torch, q), min_exp=-20, step_exp=4, max_exp=-8)
+    zl, sl, pl = lcp.lcp_lemke_regularized(_dev(torch, M), _dev(torch, q))
+    zf, sf, pf, zl, sl, pl = (t.cpu().numpy() for t in (zf, sf, pf, zl, sl, pl))
+    n = M.shape[1]
+    for b in range(64):
+        ok, zo, info = oracle.lcp_fast_regularized(M[b], q[b], min_exp=-20, step_exp=4, max_exp=-8)
+        assert info["status"] == sf[b] and info["pivots"] == pf[b], (b, info, sf[b], pf[b])
+        if ok:
+            assert np.array_equal(zf[b], zo)
+        ok, zo, info = oracle.lcp_lemke_regularized(M[b], q[b])
+        assert ok == (sl[b] != 6), (b, info, sl[b])
+        if ok:
+            T = n * np.abs(M[b]).max() * np.sqrt(np.finfo(float).eps)
+            r = lcp_residuals(M[b], q[b], zl[b])
+            assert r["min_z"] >= -T and r["min_w"] >= -T and r["max_zw"] < T
+
+
+def test_frozen_kats(torch_cuda):
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    d = np.load(os.path.join(GOLDEN, "lcp_kats.npz"))
+    for k in range(int(d["count"])):
+        M, q = d[f"M{k}"][None], d[f"q{k}"][None]
+        cap = 50 * M.shape[1] + 8
+        z, st, piv, log = LCP(log_cap=cap).lcp_fast(_dev(torch, M), _dev(torch, q))
+        assert st.item() in (0, 1)
+        assert np.array_equal(z.cpu().numpy()[0], d[f"zfast{k}"])
+        assert _log_list(log.cpu().numpy()[0]) == list(d[f"fast_log{k}"])
+        z, st, piv, log = LCP(log_cap=cap).lcp_lemke(_dev(torch, M), _dev(torch, q))
+        assert st.item() in (0, 1)
+        r = lcp_residuals(M[0], q[0], z.cpu().numpy()[0])
+        T = M.shape[1] * np.abs(M).max() * np.sqrt(np.finfo(float).eps)
+        assert r["min_z"] >= -T and r["min_w"] >= -T and r["max_zw"] < T
+
+
+def test_host_forms_and_block_path(torch_cuda, oracle):
+    """Host-buffer entry points (copies inside) and the block-per-LCP path (n too large for one warp's shared memory)."""
+    from moby_b200.lcp import lcp_fast_host, lcp_lemke_host
+    M, q = random_batch(4, 180, seed=5)
+    z, st, piv = lcp_lemke_host(M, q)
+    for b in range(4):
+        ok, zo, info = oracle.lcp_lemke(M[b], q[b])
+        assert ok and st[b] in (0, 1) and np.allclose(z[b], zo, rtol=0, atol=1e-8)
+    z, st, piv = lcp_fast_host(M, q)
+    for b in range(4):
+        ok, zo, info = oracle.lcp_fast(M[b], q[b])
+        assert ok and st[b] in (0, 1) and np.array_equal(z[b], zo)
+
+
+def test_empty_and_ragged(torch_cuda):
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    z, st, piv, _ = LCP().lcp_lemke(torch.zeros((0, 4, 4), dtype=torch.float64, device="cuda"),
+                                    torch.zeros((0, 4), dtype=torch.float64, device="cuda"))
+    assert z.shape == (0, 4)
+    # trivial problems: q >= 0 -> z = 0, status TRIVIAL
+    M, q = random_batch(5, 6, seed=1)
+    z, st, piv, _ = LCP().lcp_lemke(_dev(torch, M), _dev(torch, np.abs(q)))
+    assert (st.cpu().numpy() == 1).all() and not z.cpu().numpy().any()
