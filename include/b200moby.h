@@ -108,6 +108,8 @@ typedef struct {
   long long impact_tol_events;/* ImpactToleranceException equivalents (ImpactConstraintHandler.cpp:153-167) */
   long long contacts;         /* contact constraints generated */
   long long max_lcp_n;        /* largest LCP dimension seen */
+  long long pivot_flops;      /* sum over solves of pivots * 2 n (n+1): the algorithmic solver flops of SURVEY.md 8(d) */
+  long long assembly_flops;   /* F_delassus + F_apply per island solve + F_fd + F_narrow per mini-step (SURVEY.md 8(d) formulas) */
 } b200moby_counters;
 
 const char* b200moby_last_error(void);
@@ -138,7 +140,8 @@ b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int 
 /* ---- batched solvers: replace LCP::lcp_lemke / lcp_fast and wrappers (LCP.h:21-27) ----
  * M_dev [batch][n*n] column-major, q_dev [batch][n], z_dev [batch][n] (in: warm start for lcp_fast, out: solution),
  * status_dev [batch], pivots_dev [batch] (may be NULL), pivot_log_dev [batch][log_cap] (may be NULL):
- *   Lemke logs the leaving basis position per pivot, lcp_fast logs (moved index | 0x40000000 if moved to basic).
+ *   Lemke logs the leaving variable id per pivot (z_i: i, w_i: n+i, artificial: 2n), lcp_fast logs (moved index | 0x40000000 if moved to basic);
+ *   a -1 terminates the list when it is shorter than log_cap.
  * piv_tol / zero_tol <= 0 select the reference defaults (LCP.cpp:570-571, :761, :57-58). */
 b200moby_status b200moby_lcp_lemke_batched(int batch, int n, const double* M_dev, const double* q_dev, double* z_dev,
                                            double piv_tol, double zero_tol, int* status_dev, int* pivots_dev,

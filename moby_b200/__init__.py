@@ -6,3 +6,4 @@ CUDA library is missing.
 """
 from .capi import lib, SceneDesc, Counters, B200MobyError  # noqa: F401
 from .scenes import SceneBatch  # noqa: F401
+from .simulator import TimeSteppingSimulator  # noqa: F401

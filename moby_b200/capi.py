@@ -25,7 +25,7 @@ class SceneDesc(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(k, C.c_longlong) for k in (
         "env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
-        "impact_tol_events", "contacts", "max_lcp_n")]
+        "impact_tol_events", "contacts", "max_lcp_n", "pivot_flops", "assembly_flops")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

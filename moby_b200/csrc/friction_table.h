@@ -1,0 +1,48 @@
+// Host-side table of the friction-cone direction cosines / sines, evaluated with the host libm exactly as the
+// reference evaluates them (ImpactConstraintHandlerQP.cpp:464-468; ImpactConstraintHandlerLCP.cpp:259-275), so the
+// device never calls its own cos/sin.  Layout: [4][NKMAX+1][NKMAX/2] = QP cos, QP sin, AP cos, AP sin.
+#pragma once
+#include <cmath>
+#include <vector>
+#ifndef B2M_NKMAX
+#define B2M_NKMAX 64
+#endif
+
+inline std::vector<double> b2m_friction_table() {
+  const int H = B2M_NKMAX / 2, S = (B2M_NKMAX + 1) * H;
+  std::vector<double> t((size_t)4 * S, 0.0);
+  for (int NK = 4; NK <= B2M_NKMAX; NK++) {
+    const int half = NK / 2;
+    for (int j = 0; j < half && j < H; j++) {
+      const double theta = (double)j / (half - 1) * M_PI_2;
+      t[(size_t)NK * H + j] = std::cos(theta);
+      t[(size_t)S + (size_t)NK * H + j] = std::sin(theta);
+    }
+    const int nk4 = (NK + 4) / 4;
+    for (int k = 0; k < nk4 && k < H; k++) {
+      t[(size_t)2 * S + (size_t)NK * H + k] = std::cos((M_PI * k) / (2.0 * nk4));
+      t[(size_t)3 * S + (size_t)NK * H + k] = std::sin((M_PI * k) / (2.0 * nk4));
+    }
+  }
+  return t;
+}
+
+// Upper bounds of contacts and LCP dimension for one env of a scene (shape/enabled/NK of every body pair).
+inline void b2m_env_bounds(int nb, const int* shape, const int* enabled, const int* NK, int model, int& cmax, int& nmax, int& npairs) {
+  cmax = 0; nmax = 0; npairs = 0;
+  for (int i = 0; i < nb; i++)
+    for (int j = i + 1; j < nb; j++) {
+      if (!(enabled[i] || enabled[j])) continue;
+      if (shape[i] == 0 || shape[j] == 0) continue;
+      const int nk = NK[i * nb + j];
+      if (nk == 0) continue;
+      npairs++;
+      int cnt = 1;                                     // sphere-anything: one contact
+      const bool bi = shape[i] == 2, bj = shape[j] == 2, pi = shape[i] == 3, pj = shape[j] == 3;
+      if ((bi && pj) || (pi && bj)) cnt = 4;           // a non-degenerate box touches a plane with at most 4 vertices
+      if (bi && bj) cnt = 8;
+      if (pi && pj) cnt = 0;
+      cmax += cnt;
+      nmax += cnt * (model == 1 ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2);
+    }
+}

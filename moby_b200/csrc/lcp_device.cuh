@@ -18,14 +18,14 @@ enum {
 };
 
 // element (r,c) of M + lambda I
-__device__ __forceinline__ double m_at(const double* M, int ldm, int r, int c, double lambda) {
+B2M_DEV B2M_INL double m_at(const double* M, int ldm, int r, int c, double lambda) {
   double v = M[(size_t)c * ldm + r];
   return (r == c) ? v + lambda : v;
 }
 
 // MatrixNd::norm_inf() of M + lambda I: largest |entry|
 template <class G>
-__device__ double norm_inf(const G& g, int n, const double* M, int ldm, double lambda) {
+B2M_DEV double norm_inf(const G& g, int n, const double* M, int ldm, double lambda) {
   double m = 0.0;
   for (int e = g.tid; e < n * n; e += G::size) {
     const int c = e / n, r = e - c * n;
@@ -36,7 +36,7 @@ __device__ double norm_inf(const G& g, int n, const double* M, int ldm, double l
 
 // LCP::rand_min with the lowest-index tie rule: first minimum, then the lowest index i with v[i] < v[min] + tol.
 template <class G>
-__device__ int rand_min(const G& g, const double* v, int m, double tol) {
+B2M_DEV int rand_min(const G& g, const double* v, int m, double tol) {
   double key = B2M_INF; int idx = 0x7fffffff;
   for (int i = g.tid; i < m; i += G::size) { const double x = v[i]; if (x < key) { key = x; idx = i; } }
   g.min_key_idx(key, idx);
@@ -51,11 +51,11 @@ __device__ int rand_min(const G& g, const double* v, int m, double tol) {
 // Lemke.  Work memory: T  n*(n+2) doubles (column-major, ld n: slots 0..n nonbasic columns, column n+1 = x),
 //                      dvec n, rvec n+2 doubles; where 2n+1, bas n ints.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t lemke_work_doubles(int n) { return (size_t)n * (n + 2) + n + (n + 2); }
-__host__ __device__ inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
+B2M_HD inline size_t lemke_work_doubles(int n) { return (size_t)n * (n + 2) + n + (n + 2); }
+B2M_HD inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
 
 template <class G>
-__device__ int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
+B2M_DEV int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
                            int* log, int log_cap, int* log_len) {
   double* T = wd;
@@ -162,12 +162,12 @@ __device__ int lemke_solve(const G& g, int n, const double* M, int ldm, const do
 // first maximum, reciprocal multipliers, fma updates, column-oriented back substitution) so results are
 // bit-identical to the CPU checker.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t fast_work_doubles(int n) { return (size_t)n * n + 2 * (size_t)n; }
-__host__ __device__ inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2; }
+B2M_HD inline size_t fast_work_doubles(int n) { return (size_t)n * n + 2 * (size_t)n; }
+B2M_HD inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2; }
 
 // solves A x = b (A k x k column-major ld k, destroyed; b <- x).  Returns false on an exactly zero pivot.
 template <class G>
-__device__ bool lu_solve(const G& g, int k, double* A, double* b) {
+B2M_DEV bool lu_solve(const G& g, int k, double* A, double* b) {
   for (int j = 0; j < k; j++) {
     double key = 1.0; int p = 0x7fffffff;                       // lexicographic min of (-|a|, i) == first maximum
     for (int i = j + g.tid; i < k; i += G::size) { const double v = -fabs(A[(size_t)j * k + i]); if (v < key) { key = v; p = i; } }
@@ -198,11 +198,11 @@ __device__ bool lu_solve(const G& g, int k, double* A, double* b) {
   return true;
 }
 
-__device__ inline void list_erase(int* L, int& m, int pos) { for (int i = pos; i + 1 < m; i++) L[i] = L[i + 1]; m--; }
-__device__ inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while (i > 0 && L[i - 1] > v) { L[i] = L[i - 1]; i--; } L[i] = v; m++; }
+B2M_DEV inline void list_erase(int* L, int& m, int pos) { for (int i = pos; i + 1 < m; i++) L[i] = L[i + 1]; m--; }
+B2M_DEV inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while (i > 0 && L[i - 1] > v) { L[i] = L[i - 1]; i--; } L[i] = v; m++; }
 
 template <class G>
-__device__ int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
+B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
                               bool warm, double* z, double* wd, int* wi, int* pivots_out, int* log, int log_cap,
                               int* log_len) {
   double* A = wd;
@@ -294,7 +294,7 @@ __device__ int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const
 
 // Solution checks of the regularised wrappers (LCP.cpp:240-256 with >=, :303-319 with >); w is scratch (n).
 template <class G>
-__device__ bool lcp_verify(const G& g, int n, const double* M, int ldm, const double* q, double lambda, const double* z,
+B2M_DEV bool lcp_verify(const G& g, int n, const double* M, int ldm, const double* q, double lambda, const double* z,
                            double ZERO_TOL, bool strict, double* w) {
   double mz = B2M_INF, mw = B2M_INF, mn = B2M_INF, mx = -B2M_INF;
   for (int i = g.tid; i < n; i += G::size) {
@@ -309,11 +309,65 @@ __device__ bool lcp_verify(const G& g, int n, const double* M, int ldm, const do
   return lo_ok && (mx < ZERO_TOL);
 }
 
-__device__ __forceinline__ double pow10i(int e) { return pow(10.0, (double)e); }
+// 10^e from correctly rounded decimal literals (identical on host and device); std::pow(10, e) in the reference
+B2M_DEV inline double pow10i(int e) {
+  switch (e) {
+    case -24: return 1e-24;
+    case -23: return 1e-23;
+    case -22: return 1e-22;
+    case -21: return 1e-21;
+    case -20: return 1e-20;
+    case -19: return 1e-19;
+    case -18: return 1e-18;
+    case -17: return 1e-17;
+    case -16: return 1e-16;
+    case -15: return 1e-15;
+    case -14: return 1e-14;
+    case -13: return 1e-13;
+    case -12: return 1e-12;
+    case -11: return 1e-11;
+    case -10: return 1e-10;
+    case -9: return 1e-9;
+    case -8: return 1e-8;
+    case -7: return 1e-7;
+    case -6: return 1e-6;
+    case -5: return 1e-5;
+    case -4: return 1e-4;
+    case -3: return 1e-3;
+    case -2: return 1e-2;
+    case -1: return 1e-1;
+    case 0: return 1e0;
+    case 1: return 1e1;
+    case 2: return 1e2;
+    case 3: return 1e3;
+    case 4: return 1e4;
+    case 5: return 1e5;
+    case 6: return 1e6;
+    case 7: return 1e7;
+    case 8: return 1e8;
+    case 9: return 1e9;
+    case 10: return 1e10;
+    case 11: return 1e11;
+    case 12: return 1e12;
+    case 13: return 1e13;
+    case 14: return 1e14;
+    case 15: return 1e15;
+    case 16: return 1e16;
+    case 17: return 1e17;
+    case 18: return 1e18;
+    case 19: return 1e19;
+    case 20: return 1e20;
+    case 21: return 1e21;
+    case 22: return 1e22;
+    case 23: return 1e23;
+    case 24: return 1e24;
+    default: return pow(10.0, (double)e);
+  }
+}
 
 // lcp_fast_regularized (LCP.cpp:212-350).  stats[0] += lcp_fast calls, stats[1] += pivots (thread 0 only, may be NULL).
 template <class G>
-__device__ int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, const double* q, double zero_tol, bool warm,
+B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, const double* q, double zero_tol, bool warm,
                                     int min_exp, int step_exp, int max_exp, double* z, double* wd, int* wi,
                                     int* pivots_out, long long* stats) {
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
@@ -347,7 +401,7 @@ __device__ int lcp_fast_regularized(const G& g, int n, const double* M, int ldm,
 
 // lcp_lemke_regularized (LCP.cpp:353-487).
 template <class G>
-__device__ int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, const double* q, double piv_tol,
+B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, const double* q, double piv_tol,
                                      double zero_tol, int min_exp, int step_exp, int max_exp, double* z, double* wd,
                                      int* wi, int* pivots_out, long long* stats) {
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }

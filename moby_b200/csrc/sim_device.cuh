@@ -1,0 +1,1003 @@
+// Group-cooperative device code of the stepped path for free rigid bodies with sphere / box / plane geometry:
+// narrowphase + conservative advancement, semi-implicit Euler with Newton-Euler forward dynamics, island
+// grouping, Delassus / LCP assembly (QP-as-LCP and Anitescu-Potra), solve, impulse write-back, restitution.
+//
+// Behavioural contract (Moby tree): TimeSteppingSimulator.cpp:52-222,272-331,433-455; ConstraintSimulator.cpp:
+// 298-355,450-537; CCD.cpp:122-460,585-607; CCD.inl:3-82,805-886,1165-1259; UnilateralConstraint.cpp:695-747,
+// 940-1225,1387-1446; ImpactConstraintHandler.cpp:96-168,298-626,1590-2166; ImpactConstraintHandlerQP.cpp:94-497;
+// ImpactConstraintHandlerLCP.cpp:36-370.  One thread group (a warp for small scenes) owns one env; the env's
+// bodies, contacts, Delassus blocks, LCP matrix and solver work space all live in shared memory, so an env-step
+// touches HBM only for its state (13 doubles per body in and out) and its warm-start vector.
+#pragma once
+#include "lcp_device.cuh"
+
+namespace b2m {
+
+enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3 };
+enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LEMKE_CALLS, CNT_PIVOTS, CNT_LCP_FAIL,
+       CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_COUNT };
+#define B2M_NKMAX 64
+
+struct V3 {
+  double x, y, z;
+  B2M_HD V3() : x(0), y(0), z(0) {}
+  B2M_HD V3(double a, double b, double c) : x(a), y(b), z(c) {}
+};
+B2M_HD B2M_INL V3 operator+(const V3& a, const V3& b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+B2M_HD B2M_INL V3 operator-(const V3& a, const V3& b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+B2M_HD B2M_INL V3 operator-(const V3& a) { return V3(-a.x, -a.y, -a.z); }
+B2M_HD B2M_INL V3 operator*(const V3& a, double s) { return V3(a.x * s, a.y * s, a.z * s); }
+B2M_HD B2M_INL double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+B2M_HD B2M_INL V3 cross(const V3& a, const V3& b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+B2M_HD B2M_INL double norm(const V3& a) { return sqrt(dot(a, a)); }
+B2M_HD B2M_INL V3 normalize(const V3& a) { const double n = norm(a); return V3(a.x / n, a.y / n, a.z / n); }
+B2M_HD B2M_INL V3 rot(const double* R, const V3& v) { return V3(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z); }
+B2M_HD B2M_INL V3 rotT(const double* R, const V3& v) { return V3(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z); }
+B2M_HD B2M_INL V3 ld3(const double* p) { return V3(p[0], p[1], p[2]); }
+B2M_HD B2M_INL void st3(double* p, const V3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// Scene + state of a batch, device pointers (SoA across envs, see include/b200moby.h)
+struct SimParams {
+  int n_envs, nb, cmax, nmax, npmax, model;
+  const int* shape; const int* enabled; const double* mass; const double* dims; const double* inertia;
+  const double* mu_c; const double* mu_v; const double* eps; const double* compliance; const int* NK;
+  const double* fr_tab;        // [4][B2M_NKMAX+1][B2M_NKMAX/2]: QP cos, QP sin, AP cos, AP sin (host libm values)
+  double gx, gy, gz, contact_dist_thresh, min_step_size;
+  double* q; double* v; double* time; double* zlast; int* zlast_n;
+  unsigned long long* counters;
+  // debug taps (may be null)
+  double* tap_MM; double* tap_qq; double* tap_z; int* tap_n;
+};
+
+// Per-env working set carved out of one contiguous block of doubles + ints (shared memory for warp groups).
+struct EnvMem {
+  // doubles
+  double *bx, *bq, *bR, *bvl, *bva, *bmass, *bdims, *bJ, *xsave, *qsave;
+  double *pd_dist, *pd_pa, *pd_pb;
+  double *cp, *cnrm, *ct1, *ct2, *cdist, *cmu, *cmuv, *ceps, *ccomp;
+  double *Jr, *XJ, *Xb, *D, *Cv, *imp, *acc, *dv;
+  double *MM, *qq, *z, *work;
+  // ints
+  int *bshape, *ben, *pair_a, *pair_b, *cb1, *cb2, *cNK, *icon, *cisl, *corder, *isl_start, *gcoff, *bisl, *frow_c, *frow_j, *scal, *iwork;
+};
+
+B2M_HD inline size_t env_doubles(int nb, int cmax, int nmax, int npmax) {
+  size_t lw = lemke_work_doubles(nmax), fw = fast_work_doubles(nmax);
+  return (size_t)38 * nb + 7 * (size_t)npmax + 17 * (size_t)cmax + 72 * (size_t)cmax + 36 * (size_t)nb + 6 * (size_t)cmax * cmax +
+         9 * (size_t)cmax + 6 * (size_t)nb + (size_t)nmax * nmax + 2 * (size_t)nmax + (lw > fw ? lw : fw);
+}
+B2M_HD inline size_t env_ints(int nb, int cmax, int nmax, int npmax) {
+  size_t lw = lemke_work_ints(nmax), fw = fast_work_ints(nmax);
+  return (size_t)5 * nb + 1 + 2 * (size_t)npmax + 6 * (size_t)cmax + 2 * (size_t)nmax + 16 + (lw > fw ? lw : fw);
+}
+
+B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax, int npmax) {
+  m.bx = d; d += 3 * nb; m.bq = d; d += 4 * nb; m.bR = d; d += 9 * nb; m.bvl = d; d += 3 * nb; m.bva = d; d += 3 * nb;
+  m.bmass = d; d += nb; m.bdims = d; d += 3 * nb; m.bJ = d; d += 3 * nb; m.xsave = d; d += 3 * nb; m.qsave = d; d += 4 * nb;
+  m.pd_dist = d; d += npmax; m.pd_pa = d; d += 3 * npmax; m.pd_pb = d; d += 3 * npmax;
+  m.cp = d; d += 3 * cmax; m.cnrm = d; d += 3 * cmax; m.ct1 = d; d += 3 * cmax; m.ct2 = d; d += 3 * cmax;
+  m.cdist = d; d += cmax; m.cmu = d; d += cmax; m.cmuv = d; d += cmax; m.ceps = d; d += cmax; m.ccomp = d; d += cmax;
+  m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.D = d; d += 6 * (size_t)cmax * cmax;
+  m.Cv = d; d += 3 * cmax; m.imp = d; d += 3 * cmax; m.acc = d; d += 3 * cmax; m.dv = d; d += 6 * nb;
+  m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.work = d;
+  m.bshape = i; i += nb; m.ben = i; i += nb; m.gcoff = i; i += nb; m.bisl = i; i += nb;
+  m.pair_a = i; i += npmax; m.pair_b = i; i += npmax;
+  m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax; m.icon = i; i += cmax; m.cisl = i; i += cmax; m.corder = i; i += cmax;
+  m.isl_start = i; i += nb + 1;
+  m.frow_c = i; i += nmax; m.frow_j = i; i += nmax; m.scal = i; i += 16; m.iwork = i;
+}
+
+// scal[] slots
+enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7 };
+
+// ---------- geometry helpers (same formulas, same order as the CPU checker) ----------
+B2M_HD B2M_INL void quat_to_R(const double* qt, double* R) {
+  const double x = qt[0], y = qt[1], z = qt[2], w = qt[3];
+  R[0] = 1.0 - 2.0 * (y * y + z * z); R[1] = 2.0 * (x * y - w * z);       R[2] = 2.0 * (x * z + w * y);
+  R[3] = 2.0 * (x * y + w * z);       R[4] = 1.0 - 2.0 * (x * x + z * z); R[5] = 2.0 * (y * z - w * x);
+  R[6] = 2.0 * (x * z - w * y);       R[7] = 2.0 * (y * z + w * x);       R[8] = 1.0 - 2.0 * (x * x + y * y);
+}
+B2M_HD B2M_INL V3 box_vertex(const double* dims, int i) {   // BoxPrimitive.cpp:358-365 order
+  const double X = dims[0] * 0.5, Y = dims[1] * 0.5, Z = dims[2] * 0.5;
+  return V3((i & 4) ? -X : X, (i & 2) ? -Y : Y, (i & 1) ? -Z : Z);
+}
+struct BodyRef {
+  const double *x, *R, *vl, *va, *dims; int shape, enabled;
+};
+B2M_HD B2M_INL BodyRef body_ref(const EnvMem& m, int b) {
+  BodyRef r; r.x = m.bx + 3 * b; r.R = m.bR + 9 * b; r.vl = m.bvl + 3 * b; r.va = m.bva + 3 * b; r.dims = m.bdims + 3 * b;
+  r.shape = m.bshape[b]; r.enabled = m.ben[b]; return r;
+}
+B2M_HD B2M_INL V3 to_global(const BodyRef& b, const V3& p) { return ld3(b.x) + rot(b.R, p); }
+B2M_HD B2M_INL V3 to_local(const BodyRef& b, const V3& p) { return rotT(b.R, p - ld3(b.x)); }
+B2M_HD B2M_INL V3 point_vel(const BodyRef& b, const V3& p) {
+  if (!b.enabled) return V3();
+  return ld3(b.vl) + cross(ld3(b.va), p - ld3(b.x));
+}
+B2M_HD B2M_INL V3 lin_vel(const BodyRef& b) { return b.enabled ? ld3(b.vl) : V3(); }
+B2M_HD B2M_INL V3 ang_vel(const BodyRef& b) { return b.enabled ? ld3(b.va) : V3(); }
+
+B2M_HD inline double box_closest_point(const double* dims, const V3& point, V3& closest) {   // BoxPrimitive.cpp:788-836
+  const double ext[3] = {dims[0] * 0.5, dims[1] * 0.5, dims[2] * 0.5};
+  const double pt[3] = {point.x, point.y, point.z};
+  double cl[3] = {point.x, point.y, point.z};
+  bool inside = true;
+  double sqrDist = 0.0, intDist = -B2M_INF, delta;
+  for (int i = 0; i < 3; i++) {
+    if (pt[i] < -ext[i]) { delta = pt[i] + ext[i]; cl[i] = -ext[i]; sqrDist += delta * delta; inside = false; }
+    else if (pt[i] > ext[i]) { delta = pt[i] - ext[i]; cl[i] = ext[i]; sqrDist += delta * delta; inside = false; }
+    else if (inside) { const double d = -fmin(fabs(ext[i] - pt[i]), fabs(pt[i] + ext[i])); intDist = fmax(intDist, d); }
+  }
+  closest = V3(cl[0], cl[1], cl[2]);
+  return inside ? intDist : sqrt(sqrDist);
+}
+
+// signed distance + closest points for an ordered pair (PlanePrimitive.cpp:342-411, SpherePrimitive.cpp:104-135, BoxPrimitive.cpp:257-276)
+B2M_HD inline bool signed_dist_ordered(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
+  if (A.shape == SH_PLANE && B.shape == SH_BOX) {
+    double min_dist = B2M_INF; V3 pb_best, pthis;
+    for (int i = 0; i < 8; i++) {
+      const V3 vg = to_global(B, box_vertex(B.dims, i));
+      const V3 pv = to_local(A, vg);
+      if (pv.y < min_dist) { min_dist = pv.y; pb_best = vg; pthis = pv; }
+    }
+    pthis.y = 0.0;
+    dist = min_dist; pA = to_global(A, pthis); pB = pb_best;
+    return true;
+  }
+  if (A.shape == SH_PLANE && B.shape == SH_SPHERE) {
+    const V3 c = to_local(A, ld3(B.x));
+    const V3 lowest(c.x, c.y - B.dims[0], c.z);
+    const V3 pthis(c.x, 0.0, c.z);
+    dist = lowest.y; pA = to_global(A, pthis); pB = to_global(A, lowest);
+    return true;
+  }
+  if (A.shape == SH_SPHERE && B.shape == SH_SPHERE) {
+    const V3 d = ld3(B.x) - ld3(A.x);
+    const double len = norm(d);
+    const double dd = len - A.dims[0] - B.dims[0];
+    const V3 u = d * (1.0 / len);
+    const double sa = (dd > 0.0) ? A.dims[0] : A.dims[0] + dd, sb = (dd > 0.0) ? B.dims[0] : B.dims[0] + dd;
+    dist = dd; pA = ld3(A.x) + u * sa; pB = ld3(B.x) - u * sb;
+    return true;
+  }
+  if (A.shape == SH_BOX && B.shape == SH_SPHERE) {
+    const V3 c = to_local(A, ld3(B.x)); V3 pbox;
+    dist = box_closest_point(A.dims, c, pbox) - B.dims[0];
+    const V3 pbox_g = to_global(A, pbox);
+    const V3 v = pbox_g - ld3(B.x);
+    const double vnorm = norm(v);
+    pA = pbox_g;
+    pB = (vnorm == 0.0) ? ld3(B.x) : ld3(B.x) + v * ((B.dims[0] + fmin(dist, 0.0)) / vnorm);
+    return true;
+  }
+  return false;
+}
+B2M_HD inline bool signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
+  if (signed_dist_ordered(A, B, dist, pA, pB)) return true;
+  if (signed_dist_ordered(B, A, dist, pB, pA)) return true;
+  return false;
+}
+
+B2M_HD inline void orthonormal_basis(const V3& v1, V3& v2, V3& v3) {   // Ravelin Vector3d::determine_orthonormal_basis
+  const double x = fabs(v1.x), y = fabs(v1.y), z = fabs(v1.z);
+  V3 a;
+  if (x < y) { if (x < z) a = V3(1, 0, 0); else a = V3(0, 0, 1); }
+  else       { if (y < z) a = V3(0, 1, 0); else a = V3(0, 0, 1); }
+  v2 = normalize(cross(v1, a));
+  v3 = normalize(cross(v1, v2));
+}
+
+struct ContactOut { V3 p, n; int b1, b2; double dist; };
+
+// Contacts of one pair, at most `cap` (CCD.inl:3-82 dispatch and leaves).  Executed by ONE thread; returns the count found.
+B2M_HD inline int pair_contacts(const EnvMem& m, int ia, int ib, double TOL, ContactOut* out, int cap) {
+  const BodyRef A = body_ref(m, ia), B = body_ref(m, ib);
+  int cnt = 0;
+  if ((A.shape == SH_SPHERE && B.shape == SH_PLANE) || (A.shape == SH_PLANE && B.shape == SH_SPHERE)) {   // CCD.inl:805-846
+    const int is = (A.shape == SH_SPHERE) ? ia : ib, ip = (A.shape == SH_SPHERE) ? ib : ia;
+    const BodyRef S = body_ref(m, is), P = body_ref(m, ip);
+    const V3 c = to_local(P, ld3(S.x));
+    const double dist = c.y - S.dims[0];
+    if (dist > TOL) return 0;
+    const V3 p(c.x, 0.5 * (c.y - S.dims[0]), c.z);
+    if (cnt < cap) { out[cnt].p = to_global(P, p); out[cnt].n = rot(P.R, V3(0, 1, 0)); out[cnt].b1 = is; out[cnt].b2 = ip; out[cnt].dist = dist; }
+    return cnt + 1;
+  }
+  if ((A.shape == SH_BOX && B.shape == SH_PLANE) || (A.shape == SH_PLANE && B.shape == SH_BOX)) {         // CCD.inl:850-886
+    const int ix = (A.shape == SH_BOX) ? ia : ib, ip = (A.shape == SH_BOX) ? ib : ia;
+    const BodyRef X = body_ref(m, ix), P = body_ref(m, ip);
+    const V3 n = rot(P.R, V3(0, 1, 0));
+    for (int i = 0; i < 8; i++) {
+      const V3 vg = to_global(X, box_vertex(X.dims, i));
+      const double dist = to_local(P, vg).y;
+      if (dist <= TOL) {
+        if (cnt < cap) { out[cnt].p = vg; out[cnt].n = -n; out[cnt].b1 = ip; out[cnt].b2 = ix; out[cnt].dist = dist; }
+        cnt++;
+      }
+    }
+    return cnt;
+  }
+  if (A.shape == SH_SPHERE && B.shape == SH_SPHERE) {                                                      // CCD.inl:1165-1206
+    const V3 d = ld3(A.x) - ld3(B.x);
+    const double dist = norm(d) - A.dims[0] - B.dims[0];
+    if (dist > TOL) return 0;
+    const V3 n = normalize(d);
+    const V3 closest_A = ld3(A.x) - n * A.dims[0], closest_B = ld3(B.x) + n * B.dims[0];
+    if (cnt < cap) { out[cnt].p = (closest_A + closest_B) * 0.5; out[cnt].n = n; out[cnt].b1 = ia; out[cnt].b2 = ib; out[cnt].dist = dist; }
+    return cnt + 1;
+  }
+  if ((A.shape == SH_BOX && B.shape == SH_SPHERE) || (A.shape == SH_SPHERE && B.shape == SH_BOX)) {        // CCD.inl:1210-1259
+    const int ix = (A.shape == SH_BOX) ? ia : ib, is = (A.shape == SH_BOX) ? ib : ia;
+    const BodyRef X = body_ref(m, ix), S = body_ref(m, is);
+    const double HX = X.dims[0] * 0.5, HY = X.dims[1] * 0.5, HZ = X.dims[2] * 0.5, Rr = S.dims[0];
+    const V3 c = to_local(X, ld3(S.x));
+    const V3 pbox(fmin(fmax(c.x, -HX), HX), fmin(fmax(c.y, -HY), HY), fmin(fmax(c.z, -HZ), HZ));
+    const V3 pbox_g = to_global(X, pbox);
+    V3 psph = rotT(S.R, pbox_g - ld3(S.x));
+    const double psph_nrm = norm(psph);
+    double dist;
+    if (fabs(pbox.x) < HX || fabs(pbox.y) < HY || fabs(pbox.z) < HZ || psph_nrm < Rr) {
+      const double box_dist = fmin(HX - fabs(pbox.x), fmin(HY - fabs(pbox.y), HZ - fabs(pbox.z)));
+      dist = -fmin(box_dist, Rr - psph_nrm);
+    } else {
+      psph = psph * (Rr / psph_nrm);
+      dist = norm(to_local(X, to_global(S, psph)) - pbox);
+    }
+    if (dist > TOL) return 0;
+    const V3 psph_g = to_global(S, psph);
+    V3 p, normal;
+    if (dist > 0.0) {
+      p = (psph_g + pbox_g) * 0.5;
+      normal = pbox_g - psph_g;
+      const double nrm = norm(normal);
+      if (nrm > B2M_NEAR_ZERO) normal = normal * (1.0 / nrm);
+      else normal = normalize(rot(S.R, psph));
+    } else {
+      p = psph_g;
+      normal = normalize(rot(S.R, psph));
+    }
+    if (cnt < cap) { out[cnt].p = p; out[cnt].n = normal; out[cnt].b1 = ix; out[cnt].b2 = is; out[cnt].dist = dist; }
+    return cnt + 1;
+  }
+  return 0;
+}
+
+B2M_HD B2M_INL double contact_vel(const EnvMem& m, const ContactOut& c) {   // UnilateralConstraint.cpp:695-747
+  const V3 ta = point_vel(body_ref(m, c.b1), c.p), tb = point_vel(body_ref(m, c.b2), c.p);
+  return dot(c.n, ta - tb);
+}
+
+B2M_HD B2M_INL double calc_max_dist(const BodyRef& rb, const V3& n, double rmax) {   // CCD.cpp:585-607 (velocity taken at the GLOBAL origin)
+  if (!rb.enabled) return 0.0;
+  const V3 xd0 = ld3(rb.vl) - cross(ld3(rb.va), ld3(rb.x));
+  return dot(n, xd0) + norm(cross(ld3(rb.va), n)) * rmax;
+}
+B2M_HD B2M_INL double calc_rmax(const BodyRef& b) {                                  // CCD.cpp:1023-1101
+  if (b.shape == SH_SPHERE) return b.dims[0];
+  if (b.shape == SH_BOX) return sqrt((b.dims[0] / 2.0) * (b.dims[0] / 2.0) + (b.dims[1] / 2.0) * (b.dims[1] / 2.0) + (b.dims[2] / 2.0) * (b.dims[2] / 2.0));
+  return 0.0;
+}
+B2M_HD B2M_INL bool rel_equal(double x, double y) { return fabs(x - y) <= B2M_NEAR_ZERO * fmax(fabs(x), fmax(fabs(y), 1.0)); }
+B2M_HD B2M_INL bool collinear(const V3& a, const V3& b, const V3& c) {               // CompGeom.cpp:1923-1931
+  return rel_equal((c.z - a.z) * (b.y - a.y), (b.z - a.z) * (c.y - a.y)) &&
+         rel_equal((b.z - a.z) * (c.x - a.x), (b.x - a.x) * (c.z - a.z)) &&
+         rel_equal((b.x - a.x) * (c.y - a.y), (b.y - a.y) * (c.x - a.x));
+}
+B2M_HD inline double next_CA_box_plane(const BodyRef& box, const V3& rv_lin, const V3& rv_ang, const V3& normal, double offset0) {   // CCD.cpp:407-460
+  double max_step = B2M_INF;
+  const V3 nP = rotT(box.R, normal);
+  const V3 p0 = normal * offset0;
+  const double offset = dot(nP, to_local(box, p0));
+  const double av_norm = norm(rv_ang);
+  const double lv_dot_n = -dot(nP, rv_lin);
+  for (int i = 0; i < 8; i++) {
+    const V3 vtx = box_vertex(box.dims, i);
+    const double r = norm(vtx);
+    const double dist = dot(nP, vtx) - offset;
+    if (dist < B2M_NEAR_ZERO) continue;
+    const double speed = fmax(0.0, lv_dot_n + av_norm * r);
+    max_step = fmin(max_step, dist / speed);
+  }
+  return max_step;
+}
+
+// CCD::calc_CA_Euler_step for one pair (CCD.cpp:122-400).  Executed by ONE thread.
+B2M_HD inline double pair_CA(const EnvMem& m, int p) {
+  const int ia = m.pair_a[p], ib = m.pair_b[p];
+  const BodyRef A = body_ref(m, ia), B = body_ref(m, ib);
+  const double pdist = m.pd_dist[p];
+  if (pdist == B2M_INF) return B2M_INF;
+  ContactOut con[8];
+  if (A.shape == SH_SPHERE || B.shape == SH_SPHERE) {                       // :138-166
+    if (!(pdist > B2M_NEAR_ZERO)) {
+      const int nc = pair_contacts(m, ia, ib, B2M_NEAR_ZERO, con, 8);
+      if (nc == 1 && fabs(contact_vel(m, con[0])) < B2M_NEAR_ZERO * 10) return B2M_INF;
+    }
+  }
+  if (pdist <= 0.0) {                                                       // :189-190 -> :238-400
+    const int nc = pair_contacts(m, ia, ib, B2M_NEAR_ZERO, con, 8);
+    if (nc == 0) return B2M_INF;
+    const double d = dot(con[0].n, con[0].p);
+    for (int i = 0; i < nc; i++) if (contact_vel(m, con[i]) < -B2M_NEAR_ZERO) return 0.0;
+    if (nc >= 3 && !collinear(con[0].p, con[1].p, con[2].p)) return B2M_INF;   // :288-330 (always points 0,1,2)
+    const BodyRef gA = body_ref(m, con[0].b1), gB = body_ref(m, con[0].b2);
+    if (gA.shape == SH_BOX && gB.shape == SH_PLANE) {
+      const V3 rl = rotT(gA.R, lin_vel(gA)) - rotT(gA.R, point_vel(gB, ld3(gA.x)));
+      const V3 ra = rotT(gA.R, ang_vel(gA) - ang_vel(gB));
+      return next_CA_box_plane(gA, rl, ra, con[0].n, d);
+    }
+    if (gA.shape == SH_PLANE && gB.shape == SH_BOX) {
+      const V3 rl = rotT(gB.R, point_vel(gA, ld3(gB.x))) - rotT(gB.R, lin_vel(gB));
+      const V3 ra = rotT(gB.R, ang_vel(gA) - ang_vel(gB));
+      return next_CA_box_plane(gB, -rl, -ra, -con[0].n, -d);
+    }
+    return B2M_INF;
+  }
+  const V3 d0 = ld3(m.pd_pa + 3 * p) - ld3(m.pd_pb + 3 * p);               // :193-229
+  const double d0_norm = norm(d0);
+  const V3 n0 = d0 * (1.0 / d0_norm);
+  const double tA = calc_max_dist(A, -n0, calc_rmax(A));
+  const double tB = calc_max_dist(B, n0, calc_rmax(B));
+  double total = tA + tB;
+  if (total < 0.0) total = 0.0;
+  return fmin(B2M_INF, pdist / total);
+}
+
+// ---------- env load / store ----------
+template <class G>
+B2M_DEV void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
+  const int nb = P.nb, ne = P.n_envs;
+  for (int b = g.tid; b < nb; b += G::size) {
+    m.bshape[b] = P.shape[(size_t)b * ne + e];
+    m.ben[b] = P.enabled[(size_t)b * ne + e];
+    m.bmass[b] = P.mass[(size_t)b * ne + e];
+  }
+  for (int k = g.tid; k < 3 * nb; k += G::size) { m.bdims[k] = P.dims[(size_t)k * ne + e]; m.bJ[k] = P.inertia[(size_t)k * ne + e]; }
+  for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; m.bx[k] = P.q[((size_t)b * 7 + c) * ne + e]; }
+  for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; m.bq[k] = P.q[((size_t)b * 7 + 3 + c) * ne + e]; }
+  for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; m.bvl[k] = P.v[((size_t)b * 6 + c) * ne + e]; m.bva[k] = P.v[((size_t)b * 6 + 3 + c) * ne + e]; }
+  g.sync();
+  // quaternions are stored normalised (b200moby_set_state does what set_generalized_coordinates_euler does)
+  for (int b = g.tid; b < nb; b += G::size) quat_to_R(m.bq + 4 * b, m.bR + 9 * b);
+  if (g.tid == 0) {                                              // all-pairs table (CollisionDetection.cpp:28-54, ConstraintSimulator.cpp:471-485)
+    int np = 0;
+    for (int i = 0; i < nb; i++)
+      for (int j = i + 1; j < nb; j++) {
+        if (!(m.ben[i] || m.ben[j])) continue;
+        if (m.bshape[i] == SH_NONE || m.bshape[j] == SH_NONE) continue;
+        if (P.NK[((size_t)i * nb + j) * ne + e] == 0) continue;
+        m.pair_a[np] = i; m.pair_b[np] = j; np++;
+      }
+    m.scal[S_NPAIRS] = np;
+  }
+  g.sync();
+}
+
+template <class G>
+B2M_DEV void env_store(const G& g, const SimParams& P, int e, const EnvMem& m) {
+  const int nb = P.nb, ne = P.n_envs;
+  for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; if (m.ben[b]) { P.q[((size_t)b * 7 + c) * ne + e] = m.bx[k]; P.v[((size_t)b * 6 + c) * ne + e] = m.bvl[k]; P.v[((size_t)b * 6 + 3 + c) * ne + e] = m.bva[k]; } }
+  for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; if (m.ben[b]) P.q[((size_t)b * 7 + 3 + c) * ne + e] = m.bq[k]; }
+}
+
+template <class G>
+B2M_DEV void calc_pairwise_distances(const G& g, EnvMem& m) {       // ConstraintSimulator.cpp:450-468, one thread per pair
+  const int np = m.scal[S_NPAIRS];
+  for (int p = g.tid; p < np; p += G::size) {
+    double dist; V3 pa, pb;
+    if (!signed_dist(body_ref(m, m.pair_a[p]), body_ref(m, m.pair_b[p]), dist, pa, pb)) dist = B2M_INF;
+    m.pd_dist[p] = dist; st3(m.pd_pa + 3 * p, pa); st3(m.pd_pb + 3 * p, pb);
+  }
+  g.sync();
+}
+
+// Simulator::precalc_fwd_dyn + calc_fwd_dyn for free bodies + v += h a (Simulator.cpp:319-350,482-602;
+// TimeSteppingSimulator.cpp:181-192; GravityForce.cpp:32-48).  One thread per body.
+template <class G>
+B2M_DEV void fwd_dyn_integrate_velocity(const G& g, const SimParams& P, EnvMem& m, double h) {
+  for (int b = g.tid; b < P.nb; b += G::size) {
+    if (!m.ben[b]) continue;
+    const double* R = m.bR + 9 * b; const double* J = m.bJ + 3 * b;
+    const double mass = m.bmass[b];
+    const V3 f = V3(P.gx, P.gy, P.gz) * mass;
+    const V3 va = ld3(m.bva + 3 * b), vl = ld3(m.bvl + 3 * b);
+    const V3 wb = rotT(R, va);
+    const V3 Jw = rot(R, V3(J[0] * wb.x, J[1] * wb.y, J[2] * wb.z));
+    const V3 rhs = V3() - cross(va, Jw);
+    const V3 rb = rotT(R, rhs);
+    const V3 alpha = rot(R, V3(rb.x / J[0], rb.y / J[1], rb.z / J[2]));
+    const V3 a = f * (1.0 / mass);
+    st3(m.bvl + 3 * b, vl + a * h);
+    st3(m.bva + 3 * b, va + alpha * h);
+  }
+  g.sync();
+}
+
+// position half of the semi-implicit Euler step with conservative advancement (TimeSteppingSimulator.cpp:119-168)
+template <class G>
+B2M_DEV double integrate_positions_CA(const G& g, const SimParams& P, EnvMem& m, double dt) {
+  const int nb = P.nb;
+  for (int k = g.tid; k < 3 * nb; k += G::size) m.xsave[k] = m.bx[k];
+  for (int k = g.tid; k < 4 * nb; k += G::size) m.qsave[k] = m.bq[k];
+  g.sync();
+  double h = 0.0;
+  while (h < dt) {
+    calc_pairwise_distances(g, m);
+    const int np = m.scal[S_NPAIRS];
+    double CA = B2M_INF;
+    for (int p = g.tid; p < np; p += G::size) CA = fmin(CA, pair_CA(m, p));
+    CA = g.min(CA);
+    if (CA <= 0.0) break;
+    double tc = fmax(P.min_step_size, CA);
+    tc = fmin(dt - h, tc);
+    g.sync();
+    for (int b = g.tid; b < nb; b += G::size) {
+      if (!m.ben[b]) continue;
+      const double s = h + tc;
+      const double qx = m.qsave[4 * b], qy = m.qsave[4 * b + 1], qz = m.qsave[4 * b + 2], qw = m.qsave[4 * b + 3];
+      const V3 w = ld3(m.bva + 3 * b), vl = ld3(m.bvl + 3 * b);
+      const double dw = 0.5 * (-qx * w.x - qy * w.y - qz * w.z);   // Ravelin Quatd::deriv
+      const double dx = 0.5 * (+qw * w.x + qz * w.y - qy * w.z);
+      const double dy = 0.5 * (-qz * w.x + qw * w.y + qx * w.z);
+      const double dz = 0.5 * (+qy * w.x - qx * w.y + qw * w.z);
+      m.bx[3 * b] = vl.x * s + m.xsave[3 * b]; m.bx[3 * b + 1] = vl.y * s + m.xsave[3 * b + 1]; m.bx[3 * b + 2] = vl.z * s + m.xsave[3 * b + 2];
+      const double nx = dx * s + qx, ny = dy * s + qy, nz = dz * s + qz, nw = dw * s + qw;
+      const double nrm = sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+      double* qt = m.bq + 4 * b;
+      qt[0] = nx / nrm; qt[1] = ny / nrm; qt[2] = nz / nrm; qt[3] = nw / nrm;
+      quat_to_R(qt, m.bR + 9 * b);
+    }
+    g.sync();
+    h += tc;
+  }
+  return h;
+}
+
+// ConstraintSimulator::find_unilateral_constraints (:488-537) + preprocess_constraint (:390-417): contacts in pair order
+template <class G>
+B2M_DEV void find_unilateral_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int np = m.scal[S_NPAIRS], nb = P.nb, ne = P.n_envs;
+  if (g.tid == 0) {
+    int nc = 0; bool overflow = false;
+    ContactOut con[8];
+    for (int p = 0; p < np; p++) {
+      if (!(m.pd_dist[p] < P.contact_dist_thresh)) continue;
+      const int k = pair_contacts(m, m.pair_a[p], m.pair_b[p], P.contact_dist_thresh, con, 8);
+      for (int i = 0; i < k && i < 8; i++) {
+        if (nc >= P.cmax) { overflow = true; break; }
+        st3(m.cp + 3 * nc, con[i].p); st3(m.cnrm + 3 * nc, con[i].n);
+        V3 t1, t2; orthonormal_basis(con[i].n, t1, t2);
+        st3(m.ct1 + 3 * nc, t1); st3(m.ct2 + 3 * nc, t2);
+        m.cb1[nc] = con[i].b1; m.cb2[nc] = con[i].b2; m.cdist[nc] = con[i].dist;
+        const int lo = min(con[i].b1, con[i].b2), hi = max(con[i].b1, con[i].b2);
+        const size_t o = ((size_t)lo * nb + hi) * ne + e;
+        m.cmu[nc] = P.mu_c[o]; m.cmuv[nc] = P.mu_v[o]; m.ceps[nc] = P.eps[o]; m.ccomp[nc] = P.compliance[o]; m.cNK[nc] = P.NK[o];
+        nc++;
+      }
+    }
+    m.scal[S_NCON] = nc;
+    lc[CNT_CONTACTS] += nc;
+    if (overflow) lc[CNT_OVERFLOW]++;
+  }
+  g.sync();
+}
+
+B2M_HD B2M_INL double constraint_vel(const EnvMem& m, int c) {
+  ContactOut co; co.p = ld3(m.cp + 3 * c); co.n = ld3(m.cnrm + 3 * c); co.b1 = m.cb1[c]; co.b2 = m.cb2[c];
+  return contact_vel(m, co);
+}
+
+// 6x6 SPD inverse through Cholesky, same order as the checker's inverse_SPD (ImpactConstraintHandler.cpp:1599-1611)
+B2M_HD inline void inverse_spd6(double* A) {
+  double L[36];
+  for (int i = 0; i < 36; i++) L[i] = A[i];
+  for (int j = 0; j < 6; j++) {
+    double d = L[j * 6 + j];
+    for (int k = 0; k < j; k++) d = fma(-L[k * 6 + j], L[k * 6 + j], d);
+    d = sqrt(d);
+    L[j * 6 + j] = d;
+    for (int i = j + 1; i < 6; i++) {
+      double s = L[j * 6 + i];
+      for (int k = 0; k < j; k++) s = fma(-L[k * 6 + i], L[k * 6 + j], s);
+      L[j * 6 + i] = s / d;
+    }
+  }
+  for (int j = 0; j < 6; j++) {
+    double e[6];
+    for (int i = 0; i < 6; i++) e[i] = (i == j) ? 1.0 : 0.0;
+    for (int i = 0; i < 6; i++) { double s = e[i]; for (int k = 0; k < i; k++) s = fma(-L[k * 6 + i], e[k], s); e[i] = s / L[i * 6 + i]; }
+    for (int i = 5; i >= 0; i--) { double s = e[i]; for (int k = i + 1; k < 6; k++) s = fma(-L[i * 6 + k], e[k], s); e[i] = s / L[i * 6 + i]; }
+    for (int i = 0; i < 6; i++) A[j * 6 + i] = e[i];
+  }
+}
+
+// index helpers for the island-local arrays
+B2M_HD B2M_INL double* jrow(const EnvMem& m, int nc, int d, int i, int blk) { return m.Jr + ((((size_t)d * nc + i) * 2 + blk) * 6); }
+B2M_HD B2M_INL double* xjrow(const EnvMem& m, int nc, int d, int i, int blk) { return m.XJ + ((((size_t)d * nc + i) * 2 + blk) * 6); }
+// D blocks stored for d1<=d2: index 0:nn 1:ns 2:nt 3:ss 4:st 5:tt
+B2M_HD B2M_INL int dblk(int d1, int d2) { return d1 == 0 ? d2 : (d1 == 1 ? 2 + d2 : 5); }
+B2M_HD B2M_INL double Dn(const EnvMem& m, int nc, int d1, int d2, int i, int j) {
+  return (d1 <= d2) ? m.D[(size_t)dblk(d1, d2) * nc * nc + (size_t)i * nc + j] : m.D[(size_t)dblk(d2, d1) * nc * nc + (size_t)j * nc + i];
+}
+
+// ImpactConstraintHandler::compute_problem_data (:1898-2166) for the island whose contacts are icon[0..nc)
+template <class G>
+B2M_DEV void compute_problem_data(const G& g, const SimParams& P, EnvMem& m) {
+  const int nc = m.scal[S_NC], nb = P.nb;
+  // X = blockdiag(inverse_SPD(generalized inertia)) (:1590-1611), one thread per island body
+  for (int b = g.tid; b < nb; b += G::size) {
+    if (m.gcoff[b] < 0) continue;
+    double Mg[36];
+    for (int i = 0; i < 36; i++) Mg[i] = 0.0;
+    const double* R = m.bR + 9 * b; const double* J = m.bJ + 3 * b;
+    for (int k = 0; k < 3; k++) Mg[k * 6 + k] = m.bmass[b];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        double s = 0.0;
+        for (int k = 0; k < 3; k++) s += R[r * 3 + k] * J[k] * R[c * 3 + k];
+        Mg[(3 + c) * 6 + (3 + r)] = s;
+      }
+    inverse_spd6(Mg);
+    for (int i = 0; i < 36; i++) m.Xb[36 * b + i] = Mg[i];       // column-major: X(r,c) = Xb[c*6+r]
+  }
+  // Jacobian rows [d, r x d] (:1817-1895), one thread per (dir, contact, block)
+  for (int t = g.tid; t < 3 * nc * 2; t += G::size) {
+    const int blk = t & 1, i = (t >> 1) % nc, d = (t >> 1) / nc;
+    const int c = m.icon[i];
+    const int bi = blk == 0 ? m.cb1[c] : m.cb2[c];
+    double* row = jrow(m, nc, d, i, blk);
+    if (!m.ben[bi]) { for (int k = 0; k < 6; k++) row[k] = 0.0; continue; }
+    V3 dir = d == 0 ? ld3(m.cnrm + 3 * c) : (d == 1 ? ld3(m.ct1 + 3 * c) : ld3(m.ct2 + 3 * c));
+    if (blk == 1) dir = -dir;
+    const V3 rxd = cross(ld3(m.cp + 3 * c) - ld3(m.bx + 3 * bi), dir);
+    row[0] = dir.x; row[1] = dir.y; row[2] = dir.z; row[3] = rxd.x; row[4] = rxd.y; row[5] = rxd.z;
+  }
+  g.sync();
+  // X_CdT restricted to the block's body: XJ = row * X_body (:2125-2127), one thread per (dir, contact, block, k)
+  for (int t = g.tid; t < 3 * nc * 2 * 6; t += G::size) {
+    const int k = t % 6, rest = t / 6, blk = rest & 1, i = (rest >> 1) % nc, d = (rest >> 1) / nc;
+    const int c = m.icon[i];
+    const int bi = blk == 0 ? m.cb1[c] : m.cb2[c];
+    double s = 0.0;
+    if (m.ben[bi]) {
+      const double* row = jrow(m, nc, d, i, blk);
+      const double* X = m.Xb + 36 * bi;
+      for (int kk = 0; kk < 6; kk++) s = fma(row[kk], X[k * 6 + kk], s);
+      s = 0.0 + s;
+    }
+    xjrow(m, nc, d, i, blk)[k] = s;
+  }
+  g.sync();
+  // Delassus blocks Cd1 X Cd2^T (:2133-2149), one thread per (block, i, j)
+  for (int t = g.tid; t < 6 * nc * nc; t += G::size) {
+    const int j = t % nc, i = (t / nc) % nc, bk = t / (nc * nc);
+    const int d1 = bk < 3 ? 0 : (bk < 5 ? 1 : 2), d2 = bk < 3 ? bk : (bk < 5 ? bk - 2 : 2);
+    const int ci = m.icon[i], cj = m.icon[j];
+    double s = 0.0;
+    for (int blk = 0; blk < 2; blk++) {
+      const int bi = blk == 0 ? m.cb1[ci] : m.cb2[ci];
+      if (!m.ben[bi]) continue;
+      int blk2 = -1;
+      if (m.cb1[cj] == bi) blk2 = 0; else if (m.cb2[cj] == bi) blk2 = 1;
+      if (blk2 < 0) continue;
+      const double* row = jrow(m, nc, d1, i, blk);
+      const double* xj = xjrow(m, nc, d2, j, blk2);
+      for (int k = 0; k < 6; k++) s = fma(row[k], xj[k], s);
+    }
+    m.D[t] = s;
+  }
+  // Cd v (:2157-2159)
+  for (int t = g.tid; t < 3 * nc; t += G::size) {
+    const int i = t % nc, d = t / nc;
+    const int c = m.icon[i];
+    double s = 0.0;
+    for (int blk = 0; blk < 2; blk++) {
+      const int bi = blk == 0 ? m.cb1[c] : m.cb2[c];
+      if (!m.ben[bi]) continue;
+      const double* row = jrow(m, nc, d, i, blk);
+      const double v[6] = {m.bvl[3 * bi], m.bvl[3 * bi + 1], m.bvl[3 * bi + 2], m.bva[3 * bi], m.bva[3 * bi + 1], m.bva[3 * bi + 2]};
+      for (int k = 0; k < 6; k++) s = fma(row[k], v[k], s);
+    }
+    m.Cv[t] = s;
+    m.imp[t] = 0.0;
+  }
+  g.sync();
+}
+
+// QP-as-LCP (ImpactConstraintHandlerQP.cpp:129-148,216,271-497), nl = 0.  Returns n.
+template <class G>
+B2M_DEV int build_qp_lcp(const G& g, const SimParams& P, EnvMem& m) {
+  const int nc = m.scal[S_NC];
+  const int NV = 5 * nc;
+  if (g.tid == 0) {
+    int row = 0;
+    for (int i = 0; i < nc; i++) { const int half = m.cNK[m.icon[i]] / 2; for (int j = 0; j < half; j++) { m.frow_c[row] = i; m.frow_j[row] = j; row++; } }
+    m.scal[S_N] = NV + nc + row;
+  }
+  g.sync();
+  const int n = m.scal[S_N];
+  if (n > P.nmax) return n;
+  const double* qcos = P.fr_tab; const double* qsin = P.fr_tab + (size_t)(B2M_NKMAX + 1) * (B2M_NKMAX / 2);
+  for (int t = g.tid; t < n * n; t += G::size) {
+    const int c = t / n, r = t - c * n;
+    // entry of A = [H(0:nc,:) ; friction rows] at (a, col<NV)
+    double val = 0.0;
+    const bool upper = r < NV, left = c < NV;
+    if (upper && left) {
+      const int br = r / nc, i = r - br * nc, bc = c / nc, j = c - bc * nc;
+      const int dr = br == 0 ? 0 : (br == 1 || br == 3 ? 1 : 2), dc = bc == 0 ? 0 : (bc == 1 || bc == 3 ? 1 : 2);
+      const double v = Dn(m, nc, dr, dc, i, j);
+      val = ((br >= 3) != (bc >= 3)) ? -v : v;
+      if (r == c && r < nc) val += m.ccomp[m.icon[r]];
+    } else if (upper != left) {
+      const int a = (upper ? c : r) - NV, col = upper ? r : c;       // A(a, col); the upper-right block is -A^T
+      double av;
+      if (a < nc) {
+        const int bc = col / nc, j = col - bc * nc;
+        const int dc = bc == 0 ? 0 : (bc == 1 || bc == 3 ? 1 : 2);
+        const double v = Dn(m, nc, 0, dc, a, j);
+        av = (bc >= 3) ? -v : v;
+        if (col == a) av += m.ccomp[m.icon[a]];
+      } else {
+        const int fr = a - nc, i = m.frow_c[fr], j = m.frow_j[fr];
+        const int NKi = m.cNK[m.icon[i]];
+        const size_t ti = (size_t)NKi * (B2M_NKMAX / 2) + j;
+        if (col == i) av = m.cmu[m.icon[i]];
+        else if (col == nc + i || col == 3 * nc + i) av = -qcos[ti];
+        else if (col == 2 * nc + i || col == 4 * nc + i) av = -qsin[ti];
+        else av = 0.0;
+      }
+      val = upper ? -av : av;
+    }
+    m.MM[t] = val;
+  }
+  for (int r = g.tid; r < n; r += G::size) {
+    double v;
+    if (r < NV) { const int br = r / nc, i = r - br * nc; const int d = br == 0 ? 0 : (br == 1 || br == 3 ? 1 : 2); v = m.Cv[d * nc + i]; if (br >= 3) v = -v; }
+    else if (r < NV + nc) v = m.Cv[r - NV];
+    else { const int i = m.frow_c[r - NV - nc]; const double cs = m.Cv[nc + i], ct = m.Cv[2 * nc + i]; v = m.cmuv[m.icon[i]] * sqrt(cs * cs + ct * ct); }
+    m.qq[r] = v;
+  }
+  g.sync();
+  return n;
+}
+
+// Anitescu-Potra LCP (ImpactConstraintHandlerLCP.cpp:94-310), nl = 0.  Returns n.
+template <class G>
+B2M_DEV int build_ap_lcp(const G& g, const SimParams& P, EnvMem& m) {
+  const int NC = m.scal[S_NC];
+  const int NCONST = 5 * NC;
+  if (g.tid == 0) {
+    int row = 0;
+    for (int i = 0; i < NC; i++) { const int NKi = m.cNK[m.icon[i]]; const int k4 = NKi > 4 ? (NKi + 4) / 4 : 1; for (int k = 0; k < k4; k++) { m.frow_c[row] = i; m.frow_j[row] = k; row++; } }
+    m.scal[S_N] = NCONST + row;
+  }
+  g.sync();
+  const int n = m.scal[S_N];
+  if (n > P.nmax) return n;
+  const double* acos_ = P.fr_tab + 2 * (size_t)(B2M_NKMAX + 1) * (B2M_NKMAX / 2);
+  const double* asin_ = P.fr_tab + 3 * (size_t)(B2M_NKMAX + 1) * (B2M_NKMAX / 2);
+  for (int t = g.tid; t < n * n; t += G::size) {
+    const int c = t / n, r = t - c * n;
+    double val = 0.0;
+    const bool upper = r < NCONST, left = c < NCONST;
+    if (upper && left) {                                        // UL, block order [n, s+, s-, t+, t-]
+      const int br = r / NC, i = r - br * NC, bc = c / NC, j = c - bc * NC;
+      const int dr = br == 0 ? 0 : (br <= 2 ? 1 : 2), dc = bc == 0 ? 0 : (bc <= 2 ? 1 : 2);
+      const bool nr = (br == 2 || br == 4), ncg = (bc == 2 || bc == 4);
+      const double v = Dn(m, NC, dr, dc, i, j);
+      val = (nr != ncg) ? -v : v;
+    } else if (upper != left) {
+      const int fr = (upper ? c : r) - NCONST, col = upper ? r : c;
+      const int i = m.frow_c[fr], k = m.frow_j[fr];
+      const int NKi = m.cNK[m.icon[i]];
+      double e = 0.0;                                           // |LL(fr, col)| pattern for the friction blocks
+      const int bc = col / NC, j = col - bc * NC;
+      if (j == i && bc >= 1) {
+        if (NKi > 4) { const size_t ti = (size_t)NKi * (B2M_NKMAX / 2) + k; e = (bc <= 2) ? acos_[ti] : asin_[ti]; }
+        else e = 1.0;
+      }
+      if (upper) val = e;                                       // UR = +cos/sin (:268-275,288-293)
+      else val = (bc == 0 && j == i) ? m.cmu[m.icon[i]] : -e;   // LL = [mu, -cos.., -sin..]
+    }
+    m.MM[t] = val;
+  }
+  for (int r = g.tid; r < n; r += G::size) {
+    double v = 0.0;
+    if (r < NCONST) { const int br = r / NC, i = r - br * NC; const int d = br == 0 ? 0 : (br <= 2 ? 1 : 2); v = m.Cv[d * NC + i]; if (br == 2 || br == 4) v = -v; }
+    m.qq[r] = v;
+  }
+  g.sync();
+  return n;
+}
+
+// update_from_stacked (:298-397) without bilateral joints: v += X_CnT cn + X_CsT cs + X_CtT ct, impulses from `imp`
+template <class G>
+B2M_DEV void apply_to_bodies(const G& g, const SimParams& P, EnvMem& m, const double* imp) {
+  const int nc = m.scal[S_NC], nb = P.nb;
+  for (int t = g.tid; t < 6 * nb; t += G::size) {
+    const int b = t / 6, k = t - 6 * b;
+    if (m.gcoff[b] < 0) continue;
+    double s3[3];
+    for (int d = 0; d < 3; d++) {
+      double s = 0.0;
+      for (int i = 0; i < nc; i++) {
+        const int c = m.icon[i];
+        int blk = -1;
+        if (m.cb1[c] == b) blk = 0; else if (m.cb2[c] == b) blk = 1;
+        if (blk < 0) continue;
+        s = fma(xjrow(m, nc, d, i, blk)[k], imp[d * nc + i], s);
+      }
+      s3[d] = s;
+    }
+    m.dv[t] = (s3[0] + s3[1]) + s3[2];
+  }
+  g.sync();
+  for (int t = g.tid; t < 6 * nb; t += G::size) {
+    const int b = t / 6, k = t - 6 * b;
+    if (m.gcoff[b] < 0) continue;
+    if (k < 3) m.bvl[3 * b + k] = m.bvl[3 * b + k] + m.dv[t]; else m.bva[3 * b + k - 3] = m.bva[3 * b + k - 3] + m.dv[t];
+  }
+  g.sync();
+}
+
+// update_constraint_velocities_from_impulses (:427-464), nl = 0
+template <class G>
+B2M_DEV void update_constraint_velocities(const G& g, EnvMem& m, const double* imp) {
+  const int nc = m.scal[S_NC];
+  for (int t = g.tid; t < 3 * nc; t += G::size) {
+    const int i = t % nc, d = t / nc;
+    double acc = m.Cv[t];
+    for (int k = 0; k < 3; k++) {
+      double s = 0.0;
+      for (int j = 0; j < nc; j++) s = fma(Dn(m, nc, d, k, i, j), imp[k * nc + j], s);
+      acc += s;
+    }
+    m.Cv[t] = acc;
+  }
+  g.sync();
+}
+
+template <class G>
+B2M_DEV double min_constraint_velocity(const G& g, const EnvMem& m) {            // :413-424
+  const int nc = m.scal[S_NC];
+  double v = B2M_INF;
+  for (int i = g.tid; i < nc; i += G::size) v = fmin(v, m.Cv[i]);
+  return g.min(v);
+}
+
+// solve_qp_work (ImpactConstraintHandlerQP.cpp:94-263): fills imp = [cn | cs | ct]
+template <class G>
+B2M_DEV void solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int nc = m.scal[S_NC];
+  const int n = build_qp_lcp(g, P, m);
+  if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * nc; t += G::size) m.imp[t] = 0.0; g.sync(); return; }
+  const int ne = P.n_envs;
+  const bool warm = (P.zlast_n[e] == n);                                            // :158-162 with rule H1 (zero fill)
+  for (int i = g.tid; i < n; i += G::size) m.z[i] = warm ? P.zlast[(size_t)i * ne + e] : 0.0;
+  g.sync();
+  long long stats[2] = {0, 0};
+  int piv = 0;
+  int st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats);   // :219
+  long long fast_calls = stats[0], pivots = stats[1], lemke_calls = 0;
+  if (st == LCP_UNVERIFIED) {
+    g.sync();
+    stats[0] = stats[1] = 0;
+    st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats);      // :222-225
+    lemke_calls = stats[0]; pivots += stats[1];
+    if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
+  }
+  g.sync();
+  if (g.tid == 0) {
+    lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
+    lc[CNT_PIVOT_FLOPS] += (unsigned long long)pivots * 2ull * n * (n + 1);
+    if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
+    P.zlast_n[e] = n;
+  }
+  for (int i = g.tid; i < n; i += G::size) P.zlast[(size_t)i * ne + e] = m.z[i];    // :233
+  if (P.tap_n) {
+    if (g.tid == 0) P.tap_n[e] = n;
+    for (int t = g.tid; t < n * n; t += G::size) P.tap_MM[(size_t)e * P.nmax * P.nmax + t] = m.MM[t];
+    for (int i = g.tid; i < n; i += G::size) { P.tap_qq[(size_t)e * P.nmax + i] = m.qq[i]; P.tap_z[(size_t)e * P.nmax + i] = m.z[i]; }
+  }
+  for (int i = g.tid; i < nc; i += G::size) {                                       // update_from_stacked_qp
+    m.imp[i] = m.z[i];
+    m.imp[nc + i] = m.z[nc + i] - m.z[3 * nc + i];
+    m.imp[2 * nc + i] = m.z[2 * nc + i] - m.z[4 * nc + i];
+  }
+  g.sync();
+}
+
+// apply_model_to_connected_constraints (ImpactConstraintHandler.cpp:530-626)
+template <class G>
+B2M_DEV void apply_qp_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int nc = m.scal[S_NC];
+  solve_qp(g, P, e, m, lc);
+  apply_to_bodies(g, P, m, m.imp);
+  update_constraint_velocities(g, m, m.imp);
+  const double minv = min_constraint_velocity(g, m);
+  bool changed = false;                                           // apply_restitution(epd, z) :470-491 (H3: friction kept)
+  for (int i = g.tid; i < nc; i += G::size) {
+    const double c = m.imp[i] * m.ceps[m.icon[i]];
+    m.imp[i] = c;
+    if (c > B2M_NEAR_ZERO) changed = true;
+  }
+  changed = g.any(changed);
+  g.sync();
+  if (changed) {
+    apply_to_bodies(g, P, m, m.imp);
+    update_constraint_velocities(g, m, m.imp);
+    const double minv_plus = min_constraint_velocity(g, m);
+    if (minv_plus < 0.0 && minv_plus < minv - B2M_NEAR_ZERO) {
+      solve_qp(g, P, e, m, lc);
+      apply_to_bodies(g, P, m, m.imp);
+    }
+  }
+}
+
+// apply_ap_model (ImpactConstraintHandlerLCP.cpp:94-370): imp = this solve, acc += imp (propagate_impulse_data)
+template <class G>
+B2M_DEV void solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int NC = m.scal[S_NC];
+  const int n = build_ap_lcp(g, P, m);
+  if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * NC; t += G::size) m.imp[t] = 0.0; g.sync(); return; }
+  long long stats[2] = {0, 0};
+  int piv = 0;
+  int st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, -2, m.z, m.work, m.iwork, &piv, stats);   // :333
+  if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
+  g.sync();
+  if (g.tid == 0) {
+    lc[CNT_LCP_SOLVES]++; lc[CNT_LEMKE_CALLS] += stats[0]; lc[CNT_PIVOTS] += stats[1];
+    lc[CNT_PIVOT_FLOPS] += (unsigned long long)stats[1] * 2ull * n * (n + 1);
+    if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
+  }
+  if (P.tap_n) {
+    if (g.tid == 0) P.tap_n[e] = n;
+    for (int t = g.tid; t < n * n; t += G::size) P.tap_MM[(size_t)e * P.nmax * P.nmax + t] = m.MM[t];
+    for (int i = g.tid; i < n; i += G::size) { P.tap_qq[(size_t)e * P.nmax + i] = m.qq[i]; P.tap_z[(size_t)e * P.nmax + i] = m.z[i]; }
+  }
+  for (int i = g.tid; i < NC; i += G::size) {                     // :336-342
+    m.imp[i] = m.z[i];
+    m.imp[NC + i] = m.z[NC + i] - m.z[2 * NC + i];
+    m.imp[2 * NC + i] = m.z[3 * NC + i] - m.z[4 * NC + i];
+    for (int d = 0; d < 3; d++) m.acc[d * NC + i] += m.imp[d * NC + i];
+  }
+  g.sync();
+}
+
+template <class G>
+B2M_DEV void apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {   // ImpactConstraintHandlerLCP.cpp:36-91
+  const int nc = m.scal[S_NC];
+  for (int t = g.tid; t < 3 * nc; t += G::size) m.acc[t] = 0.0;
+  g.sync();
+  solve_ap(g, P, e, m, lc);
+  update_constraint_velocities(g, m, m.imp);
+  const double minv = min_constraint_velocity(g, m);
+  bool changed = false;                                           // apply_restitution(q) :497-524
+  for (int i = g.tid; i < nc; i += G::size) {
+    const double c = m.imp[i] * m.ceps[m.icon[i]];
+    m.imp[i] = c;
+    if (c > B2M_NEAR_ZERO) changed = true;
+  }
+  changed = g.any(changed);
+  g.sync();
+  if (changed) {
+    for (int i = g.tid; i < nc; i += G::size) { m.imp[nc + i] = 0.0; m.imp[2 * nc + i] = 0.0; }
+    g.sync();
+    update_constraint_velocities(g, m, m.imp);
+    const double minv_plus = min_constraint_velocity(g, m);
+    if (minv_plus < 0.0 && minv_plus < minv - B2M_NEAR_ZERO) solve_ap(g, P, e, m, lc);
+    else { for (int t = g.tid; t < 3 * nc; t += G::size) m.acc[t] += m.imp[t]; g.sync(); }
+  }
+  apply_to_bodies(g, P, m, m.acc);                                // apply_impulses (:676-748): accumulated contact impulses
+}
+
+// calc_impacting_unilateral_constraint_forces (ConstraintSimulator.cpp:298-355) -> apply_model (ImpactConstraintHandler.cpp:96-168)
+template <class G>
+B2M_DEV void process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int ncon = m.scal[S_NCON], nb = P.nb;
+  if (ncon == 0) return;
+  bool impacting = false;
+  for (int c = g.tid; c < ncon; c += G::size) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) impacting = true;
+  if (!g.any(impacting)) return;
+  // islands (UnilateralConstraint.cpp:940-1194) with the canonical order of rule H4: seeds in ascending body index,
+  // neighbours in contact (edge insertion) order, each visited body picks up its remaining contacts in list order.
+  if (g.tid == 0) {
+    unsigned nodes = 0;
+    for (int c = 0; c < ncon; c++) { if (m.ben[m.cb1[c]]) nodes |= 1u << m.cb1[c]; if (m.ben[m.cb2[c]]) nodes |= 1u << m.cb2[c]; }
+    for (int b = 0; b < nb; b++) m.bisl[b] = -1;
+    for (int c = 0; c < ncon; c++) m.cisl[c] = -1;
+    int nisl = 0, nord = 0;
+    unsigned active = 0;
+    int queue[B200MOBY_MAX_BODIES];
+    while (nodes) {
+      int node = 0; while (!((nodes >> node) & 1u)) node++;
+      int qh = 0, qt = 0; unsigned processed = 0, queued = 1u << node;
+      queue[qt++] = node;
+      m.isl_start[nisl] = nord;
+      while (qh < qt) {
+        node = queue[qh++];
+        nodes &= ~(1u << node);
+        processed |= 1u << node;
+        m.bisl[node] = nisl;
+        for (int c = 0; c < ncon; c++) {
+          const int b1 = m.cb1[c], b2 = m.cb2[c];
+          if (!(m.ben[b1] && m.ben[b2])) continue;
+          const int nbr = (b1 == node) ? b2 : ((b2 == node) ? b1 : -1);
+          if (nbr >= 0 && !((queued >> nbr) & 1u)) { queued |= 1u << nbr; queue[qt++] = nbr; }
+        }
+        for (int c = 0; c < ncon; c++)
+          if (m.cisl[c] < 0 && (m.cb1[c] == node || m.cb2[c] == node)) { m.cisl[c] = nisl; m.corder[nord++] = c; }
+      }
+      nisl++;
+    }
+    m.isl_start[nisl] = nord;
+    for (int c = 0; c < ncon; c++) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) active |= 1u << m.cisl[c];   // remove_inactive_groups :1197-1225
+    m.scal[S_NISL] = nisl;
+    m.scal[S_FLAG] = (int)active;
+  }
+  g.sync();
+  const int nisl = m.scal[S_NISL];
+  const unsigned active = (unsigned)m.scal[S_FLAG];
+  for (int k = 0; k < nisl; k++) {
+    if (!((active >> k) & 1u)) continue;
+    if (g.tid == 0) {
+      const int s0 = m.isl_start[k], nc = m.isl_start[k + 1] - s0;
+      for (int i = 0; i < nc; i++) m.icon[i] = m.corder[s0 + i];
+      int gc = 0;
+      for (int b = 0; b < nb; b++) { if (m.bisl[b] == k && m.ben[b]) { m.gcoff[b] = gc; gc += 6; } else m.gcoff[b] = -1; }
+      m.scal[S_NC] = nc; m.scal[S_NGC] = gc;
+    }
+    g.sync();
+    compute_problem_data(g, P, m);
+    if (g.tid == 0) {   // F_delassus = 2 (3nc) 36 b + 2 (3nc)^2 6, F_apply = 2 NGC 3nc
+      const unsigned long long nc = m.scal[S_NC], ngc = m.scal[S_NGC];
+      unsigned long long blocks = 0;
+      for (unsigned i = 0; i < nc; i++) blocks += (m.ben[m.cb1[m.icon[i]]] ? 1 : 0) + (m.ben[m.cb2[m.icon[i]]] ? 1 : 0);
+      lc[CNT_ASM_FLOPS] += 2 * 3 * 36 * blocks + 2 * (3 * nc) * (3 * nc) * 6 + 2 * ngc * 3 * nc;
+    }
+    if (P.model == 1) apply_ap_model(g, P, e, m, lc); else apply_qp_model(g, P, e, m, lc);
+    g.sync();
+  }
+  // ImpactToleranceException check over the solved islands (:153-167): counted, never fatal
+  bool still = false;
+  for (int c = g.tid; c < ncon; c += G::size) if (((active >> m.cisl[c]) & 1u) && constraint_vel(m, c) < -B2M_NEAR_ZERO) still = true;
+  if (g.any(still) && g.tid == 0) lc[CNT_IMPACT_TOL]++;
+}
+
+// TimeSteppingSimulator::do_mini_step (:114-222); returns h
+template <class G>
+B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
+  const double h = integrate_positions_CA(g, P, m, dt);
+  fwd_dyn_integrate_velocity(g, P, m, h);
+  calc_pairwise_distances(g, m);
+  find_unilateral_constraints(g, P, e, m, lc);
+  process_constraints(g, P, e, m, lc);
+  if (g.tid == 0) {     // F_fd = 60 per free body (Newton-Euler); F_narrow = 8 vertices x 20 (box) or 20 (sphere) per pair and distance pass
+    lc[CNT_MINI_STEPS]++;
+    unsigned long long f = 0;
+    for (int b = 0; b < P.nb; b++) if (m.ben[b]) f += 60;
+    for (int p = 0; p < m.scal[S_NPAIRS]; p++) f += 3 * ((m.bshape[m.pair_a[p]] == SH_BOX || m.bshape[m.pair_b[p]] == SH_BOX) ? 160 : 20);
+    lc[CNT_ASM_FLOPS] += f;
+  }
+  return h;
+}
+
+// n_steps x TimeSteppingSimulator::step (:52-111, :433-455) for env e; stabilization disabled
+template <class G>
+B2M_DEV void env_run(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int n_steps, unsigned long long* lc) {
+  env_load(g, P, e, m);
+  double t = P.time[e];
+  for (int s = 0; s < n_steps; s++) {
+    double h = 0.0;
+    while (h < dt) { const double hh = do_mini_step(g, P, e, m, dt - h, lc); h += hh; t += hh; }
+    if (g.tid == 0) lc[CNT_ENV_STEPS]++;
+  }
+  g.sync();
+  env_store(g, P, e, m);
+  if (g.tid == 0) P.time[e] = t;
+  g.sync();
+}
+
+}  // namespace b2m

@@ -133,7 +133,7 @@ void oracle_sim_counters(void* h, b200moby_counters* c) {
   const Counters& k = ((OracleSim*)h)->sim.cnt;
   c->env_steps = k.env_steps; c->mini_steps = k.mini_steps; c->lcp_solves = k.lcp_solves; c->lcp_fast_calls = k.lcp_fast_calls;
   c->lemke_calls = k.lemke_calls; c->pivots = k.pivots; c->lcp_failures = k.lcp_failures; c->impact_tol_events = k.impact_tol_events;
-  c->contacts = k.contacts; c->max_lcp_n = k.max_lcp_n;
+  c->contacts = k.contacts; c->max_lcp_n = k.max_lcp_n; c->pivot_flops = k.pivot_flops; c->assembly_flops = 0;
 }
 // LCP of the most recent impact solve: returns n; copies min(n*n, cap) etc.
 int oracle_sim_last_lcp(void* h, double* MM, double* qq, double* z, int ncap) {
@@ -192,7 +192,7 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
       Counters& c = cs[t]; const Counters& k = S.cnt;
       c.env_steps += k.env_steps; c.mini_steps += k.mini_steps; c.lcp_solves += k.lcp_solves; c.lcp_fast_calls += k.lcp_fast_calls;
       c.lemke_calls += k.lemke_calls; c.pivots += k.pivots; c.lcp_failures += k.lcp_failures; c.impact_tol_events += k.impact_tol_events;
-      c.contacts += k.contacts; c.max_lcp_n = std::max(c.max_lcp_n, k.max_lcp_n);
+      c.contacts += k.contacts; c.max_lcp_n = std::max(c.max_lcp_n, k.max_lcp_n); c.pivot_flops += k.pivot_flops;
     }
   };
   if (threads == 1) work(0);
@@ -202,9 +202,47 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
     for (auto& c : cs) {
       total->env_steps += c.env_steps; total->mini_steps += c.mini_steps; total->lcp_solves += c.lcp_solves; total->lcp_fast_calls += c.lcp_fast_calls;
       total->lemke_calls += c.lemke_calls; total->pivots += c.pivots; total->lcp_failures += c.lcp_failures; total->impact_tol_events += c.impact_tol_events;
-      total->contacts += c.contacts; total->max_lcp_n = std::max(total->max_lcp_n, c.max_lcp_n);
+      total->contacts += c.contacts; total->max_lcp_n = std::max(total->max_lcp_n, c.max_lcp_n); total->pivot_flops += c.pivot_flops;
     }
   }
 }
+
+// Persistent batch (keeps every env's simulator, including its warm start, across calls): the CPU baseline of bench.py.
+struct OracleBatch { std::vector<Sim> sims; int e0; };
+
+void* oracle_batch_create(const b200moby_scene_desc* d, const double* q, const double* v, int e0, int e1, int tie) {
+  OracleBatch* B = new OracleBatch;
+  B->e0 = e0;
+  const int nb = d->n_bodies, ne = d->n_envs;
+  B->sims.resize(e1 - e0);
+  std::vector<double> qa(nb * 7), va(nb * 6);
+  for (int e = e0; e < e1; e++) {
+    Sim& S = B->sims[e - e0];
+    fill_from_desc(S, d, e); S.lcp.tie = (TieRule)tie;
+    for (int b = 0; b < nb; b++) { for (int k = 0; k < 7; k++) qa[b * 7 + k] = q[((size_t)b * 7 + k) * ne + e]; for (int k = 0; k < 6; k++) va[b * 6 + k] = v[((size_t)b * 6 + k) * ne + e]; }
+    set_state(S, qa.data(), va.data());
+  }
+  return B;
+}
+void oracle_batch_destroy(void* h) { delete (OracleBatch*)h; }
+void oracle_batch_run(void* h, double dt, int n_steps, int threads, b200moby_counters* total) {
+  OracleBatch* B = (OracleBatch*)h;
+  if (threads < 1) threads = 1;
+  const int n = (int)B->sims.size();
+  auto work = [&](int t) { for (int i = t; i < n; i += threads) for (int s = 0; s < n_steps; s++) B->sims[i].step(dt); };
+  if (threads == 1) work(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+  if (total) {
+    std::memset(total, 0, sizeof(*total));
+    for (auto& S : B->sims) {
+      const Counters& k = S.cnt;
+      total->env_steps += k.env_steps; total->mini_steps += k.mini_steps; total->lcp_solves += k.lcp_solves; total->lcp_fast_calls += k.lcp_fast_calls;
+      total->lemke_calls += k.lemke_calls; total->pivots += k.pivots; total->lcp_failures += k.lcp_failures; total->impact_tol_events += k.impact_tol_events;
+      total->contacts += k.contacts; total->max_lcp_n = std::max(total->max_lcp_n, k.max_lcp_n); total->pivot_flops += k.pivot_flops;
+    }
+  }
+}
+// state of env (e0 + i) as AoS [body][7], [body][6]
+void oracle_batch_get_state(void* h, int i, double* q, double* v) { get_state(((OracleBatch*)h)->sims[i], q, v); }
 
 }  // extern "C"

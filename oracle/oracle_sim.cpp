@@ -690,6 +690,7 @@ static void solve_qp(Sim& S, ProblemData& q) {
     }
   }
   S.cnt.lcp_fast_calls += S.lcp.n_fast_calls - f0; S.cnt.lemke_calls += S.lcp.n_lemke_calls - l0; S.cnt.pivots += S.lcp.n_pivots_total - p0;
+  S.cnt.pivot_flops += (long long)(S.lcp.n_pivots_total - p0) * 2 * n * (n + 1);
   S.zlast = z;                                                          // :233
   S.last_n = n; S.last_MM = MM; S.last_qq = qq; S.last_z = z;
   const int nc = q.nc;                                                  // update_from_stacked_qp (UnilateralConstraintProblemData.h:218-228)
@@ -736,6 +737,7 @@ static void solve_ap(Sim& S, ProblemData& q, Vec& acc_cn, Vec& acc_cs, Vec& acc_
     z.assign(n, 0.0);
   }
   S.cnt.lemke_calls += S.lcp.n_lemke_calls - l0; S.cnt.pivots += S.lcp.n_pivots_total - p0;
+  S.cnt.pivot_flops += (long long)(S.lcp.n_pivots_total - p0) * 2 * n * (n + 1);
   S.last_n = n; S.last_MM = MM; S.last_qq = qq; S.last_z = z;
   const int NC = q.nc;
   for (int i = 0; i < NC; i++) {                                        // :336-342
@@ -792,7 +794,7 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
     if (bodies[b2].enabled) nodes.insert(b2);
     if (bodies[b1].enabled && bodies[b2].enabled) { adj[b1].push_back(b2); adj[b2].push_back(b1); }
   }
-  for (int i = 0; i < nb; i++) std::sort(adj[i].begin(), adj[i].end());   // multimap: neighbours in key order
+  // std::multimap keeps equal keys in insertion order: neighbours are visited in contact order
   std::vector<char> taken(contacts.size(), 0);
   std::vector<std::pair<std::vector<Contact*>, std::vector<int> > > groups;
   while (!nodes.empty()) {

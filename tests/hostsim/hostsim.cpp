@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE ONLY -- never part of libb200moby.so and not reachable from the C ABI.
+// Compiles the kernels' device code (moby_b200/csrc/*.cuh) for the host with a single-thread "group" so the
+// kernel logic can be checked against the oracle in the CPU test suite, where no GPU exists.  Floating-point
+// results are the ones the GPU produces (the .cu files are built with -fmad=false, this file with
+// -ffp-contract=off, and both use explicit fma at the same places).
+#include <cstring>
+#include <vector>
+#include "../../include/b200moby.h"
+#include "../../moby_b200/csrc/friction_table.h"
+#include "../../moby_b200/csrc/sim_device.cuh"
+
+using namespace b2m;
+
+extern "C" {
+
+// q [nb][7][ne], v [nb][6][ne], time [ne], zlast [nmax][ne], zlast_n [ne], counters [CNT_COUNT] all host, updated in place.
+// Returns nmax (call with q == NULL to query sizes only).
+int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time, double* zlast, int* zlast_n,
+                unsigned long long* counters, double dt, int n_steps, int e0, int e1, double* tapMM, double* tapqq, double* tapz, int* tapn) {
+  const int ne = d->n_envs, nb = d->n_bodies;
+  int cmax = 0, nmax = 0, npmax = 0;
+  std::vector<int> sh(nb), en(nb), nk(nb * nb);
+  for (int e = 0; e < ne; e++) {
+    for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
+    for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) nk[i * nb + j] = d->NK[((size_t)i * nb + j) * ne + e];
+    int c, n, np; b2m_env_bounds(nb, sh.data(), en.data(), nk.data(), d->impact_model, c, n, np);
+    cmax = std::max(cmax, c); nmax = std::max(nmax, n); npmax = std::max(npmax, np);
+  }
+  cmax = std::max(cmax, 1); nmax = std::max(nmax, 1); npmax = std::max(npmax, 1);
+  if (!q) return nmax;
+  std::vector<double> tab = b2m_friction_table();
+  SimParams P; memset(&P, 0, sizeof(P));
+  P.n_envs = ne; P.nb = nb; P.cmax = cmax; P.nmax = nmax; P.npmax = npmax; P.model = d->impact_model;
+  P.shape = d->shape; P.enabled = d->enabled; P.mass = d->mass; P.dims = d->dims; P.inertia = d->inertia;
+  P.mu_c = d->mu_coulomb; P.mu_v = d->mu_viscous; P.eps = d->epsilon; P.compliance = d->compliance; P.NK = d->NK;
+  P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
+  P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size;
+  P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
+  P.tap_MM = tapMM; P.tap_qq = tapqq; P.tap_z = tapz; P.tap_n = tapn;
+  std::vector<double> wd(env_doubles(nb, cmax, nmax, npmax));
+  std::vector<int> wi(env_ints(nb, cmax, nmax, npmax));
+  EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
+  SerialGroup g(nullptr);
+  unsigned long long lc[CNT_COUNT]; memset(lc, 0, sizeof(lc));
+  for (int e = e0; e < e1; e++) env_run(g, P, e, m, dt, n_steps, lc);
+  for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) counters[k] = std::max(counters[k], lc[k]); else counters[k] += lc[k]; }
+  return nmax;
+}
+
+// LCP solvers through the same device code (serial group)
+int hostsim_lcp(int mode, int n, const double* M, const double* q, double* z, int warm, double piv_tol, double zero_tol,
+                int min_exp, int step_exp, int max_exp, int* pivots, int* log, int log_cap, int* log_len) {
+  std::vector<double> wd(std::max(lemke_work_doubles(n), fast_work_doubles(n)) + 8);
+  std::vector<int> wi(std::max(lemke_work_ints(n), fast_work_ints(n)) + 8);
+  SerialGroup g(nullptr);
+  int piv = 0, nlog = 0, st;
+  if (!warm) for (int i = 0; i < n; i++) z[i] = 0.0;
+  std::vector<double> zz(z, z + n);
+  if (mode == 0) st = lemke_solve(g, n, M, n, q, 0.0, piv_tol, zero_tol, zz.data(), wd.data(), wi.data(), &piv, log, log_cap, &nlog);
+  else if (mode == 1) st = lcp_fast_solve(g, n, M, n, q, 0.0, zero_tol, warm != 0, zz.data(), wd.data(), wi.data(), &piv, log, log_cap, &nlog);
+  else if (mode == 2) st = lcp_lemke_regularized(g, n, M, n, q, piv_tol, zero_tol, min_exp, step_exp, max_exp, zz.data(), wd.data(), wi.data(), &piv, nullptr);
+  else st = lcp_fast_regularized(g, n, M, n, q, zero_tol, warm != 0, min_exp, step_exp, max_exp, zz.data(), wd.data(), wi.data(), &piv, nullptr);
+  const bool ok = (st == LCP_OK || st == LCP_TRIVIAL || st >= LCP_REGULARIZED);
+  if (ok || mode == 0 || mode == 2) for (int i = 0; i < n; i++) z[i] = zz[i];
+  if (pivots) *pivots = piv;
+  if (log_len) *log_len = nlog;
+  return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""ctypes wrapper of tests/hostsim/libhostsim.so: the kernels' device code compiled for the host with a
+single-thread group.  Test infrastructure only (lets the CPU suite check kernel logic against the oracle)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from moby_b200.capi import SceneDesc
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+CNT = ("env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
+       "impact_tol_events", "contacts", "max_lcp_n", "overflow", "pivot_flops", "assembly_flops")
+_lib = None
+
+
+def build():
+    src = os.path.join(HERE, "hostsim.cpp")
+    out = os.path.join(HERE, "libhostsim.so")
+    csrc = os.path.join(os.path.dirname(HERE), "..", "moby_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", out, src])
+    return out
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.hostsim_run.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+        L.hostsim_lcp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class HostSim:
+    """Steps a SceneBatch with the device code on the host; state arrays use the product's SoA layout."""
+
+    def __init__(self, scene, taps=False):
+        self.scene = scene
+        self._d = scene.cdesc()
+        self.nmax = lib().hostsim_run(C.byref(self._d), None, None, None, None, None, None, 0.0, 0, 0, 0, None, None, None, None)
+        ne = scene.n_envs
+        self.q, self.v = scene.q.copy(), scene.v.copy()
+        self.q[:, 3:7, :] /= np.sqrt((self.q[:, 3:7, :] ** 2).sum(axis=1, keepdims=True))   # as b200moby_set_state does
+        self.time = np.zeros(ne)
+        self.zlast, self.zlast_n = np.zeros((self.nmax, ne)), np.zeros(ne, np.int32)
+        self.counters = np.zeros(16, np.uint64)
+        self.taps = taps
+        if taps:
+            self.tapMM, self.tapqq = np.zeros((ne, self.nmax * self.nmax)), np.zeros((ne, self.nmax))
+            self.tapz, self.tapn = np.zeros((ne, self.nmax)), np.zeros(ne, np.int32)
+
+    def step(self, dt, n=1, e0=0, e1=None):
+        e1 = self.scene.n_envs if e1 is None else e1
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        t = [p(self.tapMM), p(self.tapqq), p(self.tapz), p(self.tapn)] if self.taps else [None] * 4
+        lib().hostsim_run(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
+                          dt, n, e0, e1, *t)
+
+    def counters_dict(self):
+        return {k: int(self.counters[i]) for i, k in enumerate(CNT)}
+
+    def last_lcp(self, e):
+        n = int(self.tapn[e])
+        return n, self.tapMM[e, :n * n].reshape(n, n).T.copy(), self.tapqq[e, :n].copy(), self.tapz[e, :n].copy()
+
+
+def lcp(mode, M, q, z0=None, piv_tol=-1.0, zero_tol=-1.0, min_exp=-20, step_exp=1, max_exp=1, log_cap=4096):
+    """mode 0 lemke, 1 fast, 2 lemke_regularized, 3 fast_regularized.  Returns (status, z, pivots, log)."""
+    n = len(q)
+    Mf = np.asfortranarray(np.asarray(M, np.float64))
+    q = np.ascontiguousarray(q, np.float64)
+    z = np.zeros(n) if z0 is None else np.array(z0, np.float64)
+    piv, ll = C.c_int(), C.c_int()
+    log = np.zeros(log_cap, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = lib().hostsim_lcp(mode, n, p(Mf), p(q), p(z), 0 if z0 is None else 1, piv_tol, zero_tol, min_exp, step_exp, max_exp,
+                           C.byref(piv), p(log), log_cap, C.byref(ll))
+    return st, z, piv.value, log[:min(ll.value, log_cap)].copy()

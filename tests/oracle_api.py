@@ -48,6 +48,11 @@ def lib():
                                                   C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_lcp_lemke_regularized.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                    C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_batch_create.restype = C.c_void_p
+        L.oracle_batch_create.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.oracle_batch_destroy.argtypes = [C.c_void_p]
+        L.oracle_batch_run.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(Counters)]
+        L.oracle_batch_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -164,3 +169,29 @@ def batch_step(scene, q, v, dt, n_steps, e0=0, e1=None, tie=TIE_LOWEST, threads=
     c = Counters()
     lib().oracle_batch_step(C.byref(d), _p(q), _p(v), e0, e1, dt, n_steps, tie, threads, C.byref(c))
     return c.as_dict()
+
+
+class OracleBatch:
+    """Persistent CPU batch (envs [e0,e1) of a scene), optionally multi-threaded: bench.py's CPU baseline."""
+
+    def __init__(self, scene, e0=0, e1=None, tie=TIE_LOWEST):
+        self._d = scene.cdesc()
+        self.e0, self.e1 = e0, scene.n_envs if e1 is None else e1
+        self.nb = scene.n_bodies
+        q, v = np.ascontiguousarray(scene.q), np.ascontiguousarray(scene.v)
+        self.h = lib().oracle_batch_create(C.byref(self._d), _p(q), _p(v), self.e0, self.e1, tie)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_batch_destroy(self.h)
+            self.h = None
+
+    def run(self, dt, n_steps, threads=1):
+        c = Counters()
+        lib().oracle_batch_run(self.h, dt, n_steps, threads, C.byref(c))
+        return c.as_dict()
+
+    def get_state(self, i):
+        q, v = np.zeros((self.nb, 7)), np.zeros((self.nb, 6))
+        lib().oracle_batch_get_state(self.h, i, _p(q), _p(v))
+        return q, v

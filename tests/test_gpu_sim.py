@@ -1,0 +1,214 @@
+"""GPU parity tests of the stepped path (through the C ABI) against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from moby_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def _scene(name):
+    sc = {"box": lambda: scenes.sitting_box(1, NK=8, y0=0.50001), "boxmu": lambda: scenes.sitting_box(1, NK=4, mu=0.5),
+          "stack": lambda: scenes.sphere_stack(1), "ball": lambda: scenes.bouncing_ball(1),
+          "box_ap": lambda: scenes.sitting_box(1, NK=8, mu=0.3)}[name]()
+    if name == "box_ap":
+        sc.impact_model = scenes.MODEL_AP
+    return sc
+
+
+@pytest.mark.parametrize("name,dt,steps,tol", [("box", 1e-3, 300, 0.0), ("boxmu", 1e-3, 200, 0.0), ("stack", 1e-3, 200, 0.0),
+                                              ("ball", 0.025, 80, 1e-14), ("box_ap", 1e-3, 100, 1e-13)])
+def test_scene_trajectories_match_oracle(torch_cuda, oracle, name, dt, steps, tol):
+    """Reference scenes, step by step: identical contact counts, LCP sizes and mini-step counts; states bit-identical
+    where only lcp_fast runs, <= 1e-13 where Lemke (tableau vs LU-per-pivot) is involved."""
+    from moby_b200 import TimeSteppingSimulator
+    sc = _scene(name)
+    sim, osim = TimeSteppingSimulator(sc), oracle.OracleSim(sc)
+    for _ in range(steps):
+        sim.step(dt)
+        osim.step(dt)
+        q, v = sim.get_state()
+        qo, vo = osim.get_state()
+        assert np.abs(q[:, :, 0] - qo).max() <= tol and np.abs(v[:, :, 0] - vo).max() <= tol
+    cg, co = sim.counters(), osim.counters()
+    for k in ("env_steps", "mini_steps", "lcp_solves", "contacts", "max_lcp_n", "lcp_failures", "lcp_fast_calls", "lemke_calls"):
+        assert cg[k] == co[k], (k, cg[k], co[k])
+    assert abs(sim.current_time[0] - osim.time) < 1e-12
+
+
+def test_sitting_box_regress_fixture(torch_cuda):
+    """regress/sitting-box.dat (sub-sampled): the box rests at y = 0.5 for 10 s; tolerance as in test_oracle_regress."""
+    from moby_b200 import TimeSteppingSimulator
+    gold = np.loadtxt(os.path.join(GOLDEN, "regress_sitting_box.txt"))
+    sim = TimeSteppingSimulator(scenes.sitting_box(1, NK=8, y0=0.50001))
+    step = 0
+    for row in gold:
+        target = int(round(row[0] / 1e-3))
+        if target > step:
+            sim.step(1e-3, target - step)
+            step = target
+        q, _ = sim.get_state()
+        assert np.allclose(q[0, :, 0], row[1:8], rtol=0, atol=1.1e-5), row[0]
+    c = sim.counters()
+    assert c["lcp_failures"] == 0 and c["impact_tol_events"] == 0 and c["max_lcp_n"] == 40 and c["env_steps"] == 10000
+
+
+def test_sphere_stack_regress_fixture(torch_cuda):
+    from moby_b200 import TimeSteppingSimulator
+    gold = np.loadtxt(os.path.join(GOLDEN, "regress_sphere_stack.txt"))
+    sim = TimeSteppingSimulator(scenes.sphere_stack(1))
+    step = 0
+    for row in gold:
+        target = int(round(row[0] / 1e-3))
+        if target > step:
+            sim.step(1e-3, target - step)
+            step = target
+        q, _ = sim.get_state()
+        assert np.allclose(q[:3, :, 0].ravel(), row[1:22], rtol=0, atol=1e-9), row[0]
+
+
+def test_random_batch_matches_oracle(torch_cuda, oracle):
+    """SURVEY 8(d) case 2 (boxes with the TestDie perturbation + bouncing balls), 203 envs (ragged vs the block
+    size), 60 steps: every env within 1e-9 relative of the oracle; summed counters equal."""
+    from moby_b200 import TimeSteppingSimulator
+    ne = 203
+    sc = scenes.small_lcp_batch(ne, seed=5)
+    sim = TimeSteppingSimulator(sc)
+    sim.step(1e-3, 30)
+    sim.step(1e-3, 30)            # state round-trips through HBM between launches
+    q, v = sim.get_state()
+    qo, vo = sc.q.copy(), sc.v.copy()
+    co = oracle.batch_step(sc, qo, vo, 1e-3, 60, threads=8)
+    scale = np.maximum(1.0, np.maximum(np.abs(qo).max(axis=(0, 1)), np.abs(vo).max(axis=(0, 1))))
+    err = np.maximum(np.abs(q - qo).max(axis=(0, 1)), np.abs(v - vo).max(axis=(0, 1))) / scale
+    assert err.max() < 1e-9, (err.max(), int(err.argmax()))
+    cg = sim.counters()
+    for k in ("env_steps", "mini_steps", "lcp_solves", "contacts", "max_lcp_n", "lcp_failures"):
+        assert cg[k] == co[k], (k, cg[k], co[k])
+
+
+def test_gpu_bit_identical_to_host_build_of_same_code(torch_cuda):
+    """The kernels and their single-thread host build must agree bit for bit: no reduction-order or race effects."""
+    import hostsim_api
+    from moby_b200 import TimeSteppingSimulator
+    sc = scenes.small_lcp_batch(64, seed=9)
+    sim, hs = TimeSteppingSimulator(sc), hostsim_api.HostSim(sc)
+    sim.step(1e-3, 150)
+    hs.step(1e-3, 150)
+    q, v = sim.get_state()
+    assert np.array_equal(q, hs.q) and np.array_equal(v, hs.v)
+    sim2 = TimeSteppingSimulator(sc)
+    sim2.step(1e-3, 150)
+    q2, v2 = sim2.get_state()
+    assert np.array_equal(q, q2) and np.array_equal(v, v2)       # run-to-run determinism
+
+
+def test_stage_kernels_match_oracle(torch_cuda, oracle):
+    """find_contacts / delassus / fwd_dyn stage kernels on resting + perturbed boxes and balls."""
+    torch = torch_cuda
+    from moby_b200 import TimeSteppingSimulator
+    ne = 32
+    sc = scenes.small_lcp_batch(ne, seed=21)
+    # put every body in touching contact: boxes flat on the plane, balls resting, all moving down
+    for e in range(ne):
+        if sc.shape[0, e] == scenes.SHAPE_BOX:
+            sc.q[0, 3:7, e] = (0, 0, 0, 1)
+            sc.q[0, 1, e] = sc.dims[0, 1, e] / 2
+        else:
+            sc.q[0, 1, e] = 1.0
+        sc.v[0, 1, e] = -abs(sc.v[0, 1, e]) - 0.1
+    sim = TimeSteppingSimulator(sc)
+    qd, vd = torch.from_numpy(sc.q).cuda(), torch.from_numpy(sc.v).cuda()
+    con = sim.find_contacts(qd, vd, cap=8)
+    nmax = 64
+    MM, qq, n = sim.delassus(qd, vd, nmax)
+    torch.cuda.synchronize()
+    count, n = con["count"].cpu().numpy(), n.cpu().numpy()
+    MM, qq = MM.cpu().numpy(), qq.cpu().numpy()
+    pt, nr, t1, t2 = (con[k].cpu().numpy() for k in ("point", "normal", "tan1", "tan2"))
+    for e in range(ne):
+        osim = oracle.OracleSim(sc, env=e)
+        no, MMo, qqo, nco = osim.assemble(ncap=nmax)
+        assert count[e] == nco and n[e] == no, (e, count[e], nco, n[e], no)
+        assert np.array_equal(MM[e, :no * no].reshape(no, no).T, MMo) and np.array_equal(qq[e, :no], qqo)
+        osim.step(1e-9)           # records the contact list (a 1 ns step leaves the geometry unchanged to 1e-9)
+        oc = osim.last_contacts()
+        assert oc["count"] == count[e]
+        for c in range(count[e]):
+            assert np.allclose(pt[c, :, e], oc["point"][c], atol=1e-8) and np.array_equal(nr[c, :, e], oc["normal"][c])
+            assert np.array_equal(t1[c, :, e], oc["tan1"][c]) and np.array_equal(t2[c, :, e], oc["tan2"][c])
+            assert con["pair"].cpu().numpy()[c, e] == oc["pair"][c]
+    # forward dynamics + velocity integration of a free tumbling body: v += h a with a from Newton-Euler
+    sc2 = scenes.small_lcp_batch(ne, seed=22)
+    sc2.q[0, 1, :] += 10.0          # far from the plane
+    sim2 = TimeSteppingSimulator(sc2)
+    qd, vd = torch.from_numpy(sc2.q).cuda(), torch.from_numpy(sc2.v).cuda()
+    sim2.fwd_dyn(qd, vd, 1e-3)
+    vg = vd.cpu().numpy()
+    for e in range(ne):
+        osim = oracle.OracleSim(sc2, env=e)
+        qo, vo = osim.get_state()
+        osim.step(1e-3)
+        _, v1 = osim.get_state()
+        # the oracle moved the pose with the old velocity first; angular acceleration depends on the pose only through
+        # R J R^T, so compare linear exactly and angular to first order
+        assert np.array_equal(vg[0, :3, e], v1[0, :3])
+        assert np.allclose(vg[0, 3:, e], v1[0, 3:], rtol=0, atol=1e-5)
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE config 2 at full size (65,536 envs): size-independent properties after 50 steps."""
+    from moby_b200 import TimeSteppingSimulator
+    ne = 65536
+    sc = scenes.small_lcp_batch(ne, seed=0xB200)
+    sim = TimeSteppingSimulator(sc)
+    sim.step(1e-3, 50)
+    q, v = sim.get_state()
+    assert np.isfinite(q).all() and np.isfinite(v).all()
+    assert np.abs(np.sqrt((q[0, 3:7, :] ** 2).sum(axis=0)) - 1.0).max() < 1e-12          # unit quaternions
+    assert np.array_equal(q[1], sc.q[1]) and not v[1].any()                              # the ground never moves
+    isbox = sc.shape[0] == scenes.SHAPE_BOX
+    R = scenes._rotmat(q[0, 3:7, :])
+    he = sc.dims[0] / 2
+    low = q[0, 1, :] - (np.abs(R[1, 0]) * he[0] + np.abs(R[1, 1]) * he[1] + np.abs(R[1, 2]) * he[2])
+    assert low[isbox].min() > -1e-5                                                      # test/TestDie.cpp:130 property
+    assert (q[0, 1, ~isbox] - 1.0).min() > -1e-5
+    c = sim.counters()
+    assert c["env_steps"] == ne * 50 and c["lcp_failures"] == 0
+    assert np.allclose(sim.current_time, 0.05, rtol=0, atol=1e-12)
+
+
+def test_edge_cases(torch_cuda, oracle):
+    from moby_b200 import TimeSteppingSimulator, capi
+    # no contact ever: free fall of a tumbling box, exact vs oracle
+    sc = scenes.sitting_box(3, NK=4, y0=100.0)
+    sc.v[0, :, :] = np.arange(18).reshape(6, 3) * 0.1
+    sim = TimeSteppingSimulator(sc)
+    sim.step(1e-2, 20)
+    q, v = sim.get_state()
+    for e in range(3):
+        o = oracle.OracleSim(sc, env=e)
+        o.step(1e-2, 20)
+        qo, vo = o.get_state()
+        assert np.array_equal(q[:, :, e], qo) and np.array_equal(v[:, :, e], vo)
+    assert sim.counters()["lcp_solves"] == 0
+    # disabled pair: the box falls through the plane
+    sc = scenes.sitting_box(1, NK=4, y0=0.5)
+    sc.NK[:] = 0
+    sim = TimeSteppingSimulator(sc)
+    sim.step(1e-2, 50)
+    assert sim.get_state()[0][0, 1, 0] < 0.0
+    # invalid descriptors are refused, not silently computed
+    sc = scenes.sitting_box(1, NK=5)
+    with pytest.raises(capi.B200MobyError):
+        TimeSteppingSimulator(sc)
