@@ -108,6 +108,8 @@ def run_reference(args, rank, world):
     sample = 4096
     cores = os.cpu_count() or 1
     scene = scenes.small_lcp_batch(sample, seed=0xB200)
+    if args.min_step == "default":
+        scene.min_step_size_env = None
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_api as O
     O.build()
@@ -125,7 +127,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env_steps_per_s", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200"},
+        "config": {"workload": WORKLOAD, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200", "min_step_size": args.min_step},
         "lcp_solves_per_s": (c1["lcp_solves"] - c0["lcp_solves"]) / el,
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"first {sample} envs of the seeded batch, one step per timed step, {cores} host threads; "
@@ -146,6 +148,9 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--preroll", type=int, default=300, help="untimed steps before warm-up so contacts are active")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-step", default="scene", choices=["scene", "default"],
+                    help="scene: min-step-size of the source scenes (test/box.xml: 1e-3, bouncing-ball.xml: sqrt(eps)); "
+                         "default: sqrt(eps) everywhere (TimeSteppingSimulator.cpp:48)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -163,6 +168,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ne = args.envs_per_gpu
     scene = scenes.small_lcp_batch(ne, seed=0xB200 + rank)      # every rank owns its own envs (contiguous shard of the job)
+    if args.min_step == "default":
+        scene.min_step_size_env = None
     sim = TimeSteppingSimulator(scene, device=local_rank)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -195,6 +202,7 @@ def main():
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = sum(kernel_ms) * 1e-3
     cnt = sim.counters()
+    r_cnt = dict(cnt)
     # ---- end to end through the public API with HOST buffers: H2D state, step, D2H state, every step ----
     qh = torch.from_numpy(q0).pin_memory()
     vh = torch.from_numpy(v0).pin_memory()
@@ -233,7 +241,6 @@ def main():
         k_ms = float(np.mean(kernel_ms))
         # roofline of the dominant (only) kernel, per launch on this rank
         alg_bytes = BYTES_PER_ENV_STEP * ne
-        r_cnt = sim.counters()
         alg_flops = (r_cnt["pivot_flops"] + r_cnt["assembly_flops"]) / args.steps
         achieved_gbs = alg_bytes / (k_ms * 1e-3) / 1e9
         achieved_tf = alg_flops / (k_ms * 1e-3) / 1e12
@@ -242,12 +249,13 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": ne, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200+rank",
+                       "min_step_size": "boxes 1e-3 (test/box.xml), balls sqrt(eps) (bouncing-ball.xml)" if args.min_step == "scene" else "sqrt(eps) everywhere",
                        "impact_model": "QP-as-LCP (default build)", "stabilization": "off (max-iterations=0)",
                        "l2": "flushed between timed steps (256 MiB write outside the events)", "parallelism": f"envs sharded x{world}"},
             "lcp_solves_per_s": lcp_solves / t_dev,
             "mini_steps_per_step": mini_steps / max(env_steps, 1.0), "lcp_solves_per_env_step": lcp_solves / max(env_steps, 1.0),
             "pivots_per_solve": pivots / max(lcp_solves, 1.0), "lemke_calls": lemke_calls, "lcp_fast_calls": fast_calls,
-            "lcp_failures": failures, "contacts_per_env_step": contacts / max(env_steps, 1.0),
+            "lcp_failures": failures, "contacts_per_env_step": contacts / max(env_steps, 1.0), "ca_iterations_per_env_step": r_cnt["ca_iterations"] / max(r_cnt["env_steps"], 1),
             "wall_s_timed_region": wall,
             "e2e": {"value": total_envs * args.steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                     "how": "pinned host q,v -> device -> b200moby_set_state_dev -> step -> get_state_dev -> pinned host, every step"},

@@ -90,6 +90,7 @@ typedef struct {
   double gravity[3];            /* GravityForce accel= (GravityForce.cpp:32-68) */
   double contact_dist_thresh;   /* ConstraintSimulator.cpp:56, default 1e-6 */
   double min_step_size;         /* TimeSteppingSimulator.cpp:48, default sqrt(eps) */
+  const double* min_step_size_env; /* optional [env] override (XML min-step-size, TimeSteppingSimulator.cpp:470-472); NULL = scalar above */
   int    impact_model;          /* B200MOBY_MODEL_* */
   int    stabilization_max_iterations; /* must be 0 this round */
 } b200moby_scene_desc;
@@ -109,6 +110,7 @@ typedef struct {
   long long contacts;         /* contact constraints generated */
   long long max_lcp_n;        /* largest LCP dimension seen */
   long long pivot_flops;      /* sum over solves of pivots * 2 n (n+1): the algorithmic solver flops of SURVEY.md 8(d) */
+  long long ca_iterations;    /* position sub-steps of the conservative-advancement loop (TimeSteppingSimulator.cpp:133-168) */
   long long assembly_flops;   /* F_delassus + F_apply per island solve + F_fd + F_narrow per mini-step (SURVEY.md 8(d) formulas) */
 } b200moby_counters;
 

@@ -18,6 +18,7 @@ class SceneDesc(C.Structure):
         ("mu_coulomb", C.POINTER(C.c_double)), ("mu_viscous", C.POINTER(C.c_double)),
         ("epsilon", C.POINTER(C.c_double)), ("compliance", C.POINTER(C.c_double)), ("NK", C.POINTER(C.c_int)),
         ("gravity", C.c_double * 3), ("contact_dist_thresh", C.c_double), ("min_step_size", C.c_double),
+        ("min_step_size_env", C.POINTER(C.c_double)),
         ("impact_model", C.c_int), ("stabilization_max_iterations", C.c_int),
     ]
 
@@ -25,7 +26,7 @@ class SceneDesc(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(k, C.c_longlong) for k in (
         "env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
-        "impact_tol_events", "contacts", "max_lcp_n", "pivot_flops", "assembly_flops")]
+        "impact_tol_events", "contacts", "max_lcp_n", "pivot_flops", "ca_iterations", "assembly_flops")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -15,7 +15,7 @@ namespace b2m {
 
 enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3 };
 enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LEMKE_CALLS, CNT_PIVOTS, CNT_LCP_FAIL,
-       CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_COUNT };
+       CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_CA_ITERS, CNT_COUNT };
 #define B2M_NKMAX 64
 
 struct V3 {
@@ -43,6 +43,7 @@ struct SimParams {
   const double* mu_c; const double* mu_v; const double* eps; const double* compliance; const int* NK;
   const double* fr_tab;        // [4][B2M_NKMAX+1][B2M_NKMAX/2]: QP cos, QP sin, AP cos, AP sin (host libm values)
   double gx, gy, gz, contact_dist_thresh, min_step_size;
+  const double* min_step_env;   // optional [env]
   double* q; double* v; double* time; double* zlast; int* zlast_n;
   unsigned long long* counters;
   // debug taps (may be null)
@@ -416,20 +417,22 @@ B2M_DEV void fwd_dyn_integrate_velocity(const G& g, const SimParams& P, EnvMem& 
 
 // position half of the semi-implicit Euler step with conservative advancement (TimeSteppingSimulator.cpp:119-168)
 template <class G>
-B2M_DEV double integrate_positions_CA(const G& g, const SimParams& P, EnvMem& m, double dt) {
+B2M_DEV double integrate_positions_CA(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
   const int nb = P.nb;
   for (int k = g.tid; k < 3 * nb; k += G::size) m.xsave[k] = m.bx[k];
   for (int k = g.tid; k < 4 * nb; k += G::size) m.qsave[k] = m.bq[k];
   g.sync();
   double h = 0.0;
+  const double min_step = P.min_step_env ? P.min_step_env[e] : P.min_step_size;
   while (h < dt) {
+    if (g.tid == 0) lc[CNT_CA_ITERS]++;
     calc_pairwise_distances(g, m);
     const int np = m.scal[S_NPAIRS];
     double CA = B2M_INF;
     for (int p = g.tid; p < np; p += G::size) CA = fmin(CA, pair_CA(m, p));
     CA = g.min(CA);
     if (CA <= 0.0) break;
-    double tc = fmax(P.min_step_size, CA);
+    double tc = fmax(min_step, CA);
     tc = fmin(dt - h, tc);
     g.sync();
     for (int b = g.tid; b < nb; b += G::size) {
@@ -969,7 +972,7 @@ B2M_DEV void process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
 // TimeSteppingSimulator::do_mini_step (:114-222); returns h
 template <class G>
 B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
-  const double h = integrate_positions_CA(g, P, m, dt);
+  const double h = integrate_positions_CA(g, P, e, m, dt, lc);
   fwd_dyn_integrate_velocity(g, P, m, h);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);

@@ -149,17 +149,13 @@ b200moby_status plan_launch(b200moby_sim* h, const void* kernel) {
   const size_t MAXS = 227 * 1024;
   if (per_warp > MAXS)
     return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "env working set (%zu bytes, LCP n <= %d) exceeds one SM's shared memory; the block-per-env path is not built yet", per_warp, h->nmax);
-  // several small blocks per SM beat one wide block here: warps diverge in trip count, and a block retires only when its slowest warp does
-  int wpb = (int)std::min<size_t>(4, MAXS / per_warp);
-  while (wpb > 1 && (size_t)(wpb - 1) * sms >= (size_t)h->n_envs) wpb--;
-  h->wpb = wpb;
-  h->shmem = per_warp * wpb;
+  // One env per 32-thread block: envs differ wildly in work (conservative-advancement sub-steps, solver retries), so
+  // the hardware block scheduler doing the load balancing beats any static env->warp assignment; shared memory,
+  // not threads, limits residency (227 KB / per-env working set blocks per SM).
+  h->wpb = 1;
+  h->shmem = per_warp;
   B2M_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
-  int per_sm = 1;
-  B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, h->shmem));
-  if (per_sm < 1) per_sm = 1;
-  const int need = (h->n_envs + wpb - 1) / wpb;
-  h->grid = std::max(1, std::min(need, sms * per_sm));
+  h->grid = h->n_envs;
   return B200MOBY_OK;
 }
 
@@ -213,6 +209,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_copy(h, tab.data(), tab.size(), &P.fr_tab));
   P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
   P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size;
+  if (d->min_step_size_env) TRY(dev_copy(h, d->min_step_size_env, (size_t)ne, &P.min_step_env));
   TRY(dev_zero(h, (size_t)nb * 7 * ne, &P.q));
   TRY(dev_zero(h, (size_t)nb * 6 * ne, &P.v));
   TRY(dev_zero(h, (size_t)ne, &P.time));
@@ -280,7 +277,7 @@ b200moby_status b200moby_get_counters(b200moby_handle h, b200moby_counters* out)
   out->env_steps = c[CNT_ENV_STEPS]; out->mini_steps = c[CNT_MINI_STEPS]; out->lcp_solves = c[CNT_LCP_SOLVES];
   out->lcp_fast_calls = c[CNT_FAST_CALLS]; out->lemke_calls = c[CNT_LEMKE_CALLS]; out->pivots = c[CNT_PIVOTS];
   out->lcp_failures = c[CNT_LCP_FAIL] + c[CNT_OVERFLOW]; out->impact_tol_events = c[CNT_IMPACT_TOL]; out->contacts = c[CNT_CONTACTS];
-  out->max_lcp_n = c[CNT_MAX_N]; out->pivot_flops = c[CNT_PIVOT_FLOPS]; out->assembly_flops = c[CNT_ASM_FLOPS];
+  out->max_lcp_n = c[CNT_MAX_N]; out->pivot_flops = c[CNT_PIVOT_FLOPS]; out->assembly_flops = c[CNT_ASM_FLOPS]; out->ca_iterations = c[CNT_CA_ITERS];
   return B200MOBY_OK;
 }
 b200moby_status b200moby_reset_counters(b200moby_handle h) {

@@ -42,6 +42,7 @@ class SceneBatch:
         self.gravity = (0.0, -9.81, 0.0)
         self.contact_dist_thresh = 1e-6      # ConstraintSimulator.cpp:56
         self.min_step_size = NEAR_ZERO       # TimeSteppingSimulator.cpp:48
+        self.min_step_size_env = None        # optional per-env override, [env]
         self.impact_model = MODEL_QP
         self.q = np.zeros((nb, 7, ne), np.float64)
         self.q[:, 6, :] = 1.0
@@ -97,6 +98,10 @@ class SceneBatch:
         d.gravity = (C.c_double * 3)(*self.gravity)
         d.contact_dist_thresh, d.min_step_size = self.contact_dist_thresh, self.min_step_size
         d.impact_model, d.stabilization_max_iterations = self.impact_model, 0
+        if self.min_step_size_env is not None:
+            a = np.ascontiguousarray(self.min_step_size_env, np.float64)
+            keep.append(a)
+            d.min_step_size_env = a.ctypes.data_as(C.POINTER(C.c_double))
         d._keep = keep
         return d
 
@@ -181,6 +186,9 @@ def small_lcp_batch(n_envs, seed=0xB200, NK_box=8):
     vel = rng.uniform(-1, 1, (6, ne))
     for k in range(6):
         s.v[0, k, :] = np.where(isbox, vel[k], 10.0 if k == 4 else 0.0)
+    # simulator attributes of the two source scenes: test/box.xml sets min-step-size="1e-3" (the TestDie scene),
+    # bouncing-ball.xml keeps the default sqrt(eps) (TimeSteppingSimulator.cpp:48,470-472)
+    s.min_step_size_env = np.where(isbox, 1e-3, NEAR_ZERO)
     return s
 
 

@@ -88,7 +88,7 @@ static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
     }
   S.gravity = V3(d->gravity[0], d->gravity[1], d->gravity[2]);
   S.contact_dist_thresh = d->contact_dist_thresh;
-  S.min_step_size = d->min_step_size;
+  S.min_step_size = d->min_step_size_env ? d->min_step_size_env[e] : d->min_step_size;
   S.model = d->impact_model;
 }
 
@@ -133,7 +133,7 @@ void oracle_sim_counters(void* h, b200moby_counters* c) {
   const Counters& k = ((OracleSim*)h)->sim.cnt;
   c->env_steps = k.env_steps; c->mini_steps = k.mini_steps; c->lcp_solves = k.lcp_solves; c->lcp_fast_calls = k.lcp_fast_calls;
   c->lemke_calls = k.lemke_calls; c->pivots = k.pivots; c->lcp_failures = k.lcp_failures; c->impact_tol_events = k.impact_tol_events;
-  c->contacts = k.contacts; c->max_lcp_n = k.max_lcp_n; c->pivot_flops = k.pivot_flops; c->assembly_flops = 0;
+  c->contacts = k.contacts; c->max_lcp_n = k.max_lcp_n; c->pivot_flops = k.pivot_flops; c->assembly_flops = 0; c->ca_iterations = k.ca_iterations;
 }
 // LCP of the most recent impact solve: returns n; copies min(n*n, cap) etc.
 int oracle_sim_last_lcp(void* h, double* MM, double* qq, double* z, int ncap) {
@@ -192,7 +192,7 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
       Counters& c = cs[t]; const Counters& k = S.cnt;
       c.env_steps += k.env_steps; c.mini_steps += k.mini_steps; c.lcp_solves += k.lcp_solves; c.lcp_fast_calls += k.lcp_fast_calls;
       c.lemke_calls += k.lemke_calls; c.pivots += k.pivots; c.lcp_failures += k.lcp_failures; c.impact_tol_events += k.impact_tol_events;
-      c.contacts += k.contacts; c.max_lcp_n = std::max(c.max_lcp_n, k.max_lcp_n); c.pivot_flops += k.pivot_flops;
+      c.contacts += k.contacts; c.max_lcp_n = std::max(c.max_lcp_n, k.max_lcp_n); c.pivot_flops += k.pivot_flops; c.ca_iterations += k.ca_iterations;
     }
   };
   if (threads == 1) work(0);
@@ -202,7 +202,7 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
     for (auto& c : cs) {
       total->env_steps += c.env_steps; total->mini_steps += c.mini_steps; total->lcp_solves += c.lcp_solves; total->lcp_fast_calls += c.lcp_fast_calls;
       total->lemke_calls += c.lemke_calls; total->pivots += c.pivots; total->lcp_failures += c.lcp_failures; total->impact_tol_events += c.impact_tol_events;
-      total->contacts += c.contacts; total->max_lcp_n = std::max(total->max_lcp_n, c.max_lcp_n); total->pivot_flops += c.pivot_flops;
+      total->contacts += c.contacts; total->max_lcp_n = std::max(total->max_lcp_n, c.max_lcp_n); total->pivot_flops += c.pivot_flops; total->ca_iterations += c.ca_iterations;
     }
   }
 }
@@ -238,7 +238,7 @@ void oracle_batch_run(void* h, double dt, int n_steps, int threads, b200moby_cou
       const Counters& k = S.cnt;
       total->env_steps += k.env_steps; total->mini_steps += k.mini_steps; total->lcp_solves += k.lcp_solves; total->lcp_fast_calls += k.lcp_fast_calls;
       total->lemke_calls += k.lemke_calls; total->pivots += k.pivots; total->lcp_failures += k.lcp_failures; total->impact_tol_events += k.impact_tol_events;
-      total->contacts += k.contacts; total->max_lcp_n = std::max(total->max_lcp_n, k.max_lcp_n); total->pivot_flops += k.pivot_flops;
+      total->contacts += k.contacts; total->max_lcp_n = std::max(total->max_lcp_n, k.max_lcp_n); total->pivot_flops += k.pivot_flops; total->ca_iterations += k.ca_iterations;
     }
   }
 }

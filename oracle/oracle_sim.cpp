@@ -376,6 +376,7 @@ double Sim::do_mini_step(double dt) {
   std::vector<std::pair<int, int> > pairs;
   std::vector<PairDist> pd;
   while (h < dt) {                                                   // :133-168
+    cnt.ca_iterations++;
     broad_phase(pairs);
     calc_pairwise_distances(pairs, pd);
     double CA_step = INF;                                            // :272-331 (no joints here)

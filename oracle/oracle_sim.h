@@ -68,7 +68,7 @@ struct PairDist {
 
 struct Counters {
   long long env_steps = 0, mini_steps = 0, lcp_solves = 0, lcp_fast_calls = 0, lemke_calls = 0, pivots = 0,
-            lcp_failures = 0, impact_tol_events = 0, contacts = 0, max_lcp_n = 0, pivot_flops = 0;
+            lcp_failures = 0, impact_tol_events = 0, contacts = 0, max_lcp_n = 0, pivot_flops = 0, ca_iterations = 0;
 };
 
 struct Sim {

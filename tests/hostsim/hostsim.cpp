@@ -34,7 +34,7 @@ int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time
   P.shape = d->shape; P.enabled = d->enabled; P.mass = d->mass; P.dims = d->dims; P.inertia = d->inertia;
   P.mu_c = d->mu_coulomb; P.mu_v = d->mu_viscous; P.eps = d->epsilon; P.compliance = d->compliance; P.NK = d->NK;
   P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
-  P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size;
+  P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
   P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
   P.tap_MM = tapMM; P.tap_qq = tapqq; P.tap_z = tapz; P.tap_n = tapn;
   std::vector<double> wd(env_doubles(nb, cmax, nmax, npmax));

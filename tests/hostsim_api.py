@@ -10,7 +10,7 @@ from moby_b200.capi import SceneDesc
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 CNT = ("env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
-       "impact_tol_events", "contacts", "max_lcp_n", "overflow", "pivot_flops", "assembly_flops")
+       "impact_tol_events", "contacts", "max_lcp_n", "overflow", "pivot_flops", "assembly_flops", "ca_iterations")
 _lib = None
 
 
