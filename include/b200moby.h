@@ -131,6 +131,10 @@ b200moby_status b200moby_set_state_dev(b200moby_handle h, const double* q_dev, c
 b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q_dev, double* v_dev, void* stream);
 /* n_steps x step(dt) for every env; asynchronous on `stream`. */
 b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* stream);
+/* Scheduling knob (results do not depend on it): an env whose LCP pivots within one b200moby_step call exceed
+ * `budget` leaves the warp-per-env kernel untouched and is re-run by the block-per-env kernel (same arithmetic, 4x the
+ * lanes per pivot), so one hard solve cannot hold a whole step.  <= 0 disables; default 96 (env B200MOBY_PIVOT_BUDGET). */
+b200moby_status b200moby_set_pivot_budget(b200moby_handle h, int budget);
 b200moby_status b200moby_get_counters(b200moby_handle h, b200moby_counters* out);
 b200moby_status b200moby_reset_counters(b200moby_handle h);
 /* Simulated time per env, [env] host buffer (Simulator::current_time). */

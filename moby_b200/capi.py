@@ -36,7 +36,7 @@ class Counters(C.Structure):
 SYMBOLS = [
     "b200moby_last_error", "b200moby_abi_version", "b200moby_device_count",
     "b200moby_create", "b200moby_destroy", "b200moby_set_state", "b200moby_get_state",
-    "b200moby_set_state_dev", "b200moby_get_state_dev", "b200moby_step", "b200moby_get_counters",
+    "b200moby_set_state_dev", "b200moby_get_state_dev", "b200moby_step", "b200moby_set_pivot_budget", "b200moby_get_counters",
     "b200moby_reset_counters", "b200moby_get_time", "b200moby_get_last_lcp",
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
     "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host",
@@ -64,6 +64,7 @@ def lib():
     L.b200moby_set_state_dev.argtypes = [C.c_void_p, dp, dp, vp]
     L.b200moby_get_state_dev.argtypes = [C.c_void_p, dp, dp, vp]
     L.b200moby_step.argtypes = [C.c_void_p, C.c_double, C.c_int, vp]
+    L.b200moby_set_pivot_budget.argtypes = [C.c_void_p, C.c_int]
     L.b200moby_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     L.b200moby_reset_counters.argtypes = [C.c_void_p]
     L.b200moby_get_time.argtypes = [C.c_void_p, dp]

@@ -14,7 +14,7 @@ namespace b2m {
 
 enum {
   LCP_OK = 0, LCP_TRIVIAL = 1, LCP_RAY = 2, LCP_MAXITER = 3, LCP_SINGULAR = 4, LCP_EMPTY_RATIO = 5,
-  LCP_UNVERIFIED = 6, LCP_REGULARIZED = 16
+  LCP_UNVERIFIED = 6, LCP_DEFER = 7, LCP_REGULARIZED = 16
 };
 
 // element (r,c) of M + lambda I
@@ -57,7 +57,7 @@ B2M_HD inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
 template <class G>
 B2M_DEV int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
-                           int* log, int log_cap, int* log_len) {
+                           int* log, int log_cap, int* log_len, int* budget = nullptr) {
   double* T = wd;
   double* dvec = T + (size_t)n * (n + 2);
   double* rvec = dvec + n;
@@ -133,14 +133,17 @@ B2M_DEV int lemke_solve(const G& g, int n, const double* M, int ldm, const doubl
     // rank-one update of the whole tableau (x included)
     {
       int i = g.tid % n, c = g.tid / n;
+      const int di = G::size % n, dc = G::size / n;
       const int total = n * (n + 2);
       for (int e = g.tid; e < total; e += G::size) {
         T[e] = (i == r) ? rvec[c] : fma(-dvec[i], rvec[c], T[e]);
-        i += G::size; while (i >= n) { i -= n; c++; }
+        i += di; c += dc;
+        if (i >= n) { i -= n; c++; }
       }
     }
     g.sync();
     if (!first) piv++;
+    if (budget && --(*budget) < 0) { status = LCP_DEFER; break; }
     first = false;
     if (leaving == t) break;                                               // :800-822 solved
     if (piv >= MAXITER) { status = LCP_MAXITER; break; }                   // :789
@@ -204,7 +207,7 @@ B2M_DEV inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while
 template <class G>
 B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
                               bool warm, double* z, double* wd, int* wi, int* pivots_out, int* log, int log_cap,
-                              int* log_len) {
+                              int* log_len, int* budget = nullptr) {
   double* A = wd;
   double* zz = A + (size_t)n * n;
   double* w = zz + n;
@@ -235,6 +238,7 @@ B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const do
   const int MAX_PIV = 2 * n;                                                         // :107
   int piv = 0, status = LCP_MAXITER;
   for (piv = 0; piv < MAX_PIV; piv++) {
+    if (budget && --(*budget) < 0) { status = LCP_DEFER; break; }
     const int k = cnt[0], nb = cnt[1];
     for (int e = g.tid; e < k * k; e += G::size) { const int c = e / k, r = e - c * k; A[e] = m_at(M, ldm, nonbas[r], nonbas[c], lambda); }   // :111
     for (int i = g.tid; i < k; i += G::size) zz[i] = -q[nonbas[i]];                  // :113-115
@@ -369,12 +373,13 @@ B2M_DEV inline double pow10i(int e) {
 template <class G>
 B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, const double* q, double zero_tol, bool warm,
                                     int min_exp, int step_exp, int max_exp, double* z, double* wd, int* wi,
-                                    int* pivots_out, long long* stats) {
+                                    int* pivots_out, long long* stats, int* budget = nullptr) {
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
   const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :228
   double* wv = wd + (size_t)n * n + n;   // the solver's w vector doubles as verification scratch
   int total = 0, piv = 0;
-  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr);
+  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
+  if (st == LCP_DEFER) return st;
   bool zvalid = warm || st == LCP_OK || st == LCP_TRIVIAL;   // z.size()==n in the reference (LCP.cpp:65): warm start of the retries
   total += piv;
   if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
@@ -386,7 +391,8 @@ B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, co
   for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :281-340
     const double lambda = pow10i(rf);
     g.sync();
-    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr);
+    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
+    if (st == LCP_DEFER) return st;
     zvalid = zvalid || st == LCP_OK || st == LCP_TRIVIAL;
     total += piv;
     if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
@@ -403,12 +409,13 @@ B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, co
 template <class G>
 B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, const double* q, double piv_tol,
                                      double zero_tol, int min_exp, int step_exp, int max_exp, double* z, double* wd,
-                                     int* wi, int* pivots_out, long long* stats) {
+                                     int* wi, int* pivots_out, long long* stats, int* budget = nullptr) {
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
   const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :369
   double* wv = wd + (size_t)n * (n + 2);   // dvec doubles as verification scratch
   int total = 0, piv = 0;
-  int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr);
+  int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
+  if (st == LCP_DEFER) return st;
   total += piv;
   if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
   if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, wv)) {
@@ -419,7 +426,8 @@ B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, c
   for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :419-477
     const double lambda = pow10i(rf);
     g.sync();
-    st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr);
+    st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
+    if (st == LCP_DEFER) return st;
     total += piv;
     if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
     if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, lambda, z, ZERO_TOL, true, wv)) {

@@ -46,6 +46,8 @@ struct SimParams {
   const double* min_step_env;   // optional [env]
   double* q; double* v; double* time; double* zlast; int* zlast_n;
   unsigned long long* counters;
+  int pivot_budget;            // > 0: per-env pivot budget of the warp kernel; over-budget envs go to defer_list
+  int* defer_list; int* defer_count;
   // debug taps (may be null)
   double* tap_MM; double* tap_qq; double* tap_z; int* tap_n;
 };
@@ -57,7 +59,7 @@ struct EnvMem {
   double *pd_dist, *pd_pa, *pd_pb;
   double *cp, *cnrm, *ct1, *ct2, *cdist, *cmu, *cmuv, *ceps, *ccomp;
   double *Jr, *XJ, *Xb, *D, *Cv, *imp, *acc, *dv;
-  double *MM, *qq, *z, *work;
+  double *MM, *qq, *z, *zl, *work;
   // ints
   int *bshape, *ben, *pair_a, *pair_b, *cb1, *cb2, *cNK, *icon, *cisl, *corder, *isl_start, *gcoff, *bisl, *frow_c, *frow_j, *scal, *iwork;
 };
@@ -65,7 +67,7 @@ struct EnvMem {
 B2M_HD inline size_t env_doubles(int nb, int cmax, int nmax, int npmax) {
   size_t lw = lemke_work_doubles(nmax), fw = fast_work_doubles(nmax);
   return (size_t)38 * nb + 7 * (size_t)npmax + 17 * (size_t)cmax + 72 * (size_t)cmax + 36 * (size_t)nb + 6 * (size_t)cmax * cmax +
-         9 * (size_t)cmax + 6 * (size_t)nb + (size_t)nmax * nmax + 2 * (size_t)nmax + (lw > fw ? lw : fw);
+         9 * (size_t)cmax + 6 * (size_t)nb + (size_t)nmax * nmax + 3 * (size_t)nmax + (lw > fw ? lw : fw);
 }
 B2M_HD inline size_t env_ints(int nb, int cmax, int nmax, int npmax) {
   size_t lw = lemke_work_ints(nmax), fw = fast_work_ints(nmax);
@@ -80,7 +82,7 @@ B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, int nb, int cmax, int
   m.cdist = d; d += cmax; m.cmu = d; d += cmax; m.cmuv = d; d += cmax; m.ceps = d; d += cmax; m.ccomp = d; d += cmax;
   m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.D = d; d += 6 * (size_t)cmax * cmax;
   m.Cv = d; d += 3 * cmax; m.imp = d; d += 3 * cmax; m.acc = d; d += 3 * cmax; m.dv = d; d += 6 * nb;
-  m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.work = d;
+  m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.zl = d; d += nmax; m.work = d;
   m.bshape = i; i += nb; m.ben = i; i += nb; m.gcoff = i; i += nb; m.bisl = i; i += nb;
   m.pair_a = i; i += npmax; m.pair_b = i; i += npmax;
   m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax; m.icon = i; i += cmax; m.cisl = i; i += cmax; m.corder = i; i += cmax;
@@ -89,7 +91,12 @@ B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, int nb, int cmax, int
 }
 
 // scal[] slots
-enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7 };
+enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8 };
+
+// Per-env solver budget: when `limit` is set and an env's pivots in this launch exceed it, the env's step is
+// abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
+// step with many more threads per pivot (same arithmetic, same results).  Keeps one hard LCP from holding a whole SM.
+struct EnvCtx { int budget; bool limit; };
 
 // ---------- geometry helpers (same formulas, same order as the CPU checker) ----------
 B2M_HD B2M_INL void quat_to_R(const double* qt, double* R) {
@@ -371,7 +378,11 @@ B2M_DEV void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
         m.pair_a[np] = i; m.pair_b[np] = j; np++;
       }
     m.scal[S_NPAIRS] = np;
+    m.scal[S_ZLN] = P.zlast_n[e];
   }
+  g.sync();
+  const int zn = m.scal[S_ZLN];                                 // ImpactConstraintHandler::_zlast, kept on chip for the whole launch
+  for (int i = g.tid; i < zn; i += G::size) m.zl[i] = P.zlast[(size_t)i * ne + e];
   g.sync();
 }
 
@@ -380,6 +391,9 @@ B2M_DEV void env_store(const G& g, const SimParams& P, int e, const EnvMem& m) {
   const int nb = P.nb, ne = P.n_envs;
   for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; if (m.ben[b]) { P.q[((size_t)b * 7 + c) * ne + e] = m.bx[k]; P.v[((size_t)b * 6 + c) * ne + e] = m.bvl[k]; P.v[((size_t)b * 6 + 3 + c) * ne + e] = m.bva[k]; } }
   for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; if (m.ben[b]) P.q[((size_t)b * 7 + 3 + c) * ne + e] = m.bq[k]; }
+  const int zn = m.scal[S_ZLN];
+  for (int i = g.tid; i < zn; i += G::size) P.zlast[(size_t)i * ne + e] = m.zl[i];
+  if (g.tid == 0) P.zlast_n[e] = zn;
 }
 
 template <class G>
@@ -770,24 +784,26 @@ B2M_DEV double min_constraint_velocity(const G& g, const EnvMem& m) {           
   return g.min(v);
 }
 
-// solve_qp_work (ImpactConstraintHandlerQP.cpp:94-263): fills imp = [cn | cs | ct]
+// solve_qp_work (ImpactConstraintHandlerQP.cpp:94-263): fills imp = [cn | cs | ct].  Returns false when the env is deferred.
 template <class G>
-B2M_DEV void solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+B2M_DEV bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int nc = m.scal[S_NC];
   const int n = build_qp_lcp(g, P, m);
-  if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * nc; t += G::size) m.imp[t] = 0.0; g.sync(); return; }
-  const int ne = P.n_envs;
-  const bool warm = (P.zlast_n[e] == n);                                            // :158-162 with rule H1 (zero fill)
-  for (int i = g.tid; i < n; i += G::size) m.z[i] = warm ? P.zlast[(size_t)i * ne + e] : 0.0;
+  if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * nc; t += G::size) m.imp[t] = 0.0; g.sync(); return true; }
+  const bool warm = (m.scal[S_ZLN] == n);                                           // :158-162 with rule H1 (zero fill)
+  for (int i = g.tid; i < n; i += G::size) m.z[i] = warm ? m.zl[i] : 0.0;
   g.sync();
   long long stats[2] = {0, 0};
   int piv = 0;
-  int st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats);   // :219
+  int* bud = cx.limit ? &cx.budget : nullptr;
+  int st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats, bud);   // :219
+  if (st == LCP_DEFER) return false;
   long long fast_calls = stats[0], pivots = stats[1], lemke_calls = 0;
   if (st == LCP_UNVERIFIED) {
     g.sync();
     stats[0] = stats[1] = 0;
-    st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats);      // :222-225
+    st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);      // :222-225
+    if (st == LCP_DEFER) return false;
     lemke_calls = stats[0]; pivots += stats[1];
     if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
   }
@@ -796,9 +812,9 @@ B2M_DEV void solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
     lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
     lc[CNT_PIVOT_FLOPS] += (unsigned long long)pivots * 2ull * n * (n + 1);
     if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
-    P.zlast_n[e] = n;
+    m.scal[S_ZLN] = n;
   }
-  for (int i = g.tid; i < n; i += G::size) P.zlast[(size_t)i * ne + e] = m.z[i];    // :233
+  for (int i = g.tid; i < n; i += G::size) m.zl[i] = m.z[i];                        // :233 _zlast = z
   if (P.tap_n) {
     if (g.tid == 0) P.tap_n[e] = n;
     for (int t = g.tid; t < n * n; t += G::size) P.tap_MM[(size_t)e * P.nmax * P.nmax + t] = m.MM[t];
@@ -810,13 +826,14 @@ B2M_DEV void solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
     m.imp[2 * nc + i] = m.z[2 * nc + i] - m.z[4 * nc + i];
   }
   g.sync();
+  return true;
 }
 
 // apply_model_to_connected_constraints (ImpactConstraintHandler.cpp:530-626)
 template <class G>
-B2M_DEV void apply_qp_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+B2M_DEV bool apply_qp_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int nc = m.scal[S_NC];
-  solve_qp(g, P, e, m, lc);
+  if (!solve_qp(g, P, e, m, lc, cx)) return false;
   apply_to_bodies(g, P, m, m.imp);
   update_constraint_velocities(g, m, m.imp);
   const double minv = min_constraint_velocity(g, m);
@@ -833,21 +850,23 @@ B2M_DEV void apply_qp_model(const G& g, const SimParams& P, int e, EnvMem& m, un
     update_constraint_velocities(g, m, m.imp);
     const double minv_plus = min_constraint_velocity(g, m);
     if (minv_plus < 0.0 && minv_plus < minv - B2M_NEAR_ZERO) {
-      solve_qp(g, P, e, m, lc);
+      if (!solve_qp(g, P, e, m, lc, cx)) return false;
       apply_to_bodies(g, P, m, m.imp);
     }
   }
+  return true;
 }
 
 // apply_ap_model (ImpactConstraintHandlerLCP.cpp:94-370): imp = this solve, acc += imp (propagate_impulse_data)
 template <class G>
-B2M_DEV void solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+B2M_DEV bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int NC = m.scal[S_NC];
   const int n = build_ap_lcp(g, P, m);
-  if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * NC; t += G::size) m.imp[t] = 0.0; g.sync(); return; }
+  if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * NC; t += G::size) m.imp[t] = 0.0; g.sync(); return true; }
   long long stats[2] = {0, 0};
   int piv = 0;
-  int st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, -2, m.z, m.work, m.iwork, &piv, stats);   // :333
+  int st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, -2, m.z, m.work, m.iwork, &piv, stats, cx.limit ? &cx.budget : nullptr);   // :333
+  if (st == LCP_DEFER) return false;
   if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
   g.sync();
   if (g.tid == 0) {
@@ -867,14 +886,15 @@ B2M_DEV void solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
     for (int d = 0; d < 3; d++) m.acc[d * NC + i] += m.imp[d * NC + i];
   }
   g.sync();
+  return true;
 }
 
 template <class G>
-B2M_DEV void apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {   // ImpactConstraintHandlerLCP.cpp:36-91
+B2M_DEV bool apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {   // ImpactConstraintHandlerLCP.cpp:36-91
   const int nc = m.scal[S_NC];
   for (int t = g.tid; t < 3 * nc; t += G::size) m.acc[t] = 0.0;
   g.sync();
-  solve_ap(g, P, e, m, lc);
+  if (!solve_ap(g, P, e, m, lc, cx)) return false;
   update_constraint_velocities(g, m, m.imp);
   const double minv = min_constraint_velocity(g, m);
   bool changed = false;                                           // apply_restitution(q) :497-524
@@ -890,20 +910,21 @@ B2M_DEV void apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, un
     g.sync();
     update_constraint_velocities(g, m, m.imp);
     const double minv_plus = min_constraint_velocity(g, m);
-    if (minv_plus < 0.0 && minv_plus < minv - B2M_NEAR_ZERO) solve_ap(g, P, e, m, lc);
+    if (minv_plus < 0.0 && minv_plus < minv - B2M_NEAR_ZERO) { if (!solve_ap(g, P, e, m, lc, cx)) return false; }
     else { for (int t = g.tid; t < 3 * nc; t += G::size) m.acc[t] += m.imp[t]; g.sync(); }
   }
   apply_to_bodies(g, P, m, m.acc);                                // apply_impulses (:676-748): accumulated contact impulses
+  return true;
 }
 
 // calc_impacting_unilateral_constraint_forces (ConstraintSimulator.cpp:298-355) -> apply_model (ImpactConstraintHandler.cpp:96-168)
 template <class G>
-B2M_DEV void process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int ncon = m.scal[S_NCON], nb = P.nb;
-  if (ncon == 0) return;
+  if (ncon == 0) return true;
   bool impacting = false;
   for (int c = g.tid; c < ncon; c += G::size) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) impacting = true;
-  if (!g.any(impacting)) return;
+  if (!g.any(impacting)) return true;
   // islands (UnilateralConstraint.cpp:940-1194) with the canonical order of rule H4: seeds in ascending body index,
   // neighbours in contact (edge insertion) order, each visited body picks up its remaining contacts in list order.
   if (g.tid == 0) {
@@ -960,23 +981,24 @@ B2M_DEV void process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
       for (unsigned i = 0; i < nc; i++) blocks += (m.ben[m.cb1[m.icon[i]]] ? 1 : 0) + (m.ben[m.cb2[m.icon[i]]] ? 1 : 0);
       lc[CNT_ASM_FLOPS] += 2 * 3 * 36 * blocks + 2 * (3 * nc) * (3 * nc) * 6 + 2 * ngc * 3 * nc;
     }
-    if (P.model == 1) apply_ap_model(g, P, e, m, lc); else apply_qp_model(g, P, e, m, lc);
+    if (!(P.model == 1 ? apply_ap_model(g, P, e, m, lc, cx) : apply_qp_model(g, P, e, m, lc, cx))) return false;
     g.sync();
   }
   // ImpactToleranceException check over the solved islands (:153-167): counted, never fatal
   bool still = false;
   for (int c = g.tid; c < ncon; c += G::size) if (((active >> m.cisl[c]) & 1u) && constraint_vel(m, c) < -B2M_NEAR_ZERO) still = true;
   if (g.any(still) && g.tid == 0) lc[CNT_IMPACT_TOL]++;
+  return true;
 }
 
-// TimeSteppingSimulator::do_mini_step (:114-222); returns h
+// TimeSteppingSimulator::do_mini_step (:114-222); returns h, or -1 when the env is deferred
 template <class G>
-B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
+B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc, EnvCtx& cx) {
   const double h = integrate_positions_CA(g, P, e, m, dt, lc);
   fwd_dyn_integrate_velocity(g, P, m, h);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
-  process_constraints(g, P, e, m, lc);
+  if (!process_constraints(g, P, e, m, lc, cx)) return -1.0;
   if (g.tid == 0) {     // F_fd = 60 per free body (Newton-Euler); F_narrow = 8 vertices x 20 (box) or 20 (sphere) per pair and distance pass
     lc[CNT_MINI_STEPS]++;
     unsigned long long f = 0;
@@ -987,20 +1009,26 @@ B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, do
   return h;
 }
 
-// n_steps x TimeSteppingSimulator::step (:52-111, :433-455) for env e; stabilization disabled
+// n_steps x TimeSteppingSimulator::step (:52-111, :433-455) for env e; stabilization disabled.
+// Returns false (and leaves the env's stored state untouched) when the env ran out of its pivot budget.
 template <class G>
-B2M_DEV void env_run(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int n_steps, unsigned long long* lc) {
+B2M_DEV bool env_run(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int n_steps, unsigned long long* lc, EnvCtx& cx) {
   env_load(g, P, e, m);
   double t = P.time[e];
   for (int s = 0; s < n_steps; s++) {
     double h = 0.0;
-    while (h < dt) { const double hh = do_mini_step(g, P, e, m, dt - h, lc); h += hh; t += hh; }
+    while (h < dt) {
+      const double hh = do_mini_step(g, P, e, m, dt - h, lc, cx);
+      if (hh < 0.0) return false;
+      h += hh; t += hh;
+    }
     if (g.tid == 0) lc[CNT_ENV_STEPS]++;
   }
   g.sync();
   env_store(g, P, e, m);
   if (g.tid == 0) P.time[e] = t;
   g.sync();
+  return true;
 }
 
 }  // namespace b2m

@@ -3,6 +3,7 @@
 // independent envs: one warp per env, the whole mini-step loop (narrowphase, conservative advancement, forward
 // dynamics, assembly, LCP solve, impulses) runs out of shared memory; HBM sees the state and the warm start only.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "friction_table.h"
@@ -17,29 +18,57 @@ struct b200moby_sim {
   SimParams P;
   std::vector<void*> allocs;
   size_t env_d = 0, env_i = 0;
-  int wpb = 1, grid = 1;
+  int wpb = 1, grid = 1, sms = 148;
   size_t shmem = 0;
   bool taps = false;
 };
 
 namespace {
 
-__global__ void __launch_bounds__(128, 1) step_warp_kernel(SimParams P, double dt, int n_steps, int wpb, size_t env_d, size_t env_i) {
+__device__ void commit_counters(const SimParams& P, const unsigned long long* lc) {
+  for (int k = 0; k < CNT_COUNT; k++) {
+    if (k == CNT_MAX_N) atomicMax(P.counters + k, lc[k]);
+    else if (lc[k]) atomicAdd(P.counters + k, lc[k]);
+  }
+}
+
+// One env per warp-sized block.  Envs whose solver work exceeds the pivot budget are queued for step_block_kernel.
+__global__ void __launch_bounds__(32) step_warp_kernel(SimParams P, double dt, int n_steps, size_t env_d) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int w = threadIdx.x >> 5;
-  double* sd = (double*)smem + (size_t)w * env_d;
-  int* si = (int*)((double*)smem + (size_t)wpb * env_d) + (size_t)w * env_i;
   EnvMem m;
-  env_carve(m, sd, si, P.nb, P.cmax, P.nmax, P.npmax);
+  env_carve(m, (double*)smem, (int*)((double*)smem + env_d), P.nb, P.cmax, P.nmax, P.npmax);
   WarpGroup g(nullptr);
   unsigned long long lc[CNT_COUNT];
-  for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
-  for (int e = blockIdx.x * wpb + w; e < P.n_envs; e += gridDim.x * wpb) env_run(g, P, e, m, dt, n_steps, lc);
-  if (g.tid == 0) {
-    for (int k = 0; k < CNT_COUNT; k++) {
-      if (k == CNT_MAX_N) atomicMax(P.counters + k, lc[k]);
-      else if (lc[k]) atomicAdd(P.counters + k, lc[k]);
+  for (int e = blockIdx.x; e < P.n_envs; e += gridDim.x) {
+    for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
+    EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
+    const bool done = env_run(g, P, e, m, dt, n_steps, lc, cx);
+    if (g.tid == 0) {
+      if (done) commit_counters(P, lc);
+      else P.defer_list[atomicAdd(P.defer_count, 1)] = e;
     }
+    g.sync();
+  }
+}
+
+// The deferred envs again, from their untouched stored state, with a whole 128-thread block per env: the same code and
+// arithmetic (reductions are order-independent), four times the lanes on every pivot.
+#define B2M_BLOCK_THREADS 128
+__global__ void __launch_bounds__(B2M_BLOCK_THREADS) step_block_kernel(SimParams P, double dt, int n_steps, size_t env_d) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red[4 * (B2M_BLOCK_THREADS / 32) + 4];
+  EnvMem m;
+  env_carve(m, (double*)smem, (int*)((double*)smem + env_d), P.nb, P.cmax, P.nmax, P.npmax);
+  BlockGroup<B2M_BLOCK_THREADS> g(red);
+  unsigned long long lc[CNT_COUNT];
+  const int count = *P.defer_count;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int e = P.defer_list[i];
+    for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
+    EnvCtx cx; cx.limit = false; cx.budget = 0;
+    env_run(g, P, e, m, dt, n_steps, lc, cx);
+    if (g.tid == 0) commit_counters(P, lc);
+    g.sync();
   }
 }
 
@@ -155,7 +184,9 @@ b200moby_status plan_launch(b200moby_sim* h, const void* kernel) {
   h->wpb = 1;
   h->shmem = per_warp;
   B2M_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
+  B2M_CUDA(cudaFuncSetAttribute(step_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
   h->grid = h->n_envs;
+  h->sms = sms;
   return B200MOBY_OK;
 }
 
@@ -216,6 +247,10 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)h->nmax * ne, &P.zlast));
   TRY(dev_zero(h, (size_t)ne, &P.zlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
+  TRY(dev_zero(h, (size_t)ne, &P.defer_list));
+  TRY(dev_zero(h, (size_t)1, &P.defer_count));
+  P.pivot_budget = 96;
+  if (const char* s = getenv("B200MOBY_PIVOT_BUDGET")) P.pivot_budget = atoi(s);
   TRY(plan_launch(h, (const void*)step_warp_kernel));
 #undef TRY
   *out = h;
@@ -264,8 +299,20 @@ b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q, double* v, 
 b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* stream) {
   if (!h || !(dt > 0.0) || n_steps < 0) return b2m_fail(B200MOBY_ERR_INVALID, "bad step arguments");
   if (n_steps == 0) return B200MOBY_OK;
-  step_warp_kernel<<<h->grid, h->wpb * 32, h->shmem, (cudaStream_t)stream>>>(h->P, dt, n_steps, h->wpb, h->env_d, h->env_i);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->P.pivot_budget > 0) B2M_CUDA(cudaMemsetAsync(h->P.defer_count, 0, sizeof(int), s));
+  step_warp_kernel<<<h->grid, 32, h->shmem, s>>>(h->P, dt, n_steps, h->env_d);
   B2M_CUDA(cudaGetLastError());
+  if (h->P.pivot_budget > 0) {
+    step_block_kernel<<<h->sms * 2, B2M_BLOCK_THREADS, h->shmem, s>>>(h->P, dt, n_steps, h->env_d);
+    B2M_CUDA(cudaGetLastError());
+  }
+  return B200MOBY_OK;
+}
+
+b200moby_status b200moby_set_pivot_budget(b200moby_handle h, int budget) {
+  if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
+  h->P.pivot_budget = budget;
   return B200MOBY_OK;
 }
 

@@ -69,6 +69,10 @@ class TimeSteppingSimulator:
         capi.check(capi.lib().b200moby_get_counters(self._h, C.byref(c)))
         return c.as_dict()
 
+    def set_pivot_budget(self, budget):
+        """Scheduling knob only (results are identical): see b200moby_set_pivot_budget."""
+        capi.check(capi.lib().b200moby_set_pivot_budget(self._h, int(budget)))
+
     def reset_counters(self):
         capi.check(capi.lib().b200moby_reset_counters(self._h))
 

@@ -42,7 +42,8 @@ int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time
   EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
   SerialGroup g(nullptr);
   unsigned long long lc[CNT_COUNT]; memset(lc, 0, sizeof(lc));
-  for (int e = e0; e < e1; e++) env_run(g, P, e, m, dt, n_steps, lc);
+  EnvCtx cx; cx.limit = false; cx.budget = 0;
+  for (int e = e0; e < e1; e++) env_run(g, P, e, m, dt, n_steps, lc, cx);
   for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) counters[k] = std::max(counters[k], lc[k]); else counters[k] += lc[k]; }
   return nmax;
 }

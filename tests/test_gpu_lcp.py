@@ -144,8 +144,10 @@ def test_host_forms_and_block_path(torch_cuda, oracle):
         assert ok and st[b] in (0, 1) and np.allclose(z[b], zo, rtol=0, atol=1e-8)
     z, st, piv = lcp_fast_host(M, q)
     for b in range(4):
-        ok, zo, info = oracle.lcp_fast(M[b], q[b])
-        assert ok and st[b] in (0, 1) and np.array_equal(z[b], zo)
+        ok, zo, info = oracle.lcp_fast(M[b], q[b])       # lcp_fast may hit its 2n cap on a cold start: then both must
+        assert ok == (st[b] in (0, 1)) and st[b] == info["status"] and piv[b] == info["pivots"]
+        if ok:
+            assert np.array_equal(z[b], zo)
 
 
 def test_empty_and_ragged(torch_cuda):
