@@ -137,6 +137,8 @@ b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* s
 b200moby_status b200moby_set_pivot_budget(b200moby_handle h, int budget);
 b200moby_status b200moby_get_counters(b200moby_handle h, b200moby_counters* out);
 b200moby_status b200moby_reset_counters(b200moby_handle h);
+/* Kernel launches issued through this handle so far (what bench.py reports as gpu_launches). */
+b200moby_status b200moby_get_launch_count(b200moby_handle h, long long* out);
 /* Simulated time per env, [env] host buffer (Simulator::current_time). */
 b200moby_status b200moby_get_time(b200moby_handle h, double* t);
 /* Debug tap: LCP of the last impact solve of each env. MM_dev: [env][nmax*nmax] column-major with
@@ -169,6 +171,13 @@ b200moby_status b200moby_lcp_lemke_host(int batch, int n, const double* M, const
                                         double zero_tol, int* status, int* pivots, int device);
 b200moby_status b200moby_lcp_fast_host(int batch, int n, const double* M, const double* q, double* z, int warm_start,
                                        double zero_tol, int* status, int* pivots, int device);
+
+/* All four solvers behind one host-buffer entry point: mode 0 lcp_lemke, 1 lcp_fast, 2 lcp_lemke_regularized,
+ * 3 lcp_fast_regularized (min_exp/step_exp/max_exp used by modes 2 and 3 only).  This is what the C++ facade's
+ * Moby::LCP methods call (include/b200moby.hpp). */
+b200moby_status b200moby_lcp_solve_host(int mode, int batch, int n, const double* M, const double* q, double* z, int warm_start,
+                                        double piv_tol, double zero_tol, int min_exp, int step_exp, int max_exp, int* status,
+                                        int* pivots, int device);
 
 /* ---- stage kernels, exposed for parity tests and for callers that keep Moby's own step loop ---- */
 /* Forward dynamics + velocity half of semi-implicit Euler for free rigid bodies

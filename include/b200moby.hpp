@@ -1,0 +1,435 @@
+// b200moby.hpp -- C++ host facade over the C ABI (include/b200moby.h) with Moby's class and member names for the
+// time-stepping contact hot path, so a program or plugin written against Moby's TimeSteppingSimulator ports by
+// recompiling against this header and linking libb200moby.so.
+//
+// What is mirrored (Moby tree, file:line):
+//   Moby::TimeSteppingSimulator::step / current_time / min_step_size        include/Moby/TimeSteppingSimulator.h:27-52, Simulator.h:50,80
+//   Moby::ConstraintSimulator members contact_dist_thresh, contact_params,
+//     cstab.max_iterations, post_mini_step_callback_fn                       include/Moby/ConstraintSimulator.h:40-100
+//   Moby::Simulator::add_dynamic_body, post_step_callback_fn                 include/Moby/Simulator.h:44-80
+//   Moby::RigidBody (set_pose / get_pose / set_enabled / set_inertia /
+//     velocity accessors / geometries / get_recurrent_forces)                include/Moby/RigidBody.h:43-80 (+ Ravelin::RigidBodyd)
+//   Moby::BoxPrimitive / SpherePrimitive / PlanePrimitive (mass properties)  src/BoxPrimitive.cpp, SpherePrimitive.cpp, PlanePrimitive.cpp
+//   Moby::ContactParameters                                                  include/Moby/ContactParameters.h:15-50
+//   Moby::GravityForce                                                       src/GravityForce.cpp:32-68
+//   Moby::LCP::lcp_lemke / lcp_fast / *_regularized                          include/Moby/LCP.h:21-27
+// Ravelin's value types are replaced by the minimal stand-ins in namespace Ravelin below (define
+// B200MOBY_NO_RAVELIN_STANDINS when the real Ravelin headers are on the include path).
+//
+// Beyond the reference: a simulator can be replicated into a batch of independent instances ("envs") that step
+// together on the GPU -- replicate(n) -- with per-env state accessors; one env behaves exactly like the reference's
+// single simulator.  Everything here is host-side glue: all arithmetic happens in the CUDA kernels behind the C ABI
+// and every call fails loudly (std::runtime_error) when no sm_100 device is present.  There is no CPU fallback.
+#ifndef B200MOBY_HPP
+#define B200MOBY_HPP
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <list>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "b200moby.h"
+
+#ifndef B200MOBY_NO_RAVELIN_STANDINS
+namespace Ravelin {
+struct Origin3d {
+  double v[3];
+  Origin3d(double x = 0, double y = 0, double z = 0) : v{x, y, z} {}
+  double& operator[](unsigned i) { return v[i]; }
+  double operator[](unsigned i) const { return v[i]; }
+  double x() const { return v[0]; }
+  double y() const { return v[1]; }
+  double z() const { return v[2]; }
+};
+typedef Origin3d Vector3d;
+struct Quatd {
+  double x, y, z, w;
+  Quatd(double x_ = 0, double y_ = 0, double z_ = 0, double w_ = 1) : x(x_), y(y_), z(z_), w(w_) {}
+};
+struct Pose3d {
+  Quatd q;
+  Origin3d x;
+  Pose3d() {}
+  Pose3d(const Quatd& q_, const Origin3d& x_) : q(q_), x(x_) {}
+};
+// spatial velocity [linear; angular] at the body's COM, global-aligned frame
+struct SVelocityd {
+  Vector3d linear, angular;
+  const Vector3d& get_linear() const { return linear; }
+  const Vector3d& get_angular() const { return angular; }
+  void set_linear(const Vector3d& l) { linear = l; }
+  void set_angular(const Vector3d& a) { angular = a; }
+};
+struct SpatialRBInertiad {
+  double m = 1.0;
+  double J[3] = {1, 1, 1};     // principal moments, body frame
+};
+typedef std::vector<double> VectorNd;
+// dense column-major matrix
+class MatrixNd {
+ public:
+  MatrixNd() : r_(0), c_(0) {}
+  MatrixNd(unsigned r, unsigned c) : r_(r), c_(c), d_((size_t)r * c, 0.0) {}
+  void resize(unsigned r, unsigned c) { r_ = r; c_ = c; d_.assign((size_t)r * c, 0.0); }
+  unsigned rows() const { return r_; }
+  unsigned columns() const { return c_; }
+  double& operator()(unsigned i, unsigned j) { return d_[(size_t)j * r_ + i]; }
+  double operator()(unsigned i, unsigned j) const { return d_[(size_t)j * r_ + i]; }
+  const double* data() const { return d_.data(); }
+  double* data() { return d_.data(); }
+ private:
+  unsigned r_, c_;
+  std::vector<double> d_;
+};
+}  // namespace Ravelin
+#endif
+
+namespace Moby {
+
+inline void b200_check(b200moby_status st, const char* what) {
+  if (st != B200MOBY_OK) throw std::runtime_error(std::string(what) + ": " + b200moby_last_error());
+}
+
+class LCPSolverException : public std::runtime_error {
+ public:
+  LCPSolverException() : std::runtime_error("LCP solver failed") {}
+};
+
+// ---------------------------------------------------------------------------------------------- LCP (LCP.h:21-27)
+class LCP {
+ public:
+  LCP(int device = 0) : pivots(0), device_(device) {}
+  bool lcp_lemke(const Ravelin::MatrixNd& M, const Ravelin::VectorNd& q, Ravelin::VectorNd& z, double piv_tol = -1.0, double zero_tol = -1.0) {
+    return single(0, M, q, z, false, piv_tol, zero_tol, 0, 1, 0);
+  }
+  bool lcp_fast(const Ravelin::MatrixNd& M, const Ravelin::VectorNd& q, Ravelin::VectorNd& z, double zero_tol = -1.0) {
+    return single(1, M, q, z, z.size() == q.size(), -1.0, zero_tol, 0, 1, 0);          // z doubles as the warm start (LCP.cpp:65)
+  }
+  bool lcp_lemke_regularized(const Ravelin::MatrixNd& M, const Ravelin::VectorNd& q, Ravelin::VectorNd& z, int min_exp = -20,
+                             unsigned step_exp = 1, int max_exp = 1, double piv_tol = -1.0, double zero_tol = -1.0) {
+    return single(2, M, q, z, false, piv_tol, zero_tol, min_exp, (int)step_exp, max_exp);
+  }
+  bool lcp_fast_regularized(const Ravelin::MatrixNd& M, const Ravelin::VectorNd& q, Ravelin::VectorNd& z, int min_exp = -20,
+                            unsigned step_exp = 4, int max_exp = 20, double /*piv_tol*/ = -1.0, double zero_tol = -1.0) {
+    return single(3, M, q, z, z.size() == q.size(), -1.0, zero_tol, min_exp, (int)step_exp, max_exp);
+  }
+  // Batched form (beyond the reference): `batch` problems of dimension n, M column-major per problem, host buffers.
+  // status[b] holds the B200MOBY_LCP_* word of each problem.
+  void lcp_lemke_batch(int batch, int n, const double* M, const double* q, double* z, int* status, int* pivots_out = nullptr) {
+    b200_check(b200moby_lcp_lemke_host(batch, n, M, q, z, -1.0, -1.0, status, pivots_out, device_), "b200moby_lcp_lemke_host");
+  }
+  void lcp_fast_batch(int batch, int n, const double* M, const double* q, double* z, bool warm, int* status, int* pivots_out = nullptr) {
+    b200_check(b200moby_lcp_fast_host(batch, n, M, q, z, warm ? 1 : 0, -1.0, status, pivots_out, device_), "b200moby_lcp_fast_host");
+  }
+  unsigned pivots;
+
+ private:
+  bool single(int mode, const Ravelin::MatrixNd& M, const Ravelin::VectorNd& q, Ravelin::VectorNd& z, bool warm, double piv_tol,
+              double zero_tol, int min_exp, int step_exp, int max_exp) {
+    const int n = (int)q.size();
+    if ((int)M.rows() != n || (int)M.columns() != n) throw std::invalid_argument("LCP: M must be n x n");
+    if (!warm) z.assign(n, 0.0);
+    if (n == 0) return true;
+    int status = 0, piv = 0;
+    b200_check(b200moby_lcp_solve_host(mode, 1, n, M.data(), q.data(), z.data(), warm ? 1 : 0, piv_tol, zero_tol, min_exp, step_exp,
+                                       max_exp, &status, &piv, device_), "b200moby_lcp_solve_host");
+    pivots = (unsigned)piv;
+    return status == B200MOBY_LCP_OK || status == B200MOBY_LCP_TRIVIAL || status >= B200MOBY_LCP_REGULARIZED;
+  }
+  int device_;
+};
+
+// ---------------------------------------------------------------------------------------------- scene objects
+class Base {
+ public:
+  virtual ~Base() {}
+  std::string id;
+};
+typedef std::shared_ptr<Base> BasePtr;
+
+class Primitive : public Base {
+ public:
+  int shape = B200MOBY_SHAPE_NONE;
+  double dims[3] = {0, 0, 0};
+  void set_mass(double m) { mass_ = m; density_ = -1.0; }
+  void set_density(double d) { density_ = d; mass_ = -1.0; }
+  virtual double volume() const { return 0.0; }
+  double get_mass() const { return mass_ >= 0.0 ? mass_ : (density_ >= 0.0 ? density_ * volume() : 0.0); }
+  virtual Ravelin::SpatialRBInertiad get_inertia() const { Ravelin::SpatialRBInertiad J; J.m = get_mass(); return J; }
+ protected:
+  double mass_ = -1.0, density_ = -1.0;
+};
+typedef std::shared_ptr<Primitive> PrimitivePtr;
+
+class BoxPrimitive : public Primitive {           // BoxPrimitive::calc_mass_properties
+ public:
+  BoxPrimitive(double xlen = 1, double ylen = 1, double zlen = 1) { shape = B200MOBY_SHAPE_BOX; dims[0] = xlen; dims[1] = ylen; dims[2] = zlen; }
+  double volume() const override { return dims[0] * dims[1] * dims[2]; }
+  Ravelin::SpatialRBInertiad get_inertia() const override {
+    Ravelin::SpatialRBInertiad J; J.m = get_mass();
+    J.J[0] = J.m * (dims[1] * dims[1] + dims[2] * dims[2]) / 12.0;
+    J.J[1] = J.m * (dims[0] * dims[0] + dims[2] * dims[2]) / 12.0;
+    J.J[2] = J.m * (dims[0] * dims[0] + dims[1] * dims[1]) / 12.0;
+    return J;
+  }
+};
+class SpherePrimitive : public Primitive {        // SpherePrimitive::calc_mass_properties
+ public:
+  explicit SpherePrimitive(double radius = 1) { shape = B200MOBY_SHAPE_SPHERE; dims[0] = radius; }
+  double volume() const override { return (4.0 / 3.0) * M_PI * dims[0] * dims[0] * dims[0]; }
+  Ravelin::SpatialRBInertiad get_inertia() const override {
+    Ravelin::SpatialRBInertiad J; J.m = get_mass();
+    J.J[0] = J.J[1] = J.J[2] = 0.4 * J.m * dims[0] * dims[0];
+    return J;
+  }
+};
+class PlanePrimitive : public Primitive {         // half-space y <= 0 of the body frame (PlanePrimitive.cpp:342-411)
+ public:
+  PlanePrimitive() { shape = B200MOBY_SHAPE_PLANE; }
+};
+
+class CollisionGeometry : public Base {
+ public:
+  void set_geometry(PrimitivePtr p) { primitive_ = p; }
+  PrimitivePtr get_geometry() const { return primitive_; }
+ private:
+  PrimitivePtr primitive_;
+};
+typedef std::shared_ptr<CollisionGeometry> CollisionGeometryPtr;
+
+class RecurrentForce : public Base {};
+typedef std::shared_ptr<RecurrentForce> RecurrentForcePtr;
+class GravityForce : public RecurrentForce {
+ public:
+  Ravelin::Vector3d gravity;
+};
+
+class TimeSteppingSimulator;
+
+class RigidBody : public Base {
+ public:
+  std::list<CollisionGeometryPtr> geometries;
+  void set_enabled(bool e) { enabled_ = e; }
+  bool is_enabled() const { return enabled_; }
+  void set_inertia(const Ravelin::SpatialRBInertiad& J) { J_ = J; }
+  const Ravelin::SpatialRBInertiad& get_inertia() const { return J_; }
+  std::list<RecurrentForcePtr>& get_recurrent_forces() { return forces_; }
+  // pose / velocity of env 0 (of env e with the second argument); reads go to the device once the simulator runs
+  void set_pose(const Ravelin::Pose3d& p, int env = -1);
+  Ravelin::Pose3d get_pose(int env = 0) const;
+  void set_velocity(const Ravelin::SVelocityd& v, int env = -1);
+  Ravelin::SVelocityd get_velocity(int env = 0) const;
+
+ private:
+  friend class TimeSteppingSimulator;
+  bool enabled_ = true;
+  Ravelin::SpatialRBInertiad J_;
+  std::list<RecurrentForcePtr> forces_;
+  Ravelin::Pose3d pose0_;
+  Ravelin::SVelocityd vel0_;
+  TimeSteppingSimulator* sim_ = nullptr;
+  int index_ = -1;
+};
+typedef std::shared_ptr<RigidBody> RigidBodyPtr;
+typedef RigidBodyPtr ControlledBodyPtr;
+
+class ContactParameters : public Base {           // defaults: ContactParameters.cpp:21-28
+ public:
+  ContactParameters() {}
+  ContactParameters(BasePtr o1, BasePtr o2) : objects(o1, o2) {}
+  std::pair<BasePtr, BasePtr> objects;
+  double epsilon = 0.0, mu_coulomb = 0.0, mu_viscous = 0.0, compliance = 0.0;
+  unsigned NK = 4;
+};
+
+struct ConstraintStabilization {                   // ConstraintStabilization.h: only the switch the path honours
+  unsigned max_iterations = 0;                     // must stay 0: stabilization is outside the accelerated path
+};
+
+// ---------------------------------------------------------------------------------------------- the simulator
+class TimeSteppingSimulator : public Base {
+ public:
+  TimeSteppingSimulator() {}
+  ~TimeSteppingSimulator() { if (h_) b200moby_destroy(h_); }
+  TimeSteppingSimulator(const TimeSteppingSimulator&) = delete;
+  TimeSteppingSimulator& operator=(const TimeSteppingSimulator&) = delete;
+
+  // --- Moby's members ---
+  double current_time = 0.0;                                     // Simulator::current_time (env 0)
+  double min_step_size = 1.4901161193847656e-08;                 // TimeSteppingSimulator.cpp:48
+  double contact_dist_thresh = 1e-6;                             // ConstraintSimulator.cpp:56
+  ConstraintStabilization cstab;
+  std::map<std::pair<BasePtr, BasePtr>, std::shared_ptr<ContactParameters> > contact_params;
+  void (*post_step_callback_fn)(TimeSteppingSimulator*) = nullptr;           // Simulator.h:80
+  void (*post_mini_step_callback_fn)(TimeSteppingSimulator*) = nullptr;      // ConstraintSimulator.h:55; see step()
+  int impact_model = B200MOBY_MODEL_QP;                          // default build; B200MOBY_MODEL_AP == -DUSE_AP_MODEL
+  int device = 0;
+
+  void add_dynamic_body(ControlledBodyPtr body) {
+    if (h_) throw std::logic_error("add_dynamic_body after the first step");
+    body->sim_ = this; body->index_ = (int)bodies_.size();
+    bodies_.push_back(body);
+  }
+  const std::vector<ControlledBodyPtr>& get_dynamic_bodies() const { return bodies_; }
+  void add_contact_parameters(std::shared_ptr<ContactParameters> cp) { contact_params[cp->objects] = cp; }
+
+  // --- batch extension: n independent copies of the scene; per-env perturbations through RigidBody::set_pose(p, env) ---
+  void replicate(int n_envs) {
+    if (h_) throw std::logic_error("replicate after the first step");
+    if (n_envs < 1) throw std::invalid_argument("replicate: n_envs >= 1");
+    n_envs_ = n_envs;
+  }
+  int num_envs() const { return n_envs_; }
+
+  // TimeSteppingSimulator::step (TimeSteppingSimulator.cpp:52-111): every env advances by dt; returns dt.
+  // post_mini_step_callback_fn is invoked once per step() (after the device finished the step's mini-steps): per
+  // mini-step host callbacks would serialise the batch, so the reference's per-mini-step granularity is not kept.
+  double step(double dt) {
+    if (!h_) compile();
+    b200_check(b200moby_step(h_, dt, 1, nullptr), "b200moby_step");
+    dirty_ = true;
+    if (post_mini_step_callback_fn) post_mini_step_callback_fn(this);
+    current_time += dt;                                           // every env advances by exactly dt per step()
+    if (post_step_callback_fn) post_step_callback_fn(this);
+    return dt;
+  }
+  // n steps without returning to the host in between (no callbacks)
+  void step_n(double dt, int n) {
+    if (!h_) compile();
+    b200_check(b200moby_step(h_, dt, n, nullptr), "b200moby_step");
+    dirty_ = true;
+    current_time += dt * n;
+  }
+  b200moby_counters counters() {
+    if (!h_) compile();
+    b200moby_counters c;
+    b200_check(b200moby_get_counters(h_, &c), "b200moby_get_counters");
+    return c;
+  }
+  b200moby_handle handle() { if (!h_) compile(); return h_; }
+
+  // host copies of the state, SoA [body][7|6][env] (regress.cpp:78-95 row order per body: x y z qx qy qz qw)
+  const std::vector<double>& q() { sync_host(); return q_; }
+  const std::vector<double>& v() { sync_host(); return v_; }
+
+ private:
+  friend class RigidBody;
+  void ensure_host() {
+    const size_t nb = bodies_.size(), ne = (size_t)n_envs_;
+    if (q_.size() == nb * 7 * ne) return;
+    q_.assign(nb * 7 * ne, 0.0); v_.assign(nb * 6 * ne, 0.0);
+    for (size_t b = 0; b < nb; b++)
+      for (size_t e = 0; e < ne; e++) write_body(b, e, bodies_[b]->pose0_, bodies_[b]->vel0_);
+  }
+  void write_body(size_t b, size_t e, const Ravelin::Pose3d& p, const Ravelin::SVelocityd& vel) {
+    const size_t ne = (size_t)n_envs_;
+    double* q = &q_[(b * 7) * ne + e];
+    q[0] = p.x[0]; q[ne] = p.x[1]; q[2 * ne] = p.x[2]; q[3 * ne] = p.q.x; q[4 * ne] = p.q.y; q[5 * ne] = p.q.z; q[6 * ne] = p.q.w;
+    double* v = &v_[(b * 6) * ne + e];
+    for (int k = 0; k < 3; k++) { v[k * ne] = vel.linear[k]; v[(3 + k) * ne] = vel.angular[k]; }
+  }
+  void sync_host() {
+    ensure_host();
+    if (h_ && dirty_) { b200_check(b200moby_get_state(h_, q_.data(), v_.data()), "b200moby_get_state"); dirty_ = false; }
+  }
+  void push_state() {
+    if (h_) { b200_check(b200moby_set_state(h_, q_.data(), v_.data()), "b200moby_set_state"); dirty_ = true; }
+  }
+  // object graph -> b200moby_scene_desc (what XMLReader::read + the simulator's containers hold in the reference)
+  void compile() {
+    if (cstab.max_iterations != 0) throw std::runtime_error("constraint stabilization is not on the accelerated path: set cstab.max_iterations = 0");
+    const int nb = (int)bodies_.size(), ne = n_envs_;
+    if (nb == 0) throw std::logic_error("no bodies");
+    ensure_host();
+    std::vector<int> shape((size_t)nb * ne), enabled((size_t)nb * ne), NK((size_t)nb * nb * ne, 0);
+    std::vector<double> mass((size_t)nb * ne), dims((size_t)nb * 3 * ne), inertia((size_t)nb * 3 * ne);
+    std::vector<double> mu_c((size_t)nb * nb * ne, 0.0), mu_v(mu_c), eps(mu_c), comp(mu_c);
+    b200moby_scene_desc d; memset(&d, 0, sizeof(d));
+    d.gravity[0] = d.gravity[1] = d.gravity[2] = 0.0;
+    for (int b = 0; b < nb; b++) {
+      const RigidBody& rb = *bodies_[b];
+      PrimitivePtr prim;
+      if (rb.geometries.size() > 1) throw std::runtime_error("one collision geometry per body on the accelerated path");
+      if (!rb.geometries.empty()) prim = rb.geometries.front()->get_geometry();
+      for (int e = 0; e < ne; e++) {
+        shape[(size_t)b * ne + e] = prim ? prim->shape : B200MOBY_SHAPE_NONE;
+        enabled[(size_t)b * ne + e] = rb.enabled_ ? 1 : 0;
+        mass[(size_t)b * ne + e] = rb.J_.m;
+        for (int k = 0; k < 3; k++) { dims[((size_t)b * 3 + k) * ne + e] = prim ? prim->dims[k] : 0.0; inertia[((size_t)b * 3 + k) * ne + e] = rb.J_.J[k]; }
+      }
+      for (const RecurrentForcePtr& f : rb.forces_)
+        if (const GravityForce* g = dynamic_cast<const GravityForce*>(f.get())) for (int k = 0; k < 3; k++) d.gravity[k] = g->gravity[k];
+    }
+    // every pair is checked with default parameters (ContactParameters.cpp:21-28) unless contact_params overrides it
+    for (int i = 0; i < nb; i++)
+      for (int j = i + 1; j < nb; j++) {
+        ContactParameters cp;
+        for (const auto& kv : contact_params) {
+          const Base* a = kv.first.first.get(); const Base* b = kv.first.second.get();
+          if ((a == bodies_[i].get() && b == bodies_[j].get()) || (a == bodies_[j].get() && b == bodies_[i].get())) cp = *kv.second;
+        }
+        if (cp.NK < 4) cp.NK = 4;                                   // ContactParameters.cpp:132-136
+        for (int e = 0; e < ne; e++) {
+          const size_t o = ((size_t)i * nb + j) * ne + e;
+          mu_c[o] = cp.mu_coulomb; mu_v[o] = cp.mu_viscous; eps[o] = cp.epsilon; comp[o] = cp.compliance; NK[o] = (int)cp.NK;
+        }
+      }
+    d.n_envs = ne; d.n_bodies = nb;
+    d.shape = shape.data(); d.enabled = enabled.data(); d.mass = mass.data(); d.dims = dims.data(); d.inertia = inertia.data();
+    d.mu_coulomb = mu_c.data(); d.mu_viscous = mu_v.data(); d.epsilon = eps.data(); d.compliance = comp.data(); d.NK = NK.data();
+    d.contact_dist_thresh = contact_dist_thresh; d.min_step_size = min_step_size; d.min_step_size_env = nullptr;
+    d.impact_model = impact_model; d.stabilization_max_iterations = 0;
+    b200_check(b200moby_create(&d, device, &h_), "b200moby_create");
+    push_state();
+  }
+
+  std::vector<ControlledBodyPtr> bodies_;
+  int n_envs_ = 1;
+  b200moby_handle h_ = nullptr;
+  std::vector<double> q_, v_;
+  bool dirty_ = false;
+};
+
+inline void RigidBody::set_pose(const Ravelin::Pose3d& p, int env) {
+  if (!sim_) { pose0_ = p; return; }
+  if (env < 0 && !sim_->h_ && sim_->q_.empty()) { pose0_ = p; return; }
+  sim_->sync_host();
+  Ravelin::SVelocityd v = get_velocity(env < 0 ? 0 : env);
+  if (env < 0) { for (int e = 0; e < sim_->n_envs_; e++) sim_->write_body(index_, e, p, get_velocity(e)); pose0_ = p; }
+  else sim_->write_body(index_, env, p, v);
+  sim_->push_state();
+}
+inline Ravelin::Pose3d RigidBody::get_pose(int env) const {
+  if (!sim_) return pose0_;
+  sim_->sync_host();
+  const size_t ne = (size_t)sim_->n_envs_;
+  const double* q = &sim_->q_[((size_t)index_ * 7) * ne + env];
+  return Ravelin::Pose3d(Ravelin::Quatd(q[3 * ne], q[4 * ne], q[5 * ne], q[6 * ne]), Ravelin::Origin3d(q[0], q[ne], q[2 * ne]));
+}
+inline void RigidBody::set_velocity(const Ravelin::SVelocityd& vel, int env) {
+  if (!sim_) { vel0_ = vel; return; }
+  if (env < 0 && !sim_->h_ && sim_->q_.empty()) { vel0_ = vel; return; }
+  sim_->sync_host();
+  if (env < 0) { for (int e = 0; e < sim_->n_envs_; e++) sim_->write_body(index_, e, get_pose(e), vel); vel0_ = vel; }
+  else sim_->write_body(index_, env, get_pose(env), vel);
+  sim_->push_state();
+}
+inline Ravelin::SVelocityd RigidBody::get_velocity(int env) const {
+  if (!sim_) return vel0_;
+  sim_->sync_host();
+  const size_t ne = (size_t)sim_->n_envs_;
+  const double* v = &sim_->v_[((size_t)index_ * 6) * ne + env];
+  Ravelin::SVelocityd out;
+  for (int k = 0; k < 3; k++) { out.linear[k] = v[k * ne]; out.angular[k] = v[(3 + k) * ne]; }
+  return out;
+}
+
+}  // namespace Moby
+
+#endif  // B200MOBY_HPP

@@ -37,9 +37,9 @@ SYMBOLS = [
     "b200moby_last_error", "b200moby_abi_version", "b200moby_device_count",
     "b200moby_create", "b200moby_destroy", "b200moby_set_state", "b200moby_get_state",
     "b200moby_set_state_dev", "b200moby_get_state_dev", "b200moby_step", "b200moby_set_pivot_budget", "b200moby_get_counters",
-    "b200moby_reset_counters", "b200moby_get_time", "b200moby_get_last_lcp",
+    "b200moby_reset_counters", "b200moby_get_launch_count", "b200moby_get_time", "b200moby_get_last_lcp",
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
-    "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host",
+    "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host", "b200moby_lcp_solve_host",
     "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_delassus_batched",
 ]
 
@@ -67,6 +67,7 @@ def lib():
     L.b200moby_set_pivot_budget.argtypes = [C.c_void_p, C.c_int]
     L.b200moby_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     L.b200moby_reset_counters.argtypes = [C.c_void_p]
+    L.b200moby_get_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     L.b200moby_get_time.argtypes = [C.c_void_p, dp]
     L.b200moby_get_last_lcp.argtypes = [C.c_void_p, ip, dp, C.c_int]
     L.b200moby_lcp_lemke_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, ip, ip, ip, C.c_int, vp]
@@ -77,6 +78,8 @@ def lib():
                                                         C.c_double, ip, ip, vp]
     L.b200moby_lcp_lemke_host.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, ip, ip, C.c_int]
     L.b200moby_lcp_fast_host.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, ip, ip, C.c_int]
+    L.b200moby_lcp_solve_host.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                          C.c_int, ip, ip, C.c_int]
     L.b200moby_fwd_dyn_batched.argtypes = [C.c_void_p, dp, dp, C.c_double, vp]
     L.b200moby_find_contacts_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, ip, dp, dp, dp, dp, ip, dp, vp]
     L.b200moby_delassus_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, ip, vp]

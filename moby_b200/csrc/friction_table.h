@@ -2,6 +2,7 @@
 // reference evaluates them (ImpactConstraintHandlerQP.cpp:464-468; ImpactConstraintHandlerLCP.cpp:259-275), so the
 // device never calls its own cos/sin.  Layout: [4][NKMAX+1][NKMAX/2] = QP cos, QP sin, AP cos, AP sin.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <vector>
 #ifndef B2M_NKMAX
@@ -45,4 +46,17 @@ inline void b2m_env_bounds(int nb, const int* shape, const int* enabled, const i
       cmax += cnt;
       nmax += cnt * (model == 1 ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2);
     }
+}
+
+// LCP classes of the impact phase: ascending bounds on the LCP dimension (and the contact count they allow); an env
+// is solved with the working set of the first class its contacts fit.  The last class is the scene's own bound.
+// Returns the number of classes (<= max_classes).
+inline int b2m_class_table(int nmax, int cmax, int model, int max_classes, int* class_nmax, int* class_cmax) {
+  static const int bounds[] = {8, 16, 24, 32, 40, 48, 64, 80, 96, 128, 160};
+  const int minper = (model == 1) ? 6 : 8;            // fewest LCP rows one contact brings (NK = 4)
+  int k = 0;
+  for (int b : bounds)
+    if (b < nmax && k < max_classes - 1) { class_nmax[k] = b; class_cmax[k] = std::max(1, std::min(cmax, b / minper)); k++; }
+  class_nmax[k] = nmax; class_cmax[k] = cmax; k++;
+  return k;
 }

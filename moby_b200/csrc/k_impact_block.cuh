@@ -1,0 +1,26 @@
+// Impact phase, one block of NT threads per env (instantiated per NT in k_impact_block{64,128,256}.cu).
+#pragma once
+#include "sim_kernel_util.cuh"
+using namespace b2m;
+
+template <int NT>
+__global__ void __launch_bounds__(NT) impact_block_kernel(SimParams P, double dt, int round, int slot) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red[4 * (NT / 32) + 4];
+  __shared__ int next;
+  const size_t ed = (env_doubles(P.nb, P.cmax, P.nmax, P.npmax) + 1) & ~(size_t)1;
+  EnvMem m;
+  env_carve(m, (double*)smem, (int*)((double*)smem + ed), P.nb, P.cmax, P.nmax, P.npmax);
+  BlockGroup<NT> g(red);
+  unsigned long long lc[CNT_COUNT];
+  for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
+  const int count = *q_count(P, round, slot);
+  const int* list = q_list(P, round, slot);
+  int* head = q_head(P, round, slot);
+  for (int i = pull_block(head, &next); i < count; i = pull_block(head, &next)) {
+    EnvCtx cx; cx.limit = false; cx.budget = 0;
+    env_impact(g, P, list[i], m, dt, round, lc, cx);
+  }
+  if (g.tid == 0) commit_counters(P, lc);
+}
+

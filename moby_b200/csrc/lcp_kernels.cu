@@ -177,9 +177,12 @@ b200moby_status b200moby_lcp_fast_regularized_batched(int batch, int n, const do
 }
 
 static b200moby_status host_form(int mode, int batch, int n, const double* M, const double* q, double* z, int warm,
-                                 double piv_tol, double zero_tol, int* status, int* pivots, int device) {
+                                 double piv_tol, double zero_tol, int min_exp, int step_exp, int max_exp, int* status,
+                                 int* pivots, int device) {
   if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  if (mode < MODE_LEMKE || mode > MODE_FAST_REG) return b2m_fail(B200MOBY_ERR_INVALID, "mode must be 0..3");
   if (batch <= 0 || n <= 0) return B200MOBY_OK;
+  if (!M || !q || !z) return b2m_fail(B200MOBY_ERR_INVALID, "null pointer");
   B2M_CUDA(cudaSetDevice(device));
   double *dM = nullptr, *dq = nullptr, *dz = nullptr; int *dst = nullptr, *dpv = nullptr;
   const size_t nM = (size_t)batch * n * n, nv = (size_t)batch * n;
@@ -192,9 +195,13 @@ static b200moby_status host_form(int mode, int batch, int n, const double* M, co
   B2M_CUDA(cudaMemcpyAsync(dM, M, nM * sizeof(double), cudaMemcpyHostToDevice, s));
   B2M_CUDA(cudaMemcpyAsync(dq, q, nv * sizeof(double), cudaMemcpyHostToDevice, s));
   if (warm) B2M_CUDA(cudaMemcpyAsync(dz, z, nv * sizeof(double), cudaMemcpyHostToDevice, s));
-  b200moby_status r = (mode == MODE_LEMKE)
-      ? b200moby_lcp_lemke_batched(batch, n, dM, dq, dz, piv_tol, zero_tol, dst, dpv, nullptr, 0, s)
-      : b200moby_lcp_fast_batched(batch, n, dM, dq, dz, warm, zero_tol, dst, dpv, nullptr, 0, s);
+  b200moby_status r;
+  switch (mode) {
+    case MODE_LEMKE: r = b200moby_lcp_lemke_batched(batch, n, dM, dq, dz, piv_tol, zero_tol, dst, dpv, nullptr, 0, s); break;
+    case MODE_FAST: r = b200moby_lcp_fast_batched(batch, n, dM, dq, dz, warm, zero_tol, dst, dpv, nullptr, 0, s); break;
+    case MODE_LEMKE_REG: r = b200moby_lcp_lemke_regularized_batched(batch, n, dM, dq, dz, min_exp, step_exp, max_exp, piv_tol, zero_tol, dst, dpv, s); break;
+    default: r = b200moby_lcp_fast_regularized_batched(batch, n, dM, dq, dz, warm, min_exp, step_exp, max_exp, zero_tol, dst, dpv, s); break;
+  }
   if (r == B200MOBY_OK) {
     B2M_CUDA(cudaMemcpyAsync(z, dz, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (status) B2M_CUDA(cudaMemcpyAsync(status, dst, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -206,13 +213,19 @@ static b200moby_status host_form(int mode, int batch, int n, const double* M, co
   return r;
 }
 
+b200moby_status b200moby_lcp_solve_host(int mode, int batch, int n, const double* M, const double* q, double* z, int warm_start,
+                                        double piv_tol, double zero_tol, int min_exp, int step_exp, int max_exp, int* status,
+                                        int* pivots, int device) {
+  return host_form(mode, batch, n, M, q, z, warm_start, piv_tol, zero_tol, min_exp, step_exp, max_exp, status, pivots, device);
+}
+
 b200moby_status b200moby_lcp_lemke_host(int batch, int n, const double* M, const double* q, double* z, double piv_tol,
                                         double zero_tol, int* status, int* pivots, int device) {
-  return host_form(MODE_LEMKE, batch, n, M, q, z, 0, piv_tol, zero_tol, status, pivots, device);
+  return host_form(MODE_LEMKE, batch, n, M, q, z, 0, piv_tol, zero_tol, 0, 1, 0, status, pivots, device);
 }
 b200moby_status b200moby_lcp_fast_host(int batch, int n, const double* M, const double* q, double* z, int warm,
                                        double zero_tol, int* status, int* pivots, int device) {
-  return host_form(MODE_FAST, batch, n, M, q, z, warm, -1.0, zero_tol, status, pivots, device);
+  return host_form(MODE_FAST, batch, n, M, q, z, warm, -1.0, zero_tol, 0, 1, 0, status, pivots, device);
 }
 
 }  // extern "C"

@@ -17,6 +17,12 @@ enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3 };
 enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LEMKE_CALLS, CNT_PIVOTS, CNT_LCP_FAIL,
        CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_CA_ITERS, CNT_COUNT };
 #define B2M_NKMAX 64
+#define B2M_MAX_CLASSES 12
+// queue slots of one round: [0, n_classes) impact classes, then the envs that still have time left in their step, then stragglers
+#define B2M_SLOT_CONT B2M_MAX_CLASSES
+#define B2M_SLOT_STRAGGLER (B2M_MAX_CLASSES + 1)
+#define B2M_SLOTS (B2M_MAX_CLASSES + 2)
+#define B2M_ROUNDS_MAX 8
 
 struct V3 {
   double x, y, z;
@@ -46,8 +52,13 @@ struct SimParams {
   const double* min_step_env;   // optional [env]
   double* q; double* v; double* time; double* zlast; int* zlast_n;
   unsigned long long* counters;
-  int pivot_budget;            // > 0: per-env pivot budget of the warp kernel; over-budget envs go to defer_list
-  int* defer_list; int* defer_count;
+  int pivot_budget;            // > 0: per-env pivot budget of the warp-per-env impact kernels; over-budget envs are re-run by the straggler kernel
+  // phased step (advance -> impact per LCP class -> advance ...): per-env progress and work queues
+  double* hacc;                // [env] seconds of the current step already simulated
+  double* hpend;               // [env] length of the mini-step waiting for its impact solve
+  int* queue;                  // queue[(round * B2M_SLOTS + slot) * n_envs + i]
+  int* qctl;                   // [2][B2M_ROUNDS_MAX][B2M_SLOTS + 1] counts, then heads (slot B2M_SLOTS: the advance launch's own head)
+  int n_classes; int class_nmax[B2M_MAX_CLASSES]; int class_cmax[B2M_MAX_CLASSES];
   // debug taps (may be null)
   double* tap_MM; double* tap_qq; double* tap_z; int* tap_n;
 };
@@ -64,34 +75,51 @@ struct EnvMem {
   int *bshape, *ben, *pair_a, *pair_b, *cb1, *cb2, *cNK, *icon, *cisl, *corder, *isl_start, *gcoff, *bisl, *frow_c, *frow_j, *scal, *iwork;
 };
 
-B2M_HD inline size_t env_doubles(int nb, int cmax, int nmax, int npmax) {
+// The working set has two segments.  "small": bodies, pair distances and the contact list -- all that the advance
+// phase (positions, forward dynamics, narrowphase) touches.  "impact": Jacobian rows, Delassus blocks, the LCP and the
+// solver's work space -- only envs with an impacting contact ever need it, and it is sized by the env's own LCP class.
+B2M_HD inline size_t env_small_doubles(int nb, int cmax, int npmax) { return (size_t)38 * nb + 7 * (size_t)npmax + 17 * (size_t)cmax; }
+B2M_HD inline size_t env_small_ints(int nb, int cmax, int npmax) { return (size_t)2 * nb + 2 * (size_t)npmax + 3 * (size_t)cmax + 16; }
+B2M_HD inline size_t env_impact_doubles(int nb, int cmax, int nmax) {
   size_t lw = lemke_work_doubles(nmax), fw = fast_work_doubles(nmax);
-  return (size_t)38 * nb + 7 * (size_t)npmax + 17 * (size_t)cmax + 72 * (size_t)cmax + 36 * (size_t)nb + 6 * (size_t)cmax * cmax +
-         9 * (size_t)cmax + 6 * (size_t)nb + (size_t)nmax * nmax + 3 * (size_t)nmax + (lw > fw ? lw : fw);
+  return 72 * (size_t)cmax + 36 * (size_t)nb + 6 * (size_t)cmax * cmax + 9 * (size_t)cmax + 6 * (size_t)nb + (size_t)nmax * nmax +
+         3 * (size_t)nmax + (lw > fw ? lw : fw);
 }
-B2M_HD inline size_t env_ints(int nb, int cmax, int nmax, int npmax) {
+B2M_HD inline size_t env_impact_ints(int nb, int cmax, int nmax) {
   size_t lw = lemke_work_ints(nmax), fw = fast_work_ints(nmax);
-  return (size_t)5 * nb + 1 + 2 * (size_t)npmax + 6 * (size_t)cmax + 2 * (size_t)nmax + 16 + (lw > fw ? lw : fw);
+  return (size_t)3 * nb + 1 + 3 * (size_t)cmax + 2 * (size_t)nmax + (lw > fw ? lw : fw);
 }
+B2M_HD inline size_t env_doubles(int nb, int cmax, int nmax, int npmax) { return env_small_doubles(nb, cmax, npmax) + env_impact_doubles(nb, cmax, nmax); }
+B2M_HD inline size_t env_ints(int nb, int cmax, int nmax, int npmax) { return env_small_ints(nb, cmax, npmax) + env_impact_ints(nb, cmax, nmax); }
 
-B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax, int npmax) {
+B2M_HD inline void env_carve_small(EnvMem& m, double* d, int* i, int nb, int cmax, int npmax) {
   m.bx = d; d += 3 * nb; m.bq = d; d += 4 * nb; m.bR = d; d += 9 * nb; m.bvl = d; d += 3 * nb; m.bva = d; d += 3 * nb;
   m.bmass = d; d += nb; m.bdims = d; d += 3 * nb; m.bJ = d; d += 3 * nb; m.xsave = d; d += 3 * nb; m.qsave = d; d += 4 * nb;
   m.pd_dist = d; d += npmax; m.pd_pa = d; d += 3 * npmax; m.pd_pb = d; d += 3 * npmax;
   m.cp = d; d += 3 * cmax; m.cnrm = d; d += 3 * cmax; m.ct1 = d; d += 3 * cmax; m.ct2 = d; d += 3 * cmax;
   m.cdist = d; d += cmax; m.cmu = d; d += cmax; m.cmuv = d; d += cmax; m.ceps = d; d += cmax; m.ccomp = d; d += cmax;
+  m.bshape = i; i += nb; m.ben = i; i += nb;
+  m.pair_a = i; i += npmax; m.pair_b = i; i += npmax;
+  m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax;
+  m.scal = i; i += 16;
+  m.Jr = nullptr; m.zl = nullptr;
+}
+B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax) {
   m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.D = d; d += 6 * (size_t)cmax * cmax;
   m.Cv = d; d += 3 * cmax; m.imp = d; d += 3 * cmax; m.acc = d; d += 3 * cmax; m.dv = d; d += 6 * nb;
   m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.zl = d; d += nmax; m.work = d;
-  m.bshape = i; i += nb; m.ben = i; i += nb; m.gcoff = i; i += nb; m.bisl = i; i += nb;
-  m.pair_a = i; i += npmax; m.pair_b = i; i += npmax;
-  m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax; m.icon = i; i += cmax; m.cisl = i; i += cmax; m.corder = i; i += cmax;
+  m.gcoff = i; i += nb; m.bisl = i; i += nb;
+  m.icon = i; i += cmax; m.cisl = i; i += cmax; m.corder = i; i += cmax;
   m.isl_start = i; i += nb + 1;
-  m.frow_c = i; i += nmax; m.frow_j = i; i += nmax; m.scal = i; i += 16; m.iwork = i;
+  m.frow_c = i; i += nmax; m.frow_j = i; i += nmax; m.iwork = i;
+}
+B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax, int npmax) {
+  env_carve_small(m, d, i, nb, cmax, npmax);
+  env_carve_impact(m, d + env_small_doubles(nb, cmax, npmax), i + env_small_ints(nb, cmax, npmax), nb, cmax, nmax);
 }
 
 // scal[] slots
-enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8 };
+enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10 };
 
 // Per-env solver budget: when `limit` is set and an env's pivots in this launch exceed it, the env's step is
 // abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
@@ -379,21 +407,33 @@ B2M_DEV void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
       }
     m.scal[S_NPAIRS] = np;
     m.scal[S_ZLN] = P.zlast_n[e];
+    m.scal[S_ZLDIRTY] = 0;
   }
   g.sync();
-  const int zn = m.scal[S_ZLN];                                 // ImpactConstraintHandler::_zlast, kept on chip for the whole launch
-  for (int i = g.tid; i < zn; i += G::size) m.zl[i] = P.zlast[(size_t)i * ne + e];
-  g.sync();
+  if (m.zl) {                                                   // ImpactConstraintHandler::_zlast, kept on chip for the whole launch
+    const int zn = m.scal[S_ZLN];                               // a longer vector than this launch's LCP class can never match (H1: zero fill)
+    if (zn <= P.nmax) for (int i = g.tid; i < zn; i += G::size) m.zl[i] = P.zlast[(size_t)i * ne + e];
+    g.sync();
+  }
 }
 
+// what: 1 positions, 2 velocities, 4 warm start
+enum { ST_POS = 1, ST_VEL = 2, ST_ZL = 4 };
 template <class G>
-B2M_DEV void env_store(const G& g, const SimParams& P, int e, const EnvMem& m) {
+B2M_DEV void env_store(const G& g, const SimParams& P, int e, const EnvMem& m, int what = ST_POS | ST_VEL | ST_ZL) {
   const int nb = P.nb, ne = P.n_envs;
-  for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; if (m.ben[b]) { P.q[((size_t)b * 7 + c) * ne + e] = m.bx[k]; P.v[((size_t)b * 6 + c) * ne + e] = m.bvl[k]; P.v[((size_t)b * 6 + 3 + c) * ne + e] = m.bva[k]; } }
-  for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; if (m.ben[b]) P.q[((size_t)b * 7 + 3 + c) * ne + e] = m.bq[k]; }
-  const int zn = m.scal[S_ZLN];
-  for (int i = g.tid; i < zn; i += G::size) P.zlast[(size_t)i * ne + e] = m.zl[i];
-  if (g.tid == 0) P.zlast_n[e] = zn;
+  for (int k = g.tid; k < 3 * nb; k += G::size) {
+    const int b = k / 3, c = k - 3 * b;
+    if (!m.ben[b]) continue;
+    if (what & ST_POS) P.q[((size_t)b * 7 + c) * ne + e] = m.bx[k];
+    if (what & ST_VEL) { P.v[((size_t)b * 6 + c) * ne + e] = m.bvl[k]; P.v[((size_t)b * 6 + 3 + c) * ne + e] = m.bva[k]; }
+  }
+  if (what & ST_POS) for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; if (m.ben[b]) P.q[((size_t)b * 7 + 3 + c) * ne + e] = m.bq[k]; }
+  if ((what & ST_ZL) && m.zl && m.scal[S_ZLDIRTY]) {
+    const int zn = m.scal[S_ZLN];
+    for (int i = g.tid; i < zn; i += G::size) P.zlast[(size_t)i * ne + e] = m.zl[i];
+    if (g.tid == 0) P.zlast_n[e] = zn;
+  }
 }
 
 template <class G>
@@ -812,7 +852,7 @@ B2M_DEV bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
     lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
     lc[CNT_PIVOT_FLOPS] += (unsigned long long)pivots * 2ull * n * (n + 1);
     if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
-    m.scal[S_ZLN] = n;
+    m.scal[S_ZLN] = n; m.scal[S_ZLDIRTY] = 1;
   }
   for (int i = g.tid; i < n; i += G::size) m.zl[i] = m.z[i];                        // :233 _zlast = z
   if (P.tap_n) {
@@ -991,14 +1031,25 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
   return true;
 }
 
-// TimeSteppingSimulator::do_mini_step (:114-222); returns h, or -1 when the env is deferred
+// First half of TimeSteppingSimulator::do_mini_step (:114-209): positions with conservative advancement, forward
+// dynamics + velocity update, distances, contacts.  Returns h; `impacting` says whether the constraint handler has
+// work to do (ConstraintSimulator.cpp:298-355 / ImpactConstraintHandler.cpp:96-120 early-outs).
 template <class G>
-B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc, EnvCtx& cx) {
+B2M_DEV double mini_step_advance(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc, bool& impacting) {
   const double h = integrate_positions_CA(g, P, e, m, dt, lc);
   fwd_dyn_integrate_velocity(g, P, m, h);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
-  if (!process_constraints(g, P, e, m, lc, cx)) return -1.0;
+  const int ncon = m.scal[S_NCON];
+  bool imp = false;
+  for (int c = g.tid; c < ncon; c += G::size) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) imp = true;
+  impacting = g.any(imp);
+  return h;
+}
+
+// bookkeeping at the end of a mini-step
+template <class G>
+B2M_DEV void mini_step_account(const G& g, const SimParams& P, const EnvMem& m, unsigned long long* lc) {
   if (g.tid == 0) {     // F_fd = 60 per free body (Newton-Euler); F_narrow = 8 vertices x 20 (box) or 20 (sphere) per pair and distance pass
     lc[CNT_MINI_STEPS]++;
     unsigned long long f = 0;
@@ -1006,7 +1057,36 @@ B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, do
     for (int p = 0; p < m.scal[S_NPAIRS]; p++) f += 3 * ((m.bshape[m.pair_a[p]] == SH_BOX || m.bshape[m.pair_b[p]] == SH_BOX) ? 160 : 20);
     lc[CNT_ASM_FLOPS] += f;
   }
+}
+
+// LCP dimension the env's contacts give if they all fall into one island (upper bound of every island's n): picks the
+// shared-memory class of the impact kernel.
+B2M_HD B2M_INL int contacts_lcp_dim(const EnvMem& m, int ncon, int model) {
+  int n = 0;
+  for (int c = 0; c < ncon; c++) { const int nk = m.cNK[c]; n += (model == 1) ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2; }
+  return n;
+}
+
+// TimeSteppingSimulator::do_mini_step (:114-222); returns h, or -1 when the env is deferred
+template <class G>
+B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc, EnvCtx& cx) {
+  bool impacting;
+  const double h = mini_step_advance(g, P, e, m, dt, lc, impacting);
+  if (impacting && !process_constraints(g, P, e, m, lc, cx)) return -1.0;
+  mini_step_account(g, P, m, lc);
   return h;
+}
+
+// The rest of one TimeSteppingSimulator::step (:433-455) from `h` seconds into it; the env is loaded.  Returns false when deferred.
+template <class G>
+B2M_DEV bool env_finish_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, double h, double& t, unsigned long long* lc, EnvCtx& cx) {
+  while (h < dt) {
+    const double hh = do_mini_step(g, P, e, m, dt - h, lc, cx);
+    if (hh < 0.0) return false;
+    h += hh; t += hh;
+  }
+  if (g.tid == 0) lc[CNT_ENV_STEPS]++;
+  return true;
 }
 
 // n_steps x TimeSteppingSimulator::step (:52-111, :433-455) for env e; stabilization disabled.
@@ -1015,20 +1095,105 @@ template <class G>
 B2M_DEV bool env_run(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int n_steps, unsigned long long* lc, EnvCtx& cx) {
   env_load(g, P, e, m);
   double t = P.time[e];
-  for (int s = 0; s < n_steps; s++) {
-    double h = 0.0;
-    while (h < dt) {
-      const double hh = do_mini_step(g, P, e, m, dt - h, lc, cx);
-      if (hh < 0.0) return false;
-      h += hh; t += hh;
-    }
-    if (g.tid == 0) lc[CNT_ENV_STEPS]++;
-  }
+  for (int s = 0; s < n_steps; s++)
+    if (!env_finish_step(g, P, e, m, dt, 0.0, t, lc, cx)) return false;
   g.sync();
   env_store(g, P, e, m);
   if (g.tid == 0) P.time[e] = t;
   g.sync();
   return true;
+}
+
+// ---------------- phased step: advance -> impact (per LCP class) -> advance ... -> finish ----------------
+// Most env-steps never need an LCP (free flight, resting without approach velocity): the advance phase runs them with
+// the small working set only, so dozens of envs are resident per SM.  An env whose contacts are impacting is parked
+// after the first half of its mini-step and queued by the LCP dimension its contacts give; the impact phase picks it
+// up with a working set of exactly that class.  Same functions, same arithmetic and the same order of operations per
+// env as the fused loop above -- results are bit-identical.
+B2M_HD B2M_INL int* q_count(const SimParams& P, int round, int slot) { return P.qctl + round * (B2M_SLOTS + 1) + slot; }
+B2M_HD B2M_INL int* q_head(const SimParams& P, int round, int slot) { return P.qctl + (B2M_ROUNDS_MAX + round) * (B2M_SLOTS + 1) + slot; }
+B2M_HD B2M_INL int* q_list(const SimParams& P, int round, int slot) { return P.queue + ((size_t)round * B2M_SLOTS + slot) * P.n_envs; }
+B2M_DEV B2M_INL int b2m_atomic_inc(int* p) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, 1);
+#else
+  return (*p)++;
+#endif
+}
+B2M_DEV B2M_INL void q_push(const SimParams& P, int round, int slot, int e) { q_list(P, round, slot)[b2m_atomic_inc(q_count(P, round, slot))] = e; }
+
+// Advance env e through its step until it completes or needs an impact solve.  `m` carries the small segment only.
+template <class G>
+B2M_DEV void env_advance(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int round, unsigned long long* lc) {
+  env_load(g, P, e, m);
+  double t = P.time[e];
+  double h = (round == 0) ? 0.0 : P.hacc[e];
+  bool parked = false;
+  while (h < dt) {
+    bool impacting;
+    const double hh = mini_step_advance(g, P, e, m, dt - h, lc, impacting);
+    if (impacting) {
+      if (g.tid == 0) {
+        P.hacc[e] = h; P.hpend[e] = hh;
+        const int ncon = m.scal[S_NCON];
+        const int n = contacts_lcp_dim(m, ncon, P.model);
+        int cls = 0;
+        while (cls < P.n_classes - 1 && (n > P.class_nmax[cls] || ncon > P.class_cmax[cls])) cls++;
+        q_push(P, round, cls, e);
+      }
+      parked = true;
+      break;
+    }
+    mini_step_account(g, P, m, lc);
+    h += hh; t += hh;
+  }
+  if (!parked && g.tid == 0) lc[CNT_ENV_STEPS]++;
+  g.sync();
+  env_store(g, P, e, m, ST_POS | ST_VEL);
+  if (g.tid == 0) P.time[e] = t;
+  g.sync();
+}
+
+// Second half of the parked mini-step: contacts again from the stored state (same inputs, same results), islands,
+// assembly, solve, impulses.  P.cmax / P.nmax are the class's.  Returns false when the env ran over its pivot budget
+// (nothing stored; it is queued for the straggler kernel).
+template <class G>
+B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int round, unsigned long long* lc, EnvCtx& cx) {
+  env_load(g, P, e, m);
+  const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
+  calc_pairwise_distances(g, m);
+  find_unilateral_constraints(g, P, e, m, lc);
+  lc[CNT_CONTACTS] = c0; lc[CNT_OVERFLOW] = o0;                  // counted by the advance phase
+  if (!process_constraints(g, P, e, m, lc, cx)) {
+    if (g.tid == 0) q_push(P, round, B2M_SLOT_STRAGGLER, e);
+    g.sync();
+    return false;
+  }
+  mini_step_account(g, P, m, lc);
+  g.sync();
+  env_store(g, P, e, m, ST_VEL | ST_ZL);
+  if (g.tid == 0) {
+    const double hh = P.hpend[e];
+    const double h = P.hacc[e] + hh;
+    P.time[e] = P.time[e] + hh;
+    if (h < dt) { P.hacc[e] = h; q_push(P, round, B2M_SLOT_CONT, e); }
+    else lc[CNT_ENV_STEPS]++;
+  }
+  g.sync();
+  return true;
+}
+
+// Whatever is left of env e's step after the last round, with the fused loop (full working set).
+template <class G>
+B2M_DEV void env_finish(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
+  env_load(g, P, e, m);
+  double t = P.time[e];
+  EnvCtx cx; cx.limit = false; cx.budget = 0;
+  env_finish_step(g, P, e, m, dt, P.hacc[e], t, lc, cx);
+  g.sync();
+  env_store(g, P, e, m);
+  if (g.tid == 0) P.time[e] = t;
+  g.sync();
 }
 
 }  // namespace b2m

@@ -1,0 +1,33 @@
+// Device-side helpers shared by the step kernels (one kernel per translation unit so they compile in parallel).
+#pragma once
+#include "../../include/b200moby.h"
+#include "sim_device.cuh"
+#include "sim_launch.h"
+
+namespace b2m {
+
+__device__ inline void commit_counters(const SimParams& P, const unsigned long long* lc) {
+  for (int k = 0; k < CNT_COUNT; k++) {
+    if (k == CNT_MAX_N) { if (lc[k]) atomicMax(P.counters + k, lc[k]); }
+    else if (lc[k]) atomicAdd(P.counters + k, lc[k]);
+  }
+}
+__device__ __forceinline__ void add_counters(unsigned long long* tot, const unsigned long long* lc) {
+  for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) { if (lc[k] > tot[k]) tot[k] = lc[k]; } else tot[k] += lc[k]; }
+}
+
+// next queue index for a warp (lane 0 pulls, broadcast) / a block (thread 0 pulls, broadcast through shared memory)
+__device__ __forceinline__ int pull_warp(int* head) {
+  int i = 0;
+  if ((threadIdx.x & 31) == 0) i = atomicAdd(head, 1);
+  return __shfl_sync(0xffffffffu, i, 0);
+}
+__device__ __forceinline__ int pull_block(int* head, int* slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) *slot = atomicAdd(head, 1);
+  __syncthreads();
+  return *slot;
+}
+
+
+}  // namespace b2m

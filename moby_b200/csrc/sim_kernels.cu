@@ -9,8 +9,18 @@
 #include "friction_table.h"
 #include "host_util.h"
 #include "sim_device.cuh"
+#include "sim_launch.h"
 
 using namespace b2m;
+
+#define B2M_SMEM_MAX (227 * 1024 - 1024)   /* dynamic shared memory we ask for at most: the opt-in limit minus the kernels' static reduction scratch */
+
+struct ClassPlan {
+  int nmax = 0, cmax = 0;
+  int threads = 32;          // 32: warp-per-env kernel (wpb warps per block); > 32: one block per env
+  int wpb = 1, grid = 1;
+  size_t shmem = 0;
+};
 
 struct b200moby_sim {
   int device = 0;
@@ -19,58 +29,19 @@ struct b200moby_sim {
   std::vector<void*> allocs;
   size_t env_d = 0, env_i = 0;
   int wpb = 1, grid = 1, sms = 148;
-  size_t shmem = 0;
+  size_t shmem = 0;          // full working set of one env (stage kernels, finish kernel)
   bool taps = false;
+  // phased step plan
+  int rounds = 2;
+  int adv_wpb = 4, adv_grid = 1; size_t adv_shmem = 0;
+  std::vector<ClassPlan> classes;
+  ClassPlan straggler;       // full-size block-per-env kernel for envs over their pivot budget
+  int fin_grid = 1;
+  bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
+  long long launches = 0;
 };
 
 namespace {
-
-__device__ void commit_counters(const SimParams& P, const unsigned long long* lc) {
-  for (int k = 0; k < CNT_COUNT; k++) {
-    if (k == CNT_MAX_N) atomicMax(P.counters + k, lc[k]);
-    else if (lc[k]) atomicAdd(P.counters + k, lc[k]);
-  }
-}
-
-// One env per warp-sized block.  Envs whose solver work exceeds the pivot budget are queued for step_block_kernel.
-__global__ void __launch_bounds__(32) step_warp_kernel(SimParams P, double dt, int n_steps, size_t env_d) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  EnvMem m;
-  env_carve(m, (double*)smem, (int*)((double*)smem + env_d), P.nb, P.cmax, P.nmax, P.npmax);
-  WarpGroup g(nullptr);
-  unsigned long long lc[CNT_COUNT];
-  for (int e = blockIdx.x; e < P.n_envs; e += gridDim.x) {
-    for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
-    EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
-    const bool done = env_run(g, P, e, m, dt, n_steps, lc, cx);
-    if (g.tid == 0) {
-      if (done) commit_counters(P, lc);
-      else P.defer_list[atomicAdd(P.defer_count, 1)] = e;
-    }
-    g.sync();
-  }
-}
-
-// The deferred envs again, from their untouched stored state, with a whole 128-thread block per env: the same code and
-// arithmetic (reductions are order-independent), four times the lanes on every pivot.
-#define B2M_BLOCK_THREADS 128
-__global__ void __launch_bounds__(B2M_BLOCK_THREADS) step_block_kernel(SimParams P, double dt, int n_steps, size_t env_d) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double red[4 * (B2M_BLOCK_THREADS / 32) + 4];
-  EnvMem m;
-  env_carve(m, (double*)smem, (int*)((double*)smem + env_d), P.nb, P.cmax, P.nmax, P.npmax);
-  BlockGroup<B2M_BLOCK_THREADS> g(red);
-  unsigned long long lc[CNT_COUNT];
-  const int count = *P.defer_count;
-  for (int i = blockIdx.x; i < count; i += gridDim.x) {
-    const int e = P.defer_list[i];
-    for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
-    EnvCtx cx; cx.limit = false; cx.budget = 0;
-    env_run(g, P, e, m, dt, n_steps, lc, cx);
-    if (g.tid == 0) commit_counters(P, lc);
-    g.sync();
-  }
-}
 
 // stage kernels: same device functions, one warp per env, results written out instead of carried on
 enum { STAGE_FWD_DYN = 0, STAGE_CONTACTS = 1, STAGE_DELASSUS = 2 };
@@ -169,24 +140,114 @@ b200moby_status dev_zero(b200moby_sim* h, size_t count, T** dst) {
   return B200MOBY_OK;
 }
 
-b200moby_status plan_launch(b200moby_sim* h, const void* kernel) {
+const void* impact_block_ptr(int nt) { return nt == 64 ? b2m_k_impact_block64() : (nt == 128 ? b2m_k_impact_block128() : b2m_k_impact_block256()); }
+
+int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
+
+size_t env_bytes(int nb, int cmax, int nmax, int npmax) {
+  return ((env_doubles(nb, cmax, nmax, npmax) + 1) & ~(size_t)1) * sizeof(double) + ((env_ints(nb, cmax, nmax, npmax) + 3) & ~(size_t)3) * sizeof(int);
+}
+
+b200moby_status plan_grid(const void* kernel, int threads, size_t shmem, int sms, int work, int* grid) {
+  B2M_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX));
+  int per_sm = 0;
+  B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, shmem));
+  if (per_sm < 1) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "kernel does not fit an SM (%d threads, %zu bytes of shared memory)", threads, shmem);
+  *grid = std::max(1, std::min(work, sms * per_sm));
+  return B200MOBY_OK;
+}
+
+// Launch plan of the phased step: grids are persistent (SMs x resident blocks, capped by the batch) and pull env
+// indices from the queues, so empty queues cost one short launch.
+b200moby_status plan_launch(b200moby_sim* h) {
   int sms = 0;
   B2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-  h->env_d = (env_doubles(h->nb, h->cmax, h->nmax, h->npmax) + 1) & ~(size_t)1;
-  h->env_i = (env_ints(h->nb, h->cmax, h->nmax, h->npmax) + 3) & ~(size_t)3;
-  const size_t per_warp = h->env_d * sizeof(double) + h->env_i * sizeof(int);
-  const size_t MAXS = 227 * 1024;
-  if (per_warp > MAXS)
-    return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "env working set (%zu bytes, LCP n <= %d) exceeds one SM's shared memory; the block-per-env path is not built yet", per_warp, h->nmax);
-  // One env per 32-thread block: envs differ wildly in work (conservative-advancement sub-steps, solver retries), so
-  // the hardware block scheduler doing the load balancing beats any static env->warp assignment; shared memory,
-  // not threads, limits residency (227 KB / per-env working set blocks per SM).
-  h->wpb = 1;
-  h->shmem = per_warp;
-  B2M_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
-  B2M_CUDA(cudaFuncSetAttribute(step_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
-  h->grid = h->n_envs;
   h->sms = sms;
+  const int nb = h->nb, ne = h->n_envs;
+  h->env_d = (env_doubles(nb, h->cmax, h->nmax, h->npmax) + 1) & ~(size_t)1;
+  h->env_i = (env_ints(nb, h->cmax, h->nmax, h->npmax) + 3) & ~(size_t)3;
+  h->shmem = h->env_d * sizeof(double) + h->env_i * sizeof(int);
+  if (h->shmem > B2M_SMEM_MAX)
+    return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "env working set (%zu bytes, LCP n <= %d) exceeds one SM's shared memory", h->shmem, h->nmax);
+  h->wpb = 1; h->grid = ne;
+  h->fused = env_int("B200MOBY_FUSED", 0) != 0;
+  h->rounds = std::max(1, std::min(B2M_ROUNDS_MAX, env_int("B200MOBY_ROUNDS", 2)));
+  B2M_CUDA(cudaFuncSetAttribute(b2m_k_step_warp(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX));
+  b200moby_status st;
+  // advance: warps_per_block envs per block, small segment only
+  {
+    const size_t sd = (env_small_doubles(nb, h->cmax, h->npmax) + 1) & ~(size_t)1, si = (env_small_ints(nb, h->cmax, h->npmax) + 3) & ~(size_t)3;
+    const size_t per = sd * sizeof(double) + si * sizeof(int);
+    int wpb = env_int("B200MOBY_ADV_WPB", 4);
+    while (wpb > 1 && per * wpb > B2M_SMEM_MAX) wpb--;
+    if (per > B2M_SMEM_MAX) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "advance working set (%zu bytes) exceeds one SM's shared memory", per);
+    h->adv_wpb = wpb; h->adv_shmem = per * wpb;
+    if ((st = plan_grid(b2m_k_advance(), wpb * 32, h->adv_shmem, sms, (ne + wpb - 1) / wpb, &h->adv_grid)) != B200MOBY_OK) return st;
+  }
+  // impact classes by LCP dimension
+  {
+    const int warp_nmax = env_int("B200MOBY_WARP_NMAX", 24); // classes up to this n: warp per env; above: block per env
+    const int bthreads = env_int("B200MOBY_IMPACT_THREADS", 64);
+    const int ncls = b2m_class_table(h->nmax, h->cmax, h->P.model, B2M_MAX_CLASSES, h->P.class_nmax, h->P.class_cmax);
+    h->classes.clear();
+    for (int k = 0; k < ncls; k++) {
+      ClassPlan c; c.nmax = h->P.class_nmax[k]; c.cmax = h->P.class_cmax[k];
+      const int n = c.nmax;
+      const size_t per = env_bytes(nb, c.cmax, c.nmax, h->npmax);
+      if (n <= warp_nmax || bthreads <= 32) {
+        c.threads = 32;
+        c.wpb = (int)std::max<size_t>(1, std::min<size_t>(4, B2M_SMEM_MAX / per));
+        c.shmem = per * c.wpb;
+        if ((st = plan_grid(b2m_k_impact_warp(), c.wpb * 32, c.shmem, sms, (ne + c.wpb - 1) / c.wpb, &c.grid)) != B200MOBY_OK) return st;
+      } else {
+        c.threads = bthreads <= 64 ? 64 : (bthreads <= 128 ? 128 : 256); c.wpb = 1; c.shmem = per;
+        if (c.threads == 64) st = plan_grid(impact_block_ptr(64), 64, per, sms, ne, &c.grid);
+        else if (c.threads == 128) st = plan_grid(impact_block_ptr(128), 128, per, sms, ne, &c.grid);
+        else st = plan_grid(impact_block_ptr(256), 256, per, sms, ne, &c.grid);
+        if (st != B200MOBY_OK) return st;
+      }
+      h->classes.push_back(c);
+    }
+    h->P.n_classes = (int)h->classes.size();
+    ClassPlan& sg = h->straggler;
+    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = 256; sg.wpb = 1; sg.shmem = h->shmem;
+    if ((st = plan_grid(impact_block_ptr(256), 256, sg.shmem, sms, ne, &sg.grid)) != B200MOBY_OK) return st;
+  }
+  if ((st = plan_grid(b2m_k_finish(), 32, h->shmem, sms, ne, &h->fin_grid)) != B200MOBY_OK) return st;
+  return B200MOBY_OK;
+}
+
+// One TimeSteppingSimulator::step for every env: advance, then per round the impact classes, stragglers and the
+// next advance; the finish kernel takes whatever the rounds left over.  All launches are asynchronous on `s`.
+b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
+  SimParams& P = h->P;
+  B2M_CUDA(cudaMemsetAsync(P.qctl, 0, sizeof(int) * 2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1), s));
+  for (int r = 0; r < h->rounds; r++) {
+    { void* a[] = {&P, &dt, &r, &h->adv_wpb};
+      B2M_CUDA(cudaLaunchKernel(b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)); h->launches++; }
+    for (size_t c = 0; c < h->classes.size(); c++) {
+      ClassPlan& cp = h->classes[c];
+      SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax;
+      int slot = (int)c;
+      if (cp.threads == 32) {
+        void* a[] = {&Pc, &dt, &r, &slot, &cp.wpb};
+        B2M_CUDA(cudaLaunchKernel(b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, s));
+      } else {
+        Pc.pivot_budget = 0;
+        void* a[] = {&Pc, &dt, &r, &slot};
+        B2M_CUDA(cudaLaunchKernel(impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, s));
+      }
+      h->launches++;
+    }
+    if (P.pivot_budget > 0) {
+      int slot = B2M_SLOT_STRAGGLER;
+      void* a[] = {&P, &dt, &r, &slot};
+      B2M_CUDA(cudaLaunchKernel(impact_block_ptr(256), dim3(h->straggler.grid), dim3(256), a, h->straggler.shmem, s)); h->launches++;
+    }
+  }
+  { int r = h->rounds - 1; void* a[] = {&P, &dt, &r};
+    B2M_CUDA(cudaLaunchKernel(b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)); h->launches++; }
+  B2M_CUDA(cudaGetLastError());
   return B200MOBY_OK;
 }
 
@@ -247,11 +308,12 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)h->nmax * ne, &P.zlast));
   TRY(dev_zero(h, (size_t)ne, &P.zlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
-  TRY(dev_zero(h, (size_t)ne, &P.defer_list));
-  TRY(dev_zero(h, (size_t)1, &P.defer_count));
-  P.pivot_budget = 96;
-  if (const char* s = getenv("B200MOBY_PIVOT_BUDGET")) P.pivot_budget = atoi(s);
-  TRY(plan_launch(h, (const void*)step_warp_kernel));
+  TRY(dev_zero(h, (size_t)ne, &P.hacc));
+  TRY(dev_zero(h, (size_t)ne, &P.hpend));
+  TRY(dev_zero(h, (size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne, &P.queue));
+  TRY(dev_zero(h, (size_t)2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1), &P.qctl));
+  P.pivot_budget = env_int("B200MOBY_PIVOT_BUDGET", 96);
+  TRY(plan_launch(h));
 #undef TRY
   *out = h;
   return B200MOBY_OK;
@@ -300,12 +362,15 @@ b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* s
   if (!h || !(dt > 0.0) || n_steps < 0) return b2m_fail(B200MOBY_ERR_INVALID, "bad step arguments");
   if (n_steps == 0) return B200MOBY_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->P.pivot_budget > 0) B2M_CUDA(cudaMemsetAsync(h->P.defer_count, 0, sizeof(int), s));
-  step_warp_kernel<<<h->grid, 32, h->shmem, s>>>(h->P, dt, n_steps, h->env_d);
-  B2M_CUDA(cudaGetLastError());
-  if (h->P.pivot_budget > 0) {
-    step_block_kernel<<<h->sms * 2, B2M_BLOCK_THREADS, h->shmem, s>>>(h->P, dt, n_steps, h->env_d);
-    B2M_CUDA(cudaGetLastError());
+  if (h->fused) {
+    void* a[] = {&h->P, &dt, &n_steps, &h->env_d};
+    B2M_CUDA(cudaLaunchKernel(b2m_k_step_warp(), dim3(h->grid), dim3(32), a, h->shmem, s));
+    h->launches++;
+    return B200MOBY_OK;
+  }
+  for (int k = 0; k < n_steps; k++) {
+    b200moby_status st = launch_step(h, dt, s);
+    if (st != B200MOBY_OK) return st;
   }
   return B200MOBY_OK;
 }
@@ -325,6 +390,11 @@ b200moby_status b200moby_get_counters(b200moby_handle h, b200moby_counters* out)
   out->lcp_fast_calls = c[CNT_FAST_CALLS]; out->lemke_calls = c[CNT_LEMKE_CALLS]; out->pivots = c[CNT_PIVOTS];
   out->lcp_failures = c[CNT_LCP_FAIL] + c[CNT_OVERFLOW]; out->impact_tol_events = c[CNT_IMPACT_TOL]; out->contacts = c[CNT_CONTACTS];
   out->max_lcp_n = c[CNT_MAX_N]; out->pivot_flops = c[CNT_PIVOT_FLOPS]; out->assembly_flops = c[CNT_ASM_FLOPS]; out->ca_iterations = c[CNT_CA_ITERS];
+  return B200MOBY_OK;
+}
+b200moby_status b200moby_get_launch_count(b200moby_handle h, long long* out) {
+  if (!h || !out) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  *out = h->launches;
   return B200MOBY_OK;
 }
 b200moby_status b200moby_reset_counters(b200moby_handle h) {
@@ -365,7 +435,7 @@ b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int 
 static b200moby_status run_stage(b200moby_handle h, int stage, const double* q, const double* v, StageOut o, void* stream) {
   if (!h || !q || !v) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
   static bool attr_set = false;
-  if (!attr_set) { B2M_CUDA(cudaFuncSetAttribute(stage_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+  if (!attr_set) { B2M_CUDA(cudaFuncSetAttribute(stage_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX)); attr_set = true; }
   SimParams P = h->P;
   P.q = const_cast<double*>(q); P.v = const_cast<double*>(v);
   stage_warp_kernel<<<h->grid, h->wpb * 32, h->shmem, (cudaStream_t)stream>>>(P, stage, o, h->wpb, h->env_d, h->env_i);

@@ -1,0 +1,10 @@
+// Kernel entry points of the stepped path, one per translation unit; the host side (sim_kernels.cu) launches them
+// through cudaLaunchKernel.  Argument lists are documented next to each kernel.
+#pragma once
+const void* b2m_k_step_warp();            // (SimParams P, double dt, int n_steps, size_t env_d)
+const void* b2m_k_finish();               // (SimParams P, double dt, int round)
+const void* b2m_k_advance();              // (SimParams P, double dt, int round, int wpb)
+const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb)
+const void* b2m_k_impact_block64();
+const void* b2m_k_impact_block128();
+const void* b2m_k_impact_block256();

@@ -73,6 +73,11 @@ class TimeSteppingSimulator:
         """Scheduling knob only (results are identical): see b200moby_set_pivot_budget."""
         capi.check(capi.lib().b200moby_set_pivot_budget(self._h, int(budget)))
 
+    def launch_count(self):
+        n = C.c_longlong()
+        capi.check(capi.lib().b200moby_get_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
     def reset_counters(self):
         capi.check(capi.lib().b200moby_reset_counters(self._h))
 

@@ -48,6 +48,80 @@ int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time
   return nmax;
 }
 
+// The phased step (advance -> impact per LCP class -> ... -> finish) exactly as sim_kernels.cu's launch_step sequences
+// it, each "kernel" a serial loop over its queue.  pivot_budget > 0 exercises the straggler path.
+int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, double* time, double* zlast, int* zlast_n,
+                       unsigned long long* counters, double dt, int n_steps, int rounds, int pivot_budget) {
+  const int ne = d->n_envs, nb = d->n_bodies;
+  int cmax = 0, nmax = 0, npmax = 0;
+  std::vector<int> sh(nb), en(nb), nk(nb * nb);
+  for (int e = 0; e < ne; e++) {
+    for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
+    for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) nk[i * nb + j] = d->NK[((size_t)i * nb + j) * ne + e];
+    int c, n, np; b2m_env_bounds(nb, sh.data(), en.data(), nk.data(), d->impact_model, c, n, np);
+    cmax = std::max(cmax, c); nmax = std::max(nmax, n); npmax = std::max(npmax, np);
+  }
+  cmax = std::max(cmax, 1); nmax = std::max(nmax, 1); npmax = std::max(npmax, 1);
+  std::vector<double> tab = b2m_friction_table();
+  SimParams P; memset(&P, 0, sizeof(P));
+  P.n_envs = ne; P.nb = nb; P.cmax = cmax; P.nmax = nmax; P.npmax = npmax; P.model = d->impact_model;
+  P.shape = d->shape; P.enabled = d->enabled; P.mass = d->mass; P.dims = d->dims; P.inertia = d->inertia;
+  P.mu_c = d->mu_coulomb; P.mu_v = d->mu_viscous; P.eps = d->epsilon; P.compliance = d->compliance; P.NK = d->NK;
+  P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
+  P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
+  P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
+  std::vector<double> hacc(ne), hpend(ne);
+  std::vector<int> queue((size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne), qctl(2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1));
+  P.hacc = hacc.data(); P.hpend = hpend.data(); P.queue = queue.data(); P.qctl = qctl.data();
+  P.pivot_budget = pivot_budget;
+  P.n_classes = b2m_class_table(nmax, cmax, P.model, B2M_MAX_CLASSES, P.class_nmax, P.class_cmax);
+  std::vector<double> wd(env_doubles(nb, cmax, nmax, npmax));
+  std::vector<int> wi(env_ints(nb, cmax, nmax, npmax));
+  SerialGroup g(nullptr);
+  unsigned long long tot[CNT_COUNT]; memset(tot, 0, sizeof(tot));
+  auto add = [&](const unsigned long long* lc) { for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) tot[k] = std::max(tot[k], lc[k]); else tot[k] += lc[k]; } };
+  for (int s = 0; s < n_steps; s++) {
+    std::fill(qctl.begin(), qctl.end(), 0);
+    for (int r = 0; r < rounds; r++) {
+      {   // advance
+        EnvMem m; env_carve_small(m, wd.data(), wi.data(), nb, cmax, npmax);
+        const int count = (r == 0) ? ne : *q_count(P, r - 1, B2M_SLOT_CONT);
+        const int* list = (r == 0) ? nullptr : q_list(P, r - 1, B2M_SLOT_CONT);
+        for (int i = 0; i < count; i++) { unsigned long long lc[CNT_COUNT] = {0}; env_advance(g, P, list ? list[i] : i, m, dt, r, lc); add(lc); }
+      }
+      for (int c = 0; c < P.n_classes; c++) {   // impact, per class, with the class's working-set size
+        SimParams Pc = P; Pc.cmax = P.class_cmax[c]; Pc.nmax = P.class_nmax[c];
+        EnvMem m; env_carve(m, wd.data(), wi.data(), nb, Pc.cmax, Pc.nmax, npmax);
+        const int count = *q_count(P, r, c);
+        const int* list = q_list(P, r, c);
+        for (int i = 0; i < count; i++) {
+          unsigned long long lc[CNT_COUNT] = {0};
+          EnvCtx cx; cx.limit = pivot_budget > 0; cx.budget = pivot_budget;
+          if (env_impact(g, Pc, list[i], m, dt, r, lc, cx)) add(lc);
+        }
+      }
+      if (pivot_budget > 0) {   // stragglers, full working set
+        EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
+        const int count = *q_count(P, r, B2M_SLOT_STRAGGLER);
+        const int* list = q_list(P, r, B2M_SLOT_STRAGGLER);
+        for (int i = 0; i < count; i++) {
+          unsigned long long lc[CNT_COUNT] = {0};
+          EnvCtx cx; cx.limit = false; cx.budget = 0;
+          env_impact(g, P, list[i], m, dt, r, lc, cx); add(lc);
+        }
+      }
+    }
+    {   // finish
+      EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
+      const int count = *q_count(P, rounds - 1, B2M_SLOT_CONT);
+      const int* list = q_list(P, rounds - 1, B2M_SLOT_CONT);
+      for (int i = 0; i < count; i++) { unsigned long long lc[CNT_COUNT] = {0}; env_finish(g, P, list[i], m, dt, lc); add(lc); }
+    }
+  }
+  for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) counters[k] = std::max(counters[k], tot[k]); else counters[k] += tot[k]; }
+  return nmax;
+}
+
 // LCP solvers through the same device code (serial group)
 int hostsim_lcp(int mode, int n, const double* M, const double* q, double* z, int warm, double piv_tol, double zero_tol,
                 int min_exp, int step_exp, int max_exp, int* pivots, int* log, int log_cap, int* log_len) {

@@ -29,6 +29,7 @@ def lib():
     if _lib is None:
         L = C.CDLL(build())
         L.hostsim_run.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+        L.hostsim_run_phased.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int]
         L.hostsim_lcp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -59,6 +60,12 @@ class HostSim:
         t = [p(self.tapMM), p(self.tapqq), p(self.tapz), p(self.tapn)] if self.taps else [None] * 4
         lib().hostsim_run(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
                           dt, n, e0, e1, *t)
+
+    def step_phased(self, dt, n=1, rounds=2, pivot_budget=0):
+        """The same steps through the phased schedule (advance / impact classes / stragglers / finish)."""
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        lib().hostsim_run_phased(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
+                                 dt, n, rounds, pivot_budget)
 
     def counters_dict(self):
         return {k: int(self.counters[i]) for i, k in enumerate(CNT)}

@@ -63,3 +63,32 @@ def test_random_batch_short_horizon(hostsim, oracle):
         worst = max(worst, np.abs(hs.q[:, :, e] - qo).max() / scale, np.abs(hs.v[:, :, e] - vo).max() / scale)
     assert worst < 1e-9, worst
     assert hs.counters_dict()["overflow"] == 0
+
+
+@pytest.mark.parametrize("rounds,budget,min_step", [(1, 0, "scene"), (2, 0, "scene"), (2, 8, "scene"), (3, 0, "default"), (2, 5, "default")])
+def test_phased_schedule_is_bit_identical_to_fused(hostsim, rounds, budget, min_step):
+    """advance / impact-class / straggler / finish phases (the GPU launch schedule) against the fused per-env loop:
+    same bits in q, v, time, warm start and the same counters, whatever the number of rounds or the pivot budget."""
+    sc = scenes.small_lcp_batch(64, seed=11)
+    if min_step == "default":
+        sc.min_step_size_env = None          # sqrt(eps) everywhere: many conservative-advancement mini-steps per step
+    a, b = hostsim.HostSim(sc), hostsim.HostSim(sc)
+    a.step(1e-3, 80)
+    for _ in range(8):
+        b.step_phased(1e-3, 10, rounds=rounds, pivot_budget=budget)
+    assert np.array_equal(a.q, b.q) and np.array_equal(a.v, b.v) and np.array_equal(a.time, b.time)
+    assert np.array_equal(a.zlast_n, b.zlast_n)
+    for e in range(64):
+        assert np.array_equal(a.zlast[:a.zlast_n[e], e], b.zlast[:b.zlast_n[e], e])
+    ca, cb = a.counters_dict(), b.counters_dict()
+    assert ca["lcp_solves"] > 100 and ca["mini_steps"] >= ca["env_steps"] == 64 * 80
+    assert ca == cb, (ca, cb)
+
+
+def test_phased_sphere_stack_multibody(hostsim):
+    sc = scenes.sphere_stack(3)
+    a, b = hostsim.HostSim(sc), hostsim.HostSim(sc)
+    a.step(1e-3, 120)
+    b.step_phased(1e-3, 120, rounds=2, pivot_budget=0)
+    assert np.array_equal(a.q, b.q) and np.array_equal(a.v, b.v)
+    assert a.counters_dict() == b.counters_dict()
