@@ -166,7 +166,8 @@ B2M_DEV int lemke_solve(const G& g, int n, const double* M, int ldm, const doubl
 // bit-identical to the CPU checker.
 // ------------------------------------------------------------------------------------------------
 B2M_HD inline size_t fast_work_doubles(int n) { return (size_t)n * n + 2 * (size_t)n; }
-B2M_HD inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2; }
+#define B2M_FAST_HIST 16   /* basis sets remembered by lcp_fast's cycle detector */
+B2M_HD inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2 + (size_t)(B2M_FAST_HIST + 1) * ((n + 31) / 32); }
 
 // solves A x = b (A k x k column-major ld k, destroyed; b <- x).  Returns false on an exactly zero pivot.
 template <class G>
@@ -204,22 +205,32 @@ B2M_DEV bool lu_solve(const G& g, int k, double* A, double* b) {
 B2M_DEV inline void list_erase(int* L, int& m, int pos) { for (int i = pos; i + 1 < m; i++) L[i] = L[i + 1]; m--; }
 B2M_DEV inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while (i > 0 && L[i - 1] > v) { L[i] = L[i - 1]; i--; } L[i] = v; m++; }
 
+// Cycle detector: one lcp_fast iteration is a pure function of the nonbasic index set (lowest-index tie rule), so a
+// set seen before in this call proves the iteration will repeat until the 2n cap (LCP.cpp:107,192-195).  The call then
+// returns what the reference returns -- failure, z untouched, pivots = 2n -- without spinning through the remaining
+// iterations.  Exact, not heuristic: results and reference-equivalent pivot counts are unchanged; *executed_out says
+// how many iterations really ran.
 template <class G>
 B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
                               bool warm, double* z, double* wd, int* wi, int* pivots_out, int* log, int log_cap,
-                              int* log_len, int* budget = nullptr) {
+                              int* log_len, int* budget = nullptr, int* executed_out = nullptr) {
   double* A = wd;
   double* zz = A + (size_t)n * n;
   double* w = zz + n;
   int* nonbas = wi;
   int* bas = wi + n;
   int* cnt = wi + 2 * n;      // cnt[0] = |nonbas|, cnt[1] = |bas|
-  int nlog = 0;
+  const int W32 = (n + 31) >> 5;
+  unsigned* cur = (unsigned*)(wi + 2 * n + 2);   // bit i set <=> i is nonbasic
+  unsigned* hist = cur + W32;                    // ring of the last B2M_FAST_HIST sets
+  int nlog = 0, nh = 0, executed = 0;
+  if (executed_out) *executed_out = 0;
   if (zero_tol < 0.0) zero_tol = n * norm_inf(g, n, M, ldm, lambda) * B2M_EPS;      // LCP.cpp:57-58
   if (warm) {                                                                        // :65-85
     if (g.tid == 0) {
       int k = 0, nb = 0;
-      for (int i = 0; i < n; i++) { if (fabs(z[i]) < zero_tol) bas[nb++] = i; else nonbas[k++] = i; }
+      for (int i = 0; i < W32; i++) cur[i] = 0u;
+      for (int i = 0; i < n; i++) { if (fabs(z[i]) < zero_tol) bas[nb++] = i; else { nonbas[k++] = i; cur[i >> 5] |= 1u << (i & 31); } }
       cnt[0] = k; cnt[1] = nb;
     }
   } else {                                                                           // :86-103
@@ -232,13 +243,31 @@ B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const do
       g.sync();
       return LCP_TRIVIAL;
     }
-    if (g.tid == 0) { nonbas[0] = idx; int nb = 0; for (int i = 0; i < n; i++) if (i != idx) bas[nb++] = i; cnt[0] = 1; cnt[1] = nb; }
+    if (g.tid == 0) {
+      nonbas[0] = idx; int nb = 0; for (int i = 0; i < n; i++) if (i != idx) bas[nb++] = i; cnt[0] = 1; cnt[1] = nb;
+      for (int i = 0; i < W32; i++) cur[i] = 0u;
+      cur[idx >> 5] |= 1u << (idx & 31);
+    }
   }
   g.sync();
   const int MAX_PIV = 2 * n;                                                         // :107
   int piv = 0, status = LCP_MAXITER;
   for (piv = 0; piv < MAX_PIV; piv++) {
     if (budget && --(*budget) < 0) { status = LCP_DEFER; break; }
+    {   // seen this basis before?  (log == nullptr only: the logged variant is the literal one, used by the pivot-log parity tests)
+      bool rep = false;
+      if (!log) {
+        const int stored = nh < B2M_FAST_HIST ? nh : B2M_FAST_HIST;
+        for (int t = g.tid; t < stored; t += G::size) {
+          bool eq = true;
+          for (int i = 0; i < W32; i++) eq = eq && (hist[t * W32 + i] == cur[i]);
+          rep = rep || eq;
+        }
+      }
+      if (g.any(rep)) { piv = MAX_PIV; break; }
+      if (!log) { for (int i = g.tid; i < W32; i += G::size) hist[(nh % B2M_FAST_HIST) * W32 + i] = cur[i]; nh++; }
+    }
+    executed++;
     const int k = cnt[0], nb = cnt[1];
     for (int e = g.tid; e < k * k; e += G::size) { const int c = e / k, r = e - c * k; A[e] = m_at(M, ldm, nonbas[r], nonbas[c], lambda); }   // :111
     for (int i = g.tid; i < k; i += G::size) zz[i] = -q[nonbas[i]];                  // :113-115
@@ -259,6 +288,7 @@ B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const do
         if (g.tid == 0) {
           int kk = k, nbb = nb; const int idx = nonbas[minz];
           list_erase(nonbas, kk, minz); list_insert_sorted(bas, nbb, idx);
+          cur[idx >> 5] &= ~(1u << (idx & 31));
           cnt[0] = kk; cnt[1] = nbb;
           if (log && nlog < log_cap) log[nlog] = idx | 0x40000000;
         }
@@ -278,10 +308,12 @@ B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const do
       if (g.tid == 0) {
         int kk = k, nbb = nb; const int idx = bas[minw];
         list_erase(bas, nbb, minw); list_insert_sorted(nonbas, kk, idx);
+        cur[idx >> 5] |= 1u << (idx & 31);
         if (log && nlog < log_cap) log[nlog] = idx;
         if (second) {                                                                // :179-188 (position in the NEW list)
           const int idx2 = nonbas[minz];
           list_erase(nonbas, kk, minz); list_insert_sorted(bas, nbb, idx2);
+          cur[idx2 >> 5] &= ~(1u << (idx2 & 31));
           if (log && nlog + 1 < log_cap) log[nlog + 1] = idx2 | 0x40000000;
         }
         cnt[0] = kk; cnt[1] = nbb;
@@ -291,6 +323,7 @@ B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const do
     g.sync();
   }
   if (pivots_out) *pivots_out = piv;
+  if (executed_out) *executed_out = executed;
   if (log_len) *log_len = nlog;
   g.sync();
   return status;
@@ -369,7 +402,8 @@ B2M_DEV inline double pow10i(int e) {
   }
 }
 
-// lcp_fast_regularized (LCP.cpp:212-350).  stats[0] += lcp_fast calls, stats[1] += pivots (thread 0 only, may be NULL).
+// lcp_fast_regularized (LCP.cpp:212-350).  stats[0] += lcp_fast calls, stats[1] += pivots as the
+// reference counts them, stats[2] += iterations actually executed (thread 0 only, may be NULL).
 template <class G>
 B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, const double* q, double zero_tol, bool warm,
                                     int min_exp, int step_exp, int max_exp, double* z, double* wd, int* wi,
@@ -377,12 +411,12 @@ B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, co
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
   const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :228
   double* wv = wd + (size_t)n * n + n;   // the solver's w vector doubles as verification scratch
-  int total = 0, piv = 0;
-  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
+  int total = 0, piv = 0, ex = 0;
+  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex);
   if (st == LCP_DEFER) return st;
   bool zvalid = warm || st == LCP_OK || st == LCP_TRIVIAL;   // z.size()==n in the reference (LCP.cpp:65): warm start of the retries
   total += piv;
-  if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+  if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }
   if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, wv)) {
     if (pivots_out) *pivots_out = piv;   // reference leaves `pivots` at the last solve's count here (:252-255)
     return st;
@@ -391,11 +425,11 @@ B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, co
   for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :281-340
     const double lambda = pow10i(rf);
     g.sync();
-    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
+    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex);
     if (st == LCP_DEFER) return st;
     zvalid = zvalid || st == LCP_OK || st == LCP_TRIVIAL;
     total += piv;
-    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }
     if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, lambda, z, ZERO_TOL, true, wv)) {
       if (pivots_out) *pivots_out = total;
       return LCP_REGULARIZED + attempt;
@@ -417,7 +451,7 @@ B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, c
   int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
   if (st == LCP_DEFER) return st;
   total += piv;
-  if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+  if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += piv; }
   if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, wv)) {
     if (pivots_out) *pivots_out = piv;
     return st;
@@ -429,7 +463,7 @@ B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, c
     st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget);
     if (st == LCP_DEFER) return st;
     total += piv;
-    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; }
+    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += piv; }
     if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, lambda, z, ZERO_TOL, true, wv)) {
       if (pivots_out) *pivots_out = total;
       return LCP_REGULARIZED + attempt;

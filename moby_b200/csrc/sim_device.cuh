@@ -833,24 +833,24 @@ B2M_DEV bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
   const bool warm = (m.scal[S_ZLN] == n);                                           // :158-162 with rule H1 (zero fill)
   for (int i = g.tid; i < n; i += G::size) m.z[i] = warm ? m.zl[i] : 0.0;
   g.sync();
-  long long stats[2] = {0, 0};
+  long long stats[3] = {0, 0, 0};
   int piv = 0;
   int* bud = cx.limit ? &cx.budget : nullptr;
   int st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats, bud);   // :219
   if (st == LCP_DEFER) return false;
-  long long fast_calls = stats[0], pivots = stats[1], lemke_calls = 0;
+  long long fast_calls = stats[0], pivots = stats[1], executed = stats[2], lemke_calls = 0;
   if (st == LCP_UNVERIFIED) {
     g.sync();
-    stats[0] = stats[1] = 0;
+    stats[0] = stats[1] = stats[2] = 0;
     st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);      // :222-225
     if (st == LCP_DEFER) return false;
-    lemke_calls = stats[0]; pivots += stats[1];
+    lemke_calls = stats[0]; pivots += stats[1]; executed += stats[2];
     if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
   }
   g.sync();
   if (g.tid == 0) {
     lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
-    lc[CNT_PIVOT_FLOPS] += (unsigned long long)pivots * 2ull * n * (n + 1);
+    lc[CNT_PIVOT_FLOPS] += (unsigned long long)executed * 2ull * n * (n + 1);   // iterations that really ran (cycle detector)
     if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
     m.scal[S_ZLN] = n; m.scal[S_ZLDIRTY] = 1;
   }
@@ -903,7 +903,7 @@ B2M_DEV bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
   const int NC = m.scal[S_NC];
   const int n = build_ap_lcp(g, P, m);
   if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * NC; t += G::size) m.imp[t] = 0.0; g.sync(); return true; }
-  long long stats[2] = {0, 0};
+  long long stats[3] = {0, 0, 0};
   int piv = 0;
   int st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, -2, m.z, m.work, m.iwork, &piv, stats, cx.limit ? &cx.budget : nullptr);   // :333
   if (st == LCP_DEFER) return false;
