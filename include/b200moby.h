@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200MOBY_ABI_VERSION 1
+#define B200MOBY_ABI_VERSION 2
 
 typedef enum {
   B200MOBY_OK = 0,
@@ -61,6 +61,43 @@ enum {
 };
 
 #define B200MOBY_MAX_BODIES 16
+#define B200MOBY_MAX_LINKS 16
+
+/* Joint types of a reduced-coordinate articulated body (RevoluteJoint.cpp, PrismaticJoint.cpp): one DoF each. */
+enum { B200MOBY_JOINT_REVOLUTE = 1, B200MOBY_JOINT_PRISMATIC = 2 };
+
+/* Forward-dynamics algorithm of the articulated body (RCArticulatedBody.cpp:178-201 fdyn-algorithm=). */
+enum {
+  B200MOBY_FDYN_FSAB = 0,  /* Featherstone articulated-body algorithm, O(N) */
+  B200MOBY_FDYN_CRB = 1    /* composite rigid body + Cholesky, O(N^3): what SDFReader.cpp:931-935 wires for the UR10 */
+};
+
+/*
+ * One fixed-base RCArticulatedBody per env (include/Moby/RCArticulatedBody.h:43; dynamics in Ravelin's
+ * RCArticulatedBodyd).  Its links are bodies [first_body, first_body + n_links) of the scene: link 0 is the base
+ * (a disabled body, welded to the world at the pose b200moby_set_state gives it), link i > 0 hangs off
+ * parent[i] < i by a one-DoF joint whose coordinate is jq[i-1].  Link body frames sit at the link's centre of mass
+ * with axes along the principal inertia axes (shape / dims / mass / inertia / contact parameters come from the body
+ * arrays of the scene descriptor, so they may differ per env); the kinematic tree below is shared by all envs.
+ * Joint limits and floating bases are outside this round's scope.
+ * All arrays are host pointers of n_links entries (entry 0 unused), copied at create time.
+ */
+typedef struct {
+  int n_links;
+  int first_body;
+  const int*    parent;      /* [link] */
+  const int*    joint_type;  /* [link] B200MOBY_JOINT_* */
+  const double* joint_axis;  /* [link][3] unit axis in the outboard link's frame */
+  const double* loc_parent;  /* [link][3] joint location in the inboard link's (COM) frame */
+  const double* loc_child;   /* [link][3] joint location in the outboard link's (COM) frame */
+  const double* rel_quat;    /* [link][4] outboard orientation relative to inboard at q = 0 (x y z w) */
+  int fdyn_algorithm;        /* B200MOBY_FDYN_* used by the stepped path */
+  /* Built-in joint-space controller standing in for the ControlledBody callback (ControlledBody.h:37-40,
+   * Simulator.cpp:339-348) with the law of example/ur10/controller.cpp:46-96:
+   *   tau_k = kp_k (amp_k sin(freq_k t) - q_k) + kv_k (amp_k cos(freq_k t) - qd_k),  t = Simulator::current_time.
+   * [dof] arrays, NULL kp = no controller.  b200moby_set_joint_forces adds a per-env feed-forward term. */
+  const double* ctrl_kp; const double* ctrl_kv; const double* ctrl_amp; const double* ctrl_freq;
+} b200moby_rc_desc;
 
 /*
  * Batch scene descriptor: `n_bodies` rigid bodies per env (static ones
@@ -93,6 +130,7 @@ typedef struct {
   const double* min_step_size_env; /* optional [env] override (XML min-step-size, TimeSteppingSimulator.cpp:470-472); NULL = scalar above */
   int    impact_model;          /* B200MOBY_MODEL_* */
   int    stabilization_max_iterations; /* must be 0 this round */
+  const b200moby_rc_desc* rc;   /* optional articulated body (NULL: free bodies only) */
 } b200moby_scene_desc;
 
 typedef struct b200moby_sim* b200moby_handle;
@@ -129,6 +167,16 @@ b200moby_status b200moby_get_state(b200moby_handle h, double* q, double* v);
 /* Same with device buffers (no host round trip). */
 b200moby_status b200moby_set_state_dev(b200moby_handle h, const double* q_dev, const double* v_dev, void* stream);
 b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q_dev, double* v_dev, void* stream);
+/* Joint state of the articulated body, [dof][env] (RCArticulatedBodyd::get/set_generalized_coordinates_euler /
+ * _velocity for a fixed base: the joint q and qd).  Setting it refreshes the link poses and velocities that
+ * b200moby_get_state reports.  INVALID when the scene has no articulated body. */
+b200moby_status b200moby_set_joint_state(b200moby_handle h, const double* jq, const double* jqd);
+b200moby_status b200moby_get_joint_state(b200moby_handle h, double* jq, double* jqd);
+b200moby_status b200moby_set_joint_state_dev(b200moby_handle h, const double* jq_dev, const double* jqd_dev, void* stream);
+b200moby_status b200moby_get_joint_state_dev(b200moby_handle h, double* jq_dev, double* jqd_dev, void* stream);
+/* Generalized joint forces added every mini-step until changed, [dof][env] host buffer (what a ControlledBody
+ * controller callback returns, Simulator.cpp:339-348); NULL clears them. */
+b200moby_status b200moby_set_joint_forces(b200moby_handle h, const double* tau);
 /* n_steps x step(dt) for every env; asynchronous on `stream`. */
 b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* stream);
 /* Scheduling knob (results do not depend on it): an env whose LCP pivots within one b200moby_step call exceed
@@ -144,6 +192,10 @@ b200moby_status b200moby_get_time(b200moby_handle h, double* t);
 /* Debug tap: LCP of the last impact solve of each env. MM_dev: [env][nmax*nmax] column-major with
  * leading dimension n[env]; any pointer may be NULL. */
 b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int zcap);
+
+/* Debug tap: SM cycles, pivots, executed solver iterations and LCP dimension of each env's most recent impact phase,
+ * prof: host buffer [4][env]; reading clears it.  The first call arms the tap. */
+b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof);
 
 /* ---- batched solvers: replace LCP::lcp_lemke / lcp_fast and wrappers (LCP.h:21-27) ----
  * M_dev [batch][n*n] column-major, q_dev [batch][n], z_dev [batch][n] (in: warm start for lcp_fast, out: solution),
@@ -183,6 +235,13 @@ b200moby_status b200moby_lcp_solve_host(int mode, int batch, int n, const double
 /* Forward dynamics + velocity half of semi-implicit Euler for free rigid bodies
  * (Simulator.cpp:319-350,482-602; TimeSteppingSimulator.cpp:181-192). q_dev [body][7][env], v_dev [body][6][env] in/out. */
 b200moby_status b200moby_fwd_dyn_batched(b200moby_handle h, const double* q_dev, double* v_dev, double dt, void* stream);
+/* Forward dynamics of the articulated body, one thread per env with the spatial recursions in registers
+ * (Simulator.cpp:544-553 -> RCArticulatedBodyd::calc_fwd_dyn; algorithm: B200MOBY_FDYN_*).
+ * jq_dev, jqd_dev, tau_dev (may be NULL), qdd_dev: [dof][env]. */
+b200moby_status b200moby_rc_fwd_dyn_batched(b200moby_handle h, int algorithm, const double* jq_dev, const double* jqd_dev,
+                                            const double* tau_dev, double* qdd_dev, void* stream);
+/* Joint-space inertia H(q) (RCArticulatedBodyd::get_generalized_inertia), H_dev [dof*dof][env] column-major. */
+b200moby_status b200moby_rc_inertia_batched(b200moby_handle h, const double* jq_dev, double* H_dev, void* stream);
 /* Narrowphase for every body pair (CCD.inl:3-82 and leaves). Outputs, per env, up to `cap` contacts:
  * count_dev [env]; point/normal/tan1/tan2 [cap][3][env]; pair_dev [cap][env] = body1*n_bodies+body2; dist_dev [cap][env]. */
 b200moby_status b200moby_find_contacts_batched(b200moby_handle h, const double* q_dev, const double* v_dev, int cap, int* count_dev,

@@ -10,6 +10,19 @@ class B200MobyError(RuntimeError):
     pass
 
 
+class RcDesc(C.Structure):
+    """b200moby_rc_desc: the fixed-base articulated body of each env."""
+    _fields_ = [
+        ("n_links", C.c_int), ("first_body", C.c_int),
+        ("parent", C.POINTER(C.c_int)), ("joint_type", C.POINTER(C.c_int)),
+        ("joint_axis", C.POINTER(C.c_double)), ("loc_parent", C.POINTER(C.c_double)), ("loc_child", C.POINTER(C.c_double)),
+        ("rel_quat", C.POINTER(C.c_double)),
+        ("fdyn_algorithm", C.c_int),
+        ("ctrl_kp", C.POINTER(C.c_double)), ("ctrl_kv", C.POINTER(C.c_double)), ("ctrl_amp", C.POINTER(C.c_double)),
+        ("ctrl_freq", C.POINTER(C.c_double)),
+    ]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int), ("n_bodies", C.c_int),
@@ -20,6 +33,7 @@ class SceneDesc(C.Structure):
         ("gravity", C.c_double * 3), ("contact_dist_thresh", C.c_double), ("min_step_size", C.c_double),
         ("min_step_size_env", C.POINTER(C.c_double)),
         ("impact_model", C.c_int), ("stabilization_max_iterations", C.c_int),
+        ("rc", C.POINTER(RcDesc)),
     ]
 
 
@@ -38,9 +52,12 @@ SYMBOLS = [
     "b200moby_create", "b200moby_destroy", "b200moby_set_state", "b200moby_get_state",
     "b200moby_set_state_dev", "b200moby_get_state_dev", "b200moby_step", "b200moby_set_pivot_budget", "b200moby_get_counters",
     "b200moby_reset_counters", "b200moby_get_launch_count", "b200moby_get_time", "b200moby_get_last_lcp",
+    "b200moby_get_impact_profile",
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
     "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host", "b200moby_lcp_solve_host",
     "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_delassus_batched",
+    "b200moby_set_joint_state", "b200moby_get_joint_state", "b200moby_set_joint_state_dev", "b200moby_get_joint_state_dev",
+    "b200moby_set_joint_forces", "b200moby_rc_fwd_dyn_batched", "b200moby_rc_inertia_batched",
 ]
 
 _lib = None
@@ -70,6 +87,7 @@ def lib():
     L.b200moby_get_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     L.b200moby_get_time.argtypes = [C.c_void_p, dp]
     L.b200moby_get_last_lcp.argtypes = [C.c_void_p, ip, dp, C.c_int]
+    L.b200moby_get_impact_profile.argtypes = [C.c_void_p, ip]
     L.b200moby_lcp_lemke_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, ip, ip, ip, C.c_int, vp]
     L.b200moby_lcp_fast_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, ip, ip, ip, C.c_int, vp]
     L.b200moby_lcp_lemke_regularized_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_int, C.c_int,
@@ -83,6 +101,13 @@ def lib():
     L.b200moby_fwd_dyn_batched.argtypes = [C.c_void_p, dp, dp, C.c_double, vp]
     L.b200moby_find_contacts_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, ip, dp, dp, dp, dp, ip, dp, vp]
     L.b200moby_delassus_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, ip, vp]
+    L.b200moby_set_joint_state.argtypes = [C.c_void_p, dp, dp]
+    L.b200moby_get_joint_state.argtypes = [C.c_void_p, dp, dp]
+    L.b200moby_set_joint_state_dev.argtypes = [C.c_void_p, dp, dp, vp]
+    L.b200moby_get_joint_state_dev.argtypes = [C.c_void_p, dp, dp, vp]
+    L.b200moby_set_joint_forces.argtypes = [C.c_void_p, dp]
+    L.b200moby_rc_fwd_dyn_batched.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, dp, vp]
+    L.b200moby_rc_inertia_batched.argtypes = [C.c_void_p, dp, dp, vp]
     _lib = L
     return L
 

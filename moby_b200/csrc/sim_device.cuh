@@ -10,6 +10,7 @@
 // touches HBM only for its state (13 doubles per body in and out) and its warm-start vector.
 #pragma once
 #include "lcp_device.cuh"
+#include "rc_device.cuh"
 
 namespace b2m {
 
@@ -61,6 +62,10 @@ struct SimParams {
   int n_classes; int class_nmax[B2M_MAX_CLASSES]; int class_cmax[B2M_MAX_CLASSES];
   // debug taps (may be null)
   double* tap_MM; double* tap_qq; double* tap_z; int* tap_n;
+  // reduced-coordinate articulated body (null / 0 when the scene has none)
+  const RCTree* rc; int rc_links, rc_first;
+  double* jq; double* jqd; const double* jtau;   // [dof][env]
+  long long* tap_prof;         // [4][env]: SM cycles, pivots, executed iterations, LCP n of the env's last impact phase
 };
 
 // Per-env working set carved out of one contiguous block of doubles + ints (shared memory for warp groups).
@@ -1159,6 +1164,10 @@ B2M_DEV void env_advance(const G& g, const SimParams& P, int e, EnvMem& m, doubl
 // (nothing stored; it is queued for the straggler kernel).
 template <class G>
 B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int round, unsigned long long* lc, EnvCtx& cx) {
+#ifdef __CUDA_ARCH__
+  const long long t0 = P.tap_prof ? clock64() : 0;
+#endif
+  const unsigned long long p0 = lc[CNT_PIVOTS], f0 = lc[CNT_PIVOT_FLOPS];
   env_load(g, P, e, m);
   const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
   calc_pairwise_distances(g, m);
@@ -1178,6 +1187,14 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
     P.time[e] = P.time[e] + hh;
     if (h < dt) { P.hacc[e] = h; q_push(P, round, B2M_SLOT_CONT, e); }
     else lc[CNT_ENV_STEPS]++;
+#ifdef __CUDA_ARCH__
+    if (P.tap_prof) {
+      const size_t ne = P.n_envs;
+      const long long n = m.scal[S_N];
+      P.tap_prof[e] = clock64() - t0; P.tap_prof[ne + e] = (long long)(lc[CNT_PIVOTS] - p0);
+      P.tap_prof[2 * ne + e] = n > 0 ? (long long)((lc[CNT_PIVOT_FLOPS] - f0) / (2ull * n * (n + 1))) : 0; P.tap_prof[3 * ne + e] = n;
+    }
+#endif
   }
   g.sync();
   return true;

@@ -10,6 +10,7 @@
 #include "host_util.h"
 #include "sim_device.cuh"
 #include "sim_launch.h"
+#include "rc_host.h"
 
 using namespace b2m;
 
@@ -39,6 +40,13 @@ struct b200moby_sim {
   int fin_grid = 1;
   bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
   long long launches = 0;
+  // the impact classes of one round touch disjoint envs: they run on side streams so that the tail of one class
+  // (a few envs with very long pivot sequences) overlaps the other classes' work
+  bool concurrent = true;
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> side_done;
+  cudaEvent_t fork = nullptr;
+  int rc_links = 0, rc_dof = 0;   // articulated body (0: none)
 };
 
 namespace {
@@ -225,18 +233,23 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
   for (int r = 0; r < h->rounds; r++) {
     { void* a[] = {&P, &dt, &r, &h->adv_wpb};
       B2M_CUDA(cudaLaunchKernel(b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)); h->launches++; }
+    const bool conc = h->concurrent && h->classes.size() > 1;
+    if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
     for (size_t c = 0; c < h->classes.size(); c++) {
       ClassPlan& cp = h->classes[c];
       SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax;
       int slot = (int)c;
+      cudaStream_t sc = conc ? h->side[c] : s;
+      if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
       if (cp.threads == 32) {
         void* a[] = {&Pc, &dt, &r, &slot, &cp.wpb};
-        B2M_CUDA(cudaLaunchKernel(b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, s));
+        B2M_CUDA(cudaLaunchKernel(b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc));
       } else {
         Pc.pivot_budget = 0;
         void* a[] = {&Pc, &dt, &r, &slot};
-        B2M_CUDA(cudaLaunchKernel(impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, s));
+        B2M_CUDA(cudaLaunchKernel(impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc));
       }
+      if (conc) { B2M_CUDA(cudaEventRecord(h->side_done[c], sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->side_done[c], 0)); }
       h->launches++;
     }
     if (P.pivot_budget > 0) {
@@ -313,7 +326,35 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne, &P.queue));
   TRY(dev_zero(h, (size_t)2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1), &P.qctl));
   P.pivot_budget = env_int("B200MOBY_PIVOT_BUDGET", 96);
+  if (d->rc && d->rc->n_links > 0) {
+    const b200moby_rc_desc& r = *d->rc;
+    RCTree T; bool unsup = false;
+    if (const char* err = b2m_rc_tree_from_desc(r, nb, T, &unsup)) { b200moby_destroy(h); return b2m_fail(unsup ? B200MOBY_ERR_UNSUPPORTED : B200MOBY_ERR_INVALID, "%s", err); }
+    for (int e = 0; e < ne; e++) {
+      if (d->enabled[(size_t)r.first_body * ne + e]) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "articulated body: floating bases are not on the accelerated path; the base link must be a disabled body"); }
+      for (int i = 1; i < r.n_links; i++) if (!d->enabled[(size_t)(r.first_body + i) * ne + e]) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_INVALID, "articulated body: link %d is disabled", i); }
+    }
+    TRY(dev_copy(h, &T, 1, &P.rc));
+    P.rc_links = r.n_links; P.rc_first = r.first_body;
+    h->rc_links = r.n_links; h->rc_dof = r.n_links - 1;
+    TRY(dev_zero(h, (size_t)h->rc_dof * ne, &P.jq));
+    TRY(dev_zero(h, (size_t)h->rc_dof * ne, &P.jqd));
+    double* tau0 = nullptr;
+    TRY(dev_zero(h, (size_t)h->rc_dof * ne, &tau0));
+    P.jtau = tau0;
+  }
   TRY(plan_launch(h));
+  h->concurrent = env_int("B200MOBY_CONCURRENT", 1) != 0;
+  if (h->concurrent) {
+    h->side.resize(h->classes.size()); h->side_done.resize(h->classes.size());
+    for (size_t c = 0; c < h->classes.size(); c++) { h->side[c] = nullptr; h->side_done[c] = nullptr; }
+    for (size_t c = 0; c < h->classes.size(); c++) {
+      if (cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->side_done[c], cudaEventDisableTiming) != cudaSuccess) {
+        b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the impact-class streams");
+      }
+    }
+    if (cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the fork event"); }
+  }
 #undef TRY
   *out = h;
   return B200MOBY_OK;
@@ -322,6 +363,9 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
 b200moby_status b200moby_destroy(b200moby_handle h) {
   if (!h) return B200MOBY_OK;
   cudaSetDevice(h->device);
+  for (cudaStream_t st : h->side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaEvent_t ev : h->side_done) if (ev) cudaEventDestroy(ev);
+  if (h->fork) cudaEventDestroy(h->fork);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return B200MOBY_OK;
@@ -355,6 +399,69 @@ b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q, double* v, 
   if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
   if (q) B2M_CUDA(cudaMemcpyAsync(q, h->P.q, sizeof(double) * h->nb * 7 * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (v) B2M_CUDA(cudaMemcpyAsync(v, h->P.v, sizeof(double) * h->nb * 6 * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B200MOBY_OK;
+}
+
+static b200moby_status rc_refresh(b200moby_handle h, cudaStream_t s) {
+  void* a[] = {&h->P};
+  B2M_CUDA(cudaLaunchKernel(b2m_k_rc_refresh(), dim3((h->n_envs + 127) / 128), dim3(128), a, 0, s));
+  h->launches++;
+  return B200MOBY_OK;
+}
+b200moby_status b200moby_set_joint_state(b200moby_handle h, const double* jq, const double* jqd) {
+  if (!h || !jq || !jqd) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  B2M_CUDA(cudaSetDevice(h->device));
+  B2M_CUDA(cudaMemcpy(h->P.jq, jq, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyHostToDevice));
+  B2M_CUDA(cudaMemcpy(h->P.jqd, jqd, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyHostToDevice));
+  return rc_refresh(h, 0);
+}
+b200moby_status b200moby_get_joint_state(b200moby_handle h, double* jq, double* jqd) {
+  if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  B2M_CUDA(cudaSetDevice(h->device));
+  if (jq) B2M_CUDA(cudaMemcpy(jq, h->P.jq, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToHost));
+  if (jqd) B2M_CUDA(cudaMemcpy(jqd, h->P.jqd, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToHost));
+  return B200MOBY_OK;
+}
+b200moby_status b200moby_set_joint_state_dev(b200moby_handle h, const double* jq, const double* jqd, void* stream) {
+  if (!h || !jq || !jqd) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  B2M_CUDA(cudaMemcpyAsync(h->P.jq, jq, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  B2M_CUDA(cudaMemcpyAsync(h->P.jqd, jqd, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return rc_refresh(h, (cudaStream_t)stream);
+}
+b200moby_status b200moby_get_joint_state_dev(b200moby_handle h, double* jq, double* jqd, void* stream) {
+  if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  if (jq) B2M_CUDA(cudaMemcpyAsync(jq, h->P.jq, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (jqd) B2M_CUDA(cudaMemcpyAsync(jqd, h->P.jqd, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B200MOBY_OK;
+}
+b200moby_status b200moby_set_joint_forces(b200moby_handle h, const double* tau) {
+  if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  B2M_CUDA(cudaSetDevice(h->device));
+  if (tau) B2M_CUDA(cudaMemcpy(const_cast<double*>(h->P.jtau), tau, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyHostToDevice));
+  else B2M_CUDA(cudaMemset(const_cast<double*>(h->P.jtau), 0, sizeof(double) * h->rc_dof * h->n_envs));
+  return B200MOBY_OK;
+}
+b200moby_status b200moby_rc_fwd_dyn_batched(b200moby_handle h, int algorithm, const double* jq, const double* jqd, const double* tau,
+                                            double* qdd, void* stream) {
+  if (!h || !jq || !jqd || !qdd) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  if (algorithm != B200MOBY_FDYN_FSAB && algorithm != B200MOBY_FDYN_CRB) return b2m_fail(B200MOBY_ERR_INVALID, "unknown forward-dynamics algorithm %d", algorithm);
+  void* a[] = {&h->P, &algorithm, &jq, &jqd, &tau, &qdd};
+  B2M_CUDA(cudaLaunchKernel(b2m_k_rc_fwd_dyn(), dim3((h->n_envs + 127) / 128), dim3(128), a, 0, (cudaStream_t)stream));
+  h->launches++;
+  return B200MOBY_OK;
+}
+b200moby_status b200moby_rc_inertia_batched(b200moby_handle h, const double* jq, double* H, void* stream) {
+  if (!h || !jq || !H) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  void* a[] = {&h->P, &jq, &H};
+  B2M_CUDA(cudaLaunchKernel(b2m_k_rc_inertia(), dim3((h->n_envs + 127) / 128), dim3(128), a, 0, (cudaStream_t)stream));
+  h->launches++;
   return B200MOBY_OK;
 }
 
@@ -429,6 +536,17 @@ b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int 
     B2M_CUDA(cudaMemcpy(tmp.data(), h->P.tap_z, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
     for (int e = 0; e < h->n_envs; e++) for (int i = 0; i < zcap; i++) z[(size_t)e * zcap + i] = (i < h->nmax) ? tmp[(size_t)e * h->nmax + i] : 0.0;
   }
+  return B200MOBY_OK;
+}
+
+// Debug tap: per-env SM cycles, pivots, executed iterations and LCP dimension of the last impact phase; prof is a host
+// buffer [4][env].  The first call arms the tap (and returns zeros).
+b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof) {
+  if (!h || !prof) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  B2M_CUDA(cudaSetDevice(h->device));
+  if (!h->P.tap_prof) { b200moby_status st; if ((st = dev_zero(h, (size_t)4 * h->n_envs, &h->P.tap_prof)) != B200MOBY_OK) return st; }
+  B2M_CUDA(cudaMemcpy(prof, h->P.tap_prof, sizeof(long long) * 4 * h->n_envs, cudaMemcpyDeviceToHost));
+  B2M_CUDA(cudaMemset(h->P.tap_prof, 0, sizeof(long long) * 4 * h->n_envs));
   return B200MOBY_OK;
 }
 

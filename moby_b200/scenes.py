@@ -9,10 +9,12 @@ import math
 
 import numpy as np
 
-from .capi import SceneDesc
+from .capi import RcDesc, SceneDesc
 
 SHAPE_NONE, SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE = 0, 1, 2, 3
 MODEL_QP, MODEL_AP = 0, 1
+JOINT_REVOLUTE, JOINT_PRISMATIC = 1, 2
+FDYN_FSAB, FDYN_CRB = 0, 1
 NEAR_ZERO = math.sqrt(np.finfo(np.float64).eps)  # Constants.h:21
 
 
@@ -48,6 +50,7 @@ class SceneBatch:
         self.q[:, 6, :] = 1.0
         self.v = np.zeros((nb, 6, ne), np.float64)
         self.name = "custom"
+        self.rc = None                        # optional ArticulatedBody
 
     # ---- primitives (InertiaFromPrimitive: BoxPrimitive / SpherePrimitive::calc_mass_properties) ----
     def set_box(self, b, xlen, ylen, zlen, density=None, mass=None, envs=slice(None)):
@@ -102,8 +105,69 @@ class SceneBatch:
             a = np.ascontiguousarray(self.min_step_size_env, np.float64)
             keep.append(a)
             d.min_step_size_env = a.ctypes.data_as(C.POINTER(C.c_double))
+        if self.rc is not None:
+            rd = self.rc.cdesc()
+            keep.append(rd)
+            d.rc = C.pointer(rd)
         d._keep = keep
         return d
+
+
+class ArticulatedBody:
+    """Fixed-base reduced-coordinate body (Moby RCArticulatedBody) whose links are bodies
+    [first_body, first_body + n_links) of `scene`; mirrors b200moby_rc_desc.  Link body frames are COM frames with
+    principal axes; joint k = link k+1's inboard joint.  jq / jqd: [dof][env] initial joint state."""
+
+    def __init__(self, scene, first_body, n_links, fdyn=FDYN_FSAB):
+        self.scene, self.first_body, self.n_links = scene, first_body, n_links
+        self.parent = np.zeros(n_links, np.int32)
+        self.joint_type = np.full(n_links, JOINT_REVOLUTE, np.int32)
+        self.joint_axis = np.zeros((n_links, 3)); self.joint_axis[:, 2] = 1.0
+        self.loc_parent = np.zeros((n_links, 3))
+        self.loc_child = np.zeros((n_links, 3))
+        self.rel_quat = np.zeros((n_links, 4)); self.rel_quat[:, 3] = 1.0
+        self.fdyn = fdyn
+        self.ctrl = None                      # (kp, kv, amp, freq), each [dof]
+        nd = n_links - 1
+        self.jq = np.zeros((nd, scene.n_envs))
+        self.jqd = np.zeros((nd, scene.n_envs))
+        scene.enabled[first_body, :] = 0      # the base is welded to the world
+        scene.rc = self
+
+    @property
+    def n_dof(self):
+        return self.n_links - 1
+
+    def set_joint(self, link, parent, jtype, axis, loc_parent, loc_child, rel_quat=(0, 0, 0, 1)):
+        self.parent[link], self.joint_type[link] = parent, jtype
+        self.joint_axis[link], self.loc_parent[link], self.loc_child[link], self.rel_quat[link] = axis, loc_parent, loc_child, rel_quat
+
+    def set_controller(self, kp, kv, amp, freq):
+        self.ctrl = tuple(np.ascontiguousarray(a, np.float64) for a in (kp, kv, amp, freq))
+
+    def cdesc(self):
+        d = RcDesc()
+        d.n_links, d.first_body, d.fdyn_algorithm = self.n_links, self.first_body, self.fdyn
+        keep = []
+        for name, ct in (("parent", C.c_int), ("joint_type", C.c_int), ("joint_axis", C.c_double), ("loc_parent", C.c_double),
+                         ("loc_child", C.c_double), ("rel_quat", C.c_double)):
+            a = np.ascontiguousarray(getattr(self, name), np.int32 if ct is C.c_int else np.float64)
+            keep.append(a)
+            setattr(d, name, a.ctypes.data_as(C.POINTER(ct)))
+        if self.ctrl is not None:
+            for name, a in zip(("ctrl_kp", "ctrl_kv", "ctrl_amp", "ctrl_freq"), self.ctrl):
+                keep.append(a)
+                setattr(d, name, a.ctypes.data_as(C.POINTER(C.c_double)))
+        d._keep = keep
+        return d
+
+    def env_mass_props(self, env):
+        """(mass [link], J [link][3], base pose [7]) of env `env` (what the oracle / host-compiled checks take)."""
+        b0, nl, sc = self.first_body, self.n_links, self.scene
+        mass = np.ascontiguousarray(sc.mass[b0:b0 + nl, env], np.float64)
+        J = np.ascontiguousarray(sc.inertia[b0:b0 + nl, :, env], np.float64)
+        pose = np.ascontiguousarray(sc.q[b0, :, env], np.float64)
+        return mass, J, pose
 
 
 # ---------------- the scenes of SURVEY.md 8(d) ----------------
@@ -197,3 +261,137 @@ def _rotmat(q):
     return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def quat_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def quat_conj(a):
+    return np.array([-a[0], -a[1], -a[2], a[3]])
+
+
+def pendulum(n_envs=1, fdyn=FDYN_FSAB):
+    """example/reduced-coords/pendulum.xml: fixed base + one link (mass 1, sphere inertia r=1.5811) on a revolute joint
+    about z at the origin, link COM at distance 1 from the joint, q = pi/2, qd = 100 in the file (tests override)."""
+    s = SceneBatch(n_envs, 2)
+    s.name = "pendulum"
+    for b in range(2):
+        s.mass[b, :] = 1.0
+        s.inertia[b, :, :] = 0.4 * 1.5811 ** 2
+    rc = ArticulatedBody(s, 0, 2, fdyn)
+    rc.set_joint(1, 0, JOINT_REVOLUTE, (0, 0, 1), (0, 0, 0), (-1.0, 0, 0))
+    return s
+
+
+def chain(n_envs=1, n_links=5, fdyn=FDYN_FSAB, seed=1, branch=False):
+    """A randomised fixed-base chain (or tree when `branch`) of revolute and prismatic joints with skew axes: the
+    forward-dynamics parity workload (no geometry).  Gravity (0,-9.81,0)."""
+    rng = np.random.default_rng(seed)
+    s = SceneBatch(n_envs, n_links)
+    s.name = "chain"
+    rc = ArticulatedBody(s, 0, n_links, fdyn)
+    for i in range(n_links):
+        s.mass[i, :] = rng.uniform(0.5, 2.0, n_envs)
+        s.inertia[i, :, :] = rng.uniform(0.01, 0.2, (3, n_envs))
+    for i in range(1, n_links):
+        parent = int(rng.integers(0, i)) if branch else i - 1
+        jt = JOINT_PRISMATIC if (i % 4 == 3) else JOINT_REVOLUTE
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        qr = rng.normal(size=4)
+        qr /= np.linalg.norm(qr)
+        rc.set_joint(i, parent, jt, ax, rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3), qr)
+    rc.jq[:] = rng.uniform(-1.0, 1.0, rc.jq.shape)
+    rc.jqd[:] = rng.uniform(-2.0, 2.0, rc.jqd.shape)
+    return s
+
+
+# example/ur10/model.sdf:5-524 -- link pose (xyz rpy, model frame), COM offset in the link frame, mass, (ixx, iyy, izz)
+_UR10_LINKS = [
+    ("base_link",      (0, 0, 0, 0, 0, 0),                                   (0, 0, 0),        4.0,   (0.00610633, 0.00610633, 0.01125)),
+    ("shoulder_link",  (0, 0, 0.1273, 0, 0, 0),                              (0, 0, 0),        7.778, (0.0314743, 0.0314743, 0.0218756)),
+    ("upper_arm_link", (0, 0.220941, 0.1273, 3.14159, 1.57079, 3.14159),     (0, 0, 0.306),    12.93, (0.421754, 0.421754, 0.0363656)),
+    ("forearm_link",   (0.612, 0.049041, 0.1273, 3.14159, 1.57079, 3.14159), (0, 0, 0.28615),  3.87,  (0.11107, 0.11107, 0.0108844)),
+    ("wrist_1_link",   (1.1843, 0.049041, 0.1273, 3.14159, 3.58979e-09, 3.14159), (0, 0, 0),   1.96,  (0.00510825, 0.00510825, 0.0055125)),
+    ("wrist_2_link",   (1.1843, 0.163941, 0.1273, 3.14159, 3.58979e-09, 3.14159), (0, 0, 0),   1.96,  (0.00510825, 0.00510825, 0.0055125)),
+    ("wrist_3_link",   (1.1843, 0.163941, 0.0116, 3.14159, 3.58979e-09, 3.14159), (0, 0, 0),   0.202, (0.000526462, 0.000526462, 0.000568125)),
+    ("hand",           (1.1843, 0.256, 0.0116, 0, 0, 0),                     (0, 0.035, 0),    0.96,  (0.00053312, 0.00065312, 0.000904)),
+    ("l_finger",       (1.1843, 0.256, 0.0116, 0, 0, 0),                     (-0.0205, 0.0798, 0), 0.12, (0.0000095236, 0.0000072, 0.0000052036)),
+    ("r_finger",       (1.1843, 0.256, 0.0116, 0, 0, 0),                     (0.0205, 0.0798, 0),  0.12, (0.0000095236, 0.0000072, 0.0000052036)),
+]
+# joint of link i: (parent, type, axis in the child link frame)  (model.sdf:78-90,123-135,...,361-371,508-524)
+_UR10_JOINTS = [None, (0, JOINT_REVOLUTE, (0, 0, 1)), (1, JOINT_REVOLUTE, (0, 1, 0)), (2, JOINT_REVOLUTE, (0, 1, 0)),
+                (3, JOINT_REVOLUTE, (0, 1, 0)), (4, JOINT_REVOLUTE, (0, 0, -1)), (5, JOINT_REVOLUTE, (0, 1, 0)),
+                (6, JOINT_REVOLUTE, (0, 0, 1)), (7, JOINT_PRISMATIC, (1, 0, 0)), (7, JOINT_PRISMATIC, (1, 0, 0))]
+
+
+def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_jitter=0.1, controller=True, mu=0.5, NK=4):
+    """SURVEY.md 8(d) case 4: the UR10 + Schunk gripper of example/ur10/model.sdf as a fixed-base chain.
+
+    Benchmark variant (the shipped ur10.xml has mesh geometry, mu = 100, joint limits and no table): `world_joint` is a
+    weld (base_link is the fixed base); `fixed_hand_to_wrist` and the two finger prismatics -- held by +-1e-5 joint
+    limits in the file, which are outside this round's scope -- are ordinary joints held at 0 by PD gains; the wrist-3
+    link, hand and fingers carry sphere / box proxies; a plane "table" (normal +z) sits at `table_z`; optionally the
+    block of ur10.xml:22-25 (box .02825 x .025 x .025, mass 1) rests on the table.  Joint PD targets follow
+    example/ur10/controller.cpp:46-96.  dt = 5e-4 (ur10.xml:2), gravity (0,0,-9.81).  Bodies: 0..9 links, 10 table,
+    11 block."""
+    rng = np.random.default_rng(seed)
+    nl = len(_UR10_LINKS)
+    nb = nl + 1 + (1 if with_block else 0)
+    s = SceneBatch(n_envs, nb)
+    s.name = "ur10"
+    s.gravity = (0.0, 0.0, -9.81)
+    s.min_step_size = 5e-4
+    rc = ArticulatedBody(s, 0, nl, fdyn)
+    pose_q, pose_x, com_w = [], [], []
+    for i, (_, pose, com, mass, (ixx, iyy, izz)) in enumerate(_UR10_LINKS):
+        ql = quat_from_rpy(np.float64(pose[3]), np.float64(pose[4]), np.float64(pose[5]))
+        R = _rotmat(ql)
+        pose_q.append(ql); pose_x.append(np.array(pose[:3], np.float64)); com_w.append(pose_x[i] + R @ np.array(com, np.float64))
+        s.mass[i, :] = mass
+        s.inertia[i, 0, :], s.inertia[i, 1, :], s.inertia[i, 2, :] = ixx, iyy, izz
+    # base pose (COM frame of base_link)
+    for k in range(3):
+        s.q[0, k, :] = com_w[0][k]
+    for i in range(1, nl):
+        parent, jt, ax = _UR10_JOINTS[i]
+        Rp, Rc = _rotmat(pose_q[parent]), _rotmat(pose_q[i])
+        joint_w = pose_x[i]                                  # SDF joints sit at the child link's frame origin
+        rc.set_joint(i, parent, jt, ax, Rp.T @ (joint_w - com_w[parent]), Rc.T @ (joint_w - com_w[i]),
+                     quat_mul(quat_conj(pose_q[parent]), pose_q[i]))
+    if controller:
+        PERIOD, AMP = 5.0, 0.5
+        SMALL = AMP * 0.1
+        amp = np.array([AMP * PERIOD, SMALL * PERIOD * 2.0, AMP * PERIOD * 2.0 / 3.0, AMP * PERIOD / 7.0, AMP * PERIOD * 2.0 / 11.0,
+                        AMP * PERIOD * 3.0 / 13.0, 0.0, 0.0, 0.0])
+        freq = np.array([1.0, 2.0, 2.0 / 3.0, 1.0 / 7.0, 2.0 / 11.0, 3.0 / 13.0, 0.0, 0.0, 0.0])
+        kp = np.array([300.0, 300.0, 60.0, 15.0, 15.0, 15.0, 15.0, 1000.0, 1000.0])
+        kv = np.array([120.0, 120.0, 24.0, 6.0, 6.0, 6.0, 6.0, 20.0, 20.0])
+        rc.set_controller(kp, kv, amp, freq)
+        rc.jqd[:6, :] = amp[:6, None]                        # controller.cpp:124-140: qd(0) = cos(0) * amplitude
+    rc.jq[:6, :] = rng.uniform(-q_jitter, q_jitter, (6, n_envs))
+    # collision proxies (centred on the link COM frames)
+    s.set_sphere(6, 0.045, mass=_UR10_LINKS[6][3]); s.inertia[6, :, :] = np.array(_UR10_LINKS[6][4])[:, None]
+    s.set_box(7, 0.10, 0.07, 0.05, mass=_UR10_LINKS[7][3]); s.inertia[7, :, :] = np.array(_UR10_LINKS[7][4])[:, None]
+    for f in (8, 9):
+        s.set_sphere(f, 0.012, mass=_UR10_LINKS[f][3]); s.inertia[f, :, :] = np.array(_UR10_LINKS[f][4])[:, None]
+    table = nl
+    if table_z is None:
+        table_z = -0.02
+    s.set_plane(table, quat=tuple(quat_from_rpy(np.float64(1.5707963267948966), 0.0, 0.0)), pos=(0.0, 0.0, table_z))
+    for link in (6, 7, 8, 9):
+        s.set_contact(link, table, mu_coulomb=mu, NK=NK)
+    if with_block:
+        blk = nl + 1
+        s.set_box(blk, 0.02825, 0.025, 0.025, mass=1.0)
+        s.q[blk, 0, :] = 1.185 + rng.uniform(-0.05, 0.05, n_envs)
+        s.q[blk, 1, :] = 0.336 + rng.uniform(-0.05, 0.05, n_envs)
+        s.q[blk, 2, :] = table_z + 0.0125
+        s.set_contact(blk, table, mu_coulomb=mu, NK=NK)
+        for f in (8, 9):
+            s.set_contact(f, blk, mu_coulomb=mu, NK=NK)
+    return s

@@ -23,6 +23,9 @@ class TimeSteppingSimulator:
         capi.check(capi.lib().b200moby_create(C.byref(self._desc), device, C.byref(self._h)))
         self.n_envs, self.n_bodies = scene.n_envs, scene.n_bodies
         self.set_state(scene.q, scene.v)
+        self.rc = getattr(scene, "rc", None)
+        if self.rc is not None:
+            self.set_joint_state(self.rc.jq, self.rc.jqd)
         self.steps_taken = 0
 
     def __del__(self):
@@ -42,6 +45,41 @@ class TimeSteppingSimulator:
         v = np.empty((self.n_bodies, 6, self.n_envs))
         capi.check(capi.lib().b200moby_get_state(self._h, q.ctypes.data, v.ctypes.data))
         return q, v
+
+    # ---- articulated body: joint state [dof][env] (RCArticulatedBodyd generalized coordinates / velocities) ----
+    def set_joint_state(self, jq, jqd):
+        jq, jqd = np.ascontiguousarray(jq, np.float64), np.ascontiguousarray(jqd, np.float64)
+        assert jq.shape == (self.rc.n_dof, self.n_envs) and jqd.shape == jq.shape
+        capi.check(capi.lib().b200moby_set_joint_state(self._h, jq.ctypes.data, jqd.ctypes.data))
+
+    def get_joint_state(self):
+        jq, jqd = np.empty((self.rc.n_dof, self.n_envs)), np.empty((self.rc.n_dof, self.n_envs))
+        capi.check(capi.lib().b200moby_get_joint_state(self._h, jq.ctypes.data, jqd.ctypes.data))
+        return jq, jqd
+
+    def set_joint_forces(self, tau):
+        """Generalized joint forces applied every mini-step until changed ([dof][env]); None clears them."""
+        if tau is None:
+            capi.check(capi.lib().b200moby_set_joint_forces(self._h, None))
+        else:
+            tau = np.ascontiguousarray(tau, np.float64)
+            assert tau.shape == (self.rc.n_dof, self.n_envs)
+            capi.check(capi.lib().b200moby_set_joint_forces(self._h, tau.ctypes.data))
+
+    def rc_fwd_dyn(self, algorithm, jq, jqd, tau=None, stream=None):
+        """Batched articulated-body forward dynamics on torch CUDA tensors [dof][env]; returns qdd."""
+        import torch
+        qdd = torch.empty_like(jq)
+        capi.check(capi.lib().b200moby_rc_fwd_dyn_batched(self._h, int(algorithm), jq.data_ptr(), jqd.data_ptr(),
+                                                          None if tau is None else tau.data_ptr(), qdd.data_ptr(), _stream(stream)))
+        return qdd
+
+    def rc_inertia(self, jq, stream=None):
+        import torch
+        nd = self.rc.n_dof
+        Hm = torch.empty((nd * nd, self.n_envs), dtype=torch.float64, device=jq.device)
+        capi.check(capi.lib().b200moby_rc_inertia_batched(self._h, jq.data_ptr(), Hm.data_ptr(), _stream(stream)))
+        return Hm
 
     # ---- state (torch CUDA tensors, no host round trip) ----
     def set_state_dev(self, q, v, stream=None):
@@ -80,6 +118,12 @@ class TimeSteppingSimulator:
 
     def reset_counters(self):
         capi.check(capi.lib().b200moby_reset_counters(self._h))
+
+    def impact_profile(self):
+        """Debug tap: (cycles, pivots, executed iterations, n) per env of the last impact phase; first call arms it."""
+        prof = np.zeros((4, self.n_envs), np.int64)
+        capi.check(capi.lib().b200moby_get_impact_profile(self._h, prof.ctypes.data))
+        return prof
 
     def last_lcp_z(self, zcap):
         n = np.zeros(self.n_envs, np.int32)

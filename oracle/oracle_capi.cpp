@@ -8,6 +8,7 @@
 #include "../include/b200moby.h"
 #include "oracle_lcp.h"
 #include "oracle_sim.h"
+#include "oracle_rc.h"
 
 using namespace oracle;
 
@@ -244,5 +245,60 @@ void oracle_batch_run(void* h, double dt, int n_steps, int threads, b200moby_cou
 }
 // state of env (e0 + i) as AoS [body][7], [body][6]
 void oracle_batch_get_state(void* h, int i, double* q, double* v) { get_state(((OracleBatch*)h)->sims[i], q, v); }
+
+// ---- reduced-coordinate articulated body (oracle_rc.h) ----
+// mass [link], J [link][3], base_pose [7] = x y z qx qy qz qw; the tree comes from the product's plain-C descriptor.
+static void rc_model_from_desc(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, RCModel& m) {
+  m.n_links = r->n_links;
+  for (int i = 0; i < r->n_links; i++) {
+    m.mass[i] = mass[i];
+    for (int c = 0; c < 3; c++) m.J[i][c] = J[3 * i + c];
+    if (i == 0) continue;
+    m.parent[i] = r->parent[i]; m.jtype[i] = r->joint_type[i];
+    double an = 0, qn = 0;
+    for (int c = 0; c < 3; c++) an += r->joint_axis[3 * i + c] * r->joint_axis[3 * i + c];
+    for (int c = 0; c < 4; c++) qn += r->rel_quat[4 * i + c] * r->rel_quat[4 * i + c];
+    an = std::sqrt(an); qn = std::sqrt(qn);
+    for (int c = 0; c < 3; c++) { m.axis[i][c] = r->joint_axis[3 * i + c] / an; m.loc_parent[i][c] = r->loc_parent[3 * i + c]; m.loc_child[i][c] = r->loc_child[3 * i + c]; }
+    for (int c = 0; c < 4; c++) m.rel_quat[i][c] = r->rel_quat[4 * i + c] / qn;
+  }
+  double qn = 0; for (int c = 0; c < 4; c++) qn += base_pose[3 + c] * base_pose[3 + c];
+  qn = std::sqrt(qn);
+  for (int c = 0; c < 3; c++) m.base_x[c] = base_pose[c];
+  for (int c = 0; c < 4; c++) m.base_quat[c] = base_pose[3 + c] / qn;
+}
+// algo: 0 = ABA (fsab), 1 = CRB + Cholesky.  Returns 1 on success.
+int oracle_rc_fwd_dyn(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, const double* g,
+                      int algo, const double* q, const double* qd, const double* tau, double* qdd) {
+  RCModel m; rc_model_from_desc(r, mass, J, base_pose, m);
+  std::vector<double> t(m.ndof(), 0.0);
+  if (tau) t.assign(tau, tau + m.ndof());
+  if (algo == 1) return rc_crb_fwd_dyn(m, q, qd, t.data(), g, qdd) ? 1 : 0;
+  rc_aba(m, q, qd, t.data(), g, qdd);
+  return 1;
+}
+// H: ndof x ndof column-major
+void oracle_rc_inertia(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, const double* q, double* H) {
+  RCModel m; rc_model_from_desc(r, mass, J, base_pose, m);
+  std::vector<double> qd(m.ndof(), 0.0);
+  RCKin k; rc_kinematics(m, q, qd.data(), k);
+  rc_crb(m, k, H);
+}
+// link world poses x [link][3], R [link][9] (row-major), COM linear / angular velocity [link][3], Jacobians [link][6*ndof]
+void oracle_rc_links(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, const double* q,
+                     const double* qd, double* x, double* R, double* vl, double* va, double* jac) {
+  RCModel m; rc_model_from_desc(r, mass, J, base_pose, m);
+  RCKin k; rc_kinematics(m, q, qd, k);
+  for (int i = 0; i < m.n_links; i++) {
+    for (int c = 0; c < 3; c++) { x[3 * i + c] = k.x[i][c]; vl[3 * i + c] = k.vl[i][c]; va[3 * i + c] = k.va[i][c]; }
+    for (int c = 0; c < 9; c++) R[9 * i + c] = k.R[i][c];
+    if (jac) rc_link_jacobian(m, k, i, jac + (size_t)i * 6 * m.ndof());
+  }
+}
+double oracle_rc_energy(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, const double* g,
+                        const double* q, const double* qd) {
+  RCModel m; rc_model_from_desc(r, mass, J, base_pose, m);
+  return rc_energy(m, q, qd, g);
+}
 
 }  // extern "C"

@@ -8,6 +8,7 @@
 #include "../../include/b200moby.h"
 #include "../../moby_b200/csrc/friction_table.h"
 #include "../../moby_b200/csrc/sim_device.cuh"
+#include "../../moby_b200/csrc/rc_host.h"
 
 using namespace b2m;
 
@@ -140,6 +141,33 @@ int hostsim_lcp(int mode, int n, const double* M, const double* q, double* z, in
   if (pivots) *pivots = piv;
   if (log_len) *log_len = nlog;
   return st;
+}
+
+// ---- articulated body: the device functions of rc_device.cuh on the host ----
+// mass [link], J [link][3], base_pose [7]; what: 0 ABA qdd, 1 CRB qdd, 2 H (ndof*ndof col-major) -> out; links (optional):
+// x [link][3], quat [link][4], vl [link][3], va [link][3]
+int hostsim_rc(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, const double* g, int what,
+               const double* q, const double* qd, const double* tau, double* out, double* lx, double* lquat, double* lvl, double* lva) {
+  RCTree T; bool unsup;
+  if (b2m_rc_tree_from_desc(*r, r->first_body + r->n_links, T, &unsup)) return -1;
+  RCState s;
+  double qt[4], nrm = 0;
+  for (int c = 0; c < 4; c++) nrm += base_pose[3 + c] * base_pose[3 + c];
+  nrm = std::sqrt(nrm);
+  for (int c = 0; c < 3; c++) s.x[0][c] = base_pose[c];
+  for (int c = 0; c < 4; c++) qt[c] = base_pose[3 + c] / nrm;
+  quat_to_R(qt, s.R[0]);
+  rc_kinematics(T, q, qd, s);
+  const int nd = T.n_links - 1;
+  std::vector<double> H((size_t)nd * nd);
+  if (what == 0 || what == 1) rc_fwd_dyn(T, what, s, mass, J, qd, tau, g, out, H.data());
+  else if (what == 2) rc_crb(T, s, mass, J, out, nd);
+  if (lx) for (int i = 0; i < T.n_links; i++) {
+    for (int c = 0; c < 3; c++) lx[3 * i + c] = s.x[i][c];
+    R_to_quat(s.R[i], lquat + 4 * i);
+    rc_link_velocity(s, i, lvl + 3 * i, lva + 3 * i);
+  }
+  return 0;
 }
 
 }  // extern "C"

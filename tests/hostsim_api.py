@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from moby_b200.capi import SceneDesc
+from moby_b200.capi import RcDesc, SceneDesc
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 CNT = ("env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
@@ -32,6 +32,7 @@ def lib():
         L.hostsim_run_phased.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int]
         L.hostsim_lcp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.hostsim_rc.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8
         _lib = L
     return _lib
 
@@ -87,3 +88,22 @@ def lcp(mode, M, q, z0=None, piv_tol=-1.0, zero_tol=-1.0, min_exp=-20, step_exp=
     st = lib().hostsim_lcp(mode, n, p(Mf), p(q), p(z), 0 if z0 is None else 1, piv_tol, zero_tol, min_exp, step_exp, max_exp,
                            C.byref(piv), p(log), log_cap, C.byref(ll))
     return st, z, piv.value, log[:min(ll.value, log_cap)].copy()
+
+
+def rc_eval(body, what, q, qd, tau=None, gravity=(0.0, -9.81, 0.0), env=0):
+    """Device articulated-body code on the host for one env of an ArticulatedBody description.
+    what: 0 ABA qdd, 1 CRB qdd, 2 joint-space inertia.  Returns (out, links dict)."""
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    d = body.cdesc()
+    mass, J, pose = body.env_mass_props(env)
+    nl, nd = body.n_links, body.n_links - 1
+    q, qd = np.ascontiguousarray(q, np.float64), np.ascontiguousarray(qd, np.float64)
+    tau = np.zeros(nd) if tau is None else np.ascontiguousarray(tau, np.float64)
+    g = np.array(gravity, np.float64)
+    out = np.zeros(nd * nd if what == 2 else nd)
+    lx, lq, lvl, lva = np.zeros((nl, 3)), np.zeros((nl, 4)), np.zeros((nl, 3)), np.zeros((nl, 3))
+    rc = lib().hostsim_rc(C.byref(d), p(mass), p(J), p(pose), p(g), what, p(q), p(qd), p(tau), p(out), p(lx), p(lq), p(lvl), p(lva))
+    assert rc == 0
+    if what == 2:
+        out = out.reshape(nd, nd).T.copy()
+    return out, dict(x=lx, quat=lq, vl=lvl, va=lva)

@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from moby_b200.capi import Counters, SceneDesc
+from moby_b200.capi import Counters, RcDesc, SceneDesc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
@@ -53,6 +53,11 @@ def lib():
         L.oracle_batch_destroy.argtypes = [C.c_void_p]
         L.oracle_batch_run.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(Counters)]
         L.oracle_batch_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_rc_fwd_dyn.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
+        L.oracle_rc_inertia.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 5
+        L.oracle_rc_links.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 10
+        L.oracle_rc_energy.restype = C.c_double
+        L.oracle_rc_energy.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -195,3 +200,46 @@ class OracleBatch:
         q, v = np.zeros((self.nb, 7)), np.zeros((self.nb, 6))
         lib().oracle_batch_get_state(self.h, i, _p(q), _p(v))
         return q, v
+
+
+# ---- reduced-coordinate articulated body (oracle/oracle_rc.h) ----
+def rc_fwd_dyn(body, algo, q, qd, tau=None, gravity=(0.0, -9.81, 0.0), env=0):
+    """algo 0: Featherstone ABA, 1: CRB + Cholesky.  `body` is a scenes.ArticulatedBody."""
+    d = body.cdesc()
+    mass, J, pose = body.env_mass_props(env)
+    nd = body.n_links - 1
+    q, qd = np.ascontiguousarray(q, np.float64), np.ascontiguousarray(qd, np.float64)
+    tau = np.zeros(nd) if tau is None else np.ascontiguousarray(tau, np.float64)
+    g = np.array(gravity, np.float64)
+    qdd = np.zeros(nd)
+    ok = lib().oracle_rc_fwd_dyn(C.byref(d), _p(mass), _p(J), _p(pose), _p(g), algo, _p(q), _p(qd), _p(tau), _p(qdd))
+    assert ok == 1
+    return qdd
+
+
+def rc_inertia(body, q, env=0):
+    d = body.cdesc()
+    mass, J, pose = body.env_mass_props(env)
+    nd = body.n_links - 1
+    q = np.ascontiguousarray(q, np.float64)
+    H = np.zeros(nd * nd)
+    lib().oracle_rc_inertia(C.byref(d), _p(mass), _p(J), _p(pose), _p(q), _p(H))
+    return H.reshape(nd, nd).T.copy()
+
+
+def rc_links(body, q, qd, env=0):
+    d = body.cdesc()
+    mass, J, pose = body.env_mass_props(env)
+    nl, nd = body.n_links, body.n_links - 1
+    q, qd = np.ascontiguousarray(q, np.float64), np.ascontiguousarray(qd, np.float64)
+    x, R, vl, va, jac = np.zeros((nl, 3)), np.zeros((nl, 3, 3)), np.zeros((nl, 3)), np.zeros((nl, 3)), np.zeros((nl, 6, nd))
+    lib().oracle_rc_links(C.byref(d), _p(mass), _p(J), _p(pose), _p(q), _p(qd), _p(x), _p(R), _p(vl), _p(va), _p(jac))
+    return dict(x=x, R=R, vl=vl, va=va, jac=jac)
+
+
+def rc_energy(body, q, qd, gravity=(0.0, -9.81, 0.0), env=0):
+    d = body.cdesc()
+    mass, J, pose = body.env_mass_props(env)
+    q, qd = np.ascontiguousarray(q, np.float64), np.ascontiguousarray(qd, np.float64)
+    g = np.array(gravity, np.float64)
+    return lib().oracle_rc_energy(C.byref(d), _p(mass), _p(J), _p(pose), _p(g), _p(q), _p(qd))
