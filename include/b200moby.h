@@ -131,6 +131,11 @@ typedef struct {
   int    impact_model;          /* B200MOBY_MODEL_* */
   int    stabilization_max_iterations; /* must be 0 this round */
   const b200moby_rc_desc* rc;   /* optional articulated body (NULL: free bodies only) */
+  /* Working-set bounds per env.  0 = the worst case over all body pairs (every pair in contact at once), which is
+   * what small scenes use; many-body scenes (a 10-box stack has 55 pairs but ~40 simultaneous contacts) give the bounds
+   * they need.  An env that exceeds them in some step skips that impact solve and is counted in lcp_failures. */
+  int max_contacts;
+  int max_lcp_n;
 } b200moby_scene_desc;
 
 typedef struct b200moby_sim* b200moby_handle;
@@ -194,7 +199,8 @@ b200moby_status b200moby_get_time(b200moby_handle h, double* t);
 b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int zcap);
 
 /* Debug tap: SM cycles, pivots, executed solver iterations and LCP dimension of each env's most recent impact phase,
- * prof: host buffer [4][env]; reading clears it.  The first call arms the tap. */
+ * followed by the cycles of nine phases (load, contacts, islands, problem data, LCP build, lcp_fast, Lemke, apply,
+ * store); prof: host buffer [13][env]; reading clears it.  The first call arms the tap. */
 b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof);
 
 /* ---- batched solvers: replace LCP::lcp_lemke / lcp_fast and wrappers (LCP.h:21-27) ----

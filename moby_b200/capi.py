@@ -34,6 +34,7 @@ class SceneDesc(C.Structure):
         ("min_step_size_env", C.POINTER(C.c_double)),
         ("impact_model", C.c_int), ("stabilization_max_iterations", C.c_int),
         ("rc", C.POINTER(RcDesc)),
+        ("max_contacts", C.c_int), ("max_lcp_n", C.c_int),
     ]
 
 

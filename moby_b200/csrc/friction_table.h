@@ -60,3 +60,29 @@ inline int b2m_class_table(int nmax, int cmax, int model, int max_classes, int* 
   class_nmax[k] = nmax; class_cmax[k] = cmax; k++;
   return k;
 }
+
+// Working-set bounds of a whole batch descriptor (shared by b200moby_create and the host-compiled test harness).
+// Returns nullptr, or a message when a friction-cone-edges value is invalid.
+#include "../../include/b200moby.h"
+inline const char* b2m_scene_bounds(const b200moby_scene_desc* d, int& cmax, int& nmax, int& npmax) {
+  const int ne = d->n_envs, nb = d->n_bodies;
+  cmax = 0; nmax = 0; npmax = 0;
+  std::vector<int> sh(nb), en(nb), nk(nb * nb);
+  int per_contact = 0;
+  for (int e = 0; e < ne; e++) {
+    for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
+    for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) {
+      const int k = d->NK[((size_t)i * nb + j) * ne + e];
+      if (k != 0 && (k < 4 || k > B2M_NKMAX || (k & 1))) return "friction-cone-edges must be even and in [4,64] (ContactParameters.cpp:129-136)";
+      nk[i * nb + j] = k;
+      if (k) per_contact = std::max(per_contact, d->impact_model == 1 ? 5 + (k > 4 ? (k + 4) / 4 : 1) : 6 + k / 2);
+    }
+    int c, n, np;
+    b2m_env_bounds(nb, sh.data(), en.data(), nk.data(), d->impact_model, c, n, np);
+    cmax = std::max(cmax, c); nmax = std::max(nmax, n); npmax = std::max(npmax, np);
+  }
+  if (d->max_contacts > 0 && d->max_contacts < cmax) { cmax = d->max_contacts; nmax = std::min(nmax, cmax * per_contact); }
+  if (d->max_lcp_n > 0 && d->max_lcp_n < nmax) nmax = d->max_lcp_n;
+  cmax = std::max(cmax, 1); nmax = std::max(nmax, 1); npmax = std::max(npmax, 1);
+  return nullptr;
+}

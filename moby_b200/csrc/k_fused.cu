@@ -6,7 +6,7 @@ using namespace b2m;
 __global__ void __launch_bounds__(32) step_warp_kernel(SimParams P, double dt, int n_steps, size_t env_d) {
   extern __shared__ __align__(16) unsigned char smem[];
   EnvMem m;
-  env_carve(m, (double*)smem, (int*)((double*)smem + env_d), P.nb, P.cmax, P.nmax, P.npmax);
+  env_mem_full(P, m, smem, 0, 1);
   WarpGroup g(nullptr);
   unsigned long long lc[CNT_COUNT];
   for (int e = blockIdx.x; e < P.n_envs; e += gridDim.x) {
@@ -21,9 +21,8 @@ __global__ void __launch_bounds__(32) step_warp_kernel(SimParams P, double dt, i
 // ---- finish: envs that still have time left in their step after the last round; fused loop, full working set ----
 __global__ void __launch_bounds__(32) finish_kernel(SimParams P, double dt, int round) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const size_t ed = (env_doubles(P.nb, P.cmax, P.nmax, P.npmax) + 1) & ~(size_t)1;
   EnvMem m;
-  env_carve(m, (double*)smem, (int*)((double*)smem + ed), P.nb, P.cmax, P.nmax, P.npmax);
+  env_mem_full(P, m, smem, 0, 1);
   WarpGroup g(nullptr);
   unsigned long long lc[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;

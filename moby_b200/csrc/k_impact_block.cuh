@@ -8,9 +8,8 @@ __global__ void __launch_bounds__(NT) impact_block_kernel(SimParams P, double dt
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double red[4 * (NT / 32) + 4];
   __shared__ int next;
-  const size_t ed = (env_doubles(P.nb, P.cmax, P.nmax, P.npmax) + 1) & ~(size_t)1;
   EnvMem m;
-  env_carve(m, (double*)smem, (int*)((double*)smem + ed), P.nb, P.cmax, P.nmax, P.npmax);
+  env_mem_full(P, m, smem, 0, 1);
   BlockGroup<NT> g(red);
   unsigned long long lc[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;

@@ -5,10 +5,9 @@ using namespace b2m;
 // ---- impact: islands, Delassus / LCP assembly, solve, impulses for the parked envs of one LCP class ----
 __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt, int round, int slot, int wpb) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const size_t ed = (env_doubles(P.nb, P.cmax, P.nmax, P.npmax) + 1) & ~(size_t)1, ei = (env_ints(P.nb, P.cmax, P.nmax, P.npmax) + 3) & ~(size_t)3;
   const int w = threadIdx.x >> 5;
   EnvMem m;
-  env_carve(m, (double*)smem + (size_t)w * ed, (int*)((double*)smem + (size_t)wpb * ed) + (size_t)w * ei, P.nb, P.cmax, P.nmax, P.npmax);
+  env_mem_full(P, m, smem, w, wpb);
   WarpGroup g(nullptr);
   unsigned long long lc[CNT_COUNT], tot[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) tot[k] = 0;

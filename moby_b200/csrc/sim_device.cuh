@@ -65,7 +65,10 @@ struct SimParams {
   // reduced-coordinate articulated body (null / 0 when the scene has none)
   const RCTree* rc; int rc_links, rc_first;
   double* jq; double* jqd; const double* jtau;   // [dof][env]
-  long long* tap_prof;         // [4][env]: SM cycles, pivots, executed iterations, LCP n of the env's last impact phase
+  // working sets that do not fit an SM's shared memory (many-body scenes, LCP n in the hundreds) live in global
+  // memory instead, one slice per resident thread group: slice g starts at gscratch + g * gstride (doubles)
+  double* gscratch; size_t gstride;
+  long long* tap_prof;         // [4 + PH_COUNT][env]: SM cycles, pivots, executed iterations, LCP n of the env's last impact phase, then cycles per phase
 };
 
 // Per-env working set carved out of one contiguous block of doubles + ints (shared memory for warp groups).
@@ -78,7 +81,18 @@ struct EnvMem {
   double *MM, *qq, *z, *zl, *work;
   // ints
   int *bshape, *ben, *pair_a, *pair_b, *cb1, *cb2, *cNK, *icon, *cisl, *corder, *isl_start, *gcoff, *bisl, *frow_c, *frow_j, *scal, *iwork;
+  long long* prof; long long prof_stride;   // debug: per-phase cycle accumulators of the env being processed (null: off)
 };
+
+// phase ids of the impact profile (rows 4.. of SimParams::tap_prof)
+enum { PH_LOAD = 0, PH_CONTACTS, PH_ISLANDS, PH_PROBLEM, PH_BUILD, PH_FAST, PH_LEMKE, PH_APPLY, PH_STORE, PH_COUNT };
+#ifdef __CUDA_ARCH__
+#define B2M_PROF_T0(m) const long long _pt0 = (m).prof ? clock64() : 0
+#define B2M_PROF_ADD(m, g, k) do { if ((m).prof && (g).tid == 0) (m).prof[(k) * (m).prof_stride] += clock64() - _pt0; } while (0)
+#else
+#define B2M_PROF_T0(m) do {} while (0)
+#define B2M_PROF_ADD(m, g, k) do {} while (0)
+#endif
 
 // The working set has two segments.  "small": bodies, pair distances and the contact list -- all that the advance
 // phase (positions, forward dynamics, narrowphase) touches.  "impact": Jacobian rows, Delassus blocks, the LCP and the
@@ -107,7 +121,7 @@ B2M_HD inline void env_carve_small(EnvMem& m, double* d, int* i, int nb, int cma
   m.pair_a = i; i += npmax; m.pair_b = i; i += npmax;
   m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax;
   m.scal = i; i += 16;
-  m.Jr = nullptr; m.zl = nullptr;
+  m.Jr = nullptr; m.zl = nullptr; m.prof = nullptr; m.prof_stride = 0;
 }
 B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax) {
   m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.D = d; d += 6 * (size_t)cmax * cmax;
@@ -157,6 +171,10 @@ B2M_HD B2M_INL V3 point_vel(const BodyRef& b, const V3& p) {
 }
 B2M_HD B2M_INL V3 lin_vel(const BodyRef& b) { return b.enabled ? ld3(b.vl) : V3(); }
 B2M_HD B2M_INL V3 ang_vel(const BodyRef& b) { return b.enabled ? ld3(b.va) : V3(); }
+
+}  // namespace b2m
+#include "boxbox_device.cuh"
+namespace b2m {
 
 B2M_HD inline double box_closest_point(const double* dims, const V3& point, V3& closest) {   // BoxPrimitive.cpp:788-836
   const double ext[3] = {dims[0] * 0.5, dims[1] * 0.5, dims[2] * 0.5};
@@ -212,6 +230,7 @@ B2M_HD inline bool signed_dist_ordered(const BodyRef& A, const BodyRef& B, doubl
     pB = (vnorm == 0.0) ? ld3(B.x) : ld3(B.x) + v * ((B.dims[0] + fmin(dist, 0.0)) / vnorm);
     return true;
   }
+  if (A.shape == SH_BOX && B.shape == SH_BOX) { boxbox_signed_dist(A, B, dist, pA, pB); return true; }   // rule H5 (boxbox_device.cuh)
   return false;
 }
 B2M_HD inline bool signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
@@ -301,6 +320,15 @@ B2M_HD inline int pair_contacts(const EnvMem& m, int ia, int ib, double TOL, Con
     if (cnt < cap) { out[cnt].p = p; out[cnt].n = normal; out[cnt].b1 = ix; out[cnt].b2 = is; out[cnt].dist = dist; }
     return cnt + 1;
   }
+  if (A.shape == SH_BOX && B.shape == SH_BOX) {                                                            // CCD.inl:86-494, rule H5
+    V3 pts[8], normal; double depth[8];
+    const int k = boxbox_contacts(A, B, TOL, pts, depth, normal);
+    for (int i = 0; i < k; i++) {
+      if (cnt < cap) { out[cnt].p = pts[i]; out[cnt].n = normal; out[cnt].b1 = ia; out[cnt].b2 = ib; out[cnt].dist = depth[i]; }
+      cnt++;
+    }
+    return cnt;
+  }
   return 0;
 }
 
@@ -372,6 +400,11 @@ B2M_HD inline double pair_CA(const EnvMem& m, int p) {
       const V3 rl = rotT(gB.R, point_vel(gA, ld3(gB.x))) - rotT(gB.R, lin_vel(gB));
       const V3 ra = rotT(gB.R, ang_vel(gA) - ang_vel(gB));
       return next_CA_box_plane(gB, -rl, -ra, -con[0].n, -d);
+    }
+    if (gA.shape == SH_BOX && gB.shape == SH_BOX) {                          // CCD.cpp:350-364 -> :468-541
+      const V3 wrel = ang_vel(gA) - ang_vel(gB);
+      const V3 rlA = rotT(gA.R, lin_vel(gA) - point_vel(gB, ld3(gA.x))), rlB = rotT(gB.R, point_vel(gA, ld3(gB.x)) - lin_vel(gB));
+      return next_CA_box_box(gA, gB, rlA, rotT(gA.R, wrel), rlB, rotT(gB.R, wrel), con[0].n, d);
     }
     return B2M_INF;
   }
@@ -833,7 +866,8 @@ B2M_DEV double min_constraint_velocity(const G& g, const EnvMem& m) {           
 template <class G>
 B2M_DEV bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int nc = m.scal[S_NC];
-  const int n = build_qp_lcp(g, P, m);
+  int n;
+  { B2M_PROF_T0(m); n = build_qp_lcp(g, P, m); B2M_PROF_ADD(m, g, PH_BUILD); }
   if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * nc; t += G::size) m.imp[t] = 0.0; g.sync(); return true; }
   const bool warm = (m.scal[S_ZLN] == n);                                           // :158-162 with rule H1 (zero fill)
   for (int i = g.tid; i < n; i += G::size) m.z[i] = warm ? m.zl[i] : 0.0;
@@ -841,13 +875,14 @@ B2M_DEV bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
   long long stats[3] = {0, 0, 0};
   int piv = 0;
   int* bud = cx.limit ? &cx.budget : nullptr;
-  int st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats, bud);   // :219
+  int st;
+  { B2M_PROF_T0(m); st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats, bud); B2M_PROF_ADD(m, g, PH_FAST); }   // :219
   if (st == LCP_DEFER) return false;
   long long fast_calls = stats[0], pivots = stats[1], executed = stats[2], lemke_calls = 0;
   if (st == LCP_UNVERIFIED) {
     g.sync();
     stats[0] = stats[1] = stats[2] = 0;
-    st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);      // :222-225
+    { B2M_PROF_T0(m); st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud); B2M_PROF_ADD(m, g, PH_LEMKE); }   // :222-225
     if (st == LCP_DEFER) return false;
     lemke_calls = stats[0]; pivots += stats[1]; executed += stats[2];
     if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
@@ -879,9 +914,11 @@ template <class G>
 B2M_DEV bool apply_qp_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int nc = m.scal[S_NC];
   if (!solve_qp(g, P, e, m, lc, cx)) return false;
+  B2M_PROF_T0(m);
   apply_to_bodies(g, P, m, m.imp);
   update_constraint_velocities(g, m, m.imp);
   const double minv = min_constraint_velocity(g, m);
+  B2M_PROF_ADD(m, g, PH_APPLY);
   bool changed = false;                                           // apply_restitution(epd, z) :470-491 (H3: friction kept)
   for (int i = g.tid; i < nc; i += G::size) {
     const double c = m.imp[i] * m.ceps[m.icon[i]];
@@ -916,7 +953,7 @@ B2M_DEV bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned
   g.sync();
   if (g.tid == 0) {
     lc[CNT_LCP_SOLVES]++; lc[CNT_LEMKE_CALLS] += stats[0]; lc[CNT_PIVOTS] += stats[1];
-    lc[CNT_PIVOT_FLOPS] += (unsigned long long)stats[1] * 2ull * n * (n + 1);
+    lc[CNT_PIVOT_FLOPS] += (unsigned long long)stats[2] * 2ull * n * (n + 1);
     if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
   }
   if (P.tap_n) {
@@ -970,6 +1007,7 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
   bool impacting = false;
   for (int c = g.tid; c < ncon; c += G::size) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) impacting = true;
   if (!g.any(impacting)) return true;
+  B2M_PROF_T0(m);
   // islands (UnilateralConstraint.cpp:940-1194) with the canonical order of rule H4: seeds in ascending body index,
   // neighbours in contact (edge insertion) order, each visited body picks up its remaining contacts in list order.
   if (g.tid == 0) {
@@ -1007,6 +1045,7 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
     m.scal[S_FLAG] = (int)active;
   }
   g.sync();
+  B2M_PROF_ADD(m, g, PH_ISLANDS);
   const int nisl = m.scal[S_NISL];
   const unsigned active = (unsigned)m.scal[S_FLAG];
   for (int k = 0; k < nisl; k++) {
@@ -1019,7 +1058,7 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
       m.scal[S_NC] = nc; m.scal[S_NGC] = gc;
     }
     g.sync();
-    compute_problem_data(g, P, m);
+    { B2M_PROF_T0(m); compute_problem_data(g, P, m); B2M_PROF_ADD(m, g, PH_PROBLEM); }
     if (g.tid == 0) {   // F_delassus = 2 (3nc) 36 b + 2 (3nc)^2 6, F_apply = 2 NGC 3nc
       const unsigned long long nc = m.scal[S_NC], ngc = m.scal[S_NGC];
       unsigned long long blocks = 0;
@@ -1168,10 +1207,13 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   const long long t0 = P.tap_prof ? clock64() : 0;
 #endif
   const unsigned long long p0 = lc[CNT_PIVOTS], f0 = lc[CNT_PIVOT_FLOPS];
-  env_load(g, P, e, m);
+  m.prof = P.tap_prof ? P.tap_prof + (size_t)4 * P.n_envs + e : nullptr; m.prof_stride = P.n_envs;
+  { B2M_PROF_T0(m); env_load(g, P, e, m); B2M_PROF_ADD(m, g, PH_LOAD); }
   const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
+  { B2M_PROF_T0(m);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
+  B2M_PROF_ADD(m, g, PH_CONTACTS); }
   lc[CNT_CONTACTS] = c0; lc[CNT_OVERFLOW] = o0;                  // counted by the advance phase
   if (!process_constraints(g, P, e, m, lc, cx)) {
     if (g.tid == 0) q_push(P, round, B2M_SLOT_STRAGGLER, e);
@@ -1180,7 +1222,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   }
   mini_step_account(g, P, m, lc);
   g.sync();
-  env_store(g, P, e, m, ST_VEL | ST_ZL);
+  { B2M_PROF_T0(m); env_store(g, P, e, m, ST_VEL | ST_ZL); B2M_PROF_ADD(m, g, PH_STORE); }
   if (g.tid == 0) {
     const double hh = P.hpend[e];
     const double h = P.hacc[e] + hh;

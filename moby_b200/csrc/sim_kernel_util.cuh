@@ -16,6 +16,18 @@ __device__ __forceinline__ void add_counters(unsigned long long* tot, const unsi
   for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) { if (lc[k] > tot[k]) tot[k] = lc[k]; } else tot[k] += lc[k]; }
 }
 
+// Full working set of thread group `slot` of this block (`slots` groups per block): shared memory, or the group's slice of
+// the global scratch when the launch was planned with one (P.gscratch).
+__device__ __forceinline__ void env_mem_full(const SimParams& P, EnvMem& m, unsigned char* smem, int slot, int slots) {
+  const size_t ed = (env_doubles(P.nb, P.cmax, P.nmax, P.npmax) + 1) & ~(size_t)1, ei = (env_ints(P.nb, P.cmax, P.nmax, P.npmax) + 3) & ~(size_t)3;
+  if (P.gscratch) {
+    double* base = P.gscratch + ((size_t)blockIdx.x * slots + slot) * P.gstride;
+    env_carve(m, base, (int*)(base + ed), P.nb, P.cmax, P.nmax, P.npmax);
+  } else {
+    env_carve(m, (double*)smem + (size_t)slot * ed, (int*)((double*)smem + (size_t)slots * ed) + (size_t)slot * ei, P.nb, P.cmax, P.nmax, P.npmax);
+  }
+}
+
 // next queue index for a warp (lane 0 pulls, broadcast) / a block (thread 0 pulls, broadcast through shared memory)
 __device__ __forceinline__ int pull_warp(int* head) {
   int i = 0;

@@ -8,8 +8,7 @@
 #include <vector>
 #include "friction_table.h"
 #include "host_util.h"
-#include "sim_device.cuh"
-#include "sim_launch.h"
+#include "sim_kernel_util.cuh"
 #include "rc_host.h"
 
 using namespace b2m;
@@ -21,6 +20,8 @@ struct ClassPlan {
   int threads = 32;          // 32: warp-per-env kernel (wpb warps per block); > 32: one block per env
   int wpb = 1, grid = 1;
   size_t shmem = 0;
+  double* gscratch = nullptr;   // non-null: the working set exceeds shared memory and lives in this global buffer
+  size_t gstride = 0;
 };
 
 struct b200moby_sim {
@@ -37,6 +38,7 @@ struct b200moby_sim {
   int adv_wpb = 4, adv_grid = 1; size_t adv_shmem = 0;
   std::vector<ClassPlan> classes;
   ClassPlan straggler;       // full-size block-per-env kernel for envs over their pivot budget
+  ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
   int fin_grid = 1;
   bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
   long long launches = 0;
@@ -62,10 +64,8 @@ struct StageOut {
 __global__ void __launch_bounds__(256) stage_warp_kernel(SimParams P, int stage, StageOut o, int wpb, size_t env_d, size_t env_i) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int w = threadIdx.x >> 5;
-  double* sd = (double*)smem + (size_t)w * env_d;
-  int* si = (int*)((double*)smem + (size_t)wpb * env_d) + (size_t)w * env_i;
   EnvMem m;
-  env_carve(m, sd, si, P.nb, P.cmax, P.nmax, P.npmax);
+  env_mem_full(P, m, smem, w, wpb);
   WarpGroup g(nullptr);
   unsigned long long lc[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
@@ -165,6 +165,30 @@ b200moby_status plan_grid(const void* kernel, int threads, size_t shmem, int sms
   return B200MOBY_OK;
 }
 
+// Shared memory a kernel needs for `slots` working sets of `per` bytes, or -- when one working set does not fit an SM --
+// a global scratch buffer with one slice per resident group (cp.gscratch / cp.gstride; the launch then asks for no
+// dynamic shared memory).
+b200moby_status plan_memory(b200moby_sim* h, const void* kernel, ClassPlan& cp, int nb, int npmax, int slots_max, int work) {
+  const size_t ed = (env_doubles(nb, cp.cmax, cp.nmax, npmax) + 1) & ~(size_t)1, ei = (env_ints(nb, cp.cmax, cp.nmax, npmax) + 3) & ~(size_t)3;
+  const size_t per = ed * sizeof(double) + ei * sizeof(int);
+  b200moby_status st;
+  if (per <= B2M_SMEM_MAX) {
+    cp.wpb = (cp.threads == 32) ? (int)std::max<size_t>(1, std::min<size_t>(slots_max, B2M_SMEM_MAX / per)) : 1;
+    cp.shmem = per * cp.wpb;
+    return plan_grid(kernel, cp.threads == 32 ? cp.wpb * 32 : cp.threads, cp.shmem, h->sms, (work + cp.wpb - 1) / cp.wpb, &cp.grid);
+  }
+  cp.wpb = (cp.threads == 32) ? slots_max : 1;
+  cp.shmem = 0;
+  if ((st = plan_grid(kernel, cp.threads == 32 ? cp.wpb * 32 : cp.threads, 0, h->sms, (work + cp.wpb - 1) / cp.wpb, &cp.grid)) != B200MOBY_OK) return st;
+  cp.gstride = ed + (ei + 1) / 2;
+  const size_t total = cp.gstride * (size_t)cp.grid * cp.wpb;
+  double* buf = nullptr;
+  B2M_CUDA(cudaMalloc((void**)&buf, total * sizeof(double)));
+  h->allocs.push_back(buf);
+  cp.gscratch = buf;
+  return B200MOBY_OK;
+}
+
 // Launch plan of the phased step: grids are persistent (SMs x resident blocks, capped by the batch) and pull env
 // indices from the queues, so empty queues cost one short launch.
 b200moby_status plan_launch(b200moby_sim* h) {
@@ -174,14 +198,18 @@ b200moby_status plan_launch(b200moby_sim* h) {
   const int nb = h->nb, ne = h->n_envs;
   h->env_d = (env_doubles(nb, h->cmax, h->nmax, h->npmax) + 1) & ~(size_t)1;
   h->env_i = (env_ints(nb, h->cmax, h->nmax, h->npmax) + 3) & ~(size_t)3;
-  h->shmem = h->env_d * sizeof(double) + h->env_i * sizeof(int);
-  if (h->shmem > B2M_SMEM_MAX)
-    return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "env working set (%zu bytes, LCP n <= %d) exceeds one SM's shared memory", h->shmem, h->nmax);
-  h->wpb = 1; h->grid = ne;
   h->fused = env_int("B200MOBY_FUSED", 0) != 0;
   h->rounds = std::max(1, std::min(B2M_ROUNDS_MAX, env_int("B200MOBY_ROUNDS", 2)));
-  B2M_CUDA(cudaFuncSetAttribute(b2m_k_step_warp(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX));
   b200moby_status st;
+  // full working set, one env per warp-sized block: finish kernel, fused comparison kernel, stage kernels
+  {
+    ClassPlan& f = h->fullws;
+    f.nmax = h->nmax; f.cmax = h->cmax; f.threads = 32;
+    B2M_CUDA(cudaFuncSetAttribute(b2m_k_step_warp(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX));
+    if ((st = plan_memory(h, b2m_k_finish(), f, nb, h->npmax, 1, ne)) != B200MOBY_OK) return st;
+    h->shmem = f.shmem; h->wpb = 1; h->grid = f.gscratch ? f.grid : ne; h->fin_grid = f.grid;
+    h->P.gscratch = f.gscratch; h->P.gstride = f.gstride;
+  }
   // advance: warps_per_block envs per block, small segment only
   {
     const size_t sd = (env_small_doubles(nb, h->cmax, h->npmax) + 1) & ~(size_t)1, si = (env_small_ints(nb, h->cmax, h->npmax) + 3) & ~(size_t)3;
@@ -196,32 +224,23 @@ b200moby_status plan_launch(b200moby_sim* h) {
   {
     const int warp_nmax = env_int("B200MOBY_WARP_NMAX", 24); // classes up to this n: warp per env; above: block per env
     const int bthreads = env_int("B200MOBY_IMPACT_THREADS", 64);
+    const int big_n = env_int("B200MOBY_BIG_N", 96);          // classes above this n always get 256 threads per env
     const int ncls = b2m_class_table(h->nmax, h->cmax, h->P.model, B2M_MAX_CLASSES, h->P.class_nmax, h->P.class_cmax);
     h->classes.clear();
     for (int k = 0; k < ncls; k++) {
       ClassPlan c; c.nmax = h->P.class_nmax[k]; c.cmax = h->P.class_cmax[k];
-      const int n = c.nmax;
-      const size_t per = env_bytes(nb, c.cmax, c.nmax, h->npmax);
-      if (n <= warp_nmax || bthreads <= 32) {
-        c.threads = 32;
-        c.wpb = (int)std::max<size_t>(1, std::min<size_t>(4, B2M_SMEM_MAX / per));
-        c.shmem = per * c.wpb;
-        if ((st = plan_grid(b2m_k_impact_warp(), c.wpb * 32, c.shmem, sms, (ne + c.wpb - 1) / c.wpb, &c.grid)) != B200MOBY_OK) return st;
-      } else {
-        c.threads = bthreads <= 64 ? 64 : (bthreads <= 128 ? 128 : 256); c.wpb = 1; c.shmem = per;
-        if (c.threads == 64) st = plan_grid(impact_block_ptr(64), 64, per, sms, ne, &c.grid);
-        else if (c.threads == 128) st = plan_grid(impact_block_ptr(128), 128, per, sms, ne, &c.grid);
-        else st = plan_grid(impact_block_ptr(256), 256, per, sms, ne, &c.grid);
-        if (st != B200MOBY_OK) return st;
-      }
+      if (c.nmax <= warp_nmax || bthreads <= 32) c.threads = 32;
+      else if (c.nmax > big_n) c.threads = 256;
+      else c.threads = bthreads <= 64 ? 64 : (bthreads <= 128 ? 128 : 256);
+      const void* kern = c.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(c.threads);
+      if ((st = plan_memory(h, kern, c, nb, h->npmax, 4, ne)) != B200MOBY_OK) return st;
       h->classes.push_back(c);
     }
     h->P.n_classes = (int)h->classes.size();
     ClassPlan& sg = h->straggler;
-    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = 256; sg.wpb = 1; sg.shmem = h->shmem;
-    if ((st = plan_grid(impact_block_ptr(256), 256, sg.shmem, sms, ne, &sg.grid)) != B200MOBY_OK) return st;
+    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = 256;
+    if ((st = plan_memory(h, impact_block_ptr(256), sg, nb, h->npmax, 1, ne)) != B200MOBY_OK) return st;
   }
-  if ((st = plan_grid(b2m_k_finish(), 32, h->shmem, sms, ne, &h->fin_grid)) != B200MOBY_OK) return st;
   return B200MOBY_OK;
 }
 
@@ -237,7 +256,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
     if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
     for (size_t c = 0; c < h->classes.size(); c++) {
       ClassPlan& cp = h->classes[c];
-      SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax;
+      SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax; Pc.gscratch = cp.gscratch; Pc.gstride = cp.gstride;
       int slot = (int)c;
       cudaStream_t sc = conc ? h->side[c] : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
@@ -254,7 +273,8 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
     }
     if (P.pivot_budget > 0) {
       int slot = B2M_SLOT_STRAGGLER;
-      void* a[] = {&P, &dt, &r, &slot};
+      SimParams Ps = P; Ps.gscratch = h->straggler.gscratch; Ps.gstride = h->straggler.gstride;
+      void* a[] = {&Ps, &dt, &r, &slot};
       B2M_CUDA(cudaLaunchKernel(impact_block_ptr(256), dim3(h->straggler.grid), dim3(256), a, h->straggler.shmem, s)); h->launches++;
     }
   }
@@ -277,22 +297,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   const int ne = d->n_envs, nb = d->n_bodies;
   // validate and size
   int cmax = 0, nmax = 0, npmax = 0;
-  {
-    std::vector<int> sh(nb), en(nb), nk(nb * nb);
-    for (int e = 0; e < ne; e++) {
-      for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
-      for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) {
-        const int k = d->NK[((size_t)i * nb + j) * ne + e];
-        if (k != 0 && (k < 4 || k > B2M_NKMAX || (k & 1))) return b2m_fail(B200MOBY_ERR_INVALID, "friction-cone-edges must be even and in [4,%d] (ContactParameters.cpp:129-136); got %d", B2M_NKMAX, k);
-        nk[i * nb + j] = k;
-      }
-      int c, n, np;
-      b2m_env_bounds(nb, sh.data(), en.data(), nk.data(), d->impact_model, c, n, np);
-      for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++)
-        if (nk[i * nb + j] && sh[i] == 2 && sh[j] == 2 && (en[i] || en[j])) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "box-box narrowphase is not on the accelerated path yet; disable the pair or use spheres");
-      cmax = std::max(cmax, c); nmax = std::max(nmax, n); npmax = std::max(npmax, np);
-    }
-  }
+  if (const char* err = b2m_scene_bounds(d, cmax, nmax, npmax)) return b2m_fail(B200MOBY_ERR_INVALID, "%s", err);
   b200moby_sim* h = new b200moby_sim;
   h->device = device; h->n_envs = ne; h->nb = nb; h->cmax = std::max(cmax, 1); h->nmax = std::max(nmax, 1); h->npmax = std::max(npmax, 1);
   SimParams& P = h->P;
@@ -540,13 +545,14 @@ b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int 
 }
 
 // Debug tap: per-env SM cycles, pivots, executed iterations and LCP dimension of the last impact phase; prof is a host
-// buffer [4][env].  The first call arms the tap (and returns zeros).
+// buffer [13][env] (4 totals + 9 phases: load, contacts, islands, problem data, LCP build, lcp_fast, Lemke, apply, store).
+// The first call arms the tap (and returns zeros).
 b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof) {
   if (!h || !prof) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
   B2M_CUDA(cudaSetDevice(h->device));
-  if (!h->P.tap_prof) { b200moby_status st; if ((st = dev_zero(h, (size_t)4 * h->n_envs, &h->P.tap_prof)) != B200MOBY_OK) return st; }
-  B2M_CUDA(cudaMemcpy(prof, h->P.tap_prof, sizeof(long long) * 4 * h->n_envs, cudaMemcpyDeviceToHost));
-  B2M_CUDA(cudaMemset(h->P.tap_prof, 0, sizeof(long long) * 4 * h->n_envs));
+  if (!h->P.tap_prof) { b200moby_status st; if ((st = dev_zero(h, (size_t)(4 + PH_COUNT) * h->n_envs, &h->P.tap_prof)) != B200MOBY_OK) return st; }
+  B2M_CUDA(cudaMemcpy(prof, h->P.tap_prof, sizeof(long long) * (4 + PH_COUNT) * h->n_envs, cudaMemcpyDeviceToHost));
+  B2M_CUDA(cudaMemset(h->P.tap_prof, 0, sizeof(long long) * (4 + PH_COUNT) * h->n_envs));
   return B200MOBY_OK;
 }
 

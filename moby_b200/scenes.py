@@ -51,6 +51,8 @@ class SceneBatch:
         self.v = np.zeros((nb, 6, ne), np.float64)
         self.name = "custom"
         self.rc = None                        # optional ArticulatedBody
+        self.max_contacts = 0                 # working-set bounds per env (0 = worst case over all pairs)
+        self.max_lcp_n = 0
 
     # ---- primitives (InertiaFromPrimitive: BoxPrimitive / SpherePrimitive::calc_mass_properties) ----
     def set_box(self, b, xlen, ylen, zlen, density=None, mass=None, envs=slice(None)):
@@ -105,6 +107,7 @@ class SceneBatch:
             a = np.ascontiguousarray(self.min_step_size_env, np.float64)
             keep.append(a)
             d.min_step_size_env = a.ctypes.data_as(C.POINTER(C.c_double))
+        d.max_contacts, d.max_lcp_n = self.max_contacts, self.max_lcp_n
         if self.rc is not None:
             rd = self.rc.cdesc()
             keep.append(rd)
@@ -394,4 +397,39 @@ def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_
         s.set_contact(blk, table, mu_coulomb=mu, NK=NK)
         for f in (8, 9):
             s.set_contact(f, blk, mu_coulomb=mu, NK=NK)
+    return s
+
+
+def box_stack(n_envs=1, n_boxes=3, jitter=1e-3, seed=0xB200, adjacent_only=True, mu=1e-4, NK=4, yaw_jitter=0.0):
+    """example/stacks/stack.xml (SURVEY.md 8(d) case 3): boxes of height 1 shrinking by 0.05 per level (x and z), density 10,
+    centres at y = 0.5, 1.5, ..., mu = 1e-4 between neighbours and on the ground, default 4 cone edges.  The file
+    registers 3 of its 7 boxes (stack.xml:85-88); BASELINE's config extends the pattern to 10.  Bodies 0..n-1 are the
+    boxes bottom-up, body n is the ground plane.  `jitter`: lateral offset U[-j, j] per box and env.
+    `adjacent_only`: only neighbouring boxes (and box 0 / ground) are collision pairs -- what the reference's broad phase
+    (CCD.cpp:702-874, swept bounding spheres) leaves for this scene; False keeps every pair with default parameters."""
+    rng = np.random.default_rng(seed)
+    nb = n_boxes + 1
+    s = SceneBatch(n_envs, nb)
+    s.name = f"stack-{n_boxes}"
+    for k in range(n_boxes):
+        w = 1.0 - 0.05 * k
+        s.set_box(k, w, 1.0, w, density=10.0)
+        s.q[k, 1, :] = 0.5 + k
+        s.q[k, 0, :] = rng.uniform(-jitter, jitter, n_envs)
+        s.q[k, 2, :] = rng.uniform(-jitter, jitter, n_envs)
+        if yaw_jitter:
+            yaw = rng.uniform(-yaw_jitter, yaw_jitter, n_envs)
+            quat = quat_from_rpy(np.zeros(n_envs), yaw, np.zeros(n_envs))
+            for c in range(4):
+                s.q[k, 3 + c, :] = quat[c]
+    s.set_plane(n_boxes)
+    if not adjacent_only:
+        for i in range(nb):
+            for j in range(i + 1, nb):
+                s.set_contact(i, j)
+    s.set_contact(0, n_boxes, mu_coulomb=mu, NK=NK)
+    for k in range(n_boxes - 1):
+        s.set_contact(k, k + 1, mu_coulomb=mu, NK=NK)
+    s.max_contacts = (8 if yaw_jitter else 4) * n_boxes + 8
+    s.max_lcp_n = s.max_contacts * (6 + NK // 2)
     return s

@@ -121,7 +121,7 @@ class TimeSteppingSimulator:
 
     def impact_profile(self):
         """Debug tap: (cycles, pivots, executed iterations, n) per env of the last impact phase; first call arms it."""
-        prof = np.zeros((4, self.n_envs), np.int64)
+        prof = np.zeros((13, self.n_envs), np.int64)
         capi.check(capi.lib().b200moby_get_impact_profile(self._h, prof.ctypes.data))
         return prof
 

@@ -1,5 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  See oracle_sim.h for scope, citations and the PARITY UNPINNED note.
 #include "oracle_sim.h"
+#include "oracle_boxbox.h"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -84,6 +85,14 @@ static double box_closest_point(const Body& box, const V3& point, V3& closest) {
   return inside ? intDist : std::sqrt(sqrDist);
 }
 
+static bb::Box bb_box(const Body& b) {
+  bb::Box X;
+  X.c = {b.x.x, b.x.y, b.x.z};
+  for (int k = 0; k < 3; k++) { X.ax[k] = {b.R[k], b.R[3 + k], b.R[6 + k]}; X.ext[k] = b.dims[k]; }
+  return X;
+}
+static inline V3 from_bb(const bb::Vec3& v) { return V3(v.x, v.y, v.z); }
+
 // signed distance + closest points (global) with (A,B) in the order given; returns false when the pair type is unsupported
 static bool signed_dist_ordered(const Body& A, const Body& B, double& dist, V3& pA, V3& pB) {
   if (A.shape == SHAPE_PLANE && B.shape == SHAPE_BOX) {            // PlanePrimitive.cpp:342-380
@@ -121,6 +130,12 @@ static bool signed_dist_ordered(const Body& A, const Body& B, double& dist, V3& 
     double vnorm = norm(v);
     pA = pbox_g;
     pB = (vnorm == 0.0) ? B.x : B.x + v * ((B.dims[0] + std::min(dist, 0.0)) / vnorm);
+    return true;
+  }
+  if (A.shape == SHAPE_BOX && B.shape == SHAPE_BOX) {              // rule H5 (oracle_boxbox.h) for BoxPrimitive.cpp:150-181 -> V-Clip
+    bb::Vec3 a, b;
+    bb::signed_dist(bb_box(A), bb_box(B), dist, a, b);
+    pA = from_bb(a); pB = from_bb(b);
     return true;
   }
   return false;
@@ -233,6 +248,13 @@ void Sim::find_contacts(int ia, int ib, double TOL, std::vector<Contact>& out) c
     out.push_back(create_contact(ix, is, p, normal, dist));
     return;
   }
+  // box / box (CCD.inl:86-494), rule H5
+  if (A.shape == SHAPE_BOX && B.shape == SHAPE_BOX) {
+    bb::Vec3 n;
+    const std::vector<bb::Point> pts = bb::contacts(bb_box(A), bb_box(B), TOL, n);
+    for (const bb::Point& c : pts) out.push_back(create_contact(ia, ib, from_bb(c.p), from_bb(n), c.violation));
+    return;
+  }
 }
 
 // ConstraintSimulator.cpp:488-537 + preprocess_constraint :390-417
@@ -295,6 +317,32 @@ static double next_CA_box_plane(const Body& box, const V3& rv_lin_boxframe, cons
   return max_step;
 }
 
+// CCD::calc_next_CA_Euler_step_polyhedron_polyhedron (CCD.cpp:468-541) with both polyhedra boxes
+static double next_CA_box_box(const Body& A, const Body& B, const V3& rvA_lin, const V3& rvA_ang, const V3& rvB_lin, const V3& rvB_ang,
+                              const V3& n0, double offset0) {
+  double max_step = INF;
+  const V3 nA = rotT(A.R, n0), nB = rotT(B.R, -n0);                   // :474-475
+  const V3 p0 = n0 * offset0;
+  const double offsetA = dot(nA, to_local(A, p0)), offsetB = dot(nB, to_local(B, p0));   // :478-480
+  const double avA_norm = norm(rvA_ang), avB_norm = norm(rvB_ang);
+  const double lvA_dot_n = -dot(nA, rvA_lin), lvB_dot_n = dot(nB, rvB_lin);              // :493-494
+  for (int i = 0; i < 8; i++) {                                       // :497-516
+    const V3 vertex = box_vertex(A, i);
+    const double r = norm(vertex), dist = dot(nA, vertex) - offsetA;
+    if (dist < NEAR_ZERO) continue;
+    const double speed = std::max(0.0, lvA_dot_n + avA_norm * r);
+    max_step = std::min(max_step, dist / speed);
+  }
+  for (int i = 0; i < 8; i++) {                                       // :519-538
+    const V3 vertex = box_vertex(B, i);
+    const double r = norm(vertex), dist = dot(nB, vertex) - offsetB;
+    if (dist < NEAR_ZERO) continue;
+    const double speed = std::max(0.0, lvB_dot_n + avB_norm * r);
+    max_step = std::min(max_step, dist / speed);
+  }
+  return max_step;
+}
+
 // CCD.cpp:122-400
 double Sim::calc_CA_Euler_step(const PairDist& pdi) const {
   const Body& A = bodies[pdi.a]; const Body& B = bodies[pdi.b];
@@ -333,6 +381,12 @@ double Sim::calc_CA_Euler_step(const PairDist& pdi) const {
       V3 rl = rotT(gB.R, point_vel(gA, gB.x)) - rotT(gB.R, gB.enabled ? gB.vl : V3());
       V3 ra = rotT(gB.R, (gA.enabled ? gA.va : V3()) - (gB.enabled ? gB.va : V3()));
       return next_CA_box_plane(gB, -rl, -ra, -c.n, -d);
+    }
+    if (gA.shape == SHAPE_BOX && gB.shape == SHAPE_BOX) {            // :350-364 -> :468-541
+      const V3 wrel = (gA.enabled ? gA.va : V3()) - (gB.enabled ? gB.va : V3());
+      const V3 rvA_lin = rotT(gA.R, (gA.enabled ? gA.vl : V3()) - point_vel(gB, gA.x));
+      const V3 rvB_lin = rotT(gB.R, point_vel(gA, gB.x) - (gB.enabled ? gB.vl : V3()));
+      return next_CA_box_box(gA, gB, rvA_lin, rotT(gA.R, wrel), rvB_lin, rotT(gB.R, wrel), c.n, d);
     }
     return INF;                                                      // :397-399
   }

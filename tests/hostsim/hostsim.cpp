@@ -20,14 +20,7 @@ int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time
                 unsigned long long* counters, double dt, int n_steps, int e0, int e1, double* tapMM, double* tapqq, double* tapz, int* tapn) {
   const int ne = d->n_envs, nb = d->n_bodies;
   int cmax = 0, nmax = 0, npmax = 0;
-  std::vector<int> sh(nb), en(nb), nk(nb * nb);
-  for (int e = 0; e < ne; e++) {
-    for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
-    for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) nk[i * nb + j] = d->NK[((size_t)i * nb + j) * ne + e];
-    int c, n, np; b2m_env_bounds(nb, sh.data(), en.data(), nk.data(), d->impact_model, c, n, np);
-    cmax = std::max(cmax, c); nmax = std::max(nmax, n); npmax = std::max(npmax, np);
-  }
-  cmax = std::max(cmax, 1); nmax = std::max(nmax, 1); npmax = std::max(npmax, 1);
+  if (b2m_scene_bounds(d, cmax, nmax, npmax)) return -1;
   if (!q) return nmax;
   std::vector<double> tab = b2m_friction_table();
   SimParams P; memset(&P, 0, sizeof(P));
@@ -55,14 +48,7 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
                        unsigned long long* counters, double dt, int n_steps, int rounds, int pivot_budget) {
   const int ne = d->n_envs, nb = d->n_bodies;
   int cmax = 0, nmax = 0, npmax = 0;
-  std::vector<int> sh(nb), en(nb), nk(nb * nb);
-  for (int e = 0; e < ne; e++) {
-    for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
-    for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) nk[i * nb + j] = d->NK[((size_t)i * nb + j) * ne + e];
-    int c, n, np; b2m_env_bounds(nb, sh.data(), en.data(), nk.data(), d->impact_model, c, n, np);
-    cmax = std::max(cmax, c); nmax = std::max(nmax, n); npmax = std::max(npmax, np);
-  }
-  cmax = std::max(cmax, 1); nmax = std::max(nmax, 1); npmax = std::max(npmax, 1);
+  if (b2m_scene_bounds(d, cmax, nmax, npmax)) return -1;
   std::vector<double> tab = b2m_friction_table();
   SimParams P; memset(&P, 0, sizeof(P));
   P.n_envs = ne; P.nb = nb; P.cmax = cmax; P.nmax = nmax; P.npmax = npmax; P.model = d->impact_model;

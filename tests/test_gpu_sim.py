@@ -213,3 +213,28 @@ def test_edge_cases(torch_cuda, oracle):
     sc = scenes.sitting_box(1, NK=5)
     with pytest.raises(capi.B200MobyError):
         TimeSteppingSimulator(sc)
+
+
+@pytest.mark.parametrize("n_boxes,steps,yaw", [(3, 40, 0.0), (3, 30, 0.3), (10, 4, 0.0)])
+def test_box_stack_matches_oracle(torch_cuda, oracle, n_boxes, steps, yaw):
+    """example/stacks/stack.xml (3 registered boxes) and BASELINE's 10-box extension: box-box contacts under rule H5, LCP
+    dimension 32 per box (n = 320 for ten boxes: the block-per-env kernel with its working set in global memory)."""
+    from moby_b200 import TimeSteppingSimulator
+    ne = 3
+    sc = scenes.box_stack(ne, n_boxes, yaw_jitter=yaw)
+    sim = TimeSteppingSimulator(sc)
+    osims = [oracle.OracleSim(sc, e) for e in range(ne)]
+    sim.step(1e-3, steps)
+    for o in osims:
+        o.step(1e-3, steps)
+    q, v = sim.get_state()
+    for e, o in enumerate(osims):
+        qo, vo = o.get_state()
+        assert np.abs(q[:, :, e] - qo).max() < 1e-9 and np.abs(v[:, :, e] - vo).max() < 1e-9
+    cg = sim.counters()
+    for k in ("env_steps", "mini_steps", "lcp_solves", "contacts"):
+        assert cg[k] == sum(o.counters()[k] for o in osims), k
+    assert cg["max_lcp_n"] == max(o.counters()["max_lcp_n"] for o in osims)
+    assert cg["lcp_failures"] == 0
+    if yaw == 0.0:
+        assert cg["max_lcp_n"] == 32 * n_boxes

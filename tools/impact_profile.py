@@ -15,14 +15,15 @@ for s in range(5):
     sim.step(1e-3, 1)
     torch.cuda.synchronize()
     p = sim.impact_profile()
-    cyc, piv, ex, n = p
+    cyc, piv, ex, n = p[:4]
+    ph = p[4:]
     m = cyc > 0
     r = dict(step=s, envs=int(m.sum()), cyc_sum=int(cyc.sum()), cyc_pct=[float(np.percentile(cyc[m], x)) for x in (50, 90, 99, 99.9, 100)],
              piv_pct=[float(np.percentile(piv[m], x)) for x in (50, 90, 99, 99.9, 100)], ex_pct=[float(np.percentile(ex[m], x)) for x in (50, 90, 99, 99.9, 100)])
     by_n = {}
     for nn in np.unique(n[m]):
         k = m & (n == nn)
-        by_n[int(nn)] = dict(envs=int(k.sum()), cyc_mean=float(cyc[k].mean()), cyc_max=int(cyc[k].max()), cyc_sum=int(cyc[k].sum()), piv_mean=float(piv[k].mean()), ex_mean=float(ex[k].mean()))
+        by_n[int(nn)] = dict(phases=[round(float(ph[j][k].mean())) for j in range(9)], envs=int(k.sum()), cyc_mean=float(cyc[k].mean()), cyc_max=int(cyc[k].max()), cyc_sum=int(cyc[k].sum()), piv_mean=float(piv[k].mean()), ex_mean=float(ex[k].mean()))
     r["by_n"] = by_n
     top = np.argsort(cyc)[-8:]
     r["top"] = [dict(e=int(e), cyc=int(cyc[e]), piv=int(piv[e]), ex=int(ex[e]), n=int(n[e])) for e in top]
