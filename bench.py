@@ -25,10 +25,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT]
 
-ENVS_PER_GPU = 65536
-DT = 1e-3
-WORKLOAD = "sitting-box/bouncing-ball batch: 65,536 randomized envs per GPU (BASELINE configs[1]; SURVEY 8d case 2)"
-BYTES_PER_ENV_STEP = 208.0        # 2 * 8 B * (7 q + 6 v) for the one moving body
+# Workloads = BASELINE.json configs.  "small" (configs[1]) is the one the metric is quoted on and the default; the
+# others are the larger single-GPU configurations, selectable with --workload.
+#   bytes: algorithmic HBM bytes per env-step, 2 * 8 B * (nq + nv) per moving body
+WORKLOADS = {
+    "small": dict(name="sitting-box/bouncing-ball batch: 65,536 randomized envs per GPU (BASELINE configs[1]; SURVEY 8d case 2)",
+                  envs=65536, dt=1e-3, preroll=300, bytes=208.0, cpu_sample=(512, 40), ref_sample=4096,
+                  make=lambda sc, ne, seed: sc.small_lcp_batch(ne, seed=seed)),
+    "stacks": dict(name="example/stacks: 10-box stack, 4,096 envs per GPU, LCP n = 320 (BASELINE configs[2]; SURVEY 8d case 3)",
+                   envs=4096, dt=1e-3, preroll=5, bytes=2080.0, cpu_sample=(4, 2), ref_sample=16,
+                   make=lambda sc, ne, seed: sc.box_stack(ne, 10, seed=seed)),
+    "ur10": dict(name="example/ur10 arm (9-DoF RCArticulatedBody, CRB forward dynamics) + block + table, 16,384 envs per GPU "
+                      "(BASELINE configs[3]; SURVEY 8d case 4)",
+                 envs=16384, dt=5e-4, preroll=100, bytes=2.0 * 8.0 * (9 + 9) + 208.0, cpu_sample=(256, 40), ref_sample=2048,
+                 make=lambda sc, ne, seed: sc.ur10(ne, seed=seed)),
+}
 
 
 def _peaks():
@@ -85,7 +96,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _cpu_baseline(scene, q, v, n_envs, n_steps, threads):
+def _cpu_baseline(scene, q, v, joints, dt, n_envs, n_steps, threads):
     """The oracle (CPU restatement of the reference; the reference itself cannot be built here) on the host cores."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_api as O
@@ -93,8 +104,10 @@ def _cpu_baseline(scene, q, v, n_envs, n_steps, threads):
     sc = copy.copy(scene)
     sc.q, sc.v = q, v
     batch = O.OracleBatch(sc, 0, n_envs)
+    if joints is not None:
+        batch.set_joint_state(*joints)
     t0 = time.perf_counter()
-    c = batch.run(DT, n_steps, threads=threads)
+    c = batch.run(dt, n_steps, threads=threads)
     el = time.perf_counter() - t0
     return c["env_steps"] / el, c["lcp_solves"] / el, el, c
 
@@ -105,11 +118,15 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from moby_b200 import scenes
-    sample = 4096
+    W = WORKLOADS[args.workload]
+    DT, WORKLOAD = W["dt"], W["name"]
+    sample = W["ref_sample"]
     cores = os.cpu_count() or 1
-    scene = scenes.small_lcp_batch(sample, seed=0xB200)
-    if args.min_step == "default":
+    scene = W["make"](scenes, sample, 0xB200)
+    if args.min_step == "default" and args.workload == "small":
         scene.min_step_size_env = None
+    if args.preroll < 0:
+        args.preroll = W["preroll"]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_api as O
     O.build()
@@ -145,8 +162,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--preroll", type=int, default=300, help="untimed steps before warm-up so contacts are active")
+    ap.add_argument("--workload", default="small", choices=sorted(WORKLOADS), help="BASELINE.json config (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's own batch size")
+    ap.add_argument("--preroll", type=int, default=-1, help="untimed steps before warm-up so contacts are active (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-step", default="scene", choices=["scene", "default"],
                     help="scene: min-step-size of the source scenes (test/box.xml: 1e-3, bouncing-ball.xml: sqrt(eps)); "
@@ -166,11 +184,16 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ne = args.envs_per_gpu
-    scene = scenes.small_lcp_batch(ne, seed=0xB200 + rank)      # every rank owns its own envs (contiguous shard of the job)
-    if args.min_step == "default":
+    W = WORKLOADS[args.workload]
+    DT, WORKLOAD = W["dt"], W["name"]
+    ne = args.envs_per_gpu or W["envs"]
+    if args.preroll < 0:
+        args.preroll = W["preroll"]
+    scene = W["make"](scenes, ne, 0xB200 + rank)                # every rank owns its own envs (contiguous shard of the job)
+    if args.min_step == "default" and args.workload == "small":
         scene.min_step_size_env = None
     sim = TimeSteppingSimulator(scene, device=local_rank)
+    has_rc = scene.rc is not None
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -187,6 +210,8 @@ def main():
     sim.reset_counters()
     launches0 = sim.launch_count()
     q0, v0 = sim.get_state()            # the state the timed region starts from (also feeds the CPU baseline)
+    j0 = sim.get_joint_state() if has_rc else None
+    sim.kernel_profile(enable=True, reset=True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -200,6 +225,7 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
+    kprof = sim.kernel_profile(enable=False, reset=True)       # per-kernel durations of exactly the timed steps
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = sum(kernel_ms) * 1e-3
     cnt = sim.counters()
@@ -211,21 +237,40 @@ def main():
     qd, vd = torch.empty_like(qh, device=dev), torch.empty_like(vh, device=dev)
     qo, vo = torch.empty_like(qh).pin_memory(), torch.empty_like(vh).pin_memory()
     h2d = qh.numel() * 8 + vh.numel() * 8
-    for _ in range(2):
-        qd.copy_(qh, non_blocking=True); vd.copy_(vh, non_blocking=True)
-        sim.set_state_dev(qd, vd); sim.step(DT, 1); sim.get_state_dev(qd, vd)
-        qo.copy_(qd, non_blocking=True); vo.copy_(vd, non_blocking=True)
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
+    if has_rc:                           # the articulated body's own state travels too
+        jh = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in j0]
+        jd = [torch.empty_like(a, device=dev) for a in jh]
+        jo = [torch.empty_like(a).pin_memory() for a in jh]
+        h2d += sum(a.numel() * 8 for a in jh)
+
+    def e2e_step():
+        nonlocal qh, qo, vh, vo
         qd.copy_(qh, non_blocking=True); vd.copy_(vh, non_blocking=True)
         sim.set_state_dev(qd, vd)
+        if has_rc:
+            for a, b in zip(jd, jh):
+                a.copy_(b, non_blocking=True)
+            sim.set_joint_state_dev(jd[0], jd[1])
         sim.step(DT, 1)
         sim.get_state_dev(qd, vd)
         qo.copy_(qd, non_blocking=True); vo.copy_(vd, non_blocking=True)
+        if has_rc:
+            sim.get_joint_state_dev(jd[0], jd[1])
+            for a, b in zip(jo, jd):
+                a.copy_(b, non_blocking=True)
         torch.cuda.synchronize()
         qh, qo = qo, qh                  # next step starts from this step's result
         vh, vo = vo, vh
+        if has_rc:
+            for k in range(2):
+                jh[k], jo[k] = jo[k], jh[k]
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
     barrier()
     t_e2e = time.perf_counter() - e0
     # ---- max over ranks, sums of counters ----
@@ -241,17 +286,23 @@ def main():
         total_envs = ne * world
         hbm_peak, hbm_src, fp64_peak, fp64_src = _peaks()
         k_ms = float(np.mean(kernel_ms))
-        # roofline of the dominant (only) kernel, per launch on this rank
-        alg_bytes = BYTES_PER_ENV_STEP * ne
-        alg_flops = (r_cnt["pivot_flops"] + r_cnt["assembly_flops"]) / args.steps
-        achieved_gbs = alg_bytes / (k_ms * 1e-3) / 1e9
-        achieved_tf = alg_flops / (k_ms * 1e-3) / 1e12
+        # roofline of the dominant kernel (largest summed duration over the timed steps), per launch on this rank:
+        # algorithmic bytes = state in + state out of the envs the launch processed (+ warm start in/out for an impact
+        # kernel), algorithmic flops = the kernel's own recorded pivot and assembly flops (SURVEY.md 8d formulas)
+        dom = max(kprof, key=lambda k: k["ms"])
+        dom_launch_ms = dom["ms"] / max(dom["launches"], 1)
+        dom_bytes_env = W["bytes"] + (2.0 * 8.0 * dom["lcp_nmax"] if dom["lcp_nmax"] else 0.0)
+        alg_bytes = dom_bytes_env * dom["envs"] / max(dom["launches"], 1)
+        alg_flops = dom["flops"] / max(dom["launches"], 1)
+        achieved_gbs = alg_bytes / (dom_launch_ms * 1e-3) / 1e9
+        achieved_tf = alg_flops / (dom_launch_ms * 1e-3) / 1e12
+        step_ms_sum = sum(k["ms"] for k in kprof) or 1.0
         out = {
             "metric": "env_steps_per_s", "value": total_envs * args.steps / t_dev, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": ne, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200+rank",
-                       "min_step_size": "boxes 1e-3 (test/box.xml), balls sqrt(eps) (bouncing-ball.xml)" if args.min_step == "scene" else "sqrt(eps) everywhere",
+                       "min_step_size": ("boxes 1e-3 (test/box.xml), balls sqrt(eps) (bouncing-ball.xml)" if args.min_step == "scene" else "sqrt(eps) everywhere") if args.workload == "small" else scene.min_step_size,
                        "impact_model": "QP-as-LCP (default build)", "stabilization": "off (max-iterations=0)",
                        "l2": "flushed between timed steps (256 MiB write outside the events)", "parallelism": f"envs sharded x{world}"},
             "lcp_solves_per_s": lcp_solves / t_dev,
@@ -264,22 +315,28 @@ def main():
             "gpu_launches": launches * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "kernel": "step_warp_kernel", "kernel_ms": k_ms, "peak_source": hbm_src,
-                         "note": "the fused env-step is not HBM-bound (208 algorithmic B per env-step); see fp64",
+                         "traffic": None, "kernel": dom["name"], "kernel_ms": dom_launch_ms, "launches": dom["launches"],
+                         "envs_per_launch": dom["envs"] / max(dom["launches"], 1), "share_of_kernel_time": dom["ms"] / step_ms_sum,
+                         "peak_source": hbm_src,
+                         "note": "pivoting is a dependent-latency chain per env: neither HBM nor the FP64 pipe is the limiter (see DESIGN.md 3-4); "
+                                 "fp64 is the same launch against the measured DFMA peak",
+                         "kernels": [{"name": k["name"], "ms_per_step": k["ms"] / args.steps, "envs_per_step": k["envs"] / args.steps,
+                                      "gflop_per_step": k["flops"] / args.steps / 1e9} for k in kprof if k["launches"]],
                          "fp64": {"achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                                   "peak_source": fp64_src,
                                   "flops": "SURVEY 8(d): sum pivots*2n(n+1) + F_delassus + F_apply per solve + F_fd + F_narrow per mini-step, all from recorded counts"}},
         }
         if not args.no_cpu_baseline:
-            n_cpu, s_cpu = 512, 40
-            v1, l1, el1, _ = _cpu_baseline(scene, q0, v0, n_cpu, s_cpu, 1)
+            n_cpu, s_cpu = W["cpu_sample"]
+            n_cpu = min(n_cpu, ne)
+            v1, l1, el1, _ = _cpu_baseline(scene, q0, v0, j0, DT, n_cpu, s_cpu, 1)
             cores = os.cpu_count() or 1
-            vn, ln, eln, _ = _cpu_baseline(scene, q0, v0, n_cpu * 4, s_cpu, cores)
+            vn, ln, eln, _ = _cpu_baseline(scene, q0, v0, j0, DT, min(n_cpu * 4, ne), s_cpu, cores)
             out["cpu_baseline"] = {"value": v1, "unit": "env-steps/s", "cores": 1, "kind": "port",
                                    "sample": f"first {n_cpu} envs of rank 0's batch from the same pre-rolled state, {s_cpu} steps, "
                                              f"1 thread ({el1:.1f} s); oracle/ restatement (the reference cannot be built here)",
                                    "lcp_solves_per_s": l1,
-                                   "all_cores": {"value": vn, "cores": cores, "sample": f"first {n_cpu * 4} envs, {s_cpu} steps ({eln:.1f} s)"}}
+                                   "all_cores": {"value": vn, "cores": cores, "sample": f"first {min(n_cpu * 4, ne)} envs, {s_cpu} steps ({eln:.1f} s)"}}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -198,6 +198,28 @@ b200moby_status b200moby_get_time(b200moby_handle h, double* t);
  * leading dimension n[env]; any pointer may be NULL. */
 b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int zcap);
 
+/* Per-kernel profile of b200moby_step: which kernels ran, for how long (CUDA events on each launch's own stream; the
+ * impact classes of one round overlap, so the durations can add up to more than the step), how many envs each
+ * processed and the algorithmic flops it did (pivots * 2n(n+1) + assembly, the formulas of SURVEY.md 8d).
+ * enable != 0 turns the event bracketing on for subsequent steps; reset != 0 clears the accumulators after reading.
+ * Synchronises the device.  out may be NULL. */
+#define B200MOBY_MAX_KERNELS 16
+typedef struct {
+  char name[48];
+  double ms;            /* summed launch durations */
+  long long launches;
+  long long envs;       /* envs processed */
+  long long flops;      /* algorithmic FP64 flops */
+  long long lcp_solves;
+  int lcp_nmax;         /* LCP class bound of an impact kernel (0 otherwise) */
+  int threads_per_env;
+} b200moby_kernel_stat;
+typedef struct {
+  int n_kernels;
+  b200moby_kernel_stat k[B200MOBY_MAX_KERNELS];
+} b200moby_kernel_profile;
+b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int reset, b200moby_kernel_profile* out);
+
 /* Debug tap: SM cycles, pivots, executed solver iterations and LCP dimension of each env's most recent impact phase,
  * followed by the cycles of nine phases (load, contacts, islands, problem data, LCP build, lcp_fast, Lemke, apply,
  * store); prof: host buffer [13][env]; reading clears it.  The first call arms the tap. */

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200moby.so")
+LIB_PATH = os.environ.get("B200MOBY_LIB", os.path.join(_HERE, "libb200moby.so"))   # override: build experiments only
 
 
 class B200MobyError(RuntimeError):
@@ -38,6 +38,15 @@ class SceneDesc(C.Structure):
     ]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_longlong), ("envs", C.c_longlong),
+                ("flops", C.c_longlong), ("lcp_solves", C.c_longlong), ("lcp_nmax", C.c_int), ("threads_per_env", C.c_int)]
+
+
+class KernelProfile(C.Structure):
+    _fields_ = [("n_kernels", C.c_int), ("k", KernelStat * 16)]
+
+
 class Counters(C.Structure):
     _fields_ = [(k, C.c_longlong) for k in (
         "env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
@@ -53,7 +62,7 @@ SYMBOLS = [
     "b200moby_create", "b200moby_destroy", "b200moby_set_state", "b200moby_get_state",
     "b200moby_set_state_dev", "b200moby_get_state_dev", "b200moby_step", "b200moby_set_pivot_budget", "b200moby_get_counters",
     "b200moby_reset_counters", "b200moby_get_launch_count", "b200moby_get_time", "b200moby_get_last_lcp",
-    "b200moby_get_impact_profile",
+    "b200moby_get_impact_profile", "b200moby_get_kernel_profile",
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
     "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host", "b200moby_lcp_solve_host",
     "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_delassus_batched",
@@ -89,6 +98,7 @@ def lib():
     L.b200moby_get_time.argtypes = [C.c_void_p, dp]
     L.b200moby_get_last_lcp.argtypes = [C.c_void_p, ip, dp, C.c_int]
     L.b200moby_get_impact_profile.argtypes = [C.c_void_p, ip]
+    L.b200moby_get_kernel_profile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(KernelProfile)]
     L.b200moby_lcp_lemke_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, ip, ip, ip, C.c_int, vp]
     L.b200moby_lcp_fast_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, ip, ip, ip, C.c_int, vp]
     L.b200moby_lcp_lemke_regularized_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_int, C.c_int,

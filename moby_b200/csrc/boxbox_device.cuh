@@ -27,7 +27,7 @@ struct BoxBoxAxis {
 
 B2M_HD B2M_INL V3 box_axis(const double* R, int i) { return V3(R[i], R[3 + i], R[6 + i]); }   // column i of the row-major rotation
 
-B2M_HD inline void boxbox_axis(const BodyRef& A, const BodyRef& B, BoxBoxAxis& r) {
+B2M_HD B2M_NOINL inline void boxbox_axis(const BodyRef& A, const BodyRef& B, BoxBoxAxis& r) {
   const double hA[3] = {A.dims[0] * 0.5, A.dims[1] * 0.5, A.dims[2] * 0.5}, hB[3] = {B.dims[0] * 0.5, B.dims[1] * 0.5, B.dims[2] * 0.5};
   const V3 p = ld3(B.x) - ld3(A.x);
   V3 a[3], b[3];
@@ -66,7 +66,7 @@ B2M_HD B2M_INL V3 box_support(const BodyRef& X, const V3& d) {
 }
 
 // closest points of the two supporting edges of an edge-edge axis (edge i of A, edge j of B, n from A toward B)
-B2M_HD inline void boxbox_edge_points(const BodyRef& A, const BodyRef& B, int i, int j, const V3& n, V3& pa, V3& pb) {
+B2M_HD B2M_NOINL inline void boxbox_edge_points(const BodyRef& A, const BodyRef& B, int i, int j, const V3& n, V3& pa, V3& pb) {
   const V3 ua = box_axis(A.R, i), ub = box_axis(B.R, j);
   // a point on each edge: the support vertex moved to the middle of the edge direction
   V3 ca = box_support(A, n), cb = box_support(B, -n);
@@ -83,7 +83,7 @@ B2M_HD inline void boxbox_edge_points(const BodyRef& A, const BodyRef& B, int i,
 }
 
 // Signed distance and closest points (pA on A, pB on B)
-B2M_HD inline void boxbox_signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
+B2M_HD B2M_NOINL inline void boxbox_signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
   BoxBoxAxis ax; boxbox_axis(A, B, ax);
   dist = ax.s;
   if (ax.code < 3) { pB = box_support(B, -ax.n); pA = pB - ax.n * ax.s; }
@@ -92,7 +92,7 @@ B2M_HD inline void boxbox_signed_dist(const BodyRef& A, const BodyRef& B, double
 }
 
 // Contacts (at most 8).  out[k].n points from B toward A; b1 / b2 are filled by the caller.
-B2M_HD inline int boxbox_contacts(const BodyRef& A, const BodyRef& B, double TOL, V3* pts, double* depth, V3& normal) {
+B2M_HD B2M_NOINL inline int boxbox_contacts(const BodyRef& A, const BodyRef& B, double TOL, V3* pts, double* depth, V3& normal) {
   BoxBoxAxis ax; boxbox_axis(A, B, ax);
   if (ax.s > TOL) return 0;
   normal = -ax.n;
@@ -146,7 +146,7 @@ B2M_HD inline int boxbox_contacts(const BodyRef& A, const BodyRef& B, double TOL
 
 // CCD::calc_next_CA_Euler_step_polyhedron_polyhedron (CCD.cpp:468-541) for two boxes: per-vertex bound on the time to
 // reach the contact plane <n0, x> = offset0.  rvA: velocity of A relative to B in A's frame; rvB the same in B's frame.
-B2M_HD inline double next_CA_box_box(const BodyRef& A, const BodyRef& B, const V3& rvA_lin, const V3& rvA_ang, const V3& rvB_lin, const V3& rvB_ang,
+B2M_HD B2M_NOINL inline double next_CA_box_box(const BodyRef& A, const BodyRef& B, const V3& rvA_lin, const V3& rvA_ang, const V3& rvB_lin, const V3& rvB_ang,
                                      const V3& n0, double offset0) {
   double max_step = B2M_INF;
   const V3 nA = rotT(A.R, n0), nB = rotT(B.R, -n0);

@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(32) finish_kernel(SimParams P, double dt, int 
   const int count = *q_count(P, round, B2M_SLOT_CONT);
   const int* list = q_list(P, round, B2M_SLOT_CONT);
   int* head = q_head(P, round, B2M_SLOT_CONT);
-  for (int i = pull_warp(head); i < count; i = pull_warp(head)) env_finish(g, P, list[i], m, dt, lc);
-  if (g.tid == 0) commit_counters(P, lc);
+  unsigned long long envs = 0;
+  for (int i = pull_warp(head); i < count; i = pull_warp(head)) { env_finish(g, P, list[i], m, dt, lc); envs++; }
+  if (g.tid == 0) commit_counters(P, lc, envs);
 }
 
 const void* b2m_k_step_warp() { return (const void*)step_warp_kernel; }

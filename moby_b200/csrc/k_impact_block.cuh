@@ -16,10 +16,12 @@ __global__ void __launch_bounds__(NT) impact_block_kernel(SimParams P, double dt
   const int count = *q_count(P, round, slot);
   const int* list = q_list(P, round, slot);
   int* head = q_head(P, round, slot);
+  unsigned long long envs = 0;
   for (int i = pull_block(head, &next); i < count; i = pull_block(head, &next)) {
     EnvCtx cx; cx.limit = false; cx.budget = 0;
     env_impact(g, P, list[i], m, dt, round, lc, cx);
+    envs++;
   }
-  if (g.tid == 0) commit_counters(P, lc);
+  if (g.tid == 0) commit_counters(P, lc, envs);
 }
 

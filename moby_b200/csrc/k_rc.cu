@@ -6,13 +6,13 @@ using namespace b2m;
 namespace {
 
 // pose of the base link and the links' mass properties for env e
-__device__ __forceinline__ void rc_load_env(const SimParams& P, const RCTree& T, int e, RCState& s, double* mass, double* J) {
+__device__ __forceinline__ void rc_load_env(const SimParams& P, const RCTree& T, int e, RCState& s, double* mass, double* J) {   // s: a view
   const size_t ne = P.n_envs;
   const int b0 = T.first_body;
   double qt[4];
-  for (int c = 0; c < 3; c++) s.x[0][c] = P.q[((size_t)b0 * 7 + c) * ne + e];
+  for (int c = 0; c < 3; c++) s.x[c] = P.q[((size_t)b0 * 7 + c) * ne + e];
   for (int c = 0; c < 4; c++) qt[c] = P.q[((size_t)b0 * 7 + 3 + c) * ne + e];
-  quat_to_R(qt, s.R[0]);
+  quat_to_R(qt, s.R);
   for (int i = 0; i < T.n_links; i++) {
     mass[i] = P.mass[(size_t)(b0 + i) * ne + e];
     for (int c = 0; c < 3; c++) J[3 * i + c] = P.inertia[((size_t)(b0 + i) * 3 + c) * ne + e];
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) rc_fwd_dyn_kernel(SimParams P, int algo, 
   const RCTree& T = *P.rc;
   const size_t ne = P.n_envs;
   const int nd = T.n_links - 1;
-  RCState s;
+  RCLocal loc; RCState s = loc.view();
   double mass[B2M_MAX_LINKS], J[3 * B2M_MAX_LINKS], q[B2M_MAX_LINKS], qd[B2M_MAX_LINKS], tq[B2M_MAX_LINKS], out[B2M_MAX_LINKS];
   double H[(B2M_MAX_LINKS - 1) * (B2M_MAX_LINKS - 1)];
   rc_load_env(P, T, e, s, mass, J);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) rc_inertia_kernel(SimParams P, const doub
   const RCTree& T = *P.rc;
   const size_t ne = P.n_envs;
   const int nd = T.n_links - 1;
-  RCState s;
+  RCLocal loc; RCState s = loc.view();
   double mass[B2M_MAX_LINKS], J[3 * B2M_MAX_LINKS], q[B2M_MAX_LINKS], qd[B2M_MAX_LINKS];
   double H[(B2M_MAX_LINKS - 1) * (B2M_MAX_LINKS - 1)];
   rc_load_env(P, T, e, s, mass, J);
@@ -63,16 +63,16 @@ __global__ void __launch_bounds__(128) rc_refresh_links_kernel(SimParams P) {
   const RCTree& T = *P.rc;
   const size_t ne = P.n_envs;
   const int nd = T.n_links - 1, b0 = T.first_body;
-  RCState s;
+  RCLocal loc; RCState s = loc.view();
   double mass[B2M_MAX_LINKS], J[3 * B2M_MAX_LINKS], q[B2M_MAX_LINKS], qd[B2M_MAX_LINKS];
   rc_load_env(P, T, e, s, mass, J);
   for (int k = 0; k < nd; k++) { q[k] = P.jq[(size_t)k * ne + e]; qd[k] = P.jqd[(size_t)k * ne + e]; }
   rc_kinematics(T, q, qd, s);
   for (int i = 1; i < T.n_links; i++) {
     double qt[4], vl[3], va[3];
-    R_to_quat(s.R[i], qt);
+    R_to_quat(s.R + 9 * i, qt);
     rc_link_velocity(s, i, vl, va);
-    for (int c = 0; c < 3; c++) P.q[((size_t)(b0 + i) * 7 + c) * ne + e] = s.x[i][c];
+    for (int c = 0; c < 3; c++) P.q[((size_t)(b0 + i) * 7 + c) * ne + e] = s.x[3 * i + c];
     for (int c = 0; c < 4; c++) P.q[((size_t)(b0 + i) * 7 + 3 + c) * ne + e] = qt[c];
     for (int c = 0; c < 3; c++) { P.v[((size_t)(b0 + i) * 6 + c) * ne + e] = vl[c]; P.v[((size_t)(b0 + i) * 6 + 3 + c) * ne + e] = va[c]; }
   }

@@ -25,7 +25,7 @@ B2M_DEV B2M_INL double m_at(const double* M, int ldm, int r, int c, double lambd
 
 // MatrixNd::norm_inf() of M + lambda I: largest |entry|
 template <class G>
-B2M_DEV double norm_inf(const G& g, int n, const double* M, int ldm, double lambda) {
+B2M_DEV B2M_NOINL double norm_inf(const G& g, int n, const double* M, int ldm, double lambda) {
   double m = 0.0;
   for (int e = g.tid; e < n * n; e += G::size) {
     const int c = e / n, r = e - c * n;
@@ -70,7 +70,7 @@ B2M_HD B2M_INL unsigned long long mix64(unsigned long long x) {
 // through a 128-bit hash of the ordered basis plus the entering variable; every thread keeps one (serial group: 32)
 // recent state, so the window is the group size.  Disabled when a pivot log is requested (literal variant).
 template <class G>
-B2M_DEV int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
+B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
                            int* log, int log_cap, int* log_len, int* budget = nullptr, int* executed_out = nullptr) {
   double* T = wd;
@@ -205,7 +205,7 @@ B2M_HD inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2 + (size_t)
 
 // solves A x = b (A k x k column-major ld k, destroyed; b <- x).  Returns false on an exactly zero pivot.
 template <class G>
-B2M_DEV bool lu_solve(const G& g, int k, double* A, double* b) {
+B2M_DEV B2M_NOINL bool lu_solve(const G& g, int k, double* A, double* b) {
   for (int j = 0; j < k; j++) {
     double key = 1.0; int p = 0x7fffffff;                       // lexicographic min of (-|a|, i) == first maximum
     for (int i = j + g.tid; i < k; i += G::size) { const double v = -fabs(A[(size_t)j * k + i]); if (v < key) { key = v; p = i; } }
@@ -245,7 +245,7 @@ B2M_DEV inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while
 // iterations.  Exact, not heuristic: results and reference-equivalent pivot counts are unchanged; *executed_out says
 // how many iterations really ran.
 template <class G>
-B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
+B2M_DEV B2M_NOINL int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
                               bool warm, double* z, double* wd, int* wi, int* pivots_out, int* log, int log_cap,
                               int* log_len, int* budget = nullptr, int* executed_out = nullptr) {
   double* A = wd;
@@ -365,7 +365,7 @@ B2M_DEV int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const do
 
 // Solution checks of the regularised wrappers (LCP.cpp:240-256 with >=, :303-319 with >); w is scratch (n).
 template <class G>
-B2M_DEV bool lcp_verify(const G& g, int n, const double* M, int ldm, const double* q, double lambda, const double* z,
+B2M_DEV B2M_NOINL bool lcp_verify(const G& g, int n, const double* M, int ldm, const double* q, double lambda, const double* z,
                            double ZERO_TOL, bool strict, double* w) {
   double mz = B2M_INF, mw = B2M_INF, mn = B2M_INF, mx = -B2M_INF;
   for (int i = g.tid; i < n; i += G::size) {

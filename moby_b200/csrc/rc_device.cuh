@@ -162,28 +162,33 @@ B2M_HD inline void rc_link_inertia(double mass, const double* J, const double* c
 // Per-thread view of one env's articulated body.  Arrays indexed by link live in local memory when the tree is
 // indexed dynamically; the running quantities of each recursion stay in registers.
 struct RCState {
-  double x[B2M_MAX_LINKS][3], R[B2M_MAX_LINKS][9];   // link poses (COM frames), world
-  double S[B2M_MAX_LINKS][6];                         // motion subspaces, world coordinates
-  double v[B2M_MAX_LINKS][6];                         // spatial velocities, world coordinates
+  double *x, *R;   // link poses (COM frames), world: [link][3], [link][9] row-major
+  double *S;       // motion subspaces, world coordinates: [link][6]
+  double *v;       // spatial velocities, world coordinates: [link][6]
+};
+// thread-local backing store for an RCState (the thread-per-env kernels)
+struct RCLocal {
+  double x[B2M_MAX_LINKS * 3], R[B2M_MAX_LINKS * 9], S[B2M_MAX_LINKS * 6], v[B2M_MAX_LINKS * 6];
+  B2M_HD RCState view() { RCState s; s.x = x; s.R = R; s.S = S; s.v = v; return s; }
 };
 
 // Link poses, motion subspaces and spatial velocities.  x[0], R[0] must hold the base pose.
 B2M_HD inline void rc_kinematics(const RCTree& T, const double* q, const double* qd, RCState& s) {
 #pragma unroll
-  for (int k = 0; k < 6; k++) s.v[0][k] = 0.0;
+  for (int k = 0; k < 6; k++) s.v[6 * (0) + k] = 0.0;
   for (int i = 1; i < T.n_links; i++) {
     const int p = T.parent[i];
-    rc_link_fk(T, i, q[i - 1], s.x[p], s.R[p], s.x[i], s.R[i], s.S[i]);
+    rc_link_fk(T, i, q[i - 1], s.x + 3 * (p), s.R + 9 * (p), s.x + 3 * (i), s.R + 9 * (i), s.S + 6 * (i));
 #pragma unroll
-    for (int k = 0; k < 6; k++) s.v[i][k] = fma(s.S[i][k], qd[i - 1], s.v[p][k]);
+    for (int k = 0; k < 6; k++) s.v[6 * i + k] = fma(s.S[6 * i + k], qd[i - 1], s.v[6 * p + k]);
   }
 }
 // COM linear velocity and angular velocity of link i, world axes (what narrowphase / conservative advancement read)
 B2M_HD B2M_INL void rc_link_velocity(const RCState& s, int i, double* vl, double* va) {
   double t[3];
-  cross3(s.v[i], s.x[i], t);
-  va[0] = s.v[i][0]; va[1] = s.v[i][1]; va[2] = s.v[i][2];
-  vl[0] = s.v[i][3] + t[0]; vl[1] = s.v[i][4] + t[1]; vl[2] = s.v[i][5] + t[2];
+  cross3(s.v + 6 * (i), s.x + 3 * (i), t);
+  va[0] = s.v[6 * (i) + 0]; va[1] = s.v[6 * (i) + 1]; va[2] = s.v[6 * (i) + 2];
+  vl[0] = s.v[6 * (i) + 3] + t[0]; vl[1] = s.v[6 * (i) + 4] + t[1]; vl[2] = s.v[6 * (i) + 5] + t[2];
 }
 
 // Featherstone's articulated-body algorithm (RBDA table 7.1) in world coordinates.
@@ -196,17 +201,17 @@ B2M_HD inline void rc_aba(const RCTree& T, const RCState& s, const double* mass,
   for (int i = 1; i < N; i++) {
     double vJ[6], Iv[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) vJ[k] = s.S[i][k] * qd[i - 1];
-    crm(s.v[i], vJ, c[i]);
-    rc_link_inertia(mass[i], J + 3 * i, s.x[i], s.R[i], IA[i]);
-    sym_mv(IA[i], s.v[i], Iv);
-    crf(s.v[i], Iv, pA[i]);
+    for (int k = 0; k < 6; k++) vJ[k] = s.S[6 * (i) + k] * qd[i - 1];
+    crm(s.v + 6 * (i), vJ, c[i]);
+    rc_link_inertia(mass[i], J + 3 * i, s.x + 3 * (i), s.R + 9 * (i), IA[i]);
+    sym_mv(IA[i], s.v + 6 * (i), Iv);
+    crf(s.v + 6 * (i), Iv, pA[i]);
   }
   for (int i = N - 1; i >= 1; i--) {
-    sym_mv(IA[i], s.S[i], U[i]);
-    const double D = dot6(s.S[i], U[i]);
+    sym_mv(IA[i], s.S + 6 * (i), U[i]);
+    const double D = dot6(s.S + 6 * (i), U[i]);
     Dinv[i] = 1.0 / D;
-    u[i] = (tau ? tau[i - 1] : 0.0) - dot6(s.S[i], pA[i]);
+    u[i] = (tau ? tau[i - 1] : 0.0) - dot6(s.S + 6 * (i), pA[i]);
     const int p = T.parent[i];
     if (p != 0) {
       double Ia[21], Iac[6];
@@ -231,7 +236,7 @@ B2M_HD inline void rc_aba(const RCTree& T, const RCState& s, const double* mass,
     const double qi = (u[i] - dot6(U[i], ap)) * Dinv[i];
     qdd[i - 1] = qi;
 #pragma unroll
-    for (int k = 0; k < 6; k++) a[i][k] = fma(s.S[i][k], qi, ap[k]);
+    for (int k = 0; k < 6; k++) a[i][k] = fma(s.S[6 * i + k], qi, ap[k]);
   }
 }
 
@@ -241,7 +246,7 @@ B2M_HD inline void rc_crb(const RCTree& T, const RCState& s, const double* mass,
   const int N = T.n_links;
   double Ic[B2M_MAX_LINKS][21];
   for (int i = 0; i < N - 1; i++) for (int j = 0; j < N - 1; j++) H[(size_t)j * ld + i] = 0.0;
-  for (int i = 1; i < N; i++) rc_link_inertia(mass[i], J + 3 * i, s.x[i], s.R[i], Ic[i]);
+  for (int i = 1; i < N; i++) rc_link_inertia(mass[i], J + 3 * i, s.x + 3 * (i), s.R + 9 * (i), Ic[i]);
   for (int i = N - 1; i >= 1; i--) {
     const int p = T.parent[i];
     if (p != 0) {
@@ -249,10 +254,10 @@ B2M_HD inline void rc_crb(const RCTree& T, const RCState& s, const double* mass,
       for (int k = 0; k < 21; k++) Ic[p][k] += Ic[i][k];
     }
     double F[6];
-    sym_mv(Ic[i], s.S[i], F);
-    H[(size_t)(i - 1) * ld + (i - 1)] = dot6(s.S[i], F);
+    sym_mv(Ic[i], s.S + 6 * (i), F);
+    H[(size_t)(i - 1) * ld + (i - 1)] = dot6(s.S + 6 * (i), F);
     for (int j = T.parent[i]; j != 0; j = T.parent[j]) {
-      const double h = dot6(F, s.S[j]);
+      const double h = dot6(F, s.S + 6 * (j));
       H[(size_t)(j - 1) * ld + (i - 1)] = h; H[(size_t)(i - 1) * ld + (j - 1)] = h;
     }
   }
@@ -267,17 +272,17 @@ B2M_HD inline void rc_bias(const RCTree& T, const RCState& s, const double* mass
     const int p = T.parent[i];
     double vJ[6], c[6], I[21], Ia[6], Iv[6], vIv[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) vJ[k] = s.S[i][k] * qd[i - 1];
-    crm(s.v[i], vJ, c);
+    for (int k = 0; k < 6; k++) vJ[k] = s.S[6 * (i) + k] * qd[i - 1];
+    crm(s.v + 6 * (i), vJ, c);
 #pragma unroll
     for (int k = 0; k < 6; k++) a[i][k] = a[p][k] + c[k];
-    rc_link_inertia(mass[i], J + 3 * i, s.x[i], s.R[i], I);
-    sym_mv(I, a[i], Ia); sym_mv(I, s.v[i], Iv); crf(s.v[i], Iv, vIv);
+    rc_link_inertia(mass[i], J + 3 * i, s.x + 3 * (i), s.R + 9 * (i), I);
+    sym_mv(I, a[i], Ia); sym_mv(I, s.v + 6 * (i), Iv); crf(s.v + 6 * (i), Iv, vIv);
 #pragma unroll
     for (int k = 0; k < 6; k++) f[i][k] = Ia[k] + vIv[k];
   }
   for (int i = N - 1; i >= 1; i--) {
-    C[i - 1] = dot6(s.S[i], f[i]);
+    C[i - 1] = dot6(s.S + 6 * (i), f[i]);
     const int p = T.parent[i];
     if (p != 0) {
 #pragma unroll

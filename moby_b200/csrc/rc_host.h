@@ -35,3 +35,16 @@ inline const char* b2m_rc_tree_from_desc(const b200moby_rc_desc& r, int n_bodies
   }
   return nullptr;
 }
+
+// Largest island dimension of a scene with an articulated body: six coordinates per enabled free body plus the joints.
+inline int b2m_dense_ngc(const b200moby_scene_desc* d) {
+  if (!d->rc || d->rc->n_links < 2) return 0;
+  const int ne = d->n_envs, nb = d->n_bodies, f = d->rc->first_body, nl = d->rc->n_links;
+  int best = 0;
+  for (int e = 0; e < ne; e++) {
+    int n = 0;
+    for (int b = 0; b < nb; b++) if ((b < f || b >= f + nl) && d->enabled[(size_t)b * ne + e]) n += 6;
+    best = n > best ? n : best;
+  }
+  return best + nl - 1;
+}

@@ -24,6 +24,7 @@ enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LE
 #define B2M_SLOT_STRAGGLER (B2M_MAX_CLASSES + 1)
 #define B2M_SLOTS (B2M_MAX_CLASSES + 2)
 #define B2M_ROUNDS_MAX 8
+#define B2M_MAX_STALL 64
 
 struct V3 {
   double x, y, z;
@@ -64,10 +65,13 @@ struct SimParams {
   double* tap_MM; double* tap_qq; double* tap_z; int* tap_n;
   // reduced-coordinate articulated body (null / 0 when the scene has none)
   const RCTree* rc; int rc_links, rc_first;
+  int ngc;                     // > 0: dense generalized-coordinate layout of the problem data (scenes with an articulated body); largest island dimension
   double* jq; double* jqd; const double* jtau;   // [dof][env]
   // working sets that do not fit an SM's shared memory (many-body scenes, LCP n in the hundreds) live in global
   // memory instead, one slice per resident thread group: slice g starts at gscratch + g * gstride (doubles)
   double* gscratch; size_t gstride;
+  // per-kernel accounting: kstat[3 * kslot + {0,1,2}] += envs processed, algorithmic flops (pivot + assembly), LCP solves
+  unsigned long long* kstat; int kslot;
   long long* tap_prof;         // [4 + PH_COUNT][env]: SM cycles, pivots, executed iterations, LCP n of the env's last impact phase, then cycles per phase
 };
 
@@ -79,8 +83,11 @@ struct EnvMem {
   double *cp, *cnrm, *ct1, *ct2, *cdist, *cmu, *cmuv, *ceps, *ccomp;
   double *Jr, *XJ, *Xb, *D, *Cv, *imp, *acc, *dv;
   double *MM, *qq, *z, *zl, *work;
+  double *Lf, *gv;             // dense layout: Cholesky factor scratch (ngc^2 + ngc), generalized velocity of the island (ngc)
+  double *jq, *jqd, *jqsave, *jtau, *rS, *rV;   // articulated body: joint state, motion subspaces and spatial velocities of the links (world)
   // ints
   int *bshape, *ben, *pair_a, *pair_b, *cb1, *cb2, *cNK, *icon, *cisl, *corder, *isl_start, *gcoff, *bisl, *frow_c, *frow_j, *scal, *iwork;
+  int *ranc, *gcb, *gcl;       // articulated body: ancestor-joint bitmask per link; island coordinate -> (super body, local index)
   long long* prof; long long prof_stride;   // debug: per-phase cycle accumulators of the env being processed (null: off)
 };
 
@@ -97,44 +104,59 @@ enum { PH_LOAD = 0, PH_CONTACTS, PH_ISLANDS, PH_PROBLEM, PH_BUILD, PH_FAST, PH_L
 // The working set has two segments.  "small": bodies, pair distances and the contact list -- all that the advance
 // phase (positions, forward dynamics, narrowphase) touches.  "impact": Jacobian rows, Delassus blocks, the LCP and the
 // solver's work space -- only envs with an impacting contact ever need it, and it is sized by the env's own LCP class.
-B2M_HD inline size_t env_small_doubles(int nb, int cmax, int npmax) { return (size_t)38 * nb + 7 * (size_t)npmax + 17 * (size_t)cmax; }
-B2M_HD inline size_t env_small_ints(int nb, int cmax, int npmax) { return (size_t)2 * nb + 2 * (size_t)npmax + 3 * (size_t)cmax + 16; }
-B2M_HD inline size_t env_impact_doubles(int nb, int cmax, int nmax) {
-  size_t lw = lemke_work_doubles(nmax), fw = fast_work_doubles(nmax);
-  return 72 * (size_t)cmax + 36 * (size_t)nb + 6 * (size_t)cmax * cmax + 9 * (size_t)cmax + 6 * (size_t)nb + (size_t)nmax * nmax +
-         3 * (size_t)nmax + (lw > fw ? lw : fw);
+struct EnvDims {
+  int nb, cmax, nmax, npmax;
+  int rcl;      // links of the articulated body (0: none)
+  int ngc;      // dense problem-data layout with this many generalized coordinates (0: two 6-wide blocks per contact)
+};
+B2M_HD inline EnvDims env_dims(const SimParams& P) { EnvDims d; d.nb = P.nb; d.cmax = P.cmax; d.nmax = P.nmax; d.npmax = P.npmax; d.rcl = P.rc_links; d.ngc = P.ngc; return d; }
+B2M_HD inline size_t env_small_doubles(const EnvDims& d) { return (size_t)38 * d.nb + 7 * (size_t)d.npmax + 17 * (size_t)d.cmax + (d.rcl ? (size_t)4 * (d.rcl - 1) + 12 * (size_t)d.rcl : 0); }
+B2M_HD inline size_t env_small_ints(const EnvDims& d) { return (size_t)2 * d.nb + 2 * (size_t)d.npmax + 3 * (size_t)d.cmax + 16 + (size_t)d.rcl; }
+B2M_HD inline size_t env_impact_doubles(const EnvDims& d) {
+  size_t lw = lemke_work_doubles(d.nmax), fw = fast_work_doubles(d.nmax);
+  const size_t jac = d.ngc ? (size_t)6 * d.cmax * d.ngc + 2 * (size_t)d.ngc * d.ngc + 3 * (size_t)d.ngc : 72 * (size_t)d.cmax + 36 * (size_t)d.nb + 6 * (size_t)d.nb;
+  return jac + 6 * (size_t)d.cmax * d.cmax + 9 * (size_t)d.cmax + (size_t)d.nmax * d.nmax + 3 * (size_t)d.nmax + (lw > fw ? lw : fw);
 }
-B2M_HD inline size_t env_impact_ints(int nb, int cmax, int nmax) {
-  size_t lw = lemke_work_ints(nmax), fw = fast_work_ints(nmax);
-  return (size_t)3 * nb + 1 + 3 * (size_t)cmax + 2 * (size_t)nmax + (lw > fw ? lw : fw);
+B2M_HD inline size_t env_impact_ints(const EnvDims& d) {
+  size_t lw = lemke_work_ints(d.nmax), fw = fast_work_ints(d.nmax);
+  return (size_t)3 * d.nb + 1 + 3 * (size_t)d.cmax + 2 * (size_t)d.nmax + 2 * (size_t)d.ngc + (lw > fw ? lw : fw);
 }
-B2M_HD inline size_t env_doubles(int nb, int cmax, int nmax, int npmax) { return env_small_doubles(nb, cmax, npmax) + env_impact_doubles(nb, cmax, nmax); }
-B2M_HD inline size_t env_ints(int nb, int cmax, int nmax, int npmax) { return env_small_ints(nb, cmax, npmax) + env_impact_ints(nb, cmax, nmax); }
+B2M_HD inline size_t env_doubles(const EnvDims& d) { return env_small_doubles(d) + env_impact_doubles(d); }
+B2M_HD inline size_t env_ints(const EnvDims& d) { return env_small_ints(d) + env_impact_ints(d); }
 
-B2M_HD inline void env_carve_small(EnvMem& m, double* d, int* i, int nb, int cmax, int npmax) {
+B2M_HD inline void env_carve_small(EnvMem& m, double* d, int* i, const EnvDims& D) {
+  const int nb = D.nb, cmax = D.cmax, npmax = D.npmax;
   m.bx = d; d += 3 * nb; m.bq = d; d += 4 * nb; m.bR = d; d += 9 * nb; m.bvl = d; d += 3 * nb; m.bva = d; d += 3 * nb;
   m.bmass = d; d += nb; m.bdims = d; d += 3 * nb; m.bJ = d; d += 3 * nb; m.xsave = d; d += 3 * nb; m.qsave = d; d += 4 * nb;
   m.pd_dist = d; d += npmax; m.pd_pa = d; d += 3 * npmax; m.pd_pb = d; d += 3 * npmax;
   m.cp = d; d += 3 * cmax; m.cnrm = d; d += 3 * cmax; m.ct1 = d; d += 3 * cmax; m.ct2 = d; d += 3 * cmax;
   m.cdist = d; d += cmax; m.cmu = d; d += cmax; m.cmuv = d; d += cmax; m.ceps = d; d += cmax; m.ccomp = d; d += cmax;
+  m.jq = m.jqd = m.jqsave = m.jtau = m.rS = m.rV = nullptr;
+  if (D.rcl) { const int nd = D.rcl - 1; m.jq = d; d += nd; m.jqd = d; d += nd; m.jqsave = d; d += nd; m.jtau = d; d += nd; m.rS = d; d += 6 * D.rcl; m.rV = d; d += 6 * D.rcl; }
   m.bshape = i; i += nb; m.ben = i; i += nb;
   m.pair_a = i; i += npmax; m.pair_b = i; i += npmax;
   m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax;
   m.scal = i; i += 16;
-  m.Jr = nullptr; m.zl = nullptr; m.prof = nullptr; m.prof_stride = 0;
+  m.ranc = i; i += D.rcl;
+  m.Jr = nullptr; m.zl = nullptr; m.prof = nullptr; m.prof_stride = 0; m.gcb = m.gcl = nullptr;
 }
-B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax) {
-  m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.D = d; d += 6 * (size_t)cmax * cmax;
-  m.Cv = d; d += 3 * cmax; m.imp = d; d += 3 * cmax; m.acc = d; d += 3 * cmax; m.dv = d; d += 6 * nb;
+B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, const EnvDims& D) {
+  const int nb = D.nb, cmax = D.cmax, nmax = D.nmax;
+  if (D.ngc) { m.Jr = d; d += (size_t)3 * cmax * D.ngc; m.XJ = d; d += (size_t)3 * cmax * D.ngc; m.Xb = d; d += (size_t)D.ngc * D.ngc; m.dv = d; d += D.ngc; m.Lf = d; d += (size_t)D.ngc * D.ngc + D.ngc; m.gv = d; d += D.ngc; }
+  else { m.Lf = m.gv = nullptr; m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.dv = d; d += 6 * nb; }
+  m.D = d; d += 6 * (size_t)cmax * cmax;
+  m.Cv = d; d += 3 * cmax; m.imp = d; d += 3 * cmax; m.acc = d; d += 3 * cmax;
   m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.zl = d; d += nmax; m.work = d;
   m.gcoff = i; i += nb; m.bisl = i; i += nb;
   m.icon = i; i += cmax; m.cisl = i; i += cmax; m.corder = i; i += cmax;
   m.isl_start = i; i += nb + 1;
-  m.frow_c = i; i += nmax; m.frow_j = i; i += nmax; m.iwork = i;
+  m.frow_c = i; i += nmax; m.frow_j = i; i += nmax;
+  m.gcb = i; i += D.ngc; m.gcl = i; i += D.ngc;
+  m.iwork = i;
 }
-B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, int nb, int cmax, int nmax, int npmax) {
-  env_carve_small(m, d, i, nb, cmax, npmax);
-  env_carve_impact(m, d + env_small_doubles(nb, cmax, npmax), i + env_small_ints(nb, cmax, npmax), nb, cmax, nmax);
+B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, const EnvDims& D) {
+  env_carve_small(m, d, i, D);
+  env_carve_impact(m, d + env_small_doubles(D), i + env_small_ints(D), D);
 }
 
 // scal[] slots
@@ -176,7 +198,7 @@ B2M_HD B2M_INL V3 ang_vel(const BodyRef& b) { return b.enabled ? ld3(b.va) : V3(
 #include "boxbox_device.cuh"
 namespace b2m {
 
-B2M_HD inline double box_closest_point(const double* dims, const V3& point, V3& closest) {   // BoxPrimitive.cpp:788-836
+B2M_HD B2M_NOINL inline double box_closest_point(const double* dims, const V3& point, V3& closest) {   // BoxPrimitive.cpp:788-836
   const double ext[3] = {dims[0] * 0.5, dims[1] * 0.5, dims[2] * 0.5};
   const double pt[3] = {point.x, point.y, point.z};
   double cl[3] = {point.x, point.y, point.z};
@@ -192,7 +214,7 @@ B2M_HD inline double box_closest_point(const double* dims, const V3& point, V3& 
 }
 
 // signed distance + closest points for an ordered pair (PlanePrimitive.cpp:342-411, SpherePrimitive.cpp:104-135, BoxPrimitive.cpp:257-276)
-B2M_HD inline bool signed_dist_ordered(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
+B2M_HD B2M_NOINL inline bool signed_dist_ordered(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
   if (A.shape == SH_PLANE && B.shape == SH_BOX) {
     double min_dist = B2M_INF; V3 pb_best, pthis;
     for (int i = 0; i < 8; i++) {
@@ -239,7 +261,7 @@ B2M_HD inline bool signed_dist(const BodyRef& A, const BodyRef& B, double& dist,
   return false;
 }
 
-B2M_HD inline void orthonormal_basis(const V3& v1, V3& v2, V3& v3) {   // Ravelin Vector3d::determine_orthonormal_basis
+B2M_HD B2M_NOINL inline void orthonormal_basis(const V3& v1, V3& v2, V3& v3) {   // Ravelin Vector3d::determine_orthonormal_basis
   const double x = fabs(v1.x), y = fabs(v1.y), z = fabs(v1.z);
   V3 a;
   if (x < y) { if (x < z) a = V3(1, 0, 0); else a = V3(0, 0, 1); }
@@ -251,7 +273,7 @@ B2M_HD inline void orthonormal_basis(const V3& v1, V3& v2, V3& v3) {   // Raveli
 struct ContactOut { V3 p, n; int b1, b2; double dist; };
 
 // Contacts of one pair, at most `cap` (CCD.inl:3-82 dispatch and leaves).  Executed by ONE thread; returns the count found.
-B2M_HD inline int pair_contacts(const EnvMem& m, int ia, int ib, double TOL, ContactOut* out, int cap) {
+B2M_HD B2M_NOINL inline int pair_contacts(const EnvMem& m, int ia, int ib, double TOL, ContactOut* out, int cap) {
   const BodyRef A = body_ref(m, ia), B = body_ref(m, ib);
   int cnt = 0;
   if ((A.shape == SH_SPHERE && B.shape == SH_PLANE) || (A.shape == SH_PLANE && B.shape == SH_SPHERE)) {   // CCD.inl:805-846
@@ -353,7 +375,7 @@ B2M_HD B2M_INL bool collinear(const V3& a, const V3& b, const V3& c) {          
          rel_equal((b.z - a.z) * (c.x - a.x), (b.x - a.x) * (c.z - a.z)) &&
          rel_equal((b.x - a.x) * (c.y - a.y), (b.y - a.y) * (c.x - a.x));
 }
-B2M_HD inline double next_CA_box_plane(const BodyRef& box, const V3& rv_lin, const V3& rv_ang, const V3& normal, double offset0) {   // CCD.cpp:407-460
+B2M_HD B2M_NOINL inline double next_CA_box_plane(const BodyRef& box, const V3& rv_lin, const V3& rv_ang, const V3& normal, double offset0) {   // CCD.cpp:407-460
   double max_step = B2M_INF;
   const V3 nP = rotT(box.R, normal);
   const V3 p0 = normal * offset0;
@@ -372,7 +394,7 @@ B2M_HD inline double next_CA_box_plane(const BodyRef& box, const V3& rv_lin, con
 }
 
 // CCD::calc_CA_Euler_step for one pair (CCD.cpp:122-400).  Executed by ONE thread.
-B2M_HD inline double pair_CA(const EnvMem& m, int p) {
+B2M_HD B2M_NOINL inline double pair_CA(const EnvMem& m, int p) {
   const int ia = m.pair_a[p], ib = m.pair_b[p];
   const BodyRef A = body_ref(m, ia), B = body_ref(m, ib);
   const double pdist = m.pd_dist[p];
@@ -418,9 +440,30 @@ B2M_HD inline double pair_CA(const EnvMem& m, int p) {
   return fmin(B2M_INF, pdist / total);
 }
 
+// ---------- articulated body inside the env working set ----------
+// Links are bodies [rc_first, rc_first + rc_links); link 0 (the base) is a disabled body.  All moving links form ONE
+// super body whose generalized coordinates are the joint positions (ImpactConstraintHandler.cpp:1905-1916 collects
+// super bodies, :1817-1895 maps link wrenches through the link Jacobian); its representative in the island code is
+// the first moving link.
+B2M_HD B2M_INL bool is_link(const SimParams& P, int b) { return P.rc_links > 0 && b > P.rc_first && b < P.rc_first + P.rc_links; }
+B2M_HD B2M_INL int super_of(const SimParams& P, int b) { return is_link(P, b) ? P.rc_first + 1 : b; }
+
+// link poses, motion subspaces, spatial and COM velocities from (jq, jqd): what RCArticulatedBodyd::update_link_poses /
+// update_link_velocities do after set_generalized_coordinates / _velocity (RCArticulatedBody.cpp:102,142-143)
+template <class G>
+B2M_DEV B2M_NOINL void rc_refresh(const G& g, const SimParams& P, EnvMem& m) {
+  if (g.tid == 0) {
+    const RCTree& T = *P.rc;
+    RCState s; s.x = m.bx + 3 * P.rc_first; s.R = m.bR + 9 * P.rc_first; s.S = m.rS; s.v = m.rV;
+    rc_kinematics(T, m.jq, m.jqd, s);
+    for (int i = 1; i < T.n_links; i++) rc_link_velocity(s, i, m.bvl + 3 * (P.rc_first + i), m.bva + 3 * (P.rc_first + i));
+  }
+  g.sync();
+}
+
 // ---------- env load / store ----------
 template <class G>
-B2M_DEV void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
+B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
   const int nb = P.nb, ne = P.n_envs;
   for (int b = g.tid; b < nb; b += G::size) {
     m.bshape[b] = P.shape[(size_t)b * ne + e];
@@ -446,6 +489,12 @@ B2M_DEV void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
     m.scal[S_NPAIRS] = np;
     m.scal[S_ZLN] = P.zlast_n[e];
     m.scal[S_ZLDIRTY] = 0;
+    if (P.rc_links) { m.ranc[0] = 0; for (int i = 1; i < P.rc_links; i++) m.ranc[i] = m.ranc[P.rc->parent[i]] | (1 << i); }
+  }
+  if (P.rc_links) {
+    for (int k = g.tid; k < P.rc_links - 1; k += G::size) { m.jq[k] = P.jq[(size_t)k * ne + e]; m.jqd[k] = P.jqd[(size_t)k * ne + e]; m.jtau[k] = P.jtau[(size_t)k * ne + e]; }
+    g.sync();
+    rc_refresh(g, P, m);
   }
   g.sync();
   if (m.zl) {                                                   // ImpactConstraintHandler::_zlast, kept on chip for the whole launch
@@ -458,8 +507,16 @@ B2M_DEV void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
 // what: 1 positions, 2 velocities, 4 warm start
 enum { ST_POS = 1, ST_VEL = 2, ST_ZL = 4 };
 template <class G>
-B2M_DEV void env_store(const G& g, const SimParams& P, int e, const EnvMem& m, int what = ST_POS | ST_VEL | ST_ZL) {
+B2M_DEV B2M_NOINL void env_store(const G& g, const SimParams& P, int e, const EnvMem& m, int what = ST_POS | ST_VEL | ST_ZL) {
   const int nb = P.nb, ne = P.n_envs;
+  if (P.rc_links) {
+    if (what & ST_POS) for (int i = 1 + g.tid; i < P.rc_links; i += G::size) R_to_quat(m.bR + 9 * (P.rc_first + i), m.bq + 4 * (P.rc_first + i));
+    for (int k = g.tid; k < P.rc_links - 1; k += G::size) {
+      if (what & ST_POS) P.jq[(size_t)k * ne + e] = m.jq[k];
+      if (what & ST_VEL) P.jqd[(size_t)k * ne + e] = m.jqd[k];
+    }
+    g.sync();
+  }
   for (int k = g.tid; k < 3 * nb; k += G::size) {
     const int b = k / 3, c = k - 3 * b;
     if (!m.ben[b]) continue;
@@ -475,7 +532,7 @@ B2M_DEV void env_store(const G& g, const SimParams& P, int e, const EnvMem& m, i
 }
 
 template <class G>
-B2M_DEV void calc_pairwise_distances(const G& g, EnvMem& m) {       // ConstraintSimulator.cpp:450-468, one thread per pair
+B2M_DEV B2M_NOINL void calc_pairwise_distances(const G& g, EnvMem& m) {       // ConstraintSimulator.cpp:450-468, one thread per pair
   const int np = m.scal[S_NPAIRS];
   for (int p = g.tid; p < np; p += G::size) {
     double dist; V3 pa, pb;
@@ -488,9 +545,23 @@ B2M_DEV void calc_pairwise_distances(const G& g, EnvMem& m) {       // Constrain
 // Simulator::precalc_fwd_dyn + calc_fwd_dyn for free bodies + v += h a (Simulator.cpp:319-350,482-602;
 // TimeSteppingSimulator.cpp:181-192; GravityForce.cpp:32-48).  One thread per body.
 template <class G>
-B2M_DEV void fwd_dyn_integrate_velocity(const G& g, const SimParams& P, EnvMem& m, double h) {
+B2M_DEV B2M_NOINL void fwd_dyn_integrate_velocity(const G& g, const SimParams& P, EnvMem& m, double h, double t) {
+  if (P.rc_links) {   // Simulator.cpp:339-348 controller, :544-553 RCArticulatedBodyd::calc_fwd_dyn (ABA or CRB), then qd += h qdd
+    if (g.tid == 0) {
+      const RCTree& T = *P.rc;
+      const int nd = T.n_links - 1;
+      RCState s; s.x = m.bx + 3 * P.rc_first; s.R = m.bR + 9 * P.rc_first; s.S = m.rS; s.v = m.rV;
+      double tau[B2M_MAX_LINKS], qdd[B2M_MAX_LINKS], Hw[(B2M_MAX_LINKS - 1) * (B2M_MAX_LINKS - 1)];
+      rc_controller(T, m.jq, m.jqd, t, m.jtau, tau);
+      const double gv[3] = {P.gx, P.gy, P.gz};
+      rc_fwd_dyn(T, T.fdyn, s, m.bmass + P.rc_first, m.bJ + 3 * P.rc_first, m.jqd, tau, gv, qdd, Hw);
+      for (int k = 0; k < nd; k++) m.jqd[k] = m.jqd[k] + qdd[k] * h;
+    }
+    g.sync();
+    rc_refresh(g, P, m);
+  }
   for (int b = g.tid; b < P.nb; b += G::size) {
-    if (!m.ben[b]) continue;
+    if (!m.ben[b] || is_link(P, b)) continue;
     const double* R = m.bR + 9 * b; const double* J = m.bJ + 3 * b;
     const double mass = m.bmass[b];
     const V3 f = V3(P.gx, P.gy, P.gz) * mass;
@@ -509,10 +580,11 @@ B2M_DEV void fwd_dyn_integrate_velocity(const G& g, const SimParams& P, EnvMem& 
 
 // position half of the semi-implicit Euler step with conservative advancement (TimeSteppingSimulator.cpp:119-168)
 template <class G>
-B2M_DEV double integrate_positions_CA(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
+B2M_DEV B2M_NOINL double integrate_positions_CA(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc) {
   const int nb = P.nb;
   for (int k = g.tid; k < 3 * nb; k += G::size) m.xsave[k] = m.bx[k];
   for (int k = g.tid; k < 4 * nb; k += G::size) m.qsave[k] = m.bq[k];
+  if (P.rc_links) for (int k = g.tid; k < P.rc_links - 1; k += G::size) m.jqsave[k] = m.jq[k];
   g.sync();
   double h = 0.0;
   const double min_step = P.min_step_env ? P.min_step_env[e] : P.min_step_size;
@@ -527,8 +599,13 @@ B2M_DEV double integrate_positions_CA(const G& g, const SimParams& P, int e, Env
     double tc = fmax(min_step, CA);
     tc = fmin(dt - h, tc);
     g.sync();
+    if (P.rc_links) {   // joint coordinates are their own Euler coordinates: q = qsave + (h + tc) qd
+      for (int k = g.tid; k < P.rc_links - 1; k += G::size) m.jq[k] = m.jqd[k] * (h + tc) + m.jqsave[k];
+      g.sync();
+      rc_refresh(g, P, m);
+    }
     for (int b = g.tid; b < nb; b += G::size) {
-      if (!m.ben[b]) continue;
+      if (!m.ben[b] || is_link(P, b)) continue;
       const double s = h + tc;
       const double qx = m.qsave[4 * b], qy = m.qsave[4 * b + 1], qz = m.qsave[4 * b + 2], qw = m.qsave[4 * b + 3];
       const V3 w = ld3(m.bva + 3 * b), vl = ld3(m.bvl + 3 * b);
@@ -551,7 +628,7 @@ B2M_DEV double integrate_positions_CA(const G& g, const SimParams& P, int e, Env
 
 // ConstraintSimulator::find_unilateral_constraints (:488-537) + preprocess_constraint (:390-417): contacts in pair order
 template <class G>
-B2M_DEV void find_unilateral_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+B2M_DEV B2M_NOINL void find_unilateral_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
   const int np = m.scal[S_NPAIRS], nb = P.nb, ne = P.n_envs;
   if (g.tid == 0) {
     int nc = 0; bool overflow = false;
@@ -584,7 +661,7 @@ B2M_HD B2M_INL double constraint_vel(const EnvMem& m, int c) {
 }
 
 // 6x6 SPD inverse through Cholesky, same order as the checker's inverse_SPD (ImpactConstraintHandler.cpp:1599-1611)
-B2M_HD inline void inverse_spd6(double* A) {
+B2M_HD B2M_NOINL inline void inverse_spd6(double* A) {
   double L[36];
   for (int i = 0; i < 36; i++) L[i] = A[i];
   for (int j = 0; j < 6; j++) {
@@ -616,9 +693,157 @@ B2M_HD B2M_INL double Dn(const EnvMem& m, int nc, int d1, int d2, int i, int j) 
   return (d1 <= d2) ? m.D[(size_t)dblk(d1, d2) * nc * nc + (size_t)i * nc + j] : m.D[(size_t)dblk(d2, d1) * nc * nc + (size_t)j * nc + i];
 }
 
+// n x n SPD inverse through Cholesky (LinAlgd::inverse_SPD, ImpactConstraintHandler.cpp:1605-1607): A (column-major,
+// leading dimension lda) is replaced by its inverse; L: n*n + n doubles of scratch.  One thread; same operation order as
+// the checker.
+B2M_HD B2M_NOINL inline void inverse_spd_n(double* A, int n, int lda, double* L) {
+  double* e = L + (size_t)n * n;
+  for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) L[(size_t)j * n + i] = A[(size_t)j * lda + i];
+  for (int j = 0; j < n; j++) {
+    double d = L[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d = fma(-L[(size_t)k * n + j], L[(size_t)k * n + j], d);
+    d = sqrt(d);
+    L[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double s = L[(size_t)j * n + i];
+      for (int k = 0; k < j; k++) s = fma(-L[(size_t)k * n + i], L[(size_t)k * n + j], s);
+      L[(size_t)j * n + i] = s / d;
+    }
+  }
+  for (int j = 0; j < n; j++) {
+    for (int i = 0; i < n; i++) e[i] = (i == j) ? 1.0 : 0.0;
+    for (int i = 0; i < n; i++) { double s = e[i]; for (int k = 0; k < i; k++) s = fma(-L[(size_t)k * n + i], e[k], s); e[i] = s / L[(size_t)i * n + i]; }
+    for (int i = n - 1; i >= 0; i--) { double s = e[i]; for (int k = i + 1; k < n; k++) s = fma(-L[(size_t)i * n + k], e[k], s); e[i] = s / L[(size_t)i * n + i]; }
+    for (int i = 0; i < n; i++) A[(size_t)j * lda + i] = e[i];
+  }
+}
+
+// ImpactConstraintHandler::compute_problem_data (:1898-2166) with an articulated body in the scene: dense rows over the
+// island's generalized coordinates [free bodies 6 each ..., joint coordinates], X = blockdiag(M_b^-1, H(q)^-1).
+// A contact wrench [d, r x d] on link L maps to joint k (an ancestor of L) as d . S_k(lin) + (p x d) . S_k(ang) with S_k
+// the joint's world-frame motion subspace about the world origin -- RCArticulatedBodyd::calc_jacobian (:1875) folded in.
+template <class G>
+B2M_DEV B2M_NOINL void compute_problem_data_dense(const G& g, const SimParams& P, EnvMem& m) {
+  const int nc = m.scal[S_NC], nb = P.nb, ngc = m.scal[S_NGC];
+  const int rep = P.rc_first + 1;
+  for (int t = g.tid; t < ngc * ngc; t += G::size) m.Xb[t] = 0.0;
+  g.sync();
+  if (g.tid == 0 && m.gcoff[rep] >= 0) {                 // joint-space inertia by CRB, then inverse_SPD
+    const RCTree& T = *P.rc;
+    RCState s; s.x = m.bx + 3 * P.rc_first; s.R = m.bR + 9 * P.rc_first; s.S = m.rS; s.v = m.rV;
+    double* H = m.Xb + (size_t)m.gcoff[rep] * ngc + m.gcoff[rep];
+    rc_crb(T, s, m.bmass + P.rc_first, m.bJ + 3 * P.rc_first, H, ngc);
+    inverse_spd_n(H, T.n_links - 1, ngc, m.Lf);
+  }
+  for (int b = g.tid; b < nb; b += G::size) {            // free bodies: 6x6 blocks as in the block layout
+    if (m.gcoff[b] < 0 || is_link(P, b)) continue;
+    double Mg[36];
+    for (int i = 0; i < 36; i++) Mg[i] = 0.0;
+    const double* R = m.bR + 9 * b; const double* J = m.bJ + 3 * b;
+    for (int k = 0; k < 3; k++) Mg[k * 6 + k] = m.bmass[b];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        double s = 0.0;
+        for (int k = 0; k < 3; k++) s += R[r * 3 + k] * J[k] * R[c * 3 + k];
+        Mg[(3 + c) * 6 + (3 + r)] = s;
+      }
+    inverse_spd6(Mg);
+    const int o = m.gcoff[b];
+    for (int c = 0; c < 6; c++) for (int r = 0; r < 6; r++) m.Xb[(size_t)(o + c) * ngc + o + r] = Mg[c * 6 + r];
+  }
+  // generalized velocity of the island
+  for (int k = g.tid; k < ngc; k += G::size) {
+    const int b = m.gcb[k], l = m.gcl[k];
+    m.gv[k] = (b == rep && P.rc_links) ? m.jqd[l] : (l < 3 ? m.bvl[3 * b + l] : m.bva[3 * b + l - 3]);
+  }
+  // Jacobian rows, one thread per (dir, contact, coordinate)
+  for (int t = g.tid; t < 3 * nc * ngc; t += G::size) {
+    const int k = t % ngc, i = (t / ngc) % nc, d = t / (ngc * nc);
+    const int c = m.icon[i];
+    const int sb = m.gcb[k], l = m.gcl[k];
+    const V3 dir0 = d == 0 ? ld3(m.cnrm + 3 * c) : (d == 1 ? ld3(m.ct1 + 3 * c) : ld3(m.ct2 + 3 * c));
+    const V3 p = ld3(m.cp + 3 * c);
+    double val = 0.0;
+    for (int blk = 0; blk < 2; blk++) {
+      const int bi = blk == 0 ? m.cb1[c] : m.cb2[c];
+      if (!m.ben[bi]) continue;
+      const V3 dir = blk == 0 ? dir0 : -dir0;
+      if (is_link(P, bi)) {
+        if (sb != rep) continue;
+        const int j = l + 1;                                      // joint of link j
+        if (!((m.ranc[bi - P.rc_first] >> j) & 1)) continue;
+        const double* S = m.rS + 6 * j;
+        const V3 pxd = cross(p, dir);
+        val += (dir.x * S[3] + dir.y * S[4] + dir.z * S[5]) + (pxd.x * S[0] + pxd.y * S[1] + pxd.z * S[2]);
+      } else {
+        if (sb != bi) continue;
+        if (l < 3) val += (l == 0 ? dir.x : (l == 1 ? dir.y : dir.z));
+        else { const V3 rxd = cross(p - ld3(m.bx + 3 * bi), dir); val += (l == 3 ? rxd.x : (l == 4 ? rxd.y : rxd.z)); }
+      }
+    }
+    m.Jr[t] = val;
+  }
+  g.sync();
+  // X_CdT = (Cd X)^T, kept as rows: XJ[row][k] = sum_kk Jr[row][kk] X[kk][k]
+  for (int t = g.tid; t < 3 * nc * ngc; t += G::size) {
+    const int k = t % ngc, row = t / ngc;
+    const double* jr = m.Jr + (size_t)row * ngc;
+    double s = 0.0;
+    for (int kk = 0; kk < ngc; kk++) s = fma(jr[kk], m.Xb[(size_t)k * ngc + kk], s);
+    m.XJ[t] = s;
+  }
+  g.sync();
+  // Delassus blocks Cd1 X Cd2^T
+  for (int t = g.tid; t < 6 * nc * nc; t += G::size) {
+    const int j = t % nc, i = (t / nc) % nc, bk = t / (nc * nc);
+    const int d1 = bk < 3 ? 0 : (bk < 5 ? 1 : 2), d2 = bk < 3 ? bk : (bk < 5 ? bk - 2 : 2);
+    const double* jr = m.Jr + ((size_t)d1 * nc + i) * ngc;
+    const double* xj = m.XJ + ((size_t)d2 * nc + j) * ngc;
+    double s = 0.0;
+    for (int k = 0; k < ngc; k++) s = fma(jr[k], xj[k], s);
+    m.D[t] = s;
+  }
+  for (int t = g.tid; t < 3 * nc; t += G::size) {
+    const double* jr = m.Jr + (size_t)t * ngc;
+    double s = 0.0;
+    for (int k = 0; k < ngc; k++) s = fma(jr[k], m.gv[k], s);
+    m.Cv[t] = s;
+    m.imp[t] = 0.0;
+  }
+  g.sync();
+}
+
+// update_from_stacked (:298-397), dense layout: generalized velocity += X_CnT cn + X_CsT cs + X_CtT ct
+template <class G>
+B2M_DEV B2M_NOINL void apply_to_bodies_dense(const G& g, const SimParams& P, EnvMem& m, const double* imp) {
+  const int nc = m.scal[S_NC], ngc = m.scal[S_NGC];
+  const int rep = P.rc_first + 1;
+  for (int k = g.tid; k < ngc; k += G::size) {
+    double s3[3];
+    for (int d = 0; d < 3; d++) {
+      double s = 0.0;
+      for (int i = 0; i < nc; i++) s = fma(m.XJ[((size_t)d * nc + i) * ngc + k], imp[d * nc + i], s);
+      s3[d] = s;
+    }
+    m.dv[k] = (s3[0] + s3[1]) + s3[2];
+  }
+  g.sync();
+  bool rc_touched = false;
+  for (int k = g.tid; k < ngc; k += G::size) {
+    const int b = m.gcb[k], l = m.gcl[k];
+    if (b == rep && P.rc_links) m.jqd[l] = m.jqd[l] + m.dv[k];
+    else if (l < 3) m.bvl[3 * b + l] = m.bvl[3 * b + l] + m.dv[k];
+    else m.bva[3 * b + l - 3] = m.bva[3 * b + l - 3] + m.dv[k];
+  }
+  rc_touched = P.rc_links && m.gcoff[rep] >= 0;
+  g.sync();
+  if (rc_touched) rc_refresh(g, P, m);
+}
+
 // ImpactConstraintHandler::compute_problem_data (:1898-2166) for the island whose contacts are icon[0..nc)
 template <class G>
-B2M_DEV void compute_problem_data(const G& g, const SimParams& P, EnvMem& m) {
+B2M_DEV B2M_NOINL void compute_problem_data(const G& g, const SimParams& P, EnvMem& m) {
+  if (P.ngc) { compute_problem_data_dense(g, P, m); return; }
   const int nc = m.scal[S_NC], nb = P.nb;
   // X = blockdiag(inverse_SPD(generalized inertia)) (:1590-1611), one thread per island body
   for (int b = g.tid; b < nb; b += G::size) {
@@ -702,7 +927,7 @@ B2M_DEV void compute_problem_data(const G& g, const SimParams& P, EnvMem& m) {
 
 // QP-as-LCP (ImpactConstraintHandlerQP.cpp:129-148,216,271-497), nl = 0.  Returns n.
 template <class G>
-B2M_DEV int build_qp_lcp(const G& g, const SimParams& P, EnvMem& m) {
+B2M_DEV B2M_NOINL int build_qp_lcp(const G& g, const SimParams& P, EnvMem& m) {
   const int nc = m.scal[S_NC];
   const int NV = 5 * nc;
   if (g.tid == 0) {
@@ -760,7 +985,7 @@ B2M_DEV int build_qp_lcp(const G& g, const SimParams& P, EnvMem& m) {
 
 // Anitescu-Potra LCP (ImpactConstraintHandlerLCP.cpp:94-310), nl = 0.  Returns n.
 template <class G>
-B2M_DEV int build_ap_lcp(const G& g, const SimParams& P, EnvMem& m) {
+B2M_DEV B2M_NOINL int build_ap_lcp(const G& g, const SimParams& P, EnvMem& m) {
   const int NC = m.scal[S_NC];
   const int NCONST = 5 * NC;
   if (g.tid == 0) {
@@ -809,7 +1034,8 @@ B2M_DEV int build_ap_lcp(const G& g, const SimParams& P, EnvMem& m) {
 
 // update_from_stacked (:298-397) without bilateral joints: v += X_CnT cn + X_CsT cs + X_CtT ct, impulses from `imp`
 template <class G>
-B2M_DEV void apply_to_bodies(const G& g, const SimParams& P, EnvMem& m, const double* imp) {
+B2M_DEV B2M_NOINL void apply_to_bodies(const G& g, const SimParams& P, EnvMem& m, const double* imp) {
+  if (P.ngc) { apply_to_bodies_dense(g, P, m, imp); return; }
   const int nc = m.scal[S_NC], nb = P.nb;
   for (int t = g.tid; t < 6 * nb; t += G::size) {
     const int b = t / 6, k = t - 6 * b;
@@ -839,7 +1065,7 @@ B2M_DEV void apply_to_bodies(const G& g, const SimParams& P, EnvMem& m, const do
 
 // update_constraint_velocities_from_impulses (:427-464), nl = 0
 template <class G>
-B2M_DEV void update_constraint_velocities(const G& g, EnvMem& m, const double* imp) {
+B2M_DEV B2M_NOINL void update_constraint_velocities(const G& g, EnvMem& m, const double* imp) {
   const int nc = m.scal[S_NC];
   for (int t = g.tid; t < 3 * nc; t += G::size) {
     const int i = t % nc, d = t / nc;
@@ -864,7 +1090,7 @@ B2M_DEV double min_constraint_velocity(const G& g, const EnvMem& m) {           
 
 // solve_qp_work (ImpactConstraintHandlerQP.cpp:94-263): fills imp = [cn | cs | ct].  Returns false when the env is deferred.
 template <class G>
-B2M_DEV bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
+B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int nc = m.scal[S_NC];
   int n;
   { B2M_PROF_T0(m); n = build_qp_lcp(g, P, m); B2M_PROF_ADD(m, g, PH_BUILD); }
@@ -941,7 +1167,7 @@ B2M_DEV bool apply_qp_model(const G& g, const SimParams& P, int e, EnvMem& m, un
 
 // apply_ap_model (ImpactConstraintHandlerLCP.cpp:94-370): imp = this solve, acc += imp (propagate_impulse_data)
 template <class G>
-B2M_DEV bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
+B2M_DEV B2M_NOINL bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int NC = m.scal[S_NC];
   const int n = build_ap_lcp(g, P, m);
   if (n > P.nmax) { if (g.tid == 0) { lc[CNT_OVERFLOW]++; } for (int t = g.tid; t < 3 * NC; t += G::size) m.imp[t] = 0.0; g.sync(); return true; }
@@ -1001,7 +1227,7 @@ B2M_DEV bool apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, un
 
 // calc_impacting_unilateral_constraint_forces (ConstraintSimulator.cpp:298-355) -> apply_model (ImpactConstraintHandler.cpp:96-168)
 template <class G>
-B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
+B2M_DEV B2M_NOINL bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
   const int ncon = m.scal[S_NCON], nb = P.nb;
   if (ncon == 0) return true;
   bool impacting = false;
@@ -1012,7 +1238,7 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
   // neighbours in contact (edge insertion) order, each visited body picks up its remaining contacts in list order.
   if (g.tid == 0) {
     unsigned nodes = 0;
-    for (int c = 0; c < ncon; c++) { if (m.ben[m.cb1[c]]) nodes |= 1u << m.cb1[c]; if (m.ben[m.cb2[c]]) nodes |= 1u << m.cb2[c]; }
+    for (int c = 0; c < ncon; c++) { if (m.ben[m.cb1[c]]) nodes |= 1u << super_of(P, m.cb1[c]); if (m.ben[m.cb2[c]]) nodes |= 1u << super_of(P, m.cb2[c]); }
     for (int b = 0; b < nb; b++) m.bisl[b] = -1;
     for (int c = 0; c < ncon; c++) m.cisl[c] = -1;
     int nisl = 0, nord = 0;
@@ -1029,13 +1255,13 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
         processed |= 1u << node;
         m.bisl[node] = nisl;
         for (int c = 0; c < ncon; c++) {
-          const int b1 = m.cb1[c], b2 = m.cb2[c];
-          if (!(m.ben[b1] && m.ben[b2])) continue;
+          if (!(m.ben[m.cb1[c]] && m.ben[m.cb2[c]])) continue;
+          const int b1 = super_of(P, m.cb1[c]), b2 = super_of(P, m.cb2[c]);
           const int nbr = (b1 == node) ? b2 : ((b2 == node) ? b1 : -1);
           if (nbr >= 0 && !((queued >> nbr) & 1u)) { queued |= 1u << nbr; queue[qt++] = nbr; }
         }
         for (int c = 0; c < ncon; c++)
-          if (m.cisl[c] < 0 && (m.cb1[c] == node || m.cb2[c] == node)) { m.cisl[c] = nisl; m.corder[nord++] = c; }
+          if (m.cisl[c] < 0 && ((m.ben[m.cb1[c]] && super_of(P, m.cb1[c]) == node) || (m.ben[m.cb2[c]] && super_of(P, m.cb2[c]) == node))) { m.cisl[c] = nisl; m.corder[nord++] = c; }
       }
       nisl++;
     }
@@ -1054,7 +1280,19 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
       const int s0 = m.isl_start[k], nc = m.isl_start[k + 1] - s0;
       for (int i = 0; i < nc; i++) m.icon[i] = m.corder[s0 + i];
       int gc = 0;
-      for (int b = 0; b < nb; b++) { if (m.bisl[b] == k && m.ben[b]) { m.gcoff[b] = gc; gc += 6; } else m.gcoff[b] = -1; }
+      for (int b = 0; b < nb; b++) {
+        if (is_link(P, b)) {                      // every moving link shares the articulated body's coordinates
+          const int rep = P.rc_first + 1;
+          if (b == rep) {
+            if (m.bisl[rep] == k) { m.gcoff[b] = gc; for (int l = 0; l < P.rc_links - 1; l++) { m.gcb[gc + l] = rep; m.gcl[gc + l] = l; } gc += P.rc_links - 1; }
+            else m.gcoff[b] = -1;
+          } else m.gcoff[b] = m.gcoff[rep];
+        } else if (m.bisl[b] == k && m.ben[b]) {
+          m.gcoff[b] = gc;
+          if (P.ngc) for (int l = 0; l < 6; l++) { m.gcb[gc + l] = b; m.gcl[gc + l] = l; }
+          gc += 6;
+        } else m.gcoff[b] = -1;
+      }
       m.scal[S_NC] = nc; m.scal[S_NGC] = gc;
     }
     g.sync();
@@ -1079,9 +1317,9 @@ B2M_DEV bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& 
 // dynamics + velocity update, distances, contacts.  Returns h; `impacting` says whether the constraint handler has
 // work to do (ConstraintSimulator.cpp:298-355 / ImpactConstraintHandler.cpp:96-120 early-outs).
 template <class G>
-B2M_DEV double mini_step_advance(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc, bool& impacting) {
+B2M_DEV double mini_step_advance(const G& g, const SimParams& P, int e, EnvMem& m, double dt, double t, unsigned long long* lc, bool& impacting) {
   const double h = integrate_positions_CA(g, P, e, m, dt, lc);
-  fwd_dyn_integrate_velocity(g, P, m, h);
+  fwd_dyn_integrate_velocity(g, P, m, h, t);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
   const int ncon = m.scal[S_NCON];
@@ -1097,7 +1335,8 @@ B2M_DEV void mini_step_account(const G& g, const SimParams& P, const EnvMem& m, 
   if (g.tid == 0) {     // F_fd = 60 per free body (Newton-Euler); F_narrow = 8 vertices x 20 (box) or 20 (sphere) per pair and distance pass
     lc[CNT_MINI_STEPS]++;
     unsigned long long f = 0;
-    for (int b = 0; b < P.nb; b++) if (m.ben[b]) f += 60;
+    for (int b = 0; b < P.nb; b++) if (m.ben[b] && !is_link(P, b)) f += 60;
+    if (P.rc_links) f += 500ull * (P.rc_links - 1);   // ABA, Featherstone's operation count
     for (int p = 0; p < m.scal[S_NPAIRS]; p++) f += 3 * ((m.bshape[m.pair_a[p]] == SH_BOX || m.bshape[m.pair_b[p]] == SH_BOX) ? 160 : 20);
     lc[CNT_ASM_FLOPS] += f;
   }
@@ -1113,9 +1352,9 @@ B2M_HD B2M_INL int contacts_lcp_dim(const EnvMem& m, int ncon, int model) {
 
 // TimeSteppingSimulator::do_mini_step (:114-222); returns h, or -1 when the env is deferred
 template <class G>
-B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, unsigned long long* lc, EnvCtx& cx) {
+B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, double t, unsigned long long* lc, EnvCtx& cx) {
   bool impacting;
-  const double h = mini_step_advance(g, P, e, m, dt, lc, impacting);
+  const double h = mini_step_advance(g, P, e, m, dt, t, lc, impacting);
   if (impacting && !process_constraints(g, P, e, m, lc, cx)) return -1.0;
   mini_step_account(g, P, m, lc);
   return h;
@@ -1124,10 +1363,16 @@ B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, do
 // The rest of one TimeSteppingSimulator::step (:433-455) from `h` seconds into it; the env is loaded.  Returns false when deferred.
 template <class G>
 B2M_DEV bool env_finish_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, double h, double& t, unsigned long long* lc, EnvCtx& cx) {
+  int stalled = 0;
   while (h < dt) {
-    const double hh = do_mini_step(g, P, e, m, dt - h, lc, cx);
+    const double hh = do_mini_step(g, P, e, m, dt - h, t, lc, cx);
     if (hh < 0.0) return false;
     h += hh; t += hh;
+    // The reference loops here until time advances (TimeSteppingSimulator.cpp:439-441) and leaves through an exception
+    // when an impact cannot be resolved (ImpactConstraintHandlerQP.cpp:224).  A batch cannot throw: after
+    // B2M_MAX_STALL zero-length mini-steps in a row the env gives up the rest of this step and is counted as failed.
+    stalled = (hh > 0.0) ? 0 : stalled + 1;
+    if (stalled >= B2M_MAX_STALL) { if (g.tid == 0) lc[CNT_LCP_FAIL]++; break; }
   }
   if (g.tid == 0) lc[CNT_ENV_STEPS]++;
   return true;
@@ -1175,7 +1420,7 @@ B2M_DEV void env_advance(const G& g, const SimParams& P, int e, EnvMem& m, doubl
   bool parked = false;
   while (h < dt) {
     bool impacting;
-    const double hh = mini_step_advance(g, P, e, m, dt - h, lc, impacting);
+    const double hh = mini_step_advance(g, P, e, m, dt - h, t, lc, impacting);
     if (impacting) {
       if (g.tid == 0) {
         P.hacc[e] = h; P.hpend[e] = hh;

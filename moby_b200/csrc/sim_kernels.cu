@@ -49,6 +49,11 @@ struct b200moby_sim {
   std::vector<cudaEvent_t> side_done;
   cudaEvent_t fork = nullptr;
   int rc_links = 0, rc_dof = 0;   // articulated body (0: none)
+  // per-kernel profile (b200moby_get_kernel_profile): slot 0 advance, 1..n impact classes, n+1 stragglers, n+2 finish
+  bool ktiming = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev_free;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> kev_pending;
+  std::vector<double> kms; std::vector<long long> klaunches;
 };
 
 namespace {
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(256) stage_warp_kernel(SimParams P, int stage,
   for (int e = blockIdx.x * wpb + w; e < ne; e += gridDim.x * wpb) {
     env_load(g, P, e, m);
     if (stage == STAGE_FWD_DYN) {
-      fwd_dyn_integrate_velocity(g, P, m, o.dt);
+      fwd_dyn_integrate_velocity(g, P, m, o.dt, P.time[e]);
       for (int k = g.tid; k < 3 * P.nb; k += 32) { const int b = k / 3, c = k - 3 * b; if (m.ben[b]) { P.v[((size_t)b * 6 + c) * ne + e] = m.bvl[k]; P.v[((size_t)b * 6 + 3 + c) * ne + e] = m.bva[k]; } }
     } else {
       calc_pairwise_distances(g, m);
@@ -152,10 +157,6 @@ const void* impact_block_ptr(int nt) { return nt == 64 ? b2m_k_impact_block64() 
 
 int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
 
-size_t env_bytes(int nb, int cmax, int nmax, int npmax) {
-  return ((env_doubles(nb, cmax, nmax, npmax) + 1) & ~(size_t)1) * sizeof(double) + ((env_ints(nb, cmax, nmax, npmax) + 3) & ~(size_t)3) * sizeof(int);
-}
-
 b200moby_status plan_grid(const void* kernel, int threads, size_t shmem, int sms, int work, int* grid) {
   B2M_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX));
   int per_sm = 0;
@@ -168,8 +169,9 @@ b200moby_status plan_grid(const void* kernel, int threads, size_t shmem, int sms
 // Shared memory a kernel needs for `slots` working sets of `per` bytes, or -- when one working set does not fit an SM --
 // a global scratch buffer with one slice per resident group (cp.gscratch / cp.gstride; the launch then asks for no
 // dynamic shared memory).
-b200moby_status plan_memory(b200moby_sim* h, const void* kernel, ClassPlan& cp, int nb, int npmax, int slots_max, int work) {
-  const size_t ed = (env_doubles(nb, cp.cmax, cp.nmax, npmax) + 1) & ~(size_t)1, ei = (env_ints(nb, cp.cmax, cp.nmax, npmax) + 3) & ~(size_t)3;
+b200moby_status plan_memory(b200moby_sim* h, const void* kernel, ClassPlan& cp, int slots_max, int work) {
+  EnvDims D = env_dims(h->P); D.cmax = cp.cmax; D.nmax = cp.nmax;
+  const size_t ed = (env_doubles(D) + 1) & ~(size_t)1, ei = (env_ints(D) + 3) & ~(size_t)3;
   const size_t per = ed * sizeof(double) + ei * sizeof(int);
   b200moby_status st;
   if (per <= B2M_SMEM_MAX) {
@@ -196,8 +198,9 @@ b200moby_status plan_launch(b200moby_sim* h) {
   B2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
   h->sms = sms;
   const int nb = h->nb, ne = h->n_envs;
-  h->env_d = (env_doubles(nb, h->cmax, h->nmax, h->npmax) + 1) & ~(size_t)1;
-  h->env_i = (env_ints(nb, h->cmax, h->nmax, h->npmax) + 3) & ~(size_t)3;
+  const EnvDims D0 = env_dims(h->P);
+  h->env_d = (env_doubles(D0) + 1) & ~(size_t)1;
+  h->env_i = (env_ints(D0) + 3) & ~(size_t)3;
   h->fused = env_int("B200MOBY_FUSED", 0) != 0;
   h->rounds = std::max(1, std::min(B2M_ROUNDS_MAX, env_int("B200MOBY_ROUNDS", 2)));
   b200moby_status st;
@@ -206,13 +209,13 @@ b200moby_status plan_launch(b200moby_sim* h) {
     ClassPlan& f = h->fullws;
     f.nmax = h->nmax; f.cmax = h->cmax; f.threads = 32;
     B2M_CUDA(cudaFuncSetAttribute(b2m_k_step_warp(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX));
-    if ((st = plan_memory(h, b2m_k_finish(), f, nb, h->npmax, 1, ne)) != B200MOBY_OK) return st;
+    if ((st = plan_memory(h, b2m_k_finish(), f, 1, ne)) != B200MOBY_OK) return st;
     h->shmem = f.shmem; h->wpb = 1; h->grid = f.gscratch ? f.grid : ne; h->fin_grid = f.grid;
     h->P.gscratch = f.gscratch; h->P.gstride = f.gstride;
   }
   // advance: warps_per_block envs per block, small segment only
   {
-    const size_t sd = (env_small_doubles(nb, h->cmax, h->npmax) + 1) & ~(size_t)1, si = (env_small_ints(nb, h->cmax, h->npmax) + 3) & ~(size_t)3;
+    const size_t sd = (env_small_doubles(D0) + 1) & ~(size_t)1, si = (env_small_ints(D0) + 3) & ~(size_t)3;
     const size_t per = sd * sizeof(double) + si * sizeof(int);
     int wpb = env_int("B200MOBY_ADV_WPB", 4);
     while (wpb > 1 && per * wpb > B2M_SMEM_MAX) wpb--;
@@ -233,14 +236,28 @@ b200moby_status plan_launch(b200moby_sim* h) {
       else if (c.nmax > big_n) c.threads = 256;
       else c.threads = bthreads <= 64 ? 64 : (bthreads <= 128 ? 128 : 256);
       const void* kern = c.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(c.threads);
-      if ((st = plan_memory(h, kern, c, nb, h->npmax, 4, ne)) != B200MOBY_OK) return st;
+      if ((st = plan_memory(h, kern, c, 4, ne)) != B200MOBY_OK) return st;
       h->classes.push_back(c);
     }
     h->P.n_classes = (int)h->classes.size();
     ClassPlan& sg = h->straggler;
     sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = 256;
-    if ((st = plan_memory(h, impact_block_ptr(256), sg, nb, h->npmax, 1, ne)) != B200MOBY_OK) return st;
+    if ((st = plan_memory(h, impact_block_ptr(256), sg, 1, ne)) != B200MOBY_OK) return st;
   }
+  return B200MOBY_OK;
+}
+
+// launch with optional event bracketing on the launch's own stream (per-kernel durations for bench.py's roofline block)
+b200moby_status timed_launch(b200moby_sim* h, int kslot, const void* kernel, dim3 grid, dim3 block, void** args, size_t shmem, cudaStream_t s) {
+  std::pair<cudaEvent_t, cudaEvent_t> ev(nullptr, nullptr);
+  if (h->ktiming) {
+    if (h->kev_free.empty()) { B2M_CUDA(cudaEventCreate(&ev.first)); B2M_CUDA(cudaEventCreate(&ev.second)); }
+    else { ev = h->kev_free.back(); h->kev_free.pop_back(); }
+    B2M_CUDA(cudaEventRecord(ev.first, s));
+  }
+  B2M_CUDA(cudaLaunchKernel(kernel, grid, block, args, shmem, s));
+  if (h->ktiming) { B2M_CUDA(cudaEventRecord(ev.second, s)); h->kev_pending.push_back(std::make_pair(kslot, ev)); }
+  h->launches++;
   return B200MOBY_OK;
 }
 
@@ -248,38 +265,42 @@ b200moby_status plan_launch(b200moby_sim* h) {
 // next advance; the finish kernel takes whatever the rounds left over.  All launches are asynchronous on `s`.
 b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
   SimParams& P = h->P;
+  b200moby_status st;
+  const int ncls = (int)h->classes.size();
   B2M_CUDA(cudaMemsetAsync(P.qctl, 0, sizeof(int) * 2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1), s));
   for (int r = 0; r < h->rounds; r++) {
-    { void* a[] = {&P, &dt, &r, &h->adv_wpb};
-      B2M_CUDA(cudaLaunchKernel(b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)); h->launches++; }
+    { SimParams Pa = P; Pa.kslot = 0;
+      void* a[] = {&Pa, &dt, &r, &h->adv_wpb};
+      if ((st = timed_launch(h, 0, b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)) != B200MOBY_OK) return st; }
     const bool conc = h->concurrent && h->classes.size() > 1;
     if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
     for (size_t c = 0; c < h->classes.size(); c++) {
       ClassPlan& cp = h->classes[c];
-      SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax; Pc.gscratch = cp.gscratch; Pc.gstride = cp.gstride;
+      SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax; Pc.gscratch = cp.gscratch; Pc.gstride = cp.gstride; Pc.kslot = 1 + (int)c;
       int slot = (int)c;
       cudaStream_t sc = conc ? h->side[c] : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
       if (cp.threads == 32) {
         void* a[] = {&Pc, &dt, &r, &slot, &cp.wpb};
-        B2M_CUDA(cudaLaunchKernel(b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc));
+        st = timed_launch(h, 1 + (int)c, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
       } else {
         Pc.pivot_budget = 0;
         void* a[] = {&Pc, &dt, &r, &slot};
-        B2M_CUDA(cudaLaunchKernel(impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc));
+        st = timed_launch(h, 1 + (int)c, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc);
       }
+      if (st != B200MOBY_OK) return st;
       if (conc) { B2M_CUDA(cudaEventRecord(h->side_done[c], sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->side_done[c], 0)); }
-      h->launches++;
     }
     if (P.pivot_budget > 0) {
       int slot = B2M_SLOT_STRAGGLER;
-      SimParams Ps = P; Ps.gscratch = h->straggler.gscratch; Ps.gstride = h->straggler.gstride;
+      SimParams Ps = P; Ps.gscratch = h->straggler.gscratch; Ps.gstride = h->straggler.gstride; Ps.kslot = 1 + ncls;
       void* a[] = {&Ps, &dt, &r, &slot};
-      B2M_CUDA(cudaLaunchKernel(impact_block_ptr(256), dim3(h->straggler.grid), dim3(256), a, h->straggler.shmem, s)); h->launches++;
+      if ((st = timed_launch(h, 1 + ncls, impact_block_ptr(256), dim3(h->straggler.grid), dim3(256), a, h->straggler.shmem, s)) != B200MOBY_OK) return st;
     }
   }
-  { int r = h->rounds - 1; void* a[] = {&P, &dt, &r};
-    B2M_CUDA(cudaLaunchKernel(b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)); h->launches++; }
+  { int r = h->rounds - 1; SimParams Pf = P; Pf.kslot = 2 + ncls;
+    void* a[] = {&Pf, &dt, &r};
+    if ((st = timed_launch(h, 2 + ncls, b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)) != B200MOBY_OK) return st; }
   B2M_CUDA(cudaGetLastError());
   return B200MOBY_OK;
 }
@@ -326,6 +347,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)h->nmax * ne, &P.zlast));
   TRY(dev_zero(h, (size_t)ne, &P.zlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
+  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 4), &P.kstat));
   TRY(dev_zero(h, (size_t)ne, &P.hacc));
   TRY(dev_zero(h, (size_t)ne, &P.hpend));
   TRY(dev_zero(h, (size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne, &P.queue));
@@ -341,6 +363,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
     }
     TRY(dev_copy(h, &T, 1, &P.rc));
     P.rc_links = r.n_links; P.rc_first = r.first_body;
+    P.ngc = b2m_dense_ngc(d);
     h->rc_links = r.n_links; h->rc_dof = r.n_links - 1;
     TRY(dev_zero(h, (size_t)h->rc_dof * ne, &P.jq));
     TRY(dev_zero(h, (size_t)h->rc_dof * ne, &P.jqd));
@@ -371,6 +394,8 @@ b200moby_status b200moby_destroy(b200moby_handle h) {
   for (cudaStream_t st : h->side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (cudaEvent_t ev : h->side_done) if (ev) cudaEventDestroy(ev);
   if (h->fork) cudaEventDestroy(h->fork);
+  for (auto& pe : h->kev_pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
+  for (auto& pe : h->kev_free) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return B200MOBY_OK;
@@ -544,6 +569,44 @@ b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int 
   return B200MOBY_OK;
 }
 
+// Per-kernel profile of the stepped path since the last call with reset != 0: enabling it brackets every launch with
+// events on the launch's own stream.  The call synchronises the device.
+b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int reset, b200moby_kernel_profile* out) {
+  if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
+  B2M_CUDA(cudaSetDevice(h->device));
+  B2M_CUDA(cudaDeviceSynchronize());
+  const int ncls = (int)h->classes.size(), nk = ncls + 3;
+  h->kms.resize(nk, 0.0); h->klaunches.resize(nk, 0);
+  for (auto& pe : h->kev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) { h->kms[pe.first] += ms; h->klaunches[pe.first]++; }
+    h->kev_free.push_back(pe.second);
+  }
+  h->kev_pending.clear();
+  if (out) {
+    memset(out, 0, sizeof(*out));
+    unsigned long long ks[3 * (B2M_MAX_CLASSES + 4)];
+    B2M_CUDA(cudaMemcpy(ks, h->P.kstat, sizeof(ks), cudaMemcpyDeviceToHost));
+    out->n_kernels = nk;
+    for (int k = 0; k < nk && k < B200MOBY_MAX_KERNELS; k++) {
+      b200moby_kernel_stat& o = out->k[k];
+      if (k == 0) snprintf(o.name, sizeof(o.name), "advance_kernel");
+      else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
+      else if (k == ncls + 1) { snprintf(o.name, sizeof(o.name), "impact_block_kernel<256>[stragglers]"); o.lcp_nmax = h->nmax; o.threads_per_env = 256; }
+      else snprintf(o.name, sizeof(o.name), "finish_kernel");
+      if (k == 0 || k == ncls + 2) o.threads_per_env = 32;
+      o.ms = h->kms[k]; o.launches = h->klaunches[k];
+      o.envs = (long long)ks[3 * k]; o.flops = (long long)ks[3 * k + 1]; o.lcp_solves = (long long)ks[3 * k + 2];
+    }
+  }
+  if (reset) {
+    std::fill(h->kms.begin(), h->kms.end(), 0.0); std::fill(h->klaunches.begin(), h->klaunches.end(), 0);
+    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 4)));
+  }
+  h->ktiming = enable != 0;
+  return B200MOBY_OK;
+}
+
 // Debug tap: per-env SM cycles, pivots, executed iterations and LCP dimension of the last impact phase; prof is a host
 // buffer [13][env] (4 totals + 9 phases: load, contacts, islands, problem data, LCP build, lcp_fast, Lemke, apply, store).
 // The first call arms the tap (and returns zeros).
@@ -558,6 +621,7 @@ b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof) 
 
 static b200moby_status run_stage(b200moby_handle h, int stage, const double* q, const double* v, StageOut o, void* stream) {
   if (!h || !q || !v) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  if (h->rc_links && stage == STAGE_DELASSUS) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "the assembly stage kernel handles free-body scenes only");
   static bool attr_set = false;
   if (!attr_set) { B2M_CUDA(cudaFuncSetAttribute(stage_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX)); attr_set = true; }
   SimParams P = h->P;

@@ -164,6 +164,28 @@ class ArticulatedBody:
         d._keep = keep
         return d
 
+    def link_poses(self, env):
+        """World pose (x [link][3], R [link][3][3]) of every link COM frame of env `env` at the stored joint state."""
+        sc, b0 = self.scene, self.first_body
+        x = np.zeros((self.n_links, 3))
+        R = np.zeros((self.n_links, 3, 3))
+        x[0], R[0] = sc.q[b0, :3, env], _rotmat(sc.q[b0, 3:, env] / np.linalg.norm(sc.q[b0, 3:, env]))
+        for i in range(1, self.n_links):
+            p = self.parent[i]
+            a = self.joint_axis[i] / np.linalg.norm(self.joint_axis[i])
+            R0 = _rotmat(self.rel_quat[i] / np.linalg.norm(self.rel_quat[i]))
+            qi = self.jq[i - 1, env]
+            if self.joint_type[i] == JOINT_REVOLUTE:
+                K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+                Rrel = R0 @ (np.eye(3) + np.sin(qi) * K + (1 - np.cos(qi)) * (K @ K))
+                r = self.loc_parent[i] - Rrel @ self.loc_child[i]
+            else:
+                Rrel = R0
+                r = self.loc_parent[i] + Rrel @ (a * qi - self.loc_child[i])
+            R[i] = R[p] @ Rrel
+            x[i] = x[p] + R[p] @ r
+        return x, R
+
     def env_mass_props(self, env):
         """(mass [link], J [link][3], base pose [7]) of env `env` (what the oracle / host-compiled checks take)."""
         b0, nl, sc = self.first_body, self.n_links, self.scene
@@ -332,7 +354,7 @@ _UR10_JOINTS = [None, (0, JOINT_REVOLUTE, (0, 0, 1)), (1, JOINT_REVOLUTE, (0, 1,
                 (6, JOINT_REVOLUTE, (0, 0, 1)), (7, JOINT_PRISMATIC, (1, 0, 0)), (7, JOINT_PRISMATIC, (1, 0, 0))]
 
 
-def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_jitter=0.1, controller=True, mu=0.5, NK=4):
+def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_jitter=0.1, controller=True, mu=0.5, NK=4, table_gap=2e-3):
     """SURVEY.md 8(d) case 4: the UR10 + Schunk gripper of example/ur10/model.sdf as a fixed-base chain.
 
     Benchmark variant (the shipped ur10.xml has mesh geometry, mu = 100, joint limits and no table): `world_joint` is a
@@ -372,8 +394,11 @@ def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_
         amp = np.array([AMP * PERIOD, SMALL * PERIOD * 2.0, AMP * PERIOD * 2.0 / 3.0, AMP * PERIOD / 7.0, AMP * PERIOD * 2.0 / 11.0,
                         AMP * PERIOD * 3.0 / 13.0, 0.0, 0.0, 0.0])
         freq = np.array([1.0, 2.0, 2.0 / 3.0, 1.0 / 7.0, 2.0 / 11.0, 3.0 / 13.0, 0.0, 0.0, 0.0])
-        kp = np.array([300.0, 300.0, 60.0, 15.0, 15.0, 15.0, 15.0, 1000.0, 1000.0])
-        kv = np.array([120.0, 120.0, 24.0, 6.0, 6.0, 6.0, 6.0, 20.0, 20.0])
+        # controller.cpp:75-78 gains for the six arm joints, except wrist 3: with the hand no longer locked to it by joint
+        # limits its axis carries ~1e-3 kg m^2 and kv = 6 is unstable under the explicit velocity update at dt = 5e-4
+        # (kv dt / I > 2); wrist 3, the hand joint and the fingers get gains inside the stability bound.
+        kp = np.array([300.0, 300.0, 60.0, 15.0, 15.0, 15.0, 5.0, 1000.0, 1000.0])
+        kv = np.array([120.0, 120.0, 24.0, 6.0, 6.0, 1.0, 0.3, 20.0, 20.0])
         rc.set_controller(kp, kv, amp, freq)
         rc.jqd[:6, :] = amp[:6, None]                        # controller.cpp:124-140: qd(0) = cos(0) * amplitude
     rc.jq[:6, :] = rng.uniform(-q_jitter, q_jitter, (6, n_envs))
@@ -383,9 +408,18 @@ def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_
     for f in (8, 9):
         s.set_sphere(f, 0.012, mass=_UR10_LINKS[f][3]); s.inertia[f, :, :] = np.array(_UR10_LINKS[f][4])[:, None]
     table = nl
+    s.set_plane(table, quat=tuple(quat_from_rpy(np.float64(1.5707963267948966), 0.0, 0.0)), pos=(0.0, 0.0, 0.0))
     if table_z is None:
-        table_z = -0.02
-    s.set_plane(table, quat=tuple(quat_from_rpy(np.float64(1.5707963267948966), 0.0, 0.0)), pos=(0.0, 0.0, table_z))
+        # per env: `table_gap` below the lowest point of the proxies at the initial joint state, so nothing starts in
+        # penetration and the first contacts come from gravity sag and the commanded motion
+        tz = np.zeros(n_envs)
+        for e in range(n_envs):
+            x, R = rc.link_poses(e)
+            low = min(x[k][2] - s.dims[k, 0, e] for k in (6, 8, 9))
+            low = min(low, x[7][2] - 0.5 * (abs(R[7][2, 0]) * s.dims[7, 0, e] + abs(R[7][2, 1]) * s.dims[7, 1, e] + abs(R[7][2, 2]) * s.dims[7, 2, e]))
+            tz[e] = low - table_gap
+        table_z = tz
+    s.q[table, 2, :] = table_z
     for link in (6, 7, 8, 9):
         s.set_contact(link, table, mu_coulomb=mu, NK=NK)
     if with_block:

@@ -57,6 +57,12 @@ class TimeSteppingSimulator:
         capi.check(capi.lib().b200moby_get_joint_state(self._h, jq.ctypes.data, jqd.ctypes.data))
         return jq, jqd
 
+    def set_joint_state_dev(self, jq, jqd, stream=None):
+        capi.check(capi.lib().b200moby_set_joint_state_dev(self._h, jq.data_ptr(), jqd.data_ptr(), _stream(stream)))
+
+    def get_joint_state_dev(self, jq, jqd, stream=None):
+        capi.check(capi.lib().b200moby_get_joint_state_dev(self._h, jq.data_ptr(), jqd.data_ptr(), _stream(stream)))
+
     def set_joint_forces(self, tau):
         """Generalized joint forces applied every mini-step until changed ([dof][env]); None clears them."""
         if tau is None:
@@ -118,6 +124,14 @@ class TimeSteppingSimulator:
 
     def reset_counters(self):
         capi.check(capi.lib().b200moby_reset_counters(self._h))
+
+    def kernel_profile(self, enable=True, reset=True):
+        """Per-kernel durations / envs / algorithmic flops of the steps since the last reset (synchronises)."""
+        kp = capi.KernelProfile()
+        capi.check(capi.lib().b200moby_get_kernel_profile(self._h, int(enable), int(reset), C.byref(kp)))
+        return [dict(name=kp.k[i].name.decode(), ms=kp.k[i].ms, launches=kp.k[i].launches, envs=kp.k[i].envs, flops=kp.k[i].flops,
+                     lcp_solves=kp.k[i].lcp_solves, lcp_nmax=kp.k[i].lcp_nmax, threads_per_env=kp.k[i].threads_per_env)
+                for i in range(kp.n_kernels)]
 
     def impact_profile(self):
         """Debug tap: (cycles, pivots, executed iterations, n) per env of the last impact phase; first call arms it."""

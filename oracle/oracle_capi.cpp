@@ -67,6 +67,7 @@ int oracle_lcp_lemke_regularized(int n, const double* M, const double* q, double
 
 // ---- simulator ----
 struct OracleSim { Sim sim; };
+static void rc_model_from_desc(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, RCModel& m);
 
 static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
   const int nb = d->n_bodies, ne = d->n_envs;
@@ -91,6 +92,24 @@ static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
   S.contact_dist_thresh = d->contact_dist_thresh;
   S.min_step_size = d->min_step_size_env ? d->min_step_size_env[e] : d->min_step_size;
   S.model = d->impact_model;
+  if (d->rc && d->rc->n_links > 0) {
+    const b200moby_rc_desc* r = d->rc;
+    S.has_rc = true; S.rc_first = r->first_body; S.rc_fdyn = r->fdyn_algorithm;
+    std::vector<double> mass(r->n_links), J(3 * r->n_links);
+    for (int i = 0; i < r->n_links; i++) { mass[i] = S.bodies[r->first_body + i].mass; for (int c = 0; c < 3; c++) J[3 * i + c] = S.bodies[r->first_body + i].J[c]; }
+    const double pose0[7] = {0, 0, 0, 0, 0, 0, 1};
+    rc_model_from_desc(r, mass.data(), J.data(), pose0, S.rc);
+    const int nd = r->n_links - 1;
+    S.jq.assign(nd, 0.0); S.jqd.assign(nd, 0.0); S.jtau.assign(nd, 0.0);
+    if (r->ctrl_kp) {
+      S.has_ctrl = true;
+      S.ctrl_kp.assign(r->ctrl_kp, r->ctrl_kp + nd);
+      S.ctrl_kv.assign(nd, 0.0); S.ctrl_amp.assign(nd, 0.0); S.ctrl_freq.assign(nd, 0.0);
+      if (r->ctrl_kv) S.ctrl_kv.assign(r->ctrl_kv, r->ctrl_kv + nd);
+      if (r->ctrl_amp) S.ctrl_amp.assign(r->ctrl_amp, r->ctrl_amp + nd);
+      if (r->ctrl_freq) S.ctrl_freq.assign(r->ctrl_freq, r->ctrl_freq + nd);
+    }
+  }
 }
 
 void* oracle_sim_create(const b200moby_scene_desc* d, int env, int tie) {
@@ -125,6 +144,21 @@ static void get_state(Sim& S, double* q, double* v) {
   }
 }
 void oracle_sim_get_state(void* h, double* q, double* v) { get_state(((OracleSim*)h)->sim, q, v); }
+// joint state of the articulated body (after oracle_sim_set_state, which places the base link)
+void oracle_sim_set_joint_state(void* h, const double* jq, const double* jqd) {
+  Sim& S = ((OracleSim*)h)->sim;
+  const int nd = S.rc.ndof();
+  S.jq.assign(jq, jq + nd); S.jqd.assign(jqd, jqd + nd);
+  S.rc_update_links();
+}
+void oracle_sim_get_joint_state(void* h, double* jq, double* jqd) {
+  Sim& S = ((OracleSim*)h)->sim;
+  for (int k = 0; k < S.rc.ndof(); k++) { jq[k] = S.jq[k]; jqd[k] = S.jqd[k]; }
+}
+void oracle_sim_set_joint_forces(void* h, const double* tau) {
+  Sim& S = ((OracleSim*)h)->sim;
+  for (int k = 0; k < S.rc.ndof(); k++) S.jtau[k] = tau ? tau[k] : 0.0;
+}
 void oracle_sim_step(void* h, double dt, int n_steps) {
   Sim& S = ((OracleSim*)h)->sim;
   for (int i = 0; i < n_steps; i++) S.step(dt);
@@ -224,6 +258,21 @@ void* oracle_batch_create(const b200moby_scene_desc* d, const double* q, const d
     set_state(S, qa.data(), va.data());
   }
   return B;
+}
+// joint state of the articulated body for every env of the batch, SoA [dof][n_envs of the descriptor]
+void oracle_batch_set_joint_state(void* h, const double* jq, const double* jqd, int ne) {
+  OracleBatch* B = (OracleBatch*)h;
+  for (size_t i = 0; i < B->sims.size(); i++) {
+    Sim& S = B->sims[i];
+    if (!S.has_rc) continue;
+    const int e = B->e0 + (int)i, nd = S.rc.ndof();
+    for (int k = 0; k < nd; k++) { S.jq[k] = jq[(size_t)k * ne + e]; S.jqd[k] = jqd[(size_t)k * ne + e]; }
+    S.rc_update_links();
+  }
+}
+void oracle_batch_get_joint_state(void* h, int i, double* jq, double* jqd) {
+  Sim& S = ((OracleBatch*)h)->sims[i];
+  for (int k = 0; k < S.rc.ndof(); k++) { jq[k] = S.jq[k]; jqd[k] = S.jqd[k]; }
 }
 void oracle_batch_destroy(void* h) { delete (OracleBatch*)h; }
 void oracle_batch_run(void* h, double dt, int n_steps, int threads, b200moby_counters* total) {

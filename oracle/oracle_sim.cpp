@@ -44,6 +44,32 @@ void Sim::update_pose(Body& b) {
   R[6] = 2.0 * (x * z - w * y);       R[7] = 2.0 * (y * z + w * x);       R[8] = 1.0 - 2.0 * (x * x + y * y);
 }
 
+// RCArticulatedBodyd::update_link_poses / update_link_velocities (RCArticulatedBody.cpp:102,142-143): link bodies follow (jq, jqd)
+static void R_to_quat(const double* R, double* q) {
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0.0) { const double s = std::sqrt(tr + 1.0) * 2.0; q[3] = 0.25 * s; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { const double s = std::sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0; q[3] = (R[7] - R[5]) / s; q[0] = 0.25 * s; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { const double s = std::sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0; q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = 0.25 * s; q[2] = (R[5] + R[7]) / s; }
+  else { const double s = std::sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0; q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25 * s; }
+}
+void Sim::rc_update_links() {
+  if (!has_rc) return;
+  const Body& base = bodies[rc_first];
+  for (int c = 0; c < 3; c++) rc.base_x[c] = base.x[c];
+  for (int c = 0; c < 4; c++) rc.base_quat[c] = base.quat[c];
+  for (int i = 0; i < rc.n_links; i++) { rc.mass[i] = bodies[rc_first + i].mass; for (int c = 0; c < 3; c++) rc.J[i][c] = bodies[rc_first + i].J[c]; }
+  RCKin k;
+  rc_kinematics(rc, jq.data(), jqd.data(), k);
+  for (int i = 1; i < rc.n_links; i++) {
+    Body& b = bodies[rc_first + i];
+    b.x = V3(k.x[i][0], k.x[i][1], k.x[i][2]);
+    for (int c = 0; c < 9; c++) b.R[c] = k.R[i][c];
+    R_to_quat(b.R, b.quat);
+    b.vl = V3(k.vl[i][0], k.vl[i][1], k.vl[i][2]);
+    b.va = V3(k.va[i][0], k.va[i][1], k.va[i][2]);
+  }
+}
+
 // velocity of the body-fixed point coincident with p: the linear part of Pose3d::transform(frame at p, v)
 static inline V3 point_vel(const Body& b, const V3& p) {
   if (!b.enabled) return V3();
@@ -404,9 +430,26 @@ double Sim::calc_CA_Euler_step(const PairDist& pdi) const {
 // v += h*a (TimeSteppingSimulator.cpp:181-192).  Ravelin RigidBodyd::calc_fwd_dyn restated:
 // a_lin = f/m, alpha = J^-1 (tau - w x J w) with J = R diag(Jb) R^T at the COM (global-aligned frame).
 void Sim::calc_fwd_dyn_and_integrate_velocity(double h) {
+  if (has_rc) {   // Simulator.cpp:339-348 (controller at current_time), :544-553 (RCArticulatedBodyd::calc_fwd_dyn), TimeSteppingSimulator.cpp:181-192
+    const int nd = rc.ndof();
+    Vec tau(nd), qdd(nd);
+    for (int k = 0; k < nd; k++) {
+      double u = jtau.empty() ? 0.0 : jtau[k];
+      if (has_ctrl) {
+        const double ph = current_time * ctrl_freq[k];
+        u += ctrl_kp[k] * (std::sin(ph) * ctrl_amp[k] - jq[k]) + ctrl_kv[k] * (std::cos(ph) * ctrl_amp[k] - jqd[k]);
+      }
+      tau[k] = u;
+    }
+    const double g[3] = {gravity.x, gravity.y, gravity.z};
+    if (rc_fdyn == 1) rc_crb_fwd_dyn(rc, jq.data(), jqd.data(), tau.data(), g, qdd.data());
+    else rc_aba(rc, jq.data(), jqd.data(), tau.data(), g, qdd.data());
+    for (int k = 0; k < nd; k++) jqd[k] = jqd[k] + qdd[k] * h;
+    rc_update_links();
+  }
   for (size_t i = 0; i < bodies.size(); i++) {
     Body& b = bodies[i];
-    if (!b.enabled) continue;
+    if (!b.enabled || is_link((int)i)) continue;
     V3 f = gravity * b.mass + b.fext;                                // GravityForce.cpp:32-48
     V3 tau = b.text;
     V3 wb = rotT(b.R, b.va);
@@ -426,6 +469,7 @@ double Sim::do_mini_step(double dt) {
   std::vector<V3> xsave(nb);
   std::vector<double> qsave(nb * 4);
   for (size_t i = 0; i < nb; i++) { xsave[i] = bodies[i].x; for (int k = 0; k < 4; k++) qsave[i * 4 + k] = bodies[i].quat[k]; }
+  const Vec jqsave = jq;
   double h = 0.0;
   std::vector<std::pair<int, int> > pairs;
   std::vector<PairDist> pd;
@@ -438,9 +482,13 @@ double Sim::do_mini_step(double dt) {
     if (CA_step <= 0.0) break;
     double tc = std::max(min_step_size, CA_step);
     tc = std::min(dt - h, tc);
+    if (has_rc) {                                                    // joint coordinates: q = qsave + (h + tc) qd
+      for (size_t k = 0; k < jq.size(); k++) jq[k] = jqd[k] * (h + tc) + jqsave[k];
+      rc_update_links();
+    }
     for (size_t i = 0; i < nb; i++) {                                // :156-164
       Body& b = bodies[i];
-      if (!b.enabled) continue;
+      if (!b.enabled || is_link((int)i)) continue;
       const double s = h + tc;
       const double qx = qsave[i * 4 + 0], qy = qsave[i * 4 + 1], qz = qsave[i * 4 + 2], qw = qsave[i * 4 + 3];
       const V3& w = b.va;
@@ -472,7 +520,15 @@ double Sim::do_mini_step(double dt) {
 // TimeSteppingSimulator::step + step_si_Euler (TimeSteppingSimulator.cpp:52-111,433-455); stabilization disabled (max_iterations = 0)
 double Sim::step(double dt) {
   double h = 0.0;
-  while (h < dt) h += do_mini_step(dt - h);
+  int stalled = 0;
+  while (h < dt) {
+    const double hh = do_mini_step(dt - h);
+    h += hh;
+    // the reference would spin (or leave through LCPSolverException) when an impact cannot be resolved; the batch
+    // contract gives up the rest of the step after 64 zero-length mini-steps in a row and counts a failure
+    stalled = (hh > 0.0) ? 0 : stalled + 1;
+    if (stalled >= 64) { cnt.lcp_failures++; break; }
+  }
   cnt.env_steps++;
   return dt;
 }
@@ -492,11 +548,119 @@ struct ProblemData {
   Vec Cv[3];                      // Cn_v, Cs_v, Ct_v
   Vec cn, cs, ct;
   double* jrow(int d, int i, int blk) { return &Jr[(((size_t)d * nc + i) * 2 + blk) * 6]; }
+  // scenes with an articulated body: dense rows Cn, Cs, Ct over the island's generalized coordinates (nc x ngc each)
+  bool dense = false;
+  Mat C[3];
 };
 }  // namespace
 
+// compute_problem_data with an RCArticulatedBody in the island (ImpactConstraintHandler.cpp:1898-2166): super bodies are
+// the enabled free bodies and the articulated body (all moving links share its joint coordinates, :1905-1916);
+// X = blockdiag(inverse_SPD(generalized inertia)) with the articulated body's inertia from get_generalized_inertia
+// (:1599-1611); a contact wrench [d, r x d] on a link is post-multiplied by the link Jacobian (:1869-1878).
+static void compute_problem_data_rc(Sim& S, ProblemData& q, const std::vector<Contact*>& cons, const std::vector<int>& island_bodies) {
+  const int nb = (int)S.bodies.size();
+  const int rep = S.rc_first + 1, nd = S.rc.ndof();
+  q.dense = true;
+  q.cons = cons;
+  q.nc = (int)cons.size();
+  q.sb.clear();
+  for (size_t i = 0; i < island_bodies.size(); i++) if (S.bodies[island_bodies[i]].enabled) q.sb.push_back(S.super_of(island_bodies[i]));
+  std::sort(q.sb.begin(), q.sb.end());                               // :1915 (pointer order -> scene order, H4)
+  q.sb.erase(std::unique(q.sb.begin(), q.sb.end()), q.sb.end());
+  q.gc.assign(nb, -1);
+  q.ngc = 0;
+  for (size_t i = 0; i < q.sb.size(); i++) { q.gc[q.sb[i]] = q.ngc; q.ngc += (q.sb[i] == rep) ? nd : 6; }
+  q.X = Mat(q.ngc, q.ngc);
+  RCKin kin;
+  rc_kinematics(S.rc, S.jq.data(), S.jqd.data(), kin);
+  Vec v(q.ngc, 0.0);                                                 // get_generalized_velocity :1801-1814
+  for (size_t i = 0; i < q.sb.size(); i++) {
+    const int g = q.gc[q.sb[i]];
+    if (q.sb[i] == rep) {
+      Vec H((size_t)nd * nd);
+      rc_crb(S.rc, kin, H.data());
+      inverse_SPD(H.data(), nd);
+      for (int r = 0; r < nd; r++) for (int c = 0; c < nd; c++) q.X(g + r, g + c) = H[(size_t)c * nd + r];
+      for (int k = 0; k < nd; k++) v[g + k] = S.jqd[k];
+      continue;
+    }
+    const Body& b = S.bodies[q.sb[i]];
+    double Mg[36] = {0};
+    for (int k = 0; k < 3; k++) Mg[k * 6 + k] = b.mass;
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        double s = 0.0;
+        for (int k = 0; k < 3; k++) s += b.R[r * 3 + k] * b.J[k] * b.R[c * 3 + k];
+        Mg[(3 + c) * 6 + (3 + r)] = s;
+      }
+    inverse_SPD(Mg, 6);
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) q.X(g + r, g + c) = Mg[c * 6 + r];
+    v[g] = b.vl.x; v[g + 1] = b.vl.y; v[g + 2] = b.vl.z; v[g + 3] = b.va.x; v[g + 4] = b.va.y; v[g + 5] = b.va.z;
+  }
+  // contact Jacobians (:1817-1895)
+  std::vector<std::vector<double> > Jl(S.rc.n_links);               // link Jacobians, computed on demand
+  for (int d = 0; d < 3; d++) q.C[d] = Mat(q.nc, q.ngc);
+  for (int i = 0; i < q.nc; i++) {
+    const Contact& c = *cons[i];
+    const V3 dirs[3] = {c.n, c.t1, c.t2};
+    for (int blk = 0; blk < 2; blk++) {
+      const int bi = blk == 0 ? c.b1 : c.b2;
+      const Body& b = S.bodies[bi];
+      if (!b.enabled) continue;
+      for (int d = 0; d < 3; d++) {
+        const V3 dd = blk == 0 ? dirs[d] : -dirs[d];
+        const V3 rxd = cross(c.p - b.x, dd);
+        const double w[6] = {dd.x, dd.y, dd.z, rxd.x, rxd.y, rxd.z};
+        if (S.is_link(bi)) {
+          const int li = bi - S.rc_first;
+          if (Jl[li].empty()) { Jl[li].assign((size_t)6 * nd, 0.0); rc_link_jacobian(S.rc, kin, li, Jl[li].data()); }
+          const int g = q.gc[rep];
+          for (int k = 0; k < nd; k++) {
+            double s = 0.0;
+            for (int r = 0; r < 6; r++) s += w[r] * Jl[li][(size_t)r * nd + k];
+            q.C[d](i, g + k) += s;
+          }
+        } else {
+          const int g = q.gc[bi];
+          for (int r = 0; r < 6; r++) q.C[d](i, g + r) += w[r];
+        }
+      }
+    }
+  }
+  for (int d = 0; d < 3; d++) {                                      // X_CdT = (Cd X)^T (:2125-2127)
+    q.XT[d] = Mat(q.ngc, q.nc);
+    for (int i = 0; i < q.nc; i++)
+      for (int k = 0; k < q.ngc; k++) {
+        double s = 0.0;
+        for (int kk = 0; kk < q.ngc; kk++) s = std::fma(q.C[d](i, kk), q.X(kk, k), s);
+        q.XT[d](k, i) = s;
+      }
+  }
+  for (int d1 = 0; d1 < 3; d1++)                                     // Delassus blocks (:2133-2149)
+    for (int d2 = d1; d2 < 3; d2++) {
+      q.D[d1][d2] = Mat(q.nc, q.nc);
+      for (int i = 0; i < q.nc; i++)
+        for (int j = 0; j < q.nc; j++) {
+          double s = 0.0;
+          for (int k = 0; k < q.ngc; k++) s = std::fma(q.C[d1](i, k), q.XT[d2](k, j), s);
+          q.D[d1][d2](i, j) = s;
+        }
+    }
+  for (int d = 0; d < 3; d++) {                                      // Cd v (:2157-2159)
+    q.Cv[d].assign(q.nc, 0.0);
+    for (int i = 0; i < q.nc; i++) {
+      double s = 0.0;
+      for (int k = 0; k < q.ngc; k++) s = std::fma(q.C[d](i, k), v[k], s);
+      q.Cv[d][i] = s;
+    }
+  }
+  q.cn.assign(q.nc, 0.0); q.cs.assign(q.nc, 0.0); q.ct.assign(q.nc, 0.0);
+}
+
 // ImpactConstraintHandler::compute_problem_data (ImpactConstraintHandler.cpp:1898-2166), free bodies only
 static void compute_problem_data(Sim& S, ProblemData& q, const std::vector<Contact*>& cons, const std::vector<int>& island_bodies) {
+  if (S.has_rc) { compute_problem_data_rc(S, q, cons, island_bodies); return; }
   const int nb = (int)S.bodies.size();
   q.cons = cons;
   q.nc = (int)cons.size();
@@ -703,6 +867,11 @@ static void apply_to_bodies(Sim& S, ProblemData& q) {
   for (size_t i = 0; i < q.sb.size(); i++) {                           // update_generalized_velocities :1784-1798
     Body& b = S.bodies[q.sb[i]];
     const int g = q.gc[q.sb[i]];
+    if (S.has_rc && q.sb[i] == S.rc_first + 1) {                       // the articulated body: joint velocities, then its links
+      for (int k = 0; k < S.rc.ndof(); k++) S.jqd[k] = S.jqd[k] + dv[g + k];
+      S.rc_update_links();
+      continue;
+    }
     b.vl = b.vl + V3(dv[g], dv[g + 1], dv[g + 2]);
     b.va = b.va + V3(dv[g + 3], dv[g + 4], dv[g + 5]);
   }
@@ -844,10 +1013,11 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
   std::set<int> nodes;
   std::vector<std::vector<int> > adj(nb);
   for (size_t i = 0; i < contacts.size(); i++) {
-    const int b1 = contacts[i].b1, b2 = contacts[i].b2;
-    if (bodies[b1].enabled) nodes.insert(b1);
-    if (bodies[b2].enabled) nodes.insert(b2);
-    if (bodies[b1].enabled && bodies[b2].enabled) { adj[b1].push_back(b2); adj[b2].push_back(b1); }
+    const int b1 = super_of(contacts[i].b1), b2 = super_of(contacts[i].b2);      // single bodies of one articulated body are one node
+    const bool e1 = bodies[contacts[i].b1].enabled, e2 = bodies[contacts[i].b2].enabled;
+    if (e1) nodes.insert(b1);
+    if (e2) nodes.insert(b2);
+    if (e1 && e2) { adj[b1].push_back(b2); adj[b2].push_back(b1); }
   }
   // std::multimap keeps equal keys in insertion order: neighbours are visited in contact order
   std::vector<char> taken(contacts.size(), 0);
@@ -865,7 +1035,7 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
       processed.insert(node);
       for (size_t k = 0; k < adj[node].size(); k++) if (!processed.count(adj[node][k])) nq.push(adj[node][k]);
       for (size_t i = 0; i < contacts.size(); i++)
-        if (!taken[i] && (contacts[i].b1 == node || contacts[i].b2 == node)) { taken[i] = 1; groups.back().first.push_back(&contacts[i]); }
+        if (!taken[i] && ((bodies[contacts[i].b1].enabled && super_of(contacts[i].b1) == node) || (bodies[contacts[i].b2].enabled && super_of(contacts[i].b2) == node))) { taken[i] = 1; groups.back().first.push_back(&contacts[i]); }
     }
     if (groups.back().first.empty()) groups.pop_back();
   }

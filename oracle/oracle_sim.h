@@ -21,6 +21,7 @@
 #pragma once
 #include <vector>
 #include "oracle_lcp.h"
+#include "oracle_rc.h"
 
 namespace oracle {
 
@@ -86,6 +87,20 @@ struct Sim {
   int last_n = 0;
   Vec last_MM, last_qq, last_z;
   std::vector<Contact> last_contacts;
+
+  // Optional fixed-base reduced-coordinate articulated body (RCArticulatedBody, oracle_rc.h): its links are bodies
+  // [rc_first, rc_first + rc.n_links) of `bodies`, link 0 (the base) a disabled body.  All moving links form one super
+  // body whose generalized coordinates are the joint positions (ImpactConstraintHandler.cpp:1817-1895,1905-1916).
+  bool has_rc = false;
+  RCModel rc;
+  int rc_first = 0;
+  int rc_fdyn = 0;                      // 0: fsab (ABA), 1: crb (RCArticulatedBody.cpp:178-201)
+  Vec jq, jqd, jtau;                    // joint positions, velocities, feed-forward generalized forces
+  bool has_ctrl = false;                // joint-space PD law of example/ur10/controller.cpp:46-96
+  Vec ctrl_kp, ctrl_kv, ctrl_amp, ctrl_freq;
+  bool is_link(int b) const { return has_rc && b > rc_first && b < rc_first + rc.n_links; }
+  int super_of(int b) const { return is_link(b) ? rc_first + 1 : b; }
+  void rc_update_links();               // update_link_poses / update_link_velocities
 
   Sim();
   void init(int nb);

@@ -12,28 +12,48 @@
 
 using namespace b2m;
 
-extern "C" {
-
-// q [nb][7][ne], v [nb][6][ne], time [ne], zlast [nmax][ne], zlast_n [ne], counters [CNT_COUNT] all host, updated in place.
-// Returns nmax (call with q == NULL to query sizes only).
-int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time, double* zlast, int* zlast_n,
-                unsigned long long* counters, double dt, int n_steps, int e0, int e1, double* tapMM, double* tapqq, double* tapz, int* tapn) {
+// SimParams over host arrays, exactly as b200moby_create fills it
+static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, const std::vector<double>& tab, const b200moby_scene_desc* d, int cmax,
+                         int nmax, int npmax, double* q, double* v, double* time, double* zlast, int* zlast_n, unsigned long long* counters,
+                         double* jq, double* jqd) {
   const int ne = d->n_envs, nb = d->n_bodies;
-  int cmax = 0, nmax = 0, npmax = 0;
-  if (b2m_scene_bounds(d, cmax, nmax, npmax)) return -1;
-  if (!q) return nmax;
-  std::vector<double> tab = b2m_friction_table();
-  SimParams P; memset(&P, 0, sizeof(P));
+  memset(&P, 0, sizeof(P));
   P.n_envs = ne; P.nb = nb; P.cmax = cmax; P.nmax = nmax; P.npmax = npmax; P.model = d->impact_model;
   P.shape = d->shape; P.enabled = d->enabled; P.mass = d->mass; P.dims = d->dims; P.inertia = d->inertia;
   P.mu_c = d->mu_coulomb; P.mu_v = d->mu_viscous; P.eps = d->epsilon; P.compliance = d->compliance; P.NK = d->NK;
   P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
   P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
   P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
+  if (d->rc && d->rc->n_links > 0) {
+    bool unsup;
+    if (b2m_rc_tree_from_desc(*d->rc, nb, tree, &unsup)) return false;
+    P.rc = &tree; P.rc_links = tree.n_links; P.rc_first = tree.first_body; P.ngc = b2m_dense_ngc(d);
+    P.jq = jq; P.jqd = jqd;
+    tau0.assign((size_t)(tree.n_links - 1) * ne, 0.0);
+    P.jtau = tau0.data();
+  }
+  return true;
+}
+
+extern "C" {
+
+// q [nb][7][ne], v [nb][6][ne], time [ne], zlast [nmax][ne], zlast_n [ne], counters [CNT_COUNT] all host, updated in place.
+// Returns nmax (call with q == NULL to query sizes only).
+int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time, double* zlast, int* zlast_n,
+                unsigned long long* counters, double dt, int n_steps, int e0, int e1, double* tapMM, double* tapqq, double* tapz, int* tapn,
+                double* jq, double* jqd) {
+  const int ne = d->n_envs, nb = d->n_bodies;
+  int cmax = 0, nmax = 0, npmax = 0;
+  if (b2m_scene_bounds(d, cmax, nmax, npmax)) return -1;
+  if (!q) return nmax;
+  std::vector<double> tab = b2m_friction_table();
+  SimParams P; RCTree tree; std::vector<double> tau0;
+  if (!setup_params(P, tree, tau0, tab, d, cmax, nmax, npmax, q, v, time, zlast, zlast_n, counters, jq, jqd)) return -1;
   P.tap_MM = tapMM; P.tap_qq = tapqq; P.tap_z = tapz; P.tap_n = tapn;
-  std::vector<double> wd(env_doubles(nb, cmax, nmax, npmax));
-  std::vector<int> wi(env_ints(nb, cmax, nmax, npmax));
-  EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
+  const EnvDims D = env_dims(P);
+  std::vector<double> wd(env_doubles(D));
+  std::vector<int> wi(env_ints(D));
+  EnvMem m; env_carve(m, wd.data(), wi.data(), D);
   SerialGroup g(nullptr);
   unsigned long long lc[CNT_COUNT]; memset(lc, 0, sizeof(lc));
   EnvCtx cx; cx.limit = false; cx.budget = 0;
@@ -45,25 +65,21 @@ int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time
 // The phased step (advance -> impact per LCP class -> ... -> finish) exactly as sim_kernels.cu's launch_step sequences
 // it, each "kernel" a serial loop over its queue.  pivot_budget > 0 exercises the straggler path.
 int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, double* time, double* zlast, int* zlast_n,
-                       unsigned long long* counters, double dt, int n_steps, int rounds, int pivot_budget) {
+                       unsigned long long* counters, double dt, int n_steps, int rounds, int pivot_budget, double* jq, double* jqd) {
   const int ne = d->n_envs, nb = d->n_bodies;
   int cmax = 0, nmax = 0, npmax = 0;
   if (b2m_scene_bounds(d, cmax, nmax, npmax)) return -1;
   std::vector<double> tab = b2m_friction_table();
-  SimParams P; memset(&P, 0, sizeof(P));
-  P.n_envs = ne; P.nb = nb; P.cmax = cmax; P.nmax = nmax; P.npmax = npmax; P.model = d->impact_model;
-  P.shape = d->shape; P.enabled = d->enabled; P.mass = d->mass; P.dims = d->dims; P.inertia = d->inertia;
-  P.mu_c = d->mu_coulomb; P.mu_v = d->mu_viscous; P.eps = d->epsilon; P.compliance = d->compliance; P.NK = d->NK;
-  P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
-  P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
-  P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
+  SimParams P; RCTree tree; std::vector<double> tau0;
+  if (!setup_params(P, tree, tau0, tab, d, cmax, nmax, npmax, q, v, time, zlast, zlast_n, counters, jq, jqd)) return -1;
   std::vector<double> hacc(ne), hpend(ne);
   std::vector<int> queue((size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne), qctl(2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1));
   P.hacc = hacc.data(); P.hpend = hpend.data(); P.queue = queue.data(); P.qctl = qctl.data();
   P.pivot_budget = pivot_budget;
   P.n_classes = b2m_class_table(nmax, cmax, P.model, B2M_MAX_CLASSES, P.class_nmax, P.class_cmax);
-  std::vector<double> wd(env_doubles(nb, cmax, nmax, npmax));
-  std::vector<int> wi(env_ints(nb, cmax, nmax, npmax));
+  const EnvDims D = env_dims(P);
+  std::vector<double> wd(env_doubles(D));
+  std::vector<int> wi(env_ints(D));
   SerialGroup g(nullptr);
   unsigned long long tot[CNT_COUNT]; memset(tot, 0, sizeof(tot));
   auto add = [&](const unsigned long long* lc) { for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) tot[k] = std::max(tot[k], lc[k]); else tot[k] += lc[k]; } };
@@ -71,14 +87,14 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
     std::fill(qctl.begin(), qctl.end(), 0);
     for (int r = 0; r < rounds; r++) {
       {   // advance
-        EnvMem m; env_carve_small(m, wd.data(), wi.data(), nb, cmax, npmax);
+        EnvMem m; env_carve_small(m, wd.data(), wi.data(), D);
         const int count = (r == 0) ? ne : *q_count(P, r - 1, B2M_SLOT_CONT);
         const int* list = (r == 0) ? nullptr : q_list(P, r - 1, B2M_SLOT_CONT);
         for (int i = 0; i < count; i++) { unsigned long long lc[CNT_COUNT] = {0}; env_advance(g, P, list ? list[i] : i, m, dt, r, lc); add(lc); }
       }
       for (int c = 0; c < P.n_classes; c++) {   // impact, per class, with the class's working-set size
         SimParams Pc = P; Pc.cmax = P.class_cmax[c]; Pc.nmax = P.class_nmax[c];
-        EnvMem m; env_carve(m, wd.data(), wi.data(), nb, Pc.cmax, Pc.nmax, npmax);
+        EnvMem m; env_carve(m, wd.data(), wi.data(), env_dims(Pc));
         const int count = *q_count(P, r, c);
         const int* list = q_list(P, r, c);
         for (int i = 0; i < count; i++) {
@@ -88,7 +104,7 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
         }
       }
       if (pivot_budget > 0) {   // stragglers, full working set
-        EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
+        EnvMem m; env_carve(m, wd.data(), wi.data(), D);
         const int count = *q_count(P, r, B2M_SLOT_STRAGGLER);
         const int* list = q_list(P, r, B2M_SLOT_STRAGGLER);
         for (int i = 0; i < count; i++) {
@@ -99,7 +115,7 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
       }
     }
     {   // finish
-      EnvMem m; env_carve(m, wd.data(), wi.data(), nb, cmax, nmax, npmax);
+      EnvMem m; env_carve(m, wd.data(), wi.data(), D);
       const int count = *q_count(P, rounds - 1, B2M_SLOT_CONT);
       const int* list = q_list(P, rounds - 1, B2M_SLOT_CONT);
       for (int i = 0; i < count; i++) { unsigned long long lc[CNT_COUNT] = {0}; env_finish(g, P, list[i], m, dt, lc); add(lc); }
@@ -136,21 +152,21 @@ int hostsim_rc(const b200moby_rc_desc* r, const double* mass, const double* J, c
                const double* q, const double* qd, const double* tau, double* out, double* lx, double* lquat, double* lvl, double* lva) {
   RCTree T; bool unsup;
   if (b2m_rc_tree_from_desc(*r, r->first_body + r->n_links, T, &unsup)) return -1;
-  RCState s;
+  RCLocal loc; RCState s = loc.view();
   double qt[4], nrm = 0;
   for (int c = 0; c < 4; c++) nrm += base_pose[3 + c] * base_pose[3 + c];
   nrm = std::sqrt(nrm);
-  for (int c = 0; c < 3; c++) s.x[0][c] = base_pose[c];
+  for (int c = 0; c < 3; c++) s.x[c] = base_pose[c];
   for (int c = 0; c < 4; c++) qt[c] = base_pose[3 + c] / nrm;
-  quat_to_R(qt, s.R[0]);
+  quat_to_R(qt, s.R);
   rc_kinematics(T, q, qd, s);
   const int nd = T.n_links - 1;
   std::vector<double> H((size_t)nd * nd);
   if (what == 0 || what == 1) rc_fwd_dyn(T, what, s, mass, J, qd, tau, g, out, H.data());
   else if (what == 2) rc_crb(T, s, mass, J, out, nd);
   if (lx) for (int i = 0; i < T.n_links; i++) {
-    for (int c = 0; c < 3; c++) lx[3 * i + c] = s.x[i][c];
-    R_to_quat(s.R[i], lquat + 4 * i);
+    for (int c = 0; c < 3; c++) lx[3 * i + c] = s.x[3 * i + c];
+    R_to_quat(s.R + 9 * i, lquat + 4 * i);
     rc_link_velocity(s, i, lvl + 3 * i, lva + 3 * i);
   }
   return 0;

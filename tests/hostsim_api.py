@@ -28,8 +28,8 @@ def lib():
     global _lib
     if _lib is None:
         L = C.CDLL(build())
-        L.hostsim_run.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
-        L.hostsim_run_phased.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int]
+        L.hostsim_run.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+        L.hostsim_run_phased.argtypes = [C.POINTER(SceneDesc)] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 2
         L.hostsim_lcp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hostsim_rc.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8
@@ -43,13 +43,16 @@ class HostSim:
     def __init__(self, scene, taps=False):
         self.scene = scene
         self._d = scene.cdesc()
-        self.nmax = lib().hostsim_run(C.byref(self._d), None, None, None, None, None, None, 0.0, 0, 0, 0, None, None, None, None)
+        self.nmax = lib().hostsim_run(C.byref(self._d), None, None, None, None, None, None, 0.0, 0, 0, 0, None, None, None, None, None, None)
         ne = scene.n_envs
         self.q, self.v = scene.q.copy(), scene.v.copy()
         self.q[:, 3:7, :] /= np.sqrt((self.q[:, 3:7, :] ** 2).sum(axis=1, keepdims=True))   # as b200moby_set_state does
         self.time = np.zeros(ne)
         self.zlast, self.zlast_n = np.zeros((self.nmax, ne)), np.zeros(ne, np.int32)
         self.counters = np.zeros(16, np.uint64)
+        self.rc = getattr(scene, "rc", None)
+        self.jq = self.rc.jq.copy() if self.rc is not None else None
+        self.jqd = self.rc.jqd.copy() if self.rc is not None else None
         self.taps = taps
         if taps:
             self.tapMM, self.tapqq = np.zeros((ne, self.nmax * self.nmax)), np.zeros((ne, self.nmax))
@@ -60,13 +63,17 @@ class HostSim:
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         t = [p(self.tapMM), p(self.tapqq), p(self.tapz), p(self.tapn)] if self.taps else [None] * 4
         lib().hostsim_run(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
-                          dt, n, e0, e1, *t)
+                          dt, n, e0, e1, *t, self._jp(self.jq), self._jp(self.jqd))
 
     def step_phased(self, dt, n=1, rounds=2, pivot_budget=0):
         """The same steps through the phased schedule (advance / impact classes / stragglers / finish)."""
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         lib().hostsim_run_phased(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
-                                 dt, n, rounds, pivot_budget)
+                                 dt, n, rounds, pivot_budget, self._jp(self.jq), self._jp(self.jqd))
+
+    @staticmethod
+    def _jp(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
 
     def counters_dict(self):
         return {k: int(self.counters[i]) for i, k in enumerate(CNT)}

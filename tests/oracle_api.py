@@ -53,6 +53,11 @@ def lib():
         L.oracle_batch_destroy.argtypes = [C.c_void_p]
         L.oracle_batch_run.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(Counters)]
         L.oracle_batch_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_batch_set_joint_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_batch_get_joint_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        for f in (L.oracle_sim_set_joint_state, L.oracle_sim_get_joint_state):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_sim_set_joint_forces.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_rc_fwd_dyn.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
         L.oracle_rc_inertia.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 5
         L.oracle_rc_links.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 10
@@ -121,6 +126,9 @@ class OracleSim:
         self.h = lib().oracle_sim_create(C.byref(self._d), env, tie)
         self.nb = scene.n_bodies
         self.set_state(scene.q[:, :, env], scene.v[:, :, env])
+        self.rc = getattr(scene, "rc", None)
+        if self.rc is not None:
+            self.set_joint_state(self.rc.jq[:, env], self.rc.jqd[:, env])
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -135,6 +143,20 @@ class OracleSim:
         q, v = np.zeros((self.nb, 7)), np.zeros((self.nb, 6))
         lib().oracle_sim_get_state(self.h, _p(q), _p(v))
         return q, v
+
+    def set_joint_state(self, jq, jqd):
+        jq, jqd = np.ascontiguousarray(jq, np.float64), np.ascontiguousarray(jqd, np.float64)
+        lib().oracle_sim_set_joint_state(self.h, _p(jq), _p(jqd))
+
+    def get_joint_state(self):
+        nd = self.rc.n_dof
+        jq, jqd = np.zeros(nd), np.zeros(nd)
+        lib().oracle_sim_get_joint_state(self.h, _p(jq), _p(jqd))
+        return jq, jqd
+
+    def set_joint_forces(self, tau):
+        tau = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        lib().oracle_sim_set_joint_forces(self.h, None if tau is None else _p(tau))
 
     def step(self, dt, n=1):
         lib().oracle_sim_step(self.h, dt, n)
@@ -185,6 +207,19 @@ class OracleBatch:
         self.nb = scene.n_bodies
         q, v = np.ascontiguousarray(scene.q), np.ascontiguousarray(scene.v)
         self.h = lib().oracle_batch_create(C.byref(self._d), _p(q), _p(v), self.e0, self.e1, tie)
+        self.rc = getattr(scene, "rc", None)
+        if self.rc is not None:
+            self.set_joint_state(self.rc.jq, self.rc.jqd)
+
+    def set_joint_state(self, jq, jqd):
+        jq, jqd = np.ascontiguousarray(jq, np.float64), np.ascontiguousarray(jqd, np.float64)
+        lib().oracle_batch_set_joint_state(self.h, _p(jq), _p(jqd), jq.shape[1])
+
+    def get_joint_state(self, i):
+        nd = self.rc.n_dof
+        jq, jqd = np.zeros(nd), np.zeros(nd)
+        lib().oracle_batch_get_joint_state(self.h, i, _p(jq), _p(jqd))
+        return jq, jqd
 
     def __del__(self):
         if getattr(self, "h", None):
