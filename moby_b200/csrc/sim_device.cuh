@@ -53,6 +53,7 @@ struct SimParams {
   double gx, gy, gz, contact_dist_thresh, min_step_size;
   const double* min_step_env;   // optional [env]
   double* q; double* v; double* time; double* zlast; int* zlast_n;
+  double* vlast; int* vlast_n;     // [cmax][env], [env]: solution / warm start of the no-slip LCP (ImpactConstraintHandler::_v)
   unsigned long long* counters;
   int pivot_budget;            // > 0: per-env pivot budget of the warp-per-env impact kernels; over-budget envs are re-run by the straggler kernel
   // phased step (advance -> impact per LCP class -> advance ...): per-env progress and work queues
@@ -82,7 +83,7 @@ struct EnvMem {
   double *pd_dist, *pd_pa, *pd_pb;
   double *cp, *cnrm, *ct1, *ct2, *cdist, *cmu, *cmuv, *ceps, *ccomp;
   double *Jr, *XJ, *Xb, *D, *Cv, *imp, *acc, *dv;
-  double *MM, *qq, *z, *zl, *work;
+  double *MM, *qq, *z, *zl, *vl, *work;
   double *Lf, *gv;             // dense layout: Cholesky factor scratch (ngc^2 + ngc), generalized velocity of the island (ngc)
   double *jq, *jqd, *jqsave, *jtau, *rS, *rV;   // articulated body: joint state, motion subspaces and spatial velocities of the links (world)
   // ints
@@ -115,7 +116,7 @@ B2M_HD inline size_t env_small_ints(const EnvDims& d) { return (size_t)2 * d.nb 
 B2M_HD inline size_t env_impact_doubles(const EnvDims& d) {
   size_t lw = lemke_work_doubles(d.nmax), fw = fast_work_doubles(d.nmax);
   const size_t jac = d.ngc ? (size_t)6 * d.cmax * d.ngc + 2 * (size_t)d.ngc * d.ngc + 3 * (size_t)d.ngc : 72 * (size_t)d.cmax + 36 * (size_t)d.nb + 6 * (size_t)d.nb;
-  return jac + 6 * (size_t)d.cmax * d.cmax + 9 * (size_t)d.cmax + (size_t)d.nmax * d.nmax + 3 * (size_t)d.nmax + (lw > fw ? lw : fw);
+  return jac + 6 * (size_t)d.cmax * d.cmax + 10 * (size_t)d.cmax + (size_t)d.nmax * d.nmax + 3 * (size_t)d.nmax + (lw > fw ? lw : fw);
 }
 B2M_HD inline size_t env_impact_ints(const EnvDims& d) {
   size_t lw = lemke_work_ints(d.nmax), fw = fast_work_ints(d.nmax);
@@ -138,7 +139,7 @@ B2M_HD inline void env_carve_small(EnvMem& m, double* d, int* i, const EnvDims& 
   m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax;
   m.scal = i; i += 16;
   m.ranc = i; i += D.rcl;
-  m.Jr = nullptr; m.zl = nullptr; m.prof = nullptr; m.prof_stride = 0; m.gcb = m.gcl = nullptr;
+  m.Jr = nullptr; m.zl = nullptr; m.vl = nullptr; m.prof = nullptr; m.prof_stride = 0; m.gcb = m.gcl = nullptr;
 }
 B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, const EnvDims& D) {
   const int nb = D.nb, cmax = D.cmax, nmax = D.nmax;
@@ -146,7 +147,7 @@ B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, const EnvDims&
   else { m.Lf = m.gv = nullptr; m.Jr = d; d += 36 * cmax; m.XJ = d; d += 36 * cmax; m.Xb = d; d += 36 * nb; m.dv = d; d += 6 * nb; }
   m.D = d; d += 6 * (size_t)cmax * cmax;
   m.Cv = d; d += 3 * cmax; m.imp = d; d += 3 * cmax; m.acc = d; d += 3 * cmax;
-  m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.zl = d; d += nmax; m.work = d;
+  m.MM = d; d += (size_t)nmax * nmax; m.qq = d; d += nmax; m.z = d; d += nmax; m.zl = d; d += nmax; m.vl = d; d += cmax; m.work = d;
   m.gcoff = i; i += nb; m.bisl = i; i += nb;
   m.icon = i; i += cmax; m.cisl = i; i += cmax; m.corder = i; i += cmax;
   m.isl_start = i; i += nb + 1;
@@ -160,7 +161,7 @@ B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, const EnvDims& D) {
 }
 
 // scal[] slots
-enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10 };
+enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10, S_VLN = 11, S_VLDIRTY = 12 };
 
 // Per-env solver budget: when `limit` is set and an env's pivots in this launch exceed it, the env's step is
 // abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
@@ -489,6 +490,8 @@ B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m
     m.scal[S_NPAIRS] = np;
     m.scal[S_ZLN] = P.zlast_n[e];
     m.scal[S_ZLDIRTY] = 0;
+    m.scal[S_VLN] = P.vlast_n ? P.vlast_n[e] : 0;
+    m.scal[S_VLDIRTY] = 0;
     if (P.rc_links) { m.ranc[0] = 0; for (int i = 1; i < P.rc_links; i++) m.ranc[i] = m.ranc[P.rc->parent[i]] | (1 << i); }
   }
   if (P.rc_links) {
@@ -500,6 +503,8 @@ B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m
   if (m.zl) {                                                   // ImpactConstraintHandler::_zlast, kept on chip for the whole launch
     const int zn = m.scal[S_ZLN];                               // a longer vector than this launch's LCP class can never match (H1: zero fill)
     if (zn <= P.nmax) for (int i = g.tid; i < zn; i += G::size) m.zl[i] = P.zlast[(size_t)i * ne + e];
+    const int vn = m.scal[S_VLN];
+    if (vn <= P.cmax) for (int i = g.tid; i < vn; i += G::size) m.vl[i] = P.vlast[(size_t)i * ne + e];
     g.sync();
   }
 }
@@ -528,6 +533,11 @@ B2M_DEV B2M_NOINL void env_store(const G& g, const SimParams& P, int e, const En
     const int zn = m.scal[S_ZLN];
     for (int i = g.tid; i < zn; i += G::size) P.zlast[(size_t)i * ne + e] = m.zl[i];
     if (g.tid == 0) P.zlast_n[e] = zn;
+  }
+  if ((what & ST_ZL) && m.vl && m.scal[S_VLDIRTY]) {
+    const int vn = m.scal[S_VLN];
+    for (int i = g.tid; i < vn; i += G::size) P.vlast[(size_t)i * ne + e] = m.vl[i];
+    if (g.tid == 0) P.vlast_n[e] = vn;
   }
 }
 
@@ -1225,6 +1235,172 @@ B2M_DEV bool apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, un
   return true;
 }
 
+// Lower Cholesky in place by the whole group (LinAlgd::factor_chol; column-major, ld n); every element is produced by the
+// same operation sequence as the checker's factor_chol, so the accept / reject decisions below are identical.
+template <class G>
+B2M_DEV B2M_NOINL bool chol_factor_group(const G& g, double* A, int n) {
+  for (int j = 0; j < n; j++) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d = fma(-A[(size_t)k * n + j], A[(size_t)k * n + j], d);
+    g.sync();
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    if (g.tid == 0) A[(size_t)j * n + j] = d;
+    for (int i = j + 1 + g.tid; i < n; i += G::size) {
+      double s = A[(size_t)j * n + i];
+      for (int k = 0; k < j; k++) s = fma(-A[(size_t)k * n + i], A[(size_t)k * n + j], s);
+      A[(size_t)j * n + i] = s / d;
+    }
+    g.sync();
+  }
+  return true;
+}
+// solve_chol_fast for one right-hand side, one thread
+B2M_HD B2M_INL void chol_solve1(const double* L, int n, double* b) {
+  for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s = fma(-L[(size_t)k * n + i], b[k], s); b[i] = s / L[(size_t)i * n + i]; }
+  for (int i = n - 1; i >= 0; i--) { double s = b[i]; for (int k = i + 1; k < n; k++) s = fma(-L[(size_t)i * n + k], b[k], s); b[i] = s / L[(size_t)i * n + i]; }
+}
+// the "check" matrix [[S X S^T, S X T^T], [T X S^T, T X T^T]] over the chosen tangent indices (:1098-1112)
+template <class G>
+B2M_DEV void noslip_form_Y(const G& g, const EnvMem& m, int nc, const int* Si, int ns, const int* Ti, int nt, double skew, double* Y) {
+  const int mm = ns + nt;
+  for (int t = g.tid; t < mm * mm; t += G::size) {
+    const int a = t % mm, b = t / mm;
+    double v;
+    if (a < ns && b < ns) v = Dn(m, nc, 1, 1, Si[a], Si[b]);
+    else if (a >= ns && b >= ns) v = Dn(m, nc, 2, 2, Ti[a - ns], Ti[b - ns]);
+    else if (a < ns) v = Dn(m, nc, 1, 2, Si[a], Ti[b - ns]);
+    else v = Dn(m, nc, 1, 2, Si[b], Ti[a - ns]);
+    if (a == b) v -= skew;
+    Y[t] = v;
+  }
+  g.sync();
+}
+
+// apply_no_slip_model (ImpactConstraintHandler.cpp:1009-1417), nl = 0, no implicit joints: greedy full-rank tangent set by
+// trial Cholesky (:1089-1145), Schur-complement LCP in the normal impulses (:1170-1236), lcp_fast with the
+// lcp_lemke_regularized fallback (:1239-1284), back-substituted tangent impulses (:1294-1308), velocity update (:1370-1400).
+// The scratch matrices live in the island's (unused) QP LCP buffer: 9 nc^2 + 5 nc doubles <= (8 nc)^2.
+template <class G>
+B2M_DEV B2M_NOINL void apply_no_slip_model(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int nc = m.scal[S_NC];
+  double* Y = m.MM; double* QXW = Y + (size_t)4 * nc * nc; double* WM = QXW + (size_t)2 * nc * nc; double* LM = WM + (size_t)2 * nc * nc;
+  double* YXv = LM + (size_t)nc * nc; double* wv = YXv + 2 * nc;
+  int* Si = m.frow_c; int* Ti = m.frow_j;
+  int ns = 0, nt = 0;
+  for (int i = 0; i < nc; i++) {
+    if (g.tid == 0) Si[ns] = i;
+    g.sync();
+    noslip_form_Y(g, m, nc, Si, ns + 1, Ti, nt, B2M_NEAR_ZERO, Y);
+    if (chol_factor_group(g, Y, ns + 1 + nt)) ns++;                       // :1115-1116
+    g.sync();
+    if (g.tid == 0) Ti[nt] = i;
+    g.sync();
+    noslip_form_Y(g, m, nc, Si, ns, Ti, nt + 1, B2M_NEAR_ZERO, Y);
+    if (chol_factor_group(g, Y, ns + nt + 1)) nt++;                       // :1140-1141
+    g.sync();
+  }
+  const int mm = ns + nt;
+  noslip_form_Y(g, m, nc, Si, ns, Ti, nt, 0.0, Y);                        // :1165-1176
+  const bool ok = (mm == 0) || chol_factor_group(g, Y, mm);               // :1179
+  for (int t = g.tid; t < nc * mm; t += G::size) {                       // Q X W^T (:1195-1204), nc x mm column-major
+    const int i = t % nc, a = t / nc;
+    QXW[t] = (a < ns) ? Dn(m, nc, 0, 1, i, Si[a]) : Dn(m, nc, 0, 2, i, Ti[a - ns]);
+  }
+  g.sync();
+  for (int i = g.tid; i < nc; i += G::size) {                            // Y (W X Q^T), one column per thread (:1207-1208)
+    for (int a = 0; a < mm; a++) WM[(size_t)i * mm + a] = QXW[(size_t)a * nc + i];
+    if (ok && mm) chol_solve1(Y, mm, WM + (size_t)i * mm);
+  }
+  if (g.tid == 0) {
+    for (int a = 0; a < ns; a++) YXv[a] = m.Cv[nc + Si[a]];              // :1220-1224
+    for (int b = 0; b < nt; b++) YXv[ns + b] = m.Cv[2 * nc + Ti[b]];
+    if (ok && mm) chol_solve1(Y, mm, YXv);                               // :1227-1228
+  }
+  g.sync();
+  for (int t = g.tid; t < nc * nc; t += G::size) {
+    const int i = t % nc, j = t / nc;
+    double s = 0.0;
+    for (int a = 0; a < mm; a++) s = fma(QXW[(size_t)a * nc + i], WM[(size_t)j * mm + a], s);   // :1211
+    LM[t] = Dn(m, nc, 0, 0, i, j) - s;                                   // :1212
+  }
+  for (int i = g.tid; i < nc; i += G::size) {
+    double s = 0.0;
+    for (int a = 0; a < mm; a++) s = fma(QXW[(size_t)a * nc + i], YXv[a], s);   // :1231
+    m.qq[i] = m.Cv[i] - s;                                               // :1215-1216,1234
+  }
+  const bool warm = (m.scal[S_VLN] == nc);                               // the member _v (rule H1 extended)
+  for (int i = g.tid; i < nc; i += G::size) m.z[i] = warm ? m.vl[i] : 0.0;
+  g.sync();
+  int piv = 0, ex = 0;
+  long long fast_calls = 0, lemke_calls = 0, pivots = 0, executed = 0;
+  bool solved = false;
+  if (ok) {
+    const int st = lcp_fast_solve(g, nc, LM, nc, m.qq, 0.0, -1.0, warm, m.z, m.work, m.iwork, &piv, nullptr, 0, nullptr, nullptr, &ex);   // :1239
+    fast_calls = 1; pivots = piv; executed = ex;
+    solved = (st == LCP_OK || st == LCP_TRIVIAL);
+    if (!solved) {
+      g.sync();
+      long long stats[3] = {0, 0, 0};
+      const int st2 = lcp_lemke_regularized(g, nc, LM, nc, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, nullptr);   // :1279
+      lemke_calls = stats[0]; pivots += stats[1]; executed += stats[2];
+      solved = (st2 != LCP_UNVERIFIED);
+    }
+  }
+  g.sync();
+  if (!solved) { for (int i = g.tid; i < nc; i += G::size) m.z[i] = 0.0; g.sync(); }
+  if (g.tid == 0) {
+    if (!solved) lc[CNT_LCP_FAIL]++;
+    lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
+    lc[CNT_PIVOT_FLOPS] += (unsigned long long)executed * 2ull * nc * (nc + 1);
+    if ((unsigned long long)nc > lc[CNT_MAX_N]) lc[CNT_MAX_N] = nc;
+    m.scal[S_VLN] = nc; m.scal[S_VLDIRTY] = 1;
+  }
+  for (int i = g.tid; i < nc; i += G::size) m.vl[i] = m.z[i];
+  if (P.tap_n) {
+    if (g.tid == 0) P.tap_n[e] = nc;
+    for (int t = g.tid; t < nc * nc; t += G::size) P.tap_MM[(size_t)e * P.nmax * P.nmax + t] = LM[t];
+    for (int i = g.tid; i < nc; i += G::size) { P.tap_qq[(size_t)e * P.nmax + i] = m.qq[i]; P.tap_z[(size_t)e * P.nmax + i] = m.z[i]; }
+  }
+  // [cs; ct] = -(Y W v + Y W X Q^T cn) (:1294-1299)
+  for (int a = g.tid; a < mm; a += G::size) { double s = 0.0; for (int i = 0; i < nc; i++) s = fma(QXW[(size_t)a * nc + i], m.z[i], s); wv[a] = s; }
+  for (int i = g.tid; i < nc; i += G::size) { m.imp[i] = m.z[i]; m.imp[nc + i] = 0.0; m.imp[2 * nc + i] = 0.0; }
+  g.sync();
+  if (g.tid == 0 && solved) {
+    if (ok && mm) chol_solve1(Y, mm, wv);
+    for (int a = 0; a < ns; a++) m.imp[nc + Si[a]] = -(YXv[a] + wv[a]);
+    for (int b = 0; b < nt; b++) m.imp[2 * nc + Ti[b]] = -(YXv[ns + b] + wv[ns + b]);
+  }
+  g.sync();
+  apply_to_bodies(g, P, m, m.imp);                                       // :1370-1400
+}
+
+// apply_no_slip_model_to_connected_constraints (ImpactConstraintHandler.cpp:236-293); rule H10: the trailing
+// update_from_stacked(_epd, _z) with the QP handler's stale _z (:288) is skipped.
+template <class G>
+B2M_DEV void apply_no_slip_to_connected(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc) {
+  const int nc = m.scal[S_NC];
+  apply_no_slip_model(g, P, e, m, lc);
+  update_constraint_velocities(g, m, m.imp);                             // :262
+  const double minv = min_constraint_velocity(g, m);
+  bool changed = false;                                                  // apply_restitution(q) :497-524
+  for (int i = g.tid; i < nc; i += G::size) {
+    const double c = m.imp[i] * m.ceps[m.icon[i]];
+    m.imp[i] = c;
+    if (c > B2M_NEAR_ZERO) changed = true;
+  }
+  changed = g.any(changed);
+  g.sync();
+  if (changed) {
+    for (int i = g.tid; i < nc; i += G::size) { m.imp[nc + i] = 0.0; m.imp[2 * nc + i] = 0.0; }
+    g.sync();
+    apply_to_bodies(g, P, m, m.imp);                                     // update_from_stacked(q) :271
+    update_constraint_velocities(g, m, m.imp);                           // :274
+    const double minv_plus = min_constraint_velocity(g, m);
+    if (minv_plus < 0.0 && minv_plus < minv - B2M_NEAR_ZERO) apply_no_slip_model(g, P, e, m, lc);   // :281-285
+  }
+}
+
 // calc_impacting_unilateral_constraint_forces (ConstraintSimulator.cpp:298-355) -> apply_model (ImpactConstraintHandler.cpp:96-168)
 template <class G>
 B2M_DEV B2M_NOINL bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
@@ -1303,7 +1479,11 @@ B2M_DEV B2M_NOINL bool process_constraints(const G& g, const SimParams& P, int e
       for (unsigned i = 0; i < nc; i++) blocks += (m.ben[m.cb1[m.icon[i]]] ? 1 : 0) + (m.ben[m.cb2[m.icon[i]]] ? 1 : 0);
       lc[CNT_ASM_FLOPS] += 2 * 3 * 36 * blocks + 2 * (3 * nc) * (3 * nc) * 6 + 2 * ngc * 3 * nc;
     }
-    if (!(P.model == 1 ? apply_ap_model(g, P, e, m, lc, cx) : apply_qp_model(g, P, e, m, lc, cx))) return false;
+    bool all_inf = true;                                             // ImpactConstraintHandler.cpp:122-135
+    for (int i = g.tid; i < m.scal[S_NC]; i += G::size) if (m.cmu[m.icon[i]] < 1e2) all_inf = false;
+    all_inf = !g.any(!all_inf);
+    if (all_inf) apply_no_slip_to_connected(g, P, e, m, lc);
+    else if (!(P.model == 1 ? apply_ap_model(g, P, e, m, lc, cx) : apply_qp_model(g, P, e, m, lc, cx))) return false;
     g.sync();
   }
   // ImpactToleranceException check over the solved islands (:153-167): counted, never fatal

@@ -346,6 +346,8 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)ne, &P.time));
   TRY(dev_zero(h, (size_t)h->nmax * ne, &P.zlast));
   TRY(dev_zero(h, (size_t)ne, &P.zlast_n));
+  TRY(dev_zero(h, (size_t)h->cmax * ne, &P.vlast));
+  TRY(dev_zero(h, (size_t)ne, &P.vlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
   TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 4), &P.kstat));
   TRY(dev_zero(h, (size_t)ne, &P.hacc));

@@ -994,6 +994,108 @@ static void apply_ap_model(Sim& S, ProblemData& q) {
   apply_to_bodies(S, q);
 }
 
+// apply_no_slip_model (ImpactConstraintHandler.cpp:1009-1417), nl = 0, no implicit joints.  The tangential directions
+// become equality constraints; the largest set of them that keeps [S;T] X [S;T]^T positive definite is chosen greedily
+// by trial Cholesky of the matrix skewed by -NEAR_ZERO (:1089-1145); the normal impulses solve the nc x nc Schur LCP
+// MM = Cn X Cn^T - (Cn X W^T) Y (W X Cn^T), qq = Cn v - (Cn X W^T) Y W v with W = [S;T], Y = (W X W^T)^-1 (:1170-1236)
+// through lcp_fast, falling back to lcp_lemke_regularized (:1239-1284).  Velocities are updated inside (:1370-1400).
+// Rule H1 extended to the member `_v` handed to lcp_fast (:1239): per env, warm start iff its size equals nc; a size
+// change takes lcp_fast's cold branch (LCP.cpp:89-103) exactly as the reference's size test would.
+static void apply_no_slip_model(Sim& S, ProblemData& q) {
+  const int nc = q.nc;
+  std::vector<int> Si, Ti;
+  Vec Y;
+  auto form_Y = [&](double skew) {                                       // :1098-1112
+    const int ns = (int)Si.size(), nt = (int)Ti.size(), m = ns + nt;
+    Y.assign((size_t)m * m, 0.0);
+    for (int a = 0; a < ns; a++) for (int b = 0; b < ns; b++) Y[(size_t)b * m + a] = Dn(q, 1, 1, Si[a], Si[b]);
+    for (int a = 0; a < nt; a++) for (int b = 0; b < nt; b++) Y[(size_t)(ns + b) * m + ns + a] = Dn(q, 2, 2, Ti[a], Ti[b]);
+    for (int a = 0; a < ns; a++) for (int b = 0; b < nt; b++) { const double v = Dn(q, 1, 2, Si[a], Ti[b]); Y[(size_t)(ns + b) * m + a] = v; Y[(size_t)a * m + ns + b] = v; }
+    for (int j = 0; j < m; j++) Y[(size_t)j * m + j] -= skew;
+    return m;
+  };
+  for (int i = 0; i < nc; i++) {
+    Si.push_back(i);
+    int m = form_Y(NEAR_ZERO);
+    if (!factor_chol(Y.data(), m)) Si.pop_back();                         // :1115-1116
+    Ti.push_back(i);
+    m = form_Y(NEAR_ZERO);
+    if (!factor_chol(Y.data(), m)) Ti.pop_back();                         // :1140-1141
+  }
+  const int ns = (int)Si.size(), nt = (int)Ti.size(), m = ns + nt;
+  form_Y(0.0);                                                            // :1165-1176
+  const bool ok = (m == 0) || factor_chol(Y.data(), m);                   // :1179 (asserted in the reference)
+  // Q X W^T : nc x m (:1195-1204), column-major
+  Vec QXW((size_t)nc * m, 0.0);
+  for (int a = 0; a < ns; a++) for (int i = 0; i < nc; i++) QXW[(size_t)a * nc + i] = Dn(q, 0, 1, i, Si[a]);
+  for (int b = 0; b < nt; b++) for (int i = 0; i < nc; i++) QXW[(size_t)(ns + b) * nc + i] = Dn(q, 0, 2, i, Ti[b]);
+  // workM = Y (W X Q^T): m x nc, one Cholesky solve per column (:1207-1208)
+  Vec WM((size_t)m * nc, 0.0);
+  for (int i = 0; i < nc; i++) {
+    for (int a = 0; a < m; a++) WM[(size_t)i * m + a] = QXW[(size_t)a * nc + i];
+    if (ok && m) solve_chol(Y.data(), m, &WM[(size_t)i * m]);
+  }
+  Vec MM((size_t)nc * nc), qq(nc);
+  for (int j = 0; j < nc; j++)
+    for (int i = 0; i < nc; i++) {
+      double s = 0.0;
+      for (int a = 0; a < m; a++) s = std::fma(QXW[(size_t)a * nc + i], WM[(size_t)j * m + a], s);   // :1211
+      MM[(size_t)j * nc + i] = Dn(q, 0, 0, i, j) - s;                   // :1212
+    }
+  Vec YXv(m);
+  for (int a = 0; a < ns; a++) YXv[a] = q.Cv[1][Si[a]];                  // :1220-1224
+  for (int b = 0; b < nt; b++) YXv[ns + b] = q.Cv[2][Ti[b]];
+  if (ok && m) solve_chol(Y.data(), m, YXv.data());                      // :1227-1228
+  for (int i = 0; i < nc; i++) {
+    double s = 0.0;
+    for (int a = 0; a < m; a++) s = std::fma(QXW[(size_t)a * nc + i], YXv[a], s);   // :1231
+    qq[i] = q.Cv[0][i] - s;                                              // :1215-1216,1234
+  }
+  S.cnt.lcp_solves++;
+  S.cnt.max_lcp_n = std::max<long long>(S.cnt.max_lcp_n, nc);
+  const unsigned long long f0 = S.lcp.n_fast_calls, l0 = S.lcp.n_lemke_calls, p0 = S.lcp.n_pivots_total;
+  Vec v = S.vlast;                                                       // the member _v: warm start iff sizes match
+  bool solved = ok && S.lcp.lcp_fast(nc, MM.data(), qq.data(), v);       // :1239
+  if (ok && !solved) { v.clear(); solved = S.lcp.lcp_lemke_regularized(nc, MM.data(), qq.data(), v); }   // :1279
+  if (!solved) { S.cnt.lcp_failures++; v.assign(nc, 0.0); }             // std::runtime_error in the reference (:1280)
+  S.cnt.lcp_fast_calls += S.lcp.n_fast_calls - f0; S.cnt.lemke_calls += S.lcp.n_lemke_calls - l0; S.cnt.pivots += S.lcp.n_pivots_total - p0;
+  S.cnt.pivot_flops += (long long)(S.lcp.n_pivots_total - p0) * 2 * nc * (nc + 1);
+  S.vlast = v;
+  S.last_n = nc; S.last_MM = MM; S.last_qq = qq; S.last_z = v;
+  // [cs; ct] = -(Y W v + Y W X Q^T cn) (:1294-1299)
+  Vec w(m, 0.0);
+  for (int a = 0; a < m; a++) { double s = 0.0; for (int i = 0; i < nc; i++) s = std::fma(QXW[(size_t)a * nc + i], v[i], s); w[a] = s; }
+  if (ok && m) solve_chol(Y.data(), m, w.data());
+  for (int i = 0; i < nc; i++) { q.cn[i] = v[i]; q.cs[i] = 0.0; q.ct[i] = 0.0; }
+  if (solved) {
+    for (int a = 0; a < ns; a++) q.cs[Si[a]] = -(YXv[a] + w[a]);
+    for (int b = 0; b < nt; b++) q.ct[Ti[b]] = -(YXv[ns + b] + w[ns + b]);
+  }
+  apply_to_bodies(S, q);                                                 // :1370-1400
+}
+
+// apply_no_slip_model_to_connected_constraints (ImpactConstraintHandler.cpp:236-293).  Rule H10: the trailing
+// update_from_stacked(_epd, _z) after a second solve (:288) re-applies the QP handler's stale member _z (empty in a
+// no-slip-only run: out-of-bounds in the reference); it is skipped here and in the kernels.
+static void apply_no_slip_to_connected(Sim& S, ProblemData& q) {
+  apply_no_slip_model(S, q);
+  update_constraint_velocities(q);                                      // :262
+  double minv = calc_min_constraint_velocity(q);
+  bool changed = false;                                                 // apply_restitution(q) :497-524
+  for (int i = 0; i < q.nc; i++) {
+    q.cn[i] *= q.cons[i]->cp.eps;
+    if (!changed && q.cn[i] > NEAR_ZERO) changed = true;
+  }
+  if (changed) {
+    std::fill(q.cs.begin(), q.cs.end(), 0.0);
+    std::fill(q.ct.begin(), q.ct.end(), 0.0);
+    apply_to_bodies(S, q);                                              // update_from_stacked(q) :271
+    update_constraint_velocities(q);                                    // :274
+    double minv_plus = calc_min_constraint_velocity(q);
+    if (minv_plus < 0.0 && minv_plus < minv - NEAR_ZERO) apply_no_slip_model(S, q);   // :281-285
+  }
+}
+
 void Sim::assemble_island_lcp(const std::vector<Contact*>& cons, const std::vector<int>& island_bodies, int& n, Vec& MM, Vec& qq) {
   ProblemData q;
   compute_problem_data(*this, q, cons, island_bodies);
@@ -1048,7 +1150,10 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
     if (!active[g]) continue;
     ProblemData q;
     compute_problem_data(*this, q, groups[g].first, groups[g].second);
-    if (model == MODEL_AP) apply_ap_model(*this, q); else apply_qp_model(*this, q);
+    bool all_inf = true;                                                // ImpactConstraintHandler.cpp:122-135
+    for (size_t i = 0; i < groups[g].first.size(); i++) if (groups[g].first[i]->cp.mu_c < 1e2) all_inf = false;
+    if (all_inf) apply_no_slip_to_connected(*this, q);
+    else if (model == MODEL_AP) apply_ap_model(*this, q); else apply_qp_model(*this, q);
   }
   // ImpactToleranceException check over the remaining groups (ImpactConstraintHandler.cpp:153-167): only logged by the caller
   bool still = false;

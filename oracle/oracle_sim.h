@@ -17,7 +17,8 @@
 // Rules adopted where the reference is history-, allocation- or rand()-dependent (SURVEY.md 8a'):
 //   H1 zlast is zero-filled on size change; H2 lowest-index tie rule (glibc-rand optional);
 //   H3 restitution re-applies friction (literal); H4 bodies by scene index, pairs lexicographic,
-//   contacts in generation order; H6 non-logging create_contact; H8 collinearity scan tests points 0,1,2.
+//   contacts in generation order; H6 non-logging create_contact; H8 collinearity scan tests points 0,1,2;
+//   H10 the no-slip path's trailing update_from_stacked(_epd, _z) with the QP handler's stale _z is skipped.
 #pragma once
 #include <vector>
 #include "oracle_lcp.h"
@@ -82,6 +83,7 @@ struct Sim {
   double current_time = 0.0;
   LCP lcp;
   Vec zlast;                            // ImpactConstraintHandler::_zlast
+  Vec vlast;                            // ImpactConstraintHandler::_v, the no-slip LCP's solution / warm start (:1239)
   Counters cnt;
   // taps for parity tests: LCP of the most recent impact solve
   int last_n = 0;

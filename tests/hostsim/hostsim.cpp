@@ -24,6 +24,7 @@ static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, 
   P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
   P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
   P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
+  P.vlast = zlast + (size_t)nmax * ne; P.vlast_n = zlast_n + ne;   // the caller's arrays carry both warm starts
   if (d->rc && d->rc->n_links > 0) {
     bool unsup;
     if (b2m_rc_tree_from_desc(*d->rc, nb, tree, &unsup)) return false;
@@ -37,7 +38,7 @@ static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, 
 
 extern "C" {
 
-// q [nb][7][ne], v [nb][6][ne], time [ne], zlast [nmax][ne], zlast_n [ne], counters [CNT_COUNT] all host, updated in place.
+// q [nb][7][ne], v [nb][6][ne], time [ne], zlast [2 nmax][ne] (QP warm start, then the no-slip one), zlast_n [2][ne], counters [CNT_COUNT] all host, updated in place.
 // Returns nmax (call with q == NULL to query sizes only).
 int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time, double* zlast, int* zlast_n,
                 unsigned long long* counters, double dt, int n_steps, int e0, int e1, double* tapMM, double* tapqq, double* tapz, int* tapn,

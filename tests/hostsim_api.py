@@ -48,7 +48,7 @@ class HostSim:
         self.q, self.v = scene.q.copy(), scene.v.copy()
         self.q[:, 3:7, :] /= np.sqrt((self.q[:, 3:7, :] ** 2).sum(axis=1, keepdims=True))   # as b200moby_set_state does
         self.time = np.zeros(ne)
-        self.zlast, self.zlast_n = np.zeros((self.nmax, ne)), np.zeros(ne, np.int32)
+        self.zlast, self.zlast_n = np.zeros((2 * self.nmax, ne)), np.zeros(2 * ne, np.int32)
         self.counters = np.zeros(16, np.uint64)
         self.rc = getattr(scene, "rc", None)
         self.jq = self.rc.jq.copy() if self.rc is not None else None
