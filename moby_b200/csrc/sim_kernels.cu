@@ -40,6 +40,7 @@ struct b200moby_sim {
   ClassPlan straggler;       // full-size block-per-env kernel for envs over their pivot budget
   ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
   int fin_grid = 1;
+  ClassPlan finblock;        // nmax > B200MOBY_BIG_N: the finish phase runs one 256-thread block per env (threads == 256 when in use)
   bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
   long long launches = 0;
   // the impact classes of one round touch disjoint envs: they run on side streams so that the tail of one class
@@ -243,6 +244,15 @@ b200moby_status plan_launch(b200moby_sim* h) {
     ClassPlan& sg = h->straggler;
     sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = 256;
     if ((st = plan_memory(h, impact_block_ptr(256), sg, 1, ne)) != B200MOBY_OK) return st;
+    // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished
+    // by one block per env, and more rounds keep that remainder small (each extra round is a handful of short launches).
+    h->finblock.threads = 32;
+    if (h->nmax > big_n) {
+      ClassPlan& fb = h->finblock;
+      fb.nmax = h->nmax; fb.cmax = h->cmax; fb.threads = 256;
+      if ((st = plan_memory(h, b2m_k_finish_block256(), fb, 1, ne)) != B200MOBY_OK) return st;
+      h->rounds = std::max(1, std::min(B2M_ROUNDS_MAX, env_int("B200MOBY_ROUNDS", 4)));
+    }
   }
   return B200MOBY_OK;
 }
@@ -300,7 +310,10 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
   }
   { int r = h->rounds - 1; SimParams Pf = P; Pf.kslot = 2 + ncls;
     void* a[] = {&Pf, &dt, &r};
-    if ((st = timed_launch(h, 2 + ncls, b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)) != B200MOBY_OK) return st; }
+    if (h->finblock.threads == 256) {
+      Pf.gscratch = h->finblock.gscratch; Pf.gstride = h->finblock.gstride;
+      if ((st = timed_launch(h, 2 + ncls, b2m_k_finish_block256(), dim3(h->finblock.grid), dim3(256), a, h->finblock.shmem, s)) != B200MOBY_OK) return st;
+    } else if ((st = timed_launch(h, 2 + ncls, b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)) != B200MOBY_OK) return st; }
   B2M_CUDA(cudaGetLastError());
   return B200MOBY_OK;
 }

@@ -8,6 +8,7 @@ const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round,
 const void* b2m_k_impact_block64();
 const void* b2m_k_impact_block128();
 const void* b2m_k_impact_block256();
+const void* b2m_k_finish_block256();      // (SimParams P, double dt, int round): block-per-env finish for large-LCP scenes
 const void* b2m_k_rc_fwd_dyn();           // (SimParams P, int algo, const double* jq, const double* jqd, const double* tau, double* qdd)
 const void* b2m_k_rc_inertia();           // (SimParams P, const double* jq, double* H)
 const void* b2m_k_rc_refresh();           // (SimParams P)
