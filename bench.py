@@ -35,10 +35,10 @@ WORKLOADS = {
     "stacks": dict(name="example/stacks: 10-box stack, 4,096 envs per GPU, LCP n = 320 (BASELINE configs[2]; SURVEY 8d case 3)",
                    envs=4096, dt=1e-3, preroll=5, bytes=2080.0, cpu_sample=(4, 2), ref_sample=16,
                    make=lambda sc, ne, seed: sc.box_stack(ne, 10, seed=seed)),
-    "ur10": dict(name="example/ur10 arm (9-DoF RCArticulatedBody, CRB forward dynamics) + block + table, 16,384 envs per GPU "
-                      "(BASELINE configs[3]; SURVEY 8d case 4)",
+    "ur10": dict(name="example/ur10 arm (9-DoF RCArticulatedBody, CRB forward dynamics) + block + table, mu = 100 as ur10.xml:20 (no-slip impact model), "
+                      "16,384 envs per GPU (BASELINE configs[3]; SURVEY 8d case 4)",
                  envs=16384, dt=5e-4, preroll=100, bytes=2.0 * 8.0 * (9 + 9) + 208.0, cpu_sample=(256, 40), ref_sample=2048,
-                 make=lambda sc, ne, seed: sc.ur10(ne, seed=seed)),
+                 make=lambda sc, ne, seed: sc.ur10(ne, seed=seed, mu=100.0)),
 }
 
 
@@ -156,13 +156,109 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def run_lcp(args, rank, world, local_rank):
+    """--workload lcp: SURVEY.md 8(d) case 6, the batched solver microbenchmark.  A step = one call of
+    b200moby_lcp_lemke_batched over a batch of random LCPs (M = A A^T / n + 1e-3 I, q ~ N(0,1)) resident in HBM;
+    metric = LCP solves/s.  Roofline: algorithmic bytes 8 (n^2 + 2n) per solve (read M, q; write z) against HBM."""
+    import torch
+    import torch.distributed as dist
+    from moby_b200 import lcp as L
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.lcp_n
+    batch = args.envs_per_gpu or max(4096, min(262144, (2 << 30) // (8 * n * n)))      # ~2 GiB of matrices: larger than L2
+    gen = torch.Generator(device=dev); gen.manual_seed(0xB200 + rank)
+    A = torch.randn(batch, n, n, dtype=torch.float64, device=dev, generator=gen)
+    M = torch.bmm(A, A.transpose(1, 2)) / n + 1e-3 * torch.eye(n, dtype=torch.float64, device=dev)
+    del A
+    q = torch.randn(batch, n, dtype=torch.float64, device=dev, generator=gen)
+    solver = L.LCP()
+    Mc = M.transpose(-1, -2).contiguous()          # column-major blocks, as the C ABI takes them
+    z = torch.zeros_like(q); status = torch.zeros(batch, dtype=torch.int32, device=dev); pivots = torch.zeros_like(status)
+    from moby_b200 import capi
+    lib = capi.lib()
+    stream = torch.cuda.current_stream()
+
+    def solve():
+        capi.check(lib.b200moby_lcp_lemke_batched(batch, n, Mc.data_ptr(), q.data_ptr(), z.data_ptr(), -1.0, -1.0, status.data_ptr(),
+                                                  pivots.data_ptr(), None, 0, L._stream_ptr(None)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        solve()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    for a, b in ev:
+        a.record(stream); solve(); b.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    ok = int(((status == 0) | (status == 1)).sum().item())
+    piv_mean = float(pivots.double().mean().item())
+    # end to end with host buffers through the host-form entry point (H2D M, q; solve; D2H z inside the call)
+    Mh, qh = M.cpu().numpy(), q.cpu().numpy()
+    nb_e2e = min(batch, 32768)
+    L.lcp_lemke_host(Mh[:nb_e2e], qh[:nb_e2e], device=local_rank)
+    e0 = time.perf_counter()
+    for _ in range(3):
+        zh, sh, ph = L.lcp_lemke_host(Mh[:nb_e2e], qh[:nb_e2e], device=local_rank)
+    t_e2e = (time.perf_counter() - e0) / 3
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+    if rank == 0:
+        hbm_peak, hbm_src, fp64_peak, fp64_src = _peaks()
+        alg_bytes = 8.0 * (n * n + 2 * n) * batch
+        ms = 1e3 * t_dev / args.steps
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        flops = piv_mean * 2.0 * n * (n + 1) * batch
+        out = {"metric": "lcp_solves_per_s", "value": batch * world * args.steps / t_dev, "unit": "LCP solves/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"batched Lemke solver microbenchmark (SURVEY 8d case 6): {batch} random LCPs per GPU, n = {n}, M = A A^T / n + 1e-3 I, operands in HBM",
+                          "batch_per_gpu": batch, "n": n, "l2": f"inputs {alg_bytes / 2**20:.0f} MiB per launch, larger than L2", "parallelism": f"problems sharded x{world}"},
+               "solved": ok, "pivots_per_solve": piv_mean,
+               "e2e": {"value": nb_e2e * world / t_e2e, "unit": "LCP solves/s", "h2d_bytes_per_step": int(8 * (n * n + n) * nb_e2e), "d2h_bytes_per_step": int(8 * n * nb_e2e + 8 * nb_e2e),
+                       "how": f"b200moby_lcp_lemke_host on {nb_e2e} problems: pageable host M, q -> device, solve, z/status/pivots -> host inside the call"},
+               "gpu_launches": args.steps * world, "clocks": clocks,
+               "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                            "kernel": "lcp_warp_kernel" if n <= 160 else "lcp_block_kernel", "kernel_ms": ms, "peak_source": hbm_src,
+                            "fp64": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / fp64_peak,
+                                     "flops": "pivots * 2 n (n + 1) (tableau rank-one update, SURVEY 8d)"}}}
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_api as O
+            O.build()
+            ns = max(8, min(2000, int(4e8 / (n ** 4 + 1))))
+            t0 = time.perf_counter()
+            for b in range(ns):
+                O.lcp_lemke(Mh[b], qh[b])
+            el = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": ns / el, "unit": "LCP solves/s", "cores": 1, "kind": "port",
+                                   "sample": f"first {ns} problems of rank 0's batch, 1 thread ({el:.1f} s); oracle/ restatement of LCP::lcp_lemke (LU per pivot, as the reference)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="small", choices=sorted(WORKLOADS), help="BASELINE.json config (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--lcp-n", type=int, default=32, help="--workload lcp: LCP dimension")
+    ap.add_argument("--workload", default="small", choices=sorted(WORKLOADS) + ["lcp"], help="BASELINE.json config (default: configs[1], the one the metric is quoted on)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's own batch size")
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps before warm-up so contacts are active (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -172,6 +268,13 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.workload == "lcp":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "--workload lcp carries its CPU arm as cpu_baseline; the reference arm times the stepped path"}))
+            return
+        run_lcp(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -303,7 +406,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": ne, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200+rank",
                        "min_step_size": ("boxes 1e-3 (test/box.xml), balls sqrt(eps) (bouncing-ball.xml)" if args.min_step == "scene" else "sqrt(eps) everywhere") if args.workload == "small" else scene.min_step_size,
-                       "impact_model": "QP-as-LCP (default build)", "stabilization": "off (max-iterations=0)",
+                       "impact_model": "QP-as-LCP (default build); no-slip model for islands with mu >= 100", "stabilization": "off (max-iterations=0)",
                        "l2": "flushed between timed steps (256 MiB write outside the events)", "parallelism": f"envs sharded x{world}"},
             "lcp_solves_per_s": lcp_solves / t_dev,
             "mini_steps_per_step": mini_steps / max(env_steps, 1.0), "lcp_solves_per_env_step": lcp_solves / max(env_steps, 1.0),

@@ -25,6 +25,14 @@ enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LE
 #define B2M_SLOTS (B2M_MAX_CLASSES + 2)
 #define B2M_ROUNDS_MAX 8
 #define B2M_MAX_STALL 64
+// B2M_LEAN builds drop the articulated-body and box-box code paths (scenes of free spheres / boxes on planes): the
+// kernels' instruction footprint, not arithmetic, bounds the stepped path (profiles/: no_instruction is the top stall).
+#ifndef B2M_LEAN
+#define B2M_LEAN 0
+#endif
+#define B2M_RC(P) (!B2M_LEAN && (P).rc_links)
+#define B2M_NGC(P) (!B2M_LEAN && (P).ngc)
+#define B2M_BOXBOX (!B2M_LEAN)
 
 struct V3 {
   double x, y, z;
@@ -253,7 +261,7 @@ B2M_HD B2M_NOINL inline bool signed_dist_ordered(const BodyRef& A, const BodyRef
     pB = (vnorm == 0.0) ? ld3(B.x) : ld3(B.x) + v * ((B.dims[0] + fmin(dist, 0.0)) / vnorm);
     return true;
   }
-  if (A.shape == SH_BOX && B.shape == SH_BOX) { boxbox_signed_dist(A, B, dist, pA, pB); return true; }   // rule H5 (boxbox_device.cuh)
+  if (B2M_BOXBOX && A.shape == SH_BOX && B.shape == SH_BOX) { boxbox_signed_dist(A, B, dist, pA, pB); return true; }   // rule H5 (boxbox_device.cuh)
   return false;
 }
 B2M_HD inline bool signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
@@ -343,7 +351,7 @@ B2M_HD B2M_NOINL inline int pair_contacts(const EnvMem& m, int ia, int ib, doubl
     if (cnt < cap) { out[cnt].p = p; out[cnt].n = normal; out[cnt].b1 = ix; out[cnt].b2 = is; out[cnt].dist = dist; }
     return cnt + 1;
   }
-  if (A.shape == SH_BOX && B.shape == SH_BOX) {                                                            // CCD.inl:86-494, rule H5
+  if (B2M_BOXBOX && A.shape == SH_BOX && B.shape == SH_BOX) {                                                            // CCD.inl:86-494, rule H5
     V3 pts[8], normal; double depth[8];
     const int k = boxbox_contacts(A, B, TOL, pts, depth, normal);
     for (int i = 0; i < k; i++) {
@@ -424,7 +432,7 @@ B2M_HD B2M_NOINL inline double pair_CA(const EnvMem& m, int p) {
       const V3 ra = rotT(gB.R, ang_vel(gA) - ang_vel(gB));
       return next_CA_box_plane(gB, -rl, -ra, -con[0].n, -d);
     }
-    if (gA.shape == SH_BOX && gB.shape == SH_BOX) {                          // CCD.cpp:350-364 -> :468-541
+    if (B2M_BOXBOX && gA.shape == SH_BOX && gB.shape == SH_BOX) {                          // CCD.cpp:350-364 -> :468-541
       const V3 wrel = ang_vel(gA) - ang_vel(gB);
       const V3 rlA = rotT(gA.R, lin_vel(gA) - point_vel(gB, ld3(gA.x))), rlB = rotT(gB.R, point_vel(gA, ld3(gB.x)) - lin_vel(gB));
       return next_CA_box_box(gA, gB, rlA, rotT(gA.R, wrel), rlB, rotT(gB.R, wrel), con[0].n, d);
@@ -446,7 +454,7 @@ B2M_HD B2M_NOINL inline double pair_CA(const EnvMem& m, int p) {
 // super body whose generalized coordinates are the joint positions (ImpactConstraintHandler.cpp:1905-1916 collects
 // super bodies, :1817-1895 maps link wrenches through the link Jacobian); its representative in the island code is
 // the first moving link.
-B2M_HD B2M_INL bool is_link(const SimParams& P, int b) { return P.rc_links > 0 && b > P.rc_first && b < P.rc_first + P.rc_links; }
+B2M_HD B2M_INL bool is_link(const SimParams& P, int b) { return B2M_RC(P) > 0 && b > P.rc_first && b < P.rc_first + P.rc_links; }
 B2M_HD B2M_INL int super_of(const SimParams& P, int b) { return is_link(P, b) ? P.rc_first + 1 : b; }
 
 // link poses, motion subspaces, spatial and COM velocities from (jq, jqd): what RCArticulatedBodyd::update_link_poses /
@@ -492,9 +500,9 @@ B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m
     m.scal[S_ZLDIRTY] = 0;
     m.scal[S_VLN] = P.vlast_n ? P.vlast_n[e] : 0;
     m.scal[S_VLDIRTY] = 0;
-    if (P.rc_links) { m.ranc[0] = 0; for (int i = 1; i < P.rc_links; i++) m.ranc[i] = m.ranc[P.rc->parent[i]] | (1 << i); }
+    if (B2M_RC(P)) { m.ranc[0] = 0; for (int i = 1; i < P.rc_links; i++) m.ranc[i] = m.ranc[P.rc->parent[i]] | (1 << i); }
   }
-  if (P.rc_links) {
+  if (B2M_RC(P)) {
     for (int k = g.tid; k < P.rc_links - 1; k += G::size) { m.jq[k] = P.jq[(size_t)k * ne + e]; m.jqd[k] = P.jqd[(size_t)k * ne + e]; m.jtau[k] = P.jtau[(size_t)k * ne + e]; }
     g.sync();
     rc_refresh(g, P, m);
@@ -514,7 +522,7 @@ enum { ST_POS = 1, ST_VEL = 2, ST_ZL = 4 };
 template <class G>
 B2M_DEV B2M_NOINL void env_store(const G& g, const SimParams& P, int e, const EnvMem& m, int what = ST_POS | ST_VEL | ST_ZL) {
   const int nb = P.nb, ne = P.n_envs;
-  if (P.rc_links) {
+  if (B2M_RC(P)) {
     if (what & ST_POS) for (int i = 1 + g.tid; i < P.rc_links; i += G::size) R_to_quat(m.bR + 9 * (P.rc_first + i), m.bq + 4 * (P.rc_first + i));
     for (int k = g.tid; k < P.rc_links - 1; k += G::size) {
       if (what & ST_POS) P.jq[(size_t)k * ne + e] = m.jq[k];
@@ -556,7 +564,7 @@ B2M_DEV B2M_NOINL void calc_pairwise_distances(const G& g, EnvMem& m) {       //
 // TimeSteppingSimulator.cpp:181-192; GravityForce.cpp:32-48).  One thread per body.
 template <class G>
 B2M_DEV B2M_NOINL void fwd_dyn_integrate_velocity(const G& g, const SimParams& P, EnvMem& m, double h, double t) {
-  if (P.rc_links) {   // Simulator.cpp:339-348 controller, :544-553 RCArticulatedBodyd::calc_fwd_dyn (ABA or CRB), then qd += h qdd
+  if (B2M_RC(P)) {   // Simulator.cpp:339-348 controller, :544-553 RCArticulatedBodyd::calc_fwd_dyn (ABA or CRB), then qd += h qdd
     if (g.tid == 0) {
       const RCTree& T = *P.rc;
       const int nd = T.n_links - 1;
@@ -594,7 +602,7 @@ B2M_DEV B2M_NOINL double integrate_positions_CA(const G& g, const SimParams& P, 
   const int nb = P.nb;
   for (int k = g.tid; k < 3 * nb; k += G::size) m.xsave[k] = m.bx[k];
   for (int k = g.tid; k < 4 * nb; k += G::size) m.qsave[k] = m.bq[k];
-  if (P.rc_links) for (int k = g.tid; k < P.rc_links - 1; k += G::size) m.jqsave[k] = m.jq[k];
+  if (B2M_RC(P)) for (int k = g.tid; k < P.rc_links - 1; k += G::size) m.jqsave[k] = m.jq[k];
   g.sync();
   double h = 0.0;
   const double min_step = P.min_step_env ? P.min_step_env[e] : P.min_step_size;
@@ -609,7 +617,7 @@ B2M_DEV B2M_NOINL double integrate_positions_CA(const G& g, const SimParams& P, 
     double tc = fmax(min_step, CA);
     tc = fmin(dt - h, tc);
     g.sync();
-    if (P.rc_links) {   // joint coordinates are their own Euler coordinates: q = qsave + (h + tc) qd
+    if (B2M_RC(P)) {   // joint coordinates are their own Euler coordinates: q = qsave + (h + tc) qd
       for (int k = g.tid; k < P.rc_links - 1; k += G::size) m.jq[k] = m.jqd[k] * (h + tc) + m.jqsave[k];
       g.sync();
       rc_refresh(g, P, m);
@@ -764,7 +772,7 @@ B2M_DEV B2M_NOINL void compute_problem_data_dense(const G& g, const SimParams& P
   // generalized velocity of the island
   for (int k = g.tid; k < ngc; k += G::size) {
     const int b = m.gcb[k], l = m.gcl[k];
-    m.gv[k] = (b == rep && P.rc_links) ? m.jqd[l] : (l < 3 ? m.bvl[3 * b + l] : m.bva[3 * b + l - 3]);
+    m.gv[k] = (b == rep && B2M_RC(P)) ? m.jqd[l] : (l < 3 ? m.bvl[3 * b + l] : m.bva[3 * b + l - 3]);
   }
   // Jacobian rows, one thread per (dir, contact, coordinate)
   for (int t = g.tid; t < 3 * nc * ngc; t += G::size) {
@@ -841,11 +849,11 @@ B2M_DEV B2M_NOINL void apply_to_bodies_dense(const G& g, const SimParams& P, Env
   bool rc_touched = false;
   for (int k = g.tid; k < ngc; k += G::size) {
     const int b = m.gcb[k], l = m.gcl[k];
-    if (b == rep && P.rc_links) m.jqd[l] = m.jqd[l] + m.dv[k];
+    if (b == rep && B2M_RC(P)) m.jqd[l] = m.jqd[l] + m.dv[k];
     else if (l < 3) m.bvl[3 * b + l] = m.bvl[3 * b + l] + m.dv[k];
     else m.bva[3 * b + l - 3] = m.bva[3 * b + l - 3] + m.dv[k];
   }
-  rc_touched = P.rc_links && m.gcoff[rep] >= 0;
+  rc_touched = B2M_RC(P) && m.gcoff[rep] >= 0;
   g.sync();
   if (rc_touched) rc_refresh(g, P, m);
 }
@@ -853,7 +861,7 @@ B2M_DEV B2M_NOINL void apply_to_bodies_dense(const G& g, const SimParams& P, Env
 // ImpactConstraintHandler::compute_problem_data (:1898-2166) for the island whose contacts are icon[0..nc)
 template <class G>
 B2M_DEV B2M_NOINL void compute_problem_data(const G& g, const SimParams& P, EnvMem& m) {
-  if (P.ngc) { compute_problem_data_dense(g, P, m); return; }
+  if (B2M_NGC(P)) { compute_problem_data_dense(g, P, m); return; }
   const int nc = m.scal[S_NC], nb = P.nb;
   // X = blockdiag(inverse_SPD(generalized inertia)) (:1590-1611), one thread per island body
   for (int b = g.tid; b < nb; b += G::size) {
@@ -1045,7 +1053,7 @@ B2M_DEV B2M_NOINL int build_ap_lcp(const G& g, const SimParams& P, EnvMem& m) {
 // update_from_stacked (:298-397) without bilateral joints: v += X_CnT cn + X_CsT cs + X_CtT ct, impulses from `imp`
 template <class G>
 B2M_DEV B2M_NOINL void apply_to_bodies(const G& g, const SimParams& P, EnvMem& m, const double* imp) {
-  if (P.ngc) { apply_to_bodies_dense(g, P, m, imp); return; }
+  if (B2M_NGC(P)) { apply_to_bodies_dense(g, P, m, imp); return; }
   const int nc = m.scal[S_NC], nb = P.nb;
   for (int t = g.tid; t < 6 * nb; t += G::size) {
     const int b = t / 6, k = t - 6 * b;
@@ -1465,7 +1473,7 @@ B2M_DEV B2M_NOINL bool process_constraints(const G& g, const SimParams& P, int e
           } else m.gcoff[b] = m.gcoff[rep];
         } else if (m.bisl[b] == k && m.ben[b]) {
           m.gcoff[b] = gc;
-          if (P.ngc) for (int l = 0; l < 6; l++) { m.gcb[gc + l] = b; m.gcl[gc + l] = l; }
+          if (B2M_NGC(P)) for (int l = 0; l < 6; l++) { m.gcb[gc + l] = b; m.gcl[gc + l] = l; }
           gc += 6;
         } else m.gcoff[b] = -1;
       }
@@ -1516,7 +1524,7 @@ B2M_DEV void mini_step_account(const G& g, const SimParams& P, const EnvMem& m, 
     lc[CNT_MINI_STEPS]++;
     unsigned long long f = 0;
     for (int b = 0; b < P.nb; b++) if (m.ben[b] && !is_link(P, b)) f += 60;
-    if (P.rc_links) f += 500ull * (P.rc_links - 1);   // ABA, Featherstone's operation count
+    if (B2M_RC(P)) f += 500ull * (P.rc_links - 1);   // ABA, Featherstone's operation count
     for (int p = 0; p < m.scal[S_NPAIRS]; p++) f += 3 * ((m.bshape[m.pair_a[p]] == SH_BOX || m.bshape[m.pair_b[p]] == SH_BOX) ? 160 : 20);
     lc[CNT_ASM_FLOPS] += f;
   }
@@ -1526,7 +1534,11 @@ B2M_DEV void mini_step_account(const G& g, const SimParams& P, const EnvMem& m, 
 // shared-memory class of the impact kernel.
 B2M_HD B2M_INL int contacts_lcp_dim(const EnvMem& m, int ncon, int model) {
   int n = 0;
-  for (int c = 0; c < ncon; c++) { const int nk = m.cNK[c]; n += (model == 1) ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2; }
+  bool all_inf = true;
+  for (int c = 0; c < ncon; c++) { const int nk = m.cNK[c]; n += (model == 1) ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2; if (m.cmu[c] < 1e2) all_inf = false; }
+  // every island of the env takes the no-slip model: its LCP is nc x nc and its scratch 9 nc^2 + 5 nc doubles of the LCP
+  // buffer, which (3 nc + 2)^2 covers -- a much smaller class than the QP / A-P dimension
+  if (all_inf && 3 * ncon + 2 < n) n = 3 * ncon + 2;
   return n;
 }
 

@@ -36,6 +36,7 @@ struct b200moby_sim {
   // phased step plan
   int rounds = 2;
   int adv_wpb = 4, adv_grid = 1; size_t adv_shmem = 0;
+  int adv_thread = -1;       // >= 0: the advance phase runs one thread per env (b2m_k_advance_thread(adv_thread)); -1: warp per env
   std::vector<ClassPlan> classes;
   ClassPlan straggler;       // full-size block-per-env kernel for envs over their pivot budget
   ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
@@ -223,6 +224,14 @@ b200moby_status plan_launch(b200moby_sim* h) {
     if (per > B2M_SMEM_MAX) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "advance working set (%zu bytes) exceeds one SM's shared memory", per);
     h->adv_wpb = wpb; h->adv_shmem = per * wpb;
     if ((st = plan_grid(b2m_k_advance(), wpb * 32, h->adv_shmem, sms, (ne + wpb - 1) / wpb, &h->adv_grid)) != B200MOBY_OK) return st;
+    // thread per env when the small working set fits one of the compiled local-memory sizes (B200MOBY_ADV_THREAD=0: off)
+    h->adv_thread = -1;
+    if (env_int("B200MOBY_ADV_THREAD", 1) != 0) {
+      const size_t nd = env_small_doubles(D0), ni = env_small_ints(D0);
+      if (nd <= 256 && ni <= 64) h->adv_thread = 0;
+      else if (nd <= 1024 && ni <= 256) h->adv_thread = 1;
+      else if (nd <= 4096 && ni <= 1024) h->adv_thread = 2;
+    }
   }
   // impact classes by LCP dimension
   {
@@ -281,7 +290,10 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
   for (int r = 0; r < h->rounds; r++) {
     { SimParams Pa = P; Pa.kslot = 0;
       void* a[] = {&Pa, &dt, &r, &h->adv_wpb};
-      if ((st = timed_launch(h, 0, b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)) != B200MOBY_OK) return st; }
+      if (h->adv_thread >= 0) {
+        const int blocks = std::max(1, std::min((h->n_envs + 127) / 128, h->sms * 16));
+        if ((st = timed_launch(h, 0, b2m_k_advance_thread(h->adv_thread), dim3(blocks), dim3(128), a, 0, s)) != B200MOBY_OK) return st;
+      } else if ((st = timed_launch(h, 0, b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)) != B200MOBY_OK) return st; }
     const bool conc = h->concurrent && h->classes.size() > 1;
     if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
     for (size_t c = 0; c < h->classes.size(); c++) {

@@ -4,6 +4,7 @@
 const void* b2m_k_step_warp();            // (SimParams P, double dt, int n_steps, size_t env_d)
 const void* b2m_k_finish();               // (SimParams P, double dt, int round)
 const void* b2m_k_advance();              // (SimParams P, double dt, int round, int wpb)
+const void* b2m_k_advance_thread(int cls); // (SimParams P, double dt, int round): thread per env; cls 0/1/2 = local working set of 256/1024/4096 doubles
 const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb)
 const void* b2m_k_impact_block64();
 const void* b2m_k_impact_block128();
