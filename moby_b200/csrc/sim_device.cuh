@@ -22,7 +22,8 @@ enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LE
 // queue slots of one round: [0, n_classes) impact classes, then the envs that still have time left in their step, then stragglers
 #define B2M_SLOT_CONT B2M_MAX_CLASSES
 #define B2M_SLOT_STRAGGLER (B2M_MAX_CLASSES + 1)
-#define B2M_SLOTS (B2M_MAX_CLASSES + 2)
+#define B2M_SLOT_HARD (B2M_MAX_CLASSES + 2)   /* envs whose previous impact was expensive: solved first, on their own stream */
+#define B2M_SLOTS (B2M_MAX_CLASSES + 3)
 #define B2M_ROUNDS_MAX 8
 #define B2M_MAX_STALL 64
 // B2M_LEAN builds drop the articulated-body and box-box code paths (scenes of free spheres / boxes on planes): the
@@ -63,6 +64,11 @@ struct SimParams {
   double* q; double* v; double* time; double* zlast; int* zlast_n;
   double* vlast; int* vlast_n;     // [cmax][env], [env]: solution / warm start of the no-slip LCP (ImpactConstraintHandler::_v)
   unsigned long long* counters;
+  // Longest-job-first: cost[env] = pivots of the env's last impact phase (1 << 30 when it ran over its budget).  An env
+  // at or above hard_cost is queued in B2M_SLOT_HARD instead of its class, and that queue is launched first, so the few
+  // envs that set the step time (degenerate contact sets: four failed lcp_fast runs, then the Lemke ladder) run
+  // alongside the bulk instead of after it.  The same envs are hard step after step (resting contact persists).
+  int* cost; int hard_cost;
   int pivot_budget;            // > 0: per-env pivot budget of the warp-per-env impact kernels; over-budget envs are re-run by the straggler kernel
   // phased step (advance -> impact per LCP class -> advance ...): per-env progress and work queues
   double* hacc;                // [env] seconds of the current step already simulated
@@ -169,7 +175,7 @@ B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, const EnvDims& D) {
 }
 
 // scal[] slots
-enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10, S_VLN = 11, S_VLDIRTY = 12 };
+enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10, S_VLN = 11, S_VLDIRTY = 12, S_FAILED = 13 };
 
 // Per-env solver budget: when `limit` is set and an env's pivots in this launch exceed it, the env's step is
 // abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
@@ -711,6 +717,47 @@ B2M_HD B2M_INL double Dn(const EnvMem& m, int nc, int d1, int d2, int i, int j) 
   return (d1 <= d2) ? m.D[(size_t)dblk(d1, d2) * nc * nc + (size_t)i * nc + j] : m.D[(size_t)dblk(d2, d1) * nc * nc + (size_t)j * nc + i];
 }
 
+// Lower Cholesky in place by the whole group (LinAlgd::factor_chol; column-major, ld n); every element is produced by the
+// same operation sequence as the checker's factor_chol, so the accept / reject decisions below are identical.
+template <class G>
+B2M_DEV B2M_NOINL bool chol_factor_group(const G& g, double* A, int n) {
+  for (int j = 0; j < n; j++) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d = fma(-A[(size_t)k * n + j], A[(size_t)k * n + j], d);
+    g.sync();
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    if (g.tid == 0) A[(size_t)j * n + j] = d;
+    for (int i = j + 1 + g.tid; i < n; i += G::size) {
+      double s = A[(size_t)j * n + i];
+      for (int k = 0; k < j; k++) s = fma(-A[(size_t)k * n + i], A[(size_t)k * n + j], s);
+      A[(size_t)j * n + i] = s / d;
+    }
+    g.sync();
+  }
+  return true;
+}
+// solve_chol_fast for one right-hand side, one thread
+B2M_HD B2M_INL void chol_solve1(const double* L, int n, double* b) {
+  for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s = fma(-L[(size_t)k * n + i], b[k], s); b[i] = s / L[(size_t)i * n + i]; }
+  for (int i = n - 1; i >= 0; i--) { double s = b[i]; for (int k = i + 1; k < n; k++) s = fma(-L[(size_t)i * n + k], b[k], s); b[i] = s / L[(size_t)i * n + i]; }
+}
+// inverse_spd_n by the whole group: the factorisation row-parallel, then one column of the inverse per thread; every
+// element goes through the same operation sequence as in inverse_spd_n, so the result is bit-identical.  n <= B2M_MAX_LINKS.
+template <class G>
+B2M_DEV B2M_NOINL void inverse_spd_group(const G& g, double* A, int n, int lda, double* L) {
+  for (int t = g.tid; t < n * n; t += G::size) { const int j = t / n, i = t - j * n; L[t] = A[(size_t)j * lda + i]; }
+  g.sync();
+  chol_factor_group(g, L, n);
+  for (int j = g.tid; j < n; j += G::size) {
+    double e[B2M_MAX_LINKS];
+    for (int i = 0; i < n; i++) e[i] = (i == j) ? 1.0 : 0.0;
+    chol_solve1(L, n, e);
+    for (int i = 0; i < n; i++) A[(size_t)j * lda + i] = e[i];
+  }
+  g.sync();
+}
+
 // n x n SPD inverse through Cholesky (LinAlgd::inverse_SPD, ImpactConstraintHandler.cpp:1605-1607): A (column-major,
 // leading dimension lda) is replaced by its inverse; L: n*n + n doubles of scratch.  One thread; same operation order as
 // the checker.
@@ -746,12 +793,15 @@ B2M_DEV B2M_NOINL void compute_problem_data_dense(const G& g, const SimParams& P
   const int rep = P.rc_first + 1;
   for (int t = g.tid; t < ngc * ngc; t += G::size) m.Xb[t] = 0.0;
   g.sync();
-  if (g.tid == 0 && m.gcoff[rep] >= 0) {                 // joint-space inertia by CRB, then inverse_SPD
+  if (m.gcoff[rep] >= 0) {                               // joint-space inertia by CRB, then inverse_SPD
     const RCTree& T = *P.rc;
-    RCState s; s.x = m.bx + 3 * P.rc_first; s.R = m.bR + 9 * P.rc_first; s.S = m.rS; s.v = m.rV;
     double* H = m.Xb + (size_t)m.gcoff[rep] * ngc + m.gcoff[rep];
-    rc_crb(T, s, m.bmass + P.rc_first, m.bJ + 3 * P.rc_first, H, ngc);
-    inverse_spd_n(H, T.n_links - 1, ngc, m.Lf);
+    if (g.tid == 0) {
+      RCState s; s.x = m.bx + 3 * P.rc_first; s.R = m.bR + 9 * P.rc_first; s.S = m.rS; s.v = m.rV;
+      rc_crb(T, s, m.bmass + P.rc_first, m.bJ + 3 * P.rc_first, H, ngc);
+    }
+    g.sync();
+    inverse_spd_group(g, H, T.n_links - 1, ngc, m.Lf);
   }
   for (int b = g.tid; b < nb; b += G::size) {            // free bodies: 6x6 blocks as in the block layout
     if (m.gcoff[b] < 0 || is_link(P, b)) continue;
@@ -1129,7 +1179,7 @@ B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m
     { B2M_PROF_T0(m); st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud); B2M_PROF_ADD(m, g, PH_LEMKE); }   // :222-225
     if (st == LCP_DEFER) return false;
     lemke_calls = stats[0]; pivots += stats[1]; executed += stats[2];
-    if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
+    if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) { lc[CNT_LCP_FAIL]++; m.scal[S_FAILED] = 1; } }
   }
   g.sync();
   if (g.tid == 0) {
@@ -1193,7 +1243,7 @@ B2M_DEV B2M_NOINL bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m
   int piv = 0;
   int st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, -2, m.z, m.work, m.iwork, &piv, stats, cx.limit ? &cx.budget : nullptr);   // :333
   if (st == LCP_DEFER) return false;
-  if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) lc[CNT_LCP_FAIL]++; }
+  if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) { lc[CNT_LCP_FAIL]++; m.scal[S_FAILED] = 1; } }
   g.sync();
   if (g.tid == 0) {
     lc[CNT_LCP_SOLVES]++; lc[CNT_LEMKE_CALLS] += stats[0]; lc[CNT_PIVOTS] += stats[1];
@@ -1243,31 +1293,6 @@ B2M_DEV bool apply_ap_model(const G& g, const SimParams& P, int e, EnvMem& m, un
   return true;
 }
 
-// Lower Cholesky in place by the whole group (LinAlgd::factor_chol; column-major, ld n); every element is produced by the
-// same operation sequence as the checker's factor_chol, so the accept / reject decisions below are identical.
-template <class G>
-B2M_DEV B2M_NOINL bool chol_factor_group(const G& g, double* A, int n) {
-  for (int j = 0; j < n; j++) {
-    double d = A[(size_t)j * n + j];
-    for (int k = 0; k < j; k++) d = fma(-A[(size_t)k * n + j], A[(size_t)k * n + j], d);
-    g.sync();
-    if (!(d > 0.0)) return false;
-    d = sqrt(d);
-    if (g.tid == 0) A[(size_t)j * n + j] = d;
-    for (int i = j + 1 + g.tid; i < n; i += G::size) {
-      double s = A[(size_t)j * n + i];
-      for (int k = 0; k < j; k++) s = fma(-A[(size_t)k * n + i], A[(size_t)k * n + j], s);
-      A[(size_t)j * n + i] = s / d;
-    }
-    g.sync();
-  }
-  return true;
-}
-// solve_chol_fast for one right-hand side, one thread
-B2M_HD B2M_INL void chol_solve1(const double* L, int n, double* b) {
-  for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s = fma(-L[(size_t)k * n + i], b[k], s); b[i] = s / L[(size_t)i * n + i]; }
-  for (int i = n - 1; i >= 0; i--) { double s = b[i]; for (int k = i + 1; k < n; k++) s = fma(-L[(size_t)i * n + k], b[k], s); b[i] = s / L[(size_t)i * n + i]; }
-}
 // the "check" matrix [[S X S^T, S X T^T], [T X S^T, T X T^T]] over the chosen tangent indices (:1098-1112)
 template <class G>
 B2M_DEV void noslip_form_Y(const G& g, const EnvMem& m, int nc, const int* Si, int ns, const int* Ti, int nt, double skew, double* Y) {
@@ -1358,7 +1383,7 @@ B2M_DEV B2M_NOINL void apply_no_slip_model(const G& g, const SimParams& P, int e
   g.sync();
   if (!solved) { for (int i = g.tid; i < nc; i += G::size) m.z[i] = 0.0; g.sync(); }
   if (g.tid == 0) {
-    if (!solved) lc[CNT_LCP_FAIL]++;
+    if (!solved) { lc[CNT_LCP_FAIL]++; m.scal[S_FAILED] = 1; }
     lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
     lc[CNT_PIVOT_FLOPS] += (unsigned long long)executed * 2ull * nc * (nc + 1);
     if ((unsigned long long)nc > lc[CNT_MAX_N]) lc[CNT_MAX_N] = nc;
@@ -1546,6 +1571,7 @@ B2M_HD B2M_INL int contacts_lcp_dim(const EnvMem& m, int ncon, int model) {
 template <class G>
 B2M_DEV double do_mini_step(const G& g, const SimParams& P, int e, EnvMem& m, double dt, double t, unsigned long long* lc, EnvCtx& cx) {
   bool impacting;
+  if (g.tid == 0) m.scal[S_FAILED] = 0;
   const double h = mini_step_advance(g, P, e, m, dt, t, lc, impacting);
   if (impacting && !process_constraints(g, P, e, m, lc, cx)) return -1.0;
   mini_step_account(g, P, m, lc);
@@ -1565,6 +1591,10 @@ B2M_DEV bool env_finish_step(const G& g, const SimParams& P, int e, EnvMem& m, d
     // B2M_MAX_STALL zero-length mini-steps in a row the env gives up the rest of this step and is counted as failed.
     stalled = (hh > 0.0) ? 0 : stalled + 1;
     if (stalled >= B2M_MAX_STALL) { if (g.tid == 0) lc[CNT_LCP_FAIL]++; break; }
+    // An unsolved LCP in a zero-length mini-step is where the reference leaves through LCPSolverException: the env gives
+    // up the rest of this step at once (the failure is already counted) instead of repeating the same solve.
+    g.sync();
+    if (hh == 0.0 && m.scal[S_FAILED]) break;
   }
   if (g.tid == 0) lc[CNT_ENV_STEPS]++;
   return true;
@@ -1620,6 +1650,7 @@ B2M_DEV void env_advance(const G& g, const SimParams& P, int e, EnvMem& m, doubl
         const int n = contacts_lcp_dim(m, ncon, P.model);
         int cls = 0;
         while (cls < P.n_classes - 1 && (n > P.class_nmax[cls] || ncon > P.class_cmax[cls])) cls++;
+        if (P.cost && P.hard_cost > 0 && P.cost[e] >= P.hard_cost) cls = B2M_SLOT_HARD;
         q_push(P, round, cls, e);
       }
       parked = true;
@@ -1647,13 +1678,14 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   m.prof = P.tap_prof ? P.tap_prof + (size_t)4 * P.n_envs + e : nullptr; m.prof_stride = P.n_envs;
   { B2M_PROF_T0(m); env_load(g, P, e, m); B2M_PROF_ADD(m, g, PH_LOAD); }
   const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
+  if (g.tid == 0) m.scal[S_FAILED] = 0;
   { B2M_PROF_T0(m);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
   B2M_PROF_ADD(m, g, PH_CONTACTS); }
   lc[CNT_CONTACTS] = c0; lc[CNT_OVERFLOW] = o0;                  // counted by the advance phase
   if (!process_constraints(g, P, e, m, lc, cx)) {
-    if (g.tid == 0) q_push(P, round, B2M_SLOT_STRAGGLER, e);
+    if (g.tid == 0) { q_push(P, round, B2M_SLOT_STRAGGLER, e); if (P.cost) P.cost[e] = 1 << 30; }
     g.sync();
     return false;
   }
@@ -1664,8 +1696,9 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
     const double hh = P.hpend[e];
     const double h = P.hacc[e] + hh;
     P.time[e] = P.time[e] + hh;
-    if (h < dt) { P.hacc[e] = h; q_push(P, round, B2M_SLOT_CONT, e); }
-    else lc[CNT_ENV_STEPS]++;
+    if (h < dt && !(hh == 0.0 && m.scal[S_FAILED])) { P.hacc[e] = h; q_push(P, round, B2M_SLOT_CONT, e); }
+    else lc[CNT_ENV_STEPS]++;        // done, or given up after an unsolved LCP in a zero-length mini-step
+    if (P.cost) { const unsigned long long dp = lc[CNT_PIVOTS] - p0; P.cost[e] = dp > (1ull << 30) ? (1 << 30) : (int)dp; }
 #ifdef __CUDA_ARCH__
     if (P.tap_prof) {
       const size_t ne = P.n_envs;

@@ -38,7 +38,7 @@ struct b200moby_sim {
   int adv_wpb = 4, adv_grid = 1; size_t adv_shmem = 0;
   int adv_thread = -1;       // >= 0: the advance phase runs one thread per env (b2m_k_advance_thread(adv_thread)); -1: warp per env
   std::vector<ClassPlan> classes;
-  ClassPlan straggler;       // full-size block-per-env kernel for envs over their pivot budget
+  ClassPlan straggler;       // full-size kernel (warp per env while the scene's LCPs fit one, else a 256-thread block) for envs over their pivot budget and for the hard queue
   ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
   int fin_grid = 1;
   ClassPlan finblock;        // nmax > B200MOBY_BIG_N: the finish phase runs one 256-thread block per env (threads == 256 when in use)
@@ -50,6 +50,7 @@ struct b200moby_sim {
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> side_done;
   cudaEvent_t fork = nullptr;
+  cudaStream_t hard_stream = nullptr; cudaEvent_t hard_done = nullptr;   // the hard queue's launch
   int rc_links = 0, rc_dof = 0;   // articulated body (0: none)
   // per-kernel profile (b200moby_get_kernel_profile): slot 0 advance, 1..n impact classes, n+1 stragglers, n+2 finish
   bool ktiming = false;
@@ -177,7 +178,14 @@ b200moby_status plan_memory(b200moby_sim* h, const void* kernel, ClassPlan& cp, 
   const size_t per = ed * sizeof(double) + ei * sizeof(int);
   b200moby_status st;
   if (per <= B2M_SMEM_MAX) {
-    cp.wpb = (cp.threads == 32) ? (int)std::max<size_t>(1, std::min<size_t>(slots_max, B2M_SMEM_MAX / per)) : 1;
+    cp.wpb = 1;
+    if (cp.threads == 32) {   // warps per block that put the most envs on an SM (228 KB per SM, 1 KB reserved per block); ties: the wider block
+      size_t best = 0;
+      for (int w = 1; w <= slots_max && per * w <= B2M_SMEM_MAX; w++) {
+        const size_t blocks = std::min<size_t>(32, (size_t)(228 * 1024) / (per * w + 1024));
+        if (blocks * w >= best) { best = blocks * w; cp.wpb = w; }
+      }
+    }
     cp.shmem = per * cp.wpb;
     return plan_grid(kernel, cp.threads == 32 ? cp.wpb * 32 : cp.threads, cp.shmem, h->sms, (work + cp.wpb - 1) / cp.wpb, &cp.grid);
   }
@@ -235,7 +243,7 @@ b200moby_status plan_launch(b200moby_sim* h) {
   }
   // impact classes by LCP dimension
   {
-    const int warp_nmax = env_int("B200MOBY_WARP_NMAX", 24); // classes up to this n: warp per env; above: block per env
+    const int warp_nmax = env_int("B200MOBY_WARP_NMAX", 40); // classes up to this n: warp per env; above: block per env
     const int bthreads = env_int("B200MOBY_IMPACT_THREADS", 64);
     const int big_n = env_int("B200MOBY_BIG_N", 96);          // classes above this n always get 256 threads per env
     const int ncls = b2m_class_table(h->nmax, h->cmax, h->P.model, B2M_MAX_CLASSES, h->P.class_nmax, h->P.class_cmax);
@@ -251,8 +259,8 @@ b200moby_status plan_launch(b200moby_sim* h) {
     }
     h->P.n_classes = (int)h->classes.size();
     ClassPlan& sg = h->straggler;
-    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = 256;
-    if ((st = plan_memory(h, impact_block_ptr(256), sg, 1, ne)) != B200MOBY_OK) return st;
+    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = (h->nmax <= warp_nmax || bthreads <= 32) ? 32 : 256;   // a lone warp has the shortest pivot latency when the LCP fits it
+    if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(256), sg, 4, ne)) != B200MOBY_OK) return st;
     // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished
     // by one block per env, and more rounds keep that remainder small (each extra round is a handful of short launches).
     h->finblock.threads = 32;
@@ -296,6 +304,17 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       } else if ((st = timed_launch(h, 0, b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)) != B200MOBY_OK) return st; }
     const bool conc = h->concurrent && h->classes.size() > 1;
     if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
+    if (P.hard_cost > 0) {   // the expensive envs first, next to the classes
+      ClassPlan& cp = h->straggler;
+      int slot = B2M_SLOT_HARD;
+      SimParams Ph = P; Ph.gscratch = cp.gscratch; Ph.gstride = cp.gstride; Ph.kslot = 3 + ncls; Ph.pivot_budget = 0;
+      cudaStream_t sc = conc ? h->hard_stream : s;
+      if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
+      if (cp.threads == 32) { void* a[] = {&Ph, &dt, &r, &slot, &cp.wpb}; st = timed_launch(h, 3 + ncls, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc); }
+      else { void* a[] = {&Ph, &dt, &r, &slot}; st = timed_launch(h, 3 + ncls, impact_block_ptr(256), dim3(cp.grid), dim3(256), a, cp.shmem, sc); }
+      if (st != B200MOBY_OK) return st;
+      if (conc) { B2M_CUDA(cudaEventRecord(h->hard_done, sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->hard_done, 0)); }
+    }
     for (size_t c = 0; c < h->classes.size(); c++) {
       ClassPlan& cp = h->classes[c];
       SimParams Pc = P; Pc.cmax = cp.cmax; Pc.nmax = cp.nmax; Pc.gscratch = cp.gscratch; Pc.gstride = cp.gstride; Pc.kslot = 1 + (int)c;
@@ -315,9 +334,11 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
     }
     if (P.pivot_budget > 0) {
       int slot = B2M_SLOT_STRAGGLER;
-      SimParams Ps = P; Ps.gscratch = h->straggler.gscratch; Ps.gstride = h->straggler.gstride; Ps.kslot = 1 + ncls;
-      void* a[] = {&Ps, &dt, &r, &slot};
-      if ((st = timed_launch(h, 1 + ncls, impact_block_ptr(256), dim3(h->straggler.grid), dim3(256), a, h->straggler.shmem, s)) != B200MOBY_OK) return st;
+      ClassPlan& cp = h->straggler;
+      SimParams Ps = P; Ps.gscratch = cp.gscratch; Ps.gstride = cp.gstride; Ps.kslot = 1 + ncls; Ps.pivot_budget = 0;
+      if (cp.threads == 32) { void* a[] = {&Ps, &dt, &r, &slot, &cp.wpb}; st = timed_launch(h, 1 + ncls, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, s); }
+      else { void* a[] = {&Ps, &dt, &r, &slot}; st = timed_launch(h, 1 + ncls, impact_block_ptr(256), dim3(cp.grid), dim3(256), a, cp.shmem, s); }
+      if (st != B200MOBY_OK) return st;
     }
   }
   { int r = h->rounds - 1; SimParams Pf = P; Pf.kslot = 2 + ncls;
@@ -374,7 +395,9 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)h->cmax * ne, &P.vlast));
   TRY(dev_zero(h, (size_t)ne, &P.vlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
-  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 4), &P.kstat));
+  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 5), &P.kstat));
+  TRY(dev_zero(h, (size_t)ne, &P.cost));
+  P.hard_cost = env_int("B200MOBY_HARD_COST", 64);
   TRY(dev_zero(h, (size_t)ne, &P.hacc));
   TRY(dev_zero(h, (size_t)ne, &P.hpend));
   TRY(dev_zero(h, (size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne, &P.queue));
@@ -408,6 +431,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
         b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the impact-class streams");
       }
     }
+    if (cudaStreamCreateWithFlags(&h->hard_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->hard_done, cudaEventDisableTiming) != cudaSuccess) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the hard-queue stream"); }
     if (cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the fork event"); }
   }
 #undef TRY
@@ -421,6 +445,8 @@ b200moby_status b200moby_destroy(b200moby_handle h) {
   for (cudaStream_t st : h->side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (cudaEvent_t ev : h->side_done) if (ev) cudaEventDestroy(ev);
   if (h->fork) cudaEventDestroy(h->fork);
+  if (h->hard_stream) { cudaStreamSynchronize(h->hard_stream); cudaStreamDestroy(h->hard_stream); }
+  if (h->hard_done) cudaEventDestroy(h->hard_done);
   for (auto& pe : h->kev_pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto& pe : h->kev_free) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (void* p : h->allocs) cudaFree(p);
@@ -602,7 +628,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
   B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaDeviceSynchronize());
-  const int ncls = (int)h->classes.size(), nk = ncls + 3;
+  const int ncls = (int)h->classes.size(), nk = ncls + 4;
   h->kms.resize(nk, 0.0); h->klaunches.resize(nk, 0);
   for (auto& pe : h->kev_pending) {
     float ms = 0.f;
@@ -612,15 +638,15 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   h->kev_pending.clear();
   if (out) {
     memset(out, 0, sizeof(*out));
-    unsigned long long ks[3 * (B2M_MAX_CLASSES + 4)];
+    unsigned long long ks[3 * (B2M_MAX_CLASSES + 5)];
     B2M_CUDA(cudaMemcpy(ks, h->P.kstat, sizeof(ks), cudaMemcpyDeviceToHost));
     out->n_kernels = nk;
     for (int k = 0; k < nk && k < B200MOBY_MAX_KERNELS; k++) {
       b200moby_kernel_stat& o = out->k[k];
       if (k == 0) snprintf(o.name, sizeof(o.name), "advance_kernel");
       else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
-      else if (k == ncls + 1) { snprintf(o.name, sizeof(o.name), "impact_block_kernel<256>[stragglers]"); o.lcp_nmax = h->nmax; o.threads_per_env = 256; }
-      else snprintf(o.name, sizeof(o.name), "finish_kernel");
+      else if (k == ncls + 1 || k == ncls + 3) { snprintf(o.name, sizeof(o.name), h->straggler.threads == 32 ? "impact_warp_kernel[%s]" : "impact_block_kernel<256>[%s]", k == ncls + 1 ? "stragglers" : "hard queue"); o.lcp_nmax = h->nmax; o.threads_per_env = h->straggler.threads; }
+      else snprintf(o.name, sizeof(o.name), h->finblock.threads == 256 ? "finish_block_kernel<256>" : "finish_kernel");
       if (k == 0 || k == ncls + 2) o.threads_per_env = 32;
       o.ms = h->kms[k]; o.launches = h->klaunches[k];
       o.envs = (long long)ks[3 * k]; o.flops = (long long)ks[3 * k + 1]; o.lcp_solves = (long long)ks[3 * k + 2];
@@ -628,7 +654,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   }
   if (reset) {
     std::fill(h->kms.begin(), h->kms.end(), 0.0); std::fill(h->klaunches.begin(), h->klaunches.end(), 0);
-    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 4)));
+    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 5)));
   }
   h->ktiming = enable != 0;
   return B200MOBY_OK;

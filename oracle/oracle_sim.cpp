@@ -465,6 +465,7 @@ void Sim::calc_fwd_dyn_and_integrate_velocity(double h) {
 
 // TimeSteppingSimulator::do_mini_step (TimeSteppingSimulator.cpp:114-222)
 double Sim::do_mini_step(double dt) {
+  mini_failed = false;
   const size_t nb = bodies.size();
   std::vector<V3> xsave(nb);
   std::vector<double> qsave(nb * 4);
@@ -528,6 +529,7 @@ double Sim::step(double dt) {
     // contract gives up the rest of the step after 64 zero-length mini-steps in a row and counts a failure
     stalled = (hh > 0.0) ? 0 : stalled + 1;
     if (stalled >= 64) { cnt.lcp_failures++; break; }
+    if (hh == 0.0 && mini_failed) break;   // LCPSolverException in the reference (ImpactConstraintHandlerQP.cpp:224): the env gives up this step
   }
   cnt.env_steps++;
   return dt;
@@ -909,7 +911,7 @@ static void solve_qp(Sim& S, ProblemData& q) {
   if (!S.lcp.lcp_fast_regularized(n, MM.data(), qq.data(), z, -20, 4, -8)) {   // :219
     z.assign(n, 0.0);                                                   // :222
     if (!S.lcp.lcp_lemke_regularized(n, MM.data(), qq.data(), z)) {     // :224
-      S.cnt.lcp_failures++;                                             // LCPSolverException: impulses are not applied
+      S.cnt.lcp_failures++; S.mini_failed = true;                       // LCPSolverException: impulses are not applied
       z.assign(n, 0.0);
     }
   }
@@ -957,7 +959,7 @@ static void solve_ap(Sim& S, ProblemData& q, Vec& acc_cn, Vec& acc_cs, Vec& acc_
   S.cnt.max_lcp_n = std::max<long long>(S.cnt.max_lcp_n, n);
   const unsigned long long l0 = S.lcp.n_lemke_calls, p0 = S.lcp.n_pivots_total;
   if (!S.lcp.lcp_lemke_regularized(n, MM.data(), qq.data(), z, -20, 1, -2)) {   // :333
-    S.cnt.lcp_failures++;
+    S.cnt.lcp_failures++; S.mini_failed = true;
     z.assign(n, 0.0);
   }
   S.cnt.lemke_calls += S.lcp.n_lemke_calls - l0; S.cnt.pivots += S.lcp.n_pivots_total - p0;
@@ -1057,7 +1059,7 @@ static void apply_no_slip_model(Sim& S, ProblemData& q) {
   Vec v = S.vlast;                                                       // the member _v: warm start iff sizes match
   bool solved = ok && S.lcp.lcp_fast(nc, MM.data(), qq.data(), v);       // :1239
   if (ok && !solved) { v.clear(); solved = S.lcp.lcp_lemke_regularized(nc, MM.data(), qq.data(), v); }   // :1279
-  if (!solved) { S.cnt.lcp_failures++; v.assign(nc, 0.0); }             // std::runtime_error in the reference (:1280)
+  if (!solved) { S.cnt.lcp_failures++; S.mini_failed = true; v.assign(nc, 0.0); }             // std::runtime_error in the reference (:1280)
   S.cnt.lcp_fast_calls += S.lcp.n_fast_calls - f0; S.cnt.lemke_calls += S.lcp.n_lemke_calls - l0; S.cnt.pivots += S.lcp.n_pivots_total - p0;
   S.cnt.pivot_flops += (long long)(S.lcp.n_pivots_total - p0) * 2 * nc * (nc + 1);
   S.vlast = v;

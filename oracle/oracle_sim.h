@@ -85,6 +85,7 @@ struct Sim {
   Vec zlast;                            // ImpactConstraintHandler::_zlast
   Vec vlast;                            // ImpactConstraintHandler::_v, the no-slip LCP's solution / warm start (:1239)
   Counters cnt;
+  bool mini_failed = false;             // an LCP of the current mini-step stayed unsolved (LCPSolverException in the reference)
   // taps for parity tests: LCP of the most recent impact solve
   int last_n = 0;
   Vec last_MM, last_qq, last_z;

@@ -77,6 +77,8 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
   std::vector<int> queue((size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne), qctl(2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1));
   P.hacc = hacc.data(); P.hpend = hpend.data(); P.queue = queue.data(); P.qctl = qctl.data();
   P.pivot_budget = pivot_budget;
+  std::vector<int> cost(ne, 0);                 // longest-job-first queue, with a low threshold so the tests exercise it
+  P.cost = cost.data(); P.hard_cost = 8;
   P.n_classes = b2m_class_table(nmax, cmax, P.model, B2M_MAX_CLASSES, P.class_nmax, P.class_cmax);
   const EnvDims D = env_dims(P);
   std::vector<double> wd(env_doubles(D));
@@ -92,6 +94,16 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
         const int count = (r == 0) ? ne : *q_count(P, r - 1, B2M_SLOT_CONT);
         const int* list = (r == 0) ? nullptr : q_list(P, r - 1, B2M_SLOT_CONT);
         for (int i = 0; i < count; i++) { unsigned long long lc[CNT_COUNT] = {0}; env_advance(g, P, list ? list[i] : i, m, dt, r, lc); add(lc); }
+      }
+      {   // hard queue first, full working set, no budget
+        EnvMem m; env_carve(m, wd.data(), wi.data(), D);
+        const int count = *q_count(P, r, B2M_SLOT_HARD);
+        const int* list = q_list(P, r, B2M_SLOT_HARD);
+        for (int i = 0; i < count; i++) {
+          unsigned long long lc[CNT_COUNT] = {0};
+          EnvCtx cx; cx.limit = false; cx.budget = 0;
+          env_impact(g, P, list[i], m, dt, r, lc, cx); add(lc);
+        }
       }
       for (int c = 0; c < P.n_classes; c++) {   // impact, per class, with the class's working-set size
         SimParams Pc = P; Pc.cmax = P.class_cmax[c]; Pc.nmax = P.class_nmax[c];
