@@ -13,13 +13,12 @@ __global__ void __launch_bounds__(NT) impact_block_kernel(SimParams P, double dt
   BlockGroup<NT> g(red);
   unsigned long long lc[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
-  const int count = *q_count(P, round, slot);
-  const int* list = q_list(P, round, slot);
+  const int count = q_size(P, round, slot);
   int* head = q_head(P, round, slot);
   unsigned long long envs = 0;
   for (int i = pull_block(head, &next); i < count; i = pull_block(head, &next)) {
     EnvCtx cx; cx.limit = false; cx.budget = 0;
-    env_impact(g, P, list[i], m, dt, round, lc, cx);
+    env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx);
     envs++;
   }
   if (g.tid == 0) commit_counters(P, lc, envs);

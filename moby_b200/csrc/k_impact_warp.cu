@@ -12,13 +12,12 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
   unsigned long long lc[CNT_COUNT], tot[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) tot[k] = 0;
   unsigned long long envs = 0;
-  const int count = *q_count(P, round, slot);
-  const int* list = q_list(P, round, slot);
+  const int count = q_size(P, round, slot);
   int* head = q_head(P, round, slot);
   for (int i = pull_warp(head); i < count; i = pull_warp(head)) {
     for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
     EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
-    if (env_impact(g, P, list[i], m, dt, round, lc, cx)) add_counters(tot, lc);
+    if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) add_counters(tot, lc);
     envs++;
   }
   if (g.tid == 0) commit_counters(P, tot, envs);

@@ -134,20 +134,21 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
       }
       executed++;
       // ratio test (:886-975)
-      double theta = B2M_INF; bool anycand = false;
-      for (int i = g.tid; i < n; i += G::size) { const double d = dvec[i]; if (d > PIV_TOL) { anycand = true; theta = fmin(theta, (xcol[i] + zero_tol) / d); } }
-      if (!g.any(anycand)) { status = LCP_RAY; break; }
+      // two group reductions per pivot: a finite ratio exists iff some d_i > PIV_TOL, and the artificial variable's row
+      // enters the second one as key -1 so that it wins whenever it passes (LCP.cpp:961-975)
+      double theta = B2M_INF;
+      for (int i = g.tid; i < n; i += G::size) { const double d = dvec[i]; if (d > PIV_TOL) theta = fmin(theta, (xcol[i] + zero_tol) / d); }
       theta = g.min(theta);
+      if (theta == B2M_INF) { status = LCP_RAY; break; }
       int lo = 0x7fffffff;
       const int trow = -(where[t] + 1);
-      bool tpass = false;
       for (int i = g.tid; i < n; i += G::size) {
         const double d = dvec[i];
-        if (d > PIV_TOL && xcol[i] / d <= theta) { if (i < lo) lo = i; if (i == trow) tpass = true; }
+        if (d > PIV_TOL && xcol[i] / d <= theta) { const int key = (i == trow) ? -1 : i; if (key < lo) lo = key; }
       }
       lo = g.min(lo);
       if (lo == 0x7fffffff) { status = LCP_EMPTY_RATIO; break; }
-      r = g.any(tpass) ? trow : lo;
+      r = (lo < 0) ? trow : lo;
     }
     const int leaving = bas[r];
     const double p = dvec[r];

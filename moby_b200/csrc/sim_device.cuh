@@ -23,7 +23,8 @@ enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LE
 #define B2M_SLOT_CONT B2M_MAX_CLASSES
 #define B2M_SLOT_STRAGGLER (B2M_MAX_CLASSES + 1)
 #define B2M_SLOT_HARD (B2M_MAX_CLASSES + 2)   /* envs whose previous impact was expensive: solved first, on their own stream */
-#define B2M_SLOTS (B2M_MAX_CLASSES + 3)
+#define B2M_SLOT_HARD_BACK (B2M_MAX_CLASSES + 3)   /* counter only: the hard queue is filled from both ends, costliest envs at the front */
+#define B2M_SLOTS (B2M_MAX_CLASSES + 4)
 #define B2M_ROUNDS_MAX 8
 #define B2M_MAX_STALL 64
 // B2M_LEAN builds drop the articulated-body and box-box code paths (scenes of free spheres / boxes on planes): the
@@ -64,7 +65,7 @@ struct SimParams {
   double* q; double* v; double* time; double* zlast; int* zlast_n;
   double* vlast; int* vlast_n;     // [cmax][env], [env]: solution / warm start of the no-slip LCP (ImpactConstraintHandler::_v)
   unsigned long long* counters;
-  // Longest-job-first: cost[env] = pivots of the env's last impact phase (1 << 30 when it ran over its budget).  An env
+  // Longest-job-first: cost[env] = solver iterations executed in the env's last impact phase, decaying by a quarter per impact (at least 4 hard_cost after it ran over a budget).  An env
   // at or above hard_cost is queued in B2M_SLOT_HARD instead of its class, and that queue is launched first, so the few
   // envs that set the step time (degenerate contact sets: four failed lcp_fast runs, then the Lemke ladder) run
   // alongside the bulk instead of after it.  The same envs are hard step after step (resting contact persists).
@@ -175,7 +176,7 @@ B2M_HD inline void env_carve(EnvMem& m, double* d, int* i, const EnvDims& D) {
 }
 
 // scal[] slots
-enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10, S_VLN = 11, S_VLDIRTY = 12, S_FAILED = 13 };
+enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLAG = 6, S_TMP = 7, S_ZLN = 8, S_ZLDIRTY = 9, S_NTOT = 10, S_VLN = 11, S_VLDIRTY = 12, S_FAILED = 13, S_EXEC = 14 };
 
 // Per-env solver budget: when `limit` is set and an env's pivots in this launch exceed it, the env's step is
 // abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
@@ -1185,6 +1186,7 @@ B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m
   if (g.tid == 0) {
     lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
     lc[CNT_PIVOT_FLOPS] += (unsigned long long)executed * 2ull * n * (n + 1);   // iterations that really ran (cycle detector)
+    m.scal[S_EXEC] += (int)executed;
     if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
     m.scal[S_ZLN] = n; m.scal[S_ZLDIRTY] = 1;
   }
@@ -1248,6 +1250,7 @@ B2M_DEV B2M_NOINL bool solve_ap(const G& g, const SimParams& P, int e, EnvMem& m
   if (g.tid == 0) {
     lc[CNT_LCP_SOLVES]++; lc[CNT_LEMKE_CALLS] += stats[0]; lc[CNT_PIVOTS] += stats[1];
     lc[CNT_PIVOT_FLOPS] += (unsigned long long)stats[2] * 2ull * n * (n + 1);
+    m.scal[S_EXEC] += (int)stats[2];
     if ((unsigned long long)n > lc[CNT_MAX_N]) lc[CNT_MAX_N] = n;
   }
   if (P.tap_n) {
@@ -1386,6 +1389,7 @@ B2M_DEV B2M_NOINL void apply_no_slip_model(const G& g, const SimParams& P, int e
     if (!solved) { lc[CNT_LCP_FAIL]++; m.scal[S_FAILED] = 1; }
     lc[CNT_LCP_SOLVES]++; lc[CNT_FAST_CALLS] += fast_calls; lc[CNT_LEMKE_CALLS] += lemke_calls; lc[CNT_PIVOTS] += pivots;
     lc[CNT_PIVOT_FLOPS] += (unsigned long long)executed * 2ull * nc * (nc + 1);
+    m.scal[S_EXEC] += (int)executed;
     if ((unsigned long long)nc > lc[CNT_MAX_N]) lc[CNT_MAX_N] = nc;
     m.scal[S_VLN] = nc; m.scal[S_VLDIRTY] = 1;
   }
@@ -1632,6 +1636,20 @@ B2M_DEV B2M_INL int b2m_atomic_inc(int* p) {
 #endif
 }
 B2M_DEV B2M_INL void q_push(const SimParams& P, int round, int slot, int e) { q_list(P, round, slot)[b2m_atomic_inc(q_count(P, round, slot))] = e; }
+// hard queue: longest jobs first.  `front` entries grow from index 0, the others from the end of the list.
+B2M_DEV B2M_INL void q_push_hard(const SimParams& P, int round, int e, bool front) {
+  int* list = q_list(P, round, B2M_SLOT_HARD);
+  if (front) list[b2m_atomic_inc(q_count(P, round, B2M_SLOT_HARD))] = e;
+  else list[P.n_envs - 1 - b2m_atomic_inc(q_count(P, round, B2M_SLOT_HARD_BACK))] = e;
+}
+// number of entries of a queue slot and its i-th entry in pull order
+B2M_HD B2M_INL int q_size(const SimParams& P, int round, int slot) { return *q_count(P, round, slot) + (slot == B2M_SLOT_HARD ? *q_count(P, round, B2M_SLOT_HARD_BACK) : 0); }
+B2M_HD B2M_INL int q_at(const SimParams& P, int round, int slot, int i) {
+  const int* list = q_list(P, round, slot);
+  if (slot != B2M_SLOT_HARD) return list[i];
+  const int nf = *q_count(P, round, B2M_SLOT_HARD);
+  return i < nf ? list[i] : list[P.n_envs - 1 - (i - nf)];
+}
 
 // Advance env e through its step until it completes or needs an impact solve.  `m` carries the small segment only.
 template <class G>
@@ -1650,8 +1668,8 @@ B2M_DEV void env_advance(const G& g, const SimParams& P, int e, EnvMem& m, doubl
         const int n = contacts_lcp_dim(m, ncon, P.model);
         int cls = 0;
         while (cls < P.n_classes - 1 && (n > P.class_nmax[cls] || ncon > P.class_cmax[cls])) cls++;
-        if (P.cost && P.hard_cost > 0 && P.cost[e] >= P.hard_cost) cls = B2M_SLOT_HARD;
-        q_push(P, round, cls, e);
+        if (P.cost && P.hard_cost > 0 && P.cost[e] >= P.hard_cost) q_push_hard(P, round, e, P.cost[e] >= 8 * P.hard_cost);
+        else q_push(P, round, cls, e);
       }
       parked = true;
       break;
@@ -1678,14 +1696,14 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   m.prof = P.tap_prof ? P.tap_prof + (size_t)4 * P.n_envs + e : nullptr; m.prof_stride = P.n_envs;
   { B2M_PROF_T0(m); env_load(g, P, e, m); B2M_PROF_ADD(m, g, PH_LOAD); }
   const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
-  if (g.tid == 0) m.scal[S_FAILED] = 0;
+  if (g.tid == 0) { m.scal[S_FAILED] = 0; m.scal[S_EXEC] = 0; }
   { B2M_PROF_T0(m);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
   B2M_PROF_ADD(m, g, PH_CONTACTS); }
   lc[CNT_CONTACTS] = c0; lc[CNT_OVERFLOW] = o0;                  // counted by the advance phase
   if (!process_constraints(g, P, e, m, lc, cx)) {
-    if (g.tid == 0) { q_push(P, round, B2M_SLOT_STRAGGLER, e); if (P.cost) P.cost[e] = 1 << 30; }
+    if (g.tid == 0) { q_push(P, round, B2M_SLOT_STRAGGLER, e); if (P.cost && P.cost[e] < 4 * P.hard_cost) P.cost[e] = 4 * P.hard_cost; }
     g.sync();
     return false;
   }
@@ -1698,7 +1716,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
     P.time[e] = P.time[e] + hh;
     if (h < dt && !(hh == 0.0 && m.scal[S_FAILED])) { P.hacc[e] = h; q_push(P, round, B2M_SLOT_CONT, e); }
     else lc[CNT_ENV_STEPS]++;        // done, or given up after an unsolved LCP in a zero-length mini-step
-    if (P.cost) { const unsigned long long dp = lc[CNT_PIVOTS] - p0; P.cost[e] = dp > (1ull << 30) ? (1 << 30) : (int)dp; }
+    if (P.cost) { const int prev = P.cost[e], dec = prev - (prev >> 2); P.cost[e] = m.scal[S_EXEC] > dec ? m.scal[S_EXEC] : dec; }   // sticky: a hard env stays in the hard queue for a few steps
 #ifdef __CUDA_ARCH__
     if (P.tap_prof) {
       const size_t ne = P.n_envs;

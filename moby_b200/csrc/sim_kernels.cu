@@ -17,7 +17,8 @@ using namespace b2m;
 
 struct ClassPlan {
   int nmax = 0, cmax = 0;
-  int threads = 32;          // 32: warp-per-env kernel (wpb warps per block); > 32: one block per env
+  int threads = 32;          // 32: warp-per-env kernel (wpb warps per block); > 32: one block per env; 1: thread per env (b2m_k_impact_thread(tvariant))
+  int tvariant = -1;
   int wpb = 1, grid = 1;
   size_t shmem = 0;
   double* gscratch = nullptr;   // non-null: the working set exceeds shared memory and lives in this global buffer
@@ -36,12 +37,14 @@ struct b200moby_sim {
   // phased step plan
   int rounds = 2;
   int adv_wpb = 4, adv_grid = 1; size_t adv_shmem = 0;
+  int thread_budget = 12;    // solver iterations a thread-per-env impact may spend on one env before deferring it
   int adv_thread = -1;       // >= 0: the advance phase runs one thread per env (b2m_k_advance_thread(adv_thread)); -1: warp per env
   std::vector<ClassPlan> classes;
   ClassPlan straggler;       // full-size kernel (warp per env while the scene's LCPs fit one, else a 256-thread block) for envs over their pivot budget and for the hard queue
   ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
   int fin_grid = 1;
   ClassPlan finblock;        // nmax > B200MOBY_BIG_N: the finish phase runs one 256-thread block per env (threads == 256 when in use)
+  bool any_thread_class = false;
   bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
   long long launches = 0;
   // the impact classes of one round touch disjoint envs: they run on side streams so that the tail of one class
@@ -250,6 +253,15 @@ b200moby_status plan_launch(b200moby_sim* h) {
     h->classes.clear();
     for (int k = 0; k < ncls; k++) {
       ClassPlan c; c.nmax = h->P.class_nmax[k]; c.cmax = h->P.class_cmax[k];
+      {   // thread per env when the class's working set fits a compiled local-memory size (B200MOBY_IMPACT_THREAD=0: off)
+        EnvDims Dc = env_dims(h->P); Dc.cmax = c.cmax; Dc.nmax = c.nmax;
+        const size_t nd = env_doubles(Dc), ni = env_ints(Dc);
+        if (env_int("B200MOBY_IMPACT_THREAD", 1) != 0 && c.nmax <= env_int("B200MOBY_THREAD_NMAX", 40)) {
+          if (nd <= B2M_THREAD_ND0 && ni <= B2M_THREAD_NI0) c.tvariant = 0;
+          else if (nd <= B2M_THREAD_ND1 && ni <= B2M_THREAD_NI1) c.tvariant = 1;
+        }
+      }
+      if (c.tvariant >= 0) { c.threads = 1; c.grid = std::max(1, std::min((ne + 127) / 128, sms * 16)); h->classes.push_back(c); continue; }
       if (c.nmax <= warp_nmax || bthreads <= 32) c.threads = 32;
       else if (c.nmax > big_n) c.threads = 256;
       else c.threads = bthreads <= 64 ? 64 : (bthreads <= 128 ? 128 : 256);
@@ -258,9 +270,14 @@ b200moby_status plan_launch(b200moby_sim* h) {
       h->classes.push_back(c);
     }
     h->P.n_classes = (int)h->classes.size();
+    for (const ClassPlan& c : h->classes) if (c.threads == 1) h->any_thread_class = true;
+    h->thread_budget = env_int("B200MOBY_THREAD_BUDGET", 12);
     ClassPlan& sg = h->straggler;
-    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = (h->nmax <= warp_nmax || bthreads <= 32) ? 32 : 256;   // a lone warp has the shortest pivot latency when the LCP fits it
-    if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(256), sg, 4, ne)) != B200MOBY_OK) return st;
+    // stragglers and the hard queue want the shortest latency per pivot for one env: measured on configs[1] (n <= 40),
+    // the worst env's chain takes 16 ms on a lone warp and 6.7 ms on a 256-thread block
+    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", 128);
+    if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
+    if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
     // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished
     // by one block per env, and more rounds keep that remainder small (each extra round is a handful of short launches).
     h->finblock.threads = 32;
@@ -311,7 +328,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       cudaStream_t sc = conc ? h->hard_stream : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
       if (cp.threads == 32) { void* a[] = {&Ph, &dt, &r, &slot, &cp.wpb}; st = timed_launch(h, 3 + ncls, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc); }
-      else { void* a[] = {&Ph, &dt, &r, &slot}; st = timed_launch(h, 3 + ncls, impact_block_ptr(256), dim3(cp.grid), dim3(256), a, cp.shmem, sc); }
+      else { void* a[] = {&Ph, &dt, &r, &slot}; st = timed_launch(h, 3 + ncls, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc); }
       if (st != B200MOBY_OK) return st;
       if (conc) { B2M_CUDA(cudaEventRecord(h->hard_done, sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->hard_done, 0)); }
     }
@@ -321,7 +338,11 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       int slot = (int)c;
       cudaStream_t sc = conc ? h->side[c] : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
-      if (cp.threads == 32) {
+      if (cp.threads == 1) {
+        Pc.pivot_budget = h->thread_budget;
+        void* a[] = {&Pc, &dt, &r, &slot};
+        st = timed_launch(h, 1 + (int)c, b2m_k_impact_thread(cp.tvariant), dim3(cp.grid), dim3(128), a, 0, sc);
+      } else if (cp.threads == 32) {
         void* a[] = {&Pc, &dt, &r, &slot, &cp.wpb};
         st = timed_launch(h, 1 + (int)c, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
       } else {
@@ -332,12 +353,12 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       if (st != B200MOBY_OK) return st;
       if (conc) { B2M_CUDA(cudaEventRecord(h->side_done[c], sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->side_done[c], 0)); }
     }
-    if (P.pivot_budget > 0) {
+    if (P.pivot_budget > 0 || h->any_thread_class) {
       int slot = B2M_SLOT_STRAGGLER;
       ClassPlan& cp = h->straggler;
       SimParams Ps = P; Ps.gscratch = cp.gscratch; Ps.gstride = cp.gstride; Ps.kslot = 1 + ncls; Ps.pivot_budget = 0;
       if (cp.threads == 32) { void* a[] = {&Ps, &dt, &r, &slot, &cp.wpb}; st = timed_launch(h, 1 + ncls, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, s); }
-      else { void* a[] = {&Ps, &dt, &r, &slot}; st = timed_launch(h, 1 + ncls, impact_block_ptr(256), dim3(cp.grid), dim3(256), a, cp.shmem, s); }
+      else { void* a[] = {&Ps, &dt, &r, &slot}; st = timed_launch(h, 1 + ncls, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, s); }
       if (st != B200MOBY_OK) return st;
     }
   }
@@ -397,7 +418,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
   TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 5), &P.kstat));
   TRY(dev_zero(h, (size_t)ne, &P.cost));
-  P.hard_cost = env_int("B200MOBY_HARD_COST", 64);
+  P.hard_cost = env_int("B200MOBY_HARD_COST", 12);
   TRY(dev_zero(h, (size_t)ne, &P.hacc));
   TRY(dev_zero(h, (size_t)ne, &P.hpend));
   TRY(dev_zero(h, (size_t)B2M_ROUNDS_MAX * B2M_SLOTS * ne, &P.queue));
@@ -644,8 +665,8 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
     for (int k = 0; k < nk && k < B200MOBY_MAX_KERNELS; k++) {
       b200moby_kernel_stat& o = out->k[k];
       if (k == 0) snprintf(o.name, sizeof(o.name), "advance_kernel");
-      else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
-      else if (k == ncls + 1 || k == ncls + 3) { snprintf(o.name, sizeof(o.name), h->straggler.threads == 32 ? "impact_warp_kernel[%s]" : "impact_block_kernel<256>[%s]", k == ncls + 1 ? "stragglers" : "hard queue"); o.lcp_nmax = h->nmax; o.threads_per_env = h->straggler.threads; }
+      else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 1) snprintf(o.name, sizeof(o.name), "impact_thread_kernel[n<=%d]", c.nmax); else if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
+      else if (k == ncls + 1 || k == ncls + 3) { if (h->straggler.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[%s]", k == ncls + 1 ? "stragglers" : "hard queue"); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[%s]", h->straggler.threads, k == ncls + 1 ? "stragglers" : "hard queue"); o.lcp_nmax = h->nmax; o.threads_per_env = h->straggler.threads; }
       else snprintf(o.name, sizeof(o.name), h->finblock.threads == 256 ? "finish_block_kernel<256>" : "finish_kernel");
       if (k == 0 || k == ncls + 2) o.threads_per_env = 32;
       o.ms = h->kms[k]; o.launches = h->klaunches[k];

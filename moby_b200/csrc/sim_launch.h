@@ -5,6 +5,12 @@ const void* b2m_k_step_warp();            // (SimParams P, double dt, int n_step
 const void* b2m_k_finish();               // (SimParams P, double dt, int round)
 const void* b2m_k_advance();              // (SimParams P, double dt, int round, int wpb)
 const void* b2m_k_advance_thread(int cls); // (SimParams P, double dt, int round): thread per env; cls 0/1/2 = local working set of 256/1024/4096 doubles
+// thread-per-env impact kernels: variant v keeps a working set of up to B2M_THREAD_ND<v> doubles / B2M_THREAD_NI<v> ints in local memory
+#define B2M_THREAD_ND0 2048
+#define B2M_THREAD_NI0 288
+#define B2M_THREAD_ND1 5632
+#define B2M_THREAD_NI1 384
+const void* b2m_k_impact_thread(int variant);   // (SimParams P, double dt, int round, int slot)
 const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb)
 const void* b2m_k_impact_block64();
 const void* b2m_k_impact_block128();

@@ -97,12 +97,11 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
       }
       {   // hard queue first, full working set, no budget
         EnvMem m; env_carve(m, wd.data(), wi.data(), D);
-        const int count = *q_count(P, r, B2M_SLOT_HARD);
-        const int* list = q_list(P, r, B2M_SLOT_HARD);
+        const int count = q_size(P, r, B2M_SLOT_HARD);
         for (int i = 0; i < count; i++) {
           unsigned long long lc[CNT_COUNT] = {0};
           EnvCtx cx; cx.limit = false; cx.budget = 0;
-          env_impact(g, P, list[i], m, dt, r, lc, cx); add(lc);
+          env_impact(g, P, q_at(P, r, B2M_SLOT_HARD, i), m, dt, r, lc, cx); add(lc);
         }
       }
       for (int c = 0; c < P.n_classes; c++) {   // impact, per class, with the class's working-set size
