@@ -39,6 +39,10 @@ WORKLOADS = {
                       "16,384 envs per GPU (BASELINE configs[3]; SURVEY 8d case 4)",
                  envs=16384, dt=5e-4, preroll=100, bytes=2.0 * 8.0 * (9 + 9) + 208.0, cpu_sample=(256, 40), ref_sample=2048,
                  make=lambda sc, ne, seed: sc.ur10(ne, seed=seed, mu=100.0)),
+    "feeder": dict(name="parts-feeder-like (SURVEY 8d case 5 variant): prismatic shaker tray (RCArticulatedBody) + free box part, mu = 0.01, "
+                        "16,384 envs per GPU (part of BASELINE configs[4])",
+                   envs=16384, dt=1e-3, preroll=50, bytes=2.0 * 8.0 * (1 + 1) + 208.0, cpu_sample=(256, 40), ref_sample=2048,
+                   make=lambda sc, ne, seed: sc.parts_feeder(ne, seed=seed)),
 }
 
 

@@ -33,6 +33,23 @@ B2M_DEV B2M_NOINL double norm_inf(const G& g, int n, const double* M, int ldm, d
   }
   return g.max(m);
 }
+// The same value in two parts, so that the regularised wrappers scan the n^2 entries once instead of once per attempt:
+// the largest off-diagonal |entry| does not depend on lambda; the diagonal's does (n entries).  max is exact, so
+// fmax(off, diag(lambda)) == norm_inf(lambda) bit for bit.
+template <class G>
+B2M_DEV B2M_NOINL double norm_inf_offdiag(const G& g, int n, const double* M, int ldm) {
+  double m = 0.0;
+  for (int c = 0; c < n; c++)
+    for (int r = g.tid; r < n; r += G::size) if (r != c) m = fmax(m, fabs(M[(size_t)c * ldm + r]));
+  return g.max(m);
+}
+template <class G>
+B2M_DEV double norm_inf_with(const G& g, int n, const double* M, int ldm, double lambda, double offdiag) {
+  if (offdiag < 0.0) return norm_inf(g, n, M, ldm, lambda);
+  double m = offdiag;
+  for (int i = g.tid; i < n; i += G::size) m = fmax(m, fabs(m_at(M, ldm, i, i, lambda)));
+  return g.max(m);
+}
 
 // LCP::rand_min with the lowest-index tie rule: first minimum, then the lowest index i with v[i] < v[min] + tol.
 template <class G>
@@ -72,7 +89,7 @@ B2M_HD B2M_INL unsigned long long mix64(unsigned long long x) {
 template <class G>
 B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
-                           int* log, int log_cap, int* log_len, int* budget = nullptr, int* executed_out = nullptr) {
+                           int* log, int log_cap, int* log_len, int* budget = nullptr, int* executed_out = nullptr, double offdiag = -1.0) {
   double* T = wd;
   double* dvec = T + (size_t)n * (n + 2);
   double* rvec = dvec + n;
@@ -83,7 +100,7 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
   const int MAXITER = min(1000, 50 * n);                                   // LCP.cpp:548
   int nlog = 0, piv = 0, status = LCP_OK;
 
-  const double nrm = norm_inf(g, n, M, ldm, lambda);
+  const double nrm = norm_inf_with(g, n, M, ldm, lambda, offdiag);
   if (zero_tol <= 0.0) zero_tol = B2M_EPS * nrm * n;                       // :570-571
   const double PIV_TOL = (piv_tol > 0.0) ? piv_tol : B2M_EPS * n * fmax(1.0, nrm);   // :761
   // trivial solution (:578-584)
@@ -248,7 +265,7 @@ B2M_DEV inline void list_insert_sorted(int* L, int& m, int v) { int i = m; while
 template <class G>
 B2M_DEV B2M_NOINL int lcp_fast_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda, double zero_tol,
                               bool warm, double* z, double* wd, int* wi, int* pivots_out, int* log, int log_cap,
-                              int* log_len, int* budget = nullptr, int* executed_out = nullptr) {
+                              int* log_len, int* budget = nullptr, int* executed_out = nullptr, double offdiag = -1.0) {
   double* A = wd;
   double* zz = A + (size_t)n * n;
   double* w = zz + n;
@@ -260,7 +277,7 @@ B2M_DEV B2M_NOINL int lcp_fast_solve(const G& g, int n, const double* M, int ldm
   unsigned* hist = cur + W32;                    // ring of the last B2M_FAST_HIST sets
   int nlog = 0, nh = 0, executed = 0;
   if (executed_out) *executed_out = 0;
-  if (zero_tol < 0.0) zero_tol = n * norm_inf(g, n, M, ldm, lambda) * B2M_EPS;      // LCP.cpp:57-58
+  if (zero_tol < 0.0) zero_tol = n * norm_inf_with(g, n, M, ldm, lambda, offdiag) * B2M_EPS;      // LCP.cpp:57-58
   if (warm) {                                                                        // :65-85
     if (g.tid == 0) {
       int k = 0, nb = 0;
@@ -444,10 +461,11 @@ B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, co
                                     int min_exp, int step_exp, int max_exp, double* z, double* wd, int* wi,
                                     int* pivots_out, long long* stats, int* budget = nullptr) {
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
-  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :228
+  const double offdiag = norm_inf_offdiag(g, n, M, ldm);
+  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf_with(g, n, M, ldm, 0.0, offdiag) * B2M_NEAR_ZERO;   // :228
   double* wv = wd + (size_t)n * n + n;   // the solver's w vector doubles as verification scratch
   int total = 0, piv = 0, ex = 0;
-  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex);
+  int st = lcp_fast_solve(g, n, M, ldm, q, 0.0, zero_tol, warm, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex, offdiag);
   if (st == LCP_DEFER) return st;
   bool zvalid = warm || st == LCP_OK || st == LCP_TRIVIAL;   // z.size()==n in the reference (LCP.cpp:65): warm start of the retries
   total += piv;
@@ -460,7 +478,7 @@ B2M_DEV int lcp_fast_regularized(const G& g, int n, const double* M, int ldm, co
   for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :281-340
     const double lambda = pow10i(rf);
     g.sync();
-    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex);
+    st = lcp_fast_solve(g, n, M, ldm, q, lambda, zero_tol, zvalid, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex, offdiag);
     if (st == LCP_DEFER) return st;
     zvalid = zvalid || st == LCP_OK || st == LCP_TRIVIAL;
     total += piv;
@@ -480,10 +498,11 @@ B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, c
                                      double zero_tol, int min_exp, int step_exp, int max_exp, double* z, double* wd,
                                      int* wi, int* pivots_out, long long* stats, int* budget = nullptr) {
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
-  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf(g, n, M, ldm, 0.0) * B2M_NEAR_ZERO;   // :369
+  const double offdiag = norm_inf_offdiag(g, n, M, ldm);
+  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf_with(g, n, M, ldm, 0.0, offdiag) * B2M_NEAR_ZERO;   // :369
   double* wv = wd + (size_t)n * (n + 2);   // dvec doubles as verification scratch
   int total = 0, piv = 0, ex = 0;
-  int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex);
+  int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex, offdiag);
   if (st == LCP_DEFER) return st;
   total += piv;
   if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }
@@ -495,7 +514,7 @@ B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, c
   for (int rf = min_exp; rf < max_exp; rf += step_exp, attempt++) {                 // :419-477
     const double lambda = pow10i(rf);
     g.sync();
-    st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex);
+    st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, wd, wi, &piv, nullptr, 0, nullptr, budget, &ex, offdiag);
     if (st == LCP_DEFER) return st;
     total += piv;
     if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }

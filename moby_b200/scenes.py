@@ -434,6 +434,46 @@ def ur10(n_envs=1, fdyn=FDYN_CRB, table_z=None, with_block=True, seed=0xB200, q_
     return s
 
 
+def parts_feeder(n_envs=1, seed=0xB200, mu=0.01, NK=4, tilt=0.05, shake_hz=30.0, shake_amp=1e-3, fdyn=FDYN_CRB):
+    """SURVEY.md 8(d) case 5, parts-feeder-like (example/parts-feeder/feeder.xml): a fixed-base RCArticulatedBody whose
+    single prismatic joint `shaker` (axis x, feeder.xml:45) carries a flat tray, tilted by `tilt` rad about y
+    (rotate="0 0.05 0", feeder.xml:38), driven by a joint-space PD law towards a sinusoid (feeder.cpp:12-21: Kp = 1e3,
+    Kv = 10, 1 mm amplitude), with one free box part (0.05 x 0.025 x 0.01, mass 0.1, feeder.xml:72-77) lying on it,
+    mu = 0.01 (feeder.xml:22), gravity (0,0,-9.81), dt = 1e-3.  Benchmark variant: the tray is one box link (the file
+    builds it from three planes attached to moving links and a fixed bar), the shake frequency is 30 Hz instead of the
+    file's 500 Hz (which aliases at dt = 1 ms), the part's position and yaw on the tray are randomised per env.
+    Bodies: 0 base (no geometry), 1 tray, 2 part."""
+    rng = np.random.default_rng(seed)
+    s = SceneBatch(n_envs, 3)
+    s.name = "parts-feeder"
+    s.gravity = (0.0, 0.0, -9.81)
+    s.min_step_size = 1e-3
+    qb = quat_from_rpy(np.float64(0.0), np.float64(tilt), np.float64(0.0))
+    for k in range(4):
+        s.q[0, 3 + k, :] = qb[k]
+    s.mass[0, :] = 1.0
+    s.set_box(1, 1.0, 0.11, 0.02, mass=1.0)
+    s.set_box(2, 0.05, 0.025, 0.01, mass=0.1)
+    rc = ArticulatedBody(s, 0, 2, fdyn)
+    rc.set_joint(1, 0, JOINT_PRISMATIC, (1, 0, 0), (0, 0, 0), (0, 0, 0))
+    w = 2.0 * math.pi * shake_hz
+    rc.set_controller(np.array([1e3]), np.array([1e1]), np.array([shake_amp]), np.array([w]))
+    # the part rests on the tray's top face (tray frame), placed and yawed at random
+    R = _rotmat(np.array(qb, np.float64))
+    px = rng.uniform(-0.3, 0.3, n_envs)
+    py = rng.uniform(-0.03, 0.03, n_envs)
+    yaw = rng.uniform(-np.pi, np.pi, n_envs)
+    for e in range(n_envs):
+        local = np.array([px[e], py[e], 0.01 + 0.005])
+        s.q[2, :3, e] = R @ local
+        qy = quat_from_rpy(np.float64(0.0), np.float64(0.0), np.float64(yaw[e]))
+        s.q[2, 3:, e] = quat_mul(np.array(qb, np.float64), np.array(qy, np.float64))
+    s.set_contact(1, 2, mu_coulomb=mu, NK=NK)
+    s.max_contacts = 8
+    s.max_lcp_n = 8 * (6 + NK // 2)
+    return s
+
+
 def box_stack(n_envs=1, n_boxes=3, jitter=1e-3, seed=0xB200, adjacent_only=True, mu=1e-4, NK=4, yaw_jitter=0.0):
     """example/stacks/stack.xml (SURVEY.md 8(d) case 3): boxes of height 1 shrinking by 0.05 per level (x and z), density 10,
     centres at y = 0.5, 1.5, ..., mu = 1e-4 between neighbours and on the ground, default 4 cone edges.  The file

@@ -67,7 +67,8 @@ def _pendulum_on_plane(n_envs):
 
 
 @pytest.mark.parametrize("make,dt,steps", [(lambda: _pendulum_on_plane(5), 1e-3, 1000), (lambda: scenes.ur10(6, fdyn=scenes.FDYN_CRB), 5e-4, 250),
-                                           (lambda: scenes.ur10(3, fdyn=scenes.FDYN_FSAB), 5e-4, 120)])
+                                           (lambda: scenes.ur10(3, fdyn=scenes.FDYN_FSAB), 5e-4, 120),
+                                               (lambda: scenes.ur10(40, mu=100.0), 5e-4, 150)])
 def test_articulated_stepping_matches_oracle(torch_cuda, oracle, make, dt, steps):
     """TimeSteppingSimulator::step with an RCArticulatedBody in the scene: joint trajectories, link poses and the free
     block within 1e-9 of the oracle, identical mini-step / contact / solver-call counts.  The pendulum batch stops at
@@ -92,3 +93,22 @@ def test_articulated_stepping_matches_oracle(torch_cuda, oracle, make, dt, steps
     for k in ("env_steps", "mini_steps", "lcp_solves", "contacts", "lcp_fast_calls", "lemke_calls"):
         assert cg[k] == sum(o.counters()[k] for o in osims), k
     assert cg["lcp_failures"] == 0
+
+
+def test_parts_feeder_matches_host_build(torch_cuda):
+    """Parts-feeder-like scene (articulated tray + free part, box-box contacts, Lemke fallbacks on the degenerate face
+    LCPs): the kernels against the host build of the same code -- same tableau arithmetic, so same bits apart from the
+    1-ulp CUDA / glibc sin-cos difference in the controller, which may pick another valid LCP solution in a few envs."""
+    import hostsim_api
+    from moby_b200 import TimeSteppingSimulator
+    sc = scenes.parts_feeder(70)
+    sim, hs = TimeSteppingSimulator(sc), hostsim_api.HostSim(sc)
+    sim.step(1e-3, 200)
+    hs.step(1e-3, 200)
+    q, v = sim.get_state()
+    jq, jqd = sim.get_joint_state()
+    err = np.maximum(np.abs(q - hs.q).max(axis=(0, 1)), np.abs(v - hs.v).max(axis=(0, 1)))
+    err = np.maximum(err, np.maximum(np.abs(jq - hs.jq).max(axis=0), np.abs(jqd - hs.jqd).max(axis=0)))
+    assert (err < 1e-9).sum() >= 60 and err.max() < 1e-3, (int((err < 1e-9).sum()), err.max())
+    cg, ch = sim.counters(), hs.counters_dict()
+    assert cg["env_steps"] == ch["env_steps"] == 70 * 200 and cg["lcp_failures"] == 0 and cg["max_lcp_n"] == 32
