@@ -33,7 +33,7 @@ WORKLOADS = {
                   envs=65536, dt=1e-3, preroll=300, bytes=208.0, cpu_sample=(512, 40), ref_sample=4096,
                   make=lambda sc, ne, seed: sc.small_lcp_batch(ne, seed=seed)),
     "stacks": dict(name="example/stacks: 10-box stack, 4,096 envs per GPU, LCP n = 320 (BASELINE configs[2]; SURVEY 8d case 3)",
-                   envs=4096, dt=1e-3, preroll=5, bytes=2080.0, cpu_sample=(4, 2), ref_sample=16,
+                   envs=4096, dt=1e-3, preroll=2, bytes=2080.0, cpu_sample=(2, 1), ref_sample=16,
                    make=lambda sc, ne, seed: sc.box_stack(ne, 10, seed=seed)),
     "ur10": dict(name="example/ur10 arm (9-DoF RCArticulatedBody, CRB forward dynamics) + block + table, mu = 100 as ur10.xml:20 (no-slip impact model), "
                       "16,384 envs per GPU (BASELINE configs[3]; SURVEY 8d case 4)",
@@ -179,7 +179,6 @@ def run_lcp(args, rank, world, local_rank):
     M = torch.bmm(A, A.transpose(1, 2)) / n + 1e-3 * torch.eye(n, dtype=torch.float64, device=dev)
     del A
     q = torch.randn(batch, n, dtype=torch.float64, device=dev, generator=gen)
-    solver = L.LCP()
     Mc = M.transpose(-1, -2).contiguous()          # column-major blocks, as the C ABI takes them
     z = torch.zeros_like(q); status = torch.zeros(batch, dtype=torch.int32, device=dev); pivots = torch.zeros_like(status)
     from moby_b200 import capi

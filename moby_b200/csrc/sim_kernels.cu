@@ -275,7 +275,7 @@ b200moby_status plan_launch(b200moby_sim* h) {
     ClassPlan& sg = h->straggler;
     // stragglers and the hard queue want the shortest latency per pivot for one env: measured on configs[1] (n <= 40),
     // the worst env's chain takes 16 ms on a lone warp and 6.7 ms on a 256-thread block
-    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", 128);
+    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : 128);   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
     if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
     if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
     // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished

