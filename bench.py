@@ -271,6 +271,7 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if args.workload == "lcp":
         if args.impl == "reference":
             if rank == 0:
@@ -403,6 +404,11 @@ def main():
         achieved_gbs = alg_bytes / (dom_launch_ms * 1e-3) / 1e9
         achieved_tf = alg_flops / (dom_launch_ms * 1e-3) / 1e12
         step_ms_sum = sum(k["ms"] for k in kprof) or 1.0
+        # DRAM bytes per launch of the dominant kernel from the one `ncu --set full` capture kept under profiles/
+        # (r01_ncu_full_final_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum); only known for configs[1]
+        ncu_traffic = {"impact_block_kernel<128>[hard queue]": 30.37e6 + 46.23e6, "impact_thread_kernel[n<=40]": 17.39e6 + 54.64e6,
+                       "advance_kernel": 64.90e6 + 117.72e6}
+        traffic = ncu_traffic.get(dom["name"]) if args.workload == "small" and ne == W["envs"] else None
         out = {
             "metric": "env_steps_per_s", "value": total_envs * args.steps / t_dev, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
@@ -421,7 +427,7 @@ def main():
             "gpu_launches": launches * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "kernel": dom["name"], "kernel_ms": dom_launch_ms, "launches": dom["launches"],
+                         "traffic": traffic, "kernel": dom["name"], "kernel_ms": dom_launch_ms, "launches": dom["launches"],
                          "envs_per_launch": dom["envs"] / max(dom["launches"], 1), "share_of_kernel_time": dom["ms"] / step_ms_sum,
                          "peak_source": hbm_src,
                          "note": "pivoting is a dependent-latency chain per env: neither HBM nor the FP64 pipe is the limiter (see DESIGN.md 3-4); "
