@@ -69,7 +69,7 @@ struct SimParams {
   // at or above hard_cost is queued in B2M_SLOT_HARD instead of its class, and that queue is launched first, so the few
   // envs that set the step time (degenerate contact sets: four failed lcp_fast runs, then the Lemke ladder) run
   // alongside the bulk instead of after it.  The same envs are hard step after step (resting contact persists).
-  int* cost; int hard_cost;
+  int* cost; int hard_cost; int cost_shift;   // decay per impact: cost -= cost >> cost_shift
   int pivot_budget;            // > 0: per-env pivot budget of the warp-per-env impact kernels; over-budget envs are re-run by the straggler kernel
   // phased step (advance -> impact per LCP class -> advance ...): per-env progress and work queues
   double* hacc;                // [env] seconds of the current step already simulated
@@ -1643,12 +1643,12 @@ B2M_DEV B2M_INL void q_push_hard(const SimParams& P, int round, int e, bool fron
   else list[P.n_envs - 1 - b2m_atomic_inc(q_count(P, round, B2M_SLOT_HARD_BACK))] = e;
 }
 // number of entries of a queue slot and its i-th entry in pull order
-B2M_HD B2M_INL int q_size(const SimParams& P, int round, int slot) { return *q_count(P, round, slot) + (slot == B2M_SLOT_HARD ? *q_count(P, round, B2M_SLOT_HARD_BACK) : 0); }
+// (slot B2M_SLOT_HARD: the front entries, the costliest envs; slot B2M_SLOT_HARD_BACK: the others, stored from the end of the
+// same list -- each part has its own consumer launch)
+B2M_HD B2M_INL int q_size(const SimParams& P, int round, int slot) { return *q_count(P, round, slot); }
 B2M_HD B2M_INL int q_at(const SimParams& P, int round, int slot, int i) {
-  const int* list = q_list(P, round, slot);
-  if (slot != B2M_SLOT_HARD) return list[i];
-  const int nf = *q_count(P, round, B2M_SLOT_HARD);
-  return i < nf ? list[i] : list[P.n_envs - 1 - (i - nf)];
+  if (slot == B2M_SLOT_HARD_BACK) return q_list(P, round, B2M_SLOT_HARD)[P.n_envs - 1 - i];
+  return q_list(P, round, slot)[i];
 }
 
 // Advance env e through its step until it completes or needs an impact solve.  `m` carries the small segment only.
@@ -1716,7 +1716,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
     P.time[e] = P.time[e] + hh;
     if (h < dt && !(hh == 0.0 && m.scal[S_FAILED])) { P.hacc[e] = h; q_push(P, round, B2M_SLOT_CONT, e); }
     else lc[CNT_ENV_STEPS]++;        // done, or given up after an unsolved LCP in a zero-length mini-step
-    if (P.cost) { const int prev = P.cost[e], dec = prev - (prev >> 2); P.cost[e] = m.scal[S_EXEC] > dec ? m.scal[S_EXEC] : dec; }   // sticky: a hard env stays in the hard queue for a few steps
+    if (P.cost) { const int prev = P.cost[e], dec = prev - (prev >> P.cost_shift); P.cost[e] = m.scal[S_EXEC] > dec ? m.scal[S_EXEC] : dec; }   // sticky: a hard env stays in the hard queue for a few steps
 #ifdef __CUDA_ARCH__
     if (P.tap_prof) {
       const size_t ne = P.n_envs;

@@ -78,7 +78,7 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
   P.hacc = hacc.data(); P.hpend = hpend.data(); P.queue = queue.data(); P.qctl = qctl.data();
   P.pivot_budget = pivot_budget;
   std::vector<int> cost(ne, 0);                 // longest-job-first queue, with a low threshold so the tests exercise it
-  P.cost = cost.data(); P.hard_cost = 8;
+  P.cost = cost.data(); P.hard_cost = 8; P.cost_shift = 2;
   P.n_classes = b2m_class_table(nmax, cmax, P.model, B2M_MAX_CLASSES, P.class_nmax, P.class_cmax);
   const EnvDims D = env_dims(P);
   std::vector<double> wd(env_doubles(D));
@@ -97,11 +97,14 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
       }
       {   // hard queue first, full working set, no budget
         EnvMem m; env_carve(m, wd.data(), wi.data(), D);
-        const int count = q_size(P, r, B2M_SLOT_HARD);
-        for (int i = 0; i < count; i++) {
-          unsigned long long lc[CNT_COUNT] = {0};
-          EnvCtx cx; cx.limit = false; cx.budget = 0;
-          env_impact(g, P, q_at(P, r, B2M_SLOT_HARD, i), m, dt, r, lc, cx); add(lc);
+        for (int part = 0; part < 2; part++) {
+          const int slot = part == 0 ? B2M_SLOT_HARD : B2M_SLOT_HARD_BACK;
+          const int count = q_size(P, r, slot);
+          for (int i = 0; i < count; i++) {
+            unsigned long long lc[CNT_COUNT] = {0};
+            EnvCtx cx; cx.limit = false; cx.budget = 0;
+            env_impact(g, P, q_at(P, r, slot, i), m, dt, r, lc, cx); add(lc);
+          }
         }
       }
       for (int c = 0; c < P.n_classes; c++) {   // impact, per class, with the class's working-set size
