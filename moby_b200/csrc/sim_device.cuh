@@ -1643,12 +1643,12 @@ B2M_DEV B2M_INL void q_push_hard(const SimParams& P, int round, int e, bool fron
   else list[P.n_envs - 1 - b2m_atomic_inc(q_count(P, round, B2M_SLOT_HARD_BACK))] = e;
 }
 // number of entries of a queue slot and its i-th entry in pull order
-// (slot B2M_SLOT_HARD: the front entries, the costliest envs; slot B2M_SLOT_HARD_BACK: the others, stored from the end of the
-// same list -- each part has its own consumer launch)
-B2M_HD B2M_INL int q_size(const SimParams& P, int round, int slot) { return *q_count(P, round, slot); }
+B2M_HD B2M_INL int q_size(const SimParams& P, int round, int slot) { return *q_count(P, round, slot) + (slot == B2M_SLOT_HARD ? *q_count(P, round, B2M_SLOT_HARD_BACK) : 0); }
 B2M_HD B2M_INL int q_at(const SimParams& P, int round, int slot, int i) {
-  if (slot == B2M_SLOT_HARD_BACK) return q_list(P, round, B2M_SLOT_HARD)[P.n_envs - 1 - i];
-  return q_list(P, round, slot)[i];
+  const int* list = q_list(P, round, slot);
+  if (slot != B2M_SLOT_HARD) return list[i];
+  const int nf = *q_count(P, round, B2M_SLOT_HARD);
+  return i < nf ? list[i] : list[P.n_envs - 1 - (i - nf)];
 }
 
 // Advance env e through its step until it completes or needs an impact solve.  `m` carries the small segment only.

@@ -43,7 +43,6 @@ struct b200moby_sim {
   ClassPlan straggler;       // full-size kernel (warp per env while the scene's LCPs fit one, else a 256-thread block) for envs over their pivot budget and for the hard queue
   ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
   int fin_grid = 1;
-  ClassPlan hardfront;       // 256 threads per env for the front of the hard queue (the envs whose chains set the step time)
   ClassPlan finblock;        // nmax > B200MOBY_BIG_N: the finish phase runs one 256-thread block per env (threads == 256 when in use)
   bool any_thread_class = false;
   bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
@@ -54,7 +53,7 @@ struct b200moby_sim {
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> side_done;
   cudaEvent_t fork = nullptr;
-  cudaStream_t hard_stream = nullptr, hard_stream2 = nullptr; cudaEvent_t hard_done = nullptr, hard_done2 = nullptr;   // the hard queue's two launches
+  cudaStream_t hard_stream = nullptr; cudaEvent_t hard_done = nullptr;   // the hard queue's launch
   int rc_links = 0, rc_dof = 0;   // articulated body (0: none)
   // per-kernel profile (b200moby_get_kernel_profile): slot 0 advance, 1..n impact classes, n+1 stragglers, n+2 finish
   bool ktiming = false;
@@ -279,11 +278,6 @@ b200moby_status plan_launch(b200moby_sim* h) {
     sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : 128);   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
     if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
     if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
-    {   // the front of the hard queue always gets 256 threads per env; it runs next to the back part, so it needs its own scratch
-      ClassPlan& hf = h->hardfront;
-      hf.nmax = h->nmax; hf.cmax = h->cmax; hf.threads = 256;
-      if ((st = plan_memory(h, impact_block_ptr(256), hf, 1, ne)) != B200MOBY_OK) return st;
-    }
     // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished
     // by one block per env, and more rounds keep that remainder small (each extra round is a handful of short launches).
     h->finblock.threads = 32;
@@ -327,19 +321,9 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       } else if ((st = timed_launch(h, 0, b2m_k_advance(), dim3(h->adv_grid), dim3(h->adv_wpb * 32), a, h->adv_shmem, s)) != B200MOBY_OK) return st; }
     const bool conc = h->concurrent && h->classes.size() > 1;
     if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
-    if (P.hard_cost > 0) {   // the expensive envs first, next to the classes: the costliest ones (front) with 256 threads per env
-      ClassPlan& cp = h->hardfront;
-      int slot = B2M_SLOT_HARD;
-      SimParams Ph = P; Ph.gscratch = cp.gscratch; Ph.gstride = cp.gstride; Ph.kslot = 4 + ncls; Ph.pivot_budget = 0;
-      cudaStream_t sc = conc ? h->hard_stream2 : s;
-      if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
-      void* a[] = {&Ph, &dt, &r, &slot};
-      if ((st = timed_launch(h, 4 + ncls, impact_block_ptr(256), dim3(cp.grid), dim3(256), a, cp.shmem, sc)) != B200MOBY_OK) return st;
-      if (conc) { B2M_CUDA(cudaEventRecord(h->hard_done2, sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->hard_done2, 0)); }
-    }
-    if (P.hard_cost > 0) {   // ... and the rest of the hard queue
+    if (P.hard_cost > 0) {   // the expensive envs first, next to the classes
       ClassPlan& cp = h->straggler;
-      int slot = B2M_SLOT_HARD_BACK;
+      int slot = B2M_SLOT_HARD;
       SimParams Ph = P; Ph.gscratch = cp.gscratch; Ph.gstride = cp.gstride; Ph.kslot = 3 + ncls; Ph.pivot_budget = 0;
       cudaStream_t sc = conc ? h->hard_stream : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
@@ -432,7 +416,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)h->cmax * ne, &P.vlast));
   TRY(dev_zero(h, (size_t)ne, &P.vlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
-  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 6), &P.kstat));
+  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 5), &P.kstat));
   TRY(dev_zero(h, (size_t)ne, &P.cost));
   P.hard_cost = env_int("B200MOBY_HARD_COST", 12);
   P.cost_shift = std::max(0, std::min(30, env_int("B200MOBY_COST_DECAY_SHIFT", 2)));
@@ -469,8 +453,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
         b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the impact-class streams");
       }
     }
-    if (cudaStreamCreateWithFlags(&h->hard_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->hard_done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->hard_stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->hard_done2, cudaEventDisableTiming) != cudaSuccess) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the hard-queue stream"); }
+    if (cudaStreamCreateWithFlags(&h->hard_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->hard_done, cudaEventDisableTiming) != cudaSuccess) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the hard-queue stream"); }
     if (cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess) { b200moby_destroy(h); return b2m_fail(B200MOBY_ERR_CUDA, "cannot create the fork event"); }
   }
 #undef TRY
@@ -486,8 +469,6 @@ b200moby_status b200moby_destroy(b200moby_handle h) {
   if (h->fork) cudaEventDestroy(h->fork);
   if (h->hard_stream) { cudaStreamSynchronize(h->hard_stream); cudaStreamDestroy(h->hard_stream); }
   if (h->hard_done) cudaEventDestroy(h->hard_done);
-  if (h->hard_stream2) { cudaStreamSynchronize(h->hard_stream2); cudaStreamDestroy(h->hard_stream2); }
-  if (h->hard_done2) cudaEventDestroy(h->hard_done2);
   for (auto& pe : h->kev_pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto& pe : h->kev_free) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (void* p : h->allocs) cudaFree(p);
@@ -669,7 +650,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
   B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaDeviceSynchronize());
-  const int ncls = (int)h->classes.size(), nk = ncls + 5;
+  const int ncls = (int)h->classes.size(), nk = ncls + 4;
   h->kms.resize(nk, 0.0); h->klaunches.resize(nk, 0);
   for (auto& pe : h->kev_pending) {
     float ms = 0.f;
@@ -679,14 +660,13 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   h->kev_pending.clear();
   if (out) {
     memset(out, 0, sizeof(*out));
-    unsigned long long ks[3 * (B2M_MAX_CLASSES + 6)];
+    unsigned long long ks[3 * (B2M_MAX_CLASSES + 5)];
     B2M_CUDA(cudaMemcpy(ks, h->P.kstat, sizeof(ks), cudaMemcpyDeviceToHost));
     out->n_kernels = nk;
     for (int k = 0; k < nk && k < B200MOBY_MAX_KERNELS; k++) {
       b200moby_kernel_stat& o = out->k[k];
       if (k == 0) snprintf(o.name, sizeof(o.name), "advance_kernel");
       else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 1) snprintf(o.name, sizeof(o.name), "impact_thread_kernel[n<=%d]", c.nmax); else if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
-      else if (k == ncls + 4) { snprintf(o.name, sizeof(o.name), "impact_block_kernel<256>[hard queue, front]"); o.lcp_nmax = h->nmax; o.threads_per_env = 256; }
       else if (k == ncls + 1 || k == ncls + 3) { if (h->straggler.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[%s]", k == ncls + 1 ? "stragglers" : "hard queue"); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[%s]", h->straggler.threads, k == ncls + 1 ? "stragglers" : "hard queue"); o.lcp_nmax = h->nmax; o.threads_per_env = h->straggler.threads; }
       else snprintf(o.name, sizeof(o.name), h->finblock.threads == 256 ? "finish_block_kernel<256>" : "finish_kernel");
       if (k == 0 || k == ncls + 2) o.threads_per_env = 32;
@@ -696,7 +676,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   }
   if (reset) {
     std::fill(h->kms.begin(), h->kms.end(), 0.0); std::fill(h->klaunches.begin(), h->klaunches.end(), 0);
-    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 6)));
+    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 5)));
   }
   h->ktiming = enable != 0;
   return B200MOBY_OK;

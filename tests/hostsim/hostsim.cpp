@@ -97,14 +97,11 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
       }
       {   // hard queue first, full working set, no budget
         EnvMem m; env_carve(m, wd.data(), wi.data(), D);
-        for (int part = 0; part < 2; part++) {
-          const int slot = part == 0 ? B2M_SLOT_HARD : B2M_SLOT_HARD_BACK;
-          const int count = q_size(P, r, slot);
-          for (int i = 0; i < count; i++) {
-            unsigned long long lc[CNT_COUNT] = {0};
-            EnvCtx cx; cx.limit = false; cx.budget = 0;
-            env_impact(g, P, q_at(P, r, slot, i), m, dt, r, lc, cx); add(lc);
-          }
+        const int count = q_size(P, r, B2M_SLOT_HARD);
+        for (int i = 0; i < count; i++) {
+          unsigned long long lc[CNT_COUNT] = {0};
+          EnvCtx cx; cx.limit = false; cx.budget = 0;
+          env_impact(g, P, q_at(P, r, B2M_SLOT_HARD, i), m, dt, r, lc, cx); add(lc);
         }
       }
       for (int c = 0; c < P.n_classes; c++) {   // impact, per class, with the class's working-set size
