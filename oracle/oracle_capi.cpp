@@ -112,6 +112,11 @@ static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
   }
 }
 
+// dense helpers, exposed so the tests can pin them against LAPACK (scipy): LinAlgd::solve_fast / factor_chol / inverse_SPD
+int oracle_solve_fast(int n, double* A, double* b, int* piv) { return oracle::solve_fast(A, n, b, piv) ? 1 : 0; }
+int oracle_factor_chol(int n, double* A) { return oracle::factor_chol(A, n) ? 1 : 0; }
+int oracle_inverse_spd(int n, double* A) { return oracle::inverse_SPD(A, n) ? 1 : 0; }
+
 void* oracle_sim_create(const b200moby_scene_desc* d, int env, int tie) {
   OracleSim* o = new OracleSim;
   fill_from_desc(o->sim, d, env);

@@ -50,7 +50,7 @@ inline double norm_inf(const double* M, int rows, int cols) {
 // trailing update with fma; forward substitution fused into the elimination;
 // column-oriented back substitution, columns descending, fma.
 // Returns false on an exactly zero pivot (SingularException).
-inline bool solve_fast(double* A, int n, double* b) {
+inline bool solve_fast(double* A, int n, double* b, int* piv = nullptr) {   // piv (optional): pivot row chosen at each column, as LAPACK's ipiv (0-based)
   for (int j = 0; j < n; j++) {
     int p = j;
     double best = std::fabs(A[(size_t)j * n + j]);
@@ -59,6 +59,7 @@ inline bool solve_fast(double* A, int n, double* b) {
       if (v > best) { best = v; p = i; }
     }
     if (A[(size_t)j * n + p] == 0.0) return false;
+    if (piv) piv[j] = p;
     if (p != j) {
       for (int c = 0; c < n; c++) { double t = A[(size_t)c * n + j]; A[(size_t)c * n + j] = A[(size_t)c * n + p]; A[(size_t)c * n + p] = t; }
       double t = b[j]; b[j] = b[p]; b[p] = t;
