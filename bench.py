@@ -64,6 +64,21 @@ def _peaks():
     return hbm, src, fp64, fsrc
 
 
+class StdoutGuard:
+    """Rank 0 prints ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr so that library banners
+    (NCCL prints its version to stdout at communicator creation) cannot precede it; emit() restores it for the line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(json.dumps(obj), flush=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -170,6 +185,7 @@ def run_lcp(args, rank, world, local_rank):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    guard = StdoutGuard()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.lcp_n
@@ -249,7 +265,7 @@ def run_lcp(args, rank, world, local_rank):
             el = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": ns / el, "unit": "LCP solves/s", "cores": 1, "kind": "port",
                                    "sample": f"first {ns} problems of rank 0's batch, 1 thread ({el:.1f} s); oracle/ restatement of LCP::lcp_lemke (LU per pivot, as the reference)"}
-        print(json.dumps(out), flush=True)
+        guard.emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -289,6 +305,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    guard = StdoutGuard()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = WORKLOADS[args.workload]
@@ -449,7 +466,7 @@ def main():
                                              f"1 thread ({el1:.1f} s); oracle/ restatement (the reference cannot be built here)",
                                    "lcp_solves_per_s": l1,
                                    "all_cores": {"value": vn, "cores": cores, "sample": f"first {min(n_cpu * 4, ne)} envs, {s_cpu} steps ({eln:.1f} s)"}}
-        print(json.dumps(out), flush=True)
+        guard.emit(out)
     if world > 1:
         dist.destroy_process_group()
 
