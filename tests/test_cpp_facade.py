@@ -49,3 +49,69 @@ def test_facade_sitting_box_matches_oracle(sitting_box, oracle):
     zf = [float(x) for x in meta["lcp_fast"][1:]]
     assert meta["lcp_lemke"][0] == "1" and np.allclose(zl, [4 / 3, 7 / 3], atol=1e-14)
     assert meta["lcp_fast"][0] == "1" and np.allclose(zf, [4 / 3, 7 / 3], atol=1e-14)
+
+
+# ---- Moby::XMLReader::read of the facade (include/b200moby_xml.hpp) against the Python loader ----
+REF = "/root/reference/example"
+
+
+def _dump(sitting_box, path):
+    exe = os.path.join(CPP, "xml_dump")
+    r = subprocess.run([exe, path], capture_output=True, text=True)
+    return r.returncode, r.stdout, r.stderr
+
+
+def _check_against_python_loader(sitting_box, path):
+    from moby_b200 import xml_scene
+    rc, out, err = _dump(sitting_box, path)
+    assert rc == 0, err
+    s, info = xml_scene.load_xml(path, 1)
+    nb = s.n_bodies
+    lines = out.splitlines()
+    head = lines[0].split()
+    assert float(head[3]) == s.min_step_size and float(head[5]) == s.contact_dist_thresh
+    bodies = [l.split() for l in lines if l.startswith("body ")]
+    assert [b[2] for b in bodies] == sorted(info["bodies"], key=info["bodies"].get)
+    for i, b in enumerate(bodies):
+        f = lambda k, n: np.array([float(x) for x in b[k:k + n]])  # noqa: E731
+        assert int(b[4]) == s.enabled[i, 0] and int(b[6]) == s.shape[i, 0]
+        assert np.array_equal(f(8, 3), s.dims[i, :, 0])
+        assert np.allclose(f(18, 7), s.q[i, :, 0], rtol=0, atol=1e-15) and np.array_equal(f(26, 6), s.v[i, :, 0])
+        assert np.array_equal(f(33, 3), np.array(s.gravity))
+        if s.enabled[i, 0]:
+            assert np.allclose(float(b[12]), s.mass[i, 0], rtol=1e-15) and np.allclose(f(14, 3), s.inertia[i, :, 0], rtol=1e-15)
+    seen = set()
+    for l in lines:
+        if not l.startswith("contact "):
+            continue
+        t = l.split()
+        a, b = int(t[1]), int(t[2])
+        o = a * nb + b
+        seen.add(o)
+        assert float(t[4]) == s.epsilon[o, 0] and float(t[6]) == s.mu_coulomb[o, 0] and float(t[8]) == s.mu_viscous[o, 0]
+        assert float(t[10]) == s.compliance[o, 0] and int(t[12]) == s.NK[o, 0]
+    for a in range(nb):                                   # pairs the file does not mention keep the defaults in both loaders
+        for b in range(a + 1, nb):
+            if a * nb + b not in seen:
+                assert s.NK[a * nb + b, 0] == 4 and s.mu_coulomb[a * nb + b, 0] == 0.0 and s.epsilon[a * nb + b, 0] == 0.0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("rel", ["simple-contact/simplest.xml", "bouncing-ball/bouncing-ball.xml", "stacks/sphere-stack.xml", "stacks/stack.xml"])
+def test_cpp_xml_reader_loads_reference_scenes(sitting_box, rel):
+    _check_against_python_loader(sitting_box, os.path.join(REF, rel))
+
+
+def test_cpp_xml_reader_inline_scene_and_errors(sitting_box, tmp_path):
+    from test_xml_scene import INLINE
+    good = tmp_path / "scene.xml"
+    good.write_text(INLINE.replace('<DisabledPair object1-id="ball" object2-id="brick" />', ""))
+    _check_against_python_loader(sitting_box, str(good))
+    bad = tmp_path / "joint.xml"
+    bad.write_text(INLINE.replace("<GravityForce", '<RevoluteJoint id="j" /> <GravityForce'))
+    rc, out, err = _dump(sitting_box, str(bad))
+    assert rc == 1 and "RevoluteJoint" in err
+    broken = tmp_path / "broken.xml"
+    broken.write_text("<XML><MOBY><Box id='b' xlen='1'></MOBY></XML>")
+    rc, out, err = _dump(sitting_box, str(broken))
+    assert rc == 1 and "XML parse error" in err
