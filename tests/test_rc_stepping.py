@@ -99,3 +99,20 @@ def test_parts_feeder_like_scene():
         assert ch["env_steps"] == co["env_steps"] == 400 and ch["lcp_failures"] == 0 and ch["max_lcp_n"] == 32 and ch["lcp_solves"] > 300
         assert hs.q[2, 0, e] > sc.q[2, 0, e]                                   # the part slides down the tilted tray
     assert exact >= 1
+
+
+@pytest.mark.parametrize("make,dt,steps", [(lambda: scenes.ur10(3, mu=100.0), 5e-4, 120), (lambda: scenes.parts_feeder(5), 1e-3, 150),
+                                           (lambda: scenes.ur10(2), 5e-4, 102)])
+@pytest.mark.parametrize("budget", [0, 6])
+def test_phased_schedule_with_queues_is_identical_to_fused(make, dt, steps, budget):
+    """The launch schedule of the GPU path (advance / hard queue / impact classes with a per-env solver budget / stragglers /
+    finish) on scenes with an articulated body: bit-identical to the fused per-env loop, whatever the budget."""
+    sc = make()
+    a, b = H.HostSim(sc), H.HostSim(sc)
+    a.step(dt, steps)
+    for _ in range(3):
+        b.step_phased(dt, steps // 3, rounds=2, pivot_budget=budget)
+    assert np.array_equal(a.jq, b.jq) and np.array_equal(a.jqd, b.jqd) and np.array_equal(a.q, b.q) and np.array_equal(a.v, b.v)
+    ca, cb = a.counters_dict(), b.counters_dict()
+    assert ca == cb, (ca, cb)
+    assert ca["lcp_solves"] > 50
