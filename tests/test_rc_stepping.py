@@ -116,3 +116,13 @@ def test_phased_schedule_with_queues_is_identical_to_fused(make, dt, steps, budg
     ca, cb = a.counters_dict(), b.counters_dict()
     assert ca == cb, (ca, cb)
     assert ca["lcp_solves"] > 50
+
+
+def test_ur10_under_the_anitescu_potra_model():
+    """-DUSE_AP_MODEL build of the reference (ImpactConstraintHandlerLCP.cpp) on the articulated scene: dense problem data +
+    A-P LCP + Lemke only."""
+    sc = scenes.ur10(2)
+    sc.impact_model = scenes.MODEL_AP
+    hs, sims = _compare(sc, 5e-4, 200, 1e-9)
+    c = hs.counters_dict()
+    assert c["lemke_calls"] >= c["lcp_solves"] > 300 and c["lcp_fast_calls"] == 0 and c["max_lcp_n"] == 24
