@@ -119,7 +119,7 @@ typedef struct {
   const double* dims;       /* box: xlen,ylen,zlen; sphere: radius,-,-; plane: -,-,- (plane is y=0 of the body frame, BoxPrimitive.cpp:358, PlanePrimitive.cpp:477) */
   const double* inertia;    /* principal body-frame inertia (InertiaFromPrimitive) */
   /* contact parameters, [body_i*n_bodies + body_j][env] for i<j (ContactParameters.cpp:97-136) */
-  const double* mu_coulomb;
+  const double* mu_coulomb;  /* an island whose contacts all have mu_coulomb >= 100 takes the no-slip model (ImpactConstraintHandler.cpp:122-135,1009-1417) */
   const double* mu_viscous;
   const double* epsilon;
   const double* compliance;
