@@ -31,7 +31,10 @@ class TimeSteppingSimulator:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            capi.lib().b200moby_destroy(h)
+            try:
+                capi.lib().b200moby_destroy(h)
+            except TypeError:            # interpreter shutdown: module globals are already gone, the process frees the device
+                pass
             self._h = None
 
     # ---- state (host buffers, SoA [body][7|6][env]) ----
