@@ -33,7 +33,7 @@ class TimeSteppingSimulator:
         if h:
             try:
                 capi.lib().b200moby_destroy(h)
-            except TypeError:            # interpreter shutdown: module globals are already gone, the process frees the device
+            except (TypeError, AttributeError):   # interpreter shutdown: module globals are already gone, the process frees the device
                 pass
             self._h = None
 
