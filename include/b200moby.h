@@ -225,6 +225,12 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
  * store); prof: host buffer [13][env]; reading clears it.  The first call arms the tap. */
 b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof);
 
+/* Debug tap: per-env solver statistics accumulated since the previous call -- LCPSolverException equivalents
+ * (ImpactConstraintHandlerQP.cpp:224), LCP::lcp_lemke calls, LCP::lcp_fast calls, impact problems solved, pivots (LCP::pivots summed); stat: host
+ * buffer [5][env]; reading clears it.  The first call arms the tap.  Used by the parity tests to match the checker env
+ * by env. */
+b200moby_status b200moby_get_env_stats(b200moby_handle h, int* stat);
+
 /* ---- batched solvers: replace LCP::lcp_lemke / lcp_fast and wrappers (LCP.h:21-27) ----
  * M_dev [batch][n*n] column-major, q_dev [batch][n], z_dev [batch][n] (in: warm start for lcp_fast, out: solution),
  * status_dev [batch], pivots_dev [batch] (may be NULL), pivot_log_dev [batch][log_cap] (may be NULL):

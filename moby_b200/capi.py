@@ -62,7 +62,7 @@ SYMBOLS = [
     "b200moby_create", "b200moby_destroy", "b200moby_set_state", "b200moby_get_state",
     "b200moby_set_state_dev", "b200moby_get_state_dev", "b200moby_step", "b200moby_set_pivot_budget", "b200moby_get_counters",
     "b200moby_reset_counters", "b200moby_get_launch_count", "b200moby_get_time", "b200moby_get_last_lcp",
-    "b200moby_get_impact_profile", "b200moby_get_kernel_profile",
+    "b200moby_get_impact_profile", "b200moby_get_kernel_profile", "b200moby_get_env_stats",
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
     "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host", "b200moby_lcp_solve_host",
     "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_delassus_batched",
@@ -98,6 +98,7 @@ def lib():
     L.b200moby_get_time.argtypes = [C.c_void_p, dp]
     L.b200moby_get_last_lcp.argtypes = [C.c_void_p, ip, dp, C.c_int]
     L.b200moby_get_impact_profile.argtypes = [C.c_void_p, ip]
+    L.b200moby_get_env_stats.argtypes = [C.c_void_p, ip]
     L.b200moby_get_kernel_profile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(KernelProfile)]
     L.b200moby_lcp_lemke_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, ip, ip, ip, C.c_int, vp]
     L.b200moby_lcp_fast_batched.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, ip, ip, ip, C.c_int, vp]

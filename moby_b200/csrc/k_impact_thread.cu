@@ -20,14 +20,19 @@ __global__ void __launch_bounds__(128) impact_thread_kernel(SimParams P, double 
   EnvMem m;
   env_carve(m, wd, wi, env_dims(P));
   SerialGroup g(nullptr);
-  unsigned long long lc[CNT_COUNT];
-  for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
+  // counters of ONE env at a time: an env that runs over its budget is abandoned untouched and re-run (and counted) by the
+  // straggler kernel, so what it counted here is dropped -- as in k_impact_warp.cu and tests/hostsim
+  unsigned long long lc[CNT_COUNT], tot[CNT_COUNT];
+  for (int k = 0; k < CNT_COUNT; k++) { lc[k] = 0; tot[k] = 0; }
   const int count = q_size(P, round, slot);
   unsigned long long envs = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
     EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
-    if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) envs++;
+    if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) add_counters(tot, lc);
+    envs++;                                            // envs handed to this launch (deferred ones included), like the warp kernel
   }
+  for (int k = 0; k < CNT_COUNT; k++) lc[k] = tot[k];
   for (int k = 0; k < CNT_COUNT; k++) {
     unsigned long long v = lc[k];
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o); v = (k == CNT_MAX_N) ? (u > v ? u : v) : v + u; }

@@ -71,21 +71,13 @@ B2M_DEV int rand_min(const G& g, const double* v, int m, double tol) {
 B2M_HD inline size_t lemke_work_doubles(int n) { return (size_t)n * (n + 2) + n + (n + 2); }
 B2M_HD inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
 
-#ifndef B2M_LEMKE_LITERAL
-#define B2M_LEMKE_LITERAL 0   /* 1: never cut a periodic pivot sequence short (test builds) */
-#endif
-// 64-bit mixers for the cycle detector's state hash (splitmix64 finaliser with two different offsets)
-B2M_HD B2M_INL unsigned long long mix64(unsigned long long x) {
-  x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull; return x ^ (x >> 31);
-}
-
-// Cycle detector: with the lowest-index tie rule a Lemke pivot is a pure function of (ordered basis, entering variable)
-// -- the reference re-derives x and the entering column from the basis with a fresh LU every pivot (LCP.cpp:834-838) --
-// so meeting a state seen before in this call proves the pivoting is periodic and will run into the iteration cap
-// (LCP.cpp:548,789; the reference has no anti-cycling rule, :926-928).  The call then returns what the reference
-// returns -- LCP_MAXITER, pivots = the cap -- without spinning through the remaining iterations.  States are compared
-// through a 128-bit hash of the ordered basis plus the entering variable; every thread keeps one (serial group: 32)
-// recent state, so the window is the group size.  Disabled when a pivot log is requested (literal variant).
+// No cycle detection: LCP.cpp has no anti-cycling rule (:926-928) and on degenerate problems the pivoting can circle until
+// the iteration cap (:548,789).  Round 1 cut such runs short when an (ordered basis, entering variable) pair recurred.
+// That is a proof of periodicity only in exact arithmetic: the reference re-solves the entering column with a fresh LU
+// every pivot (:834-838) but updates x incrementally (:983-988), the tableau here is incremental throughout, and on
+// 1,024 envs x 300 steps of configs[1] the literal run left such "cycles" through rounding 1,268 pivots before the cap
+// (same final states, different pivot counts), while a bit-exact variant (recurrence of the tracked state AND of every
+// tableau entry's bits) never fired once.  So the solver is literal: it pivots until the reference would stop.
 template <class G>
 B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
@@ -129,26 +121,12 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
   int s = n;           // entering slot
   int entering = t;
   bool first = true;   // the first pass pivots the artificial variable in (LCP.cpp:776-785); `piv` counts the pivots after it
-  constexpr int HL = (G::size >= 32) ? 1 : 32;
-  unsigned long long hk1[HL], hk2[HL]; int hen[HL];
-  for (int i = 0; i < HL; i++) { hk1[i] = 0; hk2[i] = 0; hen[i] = -1; }
-  unsigned long long h1 = 0, h2 = 0;                 // sum over rows of mix(row, bas[row]); every thread keeps its own copy
-  const unsigned long long V = 2ull * n + 1ull;
-  for (int i = 0; i < n; i++) { const unsigned long long kx = (unsigned long long)i * V + (unsigned long long)(n + i); h1 += mix64(kx); h2 += mix64(kx ^ 0x5851f42d4c957f2dull); }
-  int nhist = 0, executed = 0;
+  int executed = 0;
   for (;;) {
     // entering column
     for (int i = g.tid; i < n; i += G::size) dvec[i] = T[(size_t)s * n + i];
     g.sync();
     if (!first) {
-      if (!log && !B2M_LEMKE_LITERAL) {             // state seen before?
-        bool rep = false;
-        for (int i = 0; i < HL; i++) rep = rep || (hen[i] == entering && hk1[i] == h1 && hk2[i] == h2);
-        if (g.any(rep)) { status = LCP_MAXITER; piv = MAXITER; break; }
-        const int pos = nhist % (HL * G::size);
-        if (pos % G::size == g.tid) { hk1[pos / G::size] = h1; hk2[pos / G::size] = h2; hen[pos / G::size] = entering; }
-        nhist++;
-      }
       executed++;
       // ratio test (:886-975)
       // two group reductions per pivot: a finite ratio exists iff some d_i > PIV_TOL, and the artificial variable's row
@@ -169,8 +147,6 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
     }
     const int leaving = bas[r];
     const double p = dvec[r];
-    { const unsigned long long ko = (unsigned long long)r * V + (unsigned long long)leaving, kn = (unsigned long long)r * V + (unsigned long long)entering;
-      h1 += mix64(kn) - mix64(ko); h2 += mix64(kn ^ 0x5851f42d4c957f2dull) - mix64(ko ^ 0x5851f42d4c957f2dull); }
     g.sync();                                   // everyone has read bas/where/dvec[r] before they change
     // pivot row, scaled; the leaving variable's column (a unit vector while basic) replaces slot s
     for (int c = g.tid; c < n + 2; c += G::size) rvec[c] = (c == s) ? 1.0 / p : T[(size_t)c * n + r] / p;

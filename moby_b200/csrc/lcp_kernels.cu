@@ -176,6 +176,18 @@ b200moby_status b200moby_lcp_fast_regularized_batched(int batch, int n, const do
   return launch(a, stream);
 }
 
+// device buffers + stream of one host-form call, released on every exit path
+struct HostFormScratch {
+  cudaStream_t s = nullptr;
+  void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  ~HostFormScratch() {
+    if (!s) { for (void* q : p) if (q) cudaFree(q); return; }
+    for (void* q : p) if (q) cudaFreeAsync(q, s);
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+  }
+};
+
 static b200moby_status host_form(int mode, int batch, int n, const double* M, const double* q, double* z, int warm,
                                  double piv_tol, double zero_tol, int min_exp, int step_exp, int max_exp, int* status,
                                  int* pivots, int device) {
@@ -184,17 +196,21 @@ static b200moby_status host_form(int mode, int batch, int n, const double* M, co
   if (batch <= 0 || n <= 0) return B200MOBY_OK;
   if (!M || !q || !z) return b2m_fail(B200MOBY_ERR_INVALID, "null pointer");
   B2M_CUDA(cudaSetDevice(device));
-  double *dM = nullptr, *dq = nullptr, *dz = nullptr; int *dst = nullptr, *dpv = nullptr;
+  HostFormScratch sc;
   const size_t nM = (size_t)batch * n * n, nv = (size_t)batch * n;
-  cudaStream_t s; B2M_CUDA(cudaStreamCreate(&s));
-  B2M_CUDA(cudaMallocAsync((void**)&dM, nM * sizeof(double), s));
-  B2M_CUDA(cudaMallocAsync((void**)&dq, nv * sizeof(double), s));
-  B2M_CUDA(cudaMallocAsync((void**)&dz, nv * sizeof(double), s));
-  B2M_CUDA(cudaMallocAsync((void**)&dst, batch * sizeof(int), s));
-  B2M_CUDA(cudaMallocAsync((void**)&dpv, batch * sizeof(int), s));
+  B2M_CUDA(cudaStreamCreate(&sc.s));
+  cudaStream_t s = sc.s;
+  B2M_CUDA(cudaMallocAsync(&sc.p[0], nM * sizeof(double), s));
+  B2M_CUDA(cudaMallocAsync(&sc.p[1], nv * sizeof(double), s));
+  B2M_CUDA(cudaMallocAsync(&sc.p[2], nv * sizeof(double), s));
+  B2M_CUDA(cudaMallocAsync(&sc.p[3], batch * sizeof(int), s));
+  B2M_CUDA(cudaMallocAsync(&sc.p[4], batch * sizeof(int), s));
+  double *dM = (double*)sc.p[0], *dq = (double*)sc.p[1], *dz = (double*)sc.p[2]; int *dst = (int*)sc.p[3], *dpv = (int*)sc.p[4];
   B2M_CUDA(cudaMemcpyAsync(dM, M, nM * sizeof(double), cudaMemcpyHostToDevice, s));
   B2M_CUDA(cudaMemcpyAsync(dq, q, nv * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (warm) B2M_CUDA(cudaMemcpyAsync(dz, z, nv * sizeof(double), cudaMemcpyHostToDevice, s));
+  // z is the warm start of the lcp_fast family and is left as given when such a solve fails (LCP.cpp:118-126,192-195):
+  // the device copy always starts from the caller's z so that a failed cold solve hands back what it was given
+  B2M_CUDA(cudaMemcpyAsync(dz, z, nv * sizeof(double), cudaMemcpyHostToDevice, s));
   b200moby_status r;
   switch (mode) {
     case MODE_LEMKE: r = b200moby_lcp_lemke_batched(batch, n, dM, dq, dz, piv_tol, zero_tol, dst, dpv, nullptr, 0, s); break;
@@ -202,15 +218,12 @@ static b200moby_status host_form(int mode, int batch, int n, const double* M, co
     case MODE_LEMKE_REG: r = b200moby_lcp_lemke_regularized_batched(batch, n, dM, dq, dz, min_exp, step_exp, max_exp, piv_tol, zero_tol, dst, dpv, s); break;
     default: r = b200moby_lcp_fast_regularized_batched(batch, n, dM, dq, dz, warm, min_exp, step_exp, max_exp, zero_tol, dst, dpv, s); break;
   }
-  if (r == B200MOBY_OK) {
-    B2M_CUDA(cudaMemcpyAsync(z, dz, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (status) B2M_CUDA(cudaMemcpyAsync(status, dst, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (pivots) B2M_CUDA(cudaMemcpyAsync(pivots, dpv, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
-  }
-  cudaFreeAsync(dM, s); cudaFreeAsync(dq, s); cudaFreeAsync(dz, s); cudaFreeAsync(dst, s); cudaFreeAsync(dpv, s);
+  if (r != B200MOBY_OK) return r;
+  B2M_CUDA(cudaMemcpyAsync(z, dz, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) B2M_CUDA(cudaMemcpyAsync(status, dst, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (pivots) B2M_CUDA(cudaMemcpyAsync(pivots, dpv, batch * sizeof(int), cudaMemcpyDeviceToHost, s));
   B2M_CUDA(cudaStreamSynchronize(s));
-  cudaStreamDestroy(s);
-  return r;
+  return B200MOBY_OK;
 }
 
 b200moby_status b200moby_lcp_solve_host(int mode, int batch, int n, const double* M, const double* q, double* z, int warm_start,

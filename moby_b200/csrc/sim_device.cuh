@@ -88,6 +88,7 @@ struct SimParams {
   double* gscratch; size_t gstride;
   // per-kernel accounting: kstat[3 * kslot + {0,1,2}] += envs processed, algorithmic flops (pivot + assembly), LCP solves
   unsigned long long* kstat; int kslot;
+  int* env_stat;               // optional [5][env]: LCP failures, lcp_lemke calls, lcp_fast calls, LCP solves, pivots of each env since the tap was armed (parity tests)
   long long* tap_prof;         // [4 + PH_COUNT][env]: SM cycles, pivots, executed iterations, LCP n of the env's last impact phase, then cycles per phase
 };
 
@@ -182,6 +183,24 @@ enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLA
 // abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
 // step with many more threads per pivot (same arithmetic, same results).  Keeps one hard LCP from holding a whole SM.
 struct EnvCtx { int budget; bool limit; };
+
+// per-env solver statistics (SimParams::env_stat): the counters an env added to `lc` since `base` was taken
+struct EnvStatBase { unsigned long long fail, lemke, fast, solves, pivots; };
+B2M_HD B2M_INL EnvStatBase env_stat_base(const unsigned long long* lc);
+
+B2M_HD B2M_INL EnvStatBase env_stat_base(const unsigned long long* lc) {
+  EnvStatBase b; b.fail = lc[CNT_LCP_FAIL] + lc[CNT_OVERFLOW]; b.lemke = lc[CNT_LEMKE_CALLS]; b.fast = lc[CNT_FAST_CALLS]; b.solves = lc[CNT_LCP_SOLVES]; b.pivots = lc[CNT_PIVOTS]; return b;
+}
+template <class G>
+B2M_DEV B2M_INL void env_stat_commit(const G& g, const SimParams& P, int e, const unsigned long long* lc, const EnvStatBase& b) {
+  if (!P.env_stat || g.tid != 0) return;
+  const size_t ne = P.n_envs;
+  P.env_stat[e] += (int)(lc[CNT_LCP_FAIL] + lc[CNT_OVERFLOW] - b.fail);
+  P.env_stat[ne + e] += (int)(lc[CNT_LEMKE_CALLS] - b.lemke);
+  P.env_stat[2 * ne + e] += (int)(lc[CNT_FAST_CALLS] - b.fast);
+  P.env_stat[3 * ne + e] += (int)(lc[CNT_LCP_SOLVES] - b.solves);
+  P.env_stat[4 * ne + e] += (int)(lc[CNT_PIVOTS] - b.pivots);
+}
 
 // ---------- geometry helpers (same formulas, same order as the CPU checker) ----------
 B2M_HD B2M_INL void quat_to_R(const double* qt, double* R) {
@@ -1610,8 +1629,10 @@ template <class G>
 B2M_DEV bool env_run(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int n_steps, unsigned long long* lc, EnvCtx& cx) {
   env_load(g, P, e, m);
   double t = P.time[e];
+  const EnvStatBase sb = env_stat_base(lc);
   for (int s = 0; s < n_steps; s++)
     if (!env_finish_step(g, P, e, m, dt, 0.0, t, lc, cx)) return false;
+  env_stat_commit(g, P, e, lc, sb);
   g.sync();
   env_store(g, P, e, m);
   if (g.tid == 0) P.time[e] = t;
@@ -1693,6 +1714,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   const long long t0 = P.tap_prof ? clock64() : 0;
 #endif
   const unsigned long long p0 = lc[CNT_PIVOTS], f0 = lc[CNT_PIVOT_FLOPS];
+  const EnvStatBase sb = env_stat_base(lc);
   m.prof = P.tap_prof ? P.tap_prof + (size_t)4 * P.n_envs + e : nullptr; m.prof_stride = P.n_envs;
   { B2M_PROF_T0(m); env_load(g, P, e, m); B2M_PROF_ADD(m, g, PH_LOAD); }
   const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
@@ -1708,6 +1730,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
     return false;
   }
   mini_step_account(g, P, m, lc);
+  env_stat_commit(g, P, e, lc, sb);
   g.sync();
   { B2M_PROF_T0(m); env_store(g, P, e, m, ST_VEL | ST_ZL); B2M_PROF_ADD(m, g, PH_STORE); }
   if (g.tid == 0) {
@@ -1736,7 +1759,9 @@ B2M_DEV void env_finish(const G& g, const SimParams& P, int e, EnvMem& m, double
   env_load(g, P, e, m);
   double t = P.time[e];
   EnvCtx cx; cx.limit = false; cx.budget = 0;
+  const EnvStatBase sb = env_stat_base(lc);
   env_finish_step(g, P, e, m, dt, P.hacc[e], t, lc, cx);
+  env_stat_commit(g, P, e, lc, sb);
   g.sync();
   env_store(g, P, e, m);
   if (g.tid == 0) P.time[e] = t;

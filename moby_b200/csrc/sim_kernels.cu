@@ -34,6 +34,7 @@ struct b200moby_sim {
   int wpb = 1, grid = 1, sms = 148;
   size_t shmem = 0;          // full working set of one env (stage kernels, finish kernel)
   bool taps = false;
+  bool stage_attr_set = false;
   // phased step plan
   int rounds = 2;
   int adv_wpb = 4, adv_grid = 1; size_t adv_shmem = 0;
@@ -494,6 +495,7 @@ b200moby_status b200moby_get_state(b200moby_handle h, double* q, double* v) {
 }
 b200moby_status b200moby_set_state_dev(b200moby_handle h, const double* q, const double* v, void* stream) {
   if (!h || !q || !v) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaMemcpyAsync(h->P.q, q, sizeof(double) * h->nb * 7 * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   B2M_CUDA(cudaMemcpyAsync(h->P.v, v, sizeof(double) * h->nb * 6 * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   normalize_quat_kernel<<<(h->nb * h->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->P.q, h->nb, h->n_envs);
@@ -502,6 +504,7 @@ b200moby_status b200moby_set_state_dev(b200moby_handle h, const double* q, const
 }
 b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q, double* v, void* stream) {
   if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
+  B2M_CUDA(cudaSetDevice(h->device));
   if (q) B2M_CUDA(cudaMemcpyAsync(q, h->P.q, sizeof(double) * h->nb * 7 * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (v) B2M_CUDA(cudaMemcpyAsync(v, h->P.v, sizeof(double) * h->nb * 6 * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return B200MOBY_OK;
@@ -509,6 +512,7 @@ b200moby_status b200moby_get_state_dev(b200moby_handle h, double* q, double* v, 
 
 static b200moby_status rc_refresh(b200moby_handle h, cudaStream_t s) {
   void* a[] = {&h->P};
+  B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaLaunchKernel(b2m_k_rc_refresh(), dim3((h->n_envs + 127) / 128), dim3(128), a, 0, s));
   h->launches++;
   return B200MOBY_OK;
@@ -532,6 +536,7 @@ b200moby_status b200moby_get_joint_state(b200moby_handle h, double* jq, double* 
 b200moby_status b200moby_set_joint_state_dev(b200moby_handle h, const double* jq, const double* jqd, void* stream) {
   if (!h || !jq || !jqd) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
   if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaMemcpyAsync(h->P.jq, jq, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   B2M_CUDA(cudaMemcpyAsync(h->P.jqd, jqd, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return rc_refresh(h, (cudaStream_t)stream);
@@ -539,6 +544,7 @@ b200moby_status b200moby_set_joint_state_dev(b200moby_handle h, const double* jq
 b200moby_status b200moby_get_joint_state_dev(b200moby_handle h, double* jq, double* jqd, void* stream) {
   if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
   if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
+  B2M_CUDA(cudaSetDevice(h->device));
   if (jq) B2M_CUDA(cudaMemcpyAsync(jq, h->P.jq, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (jqd) B2M_CUDA(cudaMemcpyAsync(jqd, h->P.jqd, sizeof(double) * h->rc_dof * h->n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return B200MOBY_OK;
@@ -557,6 +563,7 @@ b200moby_status b200moby_rc_fwd_dyn_batched(b200moby_handle h, int algorithm, co
   if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
   if (algorithm != B200MOBY_FDYN_FSAB && algorithm != B200MOBY_FDYN_CRB) return b2m_fail(B200MOBY_ERR_INVALID, "unknown forward-dynamics algorithm %d", algorithm);
   void* a[] = {&h->P, &algorithm, &jq, &jqd, &tau, &qdd};
+  B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaLaunchKernel(b2m_k_rc_fwd_dyn(), dim3((h->n_envs + 127) / 128), dim3(128), a, 0, (cudaStream_t)stream));
   h->launches++;
   return B200MOBY_OK;
@@ -565,6 +572,7 @@ b200moby_status b200moby_rc_inertia_batched(b200moby_handle h, const double* jq,
   if (!h || !jq || !H) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
   if (!h->rc_links) return b2m_fail(B200MOBY_ERR_INVALID, "the scene has no articulated body");
   void* a[] = {&h->P, &jq, &H};
+  B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaLaunchKernel(b2m_k_rc_inertia(), dim3((h->n_envs + 127) / 128), dim3(128), a, 0, (cudaStream_t)stream));
   h->launches++;
   return B200MOBY_OK;
@@ -573,6 +581,7 @@ b200moby_status b200moby_rc_inertia_batched(b200moby_handle h, const double* jq,
 b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* stream) {
   if (!h || !(dt > 0.0) || n_steps < 0) return b2m_fail(B200MOBY_ERR_INVALID, "bad step arguments");
   if (n_steps == 0) return B200MOBY_OK;
+  B2M_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   if (h->fused) {
     void* a[] = {&h->P, &dt, &n_steps, &h->env_d};
@@ -694,11 +703,23 @@ b200moby_status b200moby_get_impact_profile(b200moby_handle h, long long* prof) 
   return B200MOBY_OK;
 }
 
+// Debug tap: per-env solver statistics since the previous call; stat: host buffer [5][env] (LCP failures, lcp_lemke calls,
+// lcp_fast calls, LCP solves, pivots as the reference counts them).  The first call arms the tap (and returns zeros); reading clears it.
+b200moby_status b200moby_get_env_stats(b200moby_handle h, int* stat) {
+  if (!h || !stat) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
+  B2M_CUDA(cudaSetDevice(h->device));
+  B2M_CUDA(cudaDeviceSynchronize());
+  if (!h->P.env_stat) { b200moby_status st; if ((st = dev_zero(h, (size_t)5 * h->n_envs, &h->P.env_stat)) != B200MOBY_OK) return st; }
+  B2M_CUDA(cudaMemcpy(stat, h->P.env_stat, sizeof(int) * 5 * h->n_envs, cudaMemcpyDeviceToHost));
+  B2M_CUDA(cudaMemset(h->P.env_stat, 0, sizeof(int) * 5 * h->n_envs));
+  return B200MOBY_OK;
+}
+
 static b200moby_status run_stage(b200moby_handle h, int stage, const double* q, const double* v, StageOut o, void* stream) {
   if (!h || !q || !v) return b2m_fail(B200MOBY_ERR_INVALID, "null argument");
   if (h->rc_links && stage == STAGE_DELASSUS) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "the assembly stage kernel handles free-body scenes only");
-  static bool attr_set = false;
-  if (!attr_set) { B2M_CUDA(cudaFuncSetAttribute(stage_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX)); attr_set = true; }
+  B2M_CUDA(cudaSetDevice(h->device));
+  if (!h->stage_attr_set) { B2M_CUDA(cudaFuncSetAttribute(stage_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2M_SMEM_MAX)); h->stage_attr_set = true; }   // function attributes are per device: one flag per handle
   SimParams P = h->P;
   P.q = const_cast<double*>(q); P.v = const_cast<double*>(v);
   stage_warp_kernel<<<h->grid, h->wpb * 32, h->shmem, (cudaStream_t)stream>>>(P, stage, o, h->wpb, h->env_d, h->env_i);

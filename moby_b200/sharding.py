@@ -24,6 +24,35 @@ def shard_scene(scene, rank, world):
         setattr(s, name, np.ascontiguousarray(getattr(scene, name)[..., e0:e1]))
     if scene.min_step_size_env is not None:
         s.min_step_size_env = np.ascontiguousarray(scene.min_step_size_env[e0:e1])
+    for name in getattr(scene, "per_env_extra", ()):          # per-env arrays a scene builder added (joint limits, ...)
+        setattr(s, name, np.ascontiguousarray(getattr(scene, name)[..., e0:e1]))
+    if getattr(scene, "rc", None) is not None:                # the articulated body carries per-env joint state and points at its scene
+        rc = copy.copy(scene.rc)
+        rc.scene = s
+        rc.jq = np.ascontiguousarray(scene.rc.jq[:, e0:e1])
+        rc.jqd = np.ascontiguousarray(scene.rc.jqd[:, e0:e1])
+        s.rc = rc
+    return s
+
+
+def select_envs(scene, idx):
+    """The sub-batch made of envs `idx` (any order, any subset) of `scene`: what shard_scene does for a contiguous range."""
+    import copy
+    idx = np.asarray(idx, np.int64)
+    s = copy.copy(scene)
+    s.n_envs = int(idx.size)
+    for name in ("shape", "enabled", "mass", "dims", "inertia", "mu_coulomb", "mu_viscous", "epsilon", "compliance", "NK", "q", "v"):
+        setattr(s, name, np.ascontiguousarray(getattr(scene, name)[..., idx]))
+    if scene.min_step_size_env is not None:
+        s.min_step_size_env = np.ascontiguousarray(scene.min_step_size_env[idx])
+    for name in getattr(scene, "per_env_extra", ()):
+        setattr(s, name, np.ascontiguousarray(getattr(scene, name)[..., idx]))
+    if getattr(scene, "rc", None) is not None:
+        rc = copy.copy(scene.rc)
+        rc.scene = s
+        rc.jq = np.ascontiguousarray(scene.rc.jq[:, idx])
+        rc.jqd = np.ascontiguousarray(scene.rc.jqd[:, idx])
+        s.rc = rc
     return s
 
 

@@ -142,6 +142,13 @@ class TimeSteppingSimulator:
         capi.check(capi.lib().b200moby_get_impact_profile(self._h, prof.ctypes.data))
         return prof
 
+    def env_stats(self):
+        """Debug tap: per-env (lcp_failures, lemke_calls, lcp_fast_calls, lcp_solves, pivots) since the previous call, as a dict of
+        [env] arrays; the first call arms the tap and returns zeros."""
+        st = np.zeros((5, self.n_envs), np.int32)
+        capi.check(capi.lib().b200moby_get_env_stats(self._h, st.ctypes.data))
+        return dict(lcp_failures=st[0], lemke_calls=st[1], lcp_fast_calls=st[2], lcp_solves=st[3], pivots=st[4])
+
     def last_lcp_z(self, zcap):
         n = np.zeros(self.n_envs, np.int32)
         z = np.zeros((self.n_envs, zcap))

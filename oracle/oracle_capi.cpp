@@ -299,6 +299,28 @@ void oracle_batch_run(void* h, double dt, int n_steps, int threads, b200moby_cou
 }
 // state of env (e0 + i) as AoS [body][7], [body][6]
 void oracle_batch_get_state(void* h, int i, double* q, double* v) { get_state(((OracleBatch*)h)->sims[i], q, v); }
+// state of every env of the batch in the product's SoA layout: q [body][7][n], v [body][6][n] with n = e1 - e0
+void oracle_batch_get_state_soa(void* h, double* q, double* v) {
+  OracleBatch* B = (OracleBatch*)h;
+  const int n = (int)B->sims.size();
+  if (!n) return;
+  const int nb = (int)B->sims[0].bodies.size();
+  std::vector<double> qa(nb * 7), va(nb * 6);
+  for (int i = 0; i < n; i++) {
+    get_state(B->sims[i], qa.data(), va.data());
+    for (int b = 0; b < nb; b++) { for (int k = 0; k < 7; k++) q[((size_t)b * 7 + k) * n + i] = qa[b * 7 + k]; for (int k = 0; k < 6; k++) v[((size_t)b * 6 + k) * n + i] = va[b * 6 + k]; }
+  }
+}
+// per-env solver statistics since creation, stat [5][n]: LCP failures, lcp_lemke calls, lcp_fast calls, LCP solves, pivots
+// (the checker's side of b200moby_get_env_stats)
+void oracle_batch_env_stats(void* h, int* stat) {
+  OracleBatch* B = (OracleBatch*)h;
+  const size_t n = B->sims.size();
+  for (size_t i = 0; i < n; i++) {
+    const Counters& k = B->sims[i].cnt;
+    stat[i] = (int)k.lcp_failures; stat[n + i] = (int)k.lemke_calls; stat[2 * n + i] = (int)k.lcp_fast_calls; stat[3 * n + i] = (int)k.lcp_solves; stat[4 * n + i] = (int)k.pivots;
+  }
+}
 
 // ---- reduced-coordinate articulated body (oracle_rc.h) ----
 // mass [link], J [link][3], base_pose [7] = x y z qx qy qz qw; the tree comes from the product's plain-C descriptor.

@@ -12,6 +12,8 @@
 
 using namespace b2m;
 
+static int* g_env_stat = nullptr;   // optional [5][n_envs] per-env solver statistics (SimParams::env_stat), set by hostsim_set_env_stat
+
 // SimParams over host arrays, exactly as b200moby_create fills it
 static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, const std::vector<double>& tab, const b200moby_scene_desc* d, int cmax,
                          int nmax, int npmax, double* q, double* v, double* time, double* zlast, int* zlast_n, unsigned long long* counters,
@@ -25,6 +27,7 @@ static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, 
   P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
   P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
   P.vlast = zlast + (size_t)nmax * ne; P.vlast_n = zlast_n + ne;   // the caller's arrays carry both warm starts
+  P.env_stat = g_env_stat;
   if (d->rc && d->rc->n_links > 0) {
     bool unsup;
     if (b2m_rc_tree_from_desc(*d->rc, nb, tree, &unsup)) return false;
@@ -37,6 +40,8 @@ static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, 
 }
 
 extern "C" {
+
+void hostsim_set_env_stat(int* stat) { g_env_stat = stat; }
 
 // q [nb][7][ne], v [nb][6][ne], time [ne], zlast [2 nmax][ne] (QP warm start, then the no-slip one), zlast_n [2][ne], counters [CNT_COUNT] all host, updated in place.
 // Returns nmax (call with q == NULL to query sizes only).

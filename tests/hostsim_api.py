@@ -33,6 +33,7 @@ def lib():
         L.hostsim_lcp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hostsim_rc.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8
+        L.hostsim_set_env_stat.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -42,8 +43,9 @@ class HostSim:
 
     def __init__(self, scene, taps=False):
         self.scene = scene
+        self._L = lib()
         self._d = scene.cdesc()
-        self.nmax = lib().hostsim_run(C.byref(self._d), None, None, None, None, None, None, 0.0, 0, 0, 0, None, None, None, None, None, None)
+        self.nmax = self._L.hostsim_run(C.byref(self._d), None, None, None, None, None, None, 0.0, 0, 0, 0, None, None, None, None, None, None)
         ne = scene.n_envs
         self.q, self.v = scene.q.copy(), scene.v.copy()
         self.q[:, 3:7, :] /= np.sqrt((self.q[:, 3:7, :] ** 2).sum(axis=1, keepdims=True))   # as b200moby_set_state does
@@ -53,6 +55,7 @@ class HostSim:
         self.rc = getattr(scene, "rc", None)
         self.jq = self.rc.jq.copy() if self.rc is not None else None
         self.jqd = self.rc.jqd.copy() if self.rc is not None else None
+        self.stat = np.zeros((5, ne), np.int32)     # per-env lcp_failures, lemke_calls, lcp_fast_calls, lcp_solves, pivots (SimParams::env_stat)
         self.taps = taps
         if taps:
             self.tapMM, self.tapqq = np.zeros((ne, self.nmax * self.nmax)), np.zeros((ne, self.nmax))
@@ -62,18 +65,23 @@ class HostSim:
         e1 = self.scene.n_envs if e1 is None else e1
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         t = [p(self.tapMM), p(self.tapqq), p(self.tapz), p(self.tapn)] if self.taps else [None] * 4
-        lib().hostsim_run(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
+        self._L.hostsim_set_env_stat(p(self.stat))
+        self._L.hostsim_run(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
                           dt, n, e0, e1, *t, self._jp(self.jq), self._jp(self.jqd))
 
     def step_phased(self, dt, n=1, rounds=2, pivot_budget=0):
         """The same steps through the phased schedule (advance / impact classes / stragglers / finish)."""
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        lib().hostsim_run_phased(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
+        self._L.hostsim_set_env_stat(p(self.stat))
+        self._L.hostsim_run_phased(C.byref(self._d), p(self.q), p(self.v), p(self.time), p(self.zlast), p(self.zlast_n), p(self.counters),
                                  dt, n, rounds, pivot_budget, self._jp(self.jq), self._jp(self.jqd))
 
     @staticmethod
     def _jp(a):
         return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def env_stats(self):
+        return dict(lcp_failures=self.stat[0], lemke_calls=self.stat[1], lcp_fast_calls=self.stat[2], lcp_solves=self.stat[3], pivots=self.stat[4])
 
     def counters_dict(self):
         return {k: int(self.counters[i]) for i, k in enumerate(CNT)}
@@ -83,7 +91,7 @@ class HostSim:
         return n, self.tapMM[e, :n * n].reshape(n, n).T.copy(), self.tapqq[e, :n].copy(), self.tapz[e, :n].copy()
 
 
-def lcp(mode, M, q, z0=None, piv_tol=-1.0, zero_tol=-1.0, min_exp=-20, step_exp=1, max_exp=1, log_cap=4096):
+def lcp(mode, M, q, z0=None, piv_tol=-1.0, zero_tol=-1.0, min_exp=-20, step_exp=1, max_exp=1, log_cap=4096, want_log=True):
     """mode 0 lemke, 1 fast, 2 lemke_regularized, 3 fast_regularized.  Returns (status, z, pivots, log)."""
     n = len(q)
     Mf = np.asfortranarray(np.asarray(M, np.float64))
@@ -93,7 +101,7 @@ def lcp(mode, M, q, z0=None, piv_tol=-1.0, zero_tol=-1.0, min_exp=-20, step_exp=
     log = np.zeros(log_cap, np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     st = lib().hostsim_lcp(mode, n, p(Mf), p(q), p(z), 0 if z0 is None else 1, piv_tol, zero_tol, min_exp, step_exp, max_exp,
-                           C.byref(piv), p(log), log_cap, C.byref(ll))
+                                  C.byref(piv), p(log) if want_log else None, log_cap, C.byref(ll))
     return st, z, piv.value, log[:min(ll.value, log_cap)].copy()
 
 

@@ -53,6 +53,8 @@ def lib():
         L.oracle_batch_destroy.argtypes = [C.c_void_p]
         L.oracle_batch_run.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(Counters)]
         L.oracle_batch_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_batch_get_state_soa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_batch_env_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_batch_set_joint_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_batch_get_joint_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         for f in (L.oracle_sim_set_joint_state, L.oracle_sim_get_joint_state):
@@ -235,6 +237,20 @@ class OracleBatch:
         q, v = np.zeros((self.nb, 7)), np.zeros((self.nb, 6))
         lib().oracle_batch_get_state(self.h, i, _p(q), _p(v))
         return q, v
+
+    def get_state_soa(self):
+        """State of every env of the batch in the product's layout: q [body][7][n], v [body][6][n]."""
+        n = self.e1 - self.e0
+        q, v = np.zeros((self.nb, 7, n)), np.zeros((self.nb, 6, n))
+        lib().oracle_batch_get_state_soa(self.h, _p(q), _p(v))
+        return q, v
+
+    def env_stats(self):
+        """Per-env (lcp_failures, lemke_calls, lcp_fast_calls, lcp_solves) since creation, as a dict of [n] arrays."""
+        n = self.e1 - self.e0
+        st = np.zeros((5, n), np.int32)
+        lib().oracle_batch_env_stats(self.h, _p(st))
+        return dict(lcp_failures=st[0], lemke_calls=st[1], lcp_fast_calls=st[2], lcp_solves=st[3], pivots=st[4])
 
 
 # ---- reduced-coordinate articulated body (oracle/oracle_rc.h) ----

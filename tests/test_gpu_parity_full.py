@@ -1,0 +1,108 @@
+"""VERDICT r1 items 1a / 1c on the GPU, through the C ABI: the configuration bench.py times (BASELINE configs[1] at its
+full 65,536 envs, per-scene min-step-size) and the parts-feeder scene against the ORACLE, env by env -- per step from
+identical inputs (solver-call counts, failures, states at 1e-9) and over the pre-roll horizon (failures, totals, drift).
+See tests/parity_util.py for the two statements and the one documented exception (Lemke path divergence on degenerate
+LCPs)."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as PU
+from moby_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+THREADS = min(32, os.cpu_count() or 1)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def _per_step(sc, dt, pre, sample, oracle, max_extra=4096):
+    """Pre-roll `pre` steps on the GPU, restart GPU and oracle from that state, one step, compare env by env on the first
+    `sample` envs plus every env that reported a failure or ran Lemke (up to max_extra of those)."""
+    from moby_b200 import TimeSteppingSimulator
+    ne = sc.n_envs
+    sim = TimeSteppingSimulator(sc)
+    sim.env_stats()
+    sim.step(dt, pre)
+    pre_stats = sim.env_stats()
+    q, v = sim.get_state()
+    joints = sim.get_joint_state() if sc.rc is not None else None
+    assert sim.counters()["env_steps"] == ne * pre
+    del sim
+    sc2 = PU.scene_at_state(sc, q, v, joints)
+    sim2 = TimeSteppingSimulator(sc2)
+    sim2.env_stats()
+    sim2.step(dt, 1)
+    st = sim2.env_stats()
+    q2, v2 = sim2.get_state()
+    hard = np.where((st["lcp_failures"] > 0) | (st["lemke_calls"] > 0) | (pre_stats["lcp_failures"] > 0))[0]
+    fails = np.where((st["lcp_failures"] > 0) | (pre_stats["lcp_failures"] > 0))[0]
+    idx = np.union1d(np.union1d(np.arange(min(sample, ne)), hard[:max_extra]), fails)
+    ost, qo, vo = PU.oracle_run(oracle, sc2, idx, dt, 1, THREADS)
+    return PU.compare(st, q2, v2, ost, qo, vo, idx), pre_stats, st
+
+
+@pytest.mark.parametrize("seed", [0xB200, 0xB200 + 3])
+def test_configs1_full_size_bench_config_per_step(torch_cuda, oracle, seed):
+    """65,536 envs, bench.py's min-step configuration, 300 pre-roll steps (as bench.py), then one step from identical
+    inputs on >= 2,048 sampled envs + every env that ran Lemke or failed."""
+    ne = 65536
+    sc = scenes.small_lcp_batch(ne, seed=seed)
+    rep, pre_stats, st = _per_step(sc, 1e-3, 300, 2048, oracle)
+    print("configs[1] per-step parity", seed, rep, "pre-roll failures", int(pre_stats["lcp_failures"].sum()))
+    assert rep["n"] >= 2048 and rep["sum_lcp_solves"][0] > 500 and rep["sum_lemke_calls"][0] > 50, rep
+    assert rep["mismatch_lcp_failures"] == 0, rep                 # an env fails on the GPU iff the oracle fails on it
+    assert rep["mismatch_outside_ladder"] == 0, rep               # same impact problems, same lcp_fast calls
+    assert rep["above_tol_same_path"] == 0, rep                   # same pivot path => 1e-9 (measured: 1e-12)
+    # envs whose Lemke runs part ways with the oracle's on a degenerate LCP: <= 0.1 % of the batch per step, and still
+    # within the tolerance of the wrapper's own acceptance test
+    assert rep["ladder_mismatch"] <= ne // 1000 and rep["ok_ladder_tol"], rep
+
+
+def test_configs1_horizon_failures_match_oracle(torch_cuda, oracle):
+    """The 300-step pre-roll itself on a 2,048-env sample + every env that reported an unsolved LCP: the oracle reports
+    failures on the same envs; totals agree; the share of envs above 1e-9 is the drift bench.py prints."""
+    from moby_b200 import TimeSteppingSimulator
+    ne, steps = 65536, 300
+    for seed in (0xB200, 0xB200 + 5):
+        sc = scenes.small_lcp_batch(ne, seed=seed)
+        sim = TimeSteppingSimulator(sc)
+        sim.env_stats()
+        sim.step(1e-3, steps)
+        st = sim.env_stats()
+        q, v = sim.get_state()
+        fails = np.where(st["lcp_failures"] > 0)[0]
+        idx = np.union1d(np.arange(2048), fails)
+        ost, qo, vo = PU.oracle_run(oracle, sc, idx, 1e-3, steps, THREADS)
+        rep = PU.compare(st, q, v, ost, qo, vo, idx)
+        print("configs[1] horizon", seed, rep, "failing envs", fails[:16])
+        f_gpu, f_or = set(idx[st["lcp_failures"][idx] > 0]), set(idx[ost["lcp_failures"] > 0])
+        # after 300 steps trajectories of a few envs have parted ways (drift), so failures are compared as sets with slack
+        assert len(f_gpu ^ f_or) <= max(2, len(f_gpu | f_or) // 2), (sorted(f_gpu), sorted(f_or))
+        for k in ("lemke_calls", "lcp_fast_calls", "lcp_solves"):
+            a, b = rep["sum_" + k]
+            assert abs(a - b) <= 0.05 * max(a, b, 1), rep
+        assert rep["above_tol"] <= rep["n"] // 20, rep
+        del sim
+
+
+def test_parts_feeder_matches_oracle(torch_cuda, oracle):
+    """Parts-feeder-like scene (articulated tray + free part, box-box face contacts, mu = 0.01): every impact LCP is
+    singular (cond ~ 1e17) and needs the Lemke ladder.  From identical inputs, one step: the same problems, the same
+    lcp_fast calls and failures for every env; states within 1e-9 wherever the Lemke pivot path is the oracle's; the
+    share of envs whose path differs is bounded (the oracle's own LU against LAPACK's parts ways on a similar share of
+    these LCPs: profiles/r02_lemke_path_sensitivity.json)."""
+    sc = scenes.parts_feeder(1024)
+    rep, _, _ = _per_step(sc, 1e-3, 100, 1024, oracle)
+    print("feeder per-step parity", rep)
+    assert rep["n"] == 1024 and rep["sum_lcp_solves"][0] >= 900, rep
+    assert rep["mismatch_lcp_failures"] == 0 and rep["mismatch_lcp_solves"] == 0 and rep["mismatch_lcp_fast_calls"] == 0, rep
+    assert rep["above_tol_same_path"] == 0, rep
+    assert rep["ladder_mismatch"] <= 0.45 * rep["n"], rep
+    assert rep["err_max"] < 5e-2, rep

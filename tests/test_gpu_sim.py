@@ -238,3 +238,39 @@ def test_box_stack_matches_oracle(torch_cuda, oracle, n_boxes, steps, yaw):
     assert cg["lcp_failures"] == 0
     if yaw == 0.0:
         assert cg["max_lcp_n"] == 32 * n_boxes
+
+
+def test_offset_sphere_kinetic_energy(torch_cuda, oracle):
+    """test/TestOffsetSphere.cpp:36-73 re-expressed (see tests/test_reference_properties.py): kinetic energy conserved to
+    1e-6 under sustained rolling contact, 5/7 law for the slide -> roll transition, GPU == oracle."""
+    from moby_b200 import TimeSteppingSimulator
+    from test_reference_properties import check_offset_sphere, offset_sphere_scene
+    sc = offset_sphere_scene(2)
+    sim = TimeSteppingSimulator(sc)
+    check_offset_sphere(lambda n: sim.step(1e-3, n), lambda: sim.get_state()[1][:, :, 0], sc)
+    o = oracle.OracleSim(sc)
+    o.step(1e-3, 3000)
+    qo, vo = o.get_state()
+    q, v = sim.get_state()
+    for e in range(2):
+        assert np.abs(q[:, :, e] - qo).max() < 1e-9 and np.abs(v[:, :, e] - vo).max() < 1e-9
+
+
+def test_thread_kernel_counters_do_not_depend_on_the_budget(torch_cuda):
+    """ADVICE r1: an env deferred by the thread-per-env impact kernel is re-run and counted by the straggler kernel only;
+    counters must be the same whatever the budget (0 = no deferral)."""
+    import os
+    from moby_b200 import TimeSteppingSimulator
+    sc = scenes.small_lcp_batch(4096, seed=77)
+    res = []
+    for budget in ("0", "4", "12"):
+        os.environ["B200MOBY_THREAD_BUDGET"] = budget
+        try:
+            sim = TimeSteppingSimulator(sc)
+            sim.step(1e-3, 120)
+            res.append((sim.counters(), sim.get_state()))
+        finally:
+            del os.environ["B200MOBY_THREAD_BUDGET"]
+    for c, (q, v) in res[1:]:
+        assert c == res[0][0], (c, res[0][0])
+        assert np.array_equal(q, res[0][1][0]) and np.array_equal(v, res[0][1][1])

@@ -55,3 +55,28 @@ def test_two_rank_gloo_matches_single_process(tmp_path, n_envs):
     for k in ("env_steps", "mini_steps", "lcp_solves", "pivots", "contacts", "lcp_fast_calls", "lemke_calls"):
         assert int(got["c_" + k]) == rc[k], k
     assert int(got["c_env_steps"]) == n_envs * steps
+
+
+def test_shard_scene_slices_the_articulated_body():
+    """A shard owns its own ArticulatedBody: joint state sliced, rc.scene pointing at the shard, and
+    stepping the two shards equals stepping the full batch."""
+    import hostsim_api
+    from moby_b200 import scenes, sharding
+    hostsim_api.build()
+    full = scenes.ur10(8, seed=5)
+    parts = [sharding.shard_scene(full, r, 2) for r in range(2)]
+    for r, s in enumerate(parts):
+        assert s.rc is not full.rc and s.rc.scene is s
+        assert s.rc.jq.shape == (9, 4) and s.rc.jqd.shape == (9, 4)
+        assert np.array_equal(s.rc.jq, full.rc.jq[:, 4 * r:4 * r + 4])
+        for e in range(4):                                   # link_poses / env_mass_props index the shard's own envs
+            x_s, R_s = s.rc.link_poses(e)
+            x_f, R_f = full.rc.link_poses(4 * r + e)
+            assert np.array_equal(x_s, x_f) and np.array_equal(R_s, R_f)
+            assert all(np.array_equal(a, b) for a, b in zip(s.rc.env_mass_props(e), full.rc.env_mass_props(4 * r + e)))
+    ref = hostsim_api.HostSim(full)
+    ref.step(5e-4, 20)
+    for r, s in enumerate(parts):
+        hs = hostsim_api.HostSim(s)
+        hs.step(5e-4, 20)
+        assert np.array_equal(hs.q, ref.q[..., 4 * r:4 * r + 4]) and np.array_equal(hs.jq, ref.jq[:, 4 * r:4 * r + 4])
