@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200MOBY_ABI_VERSION 2
+#define B200MOBY_ABI_VERSION 3
 
 typedef enum {
   B200MOBY_OK = 0,
@@ -129,7 +129,9 @@ typedef struct {
   double min_step_size;         /* TimeSteppingSimulator.cpp:48, default sqrt(eps) */
   const double* min_step_size_env; /* optional [env] override (XML min-step-size, TimeSteppingSimulator.cpp:470-472); NULL = scalar above */
   int    impact_model;          /* B200MOBY_MODEL_* */
-  int    stabilization_max_iterations; /* must be 0 this round */
+  int    stabilization_max_iterations; /* constraint-stabilization-max-iterations (ConstraintStabilization.cpp:53-59): 0 = off (as
+                                          example/ur10/ur10.xml:12), < 0 = the reference's default (no limit: until no pair is closer than
+                                          sqrt(eps); capped at 100 iterations per step here and counted), > 0 = that many */
   const b200moby_rc_desc* rc;   /* optional articulated body (NULL: free bodies only) */
   /* Working-set bounds per env.  0 = the worst case over all body pairs (every pair in contact at once), which is
    * what small scenes use; many-body scenes (a 10-box stack has 55 pairs but ~40 simultaneous contacts) give the bounds
@@ -155,6 +157,10 @@ typedef struct {
   long long pivot_flops;      /* sum over solves of pivots * 2 n (n+1): the algorithmic solver flops of SURVEY.md 8(d) */
   long long ca_iterations;    /* position sub-steps of the conservative-advancement loop (TimeSteppingSimulator.cpp:133-168) */
   long long assembly_flops;   /* F_delassus + F_apply per island solve + F_fd + F_narrow per mini-step (SURVEY.md 8(d) formulas) */
+  long long stab_iterations;  /* iterations of ConstraintStabilization::stabilize's loop (ConstraintStabilization.cpp:197-244) */
+  long long stab_lcp_solves;  /* frictionless position LCPs solved by determine_dq (ConstraintStabilization.cpp:932-970); their lcp_fast /
+                                 lcp_lemke calls and pivots are included in the counters above, failures in lcp_failures */
+  long long stab_line_search_failures; /* update_q gave up (t < sqrt(eps), :1186-1187) or the 100-iteration cap was hit */
 } b200moby_counters;
 
 const char* b200moby_last_error(void);
@@ -203,7 +209,7 @@ b200moby_status b200moby_get_last_lcp(b200moby_handle h, int* n, double* z, int 
  * processed and the algorithmic flops it did (pivots * 2n(n+1) + assembly, the formulas of SURVEY.md 8d).
  * enable != 0 turns the event bracketing on for subsequent steps; reset != 0 clears the accumulators after reading.
  * Synchronises the device.  out may be NULL. */
-#define B200MOBY_MAX_KERNELS 16
+#define B200MOBY_MAX_KERNELS 20
 typedef struct {
   char name[48];
   double ms;            /* summed launch durations */

@@ -44,13 +44,14 @@ class KernelStat(C.Structure):
 
 
 class KernelProfile(C.Structure):
-    _fields_ = [("n_kernels", C.c_int), ("k", KernelStat * 16)]
+    _fields_ = [("n_kernels", C.c_int), ("k", KernelStat * 20)]
 
 
 class Counters(C.Structure):
     _fields_ = [(k, C.c_longlong) for k in (
         "env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
-        "impact_tol_events", "contacts", "max_lcp_n", "pivot_flops", "ca_iterations", "assembly_flops")]
+        "impact_tol_events", "contacts", "max_lcp_n", "pivot_flops", "ca_iterations", "assembly_flops", "stab_iterations",
+        "stab_lcp_solves", "stab_line_search_failures")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

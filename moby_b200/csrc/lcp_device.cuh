@@ -71,6 +71,124 @@ B2M_DEV int rand_min(const G& g, const double* v, int m, double tol) {
 B2M_HD inline size_t lemke_work_doubles(int n) { return (size_t)n * (n + 2) + n + (n + 2); }
 B2M_HD inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
 
+#ifdef __CUDACC__
+// ---- warp-owned pivot loop (n <= 64) ------------------------------------------------------------------------------
+// The generic loop below spreads every tableau pass over the group with a flat index: for one warp that is 50+ dependent
+// load / fma / store rounds per pivot with index arithmetic in between (ncu, round 1: ~3,000 cycles per pivot at n = 40,
+// issue slots 14 % busy).  Here lane l OWNS tableau rows l and l + 32: the entering column and x stay in its registers
+// for the ratio test, both quotients of the ratio test are formed at once, the pivot element travels by shuffle, and the
+// rank-one update walks the columns in batches of eight as ONE straight-line block -- all 24 loads of a batch first, no
+// guard inside (a lone warp issues in order: ncu showed 21 cycles per instruction when every element sat behind its own
+// branch), row indices clamped instead of predicated, LDS / STS instead of generic accesses when the working set is in
+// shared memory.  No barrier other than __syncwarp, no integer division.  Every tableau entry goes through the same
+// operations in the same order as in the generic loop (x / p, fma(-d_i, r_c, t)), so results are bit-identical whichever
+// kernel runs an env.
+// B columns of the rank-one update for the two rows a lane owns: all loads, then the fmas, then the stores.  The pivot
+// row is not stored here (s0 / s1 exclude it): the lanes that formed r_c wrote it already.
+template <int B>
+static __device__ __forceinline__ void lemke_update_batch(double* q0, double* q1, const double* rvec, int c, int n, double nd0, double nd1, bool s0, bool s1) {
+  double rv[B], t0[B], t1[B];
+  const int cn = c * n;
+#pragma unroll
+  for (int k = 0; k < B; k++) { rv[k] = rvec[c + k]; t0[k] = q0[cn + k * n]; t1[k] = q1[cn + k * n]; }
+#pragma unroll
+  for (int k = 0; k < B; k++) { t0[k] = fma(nd0, rv[k], t0[k]); t1[k] = fma(nd1, rv[k], t1[k]); }
+#pragma unroll
+  for (int k = 0; k < B; k++) { if (s0) q0[cn + k * n] = t0[k]; if (s1) q1[cn + k * n] = t1[k]; }
+}
+
+// N > 0: the LCP dimension is a compile-time constant (the sizes contact sets give: 8 or 10 rows per contact), so every
+// tableau address of the update is base + immediate and the column walk is fully unrolled; N == 0: any n <= 64.
+template <bool SH, int N>
+static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
+                                                   int* log, int log_cap, int& nlog_io, int& piv_io, int& executed_io, int* budget) {
+  if (SH) { __builtin_assume(__isShared(T)); __builtin_assume(__isShared(rvec)); __builtin_assume(__isShared(where)); __builtin_assume(__isShared(bas)); }
+  const int n = N ? N : n_rt;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int t = 2 * n, MAXITER = min(1000, 50 * n), NC = n + 2;
+  const int i0 = lane, i1 = lane + 32;
+  const bool h0 = i0 < n, h1 = i1 < n;
+  const int j0 = h0 ? i0 : 0, j1 = h1 ? i1 : j0;      // always-valid row indices: a lane without a row recomputes a valid element and does not store it
+  double* const xcol = T + n * (n + 1);
+  double* const q0 = T + j0;
+  double* const q1 = T + j1;
+  int s = n, entering = t, status = LCP_OK;
+  int nlog = nlog_io, piv = piv_io, executed = executed_io, bud = budget ? *budget : 0;   // in registers for the loop (the references live on the stack)
+  bool first = true;
+  for (;;) {
+    const double d0 = q0[s * n], d1 = q1[s * n];      // entering column, my rows
+    if (!first) {
+      executed++;
+      const double x0 = xcol[j0], x1 = xcol[j1];
+      const bool c0 = h0 && d0 > PIV_TOL, c1 = h1 && d1 > PIV_TOL;
+      const double a0 = c0 ? (x0 + zero_tol) / d0 : B2M_INF, a1 = c1 ? (x1 + zero_tol) / d1 : B2M_INF;
+      const double b0 = c0 ? x0 / d0 : B2M_INF, b1 = c1 ? x1 / d1 : B2M_INF;
+      const double theta = b2m_warp_min(fmin(a0, a1));
+      if (theta == B2M_INF) { status = LCP_RAY; break; }
+      const int trow = -(where[t] + 1);
+      int lo = 0x7fffffff;
+      if (c0 && b0 <= theta) lo = (i0 == trow) ? -1 : i0;
+      if (c1 && b1 <= theta) { const int key = (i1 == trow) ? -1 : i1; if (key < lo) lo = key; }
+      lo = __reduce_min_sync(FULL, lo);
+      if (lo == 0x7fffffff) { status = LCP_EMPTY_RATIO; break; }
+      r = (lo < 0) ? trow : lo;
+    }
+    const int leaving = bas[r];
+    const double p = __shfl_sync(FULL, (r < 32) ? d0 : d1, r & 31);
+    const bool s0 = h0 && i0 != r, s1 = h1 && i1 != r;      // rows this lane stores in the update: its own, except the pivot row
+    __syncwarp();                               // everyone has read bas / where / column s before they change
+    // pivot row, scaled: lane c forms r_c and writes it both to rvec and into row r of the tableau (its final value)
+    for (int c = lane; c < NC; c += 32) { const double rv = (c == s) ? 1.0 / p : T[c * n + r] / p; rvec[c] = rv; T[c * n + r] = rv; }
+    if (s0) q0[s * n] = 0.0;                    // the leaving variable's column (a unit vector while basic) replaces slot s: starts from zero
+    if (s1) q1[s * n] = 0.0;
+    if (lane == 0) {
+      if (log && nlog < log_cap) log[nlog] = leaving;
+      where[entering] = -(r + 1); where[leaving] = s; bas[r] = entering;
+    }
+    nlog++;
+    __syncwarp();
+    const double nd0 = -d0, nd1 = -d1;
+    if (N) {
+#pragma unroll
+      for (int c = 0; c + 8 <= N + 2; c += 8) lemke_update_batch<8>(q0, q1, rvec, c, N, nd0, nd1, s0, s1);
+      if ((N + 2) & 4) lemke_update_batch<4>(q0, q1, rvec, (N + 2) & ~7, N, nd0, nd1, s0, s1);
+      if ((N + 2) & 2) lemke_update_batch<2>(q0, q1, rvec, (N + 2) & ~3, N, nd0, nd1, s0, s1);
+      if ((N + 2) & 1) lemke_update_batch<1>(q0, q1, rvec, (N + 2) & ~1, N, nd0, nd1, s0, s1);
+    } else {
+      int c = 0;
+      for (; c + 8 <= NC; c += 8) lemke_update_batch<8>(q0, q1, rvec, c, n, nd0, nd1, s0, s1);   // straight-line batches
+      if (NC & 4) { lemke_update_batch<4>(q0, q1, rvec, c, n, nd0, nd1, s0, s1); c += 4; }
+      if (NC & 2) { lemke_update_batch<2>(q0, q1, rvec, c, n, nd0, nd1, s0, s1); c += 2; }
+      if (NC & 1) lemke_update_batch<1>(q0, q1, rvec, c, n, nd0, nd1, s0, s1);
+    }
+    __syncwarp();
+    if (!first) piv++;
+    if (budget && --bud < 0) { status = LCP_DEFER; break; }
+    first = false;
+    if (leaving == t) break;
+    if (piv >= MAXITER) { status = LCP_MAXITER; break; }
+    entering = (leaving < n) ? n + leaving : leaving - n;
+    s = where[entering];
+  }
+  nlog_io = nlog; piv_io = piv; executed_io = executed; if (budget) *budget = bud;
+  return status;
+}
+template <bool SH>
+static __device__ __forceinline__ int lemke_loop_warp_n(int n, double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
+                                                        int* log, int log_cap, int& nlog, int& piv, int& executed, int* budget) {
+  switch (n) {
+    case 40: return lemke_loop_warp<SH, 40>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    case 32: return lemke_loop_warp<SH, 32>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    case 30: return lemke_loop_warp<SH, 30>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    case 24: return lemke_loop_warp<SH, 24>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    case 20: return lemke_loop_warp<SH, 20>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    case 16: return lemke_loop_warp<SH, 16>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    default: return lemke_loop_warp<SH, 0>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+  }
+}
+#endif
+
 // No cycle detection: LCP.cpp has no anti-cycling rule (:926-928) and on degenerate problems the pivoting can circle until
 // the iteration cap (:548,789).  Round 1 cut such runs short when an (ordered basis, entering variable) pair recurred.
 // That is a proof of periodicity only in exact arithmetic: the reference re-solves the entering column with a fresh LU
@@ -122,7 +240,17 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
   int entering = t;
   bool first = true;   // the first pass pivots the artificial variable in (LCP.cpp:776-785); `piv` counts the pivots after it
   int executed = 0;
-  for (;;) {
+  bool handled = false;
+#ifdef __CUDACC__
+  if constexpr (G::size == 32) {
+    if (n <= 64) {
+      status = __isShared(T) ? lemke_loop_warp_n<true>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget)
+                             : lemke_loop_warp<false, 0>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+      handled = true;
+    }
+  }
+#endif
+  while (!handled) {
     // entering column
     for (int i = g.tid; i < n; i += G::size) dvec[i] = T[(size_t)s * n + i];
     g.sync();
@@ -197,9 +325,86 @@ B2M_HD inline size_t fast_work_doubles(int n) { return (size_t)n * n + 2 * (size
 #define B2M_FAST_HIST 16   /* basis sets remembered by lcp_fast's cycle detector */
 B2M_HD inline size_t fast_work_ints(int n) { return (size_t)2 * n + 2 + (size_t)(B2M_FAST_HIST + 1) * ((n + 31) / 32); }
 
+#ifdef __CUDACC__
+// Warp-owned LU solve (k <= 64): lane l owns rows l and l + 32 of A and keeps its entries of b in registers; the pivot
+// search is one redux, the right-hand side travels by shuffle, the trailing update of a row walks the columns in
+// straight-line batches of eight (all loads of a batch before the first fma, no guard inside, clamped indices).  Same
+// operations on every element, in the same order, as the generic routine below (and as the oracle's solve_fast):
+// bit-identical results.
+template <int B>
+static __device__ __forceinline__ void lu_update_batch(double* q0, double* q1, const double* pr, int c, int k, double nl0, double nl1, bool u0, bool u1) {
+  double rv[B], a0[B], a1[B];
+  const int ck = c * k;
+#pragma unroll
+  for (int q = 0; q < B; q++) { rv[q] = pr[ck + q * k]; a0[q] = q0[ck + q * k]; a1[q] = q1[ck + q * k]; }
+#pragma unroll
+  for (int q = 0; q < B; q++) { a0[q] = fma(nl0, rv[q], a0[q]); a1[q] = fma(nl1, rv[q], a1[q]); }
+#pragma unroll
+  for (int q = 0; q < B; q++) { if (u0) q0[ck + q * k] = a0[q]; if (u1) q1[ck + q * k] = a1[q]; }
+}
+template <bool SH>
+static __device__ __noinline__ bool lu_solve_warp(int k, double* A, double* b) {
+  if (SH) { __builtin_assume(__isShared(A)); __builtin_assume(__isShared(b)); }
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int i0 = lane, i1 = lane + 32;
+  const bool h0 = i0 < k, h1 = i1 < k;
+  const int j0 = h0 ? i0 : 0, j1 = h1 ? i1 : j0;            // always-valid row indices
+  double* const q0 = A + j0;
+  double* const q1 = A + j1;
+  double b0 = b[j0], b1 = b[j1];
+  for (int j = 0; j < k; j++) {
+    double key = 1.0; int p = 0x7fffffff;                       // lexicographic min of (-|a|, i) == first maximum
+    { const double v0 = -fabs(q0[j * k]), v1 = -fabs(q1[j * k]);
+      if (h0 && i0 >= j && v0 < key) { key = v0; p = i0; }
+      if (h1 && i1 >= j && v1 < key) { key = v1; p = i1; } }
+    b2m_warp_min_key_idx(key, p);
+    if (key == 0.0 || p == 0x7fffffff) return false;
+    if (p != j) {
+      for (int c = lane; c < k; c += 32) { const double tmp = A[c * k + j]; A[c * k + j] = A[c * k + p]; A[c * k + p] = tmp; }
+      const double vj = __shfl_sync(FULL, (j < 32) ? b0 : b1, j & 31), vp = __shfl_sync(FULL, (p < 32) ? b0 : b1, p & 31);
+      if (i0 == j) b0 = vp; else if (i0 == p) b0 = vj;
+      if (i1 == j) b1 = vp; else if (i1 == p) b1 = vj;
+    }
+    __syncwarp();
+    const double rinv = 1.0 / A[j * k + j];
+    const double bj = __shfl_sync(FULL, (j < 32) ? b0 : b1, j & 31);
+    const bool u0 = h0 && i0 > j, u1 = h1 && i1 > j;
+    const double l0 = q0[j * k] * rinv, l1 = q1[j * k] * rinv;
+    if (u0) { q0[j * k] = l0; b0 = fma(-l0, bj, b0); }
+    if (u1) { q1[j * k] = l1; b1 = fma(-l1, bj, b1); }
+    const double nl0 = -l0, nl1 = -l1;
+    const double* const pr = A + j;                             // pivot row
+    int c = j + 1;
+    const int rem = k - c;
+    for (; c + 8 <= k; c += 8) lu_update_batch<8>(q0, q1, pr, c, k, nl0, nl1, u0, u1);
+    if (rem & 4) { lu_update_batch<4>(q0, q1, pr, c, k, nl0, nl1, u0, u1); c += 4; }
+    if (rem & 2) { lu_update_batch<2>(q0, q1, pr, c, k, nl0, nl1, u0, u1); c += 2; }
+    if (rem & 1) lu_update_batch<1>(q0, q1, pr, c, k, nl0, nl1, u0, u1);
+    __syncwarp();
+  }
+  // column-oriented back substitution; the diagonal is read once, x_c = b_c / u_cc travels by shuffle
+  const double dg0 = q0[j0 * k], dg1 = q1[j1 * k];
+  for (int c = k - 1; c >= 0; c--) {
+    const double a0 = q0[c * k], a1 = q1[c * k];                // independent of the running x: issued ahead of the shuffle / divide chain
+    const double bc = __shfl_sync(FULL, (c < 32) ? b0 : b1, c & 31), dc = __shfl_sync(FULL, (c < 32) ? dg0 : dg1, c & 31);
+    const double xc = bc / dc;
+    if (i0 == c) b0 = xc; else if (h0 && i0 < c) b0 = fma(-a0, xc, b0);
+    if (i1 == c) b1 = xc; else if (h1 && i1 < c) b1 = fma(-a1, xc, b1);
+  }
+  if (h0) b[i0] = b0;
+  if (h1) b[i1] = b1;
+  __syncwarp();
+  return true;
+}
+#endif
+
 // solves A x = b (A k x k column-major ld k, destroyed; b <- x).  Returns false on an exactly zero pivot.
 template <class G>
 B2M_DEV B2M_NOINL bool lu_solve(const G& g, int k, double* A, double* b) {
+#ifdef __CUDACC__
+  if constexpr (G::size == 32) { if (k <= 64) return __isShared(A) ? lu_solve_warp<true>(k, A, b) : lu_solve_warp<false>(k, A, b); }
+#endif
   for (int j = 0; j < k; j++) {
     double key = 1.0; int p = 0x7fffffff;                       // lexicographic min of (-|a|, i) == first maximum
     for (int i = j + g.tid; i < k; i += G::size) { const double v = -fabs(A[(size_t)j * k + i]); if (v < key) { key = v; p = i; } }
@@ -297,14 +502,24 @@ B2M_DEV B2M_NOINL int lcp_fast_solve(const G& g, int n, const double* M, int ldm
     }
     executed++;
     const int k = cnt[0], nb = cnt[1];
+    if (G::size == 32 && k <= 64) {                                                    // a warp fills the rows it owns: no integer division
+      const double* __restrict__ Mr = M; const int* __restrict__ nbp = nonbas; double* __restrict__ Ar = A;
+      for (int r = g.tid; r < k; r += G::size) {
+        const int nr = nbp[r];
+#pragma unroll 4
+        for (int c = 0; c < k; c++) Ar[c * k + r] = m_at(Mr, ldm, nr, nbp[c], lambda);
+      }
+    } else
     for (int e = g.tid; e < k * k; e += G::size) { const int c = e / k, r = e - c * k; A[e] = m_at(M, ldm, nonbas[r], nonbas[c], lambda); }   // :111
     for (int i = g.tid; i < k; i += G::size) zz[i] = -q[nonbas[i]];                  // :113-115
     g.sync();
     if (!lu_solve(g, k, A, zz)) { status = LCP_SINGULAR; break; }                    // :118-126
     for (int i = g.tid; i < nb; i += G::size) {                                      // :129
       const int bi = bas[i];
+      const double* __restrict__ Mr = M; const int* __restrict__ nbp = nonbas; const double* __restrict__ zr = zz;
       double sacc = 0.0;
-      for (int c = 0; c < k; c++) sacc = fma(M[(size_t)nonbas[c] * ldm + bi], zz[c], sacc);
+#pragma unroll 4
+      for (int c = 0; c < k; c++) sacc = fma(Mr[(size_t)nbp[c] * ldm + bi], zr[c], sacc);
       w[i] = sacc + q[bi];
     }
     g.sync();

@@ -16,7 +16,7 @@ namespace b2m {
 
 enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3 };
 enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LEMKE_CALLS, CNT_PIVOTS, CNT_LCP_FAIL,
-       CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_CA_ITERS, CNT_COUNT };
+       CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_CA_ITERS, CNT_STAB_ITERS, CNT_STAB_SOLVES, CNT_STAB_LSFAIL, CNT_COUNT };
 #define B2M_NKMAX 64
 #define B2M_MAX_CLASSES 12
 // queue slots of one round: [0, n_classes) impact classes, then the envs that still have time left in their step, then stragglers
@@ -61,6 +61,7 @@ struct SimParams {
   const double* mu_c; const double* mu_v; const double* eps; const double* compliance; const int* NK;
   const double* fr_tab;        // [4][B2M_NKMAX+1][B2M_NKMAX/2]: QP cos, QP sin, AP cos, AP sin (host libm values)
   double gx, gy, gz, contact_dist_thresh, min_step_size;
+  int stab_max_iterations; double stab_eps;   // ConstraintStabilization::max_iterations (0 off, < 0 unlimited) and eps (stab_device.cuh)
   const double* min_step_env;   // optional [env]
   double* q; double* v; double* time; double* zlast; int* zlast_n;
   double* vlast; int* vlast_n;     // [cmax][env], [env]: solution / warm start of the no-slip LCP (ImpactConstraintHandler::_v)
@@ -1457,6 +1458,69 @@ B2M_DEV void apply_no_slip_to_connected(const G& g, const SimParams& P, int e, E
   }
 }
 
+// Islands (UnilateralConstraint.cpp:940-1194) with the canonical order of rule H4: seeds in ascending body index,
+// neighbours in contact (edge insertion) order, each visited body picks up its remaining contacts in list order.
+// only_active: keep the islands that hold an impacting constraint (remove_inactive_groups :1197-1225); the mask of kept
+// islands goes to scal[S_FLAG].  Executed by ONE thread.
+B2M_HD B2M_NOINL inline void build_islands(const SimParams& P, EnvMem& m, int ncon, bool only_active) {
+  const int nb = P.nb;
+  unsigned nodes = 0;
+  for (int c = 0; c < ncon; c++) { if (m.ben[m.cb1[c]]) nodes |= 1u << super_of(P, m.cb1[c]); if (m.ben[m.cb2[c]]) nodes |= 1u << super_of(P, m.cb2[c]); }
+  for (int b = 0; b < nb; b++) m.bisl[b] = -1;
+  for (int c = 0; c < ncon; c++) m.cisl[c] = -1;
+  int nisl = 0, nord = 0;
+  unsigned active = 0;
+  int queue[B200MOBY_MAX_BODIES];
+  while (nodes) {
+    int node = 0; while (!((nodes >> node) & 1u)) node++;
+    int qh = 0, qt = 0; unsigned processed = 0, queued = 1u << node;
+    queue[qt++] = node;
+    m.isl_start[nisl] = nord;
+    while (qh < qt) {
+      node = queue[qh++];
+      nodes &= ~(1u << node);
+      processed |= 1u << node;
+      m.bisl[node] = nisl;
+      for (int c = 0; c < ncon; c++) {
+        if (!(m.ben[m.cb1[c]] && m.ben[m.cb2[c]])) continue;
+        const int b1 = super_of(P, m.cb1[c]), b2 = super_of(P, m.cb2[c]);
+        const int nbr = (b1 == node) ? b2 : ((b2 == node) ? b1 : -1);
+        if (nbr >= 0 && !((queued >> nbr) & 1u)) { queued |= 1u << nbr; queue[qt++] = nbr; }
+      }
+      for (int c = 0; c < ncon; c++)
+        if (m.cisl[c] < 0 && ((m.ben[m.cb1[c]] && super_of(P, m.cb1[c]) == node) || (m.ben[m.cb2[c]] && super_of(P, m.cb2[c]) == node))) { m.cisl[c] = nisl; m.corder[nord++] = c; }
+    }
+    nisl++;
+  }
+  m.isl_start[nisl] = nord;
+  if (only_active) { for (int c = 0; c < ncon; c++) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) active |= 1u << m.cisl[c]; }
+  else active = (nisl >= 32) ? 0xffffffffu : ((1u << nisl) - 1u);
+  m.scal[S_NISL] = nisl;
+  m.scal[S_FLAG] = (int)active;
+}
+
+// contacts, generalized-coordinate offsets and counts of island k (after build_islands).  Executed by ONE thread.
+B2M_HD B2M_NOINL inline void select_island(const SimParams& P, EnvMem& m, int k) {
+  const int nb = P.nb;
+  const int s0 = m.isl_start[k], nc = m.isl_start[k + 1] - s0;
+  for (int i = 0; i < nc; i++) m.icon[i] = m.corder[s0 + i];
+  int gc = 0;
+  for (int b = 0; b < nb; b++) {
+    if (is_link(P, b)) {                      // every moving link shares the articulated body's coordinates
+      const int rep = P.rc_first + 1;
+      if (b == rep) {
+        if (m.bisl[rep] == k) { m.gcoff[b] = gc; for (int l = 0; l < P.rc_links - 1; l++) { m.gcb[gc + l] = rep; m.gcl[gc + l] = l; } gc += P.rc_links - 1; }
+        else m.gcoff[b] = -1;
+      } else m.gcoff[b] = m.gcoff[rep];
+    } else if (m.bisl[b] == k && m.ben[b]) {
+      m.gcoff[b] = gc;
+      if (B2M_NGC(P)) for (int l = 0; l < 6; l++) { m.gcb[gc + l] = b; m.gcl[gc + l] = l; }
+      gc += 6;
+    } else m.gcoff[b] = -1;
+  }
+  m.scal[S_NC] = nc; m.scal[S_NGC] = gc;
+}
+
 // calc_impacting_unilateral_constraint_forces (ConstraintSimulator.cpp:298-355) -> apply_model (ImpactConstraintHandler.cpp:96-168)
 template <class G>
 B2M_DEV B2M_NOINL bool process_constraints(const G& g, const SimParams& P, int e, EnvMem& m, unsigned long long* lc, EnvCtx& cx) {
@@ -1466,67 +1530,14 @@ B2M_DEV B2M_NOINL bool process_constraints(const G& g, const SimParams& P, int e
   for (int c = g.tid; c < ncon; c += G::size) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) impacting = true;
   if (!g.any(impacting)) return true;
   B2M_PROF_T0(m);
-  // islands (UnilateralConstraint.cpp:940-1194) with the canonical order of rule H4: seeds in ascending body index,
-  // neighbours in contact (edge insertion) order, each visited body picks up its remaining contacts in list order.
-  if (g.tid == 0) {
-    unsigned nodes = 0;
-    for (int c = 0; c < ncon; c++) { if (m.ben[m.cb1[c]]) nodes |= 1u << super_of(P, m.cb1[c]); if (m.ben[m.cb2[c]]) nodes |= 1u << super_of(P, m.cb2[c]); }
-    for (int b = 0; b < nb; b++) m.bisl[b] = -1;
-    for (int c = 0; c < ncon; c++) m.cisl[c] = -1;
-    int nisl = 0, nord = 0;
-    unsigned active = 0;
-    int queue[B200MOBY_MAX_BODIES];
-    while (nodes) {
-      int node = 0; while (!((nodes >> node) & 1u)) node++;
-      int qh = 0, qt = 0; unsigned processed = 0, queued = 1u << node;
-      queue[qt++] = node;
-      m.isl_start[nisl] = nord;
-      while (qh < qt) {
-        node = queue[qh++];
-        nodes &= ~(1u << node);
-        processed |= 1u << node;
-        m.bisl[node] = nisl;
-        for (int c = 0; c < ncon; c++) {
-          if (!(m.ben[m.cb1[c]] && m.ben[m.cb2[c]])) continue;
-          const int b1 = super_of(P, m.cb1[c]), b2 = super_of(P, m.cb2[c]);
-          const int nbr = (b1 == node) ? b2 : ((b2 == node) ? b1 : -1);
-          if (nbr >= 0 && !((queued >> nbr) & 1u)) { queued |= 1u << nbr; queue[qt++] = nbr; }
-        }
-        for (int c = 0; c < ncon; c++)
-          if (m.cisl[c] < 0 && ((m.ben[m.cb1[c]] && super_of(P, m.cb1[c]) == node) || (m.ben[m.cb2[c]] && super_of(P, m.cb2[c]) == node))) { m.cisl[c] = nisl; m.corder[nord++] = c; }
-      }
-      nisl++;
-    }
-    m.isl_start[nisl] = nord;
-    for (int c = 0; c < ncon; c++) if (constraint_vel(m, c) < -B2M_NEAR_ZERO) active |= 1u << m.cisl[c];   // remove_inactive_groups :1197-1225
-    m.scal[S_NISL] = nisl;
-    m.scal[S_FLAG] = (int)active;
-  }
+  if (g.tid == 0) build_islands(P, m, ncon, true);
   g.sync();
   B2M_PROF_ADD(m, g, PH_ISLANDS);
   const int nisl = m.scal[S_NISL];
   const unsigned active = (unsigned)m.scal[S_FLAG];
   for (int k = 0; k < nisl; k++) {
     if (!((active >> k) & 1u)) continue;
-    if (g.tid == 0) {
-      const int s0 = m.isl_start[k], nc = m.isl_start[k + 1] - s0;
-      for (int i = 0; i < nc; i++) m.icon[i] = m.corder[s0 + i];
-      int gc = 0;
-      for (int b = 0; b < nb; b++) {
-        if (is_link(P, b)) {                      // every moving link shares the articulated body's coordinates
-          const int rep = P.rc_first + 1;
-          if (b == rep) {
-            if (m.bisl[rep] == k) { m.gcoff[b] = gc; for (int l = 0; l < P.rc_links - 1; l++) { m.gcb[gc + l] = rep; m.gcl[gc + l] = l; } gc += P.rc_links - 1; }
-            else m.gcoff[b] = -1;
-          } else m.gcoff[b] = m.gcoff[rep];
-        } else if (m.bisl[b] == k && m.ben[b]) {
-          m.gcoff[b] = gc;
-          if (B2M_NGC(P)) for (int l = 0; l < 6; l++) { m.gcb[gc + l] = b; m.gcl[gc + l] = l; }
-          gc += 6;
-        } else m.gcoff[b] = -1;
-      }
-      m.scal[S_NC] = nc; m.scal[S_NGC] = gc;
-    }
+    if (g.tid == 0) select_island(P, m, k);
     g.sync();
     { B2M_PROF_T0(m); compute_problem_data(g, P, m); B2M_PROF_ADD(m, g, PH_PROBLEM); }
     if (g.tid == 0) {   // F_delassus = 2 (3nc) 36 b + 2 (3nc)^2 6, F_apply = 2 NGC 3nc
@@ -1767,5 +1778,7 @@ B2M_DEV void env_finish(const G& g, const SimParams& P, int e, EnvMem& m, double
   if (g.tid == 0) P.time[e] = t;
   g.sync();
 }
+
+#include "stab_device.cuh"
 
 }  // namespace b2m

@@ -46,6 +46,8 @@ struct b200moby_sim {
   int fin_grid = 1;
   ClassPlan finblock;        // nmax > B200MOBY_BIG_N: the finish phase runs one 256-thread block per env (threads == 256 when in use)
   bool any_thread_class = false;
+  // constraint stabilization phase (k_stabilize.cu): thread-per-env variant, or -1 = warp per env over `stab_scratch`
+  int stab_variant = -1, stab_grid = 1; double* stab_scratch = nullptr; size_t stab_stride = 0, stab_nd_env = 0, stab_nd_all = 0;
   bool fused = false;        // B200MOBY_FUSED=1: the single fused warp-per-env kernel (kept for comparison)
   long long launches = 0;
   // the impact classes of one round touch disjoint envs: they run on side streams so that the tail of one class
@@ -276,7 +278,7 @@ b200moby_status plan_launch(b200moby_sim* h) {
     ClassPlan& sg = h->straggler;
     // stragglers and the hard queue want the shortest latency per pivot for one env: measured on configs[1] (n <= 40),
     // the worst env's chain takes 16 ms on a lone warp and 6.7 ms on a 256-thread block
-    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : 128);   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
+    sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : (h->nmax <= 64 ? 32 : 128));   // n <= 64: the warp-owned pivot loops (lcp_device.cuh), no block barriers   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
     if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
     if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
     // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished
@@ -287,6 +289,22 @@ b200moby_status plan_launch(b200moby_sim* h) {
       fb.nmax = h->nmax; fb.cmax = h->cmax; fb.threads = 256;
       if ((st = plan_memory(h, b2m_k_finish_block256(), fb, 1, ne)) != B200MOBY_OK) return st;
       h->rounds = std::max(1, std::min(B2M_ROUNDS_MAX, env_int("B200MOBY_ROUNDS", 4)));
+    }
+  }
+  if (h->P.stab_max_iterations != 0) {
+    SimParams Ps = h->P; Ps.nmax = Ps.cmax;                   // the stabilization LCP has one row per contact
+    const EnvDims Ds = env_dims(Ps);
+    const size_t nd = env_doubles(Ds), ni = env_ints(Ds), xd = stab_extra_doubles(Ds), xi = stab_extra_ints(Ds);
+    h->stab_nd_env = nd; h->stab_nd_all = (nd + xd + 1) & ~(size_t)1;
+    const bool thr = env_int("B200MOBY_STAB_THREAD", 1) != 0;
+    if (thr && nd + xd <= B2M_STAB_ND0 && ni + xi <= B2M_STAB_NI0) h->stab_variant = 0;
+    else if (thr && nd + xd <= B2M_STAB_ND1 && ni + xi <= B2M_STAB_NI1) h->stab_variant = 1;
+    else {
+      h->stab_variant = -1;
+      h->stab_grid = std::max(1, std::min((ne + 3) / 4, sms * 8));
+      h->stab_stride = h->stab_nd_all + (ni + xi + 1) / 2;
+      B2M_CUDA(cudaMalloc((void**)&h->stab_scratch, h->stab_stride * (size_t)h->stab_grid * 4 * sizeof(double)));
+      h->allocs.push_back(h->stab_scratch);
     }
   }
   return B200MOBY_OK;
@@ -304,6 +322,21 @@ b200moby_status timed_launch(b200moby_sim* h, int kslot, const void* kernel, dim
   if (h->ktiming) { B2M_CUDA(cudaEventRecord(ev.second, s)); h->kev_pending.push_back(std::make_pair(kslot, ev)); }
   h->launches++;
   return B200MOBY_OK;
+}
+
+// ConstraintStabilization::stabilize for every env (TimeSteppingSimulator.cpp:95-98), after the step's last kernel
+b200moby_status launch_stabilize(b200moby_sim* h, cudaStream_t s) {
+  if (h->P.stab_max_iterations == 0) return B200MOBY_OK;
+  const int ncls = (int)h->classes.size();
+  SimParams Ps = h->P; Ps.nmax = Ps.cmax; Ps.kslot = 4 + ncls;
+  if (h->stab_variant >= 0) {
+    void* a[] = {&Ps};
+    const int blocks = std::max(1, std::min((h->n_envs + 127) / 128, h->sms * 16));
+    return timed_launch(h, 4 + ncls, b2m_k_stabilize_thread(h->stab_variant), dim3(blocks), dim3(128), a, 0, s);
+  }
+  Ps.gscratch = h->stab_scratch; Ps.gstride = h->stab_stride;
+  void* a[] = {&Ps, &h->stab_nd_env, &h->stab_nd_all};
+  return timed_launch(h, 4 + ncls, b2m_k_stabilize_warp(), dim3(h->stab_grid), dim3(128), a, 0, s);
 }
 
 // One TimeSteppingSimulator::step for every env: advance, then per round the impact classes, stragglers and the
@@ -369,6 +402,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       Pf.gscratch = h->finblock.gscratch; Pf.gstride = h->finblock.gstride;
       if ((st = timed_launch(h, 2 + ncls, b2m_k_finish_block256(), dim3(h->finblock.grid), dim3(256), a, h->finblock.shmem, s)) != B200MOBY_OK) return st;
     } else if ((st = timed_launch(h, 2 + ncls, b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)) != B200MOBY_OK) return st; }
+  if ((st = launch_stabilize(h, s)) != B200MOBY_OK) return st;
   B2M_CUDA(cudaGetLastError());
   return B200MOBY_OK;
 }
@@ -381,7 +415,6 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   if (!d || !out) return b2m_fail(B200MOBY_ERR_INVALID, "null descriptor");
   if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
   if (d->n_envs <= 0 || d->n_bodies <= 0 || d->n_bodies > B200MOBY_MAX_BODIES) return b2m_fail(B200MOBY_ERR_INVALID, "n_envs > 0 and 0 < n_bodies <= %d required", B200MOBY_MAX_BODIES);
-  if (d->stabilization_max_iterations != 0) return b2m_fail(B200MOBY_ERR_UNSUPPORTED, "constraint stabilization is not on the accelerated path: set constraint-stabilization-max-iterations=0");
   B2M_CUDA(cudaSetDevice(device));
   const int ne = d->n_envs, nb = d->n_bodies;
   // validate and size
@@ -408,6 +441,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_copy(h, tab.data(), tab.size(), &P.fr_tab));
   P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
   P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size;
+  P.stab_max_iterations = d->stabilization_max_iterations; P.stab_eps = B2M_NEAR_ZERO;   // ConstraintStabilization.cpp:53-59 (rule H7)
   if (d->min_step_size_env) TRY(dev_copy(h, d->min_step_size_env, (size_t)ne, &P.min_step_env));
   TRY(dev_zero(h, (size_t)nb * 7 * ne, &P.q));
   TRY(dev_zero(h, (size_t)nb * 6 * ne, &P.v));
@@ -417,7 +451,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)h->cmax * ne, &P.vlast));
   TRY(dev_zero(h, (size_t)ne, &P.vlast_n));
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
-  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 5), &P.kstat));
+  TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 6), &P.kstat));
   TRY(dev_zero(h, (size_t)ne, &P.cost));
   P.hard_cost = env_int("B200MOBY_HARD_COST", 12);
   P.cost_shift = std::max(0, std::min(30, env_int("B200MOBY_COST_DECAY_SHIFT", 2)));
@@ -583,10 +617,16 @@ b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* s
   if (n_steps == 0) return B200MOBY_OK;
   B2M_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->fused) {
-    void* a[] = {&h->P, &dt, &n_steps, &h->env_d};
-    B2M_CUDA(cudaLaunchKernel(b2m_k_step_warp(), dim3(h->grid), dim3(32), a, h->shmem, s));
-    h->launches++;
+  if (h->fused) {   // comparison path: the whole mini-step loop of n_steps steps in one launch (one step per launch when stabilization is on)
+    const int per = h->P.stab_max_iterations != 0 ? 1 : n_steps;
+    for (int k = 0; k < n_steps; k += per) {
+      int cnt = per;
+      void* a[] = {&h->P, &dt, &cnt, &h->env_d};
+      B2M_CUDA(cudaLaunchKernel(b2m_k_step_warp(), dim3(h->grid), dim3(32), a, h->shmem, s));
+      h->launches++;
+      b200moby_status st = launch_stabilize(h, s);
+      if (st != B200MOBY_OK) return st;
+    }
     return B200MOBY_OK;
   }
   for (int k = 0; k < n_steps; k++) {
@@ -611,6 +651,7 @@ b200moby_status b200moby_get_counters(b200moby_handle h, b200moby_counters* out)
   out->lcp_fast_calls = c[CNT_FAST_CALLS]; out->lemke_calls = c[CNT_LEMKE_CALLS]; out->pivots = c[CNT_PIVOTS];
   out->lcp_failures = c[CNT_LCP_FAIL] + c[CNT_OVERFLOW]; out->impact_tol_events = c[CNT_IMPACT_TOL]; out->contacts = c[CNT_CONTACTS];
   out->max_lcp_n = c[CNT_MAX_N]; out->pivot_flops = c[CNT_PIVOT_FLOPS]; out->assembly_flops = c[CNT_ASM_FLOPS]; out->ca_iterations = c[CNT_CA_ITERS];
+  out->stab_iterations = c[CNT_STAB_ITERS]; out->stab_lcp_solves = c[CNT_STAB_SOLVES]; out->stab_line_search_failures = c[CNT_STAB_LSFAIL];
   return B200MOBY_OK;
 }
 b200moby_status b200moby_get_launch_count(b200moby_handle h, long long* out) {
@@ -659,7 +700,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   if (!h) return b2m_fail(B200MOBY_ERR_INVALID, "null handle");
   B2M_CUDA(cudaSetDevice(h->device));
   B2M_CUDA(cudaDeviceSynchronize());
-  const int ncls = (int)h->classes.size(), nk = ncls + 4;
+  const int ncls = (int)h->classes.size(), nk = ncls + 5;
   h->kms.resize(nk, 0.0); h->klaunches.resize(nk, 0);
   for (auto& pe : h->kev_pending) {
     float ms = 0.f;
@@ -669,7 +710,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   h->kev_pending.clear();
   if (out) {
     memset(out, 0, sizeof(*out));
-    unsigned long long ks[3 * (B2M_MAX_CLASSES + 5)];
+    unsigned long long ks[3 * (B2M_MAX_CLASSES + 6)];
     B2M_CUDA(cudaMemcpy(ks, h->P.kstat, sizeof(ks), cudaMemcpyDeviceToHost));
     out->n_kernels = nk;
     for (int k = 0; k < nk && k < B200MOBY_MAX_KERNELS; k++) {
@@ -677,6 +718,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
       if (k == 0) snprintf(o.name, sizeof(o.name), "advance_kernel");
       else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 1) snprintf(o.name, sizeof(o.name), "impact_thread_kernel[n<=%d]", c.nmax); else if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
       else if (k == ncls + 1 || k == ncls + 3) { if (h->straggler.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[%s]", k == ncls + 1 ? "stragglers" : "hard queue"); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[%s]", h->straggler.threads, k == ncls + 1 ? "stragglers" : "hard queue"); o.lcp_nmax = h->nmax; o.threads_per_env = h->straggler.threads; }
+      else if (k == ncls + 4) { snprintf(o.name, sizeof(o.name), h->stab_variant >= 0 ? "stabilize_thread_kernel" : "stabilize_warp_kernel"); o.threads_per_env = h->stab_variant >= 0 ? 1 : 32; }
       else snprintf(o.name, sizeof(o.name), h->finblock.threads == 256 ? "finish_block_kernel<256>" : "finish_kernel");
       if (k == 0 || k == ncls + 2) o.threads_per_env = 32;
       o.ms = h->kms[k]; o.launches = h->klaunches[k];
@@ -685,7 +727,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
   }
   if (reset) {
     std::fill(h->kms.begin(), h->kms.end(), 0.0); std::fill(h->klaunches.begin(), h->klaunches.end(), 0);
-    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 5)));
+    B2M_CUDA(cudaMemset(h->P.kstat, 0, sizeof(unsigned long long) * 3 * (B2M_MAX_CLASSES + 6)));
   }
   h->ktiming = enable != 0;
   return B200MOBY_OK;

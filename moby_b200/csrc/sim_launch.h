@@ -19,3 +19,10 @@ const void* b2m_k_finish_block256();      // (SimParams P, double dt, int round)
 const void* b2m_k_rc_fwd_dyn();           // (SimParams P, int algo, const double* jq, const double* jqd, const double* tau, double* qdd)
 const void* b2m_k_rc_inertia();           // (SimParams P, const double* jq, double* H)
 const void* b2m_k_rc_refresh();           // (SimParams P)
+// constraint stabilization: thread per env with a local working set of up to B2M_STAB_ND<v> doubles / B2M_STAB_NI<v> ints, else warp per env
+#define B2M_STAB_ND0 1024
+#define B2M_STAB_NI0 192
+#define B2M_STAB_ND1 3072
+#define B2M_STAB_NI1 512
+const void* b2m_k_stabilize_thread(int variant);   // (SimParams P) with P.nmax = P.cmax
+const void* b2m_k_stabilize_warp();       // (SimParams P, size_t env_doubles, size_t all_doubles): working set in P.gscratch

@@ -46,6 +46,10 @@ class SceneBatch:
         self.min_step_size = NEAR_ZERO       # TimeSteppingSimulator.cpp:48
         self.min_step_size_env = None        # optional per-env override, [env]
         self.impact_model = MODEL_QP
+        # constraint-stabilization-max-iterations: 0 = off, < 0 = the reference's default (unlimited), > 0 = that many
+        # (ConstraintStabilization.cpp:53-59).  The builders below keep 0 unless told otherwise: BASELINE's numbers of round 1
+        # were taken without it; bench.py --stabilization turns it on.
+        self.stabilization_max_iterations = 0
         self.q = np.zeros((nb, 7, ne), np.float64)
         self.q[:, 6, :] = 1.0
         self.v = np.zeros((nb, 6, ne), np.float64)
@@ -102,7 +106,7 @@ class SceneBatch:
             setattr(d, name, a.ctypes.data_as(C.POINTER(ct)))
         d.gravity = (C.c_double * 3)(*self.gravity)
         d.contact_dist_thresh, d.min_step_size = self.contact_dist_thresh, self.min_step_size
-        d.impact_model, d.stabilization_max_iterations = self.impact_model, 0
+        d.impact_model, d.stabilization_max_iterations = self.impact_model, self.stabilization_max_iterations
         if self.min_step_size_env is not None:
             a = np.ascontiguousarray(self.min_step_size_env, np.float64)
             keep.append(a)

@@ -67,6 +67,14 @@ int oracle_lcp_lemke_regularized(int n, const double* M, const double* q, double
 
 // ---- simulator ----
 struct OracleSim { Sim sim; };
+// checker counters -> the product's counter struct
+static void add_counters(b200moby_counters* t, const Counters& k) {
+  t->env_steps += k.env_steps; t->mini_steps += k.mini_steps; t->lcp_solves += k.lcp_solves; t->lcp_fast_calls += k.lcp_fast_calls;
+  t->lemke_calls += k.lemke_calls; t->pivots += k.pivots; t->lcp_failures += k.lcp_failures; t->impact_tol_events += k.impact_tol_events;
+  t->contacts += k.contacts; t->max_lcp_n = std::max<long long>(t->max_lcp_n, k.max_lcp_n); t->pivot_flops += k.pivot_flops; t->ca_iterations += k.ca_iterations;
+  t->stab_iterations += k.stab_iterations; t->stab_lcp_solves += k.stab_lcp_solves; t->stab_line_search_failures += k.stab_line_search_failures;
+}
+
 static void rc_model_from_desc(const b200moby_rc_desc* r, const double* mass, const double* J, const double* base_pose, RCModel& m);
 
 static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
@@ -92,6 +100,7 @@ static void fill_from_desc(Sim& S, const b200moby_scene_desc* d, int e) {
   S.contact_dist_thresh = d->contact_dist_thresh;
   S.min_step_size = d->min_step_size_env ? d->min_step_size_env[e] : d->min_step_size;
   S.model = d->impact_model;
+  S.stab_max_iterations = d->stabilization_max_iterations;
   if (d->rc && d->rc->n_links > 0) {
     const b200moby_rc_desc* r = d->rc;
     S.has_rc = true; S.rc_first = r->first_body; S.rc_fdyn = r->fdyn_algorithm;
@@ -170,10 +179,8 @@ void oracle_sim_step(void* h, double dt, int n_steps) {
 }
 double oracle_sim_time(void* h) { return ((OracleSim*)h)->sim.current_time; }
 void oracle_sim_counters(void* h, b200moby_counters* c) {
-  const Counters& k = ((OracleSim*)h)->sim.cnt;
-  c->env_steps = k.env_steps; c->mini_steps = k.mini_steps; c->lcp_solves = k.lcp_solves; c->lcp_fast_calls = k.lcp_fast_calls;
-  c->lemke_calls = k.lemke_calls; c->pivots = k.pivots; c->lcp_failures = k.lcp_failures; c->impact_tol_events = k.impact_tol_events;
-  c->contacts = k.contacts; c->max_lcp_n = k.max_lcp_n; c->pivot_flops = k.pivot_flops; c->assembly_flops = 0; c->ca_iterations = k.ca_iterations;
+  std::memset(c, 0, sizeof(*c));
+  add_counters(c, ((OracleSim*)h)->sim.cnt);
 }
 // LCP of the most recent impact solve: returns n; copies min(n*n, cap) etc.
 int oracle_sim_last_lcp(void* h, double* MM, double* qq, double* z, int ncap) {
@@ -219,7 +226,8 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
                        int threads, b200moby_counters* total) {
   const int nb = d->n_bodies, ne = d->n_envs;
   if (threads < 1) threads = 1;
-  std::vector<Counters> cs(threads);
+  std::vector<b200moby_counters> cs(threads);
+  for (auto& c : cs) std::memset(&c, 0, sizeof(c));
   auto work = [&](int t) {
     std::vector<double> qa(nb * 7), va(nb * 6);
     for (int e = e0 + t; e < e1; e += threads) {
@@ -229,10 +237,7 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
       for (int i = 0; i < n_steps; i++) S.step(dt);
       get_state(S, qa.data(), va.data());
       for (int b = 0; b < nb; b++) { for (int k = 0; k < 7; k++) q[((size_t)b * 7 + k) * ne + e] = qa[b * 7 + k]; for (int k = 0; k < 6; k++) v[((size_t)b * 6 + k) * ne + e] = va[b * 6 + k]; }
-      Counters& c = cs[t]; const Counters& k = S.cnt;
-      c.env_steps += k.env_steps; c.mini_steps += k.mini_steps; c.lcp_solves += k.lcp_solves; c.lcp_fast_calls += k.lcp_fast_calls;
-      c.lemke_calls += k.lemke_calls; c.pivots += k.pivots; c.lcp_failures += k.lcp_failures; c.impact_tol_events += k.impact_tol_events;
-      c.contacts += k.contacts; c.max_lcp_n = std::max(c.max_lcp_n, k.max_lcp_n); c.pivot_flops += k.pivot_flops; c.ca_iterations += k.ca_iterations;
+      add_counters(&cs[t], S.cnt);
     }
   };
   if (threads == 1) work(0);
@@ -243,6 +248,7 @@ void oracle_batch_step(const b200moby_scene_desc* d, double* q, double* v, int e
       total->env_steps += c.env_steps; total->mini_steps += c.mini_steps; total->lcp_solves += c.lcp_solves; total->lcp_fast_calls += c.lcp_fast_calls;
       total->lemke_calls += c.lemke_calls; total->pivots += c.pivots; total->lcp_failures += c.lcp_failures; total->impact_tol_events += c.impact_tol_events;
       total->contacts += c.contacts; total->max_lcp_n = std::max(total->max_lcp_n, c.max_lcp_n); total->pivot_flops += c.pivot_flops; total->ca_iterations += c.ca_iterations;
+      total->stab_iterations += c.stab_iterations; total->stab_lcp_solves += c.stab_lcp_solves; total->stab_line_search_failures += c.stab_line_search_failures;
     }
   }
 }
@@ -289,12 +295,7 @@ void oracle_batch_run(void* h, double dt, int n_steps, int threads, b200moby_cou
   else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
   if (total) {
     std::memset(total, 0, sizeof(*total));
-    for (auto& S : B->sims) {
-      const Counters& k = S.cnt;
-      total->env_steps += k.env_steps; total->mini_steps += k.mini_steps; total->lcp_solves += k.lcp_solves; total->lcp_fast_calls += k.lcp_fast_calls;
-      total->lemke_calls += k.lemke_calls; total->pivots += k.pivots; total->lcp_failures += k.lcp_failures; total->impact_tol_events += k.impact_tol_events;
-      total->contacts += k.contacts; total->max_lcp_n = std::max(total->max_lcp_n, k.max_lcp_n); total->pivot_flops += k.pivot_flops; total->ca_iterations += k.ca_iterations;
-    }
+    for (auto& S : B->sims) add_counters(total, S.cnt);
   }
 }
 // state of env (e0 + i) as AoS [body][7], [body][6]

@@ -26,7 +26,7 @@ static inline V3 normalize(const V3& a) { double n = norm(a); return V3(a.x / n,
 static inline V3 rot(const double* R, const V3& v) { return V3(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z); }
 static inline V3 rotT(const double* R, const V3& v) { return V3(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z); }
 
-Sim::Sim() { min_step_size = NEAR_ZERO; }
+Sim::Sim() { min_step_size = NEAR_ZERO; stab_eps = NEAR_ZERO; }
 
 void Sim::init(int nb) {
   bodies.assign(nb, Body());
@@ -518,7 +518,7 @@ double Sim::do_mini_step(double dt) {
   return h;
 }
 
-// TimeSteppingSimulator::step + step_si_Euler (TimeSteppingSimulator.cpp:52-111,433-455); stabilization disabled (max_iterations = 0)
+// TimeSteppingSimulator::step + step_si_Euler (TimeSteppingSimulator.cpp:52-111,433-455)
 double Sim::step(double dt) {
   double h = 0.0;
   int stalled = 0;
@@ -531,6 +531,7 @@ double Sim::step(double dt) {
     if (stalled >= 64) { cnt.lcp_failures++; break; }
     if (hh == 0.0 && mini_failed) break;   // LCPSolverException in the reference (ImpactConstraintHandlerQP.cpp:224): the env gives up this step
   }
+  stabilize();                             // TimeSteppingSimulator.cpp:95-98
   cnt.env_steps++;
   return dt;
 }
@@ -1104,20 +1105,15 @@ void Sim::assemble_island_lcp(const std::vector<Contact*>& cons, const std::vect
   if (model == MODEL_AP) build_ap_lcp(q, n, MM, qq); else build_qp_lcp(q, n, MM, qq);
 }
 
-// ConstraintSimulator::calc_impacting_unilateral_constraint_forces (:298-355) -> ImpactConstraintHandler::apply_model (:96-168)
-void Sim::process_constraints(std::vector<Contact>& contacts) {
-  last_contacts = contacts;
-  if (contacts.empty()) return;
-  bool none_impacting = true;
-  for (size_t i = 0; i < contacts.size(); i++)
-    if (calc_constraint_vel(contacts[i]) < -NEAR_ZERO) { none_impacting = false; break; }   // eNegative, UnilateralConstraint.cpp:1433-1446
-  if (none_impacting) return;
-  // islands: UnilateralConstraint::determine_connected_constraints (UnilateralConstraint.cpp:940-1194), canonical order H4
+// islands: UnilateralConstraint::determine_connected_constraints (UnilateralConstraint.cpp:940-1194), canonical order H4
+typedef std::vector<std::pair<std::vector<Contact*>, std::vector<int> > > IslandList;
+static void determine_connected_constraints(const Sim& S, std::vector<Contact>& contacts, IslandList& groups) {
+  const std::vector<Body>& bodies = S.bodies;
   const int nb = (int)bodies.size();
   std::set<int> nodes;
   std::vector<std::vector<int> > adj(nb);
   for (size_t i = 0; i < contacts.size(); i++) {
-    const int b1 = super_of(contacts[i].b1), b2 = super_of(contacts[i].b2);      // single bodies of one articulated body are one node
+    const int b1 = S.super_of(contacts[i].b1), b2 = S.super_of(contacts[i].b2);      // single bodies of one articulated body are one node
     const bool e1 = bodies[contacts[i].b1].enabled, e2 = bodies[contacts[i].b2].enabled;
     if (e1) nodes.insert(b1);
     if (e2) nodes.insert(b2);
@@ -1125,7 +1121,6 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
   }
   // std::multimap keeps equal keys in insertion order: neighbours are visited in contact order
   std::vector<char> taken(contacts.size(), 0);
-  std::vector<std::pair<std::vector<Contact*>, std::vector<int> > > groups;
   while (!nodes.empty()) {
     int node = *nodes.begin();
     groups.push_back(std::make_pair(std::vector<Contact*>(), std::vector<int>()));
@@ -1139,10 +1134,22 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
       processed.insert(node);
       for (size_t k = 0; k < adj[node].size(); k++) if (!processed.count(adj[node][k])) nq.push(adj[node][k]);
       for (size_t i = 0; i < contacts.size(); i++)
-        if (!taken[i] && ((bodies[contacts[i].b1].enabled && super_of(contacts[i].b1) == node) || (bodies[contacts[i].b2].enabled && super_of(contacts[i].b2) == node))) { taken[i] = 1; groups.back().first.push_back(&contacts[i]); }
+        if (!taken[i] && ((bodies[contacts[i].b1].enabled && S.super_of(contacts[i].b1) == node) || (bodies[contacts[i].b2].enabled && S.super_of(contacts[i].b2) == node))) { taken[i] = 1; groups.back().first.push_back(&contacts[i]); }
     }
     if (groups.back().first.empty()) groups.pop_back();
   }
+}
+
+// ConstraintSimulator::calc_impacting_unilateral_constraint_forces (:298-355) -> ImpactConstraintHandler::apply_model (:96-168)
+void Sim::process_constraints(std::vector<Contact>& contacts) {
+  last_contacts = contacts;
+  if (contacts.empty()) return;
+  bool none_impacting = true;
+  for (size_t i = 0; i < contacts.size(); i++)
+    if (calc_constraint_vel(contacts[i]) < -NEAR_ZERO) { none_impacting = false; break; }   // eNegative, UnilateralConstraint.cpp:1433-1446
+  if (none_impacting) return;
+  IslandList groups;
+  determine_connected_constraints(*this, contacts, groups);
   // remove_inactive_groups (:1197-1225), evaluated before any island is solved
   std::vector<char> active(groups.size(), 0);
   for (size_t g = 0; g < groups.size(); g++)
@@ -1165,6 +1172,171 @@ void Sim::process_constraints(std::vector<Contact>& contacts) {
       if (calc_constraint_vel(*groups[g].first[i]) < -NEAR_ZERO) { still = true; break; }
   }
   if (still) cnt.impact_tol_events++;
+}
+
+// ---------- constraint stabilization: ConstraintStabilization.cpp (no implicit joints, no joint limits) ----------
+namespace {
+// Euler coordinates of every body of the simulator (ConstraintStabilization::get_body_configurations :1215-1237): seven
+// per enabled free body (x y z qx qy qz qw), the joint positions of the articulated body; the same layout for dq.
+struct StabQ { std::vector<double> x; Vec j; };     // x: [body][7] (entries of disabled bodies and links unused)
+}
+static void stab_get(const Sim& S, StabQ& q) {
+  const size_t nb = S.bodies.size();
+  q.x.assign(nb * 7, 0.0);
+  for (size_t b = 0; b < nb; b++) { const Body& B = S.bodies[b]; for (int k = 0; k < 3; k++) q.x[b * 7 + k] = B.x[k]; for (int k = 0; k < 4; k++) q.x[b * 7 + 3 + k] = B.quat[k]; }
+  q.j = S.jq;
+}
+// update_body_configurations(q + t dq) (:1252-1264): set_generalized_coordinates_euler normalises the quaternion
+static void stab_set(Sim& S, const StabQ& q, const StabQ& dq, double t) {
+  for (size_t b = 0; b < S.bodies.size(); b++) {
+    Body& B = S.bodies[b];
+    if (!B.enabled || S.is_link((int)b)) continue;
+    double c[7];
+    for (int k = 0; k < 7; k++) c[k] = dq.x[b * 7 + k] * t + q.x[b * 7 + k];                 // qstar = dq; qstar *= t; qstar += q
+    B.x = V3(c[0], c[1], c[2]);
+    const double nrm = std::sqrt(c[3] * c[3] + c[4] * c[4] + c[5] * c[5] + c[6] * c[6]);
+    for (int k = 0; k < 4; k++) B.quat[k] = c[3 + k] / nrm;
+    S.update_pose(B);
+  }
+  if (S.has_rc) { for (size_t k = 0; k < S.jq.size(); k++) S.jq[k] = dq.j[k] * t + q.j[k]; S.rc_update_links(); }
+}
+// evaluate_unilateral_constraints (:88-131): the pairwise distances at the current configuration; returns the smallest
+static double stab_eval(const Sim& S, const std::vector<std::pair<int, int> >& pairs, std::vector<PairDist>& pd, std::vector<double>& uC) {
+  S.calc_pairwise_distances(pairs, pd);
+  double vio = INF;
+  uC.resize(pd.size());
+  for (size_t i = 0; i < pd.size(); i++) { uC[i] = pd[i].dist; vio = std::min(vio, uC[i]); }
+  return vio;
+}
+static double stab_sign(double x, double y) { return (y > 0.0) ? std::fabs(x) : -std::fabs(x); }
+// ridders_unilateral (:1322-1380), literally: note that the caller passes x2 = the current t with fh = the value at t = 1
+static double stab_ridders(Sim& S, const std::vector<std::pair<int, int> >& pairs, double x1, double x2, double fl, double fh, size_t idx,
+                           const StabQ& dq, const StabQ& q) {
+  const unsigned MAX_ITERATIONS = 25;
+  const double TOL = 1e-4;
+  std::vector<PairDist> pd; std::vector<double> uC;
+  auto eval = [&](double t) { stab_set(S, q, dq, t); stab_eval(S, pairs, pd, uC); return uC[idx]; };
+  double ans = INF, fm, fnew, s, xh, xl, xm, xnew;
+  if ((fl > 0.0 && fh < 0.0) || (fl < 0.0 && fh > 0.0)) {
+    xl = x1; xh = x2;
+    for (unsigned j = 0; j < MAX_ITERATIONS; j++) {
+      xm = 0.5 * (xl + xh);
+      fm = eval(xm);
+      s = std::sqrt(fm * fm - fl * fh);
+      if (s == 0.0) return ans;
+      xnew = xm + (xm - xl) * ((fl >= fh ? 1.0 : -1.0) * fm / s);
+      ans = xnew;
+      fnew = eval(ans);
+      if (std::fabs(fnew) < TOL && fnew >= 0.0) return xnew;
+      if (stab_sign(fm, fnew) != fm) { xl = xm; fl = fm; xh = ans; fh = fnew; }
+      else if (stab_sign(fl, fnew) != fl) { xh = ans; fh = fnew; }
+      else if (stab_sign(fh, fnew) != fh) { xl = ans; fl = fnew; }
+      else return 0.0;                                                     // assert(false) in the reference
+    }
+  } else {
+    if (fl == 0.0) return x1;
+    if (fh == 0.0) return x2;
+  }
+  return 0.0;
+}
+// update_q (:1055-1212): line search along dq; leaves the bodies at q + t dq and stores that in q
+static bool stab_update_q(Sim& S, const std::vector<std::pair<int, int> >& pairs, const StabQ& dq, StabQ& q) {
+  const double MIN_T = NEAR_ZERO, BETA = 0.6;
+  std::vector<PairDist> pd; std::vector<double> uC, uC_old;
+  stab_eval(S, pairs, pd, uC_old);
+  stab_set(S, q, dq, 1.0);
+  stab_eval(S, pairs, pd, uC);
+  std::vector<char> bracket(uC.size());
+  for (size_t i = 0; i < uC.size(); i++) bracket[i] = (uC_old[i] < 0.0 && uC[i] > 0.0) || (uC_old[i] > 0.0 && uC[i] < 0.0);
+  double t = 1.0;
+  const std::vector<double> uC1 = uC;                                      // the values at t = 1 (ridders evaluates into its own arrays)
+  for (size_t i = 0; i < bracket.size(); i++) {
+    if (!bracket[i]) continue;
+    const double root = stab_ridders(S, pairs, 0.0, t, uC_old[i], uC1[i], i, dq, q);
+    if (root > 0.0 && root < 1.0) t = std::min(root, t);
+  }
+  stab_set(S, q, dq, t);
+  stab_eval(S, pairs, pd, uC);
+  for (;;) {
+    bool stop = true;
+    for (size_t i = 0; i < bracket.size(); i++) if (!bracket[i] && uC[i] < 0.0 && uC_old[i] > uC[i]) { stop = false; break; }
+    if (stop) break;                                                       // no bilateral constraints: violation 0 < bilateral_eps
+    t *= BETA;
+    if (t < MIN_T) return false;
+    stab_set(S, q, dq, t);
+    stab_eval(S, pairs, pd, uC);
+  }
+  for (size_t k = 0; k < q.x.size(); k++) q.x[k] = dq.x[k] * t + q.x[k];   // q = qstar (NOT renormalised: the stored vector, :1209)
+  for (size_t k = 0; k < q.j.size(); k++) q.j[k] = dq.j[k] * t + q.j[k];
+  return true;
+}
+
+void Sim::stabilize() {
+  if (stab_max_iterations == 0) return;                                    // :173-174
+  const size_t nb = bodies.size();
+  std::vector<V3> vl_save(nb), va_save(nb);                                // save_velocities :66-75
+  for (size_t b = 0; b < nb; b++) { vl_save[b] = bodies[b].vl; va_save[b] = bodies[b].va; }
+  const Vec jqd_save = jqd;
+  StabQ q, dq;
+  stab_get(*this, q);
+  std::vector<std::pair<int, int> > pairs;
+  broad_phase(pairs);
+  std::vector<PairDist> pd; std::vector<double> uC;
+  double max_uvio = stab_eval(*this, pairs, pd, uC);                        // :187
+  const long long cap = stab_max_iterations < 0 ? 100 : std::min(100, stab_max_iterations);   // rule H12
+  long long iterations = 0;
+  while (max_uvio < stab_eps) {                                             // :197 (bilateral violation is 0)
+    if (iterations == cap) { if (stab_max_iterations < 0 || stab_max_iterations > 100) cnt.stab_line_search_failures++; break; }
+    for (size_t b = 0; b < nb; b++) { bodies[b].vl = V3(); bodies[b].va = V3(); }      // :211-217
+    if (has_rc) { for (size_t k = 0; k < jqd.size(); k++) jqd[k] = 0.0; rc_update_links(); }
+    // compute_problem_data (:348-478): one contact at the closest points of a separated pair, the narrowphase's
+    // contacts (TOL = NEAR_ZERO, CollisionDetection.h:46) of a touching / penetrating one
+    std::vector<Contact> contacts;
+    calc_pairwise_distances(pairs, pd);
+    for (size_t p = 0; p < pd.size(); p++) {                               // add_contact_constraints :304-345
+      if (pd[p].dist == INF) continue;
+      if (pd[p].dist >= NEAR_ZERO) {
+        const V3 normal = normalize(pd[p].pb - pd[p].pa);
+        contacts.push_back(create_contact(pd[p].a, pd[p].b, pd[p].pa, normal, pd[p].dist));
+      } else find_contacts(pd[p].a, pd[p].b, NEAR_ZERO, contacts);
+    }
+    IslandList groups;
+    determine_connected_constraints(*this, contacts, groups);
+    dq.x.assign(nb * 7, 0.0); dq.j.assign(jq.size(), 0.0);
+    for (size_t g = 0; g < groups.size(); g++) {                           // determine_dq :932-970
+      ProblemData pq;
+      compute_problem_data(*this, pq, groups[g].first, groups[g].second);
+      const int n = pq.nc;
+      Vec MM((size_t)n * n), qq(n), z;
+      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) MM[(size_t)j * n + i] = pq.D[0][0](i, j);
+      for (int i = 0; i < n; i++) qq[i] = pq.cons[i]->dist - std::fabs(stab_eps) - NEAR_ZERO;   // :432-433
+      const unsigned long long f0 = stab_lcp.n_fast_calls, l0 = stab_lcp.n_lemke_calls, p0 = stab_lcp.n_pivots_total;
+      cnt.stab_lcp_solves++;
+      if (!stab_lcp.lcp_fast(n, MM.data(), qq.data(), z))                   // :961 (z is a fresh vector: cold start)
+        if (!stab_lcp.lcp_lemke_regularized(n, MM.data(), qq.data(), z)) { z.assign(n, 0.0); cnt.lcp_failures++; }   // rule H12
+      cnt.lcp_fast_calls += stab_lcp.n_fast_calls - f0; cnt.lemke_calls += stab_lcp.n_lemke_calls - l0; cnt.pivots += stab_lcp.n_pivots_total - p0;
+      for (int i = 0; i < n; i++) { pq.cn[i] = z[i]; pq.cs[i] = 0.0; pq.ct[i] = 0.0; }
+      apply_to_bodies(*this, pq);                                          // update_from_stacked :965
+      for (size_t k = 0; k < pq.sb.size(); k++) {                          // dq <- generalized velocity in Euler coordinates :968-975
+        const int b = pq.sb[k];
+        if (has_rc && b == rc_first + 1) { dq.j = jqd; continue; }
+        const Body& B = bodies[b];
+        const double qx = B.quat[0], qy = B.quat[1], qz = B.quat[2], qw = B.quat[3];
+        const V3& w = B.va;
+        dq.x[b * 7 + 0] = B.vl.x; dq.x[b * 7 + 1] = B.vl.y; dq.x[b * 7 + 2] = B.vl.z;
+        dq.x[b * 7 + 3] = 0.5 * (+qw * w.x + qz * w.y - qy * w.z);         // Quatd::deriv, as in do_mini_step
+        dq.x[b * 7 + 4] = 0.5 * (-qz * w.x + qw * w.y + qx * w.z);
+        dq.x[b * 7 + 5] = 0.5 * (+qy * w.x - qx * w.y + qw * w.z);
+        dq.x[b * 7 + 6] = 0.5 * (-qx * w.x - qy * w.y - qz * w.z);
+      }
+    }
+    if (!stab_update_q(*this, pairs, dq, q)) { cnt.stab_line_search_failures++; break; }   // :231-235
+    max_uvio = stab_eval(*this, pairs, pd, uC);                             // :238
+    iterations++;
+  }
+  cnt.stab_iterations += iterations;
+  for (size_t b = 0; b < nb; b++) { bodies[b].vl = vl_save[b]; bodies[b].va = va_save[b]; }   // restore_velocities :78-85
+  if (has_rc) { jqd = jqd_save; rc_update_links(); }
 }
 
 }  // namespace oracle

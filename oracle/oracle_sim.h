@@ -18,7 +18,11 @@
 //   H1 zlast is zero-filled on size change; H2 lowest-index tie rule (glibc-rand optional);
 //   H3 restitution re-applies friction (literal); H4 bodies by scene index, pairs lexicographic,
 //   contacts in generation order; H6 non-logging create_contact; H8 collinearity scan tests points 0,1,2;
-//   H10 the no-slip path's trailing update_from_stacked(_epd, _z) with the QP handler's stale _z is skipped.
+//   H10 the no-slip path's trailing update_from_stacked(_epd, _z) with the QP handler's stale _z is skipped;
+//   H7 stabilization runs while min dist < +NEAR_ZERO (as coded, ConstraintStabilization.cpp:58-59,197);
+//   H12 a stabilization LCP that neither lcp_fast nor lcp_lemke_regularized solves contributes dq = 0 (the reference
+//       ignores lcp_lemke_regularized's return value and uses whatever z it left, :961-962); the stabilization loop is
+//       also capped at 100 iterations per step (the reference's default is unbounded): both are counted.
 #pragma once
 #include <vector>
 #include "oracle_lcp.h"
@@ -70,7 +74,8 @@ struct PairDist {
 
 struct Counters {
   long long env_steps = 0, mini_steps = 0, lcp_solves = 0, lcp_fast_calls = 0, lemke_calls = 0, pivots = 0,
-            lcp_failures = 0, impact_tol_events = 0, contacts = 0, max_lcp_n = 0, pivot_flops = 0, ca_iterations = 0;
+            lcp_failures = 0, impact_tol_events = 0, contacts = 0, max_lcp_n = 0, pivot_flops = 0, ca_iterations = 0,
+            stab_iterations = 0, stab_lcp_solves = 0, stab_line_search_failures = 0;
 };
 
 struct Sim {
@@ -85,6 +90,11 @@ struct Sim {
   Vec zlast;                            // ImpactConstraintHandler::_zlast
   Vec vlast;                            // ImpactConstraintHandler::_v, the no-slip LCP's solution / warm start (:1239)
   Counters cnt;
+  // ConstraintStabilization (ConstraintStabilization.cpp:53-66): max_iterations 0 = off, < 0 = the reference's default
+  // (UINT_MAX, i.e. until no pair is closer than eps); eps = +NEAR_ZERO as coded (rule H7)
+  int stab_max_iterations = 0;
+  double stab_eps;
+  LCP stab_lcp;                         // ConstraintStabilization::_lcp
   bool mini_failed = false;             // an LCP of the current mini-step stayed unsolved (LCPSolverException in the reference)
   // taps for parity tests: LCP of the most recent impact solve
   int last_n = 0;
@@ -119,6 +129,7 @@ struct Sim {
   double calc_constraint_vel(const Contact& c) const;
   void calc_fwd_dyn_and_integrate_velocity(double h);
   void process_constraints(std::vector<Contact>& contacts);
+  void stabilize();                             // ConstraintStabilization::stabilize, called at the end of step()
   // assemble the LCP (MM,qq) of one island without solving (for the assembly parity test)
   void assemble_island_lcp(const std::vector<Contact*>& cons, const std::vector<int>& island_bodies, int& n, Vec& MM, Vec& qq);
 };

@@ -25,6 +25,7 @@ static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, 
   P.mu_c = d->mu_coulomb; P.mu_v = d->mu_viscous; P.eps = d->epsilon; P.compliance = d->compliance; P.NK = d->NK;
   P.fr_tab = tab.data(); P.gx = d->gravity[0]; P.gy = d->gravity[1]; P.gz = d->gravity[2];
   P.contact_dist_thresh = d->contact_dist_thresh; P.min_step_size = d->min_step_size; P.min_step_env = d->min_step_size_env;
+  P.stab_max_iterations = d->stabilization_max_iterations; P.stab_eps = B2M_NEAR_ZERO;
   P.q = q; P.v = v; P.time = time; P.zlast = zlast; P.zlast_n = zlast_n; P.counters = counters;
   P.vlast = zlast + (size_t)nmax * ne; P.vlast_n = zlast_n + ne;   // the caller's arrays carry both warm starts
   P.env_stat = g_env_stat;
@@ -37,6 +38,24 @@ static bool setup_params(SimParams& P, RCTree& tree, std::vector<double>& tau0, 
     P.jtau = tau0.data();
   }
   return true;
+}
+
+// the stabilization phase of one env, as k_stabilize.cu runs it (working set with nmax = cmax + the stabilization extras)
+static void stabilize_env_host(const SimParams& P, int e, unsigned long long* lc) {
+  if (P.stab_max_iterations == 0) return;
+  SimParams Ps = P; Ps.nmax = Ps.cmax;
+  const EnvDims D = env_dims(Ps);
+  std::vector<double> wd(env_doubles(D) + stab_extra_doubles(D));
+  std::vector<int> wi(env_ints(D) + stab_extra_ints(D));
+  EnvMem m; StabMem s;
+  env_carve(m, wd.data(), wi.data(), D);
+  stab_carve(s, wd.data() + env_doubles(D), wi.data() + env_ints(D), D);
+  SerialGroup g(nullptr);
+  env_load(g, Ps, e, m);
+  const EnvStatBase sb = env_stat_base(lc);
+  env_stabilize(g, Ps, e, m, s, lc);
+  env_stat_commit(g, Ps, e, lc, sb);
+  env_store(g, Ps, e, m, ST_POS);
 }
 
 extern "C" {
@@ -63,7 +82,10 @@ int hostsim_run(const b200moby_scene_desc* d, double* q, double* v, double* time
   SerialGroup g(nullptr);
   unsigned long long lc[CNT_COUNT]; memset(lc, 0, sizeof(lc));
   EnvCtx cx; cx.limit = false; cx.budget = 0;
-  for (int e = e0; e < e1; e++) env_run(g, P, e, m, dt, n_steps, lc, cx);
+  for (int e = e0; e < e1; e++) {
+    if (P.stab_max_iterations == 0) { env_run(g, P, e, m, dt, n_steps, lc, cx); continue; }
+    for (int s = 0; s < n_steps; s++) { env_run(g, P, e, m, dt, 1, lc, cx); stabilize_env_host(P, e, lc); }   // TimeSteppingSimulator.cpp:95-98
+  }
   for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) counters[k] = std::max(counters[k], lc[k]); else counters[k] += lc[k]; }
   return nmax;
 }
@@ -137,6 +159,7 @@ int hostsim_run_phased(const b200moby_scene_desc* d, double* q, double* v, doubl
       const int* list = q_list(P, rounds - 1, B2M_SLOT_CONT);
       for (int i = 0; i < count; i++) { unsigned long long lc[CNT_COUNT] = {0}; env_finish(g, P, list[i], m, dt, lc); add(lc); }
     }
+    for (int e = 0; e < ne; e++) { unsigned long long lc[CNT_COUNT] = {0}; stabilize_env_host(P, e, lc); add(lc); }   // stabilization phase (k_stabilize.cu)
   }
   for (int k = 0; k < CNT_COUNT; k++) { if (k == CNT_MAX_N) counters[k] = std::max(counters[k], tot[k]); else counters[k] += tot[k]; }
   return nmax;

@@ -10,7 +10,8 @@ from moby_b200.capi import RcDesc, SceneDesc
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 CNT = ("env_steps", "mini_steps", "lcp_solves", "lcp_fast_calls", "lemke_calls", "pivots", "lcp_failures",
-       "impact_tol_events", "contacts", "max_lcp_n", "overflow", "pivot_flops", "assembly_flops", "ca_iterations")
+       "impact_tol_events", "contacts", "max_lcp_n", "overflow", "pivot_flops", "assembly_flops", "ca_iterations",
+       "stab_iterations", "stab_lcp_solves", "stab_line_search_failures")
 _lib = None
 
 
@@ -51,7 +52,7 @@ class HostSim:
         self.q[:, 3:7, :] /= np.sqrt((self.q[:, 3:7, :] ** 2).sum(axis=1, keepdims=True))   # as b200moby_set_state does
         self.time = np.zeros(ne)
         self.zlast, self.zlast_n = np.zeros((2 * self.nmax, ne)), np.zeros(2 * ne, np.int32)
-        self.counters = np.zeros(16, np.uint64)
+        self.counters = np.zeros(24, np.uint64)
         self.rc = getattr(scene, "rc", None)
         self.jq = self.rc.jq.copy() if self.rc is not None else None
         self.jqd = self.rc.jqd.copy() if self.rc is not None else None

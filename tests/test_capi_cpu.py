@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(L):
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.b200moby_abi_version() == 2
+    assert L.b200moby_abi_version() == 3
 
 
 def test_no_cpu_fallback(L):
