@@ -131,6 +131,78 @@ def _cpu_baseline(scene, q, v, joints, dt, n_envs, n_steps, threads):
     return c["env_steps"] / el, c["lcp_solves"] / el, el, c
 
 
+def _stab_iters(args):
+    """constraint-stabilization-max-iterations of the measured scene: ur10.xml sets 0 itself (example/ur10/ur10.xml:12)."""
+    return 0 if (args.stabilization == "off" or args.workload == "ur10") else -1
+
+
+def _stab_text(args):
+    return ("on (reference default: until no pair is closer than sqrt(eps), ConstraintStabilization.cpp:53-59)" if _stab_iters(args)
+            else "off (constraint-stabilization-max-iterations=0" + (", as example/ur10/ur10.xml:12)" if args.workload == "ur10" else ")"))
+
+
+def _device_timed(sim, dt, steps, warmup, flush, stream):
+    """steps x step(dt) timed with CUDA events on the launching stream, L2 flushed between steps; returns seconds."""
+    import torch
+    for _ in range(warmup):
+        flush.fill_(1)
+        sim.step(dt, 1)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(0)
+        a.record(stream)
+        sim.step(dt, 1)
+        b.record(stream)
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+
+
+def _secondary(args, W, scenes, rank_seed, local_rank, flush, stream):
+    """Rank 0, after the headline measurement: (1) the same workload with constraint stabilization off -- round 1's
+    configuration, kept beside the headline; (2) drift against the oracle: a fresh 512-env batch of the workload stepped
+    300 steps on the GPU and by the oracle from the same initial state, share of envs above 1e-9 (relative)."""
+    import copy
+    from moby_b200 import TimeSteppingSimulator, sharding
+    out = {}
+    DT = W["dt"]
+    ne = args.envs_per_gpu or W["envs"]
+    if _stab_iters(args) != 0:
+        sc = W["make"](scenes, ne, rank_seed)
+        if args.min_step == "default" and args.workload == "small":
+            sc.min_step_size_env = None
+        sc.stabilization_max_iterations = 0
+        sim = TimeSteppingSimulator(sc, device=local_rank)
+        sim.step(DT, args.preroll)
+        steps = max(5, args.steps // 2)
+        t = _device_timed(sim, DT, steps, 3, flush, stream)
+        out["stabilization_off"] = {"value": ne * steps / t, "unit": "env-steps/s", "ms_per_step": 1e3 * t / steps, "steps": steps, "n_gpus": 1,
+                                    "note": "same workload and seed on rank 0's GPU with constraint-stabilization-max-iterations=0 (the configuration of round 1's numbers)"}
+        del sim
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as O
+        n_d, s_d = min(512, ne), 300
+        full = W["make"](scenes, max(n_d, 512), rank_seed)
+        if args.min_step == "default" and args.workload == "small":
+            full.min_step_size_env = None
+        full.stabilization_max_iterations = _stab_iters(args)
+        sc = sharding.select_envs(full, np.arange(n_d))
+        sim = TimeSteppingSimulator(sc, device=local_rank)
+        sim.step(DT, s_d)
+        q, v = sim.get_state()
+        ob = O.OracleBatch(sc)
+        ob.run(DT, s_d, threads=os.cpu_count() or 1)
+        qo, vo = ob.get_state_soa()
+        scale = np.maximum(1.0, np.maximum(np.abs(qo).max(axis=(0, 1)), np.abs(vo).max(axis=(0, 1))))
+        err = np.maximum(np.abs(q - qo).max(axis=(0, 1)), np.abs(v - vo).max(axis=(0, 1))) / scale
+        out["drift"] = {"envs": n_d, "steps": s_d, "envs_above_1e-9": int((err > 1e-9).sum()), "share_above_1e-9": float((err > 1e-9).mean()),
+                        "max_rel_err": float(err.max()), "median_rel_err": float(np.median(err)),
+                        "note": "GPU vs oracle/ from the same initial state; envs above 1e-9 ran Lemke on a singular LCP whose pivot path "
+                                "differs between the tableau and the LU-per-pivot form (tests/parity_util.py, profiles/r02_lemke_path_sensitivity.json)"}
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path, restated (oracle/, kind "port"),
     all host threads, each step = one step of a bounded 4,096-env sample of the same seeded workload."""
@@ -144,6 +216,7 @@ def run_reference(args, rank, world):
     scene = W["make"](scenes, sample, 0xB200)
     if args.min_step == "default" and args.workload == "small":
         scene.min_step_size_env = None
+    scene.stabilization_max_iterations = _stab_iters(args)
     if args.preroll < 0:
         args.preroll = W["preroll"]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -163,7 +236,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env_steps_per_s", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200", "min_step_size": args.min_step},
+        "config": {"workload": WORKLOAD, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200", "min_step_size": args.min_step,
+                   "stabilization": _stab_text(args)},
         "lcp_solves_per_s": (c1["lcp_solves"] - c0["lcp_solves"]) / el,
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"first {sample} envs of the seeded batch, one step per timed step, {cores} host threads; "
@@ -281,6 +355,10 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's own batch size")
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps before warm-up so contacts are active (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stabilization", default="on", choices=["on", "off"],
+                    help="on: ConstraintStabilization after every step, the reference's default (ConstraintStabilization.cpp:53-59); "
+                         "off: constraint-stabilization-max-iterations=0 (round 1's configuration, as example/ur10/ur10.xml:12)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary measurements (stabilization off, drift against the oracle)")
     ap.add_argument("--min-step", default="scene", choices=["scene", "default"],
                     help="scene: min-step-size of the source scenes (test/box.xml: 1e-3, bouncing-ball.xml: sqrt(eps)); "
                          "default: sqrt(eps) everywhere (TimeSteppingSimulator.cpp:48)")
@@ -316,6 +394,7 @@ def main():
     scene = W["make"](scenes, ne, 0xB200 + rank)                # every rank owns its own envs (contiguous shard of the job)
     if args.min_step == "default" and args.workload == "small":
         scene.min_step_size_env = None
+    scene.stabilization_max_iterations = _stab_iters(args)
     sim = TimeSteppingSimulator(scene, device=local_rank)
     has_rc = scene.rc is not None
     stream = torch.cuda.current_stream()
@@ -432,7 +511,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": ne, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200+rank",
                        "min_step_size": ("boxes 1e-3 (test/box.xml), balls sqrt(eps) (bouncing-ball.xml)" if args.min_step == "scene" else "sqrt(eps) everywhere") if args.workload == "small" else scene.min_step_size,
-                       "impact_model": "QP-as-LCP (default build); no-slip model for islands with mu >= 100", "stabilization": "off (max-iterations=0)",
+                       "impact_model": "QP-as-LCP (default build); no-slip model for islands with mu >= 100", "stabilization": _stab_text(args),
                        "l2": "flushed between timed steps (256 MiB write outside the events)", "parallelism": f"envs sharded x{world}"},
             "lcp_solves_per_s": lcp_solves / t_dev,
             "mini_steps_per_step": mini_steps / max(env_steps, 1.0), "lcp_solves_per_env_step": lcp_solves / max(env_steps, 1.0),
@@ -455,6 +534,11 @@ def main():
                                   "peak_source": fp64_src,
                                   "flops": "SURVEY 8(d): sum pivots*2n(n+1) + F_delassus + F_apply per solve + F_fd + F_narrow per mini-step, all from recorded counts"}},
         }
+        if not args.no_secondary:
+            out["secondary"] = _secondary(args, W, scenes, 0xB200 + rank, local_rank, flush, stream)
+        out["stabilization"] = {"iterations_per_env_step": r_cnt["stab_iterations"] / max(r_cnt["env_steps"], 1),
+                                "lcp_solves_per_env_step": r_cnt["stab_lcp_solves"] / max(r_cnt["env_steps"], 1),
+                                "line_search_failures": r_cnt["stab_line_search_failures"]}
         if not args.no_cpu_baseline:
             n_cpu, s_cpu = W["cpu_sample"]
             n_cpu = min(n_cpu, ne)

@@ -264,6 +264,11 @@ b200moby_status b200moby_lcp_lemke_host(int batch, int n, const double* M, const
 b200moby_status b200moby_lcp_fast_host(int batch, int n, const double* M, const double* q, double* z, int warm_start,
                                        double zero_tol, int* status, int* pivots, int device);
 
+/* Self-test hook: the kernels form the quotients of Lemke's ratio test several at a time with their own IEEE division
+ * (moby_b200/csrc/common.cuh b2m_divn); q_dev receives that division of x_dev[i] / y_dev[i], qref_dev the compiler's.  n must
+ * be a multiple of 4.  The two must be bit-identical (tests/test_gpu_lcp.py). */
+b200moby_status b200moby_selftest_div(int n, const double* x_dev, const double* y_dev, double* q_dev, double* qref_dev, void* stream);
+
 /* All four solvers behind one host-buffer entry point: mode 0 lcp_lemke, 1 lcp_fast, 2 lcp_lemke_regularized,
  * 3 lcp_fast_regularized (min_exp/step_exp/max_exp used by modes 2 and 3 only).  This is what the C++ facade's
  * Moby::LCP methods call (include/b200moby.hpp). */

@@ -248,8 +248,9 @@ class ContactParameters : public Base {           // defaults: ContactParameters
   unsigned NK = 4;
 };
 
-struct ConstraintStabilization {                   // ConstraintStabilization.h: only the switch the path honours
-  unsigned max_iterations = 0;                     // must stay 0: stabilization is outside the accelerated path
+struct ConstraintStabilization {                   // ConstraintStabilization.h:27-37: the members the path honours
+  unsigned max_iterations = 0xffffffffu;           // ConstraintStabilization.cpp:56: no limit by default; 0 switches stabilization off (ur10.xml:12)
+  double eps = 1.4901161193847656e-08;             // :59 (+sqrt(eps), rule H7); other values are refused at compile()
 };
 
 // ---------------------------------------------------------------------------------------------- the simulator
@@ -343,7 +344,7 @@ class TimeSteppingSimulator : public Base {
   }
   // object graph -> b200moby_scene_desc (what XMLReader::read + the simulator's containers hold in the reference)
   void compile() {
-    if (cstab.max_iterations != 0) throw std::runtime_error("constraint stabilization is not on the accelerated path: set cstab.max_iterations = 0");
+    if (cstab.eps != 1.4901161193847656e-08) throw std::runtime_error("cstab.eps: only the default sqrt(eps) (ConstraintStabilization.cpp:59) is on the accelerated path");
     const int nb = (int)bodies_.size(), ne = n_envs_;
     if (nb == 0) throw std::logic_error("no bodies");
     ensure_host();
@@ -384,7 +385,8 @@ class TimeSteppingSimulator : public Base {
     d.shape = shape.data(); d.enabled = enabled.data(); d.mass = mass.data(); d.dims = dims.data(); d.inertia = inertia.data();
     d.mu_coulomb = mu_c.data(); d.mu_viscous = mu_v.data(); d.epsilon = eps.data(); d.compliance = comp.data(); d.NK = NK.data();
     d.contact_dist_thresh = contact_dist_thresh; d.min_step_size = min_step_size; d.min_step_size_env = nullptr;
-    d.impact_model = impact_model; d.stabilization_max_iterations = 0;
+    d.impact_model = impact_model;
+    d.stabilization_max_iterations = cstab.max_iterations > 0x7fffffffu ? -1 : (int)cstab.max_iterations;   // UINT_MAX (the default) = no limit
     b200_check(b200moby_create(&d, device, &h_), "b200moby_create");
     push_state();
   }

@@ -208,8 +208,8 @@ class XMLReader {
     sim->id = sn.get_attrib("id") ? *sn.get_attrib("id") : "simulator";
     if (sn.get_attrib("min-step-size")) sim->min_step_size = num(sn, "min-step-size", sim->min_step_size);
     if (sn.get_attrib("contact-dist-thresh")) sim->contact_dist_thresh = num(sn, "contact-dist-thresh", sim->contact_dist_thresh);
-    // the reference's default is "stabilize after every step" (ConstraintStabilization.cpp:56-59); the facade honours only 0
-    sim->cstab.max_iterations = sn.get_attrib("constraint-stabilization-max-iterations") ? (unsigned)num(sn, "constraint-stabilization-max-iterations", 0.0) : 0u;
+    // absent: the reference's default, stabilize after every step without an iteration limit (ConstraintStabilization.cpp:56-59)
+    if (sn.get_attrib("constraint-stabilization-max-iterations")) sim->cstab.max_iterations = (unsigned)num(sn, "constraint-stabilization-max-iterations", 0.0);
     std::vector<RecurrentForcePtr> forces;
     for (const XMLTree* rf : sn.child_nodes("RecurrentForce")) {
       const std::string fid = rf->get_attrib("recurrent-force-id") ? *rf->get_attrib("recurrent-force-id") : "";

@@ -66,6 +66,7 @@ SYMBOLS = [
     "b200moby_get_impact_profile", "b200moby_get_kernel_profile", "b200moby_get_env_stats",
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
     "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host", "b200moby_lcp_solve_host",
+    "b200moby_selftest_div",
     "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_delassus_batched",
     "b200moby_set_joint_state", "b200moby_get_joint_state", "b200moby_set_joint_state_dev", "b200moby_get_joint_state_dev",
     "b200moby_set_joint_forces", "b200moby_rc_fwd_dyn_batched", "b200moby_rc_inertia_batched",
@@ -111,6 +112,7 @@ def lib():
     L.b200moby_lcp_fast_host.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, ip, ip, C.c_int]
     L.b200moby_lcp_solve_host.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, ip, C.c_int]
+    L.b200moby_selftest_div.argtypes = [C.c_int, dp, dp, dp, dp, vp]
     L.b200moby_fwd_dyn_batched.argtypes = [C.c_void_p, dp, dp, C.c_double, vp]
     L.b200moby_find_contacts_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, ip, dp, dp, dp, dp, ip, dp, vp]
     L.b200moby_delassus_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, ip, vp]

@@ -122,8 +122,12 @@ static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* 
       executed++;
       const double x0 = xcol[j0], x1 = xcol[j1];
       const bool c0 = h0 && d0 > PIV_TOL, c1 = h1 && d1 > PIV_TOL;
-      const double a0 = c0 ? (x0 + zero_tol) / d0 : B2M_INF, a1 = c1 ? (x1 + zero_tol) / d1 : B2M_INF;
-      const double b0 = c0 ? x0 / d0 : B2M_INF, b1 = c1 ? x1 / d1 : B2M_INF;
+      // the four quotients of the ratio test in lock step (b2m_divn: bit-identical to `/`); rows that are no candidates divide by 1
+      const double num[4] = {x0 + zero_tol, x1 + zero_tol, x0, x1}, den[4] = {c0 ? d0 : 1.0, c1 ? d1 : 1.0, c0 ? d0 : 1.0, c1 ? d1 : 1.0};
+      double quo[4];
+      b2m_divn<4>(num, den, quo);
+      const double a0 = c0 ? quo[0] : B2M_INF, a1 = c1 ? quo[1] : B2M_INF;
+      const double b0 = c0 ? quo[2] : B2M_INF, b1 = c1 ? quo[3] : B2M_INF;
       const double theta = b2m_warp_min(fmin(a0, a1));
       if (theta == B2M_INF) { status = LCP_RAY; break; }
       const int trow = -(where[t] + 1);
@@ -139,7 +143,18 @@ static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* 
     const bool s0 = h0 && i0 != r, s1 = h1 && i1 != r;      // rows this lane stores in the update: its own, except the pivot row
     __syncwarp();                               // everyone has read bas / where / column s before they change
     // pivot row, scaled: lane c forms r_c and writes it both to rvec and into row r of the tableau (its final value)
-    for (int c = lane; c < NC; c += 32) { const double rv = (c == s) ? 1.0 / p : T[c * n + r] / p; rvec[c] = rv; T[c * n + r] = rv; }
+    {
+      const int ca = lane, cb = lane + 32;                 // NC <= 66: two columns per lane, a third one only for lanes 0 and 1 at n = 63, 64
+      const bool ha = ca < NC, hb = cb < NC;
+      double* const pa = T + (ha ? ca : 0) * n + r;
+      double* const pb = T + (hb ? cb : 0) * n + r;
+      const double num[2] = {(ca == s) ? 1.0 : *pa, (cb == s) ? 1.0 : *pb}, den[2] = {p, p};
+      double rv[2];
+      b2m_divn<2>(num, den, rv);
+      if (ha) { rvec[ca] = rv[0]; *pa = rv[0]; }
+      if (hb) { rvec[cb] = rv[1]; *pb = rv[1]; }
+      for (int c = lane + 64; c < NC; c += 32) { const double v = (c == s) ? 1.0 / p : T[c * n + r] / p; rvec[c] = v; T[c * n + r] = v; }
+    }
     if (s0) q0[s * n] = 0.0;                    // the leaving variable's column (a unit vector while basic) replaces slot s: starts from zero
     if (s1) q1[s * n] = 0.0;
     if (lane == 0) {

@@ -94,6 +94,16 @@ __global__ void __launch_bounds__(256) lcp_block_kernel(LcpArgs a) {
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) solve_one(g, a, b, wd, wi);
 }
 
+// self-test of b2m_divn (common.cuh): q = the lock-step division, qref = the compiler's `/`, four pairs per thread
+__global__ void div_selftest_kernel(int n, const double* x, const double* y, double* q, double* qref) {
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i + 3 >= n) return;
+  const double xs[4] = {x[i], x[i + 1], x[i + 2], x[i + 3]}, ys[4] = {y[i], y[i + 1], y[i + 2], y[i + 3]};
+  double qs[4];
+  b2m_divn<4>(xs, ys, qs);
+  for (int k = 0; k < 4; k++) { q[i + k] = qs[k]; qref[i + k] = xs[k] / ys[k]; }
+}
+
 b200moby_status launch(LcpArgs a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (a.batch < 0 || a.n < 0 || (a.batch > 0 && a.n > 0 && (!a.M || !a.q || !a.z || !a.status))) return b2m_fail(B200MOBY_ERR_INVALID, "null pointer or negative size");
@@ -187,6 +197,15 @@ struct HostFormScratch {
     cudaStreamDestroy(s);
   }
 };
+
+b200moby_status b200moby_selftest_div(int n, const double* x_dev, const double* y_dev, double* q_dev, double* qref_dev, void* stream) {
+  if (!b2m_have_device()) return b2m_fail(B200MOBY_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback");
+  if (n < 0 || (n & 3) || !x_dev || !y_dev || !q_dev || !qref_dev) return b2m_fail(B200MOBY_ERR_INVALID, "n must be a multiple of 4 and the pointers non-null");
+  if (n == 0) return B200MOBY_OK;
+  div_selftest_kernel<<<(n / 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, x_dev, y_dev, q_dev, qref_dev);
+  B2M_CUDA(cudaGetLastError());
+  return B200MOBY_OK;
+}
 
 static b200moby_status host_form(int mode, int batch, int n, const double* M, const double* q, double* z, int warm,
                                  double piv_tol, double zero_tol, int min_exp, int step_exp, int max_exp, int* status,

@@ -16,8 +16,11 @@ Attribute semantics follow the reference's loaders:
                                                                                ConstraintSimulator.cpp:585-611, Simulator.cpp:860-928
 Bodies are numbered in the order of the simulator's DynamicBody tags (rule H4: bodies by scene index).  Pairs without a
 ContactParameters entry keep the constraint defaults (4 cone edges, mu = epsilon = 0, UnilateralConstraint.cpp:52,
-ConstraintSimulator.cpp:402-404).  Anything outside the subset (joints, articulated bodies, other primitives, geometry
-offsets on moving bodies, stabilization enabled) raises ValueError naming the construct -- nothing is silently dropped.
+ConstraintSimulator.cpp:402-404).  constraint-stabilization-max-iterations is carried into the descriptor; a file that omits
+it gets the reference's default -- stabilize after every step, no iteration limit (ConstraintStabilization.cpp:53-59,
+TimeSteppingSimulator.cpp:474) -- which the kernels run (stab_device.cuh).  Anything outside the subset (joints,
+articulated bodies, other primitives, geometry offsets on moving bodies) raises ValueError naming the construct --
+nothing is silently dropped.
 """
 import math
 import xml.etree.ElementTree as ET
@@ -95,6 +98,8 @@ def load_xml(source, n_envs=1):
     if sim.get("contact-dist-thresh") is not None:
         s.contact_dist_thresh = float(sim.get("contact-dist-thresh"))
     stab = sim.get("constraint-stabilization-max-iterations")
+    # absent: the reference's default, UINT_MAX = no limit (-1 in the descriptor); present: that many (0 = off)
+    s.stabilization_max_iterations = -1 if stab is None else min(int(stab), 2 ** 31 - 1)
     info = {"bodies": index, "stabilization_max_iterations": None if stab is None else int(stab)}
     drv = root.find("DRIVER")
     if drv is not None and drv.get("step-size") is not None:

@@ -160,3 +160,38 @@ def test_empty_and_ragged(torch_cuda):
     M, q = random_batch(5, 6, seed=1)
     z, st, piv, _ = LCP().lcp_lemke(_dev(torch, M), _dev(torch, np.abs(q)))
     assert (st.cpu().numpy() == 1).all() and not z.cpu().numpy().any()
+
+
+def test_lockstep_division_is_ieee_division(torch_cuda):
+    """b2m_divn (the lock-step division of Lemke's ratio test) against the compiler's `/`, bit for bit: 2^27 random operand
+    pairs over 600 binades and over one binade (where misrounding of a Newton-Raphson quotient would show: a seed with a
+    zero low word instead of the compiler's 1 failed the stepped-path parity tests at a rate this test now catches),
+    small-integer ratios (exact ties), powers of two, zeros, denormals, infinities and NaNs (the last take the fallback)."""
+    import torch
+    from moby_b200 import capi
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    n = 1 << 25
+    special = torch.tensor([0.0, -0.0, 1.0, -1.0, 3.0, 1e-310, -4e-320, 2.0 ** -500, 2.0 ** 500, 1e300, 1e-300, float("inf"), float("-inf"),
+                            float("nan"), 2.0 ** -1022, 1.7976931348623157e308], dtype=torch.float64, device="cuda")
+    m = special.numel()
+    for kind in ("wide", "binade", "binade", "integers"):
+        if kind == "integers":
+            x = torch.randint(1, 4096, (n,), device="cuda", generator=g).double() * 2.0 ** -12
+            y = torch.randint(1, 4096, (n,), device="cuda", generator=g).double() * 2.0 ** -9
+        else:
+            mant = torch.rand(2, n, dtype=torch.float64, device="cuda", generator=g) + 1.0
+            span = 300 if kind == "wide" else 1
+            ex = torch.randint(-span, span, (2, n), device="cuda", generator=g).double()
+            sign = torch.randint(0, 2, (2, n), device="cuda", generator=g).double() * 2 - 1
+            x, y = (sign * mant * torch.exp2(ex)).unbind(0)
+            x, y = x.clone(), y.clone()
+            del mant, ex, sign
+        x[:m * m] = special.repeat_interleave(m)
+        y[:m * m] = special.repeat(m)
+        x[m * m:m * m + 4096] = y[m * m:m * m + 4096] * 3.0            # exact quotients
+        q, qref = torch.empty_like(x), torch.empty_like(x)
+        capi.check(capi.lib().b200moby_selftest_div(n, x.data_ptr(), y.data_ptr(), q.data_ptr(), qref.data_ptr(), None))
+        torch.cuda.synchronize()
+        same = (q.view(torch.int64) == qref.view(torch.int64)) | (q.isnan() & qref.isnan())
+        assert bool(same.all()), (kind, x[~same][:4], y[~same][:4], q[~same][:4], qref[~same][:4])
+        del x, y, q, qref, same

@@ -3,7 +3,7 @@
 set -e
 name=$1; shift
 mkdir -p build/$name
-for f in capi_common lcp_kernels sim_kernels k_fused k_advance k_impact_warp k_impact_thread k_impact_block64 k_impact_block128 k_impact_block256 k_rc; do
+for f in capi_common lcp_kernels sim_kernels k_fused k_advance k_impact_warp k_impact_thread k_impact_block64 k_impact_block128 k_impact_block256 k_rc k_stabilize; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O2 -w "$@" -c moby_b200/csrc/$f.cu -o build/$name/$f.o &
 done
 wait
