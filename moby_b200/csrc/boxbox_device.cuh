@@ -4,9 +4,10 @@
 // point, qhull half-space intersection, qhull 2-D hulls + O'Rourke polygon clipping for the "kissing" case) whose
 // outputs depend on qhull's vertex order (rule H5).  The rule adopted here, by oracle and kernels alike:
 //   * distance = largest separation over the 15 separating axes (3 + 3 face normals, 9 edge x edge); negative =
-//     penetration depth.  Exact whenever the closest features are face-vertex, face-edge, face-face or edge-edge with
-//     interior closest points (every resting configuration); a lower bound for vertex-vertex / vertex-edge near misses,
-//     which only makes conservative advancement more conservative.
+//     penetration depth.  For separated boxes that is the Euclidean distance whenever the closest features are
+//     face-vertex, face-edge, face-face or edge-edge with interior closest points (every resting configuration); for
+//     vertex-vertex / vertex-edge near misses the Euclidean distance is found by exhaustion (vertices against boxes, edge
+//     pairs), so separated boxes get what V-Clip returns (test/VClipTest.cpp:24-107).
 //   * a face axis wins unless an edge axis separates by more than BB_EDGE_SLACK more;
 //   * face axis: the incident face (most anti-parallel face of the other box) is clipped against the side planes of
 //     the reference face (Sutherland-Hodgman, incident-face vertex order, clip order -u,+u,-v,+v); every clipped vertex
@@ -82,13 +83,77 @@ B2M_HD B2M_NOINL inline void boxbox_edge_points(const BodyRef& A, const BodyRef&
   pa = ca + ua * s; pb = cb + ub * t;
 }
 
-// Signed distance and closest points (pA on A, pB on B)
+// closest point of box X to the world point p (clamp in the box frame)
+B2M_HD B2M_INL V3 box_closest_world(const BodyRef& X, const V3& p) {
+  V3 v = ld3(X.x);
+  const V3 r = p - ld3(X.x);
+  for (int k = 0; k < 3; k++) { const V3 ax = box_axis(X.R, k); const double h = 0.5 * X.dims[k]; v = v + ax * fmin(fmax(dot(r, ax), -h), h); }
+  return v;
+}
+B2M_HD B2M_INL V3 box_corner(const BodyRef& X, int i) {
+  V3 v = ld3(X.x);
+  for (int k = 0; k < 3; k++) v = v + box_axis(X.R, k) * ((((i >> (2 - k)) & 1) ? -0.5 : 0.5) * X.dims[k]);
+  return v;
+}
+// edge e (0..11) of box X: axis e / 4, the four sign combinations of the other two axes; endpoints p0, p0 + d
+B2M_HD B2M_INL void box_edge(const BodyRef& X, int e, V3& p0, V3& d) {
+  const int k = e / 4, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+  const double s1 = (e & 1) ? -0.5 : 0.5, s2 = (e & 2) ? -0.5 : 0.5;
+  const V3 ak = box_axis(X.R, k);
+  p0 = (ld3(X.x) + box_axis(X.R, k1) * (s1 * X.dims[k1])) + (box_axis(X.R, k2) * (s2 * X.dims[k2]) + ak * (-0.5 * X.dims[k]));
+  d = ak * X.dims[k];
+}
+// closest points of two segments p1 + s d1, p2 + t d2 (s, t in [0,1])
+B2M_HD B2M_INL void segment_points(const V3& p1, const V3& d1, const V3& p2, const V3& d2, V3& c1, V3& c2) {
+  const V3 r = p1 - p2;
+  const double a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+  const double denom = a * e - b * b;
+  double s = (denom > 1e-300) ? fmin(fmax((b * f - c * e) / denom, 0.0), 1.0) : 0.0;
+  double t = (b * s + f) / e;
+  if (t < 0.0) { t = 0.0; s = fmin(fmax(-c / a, 0.0), 1.0); }
+  else if (t > 1.0) { t = 1.0; s = fmin(fmax((b - c) / a, 0.0), 1.0); }
+  c1 = p1 + d1 * s; c2 = p2 + d2 * t;
+}
+// Euclidean distance of two SEPARATED boxes by exhaustion: every vertex of one box against the other box, every edge
+// pair -- what Polyhedron::vclip (src/Polyhedron.cpp:1238) returns for them and what test/VClipTest.cpp:24-107 checks
+B2M_HD B2M_NOINL inline void boxbox_separated_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
+  double best = B2M_INF;
+  for (int i = 0; i < 8; i++) { const V3 v = box_corner(A, i), c = box_closest_world(B, v); const double d = norm(v - c); if (d < best) { best = d; pA = v; pB = c; } }
+  for (int i = 0; i < 8; i++) { const V3 v = box_corner(B, i), c = box_closest_world(A, v); const double d = norm(v - c); if (d < best) { best = d; pA = c; pB = v; } }
+  for (int ea = 0; ea < 12; ea++) {
+    V3 p1, d1; box_edge(A, ea, p1, d1);
+    for (int eb = 0; eb < 12; eb++) {
+      V3 p2, d2, c1, c2; box_edge(B, eb, p2, d2);
+      segment_points(p1, d1, p2, d2, c1, c2);
+      const double d = norm(c1 - c2);
+      if (d < best) { best = d; pA = c1; pB = c2; }
+    }
+  }
+  dist = best;
+}
+
+// Signed distance and closest points (pA on A, pB on B).  Touching / penetrating (largest separation over the 15 axes
+// <= 0): that separation (the penetration depth of the Minkowski difference, test/VClipTest.cpp:177-247).  Separated:
+// the separation IS the Euclidean distance when the closest features are a face and a vertex that projects into the
+// face, or two edges at interior points; otherwise (vertex-vertex, vertex-edge, clamped edge-edge) the exhaustive search.
 B2M_HD B2M_NOINL inline void boxbox_signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
   BoxBoxAxis ax; boxbox_axis(A, B, ax);
   dist = ax.s;
-  if (ax.code < 3) { pB = box_support(B, -ax.n); pA = pB - ax.n * ax.s; }
-  else if (ax.code < 6) { pA = box_support(A, ax.n); pB = pA + ax.n * ax.s; }
-  else boxbox_edge_points(A, B, (ax.code - 6) / 3, (ax.code - 6) % 3, ax.n, pA, pB);
+  bool exact = true;
+  if (ax.code < 6) {
+    const bool refA = ax.code < 3;
+    const BodyRef& Rb = refA ? A : B;
+    const int k = refA ? ax.code : ax.code - 3;
+    if (refA) { pB = box_support(B, -ax.n); pA = pB - ax.n * ax.s; }
+    else { pA = box_support(A, ax.n); pB = pA + ax.n * ax.s; }
+    const V3 onface = (refA ? pA : pB) - ld3(Rb.x);
+    for (int j = 1; j <= 2; j++) { const int kk = (k + j) % 3; if (fabs(dot(onface, box_axis(Rb.R, kk))) > 0.5 * Rb.dims[kk]) exact = false; }
+  } else {
+    boxbox_edge_points(A, B, (ax.code - 6) / 3, (ax.code - 6) % 3, ax.n, pA, pB);
+    const V3 w = pB - pA;
+    if (fabs(dot(w, ax.n) - ax.s) > 1e-12 * fmax(1.0, fabs(ax.s)) || fabs(norm(w) - fabs(ax.s)) > 1e-12 * fmax(1.0, fabs(ax.s))) exact = false;
+  }
+  if (ax.s > 0.0 && !exact) boxbox_separated_dist(A, B, dist, pA, pB);
 }
 
 // Contacts (at most 8).  out[k].n points from B toward A; b1 / b2 are filled by the caller.

@@ -3,7 +3,9 @@
 using namespace b2m;
 
 // ---- impact: islands, Delassus / LCP assembly, solve, impulses for the parked envs of one LCP class ----
-__global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt, int round, int slot, int wpb) {
+// L.ctl != nullptr: the launch runs the Lemke ladder's rungs as tasks (lcp_device.cuh): a warp that has run out of envs
+// keeps taking tasks until every warp of the launch has run out of envs and the task list is empty.
+__global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt, int round, int slot, int wpb, LadderPool L) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int w = threadIdx.x >> 5;
   EnvMem m;
@@ -14,13 +16,27 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
   unsigned long long envs = 0;
   const int count = q_size(P, round, slot);
   int* head = q_head(P, round, slot);
+  LadderCtx C; C.pool = L; C.owner = blockIdx.x * wpb + w; C.wd = m.work; C.wi = m.iwork;
   for (int i = pull_warp(head); i < count; i = pull_warp(head)) {
+    if (L.ctl) while (ladder_help_one(L, m.work, m.iwork)) {}     // rungs of a running ladder are on some env's critical path: they go before the next env
     for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
     EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
+    if (L.ctl && !cx.limit) cx.ladder = &C;
     if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) add_counters(tot, lc);
     envs++;
   }
   if (g.tid == 0) commit_counters(P, tot, envs);
+  if (L.ctl) {                                     // no env left for this warp: serve ladder tasks until the launch has none left
+    const int total_warps = gridDim.x * wpb;
+    if (g.tid == 0) { __threadfence(); atomicAdd(L.ctl + 2, 1); }
+    for (;;) {
+      if (ladder_help_one(L, m.work, m.iwork)) continue;
+      int done = 0;
+      if (g.tid == 0) { volatile int* ctl = L.ctl; done = (ctl[2] >= total_warps && ctl[1] >= min(ctl[0], L.cap)) ? 1 : 0; }
+      if (__shfl_sync(0xffffffffu, done, 0)) break;
+      __nanosleep(500);
+    }
+  }
 }
 
 const void* b2m_k_impact_warp() { return (const void*)impact_warp_kernel; }

@@ -101,7 +101,7 @@ static __device__ __forceinline__ void lemke_update_batch(double* q0, double* q1
 // tableau address of the update is base + immediate and the column walk is fully unrolled; N == 0: any n <= 64.
 template <bool SH, int N>
 static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
-                                                   int* log, int log_cap, int& nlog_io, int& piv_io, int& executed_io, int* budget) {
+                                                   int* log, int log_cap, int& nlog_io, int& piv_io, int& executed_io, int* budget, const volatile int* cancel) {
   if (SH) { __builtin_assume(__isShared(T)); __builtin_assume(__isShared(rvec)); __builtin_assume(__isShared(where)); __builtin_assume(__isShared(bas)); }
   const int n = N ? N : n_rt;
   const unsigned FULL = 0xffffffffu;
@@ -180,6 +180,7 @@ static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* 
     __syncwarp();
     if (!first) piv++;
     if (budget && --bud < 0) { status = LCP_DEFER; break; }
+    if (cancel && (piv & 63) == 63 && *cancel) { status = LCP_DEFER; break; }     // a speculative rung nobody needs any more (ladder task pool)
     first = false;
     if (leaving == t) break;
     if (piv >= MAXITER) { status = LCP_MAXITER; break; }
@@ -191,15 +192,15 @@ static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* 
 }
 template <bool SH>
 static __device__ __forceinline__ int lemke_loop_warp_n(int n, double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
-                                                        int* log, int log_cap, int& nlog, int& piv, int& executed, int* budget) {
+                                                        int* log, int log_cap, int& nlog, int& piv, int& executed, int* budget, const volatile int* cancel) {
   switch (n) {
-    case 40: return lemke_loop_warp<SH, 40>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
-    case 32: return lemke_loop_warp<SH, 32>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
-    case 30: return lemke_loop_warp<SH, 30>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
-    case 24: return lemke_loop_warp<SH, 24>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
-    case 20: return lemke_loop_warp<SH, 20>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
-    case 16: return lemke_loop_warp<SH, 16>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
-    default: return lemke_loop_warp<SH, 0>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+    case 40: return lemke_loop_warp<SH, 40>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+    case 32: return lemke_loop_warp<SH, 32>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+    case 30: return lemke_loop_warp<SH, 30>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+    case 24: return lemke_loop_warp<SH, 24>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+    case 20: return lemke_loop_warp<SH, 20>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+    case 16: return lemke_loop_warp<SH, 16>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+    default: return lemke_loop_warp<SH, 0>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
   }
 }
 #endif
@@ -214,7 +215,8 @@ static __device__ __forceinline__ int lemke_loop_warp_n(int n, double* T, double
 template <class G>
 B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
-                           int* log, int log_cap, int* log_len, int* budget = nullptr, int* executed_out = nullptr, double offdiag = -1.0) {
+                           int* log, int log_cap, int* log_len, int* budget = nullptr, int* executed_out = nullptr, double offdiag = -1.0,
+                           const volatile int* cancel = nullptr) {      // cancel: warp-owned loop only (ladder task pool); a cancelled run returns LCP_DEFER
   double* T = wd;
   double* dvec = T + (size_t)n * (n + 2);
   double* rvec = dvec + n;
@@ -259,8 +261,8 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
 #ifdef __CUDACC__
   if constexpr (G::size == 32) {
     if (n <= 64) {
-      status = __isShared(T) ? lemke_loop_warp_n<true>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget)
-                             : lemke_loop_warp<false, 0>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget);
+      status = __isShared(T) ? lemke_loop_warp_n<true>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel)
+                             : lemke_loop_warp<false, 0>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
       handled = true;
     }
   }
@@ -734,5 +736,199 @@ B2M_DEV int lcp_lemke_regularized(const G& g, int n, const double* M, int ldm, c
   g.sync();
   return LCP_UNVERIFIED;
 }
+
+#ifdef __CUDACC__
+// ---- the regularisation ladder of lcp_lemke_regularized, its rungs solved side by side ------------------------------
+// LCP.cpp:353-487 tries lambda = 0, then lambda = 10^rf for rf = min_exp, min_exp + step, ... one after the other and
+// returns the first solve that passes its checks.  lcp_lemke ignores the incoming z (rule H9), so the rungs do not
+// depend on each other: solving them at once on different warps and taking the FIRST rung that verifies, in ladder
+// order, returns exactly what the sequential loop returns -- the same z, the same status and the same counters (calls,
+// pivots and executed iterations are summed over the rungs up to the accepted one; what later rungs did is discarded).
+// Every step a dozen envs of a 65,536-env batch (different ones each step: profiles/r02_impact_profile_*) run a ladder
+// of six to ten rungs that each circle to the 1,000-pivot cap (LCP.cpp:548); the step time used to be the latency of
+// that whole ladder on one warp.  With the rungs as stealable tasks it is the latency of two rungs.
+//
+// Mechanism (impact_warp_kernel): the warp that owns the env solves rung 0 itself; if that fails it copies (M, q) to its
+// job buffer in global memory and posts one task per remaining rung to the launch's task list.  Any warp of the launch
+// that has run out of envs -- and the owner itself while it waits -- takes tasks in order, solves them with the same
+// lemke_solve / lcp_verify in its own shared-memory work area and writes status, pivots and z to the job's result
+// slots.  The owner reads the results in rung order and cancels what has not started once it has its answer.  Owners
+// execute tasks themselves while waiting, helpers never wait: no deadlock.  A task carries the job's generation so
+// that tasks of an earlier request are skipped, and a job buffer is reused only when none of its tasks is running.
+struct LadderPool {
+  int* ctl;                 // [0] tasks posted, [1] tasks taken, [2] warps of the launch that may still post
+  int* tasks;               // task list: (owner + 1) << 6 | rung, 0 = not yet published
+  int* task_gen;            // generation of the owner's request the task belongs to
+  int cap;                  // capacity of the task list
+  double* jobs; size_t job_stride;    // per owner: M (nmax^2, ld n), q (nmax), then z of rung r at nmax^2 + nmax + r * nmax
+  int* meta; size_t meta_stride;      // per owner: the words below, then 5 per rung (ready, status, ok, pivots, executed)
+  double* jobd;             // per owner 4 doubles: piv_tol, zero_tol, ZERO_TOL, offdiag
+  int nmax;
+};
+enum { LJ_GEN = 0, LJ_CANCEL, LJ_INFLIGHT, LJ_N, LJ_NRUNGS, LJ_MINEXP, LJ_STEPEXP, LJ_HDR = 8 };
+#define B2M_LADDER_MAX_RUNGS 24
+#define B2M_LADDER_PROBE 128
+B2M_HD inline size_t ladder_job_doubles(int nmax) { return (size_t)nmax * nmax + nmax + (size_t)B2M_LADDER_MAX_RUNGS * nmax; }
+B2M_HD inline size_t ladder_job_ints() { return LJ_HDR + 5 * B2M_LADDER_MAX_RUNGS; }
+struct LadderCtx { LadderPool pool; int owner; double* wd; int* wi; };    // wd / wi: this warp's Lemke work area (shared memory)
+
+// takes one task from the list and runs it; false when there was none
+static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double* wd, int* wi) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int v = 0, tg = 0, run = 0;
+  if (lane == 0) {
+    volatile int* ctl = L.ctl;
+    for (;;) {
+      const int h = ctl[1], t = min(ctl[0], L.cap);
+      if (h >= t) break;
+      if (atomicCAS(L.ctl + 1, h, h + 1) != h) continue;
+      volatile int* tk = L.tasks;
+      while ((v = tk[h]) == 0) {}
+      __threadfence();
+      tg = ((volatile int*)L.task_gen)[h];
+      int* mo = L.meta + (size_t)((v >> 6) - 1) * L.meta_stride;
+      atomicAdd(mo + LJ_INFLIGHT, 1);
+      __threadfence();
+      if (((volatile int*)mo)[LJ_GEN] == tg && ((volatile int*)mo)[LJ_CANCEL] == 0) { run = 1; ((volatile int*)mo)[LJ_HDR + 5 * (v & 63)] = 2; }   // 2: taken, running
+      else { atomicSub(mo + LJ_INFLIGHT, 1); run = 2; }      // stale or cancelled: skipped, but a task was consumed
+      break;
+    }
+  }
+  v = __shfl_sync(FULL, v, 0); run = __shfl_sync(FULL, run, 0);
+  if (run == 0) return false;
+  if (run == 2) return true;
+  const int owner = (v >> 6) - 1, rung = v & 63;
+  int* mo = L.meta + (size_t)owner * L.meta_stride;
+  const double* jd = L.jobd + (size_t)owner * 4;
+  double* job = L.jobs + (size_t)owner * L.job_stride;
+  const int n = mo[LJ_N];
+  const double* M = job; const double* q = job + (size_t)L.nmax * L.nmax;
+  double* zr = job + (size_t)L.nmax * L.nmax + L.nmax + (size_t)rung * L.nmax;
+  const double lambda = (rung == 0) ? 0.0 : pow10i(mo[LJ_MINEXP] + (rung - 1) * mo[LJ_STEPEXP]);
+  WarpGroup g(nullptr);
+  int piv = 0, ex = 0;
+  const int st = lemke_solve(g, n, M, n, q, lambda, jd[0], jd[1], zr, wd, wi, &piv, nullptr, 0, nullptr, nullptr, &ex, jd[3], (const volatile int*)(mo + LJ_CANCEL));
+  const bool ok = (st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, n, q, lambda, zr, jd[2], rung > 0, wd + (size_t)n * (n + 2));
+  __syncwarp();
+  if (lane == 0) {
+    int* r = mo + LJ_HDR + 5 * rung;
+    r[1] = st; r[2] = ok ? 1 : 0; r[3] = piv; r[4] = ex;
+    __threadfence();
+    ((volatile int*)r)[0] = 1;
+    __threadfence();
+    atomicSub(mo + LJ_INFLIGHT, 1);
+  }
+  __syncwarp();
+  return true;
+}
+
+// lcp_lemke_regularized for the warp that owns the env (g: its WarpGroup): same results and statistics as the sequential form
+static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g, const LadderCtx& C, int n, const double* M, int ldm, const double* q, double piv_tol,
+                                                              double zero_tol, int min_exp, int step_exp, int max_exp, double* z, int* pivots_out, long long* stats) {
+  const unsigned FULL = 0xffffffffu;
+  if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
+  const LadderPool& L = C.pool;
+  const double offdiag = norm_inf_offdiag(g, n, M, ldm);
+  const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf_with(g, n, M, ldm, 0.0, offdiag) * B2M_NEAR_ZERO;   // :369
+  int total = 0, piv = 0, ex = 0;
+  // Rung 0 here, but only for B2M_LADDER_PROBE pivots: a solve that is going to succeed is over long before that
+  // (profiles/: < 60 pivots at n = 40); one that is still pivoting is very likely circling towards the cap, and then the
+  // whole ladder -- rung 0 included, started afresh -- goes to the task list at once instead of after 1,000 pivots.
+  int probe = B2M_LADDER_PROBE;
+  int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, C.wd, C.wi, &piv, nullptr, 0, nullptr, &probe, &ex, offdiag);
+  int first_rung = 1;
+  if (st == LCP_DEFER) first_rung = 0;
+  else {
+    total += piv;
+    if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }
+    if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, C.wd + (size_t)n * (n + 2))) {
+      if (pivots_out) *pivots_out = piv;
+      return st;
+    }
+  }
+  int n_rungs = 1;
+  for (int rf = min_exp; rf < max_exp && n_rungs < B2M_LADDER_MAX_RUNGS; rf += step_exp) n_rungs++;
+  if (n_rungs == 1 && first_rung == 1) { if (pivots_out) *pivots_out = total; for (int i = g.tid; i < n; i += 32) z[i] = 0.0; g.sync(); return LCP_UNVERIFIED; }
+  // the job: wait until no task of this warp's previous request is running, then publish (M, q) and the rungs
+  int* mo = L.meta + (size_t)C.owner * L.meta_stride;
+  double* job = L.jobs + (size_t)C.owner * L.job_stride;
+  double* jd = L.jobd + (size_t)C.owner * 4;
+  int gen = 0;
+  if (g.tid == 0) {
+    while (((volatile int*)mo)[LJ_INFLIGHT] != 0) __nanosleep(100);
+    gen = mo[LJ_GEN] + 1;
+    mo[LJ_CANCEL] = 0; mo[LJ_N] = n; mo[LJ_NRUNGS] = n_rungs; mo[LJ_MINEXP] = min_exp; mo[LJ_STEPEXP] = step_exp;
+    jd[0] = piv_tol; jd[1] = zero_tol; jd[2] = ZERO_TOL; jd[3] = offdiag;
+    for (int k = first_rung; k < n_rungs; k++) mo[LJ_HDR + 5 * k] = 0;
+  }
+  g.sync();
+  for (int e = g.tid; e < n * n; e += 32) { const int c = e / n, r = e - c * n; job[e] = M[(size_t)c * ldm + r]; }
+  for (int i = g.tid; i < n; i += 32) job[(size_t)L.nmax * L.nmax + i] = q[i];
+  __threadfence();
+  g.sync();
+  int posted = 0;
+  if (g.tid == 0) {
+    ((volatile int*)mo)[LJ_GEN] = gen;
+    __threadfence();
+    const int cnt = n_rungs - first_rung;
+    if (((volatile int*)L.ctl)[0] + cnt <= L.cap) {
+      const int base = atomicAdd(L.ctl, cnt);
+      if (base + cnt <= L.cap) {
+        posted = 1;
+        for (int k = first_rung; k < n_rungs; k++) { const int idx = base + k - first_rung; L.task_gen[idx] = gen; __threadfence(); ((volatile int*)L.tasks)[idx] = ((C.owner + 1) << 6) | k; }
+      } else {                                            // the list filled up in between: publish skip entries so that takers do not wait on them
+        for (int k = first_rung; k < n_rungs; k++) { const int idx = base + k - first_rung; if (idx < L.cap) { L.task_gen[idx] = -1; __threadfence(); ((volatile int*)L.tasks)[idx] = ((C.owner + 1) << 6) | k; } }
+      }
+    }
+  }
+  posted = __shfl_sync(FULL, posted, 0);
+  int result = LCP_UNVERIFIED;
+  if (!posted) {                                          // task list full: the remaining rungs one after the other, as the generic wrapper does
+    if (first_rung == 0) {
+      g.sync();
+      st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, C.wd, C.wi, &piv, nullptr, 0, nullptr, nullptr, &ex, offdiag);
+      total += piv;
+      if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }
+      if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, 0.0, z, ZERO_TOL, false, C.wd + (size_t)n * (n + 2))) { if (pivots_out) *pivots_out = piv; return st; }
+    }
+    int attempt = 0;
+    for (int rf = min_exp; rf < max_exp && result == LCP_UNVERIFIED; rf += step_exp, attempt++) {
+      const double lambda = pow10i(rf);
+      g.sync();
+      st = lemke_solve(g, n, M, ldm, q, lambda, piv_tol, zero_tol, z, C.wd, C.wi, &piv, nullptr, 0, nullptr, nullptr, &ex, offdiag);
+      total += piv;
+      if (stats && g.tid == 0) { stats[0]++; stats[1] += piv; stats[2] += ex; }
+      if ((st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, ldm, q, lambda, z, ZERO_TOL, true, C.wd + (size_t)n * (n + 2))) result = LCP_REGULARIZED + attempt;
+    }
+  }
+  for (int k = first_rung; posted && k < n_rungs; k++) {
+    volatile int* r = mo + LJ_HDR + 5 * k;
+    for (;;) {
+      int ready = 0;
+      if (g.tid == 0) ready = r[0];
+      ready = __shfl_sync(FULL, ready, 0);
+      if (ready == 1) break;
+      if (ready == 2 || !ladder_help_one(L, C.wd, C.wi)) __nanosleep(200);      // somebody is on it: wait; not taken yet: take tasks (maybe this one)
+    }
+    __threadfence();
+    const int pk = r[3], ek = r[4], okk = r[2];
+    total += pk;
+    if (stats && g.tid == 0) { stats[0]++; stats[1] += pk; stats[2] += ek; }
+    if (okk) {
+      const double* zr = job + (size_t)L.nmax * L.nmax + L.nmax + (size_t)k * L.nmax;
+      for (int i = g.tid; i < n; i += 32) z[i] = ((const volatile double*)zr)[i];
+      result = (k == 0) ? r[1] : LCP_REGULARIZED + (k - 1);
+      if (k == 0) total = pk;                           // the wrapper reports the first solve's own count when it is accepted (:252-255)
+      break;
+    }
+  }
+  if (g.tid == 0) { ((volatile int*)mo)[LJ_CANCEL] = 1; __threadfence(); }
+  if (pivots_out) *pivots_out = total;
+  if (result == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += 32) z[i] = 0.0; }
+  g.sync();
+  return result;
+}
+#endif
 
 }  // namespace b2m

@@ -183,7 +183,7 @@ enum { S_NPAIRS = 0, S_NCON = 1, S_NC = 2, S_NGC = 3, S_N = 4, S_NISL = 5, S_FLA
 // Per-env solver budget: when `limit` is set and an env's pivots in this launch exceed it, the env's step is
 // abandoned without touching its stored state and the env is queued for the block-per-env kernel, which redoes the
 // step with many more threads per pivot (same arithmetic, same results).  Keeps one hard LCP from holding a whole SM.
-struct EnvCtx { int budget; bool limit; };
+struct EnvCtx { int budget; bool limit; void* ladder = nullptr; };   // ladder: LadderCtx of an impact_warp_kernel warp (the rungs of the Lemke ladder become tasks other warps take, lcp_device.cuh)
 
 // per-env solver statistics (SimParams::env_stat): the counters an env added to `lc` since `base` was taken
 struct EnvStatBase { unsigned long long fail, lemke, fast, solves, pivots; };
@@ -1197,7 +1197,15 @@ B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m
   if (st == LCP_UNVERIFIED) {
     g.sync();
     stats[0] = stats[1] = stats[2] = 0;
-    { B2M_PROF_T0(m); st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud); B2M_PROF_ADD(m, g, PH_LEMKE); }   // :222-225
+    { B2M_PROF_T0(m);
+#ifdef __CUDACC__
+      if constexpr (G::size == 32) {
+        if (cx.ladder) st = lcp_lemke_regularized_pool(g, *(const LadderCtx*)cx.ladder, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, &piv, stats);
+        else st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);
+      } else
+#endif
+      st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);   // :222-225
+      B2M_PROF_ADD(m, g, PH_LEMKE); }
     if (st == LCP_DEFER) return false;
     lemke_calls = stats[0]; pivots += stats[1]; executed += stats[2];
     if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) { lc[CNT_LCP_FAIL]++; m.scal[S_FAILED] = 1; } }
@@ -1756,7 +1764,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
       const size_t ne = P.n_envs;
       const long long n = m.scal[S_N];
       P.tap_prof[e] = clock64() - t0; P.tap_prof[ne + e] = (long long)(lc[CNT_PIVOTS] - p0);
-      P.tap_prof[2 * ne + e] = n > 0 ? (long long)((lc[CNT_PIVOT_FLOPS] - f0) / (2ull * n * (n + 1))) : 0; P.tap_prof[3 * ne + e] = n;
+      P.tap_prof[2 * ne + e] = n > 0 ? (long long)((lc[CNT_PIVOT_FLOPS] - f0) / (2ull * n * (n + 1))) : 0; P.tap_prof[3 * ne + e] = n + 1000ll * P.kslot;   // LCP dimension + 1000 x the kernel slot that ran the env
     }
 #endif
   }

@@ -41,6 +41,8 @@ struct b200moby_sim {
   int thread_budget = 12;    // solver iterations a thread-per-env impact may spend on one env before deferring it
   int adv_thread = -1;       // >= 0: the advance phase runs one thread per env (b2m_k_advance_thread(adv_thread)); -1: warp per env
   std::vector<ClassPlan> classes;
+  LadderPool pool;           // task pool of the Lemke ladder (lcp_device.cuh) for the hard-queue / straggler launches; ctl == nullptr: off
+  int pool_owners = 0;
   ClassPlan straggler;       // full-size kernel (warp per env while the scene's LCPs fit one, else a 256-thread block) for envs over their pivot budget and for the hard queue
   ClassPlan fullws;          // scratch of the full-working-set warp kernels (finish, fused, stage) when it exceeds shared memory
   int fin_grid = 1;
@@ -281,6 +283,21 @@ b200moby_status plan_launch(b200moby_sim* h) {
     sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : (h->nmax <= 64 ? 32 : 128));   // n <= 64: the warp-owned pivot loops (lcp_device.cuh), no block barriers   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
     if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
     if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
+    // the Lemke ladder as a task pool: one job buffer per warp of the hard-queue / straggler launches
+    memset(&h->pool, 0, sizeof(h->pool));
+    if (sg.threads == 32 && !sg.gscratch && h->nmax <= 64 && h->P.model == 0 && env_int("B200MOBY_LADDER", 1) != 0) {
+      LadderPool& L = h->pool;
+      h->pool_owners = sg.grid * sg.wpb;
+      L.nmax = h->nmax; L.cap = h->pool_owners * 64;
+      L.job_stride = ladder_job_doubles(h->nmax); L.meta_stride = ladder_job_ints();
+      b200moby_status s2;
+      if ((s2 = dev_zero(h, (size_t)4, &L.ctl)) != B200MOBY_OK) return s2;
+      if ((s2 = dev_zero(h, (size_t)L.cap, &L.tasks)) != B200MOBY_OK) return s2;
+      if ((s2 = dev_zero(h, (size_t)L.cap, &L.task_gen)) != B200MOBY_OK) return s2;
+      if ((s2 = dev_zero(h, L.job_stride * h->pool_owners, &L.jobs)) != B200MOBY_OK) return s2;
+      if ((s2 = dev_zero(h, L.meta_stride * h->pool_owners, &L.meta)) != B200MOBY_OK) return s2;
+      if ((s2 = dev_zero(h, (size_t)4 * h->pool_owners, &L.jobd)) != B200MOBY_OK) return s2;
+    }
     // Large LCPs (n in the hundreds): a warp would spend seconds per solve, so whatever the rounds leave over is finished
     // by one block per env, and more rounds keep that remainder small (each extra round is a handful of short launches).
     h->finblock.threads = 32;
@@ -324,6 +341,25 @@ b200moby_status timed_launch(b200moby_sim* h, int kslot, const void* kernel, dim
   return B200MOBY_OK;
 }
 
+// one launch of an impact kernel (warp per env or block per env, per the plan) over queue `slot`; pool: the launch runs
+// the rungs of the Lemke ladder as tasks (lcp_device.cuh) -- its task list is cleared on the launch's stream first
+b200moby_status launch_impact(b200moby_sim* h, int kslot, const ClassPlan& cp, SimParams& Pk, double dt, int r, int slot, bool pool, cudaStream_t sc) {
+  Pk.gscratch = cp.gscratch; Pk.gstride = cp.gstride; Pk.kslot = kslot;
+  if (cp.threads == 32) {
+    LadderPool L; memset(&L, 0, sizeof(L));
+    if (pool && h->pool.ctl && cp.grid * cp.wpb <= h->pool_owners) {
+      L = h->pool;
+      B2M_CUDA(cudaMemsetAsync(L.ctl, 0, sizeof(int) * 4, sc));
+      B2M_CUDA(cudaMemsetAsync(L.tasks, 0, sizeof(int) * L.cap, sc));
+    }
+    int wpb = cp.wpb;
+    void* a[] = {&Pk, &dt, &r, &slot, &wpb, &L};
+    return timed_launch(h, kslot, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
+  }
+  void* a[] = {&Pk, &dt, &r, &slot};
+  return timed_launch(h, kslot, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc);
+}
+
 // ConstraintStabilization::stabilize for every env (TimeSteppingSimulator.cpp:95-98), after the step's last kernel
 b200moby_status launch_stabilize(b200moby_sim* h, cudaStream_t s) {
   if (h->P.stab_max_iterations == 0) return B200MOBY_OK;
@@ -356,14 +392,10 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
     const bool conc = h->concurrent && h->classes.size() > 1;
     if (conc) B2M_CUDA(cudaEventRecord(h->fork, s));
     if (P.hard_cost > 0) {   // the expensive envs first, next to the classes
-      ClassPlan& cp = h->straggler;
-      int slot = B2M_SLOT_HARD;
-      SimParams Ph = P; Ph.gscratch = cp.gscratch; Ph.gstride = cp.gstride; Ph.kslot = 3 + ncls; Ph.pivot_budget = 0;
+      SimParams Ph = P; Ph.pivot_budget = 0;
       cudaStream_t sc = conc ? h->hard_stream : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
-      if (cp.threads == 32) { void* a[] = {&Ph, &dt, &r, &slot, &cp.wpb}; st = timed_launch(h, 3 + ncls, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc); }
-      else { void* a[] = {&Ph, &dt, &r, &slot}; st = timed_launch(h, 3 + ncls, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc); }
-      if (st != B200MOBY_OK) return st;
+      if ((st = launch_impact(h, 3 + ncls, h->straggler, Ph, dt, r, B2M_SLOT_HARD, true, sc)) != B200MOBY_OK) return st;
       if (conc) { B2M_CUDA(cudaEventRecord(h->hard_done, sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->hard_done, 0)); }
     }
     for (size_t c = 0; c < h->classes.size(); c++) {
@@ -376,24 +408,16 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
         Pc.pivot_budget = h->thread_budget;
         void* a[] = {&Pc, &dt, &r, &slot};
         st = timed_launch(h, 1 + (int)c, b2m_k_impact_thread(cp.tvariant), dim3(cp.grid), dim3(128), a, 0, sc);
-      } else if (cp.threads == 32) {
-        void* a[] = {&Pc, &dt, &r, &slot, &cp.wpb};
-        st = timed_launch(h, 1 + (int)c, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
       } else {
-        Pc.pivot_budget = 0;
-        void* a[] = {&Pc, &dt, &r, &slot};
-        st = timed_launch(h, 1 + (int)c, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc);
+        if (cp.threads != 32) Pc.pivot_budget = 0;
+        st = launch_impact(h, 1 + (int)c, cp, Pc, dt, r, slot, false, sc);
       }
       if (st != B200MOBY_OK) return st;
       if (conc) { B2M_CUDA(cudaEventRecord(h->side_done[c], sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->side_done[c], 0)); }
     }
     if (P.pivot_budget > 0 || h->any_thread_class) {
-      int slot = B2M_SLOT_STRAGGLER;
-      ClassPlan& cp = h->straggler;
-      SimParams Ps = P; Ps.gscratch = cp.gscratch; Ps.gstride = cp.gstride; Ps.kslot = 1 + ncls; Ps.pivot_budget = 0;
-      if (cp.threads == 32) { void* a[] = {&Ps, &dt, &r, &slot, &cp.wpb}; st = timed_launch(h, 1 + ncls, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, s); }
-      else { void* a[] = {&Ps, &dt, &r, &slot}; st = timed_launch(h, 1 + ncls, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, s); }
-      if (st != B200MOBY_OK) return st;
+      SimParams Ps = P; Ps.pivot_budget = 0;
+      if ((st = launch_impact(h, 1 + ncls, h->straggler, Ps, dt, r, B2M_SLOT_STRAGGLER, true, s)) != B200MOBY_OK) return st;
     }
   }
   { int r = h->rounds - 1; SimParams Pf = P; Pf.kslot = 2 + ncls;

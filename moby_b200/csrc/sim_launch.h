@@ -11,7 +11,7 @@ const void* b2m_k_advance_thread(int cls); // (SimParams P, double dt, int round
 #define B2M_THREAD_ND1 5632
 #define B2M_THREAD_NI1 384
 const void* b2m_k_impact_thread(int variant);   // (SimParams P, double dt, int round, int slot)
-const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb)
+const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb, LadderPool L)
 const void* b2m_k_impact_block64();
 const void* b2m_k_impact_block128();
 const void* b2m_k_impact_block256();

@@ -6,7 +6,9 @@
 // that depends on qhull's output.  qhull is not available and its vertex order cannot be restated, so oracle and product
 // adopt one analytic rule (a deliberate, documented deviation; contact SETS of resting boxes match the reference's
 // polygon-intersection vertices, contact ORDER is canonical):
-//   1. signed distance = max separation over the 15 separating axes (face normals of A, of B, edge x edge);
+//   1. signed distance = max separation over the 15 separating axes (face normals of A, of B, edge x edge) -- the
+//      penetration depth when negative; for separated boxes whose closest features are not face-vertex / interior
+//      edge-edge, the Euclidean distance by exhaustion (vertices against boxes, edge pairs), as V-Clip returns it;
 //      a face axis is kept unless an edge axis separates by more than 1e-9 more;
 //   2. face axis: clip the incident face of the other box (Sutherland-Hodgman) against the side planes of the reference
 //      face, in the order -u, +u, -v, +v with (u, v) the two axes following the face axis cyclically; each surviving
@@ -89,12 +91,78 @@ static inline void edge_points(const Box& A, const Box& B, int i, int j, Vec3 n,
   pa = add(ca, mul(ua, s)); pb = add(cb, mul(ub, t));
 }
 
+// closest point of box X to the world point p (clamp in the box frame)
+static inline Vec3 closest_on_box(const Box& X, Vec3 p) {
+  Vec3 v = X.c;
+  const Vec3 r = sub(p, X.c);
+  for (int k = 0; k < 3; k++) { const double h = 0.5 * X.ext[k]; v = add(v, mul(X.ax[k], std::fmin(std::fmax(dt(r, X.ax[k]), -h), h))); }
+  return v;
+}
+static inline Vec3 corner(const Box& X, int i) {
+  Vec3 v = X.c;
+  for (int k = 0; k < 3; k++) v = add(v, mul(X.ax[k], (((i >> (2 - k)) & 1) ? -0.5 : 0.5) * X.ext[k]));
+  return v;
+}
+// edge e (0..11) of box X: axis e / 4, the four sign combinations of the other two axes; endpoints p0, p0 + d
+static inline void edge_of(const Box& X, int e, Vec3& p0, Vec3& d) {
+  const int k = e / 4, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+  const double s1 = (e & 1) ? -0.5 : 0.5, s2 = (e & 2) ? -0.5 : 0.5;
+  p0 = add(add(X.c, mul(X.ax[k1], s1 * X.ext[k1])), add(mul(X.ax[k2], s2 * X.ext[k2]), mul(X.ax[k], -0.5 * X.ext[k])));
+  d = mul(X.ax[k], X.ext[k]);
+}
+// closest points of two segments p1 + s d1, p2 + t d2 (s, t in [0,1])
+static inline void segment_points(Vec3 p1, Vec3 d1, Vec3 p2, Vec3 d2, Vec3& c1, Vec3& c2) {
+  const Vec3 r = sub(p1, p2);
+  const double a = dt(d1, d1), e = dt(d2, d2), f = dt(d2, r), c = dt(d1, r), b = dt(d1, d2);
+  const double denom = a * e - b * b;
+  double s = (denom > 1e-300) ? std::fmin(std::fmax((b * f - c * e) / denom, 0.0), 1.0) : 0.0;
+  double t = (b * s + f) / e;
+  if (t < 0.0) { t = 0.0; s = std::fmin(std::fmax(-c / a, 0.0), 1.0); }
+  else if (t > 1.0) { t = 1.0; s = std::fmin(std::fmax((b - c) / a, 0.0), 1.0); }
+  c1 = add(p1, mul(d1, s)); c2 = add(p2, mul(d2, t));
+}
+// Euclidean distance of two SEPARATED boxes by exhaustion: every vertex of one box against the other box, every edge
+// pair -- what Polyhedron::vclip (src/Polyhedron.cpp:1238) returns for them and what test/VClipTest.cpp:24-107 checks
+static inline void separated_dist(const Box& A, const Box& B, double& dist, Vec3& pA, Vec3& pB) {
+  double best = 1.7976931348623157e308;
+  for (int i = 0; i < 8; i++) { const Vec3 v = corner(A, i), c = closest_on_box(B, v); const double d = len(sub(v, c)); if (d < best) { best = d; pA = v; pB = c; } }
+  for (int i = 0; i < 8; i++) { const Vec3 v = corner(B, i), c = closest_on_box(A, v); const double d = len(sub(v, c)); if (d < best) { best = d; pA = c; pB = v; } }
+  for (int ea = 0; ea < 12; ea++) {
+    Vec3 p1, d1; edge_of(A, ea, p1, d1);
+    for (int eb = 0; eb < 12; eb++) {
+      Vec3 p2, d2, c1, c2; edge_of(B, eb, p2, d2);
+      segment_points(p1, d1, p2, d2, c1, c2);
+      const double d = len(sub(c1, c2));
+      if (d < best) { best = d; pA = c1; pB = c2; }
+    }
+  }
+  dist = best;
+}
+
+// Signed distance and closest points.  Touching / penetrating (largest separation over the 15 axes <= 0): that separation
+// (the penetration depth of the Minkowski difference, test/VClipTest.cpp:177-247).  Separated: the separation IS the
+// Euclidean distance when the closest features are a face and a vertex that projects into the face, or two edges at
+// interior points; otherwise (vertex-vertex, vertex-edge, clamped edge-edge) the exhaustive search above.
 static inline void signed_dist(const Box& A, const Box& B, double& dist, Vec3& pA, Vec3& pB) {
   const Axis ax = best_axis(A, B);
   dist = ax.sep;
-  if (ax.code < 3) { pB = support(B, mul(ax.n, -1.0)); pA = sub(pB, mul(ax.n, ax.sep)); }
-  else if (ax.code < 6) { pA = support(A, ax.n); pB = add(pA, mul(ax.n, ax.sep)); }
-  else edge_points(A, B, (ax.code - 6) / 3, (ax.code - 6) % 3, ax.n, pA, pB);
+  bool exact = true;
+  if (ax.code < 6) {
+    const bool refA = ax.code < 3;
+    const Box& Rb = refA ? A : B;
+    const int k = refA ? ax.code : ax.code - 3;
+    if (refA) { pB = support(B, mul(ax.n, -1.0)); pA = sub(pB, mul(ax.n, ax.sep)); }
+    else { pA = support(A, ax.n); pB = add(pA, mul(ax.n, ax.sep)); }
+    const Vec3 onface = sub(refA ? pA : pB, Rb.c);
+    for (int j = 1; j <= 2; j++) { const int kk = (k + j) % 3; if (std::fabs(dt(onface, Rb.ax[kk])) > 0.5 * Rb.ext[kk]) exact = false; }
+  } else {
+    const int i = (ax.code - 6) / 3, j = (ax.code - 6) % 3;
+    edge_points(A, B, i, j, ax.n, pA, pB);
+    // interior closest points: the connecting segment is (anti)parallel to the axis and as long as the separation
+    const Vec3 w = sub(pB, pA);
+    if (std::fabs(dt(w, ax.n) - ax.sep) > 1e-12 * std::fmax(1.0, std::fabs(ax.sep)) || std::fabs(len(w) - std::fabs(ax.sep)) > 1e-12 * std::fmax(1.0, std::fabs(ax.sep))) exact = false;
+  }
+  if (ax.sep > 0.0 && !exact) separated_dist(A, B, dist, pA, pB);
 }
 
 struct Point { Vec3 p; double violation; };

@@ -9,6 +9,7 @@
 #include "oracle_lcp.h"
 #include "oracle_sim.h"
 #include "oracle_rc.h"
+#include "oracle_boxbox.h"
 
 using namespace oracle;
 
@@ -321,6 +322,21 @@ void oracle_batch_env_stats(void* h, int* stat) {
     const Counters& k = B->sims[i].cnt;
     stat[i] = (int)k.lcp_failures; stat[n + i] = (int)k.lemke_calls; stat[2 * n + i] = (int)k.lcp_fast_calls; stat[3 * n + i] = (int)k.lcp_solves; stat[4 * n + i] = (int)k.pivots;
   }
+}
+
+// box-box signed distance of oracle_boxbox.h for two posed boxes: box = centre[3], rotation R[9] row-major, edge lengths[3];
+// out = dist, pA[3], pB[3]
+void oracle_boxbox_dist(const double* A, const double* B, double* out) {
+  bb::Box X[2];
+  const double* src[2] = {A, B};
+  for (int b = 0; b < 2; b++) {
+    X[b].c = {src[b][0], src[b][1], src[b][2]};
+    const double* R = src[b] + 3;
+    for (int k = 0; k < 3; k++) { X[b].ax[k] = {R[k], R[3 + k], R[6 + k]}; X[b].ext[k] = src[b][12 + k]; }
+  }
+  bb::Vec3 pA{0, 0, 0}, pB{0, 0, 0};
+  bb::signed_dist(X[0], X[1], out[0], pA, pB);
+  out[1] = pA.x; out[2] = pA.y; out[3] = pA.z; out[4] = pB.x; out[5] = pB.y; out[6] = pB.z;
 }
 
 // ---- reduced-coordinate articulated body (oracle_rc.h) ----

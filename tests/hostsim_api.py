@@ -35,6 +35,7 @@ def lib():
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hostsim_rc.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8
         L.hostsim_set_env_stat.argtypes = [C.c_void_p]
+        L.hostsim_boxbox_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -104,6 +105,16 @@ def lcp(mode, M, q, z0=None, piv_tol=-1.0, zero_tol=-1.0, min_exp=-20, step_exp=
     st = lib().hostsim_lcp(mode, n, p(Mf), p(q), p(z), 0 if z0 is None else 1, piv_tol, zero_tol, min_exp, step_exp, max_exp,
                                   C.byref(piv), p(log) if want_log else None, log_cap, C.byref(ll))
     return st, z, piv.value, log[:min(ll.value, log_cap)].copy()
+
+
+def boxbox_dist(cA, RA, extA, cB, RB, extB):
+    """Signed distance and closest points of two posed boxes through the kernels' device code: (dist, pA, pB)."""
+    A = np.concatenate([np.asarray(cA, np.float64), np.asarray(RA, np.float64).ravel(), np.asarray(extA, np.float64)])
+    B = np.concatenate([np.asarray(cB, np.float64), np.asarray(RB, np.float64).ravel(), np.asarray(extB, np.float64)])
+    out = np.zeros(7)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hostsim_boxbox_dist(p(A), p(B), p(out))
+    return out[0], out[1:4].copy(), out[4:7].copy()
 
 
 def rc_eval(body, what, q, qd, tau=None, gravity=(0.0, -9.81, 0.0), env=0):

@@ -60,6 +60,7 @@ def lib():
         for f in (L.oracle_sim_set_joint_state, L.oracle_sim_get_joint_state):
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_sim_set_joint_forces.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_boxbox_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_rc_fwd_dyn.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
         L.oracle_rc_inertia.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 5
         L.oracle_rc_links.argtypes = [C.POINTER(RcDesc)] + [C.c_void_p] * 10
@@ -251,6 +252,15 @@ class OracleBatch:
         st = np.zeros((5, n), np.int32)
         lib().oracle_batch_env_stats(self.h, _p(st))
         return dict(lcp_failures=st[0], lemke_calls=st[1], lcp_fast_calls=st[2], lcp_solves=st[3], pivots=st[4])
+
+
+def boxbox_dist(cA, RA, extA, cB, RB, extB):
+    """Signed distance and closest points of two posed boxes (oracle/oracle_boxbox.h): returns (dist, pA, pB)."""
+    A = np.concatenate([np.asarray(cA, np.float64), np.asarray(RA, np.float64).ravel(), np.asarray(extA, np.float64)])
+    B = np.concatenate([np.asarray(cB, np.float64), np.asarray(RB, np.float64).ravel(), np.asarray(extB, np.float64)])
+    out = np.zeros(7)
+    lib().oracle_boxbox_dist(_p(A), _p(B), _p(out))
+    return out[0], out[1:4].copy(), out[4:7].copy()
 
 
 # ---- reduced-coordinate articulated body (oracle/oracle_rc.h) ----

@@ -108,3 +108,72 @@ def test_stack_device_code_matches_oracle(n_boxes, steps, yaw):
     if yaw == 0.0:
         assert ch["max_lcp_n"] == 4 * n_boxes * 8
     assert ch["overflow"] == 0 and ch["lcp_failures"] == 0
+
+
+# ---- test/VClipTest.cpp re-expressed: box-box signed distance against an independent computation ----
+def _rand_pose(rng, lo, hi):
+    q = rng.uniform(-1, 1, 4)                       # VClipTest.cpp:60-68: quaternion from four uniforms, normalised
+    q /= np.linalg.norm(q)
+    return rng.uniform(lo, hi, 3), scenes._rotmat(np.array([q[0], q[1], q[2], q[3]]))
+
+
+def _independent_distance(cB, RB):
+    """Distance of two separated 2x2x2 boxes (A at the origin, axis-aligned) by bound-constrained minimisation of
+    |a - (cB + RB b)|^2 over a, b in [-1,1]^3 -- a convex problem; no feature enumeration involved."""
+    from scipy.optimize import minimize
+    def f(u):
+        d = u[:3] - (cB + RB @ u[3:])
+        J = np.concatenate([2 * d, -2 * (RB.T @ d)])
+        return d @ d, J
+    best = np.inf
+    for start in (np.zeros(6), np.concatenate([np.sign(cB), -np.sign(RB.T @ cB)])):
+        r = minimize(f, start, jac=True, bounds=[(-1, 1)] * 6, method="L-BFGS-B", options=dict(maxiter=2000, ftol=1e-18, gtol=1e-14))
+        best = min(best, r.fun)
+    return np.sqrt(best)
+
+
+def test_vclip_apart_boxes_distance():
+    """test/VClipTest.cpp:24-107 (Apart_BB_VClip): two 2x2x2 boxes, the second translated by U[2.5,10]^3 and rotated at
+    random; the signed distance must equal the polytope distance to 1e-6 (the gtest's TOL).  Oracle and device code."""
+    rng = np.random.default_rng(24)
+    I, ext = np.eye(3), np.full(3, 2.0)
+    worst = 0.0
+    kinds = set()
+    for _ in range(300):
+        cB, RB = _rand_pose(rng, 2.5, 10.0)
+        ref = _independent_distance(cB, RB)
+        d_o, pA, pB = O.boxbox_dist(np.zeros(3), I, ext, cB, RB, ext)
+        d_h, pAh, pBh = H.boxbox_dist(np.zeros(3), I, ext, cB, RB, ext)
+        assert d_o == d_h and np.array_equal(pA, pAh) and np.array_equal(pB, pBh)              # device code == oracle, bit for bit
+        assert abs(d_o - ref) < 1e-6, (d_o, ref)
+        assert abs(np.linalg.norm(pA - pB) - d_o) < 1e-9                                         # the closest points realise the distance
+        assert np.abs(pA).max() <= 1 + 1e-12 and np.abs(RB.T @ (pB - cB)).max() <= 1 + 1e-12     # ... and lie on the boxes
+        worst = max(worst, abs(d_o - ref))
+        onA = np.isclose(np.abs(pA), 1.0).sum()
+        onB = np.isclose(np.abs(RB.T @ (pB - cB)), 1.0).sum()
+        kinds.add((int(onA), int(onB)))
+    assert (3, 3) in kinds or (3, 2) in kinds or (2, 3) in kinds         # vertex-vertex / vertex-edge cases were among them
+
+
+def test_vclip_penetrating_boxes_depth():
+    """test/VClipTest.cpp:177-247 (Penetrating_BB_Vclip): translation U[-1,1]^3; the signed distance of overlapping boxes is
+    the signed distance of the origin to their Minkowski difference (here: its convex hull through scipy / qhull, facet
+    equations n.x + c <= 0 inside)."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(177)
+    I, ext = np.eye(3), np.full(3, 2.0)
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float)
+    n_pen = 0
+    for _ in range(200):
+        cB, RB = _rand_pose(rng, -1.0, 1.0)
+        VB = cB + corners @ RB.T
+        md = (corners[:, None, :] - VB[None, :, :]).reshape(-1, 3)
+        hull = ConvexHull(md)
+        ref = hull.equations[:, 3].max()                              # signed distance of the origin (negative inside)
+        d_o, _, _ = O.boxbox_dist(np.zeros(3), I, ext, cB, RB, ext)
+        d_h, _, _ = H.boxbox_dist(np.zeros(3), I, ext, cB, RB, ext)
+        assert d_o == d_h
+        if ref < 0:
+            n_pen += 1
+            assert abs(d_o - ref) < 1e-6, (d_o, ref)
+    assert n_pen > 150

@@ -274,3 +274,24 @@ def test_thread_kernel_counters_do_not_depend_on_the_budget(torch_cuda):
     for c, (q, v) in res[1:]:
         assert c == res[0][0], (c, res[0][0])
         assert np.array_equal(q, res[0][1][0]) and np.array_equal(v, res[0][1][1])
+
+
+def test_ladder_task_pool_gives_the_sequential_results(torch_cuda):
+    """The hard-queue / straggler launches run the rungs of lcp_lemke_regularized as tasks that idle warps take
+    (lcp_device.cuh: lcp_lemke_regularized_pool): states and every counter must equal the run with the pool switched off
+    (B200MOBY_LADDER=0: rungs one after the other on the env's own warp)."""
+    import os
+    from moby_b200 import TimeSteppingSimulator
+    sc = scenes.small_lcp_batch(16384, seed=0xB200)
+    res = []
+    for ladder in ("1", "0"):
+        os.environ["B200MOBY_LADDER"] = ladder
+        try:
+            sim = TimeSteppingSimulator(sc)
+            sim.step(1e-3, 350)
+            res.append((sim.counters(), sim.get_state()))
+        finally:
+            del os.environ["B200MOBY_LADDER"]
+    assert res[0][0] == res[1][0], (res[0][0], res[1][0])
+    assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
+    assert res[0][0]["lemke_calls"] > res[0][0]["lcp_solves"] // 50 and res[0][0]["lemke_calls"] > 20000       # ladders beyond rung 0 were run

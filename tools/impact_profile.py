@@ -16,6 +16,7 @@ for s in range(5):
     torch.cuda.synchronize()
     p = sim.impact_profile()
     cyc, piv, ex, n = p[:4]
+    kslot, n = n // 1000, n % 1000
     ph = p[4:]
     m = cyc > 0
     r = dict(step=s, envs=int(m.sum()), cyc_sum=int(cyc.sum()), cyc_pct=[float(np.percentile(cyc[m], x)) for x in (50, 90, 99, 99.9, 100)],
@@ -26,6 +27,9 @@ for s in range(5):
         by_n[int(nn)] = dict(phases=[round(float(ph[j][k].mean())) for j in range(9)], envs=int(k.sum()), cyc_mean=float(cyc[k].mean()), cyc_max=int(cyc[k].max()), cyc_sum=int(cyc[k].sum()), piv_mean=float(piv[k].mean()), ex_mean=float(ex[k].mean()))
     r["by_n"] = by_n
     top = np.argsort(cyc)[-8:]
-    r["top"] = [dict(e=int(e), cyc=int(cyc[e]), piv=int(piv[e]), ex=int(ex[e]), n=int(n[e])) for e in top]
+    r["top"] = [dict(e=int(e), cyc=int(cyc[e]), piv=int(piv[e]), ex=int(ex[e]), n=int(n[e]), kslot=int(kslot[e]), fast_cyc=int(ph[5][e]), lemke_cyc=int(ph[6][e])) for e in top]
+    r["by_kslot"] = {int(k): dict(envs=int((m & (kslot == k)).sum()), cyc_max=int(cyc[m & (kslot == k)].max()), cyc_sum=int(cyc[m & (kslot == k)].sum()), ex_max=int(ex[m & (kslot == k)].max())) for k in np.unique(kslot[m])}
+    big = np.where(m & (ex >= 500))[0]
+    r["long"] = [dict(e=int(e), ex=int(ex[e]), cyc=int(cyc[e]), kslot=int(kslot[e]), n=int(n[e])) for e in big]
     res.append(r)
 print(json.dumps(res, indent=1))
