@@ -52,7 +52,12 @@ enum {
 };
 
 /* Shapes the narrowphase handles. */
-enum { B200MOBY_SHAPE_NONE = 0, B200MOBY_SHAPE_SPHERE = 1, B200MOBY_SHAPE_BOX = 2, B200MOBY_SHAPE_PLANE = 3 };
+enum { B200MOBY_SHAPE_NONE = 0, B200MOBY_SHAPE_SPHERE = 1, B200MOBY_SHAPE_BOX = 2, B200MOBY_SHAPE_PLANE = 3,
+       /* The rimless wheel of example/rimless-wheel: a body whose CollisionGeometry has no primitive and whose distance,
+        * contacts and conservative-advancement step come from the collision-detection plugin (coldet-plugin.cpp:86-137,
+        * 214-334; extern "C" factory() :340-346).  Built in as a shape: dims = (R, W, N_SPOKES) (params.h:4-6), spokes in the
+        * body's x-z plane, checked against planes only. */
+       B200MOBY_SHAPE_WHEEL = 4 };
 
 /* Impact models (ImpactConstraintHandler.cpp:122-146). */
 enum {
@@ -116,7 +121,7 @@ typedef struct {
   const int*    enabled;    /* RigidBody enabled= (0: static) */
   const double* mass;       /* kg; ignored for disabled bodies */
   /* [body][3][env] */
-  const double* dims;       /* box: xlen,ylen,zlen; sphere: radius,-,-; plane: -,-,- (plane is y=0 of the body frame, BoxPrimitive.cpp:358, PlanePrimitive.cpp:477) */
+  const double* dims;       /* box: xlen,ylen,zlen; sphere: radius,-,-; plane: -,-,- (plane is y=0 of the body frame, BoxPrimitive.cpp:358, PlanePrimitive.cpp:477); wheel: R,W,N_SPOKES (<= 16) */
   const double* inertia;    /* principal body-frame inertia (InertiaFromPrimitive) */
   /* contact parameters, [body_i*n_bodies + body_j][env] for i<j (ContactParameters.cpp:97-136) */
   const double* mu_coulomb;  /* an island whose contacts all have mu_coulomb >= 100 takes the no-slip model (ImpactConstraintHandler.cpp:122-135,1009-1417) */

@@ -1,6 +1,8 @@
 // Host-side table of the friction-cone direction cosines / sines, evaluated with the host libm exactly as the
 // reference evaluates them (ImpactConstraintHandlerQP.cpp:464-468; ImpactConstraintHandlerLCP.cpp:259-275), so the
-// device never calls its own cos/sin.  Layout: [4][NKMAX+1][NKMAX/2] = QP cos, QP sin, AP cos, AP sin.
+// device never calls its own cos/sin.  Layout: [4][NKMAX+1][NKMAX/2] = QP cos, QP sin, AP cos, AP sin, followed by the
+// spoke directions of the rimless wheel (example/rimless-wheel/coldet-plugin.cpp:107): [WHEEL_NS_MAX+1][WHEEL_NS_MAX][2] =
+// cos, sin of theta = M_PI * i * 2.0 / N for N spokes, spoke i.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -8,10 +10,20 @@
 #ifndef B2M_NKMAX
 #define B2M_NKMAX 64
 #endif
+#ifndef B2M_WHEEL_NS_MAX
+#define B2M_WHEEL_NS_MAX 16
+#endif
+#define B2M_WTAB_OFF ((size_t)4 * (B2M_NKMAX + 1) * (B2M_NKMAX / 2))
 
 inline std::vector<double> b2m_friction_table() {
   const int H = B2M_NKMAX / 2, S = (B2M_NKMAX + 1) * H;
-  std::vector<double> t((size_t)4 * S, 0.0);
+  std::vector<double> t((size_t)4 * S + (size_t)2 * (B2M_WHEEL_NS_MAX + 1) * B2M_WHEEL_NS_MAX, 0.0);
+  for (unsigned N = 1; N <= B2M_WHEEL_NS_MAX; N++)
+    for (unsigned i = 0; i < N; i++) {
+      const double theta = M_PI * i * 2.0 / N;
+      t[B2M_WTAB_OFF + 2 * ((size_t)N * B2M_WHEEL_NS_MAX + i)] = std::cos(theta);
+      t[B2M_WTAB_OFF + 2 * ((size_t)N * B2M_WHEEL_NS_MAX + i) + 1] = std::sin(theta);
+    }
   for (int NK = 4; NK <= B2M_NKMAX; NK++) {
     const int half = NK / 2;
     for (int j = 0; j < half && j < H; j++) {
@@ -43,6 +55,7 @@ inline void b2m_env_bounds(int nb, const int* shape, const int* enabled, const i
       if ((bi && pj) || (pi && bj)) cnt = 4;           // a non-degenerate box touches a plane with at most 4 vertices
       if (bi && bj) cnt = 8;
       if (pi && pj) cnt = 0;
+      if (shape[i] == 4 || shape[j] == 4) cnt = (pi || pj) ? 4 : 0;   // rimless wheel: spoke tips against a plane only (two tips, two sides when W > 0)
       cmax += cnt;
       nmax += cnt * (model == 1 ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2);
     }
@@ -70,7 +83,13 @@ inline const char* b2m_scene_bounds(const b200moby_scene_desc* d, int& cmax, int
   std::vector<int> sh(nb), en(nb), nk(nb * nb);
   int per_contact = 0;
   for (int e = 0; e < ne; e++) {
-    for (int b = 0; b < nb; b++) { sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e]; }
+    for (int b = 0; b < nb; b++) {
+      sh[b] = d->shape[(size_t)b * ne + e]; en[b] = d->enabled[(size_t)b * ne + e];
+      if (sh[b] == 4) {
+        const double ns = d->dims[((size_t)b * 3 + 2) * ne + e];
+        if (!(ns >= 1 && ns <= B2M_WHEEL_NS_MAX) || ns != (double)(int)ns) return "rimless wheel: dims = (R, W, N_SPOKES) with 1 <= N_SPOKES <= 16";
+      }
+    }
     for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) {
       const int k = d->NK[((size_t)i * nb + j) * ne + e];
       if (k != 0 && (k < 4 || k > B2M_NKMAX || (k & 1))) return "friction-cone-edges must be even and in [4,64] (ContactParameters.cpp:129-136)";

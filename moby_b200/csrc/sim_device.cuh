@@ -14,10 +14,13 @@
 
 namespace b2m {
 
-enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3 };
+enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3,
+       SH_WHEEL = 4 };   // rimless wheel of example/rimless-wheel/coldet-plugin.cpp: dims = (R, W, N_SPOKES) (params.h:4-6); collides with planes only
 enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LEMKE_CALLS, CNT_PIVOTS, CNT_LCP_FAIL,
        CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_CA_ITERS, CNT_STAB_ITERS, CNT_STAB_SOLVES, CNT_STAB_LSFAIL, CNT_COUNT };
 #define B2M_NKMAX 64
+#define B2M_WHEEL_NS_MAX 16
+#define B2M_WTAB_OFF ((size_t)4 * (B2M_NKMAX + 1) * (B2M_NKMAX / 2))   // spoke directions after the friction tables (friction_table.h)
 #define B2M_MAX_CLASSES 12
 // queue slots of one round: [0, n_classes) impact classes, then the envs that still have time left in their step, then stragglers
 #define B2M_SLOT_CONT B2M_MAX_CLASSES
@@ -59,7 +62,7 @@ struct SimParams {
   int n_envs, nb, cmax, nmax, npmax, model;
   const int* shape; const int* enabled; const double* mass; const double* dims; const double* inertia;
   const double* mu_c; const double* mu_v; const double* eps; const double* compliance; const int* NK;
-  const double* fr_tab;        // [4][B2M_NKMAX+1][B2M_NKMAX/2]: QP cos, QP sin, AP cos, AP sin (host libm values)
+  const double* fr_tab;        // [4][B2M_NKMAX+1][B2M_NKMAX/2]: QP cos, QP sin, AP cos, AP sin (host libm values), then the rimless wheel's spoke directions
   double gx, gy, gz, contact_dist_thresh, min_step_size;
   int stab_max_iterations; double stab_eps;   // ConstraintStabilization::max_iterations (0 off, < 0 unlimited) and eps (stab_device.cuh)
   const double* min_step_env;   // optional [env]
@@ -107,6 +110,8 @@ struct EnvMem {
   int *bshape, *ben, *pair_a, *pair_b, *cb1, *cb2, *cNK, *icon, *cisl, *corder, *isl_start, *gcoff, *bisl, *frow_c, *frow_j, *scal, *iwork;
   int *ranc, *gcb, *gcl;       // articulated body: ancestor-joint bitmask per link; island coordinate -> (super body, local index)
   long long* prof; long long prof_stride;   // debug: per-phase cycle accumulators of the env being processed (null: off)
+  const double* wtab;                       // SimParams::fr_tab + B2M_WTAB_OFF
+  double cdt;                               // SimParams::contact_dist_thresh (the rimless wheel's contact generator reads the simulator's, whatever TOL its caller passes)
 };
 
 // phase ids of the impact profile (rows 4.. of SimParams::tap_prof)
@@ -156,7 +161,7 @@ B2M_HD inline void env_carve_small(EnvMem& m, double* d, int* i, const EnvDims& 
   m.cb1 = i; i += cmax; m.cb2 = i; i += cmax; m.cNK = i; i += cmax;
   m.scal = i; i += 16;
   m.ranc = i; i += D.rcl;
-  m.Jr = nullptr; m.zl = nullptr; m.vl = nullptr; m.prof = nullptr; m.prof_stride = 0; m.gcb = m.gcl = nullptr;
+  m.Jr = nullptr; m.zl = nullptr; m.vl = nullptr; m.prof = nullptr; m.prof_stride = 0; m.gcb = m.gcl = nullptr; m.cdt = 0.0; m.wtab = nullptr;
 }
 B2M_HD inline void env_carve_impact(EnvMem& m, double* d, int* i, const EnvDims& D) {
   const int nb = D.nb, cmax = D.cmax, nmax = D.nmax;
@@ -216,10 +221,11 @@ B2M_HD B2M_INL V3 box_vertex(const double* dims, int i) {   // BoxPrimitive.cpp:
 }
 struct BodyRef {
   const double *x, *R, *vl, *va, *dims; int shape, enabled;
+  const double* wtab;   // spoke directions (EnvMem::wtab)
 };
 B2M_HD B2M_INL BodyRef body_ref(const EnvMem& m, int b) {
   BodyRef r; r.x = m.bx + 3 * b; r.R = m.bR + 9 * b; r.vl = m.bvl + 3 * b; r.va = m.bva + 3 * b; r.dims = m.bdims + 3 * b;
-  r.shape = m.bshape[b]; r.enabled = m.ben[b]; return r;
+  r.shape = m.bshape[b]; r.enabled = m.ben[b]; r.wtab = m.wtab; return r;
 }
 B2M_HD B2M_INL V3 to_global(const BodyRef& b, const V3& p) { return ld3(b.x) + rot(b.R, p); }
 B2M_HD B2M_INL V3 to_local(const BodyRef& b, const V3& p) { return rotT(b.R, p - ld3(b.x)); }
@@ -291,7 +297,28 @@ B2M_HD B2M_NOINL inline bool signed_dist_ordered(const BodyRef& A, const BodyRef
   if (B2M_BOXBOX && A.shape == SH_BOX && B.shape == SH_BOX) { boxbox_signed_dist(A, B, dist, pA, pB); return true; }   // rule H5 (boxbox_device.cuh)
   return false;
 }
+// Spoke tip i of the rimless wheel, side s (+1: y = +W/2, -1: y = -W/2), in the wheel frame (coldet-plugin.cpp:110-115)
+B2M_HD B2M_INL V3 wheel_tip(const BodyRef& Wh, int i, int s) {
+  const double* cs = Wh.wtab + 2 * ((size_t)(int)Wh.dims[2] * B2M_WHEEL_NS_MAX + i);   // host libm cos / sin of M_PI * i * 2.0 / N_SPOKES
+  return V3(cs[0] * Wh.dims[0], s * (Wh.dims[1] * .5), cs[1] * Wh.dims[0]);
+}
+// BladePlanePlugin::calc_signed_dist_wheel_plane (coldet-plugin.cpp:86-137): lowest spoke tip over the plane
+B2M_HD B2M_NOINL inline double wheel_plane_signed_dist(const BodyRef& Wh, const BodyRef& P, V3& pwheel, V3& pground) {
+  double min_dist = B2M_INF;
+  const int ns = (int)Wh.dims[2];
+  for (int i = 0; i < ns; i++)
+    for (int s = 1; s >= -1; s -= 2) {                         // p1 then p2; strict test, so p2 never wins when W = 0
+      const V3 pg = to_global(Wh, wheel_tip(Wh, i, s));
+      V3 pp = to_local(P, pg);
+      if (pp.y < min_dist) { min_dist = pp.y; pp.y = 0.0; pground = to_global(P, pp); pwheel = pg; }
+    }
+  return min_dist;
+}
 B2M_HD inline bool signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
+  // coldet-plugin.cpp:324-334: both argument orders hand (pA, pB) to (pwheel, pground); with the pair the plugin queues,
+  // (ground, wheel) (:70), the point reported for the ground is the wheel's and vice versa.  Literal.
+  if (A.shape == SH_WHEEL && B.shape == SH_PLANE) { dist = wheel_plane_signed_dist(A, B, pA, pB); return true; }
+  if (A.shape == SH_PLANE && B.shape == SH_WHEEL) { dist = wheel_plane_signed_dist(B, A, pA, pB); return true; }
   if (signed_dist_ordered(A, B, dist, pA, pB)) return true;
   if (signed_dist_ordered(B, A, dist, pB, pA)) return true;
   return false;
@@ -312,6 +339,24 @@ struct ContactOut { V3 p, n; int b1, b2; double dist; };
 B2M_HD B2M_NOINL inline int pair_contacts(const EnvMem& m, int ia, int ib, double TOL, ContactOut* out, int cap) {
   const BodyRef A = body_ref(m, ia), B = body_ref(m, ib);
   int cnt = 0;
+  if ((A.shape == SH_WHEEL && B.shape == SH_PLANE) || (A.shape == SH_PLANE && B.shape == SH_WHEEL)) {     // coldet-plugin.cpp:222-310
+    const int iw = (A.shape == SH_WHEEL) ? ia : ib, ip = (A.shape == SH_WHEEL) ? ib : ia;
+    const BodyRef Wh = body_ref(m, iw), P = body_ref(m, ip);
+    const V3 n = rot(P.R, V3(0, 1, 0));
+    const int ns = (int)Wh.dims[2];
+    for (int i = 0; i < ns; i++)
+      for (int s = 1; s >= -1; s -= 2) {
+        if (s < 0 && !(Wh.dims[1] > 0.0)) continue;            // :283
+        const V3 pg = to_global(Wh, wheel_tip(Wh, i, s));
+        V3 pp = to_local(P, pg);
+        const double h = pp.y;
+        if (!(h < m.cdt)) continue;                            // the plugin ignores the caller's TOL: `< sim->contact_dist_thresh` (:225,:270)
+        pp.y = 0.0;
+        if (cnt < cap) { out[cnt].p = (pg + to_global(P, pp)) * 0.5; out[cnt].n = n; out[cnt].b1 = iw; out[cnt].b2 = ip; out[cnt].dist = h; }
+        cnt++;
+      }
+    return cnt;
+  }
   if ((A.shape == SH_SPHERE && B.shape == SH_PLANE) || (A.shape == SH_PLANE && B.shape == SH_SPHERE)) {   // CCD.inl:805-846
     const int is = (A.shape == SH_SPHERE) ? ia : ib, ip = (A.shape == SH_SPHERE) ? ib : ia;
     const BodyRef S = body_ref(m, is), P = body_ref(m, ip);
@@ -403,7 +448,7 @@ B2M_HD B2M_INL double calc_max_dist(const BodyRef& rb, const V3& n, double rmax)
 B2M_HD B2M_INL double calc_rmax(const BodyRef& b) {                                  // CCD.cpp:1023-1101
   if (b.shape == SH_SPHERE) return b.dims[0];
   if (b.shape == SH_BOX) return sqrt((b.dims[0] / 2.0) * (b.dims[0] / 2.0) + (b.dims[1] / 2.0) * (b.dims[1] / 2.0) + (b.dims[2] / 2.0) * (b.dims[2] / 2.0));
-  return 0.0;
+  return 0.0;   // SH_WHEEL too: the plugin keeps the wheel out of CCD::broad_phase (coldet-plugin.cpp:53-67), so _rmax[wheel_cg] stays the map default
 }
 B2M_HD B2M_INL bool rel_equal(double x, double y) { return fabs(x - y) <= B2M_NEAR_ZERO * fmax(fabs(x), fmax(fabs(y), 1.0)); }
 B2M_HD B2M_INL bool collinear(const V3& a, const V3& b, const V3& c) {               // CompGeom.cpp:1923-1931
@@ -442,6 +487,7 @@ B2M_HD B2M_NOINL inline double pair_CA(const EnvMem& m, int p) {
       if (nc == 1 && fabs(contact_vel(m, con[0])) < B2M_NEAR_ZERO * 10) return B2M_INF;
     }
   }
+  if (pdist <= 0.0 && (A.shape == SH_WHEEL || B.shape == SH_WHEEL)) return B2M_INF;   // coldet-plugin.cpp:214-217 overrides calc_next_CA_Euler_step
   if (pdist <= 0.0) {                                                       // :189-190 -> :238-400
     const int nc = pair_contacts(m, ia, ib, B2M_NEAR_ZERO, con, 8);
     if (nc == 0) return B2M_INF;
@@ -501,6 +547,7 @@ B2M_DEV B2M_NOINL void rc_refresh(const G& g, const SimParams& P, EnvMem& m) {
 template <class G>
 B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
   const int nb = P.nb, ne = P.n_envs;
+  m.cdt = P.contact_dist_thresh; m.wtab = P.fr_tab + B2M_WTAB_OFF;
   for (int b = g.tid; b < nb; b += G::size) {
     m.bshape[b] = P.shape[(size_t)b * ne + e];
     m.ben[b] = P.enabled[(size_t)b * ne + e];

@@ -11,7 +11,7 @@ import numpy as np
 
 from .capi import RcDesc, SceneDesc
 
-SHAPE_NONE, SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE = 0, 1, 2, 3
+SHAPE_NONE, SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE, SHAPE_WHEEL = 0, 1, 2, 3, 4
 MODEL_QP, MODEL_AP = 0, 1
 JOINT_REVOLUTE, JOINT_PRISMATIC = 1, 2
 FDYN_FSAB, FDYN_CRB = 0, 1
@@ -77,6 +77,16 @@ class SceneBatch:
         self.mass[b, envs] = m
         for k in range(3):
             self.inertia[b, k, envs] = 0.4 * m * radius ** 2
+
+    def set_wheel(self, b, radius=1.0, width=0.0, n_spokes=6, mass=1.0, inertia=(2.0, 1.0, 2.0), envs=slice(None)):
+        """Rimless wheel of example/rimless-wheel (params.h:4-6, wheel.xml:42): spokes in the body's x-z plane, tips at
+        (cos(2 pi i / N) R, +-W/2, sin(2 pi i / N) R); it collides with planes only, through the spoke-tip generator of
+        coldet-plugin.cpp:86-137,222-310."""
+        self.shape[b, envs] = SHAPE_WHEEL
+        self.dims[b, 0, envs], self.dims[b, 1, envs], self.dims[b, 2, envs] = radius, width, n_spokes
+        self.mass[b, envs] = mass
+        for k in range(3):
+            self.inertia[b, k, envs] = inertia[k]
 
     def set_plane(self, b, quat=(0, 0, 0, 1), pos=(0, 0, 0)):
         """Static half-space y<=0 of the body frame (PlanePrimitive)."""
@@ -239,6 +249,28 @@ def sphere_stack(n_envs=1):
     s.set_contact(0, 2, NK=4)
     s.set_contact(1, 3, NK=4)
     s.set_contact(2, 3, NK=4)
+    return s
+
+
+def rimless_wheel(n_envs=1, theta_dot=0.3, seed=None, alpha_gravity=(0.099833, 0.0, -0.995), stabilization=-1, inertia=(2.0, 1.0, 2.0)):
+    """example/rimless-wheel/wheel.xml + init.cpp:150-175: bodies GROUND (plane z = 0), WHEEL (6 spokes, R = 1, W = 0, mass 1,
+    inertia diag(2,1,2)), gravity tilted by alpha = 0.1 (downhill along +x), mu = 100 (no-slip model), epsilon = 0, the
+    reference's default constraint stabilization.  The initializer puts the wheel on two spokes (z = sin 60 deg) rolling with
+    angular velocity theta_dot about y and linear velocity theta_dot * R along x (RIMLESS_WHEEL_THETAD).
+    seed != None: theta_dot is drawn per env from [0.5, 1.5] x theta_dot (randomised-initial-state batch)."""
+    s = SceneBatch(n_envs, 2)
+    s.name = "rimless-wheel"
+    s.set_plane(0, quat=tuple(quat_from_rpy(np.float64(1.570796326949), 0.0, 0.0)))   # wheel.xml:56
+    s.set_wheel(1, inertia=inertia)
+    s.gravity = tuple(alpha_gravity)
+    s.set_contact(0, 1, mu_coulomb=100.0, epsilon=0.0, NK=4)
+    s.stabilization_max_iterations = stabilization
+    td = np.full(n_envs, float(theta_dot))
+    if seed is not None:
+        td = td * np.random.default_rng(seed).uniform(0.5, 1.5, n_envs)
+    s.q[1, 2, :] = 0.866025403784439            # init.cpp:163
+    s.v[1, 0, :] = 2 * math.pi * 1.0 * (td / (math.pi * 2.0))   # DIST_PER_REV * REV_PER_SEC (init.cpp:154-156)
+    s.v[1, 4, :] = td
     return s
 
 

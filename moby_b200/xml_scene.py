@@ -1,5 +1,6 @@
 """Moby XML scene -> batch descriptor: the subset of the reference's scene format that the accelerated
-path covers -- free rigid bodies with Sphere / Box / Plane collision geometry, a GravityForce, and a
+path covers -- free rigid bodies with Sphere / Box / Plane collision geometry (or the rimless wheel's collision-detection
+plugin, mapped to the built-in spoke-tip shape), a GravityForce, and a
 TimeSteppingSimulator with ContactParameters / DisabledPair children -- so existing scenes such as
 example/simple-contact/simplest.xml, example/bouncing-ball/bouncing-ball.xml and example/stacks/*.xml load unmodified.
 
@@ -30,6 +31,10 @@ import numpy as np
 from . import scenes
 
 _PRIMS = ("Box", "Sphere", "Plane")
+# Collision-detection plugins (XMLReader.cpp:334-388, ConstraintSimulator.cpp:562-572) the accelerated path has a built-in
+# equivalent for: plugin file name -> {body id: (shape setter arguments)}.  The rimless wheel's plugin finds its bodies by
+# the ids "WHEEL" and "GROUND" (coldet-plugin.cpp:29-36) and takes R, W, N_SPOKES from params.h:4-6.
+_COLDET_PLUGINS = {"librimless-wheel-coldet-plugin.so": {"WHEEL": dict(radius=1.0, width=0.0, n_spokes=6), "GROUND": None}}
 _UNSUPPORTED_PRIMS = ("Cone", "Cylinder", "Torus", "Heightmap", "TriangleMesh", "Polyhedron", "CSG", "GaussianMixture")
 
 
@@ -85,6 +90,12 @@ def load_xml(source, n_envs=1):
     if len(sims) != 1:
         raise ValueError("exactly one <TimeSteppingSimulator> expected (EventDrivenSimulator and others are out of scope)")
     sim = sims[0]
+    plugin_bodies = {}
+    if sim.get("collision-detection-plugin") is not None:
+        pl = {n.get("id"): n.get("plugin") for n in moby.iter("CollisionDetectionPlugin")}.get(sim.get("collision-detection-plugin"))
+        if pl not in _COLDET_PLUGINS:
+            raise ValueError(f"collision-detection-plugin {pl!r}: no built-in equivalent on the accelerated path (known: {sorted(_COLDET_PLUGINS)})")
+        plugin_bodies = _COLDET_PLUGINS[pl]
     order = [n.get("dynamic-body-id") for n in sim.findall("DynamicBody")]
     for b in order:
         if b not in bodies:
@@ -125,8 +136,12 @@ def load_xml(source, n_envs=1):
             if any(cg.get(k) is not None for k in ("relative-origin", "relative-rpy", "relative-quat")):
                 raise ValueError(f"body {bid!r}: CollisionGeometry offsets are not supported")
             p = prims.get(cg.get("primitive-id"))
-            if p is None:
+            if p is None and cg.get("primitive-id") is None and plugin_bodies.get(bid) is not None:
+                s.set_wheel(i, **plugin_bodies[bid])                 # geometry without a primitive: the plugin's own shape
+                cgs = []
+            elif p is None:
                 raise ValueError(f"body {bid!r}: primitive {cg.get('primitive-id')!r} is not a Box / Sphere / Plane of this file")
+        if cgs:
             px, pq = _pose(p)
             if p.tag == "Plane":
                 if enabled:
@@ -163,12 +178,16 @@ def load_xml(source, n_envs=1):
             else:
                 s.set_sphere(i, float(p.get("radius")), **kw)
             s.shape[i], s.dims[i] = shape, dims                     # the collision shape stays what CollisionGeometry said
-        elif enabled:
-            raise ValueError(f"body {bid!r}: an enabled body needs InertiaFromPrimitive (explicit inertia matrices are not read yet)")
+        elif enabled and (node.get("inertia") is None or node.get("mass") is None):
+            raise ValueError(f"body {bid!r}: an enabled body needs InertiaFromPrimitive or both mass and inertia attributes")
         if node.get("mass") is not None:
             s.mass[i, :] = float(node.get("mass"))                   # RigidBody.cpp:182-188: J.m only
-        if node.get("inertia") is not None:
-            raise ValueError(f"body {bid!r}: explicit inertia matrices are not read yet")
+        if node.get("inertia") is not None:                          # RigidBody.cpp:191-197: J.J, rows separated by ';'
+            J = np.array([_vec(r, 3) for r in node.get("inertia").split(";") if r.strip()])
+            if J.shape != (3, 3) or np.abs(J - np.diag(np.diag(J))).max() != 0.0:
+                raise ValueError(f"body {bid!r}: the body frame must be the principal frame (diagonal inertia matrix)")
+            for k in range(3):
+                s.inertia[i, k, :] = J[k, k]
         s.enabled[i, :] = 1 if enabled else 0
         if node.get("linear-velocity") is not None:
             s.v[i, 0:3, :] = _vec(node.get("linear-velocity"), 3)[:, None]

@@ -167,7 +167,31 @@ static bool signed_dist_ordered(const Body& A, const Body& B, double& dist, V3& 
   return false;
 }
 
+// Spoke tip i of the rimless wheel, side s (+1: y = +W/2, -1: y = -W/2), in the wheel frame (coldet-plugin.cpp:110-115)
+static V3 wheel_tip(const Body& Wh, int i, int s) {
+  const double theta = M_PI * i * 2.0 / (unsigned)Wh.dims[2];
+  return V3(std::cos(theta) * Wh.dims[0], s * (Wh.dims[1] * .5), std::sin(theta) * Wh.dims[0]);
+}
+
+// BladePlanePlugin::calc_signed_dist_wheel_plane (coldet-plugin.cpp:86-137): lowest spoke tip over the plane; pwheel is
+// the tip, pground its projection (both returned in the global frame here).
+static double wheel_plane_signed_dist(const Body& Wh, const Body& P, V3& pwheel, V3& pground) {
+  double min_dist = INF;
+  const int ns = (int)Wh.dims[2];
+  for (int i = 0; i < ns; i++)
+    for (int s = 1; s >= -1; s -= 2) {                                // p1 then p2 (:121-134); the test is strict, so p2 never wins when W = 0
+      const V3 pg = to_global(Wh, wheel_tip(Wh, i, s));
+      V3 pp = to_local(P, pg);
+      if (pp.y < min_dist) { min_dist = pp.y; pp.y = 0.0; pground = to_global(P, pp); pwheel = pg; }
+    }
+  return min_dist;
+}
+
 static bool signed_dist(const Body& A, const Body& B, double& dist, V3& pA, V3& pB) {
+  // coldet-plugin.cpp:324-334: BOTH argument orders hand (pA, pB) to (pwheel, pground) -- with the pair the plugin
+  // queues, (ground, wheel) (:70), the point reported for the ground is the wheel's and vice versa.  Literal.
+  if (A.shape == SHAPE_WHEEL && B.shape == SHAPE_PLANE) { dist = wheel_plane_signed_dist(A, B, pA, pB); return true; }
+  if (A.shape == SHAPE_PLANE && B.shape == SHAPE_WHEEL) { dist = wheel_plane_signed_dist(B, A, pA, pB); return true; }
   if (signed_dist_ordered(A, B, dist, pA, pB)) return true;
   if (signed_dist_ordered(B, A, dist, pB, pA)) return true;        // BoxPrimitive.cpp:150-181, SpherePrimitive.cpp:282-303 swap the roles
   return false;
@@ -205,6 +229,25 @@ static Contact create_contact(int a, int b, const V3& point, const V3& normal, d
 // CCD.inl:3-82 dispatch and leaves
 void Sim::find_contacts(int ia, int ib, double TOL, std::vector<Contact>& out) const {
   const Body& A = bodies[ia]; const Body& B = bodies[ib];
+  // rimless wheel / plane (coldet-plugin.cpp:222-310): one candidate per spoke tip (two when W > 0); the plugin ignores
+  // the caller's TOL and tests `< sim->contact_dist_thresh` (:225,:270,:283)
+  if ((A.shape == SHAPE_WHEEL && B.shape == SHAPE_PLANE) || (A.shape == SHAPE_PLANE && B.shape == SHAPE_WHEEL)) {
+    const int iw = (A.shape == SHAPE_WHEEL) ? ia : ib, ip = (A.shape == SHAPE_WHEEL) ? ib : ia;
+    const Body& Wh = bodies[iw]; const Body& P = bodies[ip];
+    const V3 n = rot(P.R, V3(0, 1, 0));
+    const int ns = (int)Wh.dims[2];
+    for (int i = 0; i < ns; i++)
+      for (int s = 1; s >= -1; s -= 2) {
+        if (s < 0 && !(Wh.dims[1] > 0.0)) continue;                   // :283
+        const V3 pg = to_global(Wh, wheel_tip(Wh, i, s));
+        V3 pp = to_local(P, pg);
+        const double h = pp.y;
+        if (!(h < contact_dist_thresh)) continue;
+        pp.y = 0.0;
+        out.push_back(create_contact(iw, ip, (pg + to_global(P, pp)) * 0.5, n, h));
+      }
+    return;
+  }
   // sphere / plane (CCD.inl:805-846): cgA = sphere, cgB = plane
   if ((A.shape == SHAPE_SPHERE && B.shape == SHAPE_PLANE) || (A.shape == SHAPE_PLANE && B.shape == SHAPE_SPHERE)) {
     const int is = (A.shape == SHAPE_SPHERE) ? ia : ib, ip = (A.shape == SHAPE_SPHERE) ? ib : ia;
@@ -313,6 +356,8 @@ static double calc_max_dist(const Body& rb, const V3& n, double rmax) {
 static double calc_rmax(const Body& b) {
   if (b.shape == SHAPE_SPHERE) return b.dims[0];
   if (b.shape == SHAPE_BOX) return std::sqrt((b.dims[0] / 2.0) * (b.dims[0] / 2.0) + (b.dims[1] / 2.0) * (b.dims[1] / 2.0) + (b.dims[2] / 2.0) * (b.dims[2] / 2.0));
+  // SHAPE_WHEEL: 0.  The plugin takes the wheel out of the body list before CCD::broad_phase (coldet-plugin.cpp:53-67),
+  // the only place _rmax is filled (CCD.cpp:739), so _rmax[wheel_cg] is the map's default-constructed 0.0.
   return 0.0;
 }
 
@@ -382,6 +427,7 @@ double Sim::calc_CA_Euler_step(const PairDist& pdi) const {
     }
   }
   // :169-235 generic
+  if (pdi.dist <= 0.0 && (A.shape == SHAPE_WHEEL || B.shape == SHAPE_WHEEL)) return INF;   // coldet-plugin.cpp:214-217 overrides calc_next_CA_Euler_step
   if (pdi.dist <= 0.0) {
     // :238-400 bodies in contact
     std::vector<Contact> contacts;

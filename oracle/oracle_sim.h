@@ -38,7 +38,8 @@ struct V3 {
   double operator[](int i) const { return (&x)[i]; }
 };
 
-enum Shape { SHAPE_NONE = 0, SHAPE_SPHERE = 1, SHAPE_BOX = 2, SHAPE_PLANE = 3 };
+enum Shape { SHAPE_NONE = 0, SHAPE_SPHERE = 1, SHAPE_BOX = 2, SHAPE_PLANE = 3,
+             SHAPE_WHEEL = 4 };   // rimless wheel of example/rimless-wheel/coldet-plugin.cpp: dims = (R, W, N_SPOKES), params.h:4-6; collides with planes only
 enum Model { MODEL_QP = 0, MODEL_AP = 1 };
 
 struct Body {

@@ -189,7 +189,7 @@ int hostsim_lcp(int mode, int n, const double* M, const double* q, double* z, in
 void hostsim_boxbox_dist(const double* A, const double* B, double* out) {
   BodyRef X[2];
   const double* src[2] = {A, B};
-  for (int b = 0; b < 2; b++) { X[b].x = src[b]; X[b].R = src[b] + 3; X[b].dims = src[b] + 12; X[b].vl = X[b].va = src[b]; X[b].shape = SH_BOX; X[b].enabled = 1; }
+  for (int b = 0; b < 2; b++) { X[b].x = src[b]; X[b].R = src[b] + 3; X[b].dims = src[b] + 12; X[b].vl = X[b].va = src[b]; X[b].shape = SH_BOX; X[b].enabled = 1; X[b].wtab = nullptr; }
   double dist; V3 pA, pB;
   boxbox_signed_dist(X[0], X[1], dist, pA, pB);
   out[0] = dist; out[1] = pA.x; out[2] = pA.y; out[3] = pA.z; out[4] = pB.x; out[5] = pB.y; out[6] = pB.z;
