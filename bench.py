@@ -43,7 +43,60 @@ WORKLOADS = {
                         "16,384 envs per GPU (part of BASELINE configs[4])",
                    envs=16384, dt=1e-3, preroll=50, bytes=2.0 * 8.0 * (1 + 1) + 208.0, cpu_sample=(256, 40), ref_sample=2048,
                    make=lambda sc, ne, seed: sc.parts_feeder(ne, seed=seed)),
+    "wheel": dict(name="example/rimless-wheel (wheel.xml + init.cpp): 6-spoke wheel rolling downhill, spoke-tip contacts of coldet-plugin.cpp, mu = 100 "
+                       "(no-slip impact model), theta_dot in [0.5, 1.5] rad/s, 16,384 envs per GPU (part of BASELINE configs[4])",
+                  envs=16384, dt=1e-3, preroll=50, bytes=208.0, cpu_sample=(512, 40), ref_sample=4096,
+                  make=lambda sc, ne, seed: sc.rimless_wheel(ne, theta_dot=1.0, seed=seed)),
 }
+# BASELINE configs[4]: both scene types on EVERY GPU in equal shares (interleave scene types across GPUs rather
+# than giving each GPU one scene), two batches stepped concurrently on two streams of the rank's GPU.
+MIX = dict(name="parts-feeder / rimless-wheel mix (BASELINE configs[4]; SURVEY 8d case 5): per GPU 8,192 parts-feeder-like envs (prismatic shaker tray + "
+                "free box part, mu = 0.01) and 8,192 rimless wheels (mu = 100), two batches stepped concurrently",
+           envs=16384, dt=1e-3, preroll=50, parts=("feeder", "wheel"))
+
+
+class SimGroup:
+    """Several batches (one TimeSteppingSimulator handle each) of one GPU stepped together: each batch on its own stream,
+    forked from and joined to the caller's stream, so events on the caller's stream bracket all of them."""
+
+    def __init__(self, sims, names):
+        import torch
+        self.sims, self.names = sims, names
+        self.streams = [torch.cuda.Stream() for _ in sims]
+
+    def step(self, dt, n_steps=1):
+        import torch
+        cur = torch.cuda.current_stream()
+        for sim, st in zip(self.sims, self.streams):
+            st.wait_stream(cur)
+            sim.step(dt, n_steps, stream=st.cuda_stream)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return dt
+
+    def reset_counters(self):
+        for sim in self.sims:
+            sim.reset_counters()
+
+    def launch_count(self):
+        return sum(sim.launch_count() for sim in self.sims)
+
+    def counters(self):
+        out = {}
+        for sim in self.sims:
+            for k, v in sim.counters().items():
+                out[k] = max(out.get(k, 0), v) if k == "max_lcp_n" else out.get(k, 0) + v
+        return out
+
+    def kernel_profile(self, enable=True, reset=True):
+        out = []
+        for sim, name in zip(self.sims, self.names):
+            for k in sim.kernel_profile(enable=enable, reset=reset) or []:
+                k = dict(k)
+                k["name"] = name + ":" + k["name"]
+                out.append(k)
+        return out
+
 
 
 def _peaks():
@@ -209,29 +262,36 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from moby_b200 import scenes
-    W = WORKLOADS[args.workload]
+    W = MIX if args.workload == "mix" else WORKLOADS[args.workload]
     DT, WORKLOAD = W["dt"], W["name"]
-    sample = W["ref_sample"]
+    names = W.get("parts", (args.workload,))
     cores = os.cpu_count() or 1
-    scene = W["make"](scenes, sample, 0xB200)
-    if args.min_step == "default" and args.workload == "small":
-        scene.min_step_size_env = None
-    scene.stabilization_max_iterations = _stab_iters(args)
     if args.preroll < 0:
         args.preroll = W["preroll"]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_api as O
     O.build()
-    batch = O.OracleBatch(scene, 0, sample)
-    batch.run(DT, args.preroll, threads=cores)
-    for _ in range(args.warmup):
-        batch.run(DT, 1, threads=cores)
-    c0 = batch.run(DT, 0, threads=1)
+    batches, sample = [], 0
+    for nm in names:
+        n_i = WORKLOADS[nm]["ref_sample"] // len(names)
+        scene = WORKLOADS[nm]["make"](scenes, n_i, 0xB200)
+        if args.min_step == "default" and nm == "small":
+            scene.min_step_size_env = None
+        scene.stabilization_max_iterations = _stab_iters(args)
+        batch = O.OracleBatch(scene, 0, n_i)
+        batch.run(DT, args.preroll, threads=cores)
+        for _ in range(args.warmup):
+            batch.run(DT, 1, threads=cores)
+        batches.append(batch)
+        sample += n_i
+    c0 = [b.run(DT, 0, threads=1) for b in batches]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c1 = batch.run(DT, 1, threads=cores)
+        c1 = [b.run(DT, 1, threads=cores) for b in batches]
     el = time.perf_counter() - t0
     val = sample * args.steps / el
+    c0 = {"lcp_solves": sum(c["lcp_solves"] for c in c0)}
+    c1 = {"lcp_solves": sum(c["lcp_solves"] for c in c1)}
     out = {
         "impl": "reference", "metric": "env_steps_per_s", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
@@ -351,7 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lcp-n", type=int, default=32, help="--workload lcp: LCP dimension")
-    ap.add_argument("--workload", default="small", choices=sorted(WORKLOADS) + ["lcp"], help="BASELINE.json config (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--workload", default="small", choices=sorted(WORKLOADS) + ["lcp", "mix"], help="BASELINE.json config (default: configs[1], the one the metric is quoted on)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's own batch size")
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps before warm-up so contacts are active (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -386,17 +446,25 @@ def main():
     guard = StdoutGuard()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W = WORKLOADS[args.workload]
+    W = MIX if args.workload == "mix" else WORKLOADS[args.workload]
     DT, WORKLOAD = W["dt"], W["name"]
     ne = args.envs_per_gpu or W["envs"]
     if args.preroll < 0:
         args.preroll = W["preroll"]
-    scene = W["make"](scenes, ne, 0xB200 + rank)                # every rank owns its own envs (contiguous shard of the job)
-    if args.min_step == "default" and args.workload == "small":
-        scene.min_step_size_env = None
-    scene.stabilization_max_iterations = _stab_iters(args)
-    sim = TimeSteppingSimulator(scene, device=local_rank)
-    has_rc = scene.rc is not None
+    # parts: (name, workload entry, envs); one batch normally, one per scene type for the mix
+    names = W.get("parts", (args.workload,))
+    sizes = [ne // len(names) + (1 if i < ne % len(names) else 0) for i in range(len(names))]
+    part_scenes = []
+    for nm, n_i in zip(names, sizes):
+        sc = WORKLOADS[nm]["make"](scenes, n_i, 0xB200 + rank)  # every rank owns its own envs (contiguous shard of the job)
+        if args.min_step == "default" and nm == "small":
+            sc.min_step_size_env = None
+        sc.stabilization_max_iterations = _stab_iters(args)
+        part_scenes.append(sc)
+    part_sims = [TimeSteppingSimulator(sc, device=local_rank) for sc in part_scenes]
+    scene = part_scenes[0]
+    sim = part_sims[0] if len(part_sims) == 1 else SimGroup(part_sims, names)
+    bytes_env = sum(WORKLOADS[nm]["bytes"] * n_i for nm, n_i in zip(names, sizes)) / ne
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -412,8 +480,8 @@ def main():
     barrier()
     sim.reset_counters()
     launches0 = sim.launch_count()
-    q0, v0 = sim.get_state()            # the state the timed region starts from (also feeds the CPU baseline)
-    j0 = sim.get_joint_state() if has_rc else None
+    # the state the timed region starts from (also feeds the CPU baseline): per part q, v and the articulated body's joint state
+    state0 = [(ps.get_state(), ps.get_joint_state() if sc.rc is not None else None) for ps, sc in zip(part_sims, part_scenes)]
     sim.kernel_profile(enable=True, reset=True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
@@ -435,38 +503,43 @@ def main():
     r_cnt = dict(cnt)
     launches = sim.launch_count() - launches0
     # ---- end to end through the public API with HOST buffers: H2D state, step, D2H state, every step ----
-    qh = torch.from_numpy(q0).pin_memory()
-    vh = torch.from_numpy(v0).pin_memory()
-    qd, vd = torch.empty_like(qh, device=dev), torch.empty_like(vh, device=dev)
-    qo, vo = torch.empty_like(qh).pin_memory(), torch.empty_like(vh).pin_memory()
-    h2d = qh.numel() * 8 + vh.numel() * 8
-    if has_rc:                           # the articulated body's own state travels too
-        jh = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in j0]
-        jd = [torch.empty_like(a, device=dev) for a in jh]
-        jo = [torch.empty_like(a).pin_memory() for a in jh]
-        h2d += sum(a.numel() * 8 for a in jh)
+    class HostLoop:
+        """One batch's host-resident state: pinned q, v (and joint state) in, pinned out, swapped after every step."""
+
+        def __init__(self, ps, st0, st):
+            (q0, v0), j0 = st0
+            self.sim, self.stream = ps, st
+            self.inp = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (q0, v0) + (tuple(j0) if j0 is not None else ())]
+            self.dev = [torch.empty_like(a, device=dev) for a in self.inp]
+            self.out = [torch.empty_like(a).pin_memory() for a in self.inp]
+            self.bytes = sum(a.numel() * 8 for a in self.inp)
+
+        def issue(self):
+            with torch.cuda.stream(self.stream):
+                for d, h in zip(self.dev, self.inp):
+                    d.copy_(h, non_blocking=True)
+                self.sim.set_state_dev(self.dev[0], self.dev[1])
+                if len(self.dev) > 2:
+                    self.sim.set_joint_state_dev(self.dev[2], self.dev[3])
+                self.sim.step(DT, 1)
+                self.sim.get_state_dev(self.dev[0], self.dev[1])
+                if len(self.dev) > 2:
+                    self.sim.get_joint_state_dev(self.dev[2], self.dev[3])
+                for h, d in zip(self.out, self.dev):
+                    h.copy_(d, non_blocking=True)
+
+        def swap(self):
+            self.inp, self.out = self.out, self.inp          # next step starts from this step's result
+
+    loops = [HostLoop(ps, st0, stream if len(part_sims) == 1 else torch.cuda.Stream()) for ps, st0 in zip(part_sims, state0)]
+    h2d = sum(l.bytes for l in loops)
 
     def e2e_step():
-        nonlocal qh, qo, vh, vo
-        qd.copy_(qh, non_blocking=True); vd.copy_(vh, non_blocking=True)
-        sim.set_state_dev(qd, vd)
-        if has_rc:
-            for a, b in zip(jd, jh):
-                a.copy_(b, non_blocking=True)
-            sim.set_joint_state_dev(jd[0], jd[1])
-        sim.step(DT, 1)
-        sim.get_state_dev(qd, vd)
-        qo.copy_(qd, non_blocking=True); vo.copy_(vd, non_blocking=True)
-        if has_rc:
-            sim.get_joint_state_dev(jd[0], jd[1])
-            for a, b in zip(jo, jd):
-                a.copy_(b, non_blocking=True)
+        for l in loops:
+            l.issue()
         torch.cuda.synchronize()
-        qh, qo = qo, qh                  # next step starts from this step's result
-        vh, vo = vo, vh
-        if has_rc:
-            for k in range(2):
-                jh[k], jo[k] = jo[k], jh[k]
+        for l in loops:
+            l.swap()
 
     for _ in range(2):
         e2e_step()
@@ -494,7 +567,7 @@ def main():
         # kernel), algorithmic flops = the kernel's own recorded pivot and assembly flops (SURVEY.md 8d formulas)
         dom = max(kprof, key=lambda k: k["ms"])
         dom_launch_ms = dom["ms"] / max(dom["launches"], 1)
-        dom_bytes_env = W["bytes"] + (2.0 * 8.0 * dom["lcp_nmax"] if dom["lcp_nmax"] else 0.0)
+        dom_bytes_env = (WORKLOADS[dom["name"].split(":")[0]]["bytes"] if ":" in dom["name"] else bytes_env) + (2.0 * 8.0 * dom["lcp_nmax"] if dom["lcp_nmax"] else 0.0)
         alg_bytes = dom_bytes_env * dom["envs"] / max(dom["launches"], 1)
         alg_flops = dom["flops"] / max(dom["launches"], 1)
         achieved_gbs = alg_bytes / (dom_launch_ms * 1e-3) / 1e9
@@ -534,22 +607,28 @@ def main():
                                   "peak_source": fp64_src,
                                   "flops": "SURVEY 8(d): sum pivots*2n(n+1) + F_delassus + F_apply per solve + F_fd + F_narrow per mini-step, all from recorded counts"}},
         }
-        if not args.no_secondary:
+        if not args.no_secondary and len(names) == 1:
             out["secondary"] = _secondary(args, W, scenes, 0xB200 + rank, local_rank, flush, stream)
         out["stabilization"] = {"iterations_per_env_step": r_cnt["stab_iterations"] / max(r_cnt["env_steps"], 1),
                                 "lcp_solves_per_env_step": r_cnt["stab_lcp_solves"] / max(r_cnt["env_steps"], 1),
                                 "line_search_failures": r_cnt["stab_line_search_failures"]}
         if not args.no_cpu_baseline:
-            n_cpu, s_cpu = W["cpu_sample"]
-            n_cpu = min(n_cpu, ne)
-            v1, l1, el1, _ = _cpu_baseline(scene, q0, v0, j0, DT, n_cpu, s_cpu, 1)
             cores = os.cpu_count() or 1
-            vn, ln, eln, _ = _cpu_baseline(scene, q0, v0, j0, DT, min(n_cpu * 4, ne), s_cpu, cores)
-            out["cpu_baseline"] = {"value": v1, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                   "sample": f"first {n_cpu} envs of rank 0's batch from the same pre-rolled state, {s_cpu} steps, "
-                                             f"1 thread ({el1:.1f} s); oracle/ restatement (the reference cannot be built here)",
-                                   "lcp_solves_per_s": l1,
-                                   "all_cores": {"value": vn, "cores": cores, "sample": f"first {min(n_cpu * 4, ne)} envs, {s_cpu} steps ({eln:.1f} s)"}}
+            tot = {1: [0.0, 0.0, 0.0], cores: [0.0, 0.0, 0.0]}        # env-steps, LCP solves, seconds
+            desc = []
+            for nm, sc, n_i, ((q0, v0), j0) in zip(names, part_scenes, sizes, state0):
+                n_cpu, s_cpu = WORKLOADS[nm]["cpu_sample"]
+                n_cpu = min(n_cpu, n_i)
+                for thr, n_s in ((1, n_cpu), (cores, min(n_cpu * 4, n_i))):
+                    val, lps, el, _ = _cpu_baseline(sc, q0, v0, j0, DT, n_s, s_cpu, thr)
+                    tot[thr][0] += val * el; tot[thr][1] += lps * el; tot[thr][2] += el
+                desc.append(f"first {n_cpu} {nm} envs" if len(names) > 1 else f"first {n_cpu} envs")
+            out["cpu_baseline"] = {"value": tot[1][0] / tot[1][2], "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                   "sample": f"{' + '.join(desc)} of rank 0's batch from the same pre-rolled state, {s_cpu} steps, "
+                                             f"1 thread ({tot[1][2]:.1f} s); oracle/ restatement (the reference cannot be built here)",
+                                   "lcp_solves_per_s": tot[1][1] / tot[1][2],
+                                   "all_cores": {"value": tot[cores][0] / tot[cores][2], "cores": cores,
+                                                 "sample": f"4x the envs, {s_cpu} steps ({tot[cores][2]:.1f} s)"}}
         guard.emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -26,7 +26,12 @@ __global__ void __launch_bounds__(128) impact_thread_kernel(SimParams P, double 
   for (int k = 0; k < CNT_COUNT; k++) { lc[k] = 0; tot[k] = 0; }
   const int count = q_size(P, round, slot);
   unsigned long long envs = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+  // P.thread_lanes (<= 32) envs per warp: fewer lanes in lock step trade lane utilisation for more warps in flight (this
+  // kernel is bound by the latency of its dependent chains through local memory, not by issue slots) and for less
+  // divergence (a warp lasts as long as its slowest env)
+  const int lanes = P.thread_lanes > 0 && P.thread_lanes < 32 ? P.thread_lanes : 32;
+  const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp * lanes + lane; lane < lanes && i < count; i += nwarps * lanes) {
     for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
     EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
     if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) add_counters(tot, lc);

@@ -5,7 +5,15 @@ using namespace b2m;
 // ---- impact: islands, Delassus / LCP assembly, solve, impulses for the parked envs of one LCP class ----
 // L.ctl != nullptr: the launch runs the Lemke ladder's rungs as tasks (lcp_device.cuh): a warp that has run out of envs
 // keeps taking tasks until every warp of the launch has run out of envs and the task list is empty.
-__global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt, int round, int slot, int wpb, LadderPool L) {
+// feed_slot >= 0 (the hard-queue launch): once its own queue is empty the launch also takes the envs that the class launches
+// running next to it hand on (the straggler queue of the round) -- as they arrive, instead of in a launch of their own after
+// every class has finished.  feed_done counts the class launches that have completed (one signal_kernel per class, queued
+// behind it on its stream); an entry of the fed queue is valid once it is no longer -1 (the producer bumps the count
+// first).  A timeout ends the wait whatever happens; what is left over is run by the straggler launch that follows.
+__global__ void signal_kernel(int* ctr) { __threadfence(); atomicAdd(ctr, 1); }
+const void* b2m_k_signal() { return (const void*)signal_kernel; }
+
+__global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt, int round, int slot, int wpb, LadderPool L, int feed_slot, int* feed_done, int feed_expect) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int w = threadIdx.x >> 5;
   EnvMem m;
@@ -24,6 +32,37 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
     if (L.ctl && !cx.limit) cx.ladder = &C;
     if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) add_counters(tot, lc);
     envs++;
+  }
+  if (feed_slot >= 0) {
+    int* fhead = q_head(P, round, feed_slot);
+    volatile int* fcount = q_count(P, round, feed_slot);
+    volatile int* flist = q_list(P, round, feed_slot);
+    volatile int* fdone = feed_done;
+    long long t_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    for (;;) {
+      if (L.ctl && ladder_help_one(L, m.work, m.iwork)) continue;
+      int e = -2;                                        // -2: nothing to take now, -3: the producers are done and the queue is empty
+      if (g.tid == 0) {
+        const int finished = *fdone >= feed_expect;      // read BEFORE the count: a count read after it is final
+        __threadfence();
+        const int hd = *(volatile int*)fhead, cn = *fcount;
+        if (hd < cn) {
+          if (atomicCAS(fhead, hd, hd + 1) == hd) { while ((e = flist[hd]) < 0) __nanosleep(100); }
+        } else if (finished) e = -3;
+        else {
+          long long t_now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+          if (t_now - t_begin > 30000000ll) e = -3;        // 30 ms: never spin on a producer that cannot run
+        }
+      }
+      e = __shfl_sync(0xffffffffu, e, 0);
+      if (e == -3) break;
+      if (e < 0) { __nanosleep(1000); continue; }
+      for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
+      EnvCtx cx; cx.limit = false; cx.budget = 0;
+      if (L.ctl) cx.ladder = &C;
+      if (env_impact(g, P, e, m, dt, round, lc, cx)) add_counters(tot, lc);
+      envs++;
+    }
   }
   if (g.tid == 0) commit_counters(P, tot, envs);
   if (L.ctl) {                                     // no env left for this warp: serve ladder tasks until the launch has none left

@@ -27,6 +27,20 @@ B2M_DEV B2M_INL double m_at(const double* M, int ldm, int r, int c, double lambd
 template <class G>
 B2M_DEV B2M_NOINL double norm_inf(const G& g, int n, const double* M, int ldm, double lambda) {
   double m = 0.0;
+  if constexpr (G::size == 1) {                                  // one thread: eight loads in flight (max is exact: any order gives the same value)
+    double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    for (int c = 0; c < n; c++) {
+      const double* Mc = M + (size_t)c * ldm;
+      int r = 0;
+      for (; r + 8 <= n; r += 8) {
+        double v0 = Mc[r], v1 = Mc[r + 1], v2 = Mc[r + 2], v3 = Mc[r + 3], v4 = Mc[r + 4], v5 = Mc[r + 5], v6 = Mc[r + 6], v7 = Mc[r + 7];
+        if ((unsigned)(c - r) < 8u) { const int d = c - r; if (d == 0) v0 += lambda; else if (d == 1) v1 += lambda; else if (d == 2) v2 += lambda; else if (d == 3) v3 += lambda; else if (d == 4) v4 += lambda; else if (d == 5) v5 += lambda; else if (d == 6) v6 += lambda; else v7 += lambda; }
+        m = fmax(m, fmax(fabs(v0), fabs(v4))); m1 = fmax(m1, fmax(fabs(v1), fabs(v5))); m2 = fmax(m2, fmax(fabs(v2), fabs(v6))); m3 = fmax(m3, fmax(fabs(v3), fabs(v7)));
+      }
+      for (; r < n; r++) m = fmax(m, fabs(m_at(M, ldm, r, c, lambda)));
+    }
+    return fmax(fmax(m, m1), fmax(m2, m3));
+  }
   for (int e = g.tid; e < n * n; e += G::size) {
     const int c = e / n, r = e - c * n;
     m = fmax(m, fabs(m_at(M, ldm, r, c, lambda)));
@@ -39,6 +53,20 @@ B2M_DEV B2M_NOINL double norm_inf(const G& g, int n, const double* M, int ldm, d
 template <class G>
 B2M_DEV B2M_NOINL double norm_inf_offdiag(const G& g, int n, const double* M, int ldm) {
   double m = 0.0;
+  if constexpr (G::size == 1) {                                  // one thread: eight loads in flight (ncu: this scan, one dependent L2-latency load per entry, was 31 % of the thread-per-env impact kernel)
+    double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    for (int c = 0; c < n; c++) {
+      const double* Mc = M + (size_t)c * ldm;
+      int r = 0;
+      for (; r + 8 <= n; r += 8) {
+        double v0 = Mc[r], v1 = Mc[r + 1], v2 = Mc[r + 2], v3 = Mc[r + 3], v4 = Mc[r + 4], v5 = Mc[r + 5], v6 = Mc[r + 6], v7 = Mc[r + 7];
+        if ((unsigned)(c - r) < 8u) { const int d = c - r; if (d == 0) v0 = 0.0; else if (d == 1) v1 = 0.0; else if (d == 2) v2 = 0.0; else if (d == 3) v3 = 0.0; else if (d == 4) v4 = 0.0; else if (d == 5) v5 = 0.0; else if (d == 6) v6 = 0.0; else v7 = 0.0; }
+        m = fmax(m, fmax(fabs(v0), fabs(v4))); m1 = fmax(m1, fmax(fabs(v1), fabs(v5))); m2 = fmax(m2, fmax(fabs(v2), fabs(v6))); m3 = fmax(m3, fmax(fabs(v3), fabs(v7)));
+      }
+      for (; r < n; r++) if (r != c) m = fmax(m, fabs(Mc[r]));
+    }
+    return fmax(fmax(m, m1), fmax(m2, m3));
+  }
   for (int c = 0; c < n; c++)
     for (int r = g.tid; r < n; r += G::size) if (r != c) m = fmax(m, fabs(M[(size_t)c * ldm + r]));
   return g.max(m);
@@ -417,8 +445,86 @@ static __device__ __noinline__ bool lu_solve_warp(int k, double* A, double* b) {
 #endif
 
 // solves A x = b (A k x k column-major ld k, destroyed; b <- x).  Returns false on an exactly zero pivot.
+// One thread per system (the thread-per-env kernels: A and b in the thread's local memory).  Same pivot rule and the
+// same fma per element as the generic loop below, but organised for instruction-level parallelism: a lone thread is bound
+// by the latency of its dependent load -> fma -> store chains, so every pass reads a batch of operands before it writes
+// any (the compiler cannot reorder the generic loop's loads across its stores: it cannot prove that A[c*k+j] and
+// A[c*k+i] differ), and the elimination walks columns in the outer loop so the inner one is unit-stride.
+// lda is the column stride: the thread-per-env kernels pass the LCP dimension n, the same for every env of a warp, so
+// that equal (row, column) of the 32 systems a warp factors in lock step sit at equal local-memory offsets and the
+// hardware coalesces them; with lda = k (each env's own count of nonbasic variables) every access of the warp touched up
+// to 32 different lines, and the L1's line-per-cycle pipeline -- not latency -- set the kernel's speed.
+B2M_DEV B2M_NOINL inline bool lu_solve_serial(int k, double* A, int lda, double* b) {
+  for (int j = 0; j < k; j++) {
+    double* Aj = A + (size_t)j * lda;
+    double key = 1.0; int p = 0x7fffffff;                       // first maximum of |A(i,j)|, i >= j
+    for (int i = j; i < k; i++) { const double v = -fabs(Aj[i]); if (v < key) { key = v; p = i; } }
+    if (key == 0.0 || p == 0x7fffffff) return false;
+    if (p != j) {
+      int c = 0;
+      for (; c + 4 <= k; c += 4) {
+        double* r0 = A + (size_t)c * lda; double* r1 = r0 + lda; double* r2 = r1 + lda; double* r3 = r2 + lda;
+        const double a0 = r0[j], a1 = r1[j], a2 = r2[j], a3 = r3[j], b0 = r0[p], b1 = r1[p], b2 = r2[p], b3 = r3[p];
+        r0[j] = b0; r1[j] = b1; r2[j] = b2; r3[j] = b3; r0[p] = a0; r1[p] = a1; r2[p] = a2; r3[p] = a3;
+      }
+      for (; c < k; c++) { double* r0 = A + (size_t)c * lda; const double a0 = r0[j]; r0[j] = r0[p]; r0[p] = a0; }
+      const double tmp = b[j]; b[j] = b[p]; b[p] = tmp;
+    }
+    const double rinv = 1.0 / Aj[j];
+    const double bj = b[j];
+    {   // multipliers l_i = A(i,j) / A(j,j) and the right-hand side
+      int i = j + 1;
+      for (; i + 4 <= k; i += 4) {
+        const double l0 = Aj[i] * rinv, l1 = Aj[i + 1] * rinv, l2 = Aj[i + 2] * rinv, l3 = Aj[i + 3] * rinv;
+        const double c0 = b[i], c1 = b[i + 1], c2 = b[i + 2], c3 = b[i + 3];
+        Aj[i] = l0; Aj[i + 1] = l1; Aj[i + 2] = l2; Aj[i + 3] = l3;
+        b[i] = fma(-l0, bj, c0); b[i + 1] = fma(-l1, bj, c1); b[i + 2] = fma(-l2, bj, c2); b[i + 3] = fma(-l3, bj, c3);
+      }
+      for (; i < k; i++) { const double l0 = Aj[i] * rinv; Aj[i] = l0; b[i] = fma(-l0, bj, b[i]); }
+    }
+    int c = j + 1;
+    for (; c + 2 <= k; c += 2) {                                // two columns at a time, four rows per batch
+      double* A0 = A + (size_t)c * lda; double* A1 = A0 + lda;
+      const double u0 = A0[j], u1 = A1[j];
+      int i = j + 1;
+      for (; i + 4 <= k; i += 4) {
+        const double l0 = Aj[i], l1 = Aj[i + 1], l2 = Aj[i + 2], l3 = Aj[i + 3];
+        const double x0 = A0[i], x1 = A0[i + 1], x2 = A0[i + 2], x3 = A0[i + 3];
+        const double y0 = A1[i], y1 = A1[i + 1], y2 = A1[i + 2], y3 = A1[i + 3];
+        A0[i] = fma(-l0, u0, x0); A0[i + 1] = fma(-l1, u0, x1); A0[i + 2] = fma(-l2, u0, x2); A0[i + 3] = fma(-l3, u0, x3);
+        A1[i] = fma(-l0, u1, y0); A1[i + 1] = fma(-l1, u1, y1); A1[i + 2] = fma(-l2, u1, y2); A1[i + 3] = fma(-l3, u1, y3);
+      }
+      for (; i < k; i++) { const double l0 = Aj[i], x0 = A0[i], y0 = A1[i]; A0[i] = fma(-l0, u0, x0); A1[i] = fma(-l0, u1, y0); }
+    }
+    for (; c < k; c++) {
+      double* A0 = A + (size_t)c * lda;
+      const double u0 = A0[j];
+      int i = j + 1;
+      for (; i + 4 <= k; i += 4) {
+        const double l0 = Aj[i], l1 = Aj[i + 1], l2 = Aj[i + 2], l3 = Aj[i + 3];
+        const double x0 = A0[i], x1 = A0[i + 1], x2 = A0[i + 2], x3 = A0[i + 3];
+        A0[i] = fma(-l0, u0, x0); A0[i + 1] = fma(-l1, u0, x1); A0[i + 2] = fma(-l2, u0, x2); A0[i + 3] = fma(-l3, u0, x3);
+      }
+      for (; i < k; i++) { const double l0 = Aj[i], x0 = A0[i]; A0[i] = fma(-l0, u0, x0); }
+    }
+  }
+  for (int c = k - 1; c >= 0; c--) {
+    const double* Ac = A + (size_t)c * lda;
+    const double xc = b[c] / Ac[c];
+    b[c] = xc;
+    int i = 0;
+    for (; i + 4 <= c; i += 4) {
+      const double a0 = Ac[i], a1 = Ac[i + 1], a2 = Ac[i + 2], a3 = Ac[i + 3], c0 = b[i], c1 = b[i + 1], c2 = b[i + 2], c3 = b[i + 3];
+      b[i] = fma(-a0, xc, c0); b[i + 1] = fma(-a1, xc, c1); b[i + 2] = fma(-a2, xc, c2); b[i + 3] = fma(-a3, xc, c3);
+    }
+    for (; i < c; i++) b[i] = fma(-Ac[i], xc, b[i]);
+  }
+  return true;
+}
+
 template <class G>
 B2M_DEV B2M_NOINL bool lu_solve(const G& g, int k, double* A, double* b) {
+  if constexpr (G::size == 1) return lu_solve_serial(k, A, k, b);
 #ifdef __CUDACC__
   if constexpr (G::size == 32) { if (k <= 64) return __isShared(A) ? lu_solve_warp<true>(k, A, b) : lu_solve_warp<false>(k, A, b); }
 #endif
@@ -526,11 +632,48 @@ B2M_DEV B2M_NOINL int lcp_fast_solve(const G& g, int n, const double* M, int ldm
 #pragma unroll 4
         for (int c = 0; c < k; c++) Ar[c * k + r] = m_at(Mr, ldm, nr, nbp[c], lambda);
       }
+    } else if (G::size == 1) {                                                         // one thread: column by column, four loads in flight, no integer division
+      for (int c = 0; c < k; c++) {
+        const int nc = nonbas[c];
+        const double* Mc = M + (size_t)nc * ldm;
+        double* Ac = A + (size_t)c * n;                                                 // column stride n, not k: see lu_solve_serial
+        int r = 0;
+        for (; r + 4 <= k; r += 4) {
+          const int r0 = nonbas[r], r1 = nonbas[r + 1], r2 = nonbas[r + 2], r3 = nonbas[r + 3];
+          const double v0 = Mc[r0], v1 = Mc[r1], v2 = Mc[r2], v3 = Mc[r3];
+          Ac[r] = (r0 == nc) ? v0 + lambda : v0; Ac[r + 1] = (r1 == nc) ? v1 + lambda : v1;
+          Ac[r + 2] = (r2 == nc) ? v2 + lambda : v2; Ac[r + 3] = (r3 == nc) ? v3 + lambda : v3;
+        }
+        for (; r < k; r++) { const int r0 = nonbas[r]; const double v0 = Mc[r0]; Ac[r] = (r0 == nc) ? v0 + lambda : v0; }
+      }
     } else
     for (int e = g.tid; e < k * k; e += G::size) { const int c = e / k, r = e - c * k; A[e] = m_at(M, ldm, nonbas[r], nonbas[c], lambda); }   // :111
     for (int i = g.tid; i < k; i += G::size) zz[i] = -q[nonbas[i]];                  // :113-115
     g.sync();
-    if (!lu_solve(g, k, A, zz)) { status = LCP_SINGULAR; break; }                    // :118-126
+    bool lu_ok;
+    if constexpr (G::size == 1) lu_ok = lu_solve_serial(k, A, n, zz); else lu_ok = lu_solve(g, k, A, zz);
+    if (!lu_ok) { status = LCP_SINGULAR; break; }                                    // :118-126
+    if (G::size == 1) {                                                              // :129, four rows of w per pass: four independent fma chains
+      int i = 0;
+      for (; i + 4 <= nb; i += 4) {
+        const int b0 = bas[i], b1 = bas[i + 1], b2 = bas[i + 2], b3 = bas[i + 3];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int c = 0; c < k; c++) {
+          const double* Mc = M + (size_t)nonbas[c] * ldm;
+          const double zc = zz[c];
+          const double m0 = Mc[b0], m1 = Mc[b1], m2 = Mc[b2], m3 = Mc[b3];
+          s0 = fma(m0, zc, s0); s1 = fma(m1, zc, s1); s2 = fma(m2, zc, s2); s3 = fma(m3, zc, s3);
+        }
+        const double q0 = q[b0], q1 = q[b1], q2 = q[b2], q3 = q[b3];
+        w[i] = s0 + q0; w[i + 1] = s1 + q1; w[i + 2] = s2 + q2; w[i + 3] = s3 + q3;
+      }
+      for (; i < nb; i++) {
+        const int b0 = bas[i];
+        double s0 = 0.0;
+        for (int c = 0; c < k; c++) s0 = fma(M[(size_t)nonbas[c] * ldm + b0], zz[c], s0);
+        w[i] = s0 + q[b0];
+      }
+    } else
     for (int i = g.tid; i < nb; i += G::size) {                                      // :129
       const int bi = bas[i];
       const double* __restrict__ Mr = M; const int* __restrict__ nbp = nonbas; const double* __restrict__ zr = zz;
@@ -594,6 +737,27 @@ template <class G>
 B2M_DEV B2M_NOINL bool lcp_verify(const G& g, int n, const double* M, int ldm, const double* q, double lambda, const double* z,
                            double ZERO_TOL, bool strict, double* w) {
   double mz = B2M_INF, mw = B2M_INF, mn = B2M_INF, mx = -B2M_INF;
+  if constexpr (G::size == 1) {                                  // one thread: four rows of w = (M + lambda I) z + q per pass (four independent fma chains, each in column order)
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int c = 0; c < n; c++) {
+        const double* Mc = M + (size_t)c * ldm + i;
+        const double zc = z[c];
+        double a0 = Mc[0], a1 = Mc[1], a2 = Mc[2], a3 = Mc[3];
+        if ((unsigned)(c - i) < 4u) { const int d = c - i; if (d == 0) a0 += lambda; else if (d == 1) a1 += lambda; else if (d == 2) a2 += lambda; else a3 += lambda; }
+        s0 = fma(a0, zc, s0); s1 = fma(a1, zc, s1); s2 = fma(a2, zc, s2); s3 = fma(a3, zc, s3);
+      }
+      const double w4[4] = {s0 + q[i], s1 + q[i + 1], s2 + q[i + 2], s3 + q[i + 3]};
+      for (int u = 0; u < 4; u++) { const double zi = z[i + u], pr = zi * w4[u]; mz = fmin(mz, zi); mw = fmin(mw, w4[u]); mn = fmin(mn, pr); mx = fmax(mx, pr); }
+    }
+    for (; i < n; i++) {
+      double sacc = 0.0;
+      for (int c = 0; c < n; c++) sacc = fma(m_at(M, ldm, i, c, lambda), z[c], sacc);
+      const double wi = sacc + q[i], pr = z[i] * wi;
+      mz = fmin(mz, z[i]); mw = fmin(mw, wi); mn = fmin(mn, pr); mx = fmax(mx, pr);
+    }
+  } else
   for (int i = g.tid; i < n; i += G::size) {
     double sacc = 0.0;
     for (int c = 0; c < n; c++) sacc = fma(m_at(M, ldm, i, c, lambda), z[c], sacc);

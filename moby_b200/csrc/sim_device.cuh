@@ -74,6 +74,7 @@ struct SimParams {
   // envs that set the step time (degenerate contact sets: four failed lcp_fast runs, then the Lemke ladder) run
   // alongside the bulk instead of after it.  The same envs are hard step after step (resting contact persists).
   int* cost; int hard_cost; int cost_shift;   // decay per impact: cost -= cost >> cost_shift
+  int thread_lanes;            // envs per warp of the thread-per-env impact kernels (0 / 32: all lanes)
   int pivot_budget;            // > 0: per-env pivot budget of the warp-per-env impact kernels; over-budget envs are re-run by the straggler kernel
   // phased step (advance -> impact per LCP class -> advance ...): per-env progress and work queues
   double* hacc;                // [env] seconds of the current step already simulated
@@ -81,6 +82,7 @@ struct SimParams {
   int* queue;                  // queue[(round * B2M_SLOTS + slot) * n_envs + i]
   int* qctl;                   // [2][B2M_ROUNDS_MAX][B2M_SLOTS + 1] counts, then heads (slot B2M_SLOTS: the advance launch's own head)
   int n_classes; int class_nmax[B2M_MAX_CLASSES]; int class_cmax[B2M_MAX_CLASSES];
+  int class_budget[B2M_MAX_CLASSES];   // solver-iteration budget of the class's thread-per-env launch (0: none); an env whose cost history reaches it goes to the hard queue instead
   // debug taps (may be null)
   double* tap_MM; double* tap_qq; double* tap_z; int* tap_n;
   // reduced-coordinate articulated body (null / 0 when the scene has none)
@@ -93,6 +95,7 @@ struct SimParams {
   // per-kernel accounting: kstat[3 * kslot + {0,1,2}] += envs processed, algorithmic flops (pivot + assembly), LCP solves
   unsigned long long* kstat; int kslot;
   int* env_stat;               // optional [5][env]: LCP failures, lcp_lemke calls, lcp_fast calls, LCP solves, pivots of each env since the tap was armed (parity tests)
+  int tap_times;               // debug: tap_prof rows PH_ISLANDS / PH_STORE hold global-timer start / end of the env's impact (B200MOBY_TAP_TIMES=1)
   long long* tap_prof;         // [4 + PH_COUNT][env]: SM cycles, pivots, executed iterations, LCP n of the env's last impact phase, then cycles per phase
 };
 
@@ -1075,6 +1078,77 @@ B2M_DEV B2M_NOINL int build_qp_lcp(const G& g, const SimParams& P, EnvMem& m) {
   const int n = m.scal[S_N];
   if (n > P.nmax) return n;
   const double* qcos = P.fr_tab; const double* qsin = P.fr_tab + (size_t)(B2M_NKMAX + 1) * (B2M_NKMAX / 2);
+  if constexpr (G::size == 1) {
+    // One thread per env: the same entries as the flat loop below, written block by block -- no integer division or
+    // per-entry branching, unit-stride stores, several loads in flight (a lone thread is latency-bound; see lu_solve_serial).
+    const int nfr = n - NV - nc;
+    for (int c = 0; c < n; c++) {
+      double* col = m.MM + (size_t)c * n;
+      if (c < NV) {
+        const int bc = c / nc, j = c - bc * nc;
+        const int dc = bc == 0 ? 0 : (bc == 1 || bc == 3 ? 1 : 2);
+        const bool cneg = bc >= 3;
+        for (int br = 0; br < 5; br++) {                                  // upper-left: +-D(dr,dc)(i,j)
+          const int dr = br == 0 ? 0 : (br == 1 || br == 3 ? 1 : 2);
+          const bool neg = (br >= 3) != cneg;
+          const double* src; int stride;
+          if (dr <= dc) { src = m.D + (size_t)dblk(dr, dc) * nc * nc + j; stride = nc; }
+          else { src = m.D + (size_t)dblk(dc, dr) * nc * nc + (size_t)j * nc; stride = 1; }
+          double* dst = col + br * nc;
+          int i = 0;
+          for (; i + 4 <= nc; i += 4) {
+            const double v0 = src[(size_t)i * stride], v1 = src[(size_t)(i + 1) * stride], v2 = src[(size_t)(i + 2) * stride], v3 = src[(size_t)(i + 3) * stride];
+            dst[i] = neg ? -v0 : v0; dst[i + 1] = neg ? -v1 : v1; dst[i + 2] = neg ? -v2 : v2; dst[i + 3] = neg ? -v3 : v3;
+          }
+          for (; i < nc; i++) { const double v0 = src[(size_t)i * stride]; dst[i] = neg ? -v0 : v0; }
+        }
+        if (c < nc) col[c] += m.ccomp[m.icon[c]];
+        {                                                                  // lower-left, normal rows: A(a, c) = +-D(0,dc)(a,j) [+ compliance]
+          const double* src = m.D + (size_t)dblk(0, dc) * nc * nc + j;
+          double* dst = col + NV;
+          for (int a = 0; a < nc; a++) {
+            const double v = src[(size_t)a * nc];
+            double av = cneg ? -v : v;
+            if (c == a) av += m.ccomp[m.icon[a]];
+            dst[a] = av;
+          }
+        }
+        double* dst = col + NV + nc;                                       // lower-left, friction rows
+        for (int fr = 0; fr < nfr; fr++) {
+          const int i = m.frow_c[fr], jj = m.frow_j[fr];
+          const size_t ti = (size_t)m.cNK[m.icon[i]] * (B2M_NKMAX / 2) + jj;
+          double av;
+          if (c == i) av = m.cmu[m.icon[i]];
+          else if (c == nc + i || c == 3 * nc + i) av = -qcos[ti];
+          else if (c == 2 * nc + i || c == 4 * nc + i) av = -qsin[ti];
+          else av = 0.0;
+          dst[fr] = av;
+        }
+      } else {
+        const int a = c - NV;                                              // upper-right = -A^T, lower-right = 0
+        if (a < nc) {
+          for (int bc = 0; bc < 5; bc++) {
+            const int dc = bc == 0 ? 0 : (bc == 1 || bc == 3 ? 1 : 2);
+            const double* src = m.D + (size_t)dblk(0, dc) * nc * nc + (size_t)a * nc;
+            double* dst = col + bc * nc;
+            for (int j = 0; j < nc; j++) {
+              const double v = src[j];
+              double av = (bc >= 3) ? -v : v;
+              if (bc * nc + j == a) av += m.ccomp[m.icon[a]];
+              dst[j] = -av;
+            }
+          }
+        } else {
+          const int fr = a - nc, i = m.frow_c[fr], jj = m.frow_j[fr];
+          const size_t ti = (size_t)m.cNK[m.icon[i]] * (B2M_NKMAX / 2) + jj;
+          const double mu = m.cmu[m.icon[i]], cs = qcos[ti], sn = qsin[ti];
+          for (int r = 0; r < NV; r++) col[r] = -0.0;
+          col[i] = -mu; col[nc + i] = -(-cs); col[3 * nc + i] = -(-cs); col[2 * nc + i] = -(-sn); col[4 * nc + i] = -(-sn);
+        }
+        for (int r = NV; r < n; r++) col[r] = 0.0;
+      }
+    }
+  } else
   for (int t = g.tid; t < n * n; t += G::size) {
     const int c = t / n, r = t - c * n;
     // entry of A = [H(0:nc,:) ; friction rows] at (a, col<NV)
@@ -1755,7 +1829,8 @@ B2M_DEV void env_advance(const G& g, const SimParams& P, int e, EnvMem& m, doubl
         const int n = contacts_lcp_dim(m, ncon, P.model);
         int cls = 0;
         while (cls < P.n_classes - 1 && (n > P.class_nmax[cls] || ncon > P.class_cmax[cls])) cls++;
-        if (P.cost && P.hard_cost > 0 && P.cost[e] >= P.hard_cost) q_push_hard(P, round, e, P.cost[e] >= 8 * P.hard_cost);
+        const int hc = P.class_budget[cls] > P.hard_cost ? P.class_budget[cls] : P.hard_cost;   // small classes afford more iterations per env (an iteration costs ~n^2..n^3)
+        if (P.cost && P.hard_cost > 0 && P.cost[e] >= hc) q_push_hard(P, round, e, P.cost[e] >= 8 * P.hard_cost);
         else q_push(P, round, cls, e);
       }
       parked = true;
@@ -1778,6 +1853,8 @@ template <class G>
 B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double dt, int round, unsigned long long* lc, EnvCtx& cx) {
 #ifdef __CUDA_ARCH__
   const long long t0 = P.tap_prof ? clock64() : 0;
+  long long gt0 = 0;
+  if (P.tap_prof && P.tap_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 #endif
   const unsigned long long p0 = lc[CNT_PIVOTS], f0 = lc[CNT_PIVOT_FLOPS];
   const EnvStatBase sb = env_stat_base(lc);
@@ -1791,7 +1868,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   B2M_PROF_ADD(m, g, PH_CONTACTS); }
   lc[CNT_CONTACTS] = c0; lc[CNT_OVERFLOW] = o0;                  // counted by the advance phase
   if (!process_constraints(g, P, e, m, lc, cx)) {
-    if (g.tid == 0) { q_push(P, round, B2M_SLOT_STRAGGLER, e); if (P.cost && P.cost[e] < 4 * P.hard_cost) P.cost[e] = 4 * P.hard_cost; }
+    if (g.tid == 0) { const int hc = P.pivot_budget > P.hard_cost ? P.pivot_budget : P.hard_cost; q_push(P, round, B2M_SLOT_STRAGGLER, e); if (P.cost && P.cost[e] < 4 * hc) P.cost[e] = 4 * hc; }
     g.sync();
     return false;
   }
@@ -1812,6 +1889,10 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
       const long long n = m.scal[S_N];
       P.tap_prof[e] = clock64() - t0; P.tap_prof[ne + e] = (long long)(lc[CNT_PIVOTS] - p0);
       P.tap_prof[2 * ne + e] = n > 0 ? (long long)((lc[CNT_PIVOT_FLOPS] - f0) / (2ull * n * (n + 1))) : 0; P.tap_prof[3 * ne + e] = n + 1000ll * P.kslot;   // LCP dimension + 1000 x the kernel slot that ran the env
+      if (P.tap_times) {   // timeline mode: the islands / store rows carry the env's start / end on the global timer (ns) instead
+        long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        P.tap_prof[(4 + PH_ISLANDS) * ne + e] = gt0; P.tap_prof[(4 + PH_STORE) * ne + e] = gt1;
+      }
     }
 #endif
   }

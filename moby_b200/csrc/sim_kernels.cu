@@ -41,6 +41,8 @@ struct b200moby_sim {
   int thread_budget = 12;    // solver iterations a thread-per-env impact may spend on one env before deferring it
   int adv_thread = -1;       // >= 0: the advance phase runs one thread per env (b2m_k_advance_thread(adv_thread)); -1: warp per env
   std::vector<ClassPlan> classes;
+  int* feed_ctr = nullptr;   // [B2M_ROUNDS_MAX] class launches completed in the round (k_impact_warp.cu: the hard-queue launch takes their stragglers)
+  bool all_thread_classes = false;
   LadderPool pool;           // task pool of the Lemke ladder (lcp_device.cuh) for the hard-queue / straggler launches; ctl == nullptr: off
   int pool_owners = 0;
   ClassPlan straggler;       // full-size kernel (warp per env while the scene's LCPs fit one, else a 256-thread block) for envs over their pivot budget and for the hard queue
@@ -266,7 +268,12 @@ b200moby_status plan_launch(b200moby_sim* h) {
           else if (nd <= B2M_THREAD_ND1 && ni <= B2M_THREAD_NI1) c.tvariant = 1;
         }
       }
-      if (c.tvariant >= 0) { c.threads = 1; c.grid = std::max(1, std::min((ne + 127) / 128, sms * 16)); h->classes.push_back(c); continue; }
+      if (c.tvariant >= 0) {
+        const int lanes = std::max(1, std::min(32, env_int("B200MOBY_THREAD_LANES", 32)));
+        h->P.thread_lanes = lanes;
+        c.threads = 1; c.grid = std::max(1, std::min((ne + 4 * lanes - 1) / (4 * lanes), sms * 16 * (32 / lanes)));
+        h->classes.push_back(c); continue;
+      }
       if (c.nmax <= warp_nmax || bthreads <= 32) c.threads = 32;
       else if (c.nmax > big_n) c.threads = 256;
       else c.threads = bthreads <= 64 ? 64 : (bthreads <= 128 ? 128 : 256);
@@ -276,7 +283,17 @@ b200moby_status plan_launch(b200moby_sim* h) {
     }
     h->P.n_classes = (int)h->classes.size();
     for (const ClassPlan& c : h->classes) if (c.threads == 1) h->any_thread_class = true;
+    h->all_thread_classes = true;
+    for (const ClassPlan& c : h->classes) if (c.threads != 1) h->all_thread_classes = false;
+    if (env_int("B200MOBY_FEED", 1) != 0) { b200moby_status s3; if ((s3 = dev_zero(h, (size_t)B2M_ROUNDS_MAX, &h->feed_ctr)) != B200MOBY_OK) return s3; }
     h->thread_budget = env_int("B200MOBY_THREAD_BUDGET", 12);
+    {   // per-class budget: base x (40 / n)^p, at most 8 x base (an iteration of a small LCP is cheap, so a small class can keep envs the n <= 40 class must hand on)
+      const double pw = env_int("B200MOBY_BUDGET_POW10", 0) / 10.0;
+      for (size_t k = 0; k < h->classes.size(); k++) {
+        const double f = h->classes[k].nmax < 40 ? std::pow(40.0 / h->classes[k].nmax, pw) : 1.0;
+        h->P.class_budget[k] = h->classes[k].threads == 1 ? (int)std::min(8.0 * h->thread_budget, std::floor(h->thread_budget * f)) : 0;
+      }
+    }
     ClassPlan& sg = h->straggler;
     // stragglers and the hard queue want the shortest latency per pivot for one env: measured on configs[1] (n <= 40),
     // the worst env's chain takes 16 ms on a lone warp and 6.7 ms on a 256-thread block
@@ -343,7 +360,7 @@ b200moby_status timed_launch(b200moby_sim* h, int kslot, const void* kernel, dim
 
 // one launch of an impact kernel (warp per env or block per env, per the plan) over queue `slot`; pool: the launch runs
 // the rungs of the Lemke ladder as tasks (lcp_device.cuh) -- its task list is cleared on the launch's stream first
-b200moby_status launch_impact(b200moby_sim* h, int kslot, const ClassPlan& cp, SimParams& Pk, double dt, int r, int slot, bool pool, cudaStream_t sc) {
+b200moby_status launch_impact(b200moby_sim* h, int kslot, const ClassPlan& cp, SimParams& Pk, double dt, int r, int slot, bool pool, cudaStream_t sc, bool feed = false) {
   Pk.gscratch = cp.gscratch; Pk.gstride = cp.gstride; Pk.kslot = kslot;
   if (cp.threads == 32) {
     LadderPool L; memset(&L, 0, sizeof(L));
@@ -353,7 +370,9 @@ b200moby_status launch_impact(b200moby_sim* h, int kslot, const ClassPlan& cp, S
       B2M_CUDA(cudaMemsetAsync(L.tasks, 0, sizeof(int) * L.cap, sc));
     }
     int wpb = cp.wpb;
-    void* a[] = {&Pk, &dt, &r, &slot, &wpb, &L};
+    int feed_slot = feed ? B2M_SLOT_STRAGGLER : -1, feed_expect = (int)h->classes.size();
+    int* feed_done = h->feed_ctr ? h->feed_ctr + r : nullptr;
+    void* a[] = {&Pk, &dt, &r, &slot, &wpb, &L, &feed_slot, &feed_done, &feed_expect};
     return timed_launch(h, kslot, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
   }
   void* a[] = {&Pk, &dt, &r, &slot};
@@ -382,6 +401,13 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
   b200moby_status st;
   const int ncls = (int)h->classes.size();
   B2M_CUDA(cudaMemsetAsync(P.qctl, 0, sizeof(int) * 2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1), s));
+  // the hard-queue launch also takes the stragglers of the classes running next to it (k_impact_warp.cu): only when every
+  // class is a thread-per-env launch (no shared memory: they are sure to be resident beside it) on concurrent streams
+  const bool feed = h->feed_ctr && h->concurrent && h->classes.size() > 1 && h->all_thread_classes && h->straggler.threads == 32 && P.hard_cost > 0;
+  if (feed) {
+    B2M_CUDA(cudaMemsetAsync(h->feed_ctr, 0, sizeof(int) * B2M_ROUNDS_MAX, s));
+    for (int r = 0; r < h->rounds; r++) B2M_CUDA(cudaMemsetAsync(q_list(P, r, B2M_SLOT_STRAGGLER), 0xff, sizeof(int) * h->n_envs, s));
+  }
   for (int r = 0; r < h->rounds; r++) {
     { SimParams Pa = P; Pa.kslot = 0;
       void* a[] = {&Pa, &dt, &r, &h->adv_wpb};
@@ -395,7 +421,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       SimParams Ph = P; Ph.pivot_budget = 0;
       cudaStream_t sc = conc ? h->hard_stream : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
-      if ((st = launch_impact(h, 3 + ncls, h->straggler, Ph, dt, r, B2M_SLOT_HARD, true, sc)) != B200MOBY_OK) return st;
+      if ((st = launch_impact(h, 3 + ncls, h->straggler, Ph, dt, r, B2M_SLOT_HARD, true, sc, feed)) != B200MOBY_OK) return st;
       if (conc) { B2M_CUDA(cudaEventRecord(h->hard_done, sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->hard_done, 0)); }
     }
     for (size_t c = 0; c < h->classes.size(); c++) {
@@ -405,7 +431,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       cudaStream_t sc = conc ? h->side[c] : s;
       if (conc) B2M_CUDA(cudaStreamWaitEvent(sc, h->fork, 0));
       if (cp.threads == 1) {
-        Pc.pivot_budget = h->thread_budget;
+        Pc.pivot_budget = h->P.class_budget[c] > 0 ? h->P.class_budget[c] : h->thread_budget;
         void* a[] = {&Pc, &dt, &r, &slot};
         st = timed_launch(h, 1 + (int)c, b2m_k_impact_thread(cp.tvariant), dim3(cp.grid), dim3(128), a, 0, sc);
       } else {
@@ -413,6 +439,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
         st = launch_impact(h, 1 + (int)c, cp, Pc, dt, r, slot, false, sc);
       }
       if (st != B200MOBY_OK) return st;
+      if (feed) { int* ctr = h->feed_ctr + r; void* sa[] = {&ctr}; B2M_CUDA(cudaLaunchKernel(b2m_k_signal(), dim3(1), dim3(1), sa, 0, sc)); h->launches++; }
       if (conc) { B2M_CUDA(cudaEventRecord(h->side_done[c], sc)); B2M_CUDA(cudaStreamWaitEvent(s, h->side_done[c], 0)); }
     }
     if (P.pivot_budget > 0 || h->any_thread_class) {
@@ -477,6 +504,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   TRY(dev_zero(h, (size_t)CNT_COUNT, &P.counters));
   TRY(dev_zero(h, (size_t)3 * (B2M_MAX_CLASSES + 6), &P.kstat));
   TRY(dev_zero(h, (size_t)ne, &P.cost));
+  P.tap_times = env_int("B200MOBY_TAP_TIMES", 0);
   P.hard_cost = env_int("B200MOBY_HARD_COST", 12);
   P.cost_shift = std::max(0, std::min(30, env_int("B200MOBY_COST_DECAY_SHIFT", 2)));
   TRY(dev_zero(h, (size_t)ne, &P.hacc));

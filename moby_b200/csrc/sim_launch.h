@@ -11,7 +11,8 @@ const void* b2m_k_advance_thread(int cls); // (SimParams P, double dt, int round
 #define B2M_THREAD_ND1 5632
 #define B2M_THREAD_NI1 384
 const void* b2m_k_impact_thread(int variant);   // (SimParams P, double dt, int round, int slot)
-const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb, LadderPool L)
+const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb, LadderPool L, int feed_slot, int* feed_done, int feed_expect)
+const void* b2m_k_signal();               // (int* counter): one thread, counter += 1 (stream-ordered completion signal of a class launch)
 const void* b2m_k_impact_block64();
 const void* b2m_k_impact_block128();
 const void* b2m_k_impact_block256();

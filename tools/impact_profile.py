@@ -26,6 +26,8 @@ for s in range(5):
         k = m & (n == nn)
         by_n[int(nn)] = dict(phases=[round(float(ph[j][k].mean())) for j in range(9)], envs=int(k.sum()), cyc_mean=float(cyc[k].mean()), cyc_max=int(cyc[k].max()), cyc_sum=int(cyc[k].sum()), piv_mean=float(piv[k].mean()), ex_mean=float(ex[k].mean()))
     r["by_n"] = by_n
+    r["by_kslot_n"] = {f"{int(ks)}:{int(nn)}": dict(phases=[round(float(ph[j][k2].mean())) for j in range(9)], envs=int(k2.sum()), cyc_mean=float(cyc[k2].mean()), cyc_max=int(cyc[k2].max()), ex_mean=float(ex[k2].mean()), ex_max=int(ex[k2].max()))
+                       for ks in np.unique(kslot[m]) for nn in np.unique(n[m & (kslot == ks)]) for k2 in [m & (kslot == ks) & (n == nn)]}
     top = np.argsort(cyc)[-8:]
     r["top"] = [dict(e=int(e), cyc=int(cyc[e]), piv=int(piv[e]), ex=int(ex[e]), n=int(n[e]), kslot=int(kslot[e]), fast_cyc=int(ph[5][e]), lemke_cyc=int(ph[6][e])) for e in top]
     r["by_kslot"] = {int(k): dict(envs=int((m & (kslot == k)).sum()), cyc_max=int(cyc[m & (kslot == k)].max()), cyc_sum=int(cyc[m & (kslot == k)].sum()), ex_max=int(ex[m & (kslot == k)].max())) for k in np.unique(kslot[m])}
