@@ -573,11 +573,18 @@ def main():
         achieved_gbs = alg_bytes / (dom_launch_ms * 1e-3) / 1e9
         achieved_tf = alg_flops / (dom_launch_ms * 1e-3) / 1e12
         step_ms_sum = sum(k["ms"] for k in kprof) or 1.0
-        # DRAM bytes per launch of the dominant kernel from the one `ncu --set full` capture kept under profiles/
-        # (r01_ncu_full_final_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum); only known for configs[1]
-        ncu_traffic = {"impact_block_kernel<128>[hard queue]": 30.37e6 + 46.23e6, "impact_thread_kernel[n<=40]": 17.39e6 + 54.64e6,
-                       "advance_kernel": 64.90e6 + 117.72e6}
-        traffic = ncu_traffic.get(dom["name"]) if args.workload == "small" and ne == W["envs"] else None
+        # DRAM bytes per launch of the dominant kernel: read from the round's ncu capture summary under profiles/ (written by
+        # hand from `ncu --set full` raw pages, see its "source" key) when it covers this workload, batch size and kernel; null otherwise
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("workload") == args.workload and tj.get("envs_per_gpu") == ne:
+                    traffic = tj["kernels"].get(dom["name"])
+                    traffic_src = "profiles/r02_ncu_traffic.json" if traffic is not None else None
+            except Exception:
+                pass
         out = {
             "metric": "env_steps_per_s", "value": total_envs * args.steps / t_dev, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
@@ -592,11 +599,13 @@ def main():
             "lcp_failures": failures, "contacts_per_env_step": contacts / max(env_steps, 1.0), "ca_iterations_per_env_step": r_cnt["ca_iterations"] / max(r_cnt["env_steps"], 1),
             "wall_s_timed_region": wall,
             "e2e": {"value": total_envs * args.steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
-                    "how": "pinned host q,v -> device -> b200moby_set_state_dev -> step -> get_state_dev -> pinned host, every step"},
+                    "how": "pinned host q,v (+ joint state) -> device -> b200moby_set_state_dev -> step -> get_state_dev -> pinned host, every step; wall clock around "
+                           "the loop, no L2 flush between steps (the device-timed `value` flushes L2 before every step, so e2e can come out above it); the host-pointer "
+                           "entry points b200moby_set_state / get_state do the same copies synchronously from pageable memory"},
             "gpu_launches": launches * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": traffic, "kernel": dom["name"], "kernel_ms": dom_launch_ms, "launches": dom["launches"],
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": dom["name"], "kernel_ms": dom_launch_ms, "launches": dom["launches"],
                          "envs_per_launch": dom["envs"] / max(dom["launches"], 1), "share_of_kernel_time": dom["ms"] / step_ms_sum,
                          "peak_source": hbm_src,
                          "note": "pivoting is a dependent-latency chain per env: neither HBM nor the FP64 pipe is the limiter (see DESIGN.md 3-4); "

@@ -218,9 +218,160 @@ static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* 
   nlog_io = nlog; piv_io = piv; executed_io = executed; if (budget) *budget = bud;
   return status;
 }
+
+// ---- register-resident tableau (compile-time n, working set in shared memory) ---------------------------------------
+// Measured on the hard queue of configs[1] (profiles/r02_hard_queue_timeline.json): a 1,000-pivot rung takes 1.3 ms on an
+// idle SM and 4-5 ms while four other warps of the launch pivot next to it -- the shared-memory pipe, not latency, sets
+// the pace once several warps walk their tableaus through LDS / STS (about 400 wavefronts per pivot at n = 40).  Here
+// lane l keeps its rows l and l + 32 in REGISTERS for the whole solve (2 x (n + 2) doubles, every index a compile-time
+// constant in the unrolled loops); per pivot the shared-memory traffic is the pivot row (written once by the lane that
+// owns it, scaled by the lanes in parallel, read back as broadcasts) plus bas / where -- about 90 wavefronts -- and the
+// rank-one update is a straight run of register fmas.  The entering column of the NEXT pivot is picked up during the
+// update (its slot is known as soon as the leaving variable is), so no dynamic register indexing is ever needed.
+// Same operations per entry in the same order as lemke_loop_warp and the generic loop: bit-identical results.
+// f(integral_constant<int, c>) for the c in [0, NC) that equals s.  s is warp-uniform, so this is one jump for the whole
+// warp: the way to reach "register number s" without a per-element select (an FSEL pair per entry made the first version
+// of the loop below three times longer than the shared-memory one).
+template <int C> struct b2m_ic { static constexpr int value = C; };
+#define B2M_SW_CASE(c) case c: if constexpr (c < NC) { asm volatile(""); f(b2m_ic<c>{}); } break;   /* the empty asm keeps the compiler from turning the jump into NC select pairs */
+template <int NC, class F>
+static __device__ __forceinline__ void b2m_static_switch(int s, F&& f) {
+  static_assert(NC <= 44, "extend the case list");
+  switch (s) {
+    B2M_SW_CASE(0) B2M_SW_CASE(1) B2M_SW_CASE(2) B2M_SW_CASE(3) B2M_SW_CASE(4) B2M_SW_CASE(5) B2M_SW_CASE(6) B2M_SW_CASE(7) B2M_SW_CASE(8) B2M_SW_CASE(9) B2M_SW_CASE(10)
+    B2M_SW_CASE(11) B2M_SW_CASE(12) B2M_SW_CASE(13) B2M_SW_CASE(14) B2M_SW_CASE(15) B2M_SW_CASE(16) B2M_SW_CASE(17) B2M_SW_CASE(18) B2M_SW_CASE(19) B2M_SW_CASE(20) B2M_SW_CASE(21)
+    B2M_SW_CASE(22) B2M_SW_CASE(23) B2M_SW_CASE(24) B2M_SW_CASE(25) B2M_SW_CASE(26) B2M_SW_CASE(27) B2M_SW_CASE(28) B2M_SW_CASE(29) B2M_SW_CASE(30) B2M_SW_CASE(31) B2M_SW_CASE(32)
+    B2M_SW_CASE(33) B2M_SW_CASE(34) B2M_SW_CASE(35) B2M_SW_CASE(36) B2M_SW_CASE(37) B2M_SW_CASE(38) B2M_SW_CASE(39) B2M_SW_CASE(40) B2M_SW_CASE(41) B2M_SW_CASE(42) B2M_SW_CASE(43)
+    default: break;
+  }
+}
+#undef B2M_SW_CASE
+
+template <int N>
+static __device__ __noinline__ int lemke_loop_warp_reg(double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
+                                                       int* log, int log_cap, int& nlog_io, int& piv_io, int& executed_io, int* budget, const volatile int* cancel) {
+  __builtin_assume(__isShared(T)); __builtin_assume(__isShared(rvec)); __builtin_assume(__isShared(where)); __builtin_assume(__isShared(bas));
+  constexpr int n = N, NC = N + 2, t = 2 * N;
+  constexpr bool TWO = N > 32;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int MAXITER = min(1000, 50 * n);
+  const int i0 = lane, i1 = lane + 32;
+  const bool h0 = i0 < n, h1 = TWO && i1 < n;
+  const int j0 = h0 ? i0 : 0, j1 = h1 ? i1 : j0;
+  double R0[NC], R1[TWO ? NC : 1];
+#pragma unroll
+  for (int c = 0; c < NC; c++) { R0[c] = T[c * n + j0]; if (TWO) R1[c] = T[c * n + j1]; }
+  int s = n, entering = t, status = LCP_OK;
+  int nlog = nlog_io, piv = piv_io, executed = executed_io, bud = budget ? *budget : 0;
+  bool first = true;
+  for (;;) {
+    double d0 = 0.0, d1 = 0.0;                                   // entering column, my rows: "register s", reached by one warp-uniform jump
+    b2m_static_switch<NC>(s, [&](auto ic) { constexpr int c = decltype(ic)::value; d0 = R0[c]; if (TWO) d1 = R1[c]; });
+    if (!first) {
+      executed++;
+      const double x0 = R0[N + 1], x1 = TWO ? R1[N + 1] : 0.0;
+      const bool c0 = h0 && d0 > PIV_TOL, c1 = h1 && d1 > PIV_TOL;
+      double a0, a1, b0, b1;
+      if (TWO) {
+        const double num[4] = {x0 + zero_tol, x1 + zero_tol, x0, x1}, den[4] = {c0 ? d0 : 1.0, c1 ? d1 : 1.0, c0 ? d0 : 1.0, c1 ? d1 : 1.0};
+        double quo[4];
+        b2m_divn<4>(num, den, quo);
+        a0 = c0 ? quo[0] : B2M_INF; a1 = c1 ? quo[1] : B2M_INF; b0 = c0 ? quo[2] : B2M_INF; b1 = c1 ? quo[3] : B2M_INF;
+      } else {
+        const double num[2] = {x0 + zero_tol, x0}, den[2] = {c0 ? d0 : 1.0, c0 ? d0 : 1.0};
+        double quo[2];
+        b2m_divn<2>(num, den, quo);
+        a0 = c0 ? quo[0] : B2M_INF; b0 = c0 ? quo[1] : B2M_INF; a1 = B2M_INF; b1 = B2M_INF;
+      }
+      const double theta = b2m_warp_min(fmin(a0, a1));
+      if (theta == B2M_INF) { status = LCP_RAY; break; }
+      const int trow = -(where[t] + 1);
+      int lo = 0x7fffffff;
+      if (c0 && b0 <= theta) lo = (i0 == trow) ? -1 : i0;
+      if (c1 && b1 <= theta) { const int key = (i1 == trow) ? -1 : i1; if (key < lo) lo = key; }
+      lo = __reduce_min_sync(FULL, lo);
+      if (lo == 0x7fffffff) { status = LCP_EMPTY_RATIO; break; }
+      r = (lo < 0) ? trow : lo;
+    }
+    const int leaving = bas[r];
+    const double p = __shfl_sync(FULL, (r < 32) ? d0 : d1, r & 31);
+    const bool is0 = h0 && i0 == r, is1 = h1 && i1 == r;        // this lane owns the pivot row
+    __syncwarp();                                               // everyone has read bas / where / rvec before they change
+    // The owner hands its row over and clears it to -0.0: with the multiplier 1 below, fma(1, r_c, -0.0) == r_c bit for bit
+    // (signed zeros included), so the pivot row needs no special case in the update.
+    if (is0) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) { rvec[c] = R0[c]; R0[c] = -0.0; }
+    }
+    if (TWO && is1) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) { rvec[c] = R1[c]; R1[c] = -0.0; }
+    }
+    // the leaving variable's column (a unit vector while basic) replaces slot s: every other row starts it from zero
+    b2m_static_switch<NC>(s, [&](auto ic) { constexpr int c = decltype(ic)::value; if (!is0) R0[c] = 0.0; if (TWO && !is1) R1[c] = 0.0; });
+    __syncwarp();
+    {   // pivot row, scaled: lane c forms r_c (and r_{c+32})
+      const int ca = lane, cb = lane + 32;
+      const bool ha = ca < NC, hb = cb < NC;
+      const double num[2] = {(ca == s) ? 1.0 : rvec[ha ? ca : 0], (cb == s) ? 1.0 : rvec[hb ? cb : 0]}, den[2] = {p, p};
+      double rv[2];
+      b2m_divn<2>(num, den, rv);
+      if (ha) rvec[ca] = rv[0];
+      if (hb) rvec[cb] = rv[1];
+    }
+    if (lane == 0) {
+      if (log && nlog < log_cap) log[nlog] = leaving;
+      where[entering] = -(r + 1); where[leaving] = s; bas[r] = entering;
+    }
+    nlog++;
+    __syncwarp();
+    const double m0 = is0 ? 1.0 : -d0, m1 = is1 ? 1.0 : -d1;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const double rc = rvec[c];
+      R0[c] = fma(m0, rc, R0[c]);
+      if (TWO) R1[c] = fma(m1, rc, R1[c]);
+    }
+    if (!first) piv++;
+    if (budget && --bud < 0) { status = LCP_DEFER; break; }
+    if (cancel && (piv & 63) == 63 && *cancel) { status = LCP_DEFER; break; }
+    first = false;
+    if (leaving == t) break;
+    if (piv >= MAXITER) { status = LCP_MAXITER; break; }
+    entering = (leaving < n) ? n + leaving : leaving - n;
+    s = where[entering];
+  }
+  __syncwarp();
+  if (h0) T[n * (n + 1) + i0] = R0[N + 1];                      // x back to the tableau: the caller reads the solution from it
+  if (h1) T[n * (n + 1) + i1] = R1[N + 1];
+  __syncwarp();
+  nlog_io = nlog; piv_io = piv; executed_io = executed; if (budget) *budget = bud;
+  return status;
+}
+// Measured and NOT used by default (profiles/r02_lemke_register_tableau.json): 16.2 M against 22.9 M solves/s at n = 40 and
+// 54.8 M against 95.5 M at n = 20 on the batched solver microbenchmark, 8.0 against 7.0 ms for the hard queue of configs[1].
+// Shared-memory wavefronts do drop 3.4x (467 M against 1,601 M per launch), but the 2 x 42 register rows leave the
+// compiler no registers to keep the pivot-row loads ahead of the fmas (short-scoreboard stalls on every r_c), and the
+// jump into "register s" costs instruction fetches (no_instruction stalls) that the compact shared-memory loop never pays.
+#ifndef B2M_LEMKE_REG
+#define B2M_LEMKE_REG 0
+#endif
 template <bool SH>
 static __device__ __forceinline__ int lemke_loop_warp_n(int n, double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
                                                         int* log, int log_cap, int& nlog, int& piv, int& executed, int* budget, const volatile int* cancel) {
+  if (SH && B2M_LEMKE_REG) {
+    switch (n) {
+      case 40: return lemke_loop_warp_reg<40>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      case 30: return lemke_loop_warp_reg<30>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      case 20: return lemke_loop_warp_reg<20>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      case 10: return lemke_loop_warp_reg<10>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      case 32: return lemke_loop_warp_reg<32>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      case 24: return lemke_loop_warp_reg<24>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      case 16: return lemke_loop_warp_reg<16>(T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
+      default: break;
+    }
+  }
   switch (n) {
     case 40: return lemke_loop_warp<SH, 40>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
     case 32: return lemke_loop_warp<SH, 32>(n, T, rvec, where, bas, PIV_TOL, zero_tol, r, log, log_cap, nlog, piv, executed, budget, cancel);
@@ -931,10 +1082,13 @@ struct LadderPool {
 };
 enum { LJ_GEN = 0, LJ_CANCEL, LJ_INFLIGHT, LJ_N, LJ_NRUNGS, LJ_MINEXP, LJ_STEPEXP, LJ_HDR = 8 };
 #define B2M_LADDER_MAX_RUNGS 24
+#define LJ_RW 8            /* ints per rung: ready, status, ok, pivots, executed, then (debug) pick-up and finish time in us */
+#define LJ_POST 7          /* header word: (debug) time the job was posted, us */
+__device__ __forceinline__ int b2m_now_us() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (int)((t / 1000) & 0x7fffffff); }
 #define B2M_LADDER_PROBE 128
 B2M_HD inline size_t ladder_job_doubles(int nmax) { return (size_t)nmax * nmax + nmax + (size_t)B2M_LADDER_MAX_RUNGS * nmax; }
-B2M_HD inline size_t ladder_job_ints() { return LJ_HDR + 5 * B2M_LADDER_MAX_RUNGS; }
-struct LadderCtx { LadderPool pool; int owner; double* wd; int* wi; };    // wd / wi: this warp's Lemke work area (shared memory)
+B2M_HD inline size_t ladder_job_ints() { return LJ_HDR + LJ_RW * B2M_LADDER_MAX_RUNGS; }
+struct LadderCtx { LadderPool pool; int owner; double* wd; int* wi; long long* dbg = nullptr; };    // wd / wi: this warp's Lemke work area (shared memory)
 
 // takes one task from the list and runs it; false when there was none
 static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double* wd, int* wi) {
@@ -954,7 +1108,7 @@ static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double*
       int* mo = L.meta + (size_t)((v >> 6) - 1) * L.meta_stride;
       atomicAdd(mo + LJ_INFLIGHT, 1);
       __threadfence();
-      if (((volatile int*)mo)[LJ_GEN] == tg && ((volatile int*)mo)[LJ_CANCEL] == 0) { run = 1; ((volatile int*)mo)[LJ_HDR + 5 * (v & 63)] = 2; }   // 2: taken, running
+      if (((volatile int*)mo)[LJ_GEN] == tg && ((volatile int*)mo)[LJ_CANCEL] == 0) { run = 1; mo[LJ_HDR + LJ_RW * (v & 63) + 5] = b2m_now_us(); ((volatile int*)mo)[LJ_HDR + LJ_RW * (v & 63)] = 2; }   // 2: taken, running
       else { atomicSub(mo + LJ_INFLIGHT, 1); run = 2; }      // stale or cancelled: skipped, but a task was consumed
       break;
     }
@@ -976,8 +1130,8 @@ static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double*
   const bool ok = (st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, n, q, lambda, zr, jd[2], rung > 0, wd + (size_t)n * (n + 2));
   __syncwarp();
   if (lane == 0) {
-    int* r = mo + LJ_HDR + 5 * rung;
-    r[1] = st; r[2] = ok ? 1 : 0; r[3] = piv; r[4] = ex;
+    int* r = mo + LJ_HDR + LJ_RW * rung;
+    r[1] = st; r[2] = ok ? 1 : 0; r[3] = piv; r[4] = ex; r[6] = b2m_now_us();
     __threadfence();
     ((volatile int*)r)[0] = 1;
     __threadfence();
@@ -1022,9 +1176,10 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
   if (g.tid == 0) {
     while (((volatile int*)mo)[LJ_INFLIGHT] != 0) __nanosleep(100);
     gen = mo[LJ_GEN] + 1;
+    mo[LJ_POST] = b2m_now_us();
     mo[LJ_CANCEL] = 0; mo[LJ_N] = n; mo[LJ_NRUNGS] = n_rungs; mo[LJ_MINEXP] = min_exp; mo[LJ_STEPEXP] = step_exp;
     jd[0] = piv_tol; jd[1] = zero_tol; jd[2] = ZERO_TOL; jd[3] = offdiag;
-    for (int k = first_rung; k < n_rungs; k++) mo[LJ_HDR + 5 * k] = 0;
+    for (int k = first_rung; k < n_rungs; k++) mo[LJ_HDR + LJ_RW * k] = 0;
   }
   g.sync();
   for (int e = g.tid; e < n * n; e += 32) { const int c = e / n, r = e - c * n; job[e] = M[(size_t)c * ldm + r]; }
@@ -1067,7 +1222,7 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
     }
   }
   for (int k = first_rung; posted && k < n_rungs; k++) {
-    volatile int* r = mo + LJ_HDR + 5 * k;
+    volatile int* r = mo + LJ_HDR + LJ_RW * k;
     for (;;) {
       int ready = 0;
       if (g.tid == 0) ready = r[0];
@@ -1077,6 +1232,13 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
     }
     __threadfence();
     const int pk = r[3], ek = r[4], okk = r[2];
+    if (C.dbg && g.tid == 0) {                            // timeline taps: worst pick-up delay and run time of the rungs consumed, how many
+      const int post = mo[LJ_POST], pick = r[5] - post, run = r[6] - r[5];
+      if (pick > C.dbg[0]) C.dbg[0] = pick;
+      if (run > C.dbg[1]) C.dbg[1] = run;
+      C.dbg[2]++;
+      if (pk >= 1000) C.dbg[3]++;
+    }
     total += pk;
     if (stats && g.tid == 0) { stats[0]++; stats[1] += pk; stats[2] += ek; }
     if (okk) {

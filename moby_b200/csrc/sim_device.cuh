@@ -114,6 +114,7 @@ struct EnvMem {
   int *ranc, *gcb, *gcl;       // articulated body: ancestor-joint bitmask per link; island coordinate -> (super body, local index)
   long long* prof; long long prof_stride;   // debug: per-phase cycle accumulators of the env being processed (null: off)
   const double* wtab;                       // SimParams::fr_tab + B2M_WTAB_OFF
+  long long dbg[4];                         // debug (timeline taps): worst pick-up delay / run time (us), rungs consumed, rungs that hit the pivot cap
   double cdt;                               // SimParams::contact_dist_thresh (the rimless wheel's contact generator reads the simulator's, whatever TOL its caller passes)
 };
 
@@ -1312,7 +1313,14 @@ B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m
   int piv = 0;
   int* bud = cx.limit ? &cx.budget : nullptr;
   int st;
+#ifdef __CUDA_ARCH__
+#define B2M_STAMP(row) do { if (m.prof && P.tap_times && g.tid == 0) { long long _gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_gt)); m.prof[(row) * m.prof_stride] = _gt; } } while (0)
+#else
+#define B2M_STAMP(row) do {} while (0)
+#endif
+  B2M_STAMP(PH_CONTACTS);                                                            // timeline mode: before the lcp_fast ladder
   { B2M_PROF_T0(m); st = lcp_fast_regularized(g, n, m.MM, n, m.qq, -1.0, true, -20, 4, -8, m.z, m.work, m.iwork, &piv, stats, bud); B2M_PROF_ADD(m, g, PH_FAST); }   // :219
+  B2M_STAMP(PH_PROBLEM);                                                             // after it
   if (st == LCP_DEFER) return false;
   long long fast_calls = stats[0], pivots = stats[1], executed = stats[2], lemke_calls = 0;
   if (st == LCP_UNVERIFIED) {
@@ -1321,13 +1329,18 @@ B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m
     { B2M_PROF_T0(m);
 #ifdef __CUDACC__
       if constexpr (G::size == 32) {
-        if (cx.ladder) st = lcp_lemke_regularized_pool(g, *(const LadderCtx*)cx.ladder, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, &piv, stats);
+        if (cx.ladder) {
+          LadderCtx LC = *(const LadderCtx*)cx.ladder;
+          if (m.prof && P.tap_times) LC.dbg = m.dbg;
+          st = lcp_lemke_regularized_pool(g, LC, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, &piv, stats);
+        }
         else st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);
       } else
 #endif
       st = lcp_lemke_regularized(g, n, m.MM, n, m.qq, -1.0, -1.0, -20, 1, 1, m.z, m.work, m.iwork, &piv, stats, bud);   // :222-225
       B2M_PROF_ADD(m, g, PH_LEMKE); }
     if (st == LCP_DEFER) return false;
+    B2M_STAMP(PH_BUILD);                                                             // after the Lemke ladder
     lemke_calls = stats[0]; pivots += stats[1]; executed += stats[2];
     if (st == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) m.z[i] = 0.0; if (g.tid == 0) { lc[CNT_LCP_FAIL]++; m.scal[S_FAILED] = 1; } }
   }
@@ -1862,6 +1875,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
   { B2M_PROF_T0(m); env_load(g, P, e, m); B2M_PROF_ADD(m, g, PH_LOAD); }
   const unsigned long long c0 = lc[CNT_CONTACTS], o0 = lc[CNT_OVERFLOW];
   if (g.tid == 0) { m.scal[S_FAILED] = 0; m.scal[S_EXEC] = 0; }
+  m.dbg[0] = m.dbg[1] = m.dbg[2] = m.dbg[3] = 0;
   { B2M_PROF_T0(m);
   calc_pairwise_distances(g, m);
   find_unilateral_constraints(g, P, e, m, lc);
@@ -1892,6 +1906,7 @@ B2M_DEV bool env_impact(const G& g, const SimParams& P, int e, EnvMem& m, double
       if (P.tap_times) {   // timeline mode: the islands / store rows carry the env's start / end on the global timer (ns) instead
         long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
         P.tap_prof[(4 + PH_ISLANDS) * ne + e] = gt0; P.tap_prof[(4 + PH_STORE) * ne + e] = gt1;
+        P.tap_prof[(4 + PH_APPLY) * ne + e] = m.dbg[0]; P.tap_prof[(4 + PH_LOAD) * ne + e] = m.dbg[1]; P.tap_prof[(4 + PH_LEMKE) * ne + e] = m.dbg[2] + 1000 * m.dbg[3];
       }
     }
 #endif

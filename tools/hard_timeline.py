@@ -29,6 +29,9 @@ for s in range(3):
         lng = np.where(ex[k] >= 500)[0]
         r[int(ks)] = dict(envs=int(k.sum()), span_ms=float(b.max()), grid_ms=[round(float(x), 2) for x in grid], inflight=inflight, started=started,
                           dur_ms_pct=[round(float(np.percentile(b - a, q)), 3) for q in (50, 90, 99, 100)],
-                          long=[dict(start=round(float(a[i]), 2), end=round(float(b[i]), 2), ex=int(ex[k][i]), n=int(n[k][i])) for i in lng])
+                          long=[dict(start=round(float(a[i]), 2), end=round(float(b[i]), 2), ex=int(ex[k][i]), n=int(n[k][i]),
+                                     fast0=round(float((p[4 + 1][k][i] - base) / 1e6), 2), fast1=round(float((p[4 + 3][k][i] - base) / 1e6), 2),
+                                     lemke1=round(float((p[4 + 4][k][i] - base) / 1e6), 2), max_pick_ms=float(p[4 + 7][k][i]) / 1e3, max_run_ms=float(p[4 + 0][k][i]) / 1e3,
+                                     rungs=int(p[4 + 6][k][i] % 1000), rungs_1000=int(p[4 + 6][k][i] // 1000)) for i in lng])
     out.append(r)
 print(json.dumps(out))
