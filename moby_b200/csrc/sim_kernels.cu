@@ -41,6 +41,10 @@ struct b200moby_sim {
   int thread_budget = 12;    // solver iterations a thread-per-env impact may spend on one env before deferring it
   int adv_thread = -1;       // >= 0: the advance phase runs one thread per env (b2m_k_advance_thread(adv_thread)); -1: warp per env
   std::vector<ClassPlan> classes;
+  // one step captured as a CUDA graph (b200moby_step): ~25 launches, memsets and the stream fork / join of a step become
+  // one cudaGraphLaunch.  Captured on an internal stream; re-captured when dt or anything in SimParams changes.
+  cudaGraphExec_t graph_exec = nullptr; cudaStream_t graph_stream = nullptr;
+  SimParams graph_P; double graph_dt = 0.0; long long graph_launches = 0; bool graph_on = true; int graph_captures = 0;
   int* feed_ctr = nullptr;   // [B2M_ROUNDS_MAX] class launches completed in the round (k_impact_warp.cu: the hard-queue launch takes their stragglers)
   bool all_thread_classes = false;
   LadderPool pool;           // task pool of the Lemke ladder (lcp_device.cuh) for the hard-queue / straggler launches; ctl == nullptr: off
@@ -532,6 +536,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   }
   TRY(plan_launch(h));
   h->concurrent = env_int("B200MOBY_CONCURRENT", 1) != 0;
+  h->graph_on = env_int("B200MOBY_GRAPH", 1) != 0;
   if (h->concurrent) {
     h->side.resize(h->classes.size()); h->side_done.resize(h->classes.size());
     for (size_t c = 0; c < h->classes.size(); c++) { h->side[c] = nullptr; h->side_done[c] = nullptr; }
@@ -556,6 +561,8 @@ b200moby_status b200moby_destroy(b200moby_handle h) {
   if (h->fork) cudaEventDestroy(h->fork);
   if (h->hard_stream) { cudaStreamSynchronize(h->hard_stream); cudaStreamDestroy(h->hard_stream); }
   if (h->hard_done) cudaEventDestroy(h->hard_done);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
   for (auto& pe : h->kev_pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto& pe : h->kev_free) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (void* p : h->allocs) cudaFree(p);
@@ -680,6 +687,30 @@ b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* s
       if (st != B200MOBY_OK) return st;
     }
     return B200MOBY_OK;
+  }
+  if (h->graph_on && !h->ktiming) {
+    if (!h->graph_exec || h->graph_dt != dt || memcmp(&h->graph_P, &h->P, sizeof(SimParams)) != 0) {
+      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+      if (!h->graph_stream) B2M_CUDA(cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+      const long long l0 = h->launches;
+      cudaGraph_t graph = nullptr;
+      B2M_CUDA(cudaStreamBeginCapture(h->graph_stream, cudaStreamCaptureModeRelaxed));
+      const b200moby_status st = launch_step(h, dt, h->graph_stream);
+      const cudaError_t ce = cudaStreamEndCapture(h->graph_stream, &graph);
+      h->graph_launches = h->launches - l0; h->launches = l0;
+      if (st != B200MOBY_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+      if (ce != cudaSuccess || !graph) { cudaGetLastError(); h->graph_on = false; }      // capture not possible here: plain launches from now on
+      else {
+        const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); h->graph_exec = nullptr; h->graph_on = false; }
+        else { h->graph_P = h->P; h->graph_dt = dt; h->graph_captures++; }
+      }
+    }
+    if (h->graph_exec) {
+      for (int k = 0; k < n_steps; k++) { B2M_CUDA(cudaGraphLaunch(h->graph_exec, s)); h->launches += h->graph_launches; }
+      return B200MOBY_OK;
+    }
   }
   for (int k = 0; k < n_steps; k++) {
     b200moby_status st = launch_step(h, dt, s);

@@ -295,3 +295,27 @@ def test_ladder_task_pool_gives_the_sequential_results(torch_cuda):
     assert res[0][0] == res[1][0], (res[0][0], res[1][0])
     assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
     assert res[0][0]["lemke_calls"] > res[0][0]["lcp_solves"] // 50 and res[0][0]["lemke_calls"] > 20000       # ladders beyond rung 0 were run
+
+
+@pytest.mark.parametrize("knob", ["B200MOBY_GRAPH", "B200MOBY_FEED"])
+def test_schedule_knobs_do_not_change_results(torch_cuda, knob):
+    """One step as a CUDA graph (re-captured when dt changes) against plain launches, and the hard-queue launch taking the
+    classes' stragglers as they arrive against a straggler launch of its own: scheduling only -- states and every counter equal."""
+    import os
+    from moby_b200 import TimeSteppingSimulator
+    sc = scenes.small_lcp_batch(8192, seed=0xB200)
+    sc.stabilization_max_iterations = -1
+    res = []
+    for val in ("1", "0"):
+        os.environ[knob] = val
+        try:
+            sim = TimeSteppingSimulator(sc)
+            sim.step(1e-3, 200)
+            sim.step(5e-4, 50)           # another dt: the graph is captured again
+            sim.step(1e-3, 50)
+            res.append((sim.counters(), sim.get_state(), sim.launch_count()))
+        finally:
+            del os.environ[knob]
+    assert res[0][0] == res[1][0], (res[0][0], res[1][0])
+    assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
+    assert res[0][0]["lcp_failures"] == 0 and res[0][2] > 0
