@@ -297,6 +297,10 @@ b200moby_status b200moby_rc_inertia_batched(b200moby_handle h, const double* jq_
 b200moby_status b200moby_find_contacts_batched(b200moby_handle h, const double* q_dev, const double* v_dev, int cap, int* count_dev,
                                                double* point_dev, double* normal_dev, double* tan1_dev,
                                                double* tan2_dev, int* pair_dev, double* dist_dev, void* stream);
+/* The same for the simulator's current state with HOST output buffers (synchronous; what ConstraintSimulator::get_rigid_constraints
+ * and the constraint callbacks of ConstraintSimulator.h:51-68 need on the host; a slow path by design). */
+b200moby_status b200moby_find_contacts_host(b200moby_handle h, int cap, int* count, double* point, double* normal, double* tan1,
+                                            double* tan2, int* pair, double* dist);
 /* Delassus / LCP assembly for the contacts found at (q,v): writes MM [env][nmax*nmax] (column-major, ld = n[env]),
  * qq [env][nmax], n_dev [env] (ImpactConstraintHandler.cpp:1898-2166 + ImpactConstraintHandlerQP.cpp:271-497
  * or ImpactConstraintHandlerLCP.cpp:94-310). Only the first island of each env is assembled. */

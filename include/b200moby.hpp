@@ -212,8 +212,17 @@ class GravityForce : public RecurrentForce {
 
 class TimeSteppingSimulator;
 
-class RigidBody : public Base {
+// ControlledBody (ControlledBody.h:37-40): the controller callback and its argument
+class ControlledBody : public Base, public std::enable_shared_from_this<ControlledBody> {
  public:
+  Ravelin::VectorNd& (*controller)(std::shared_ptr<ControlledBody>, Ravelin::VectorNd&, double, void*) = nullptr;
+  void* controller_arg = nullptr;
+};
+typedef std::shared_ptr<ControlledBody> ControlledBodyPtr;
+
+class RigidBody : public ControlledBody {
+ public:
+  std::string body_id;
   std::list<CollisionGeometryPtr> geometries;
   void set_enabled(bool e) { enabled_ = e; }
   bool is_enabled() const { return enabled_; }
@@ -228,6 +237,7 @@ class RigidBody : public Base {
 
  private:
   friend class TimeSteppingSimulator;
+  friend class RCArticulatedBody;
   bool enabled_ = true;
   Ravelin::SpatialRBInertiad J_;
   std::list<RecurrentForcePtr> forces_;
@@ -237,7 +247,73 @@ class RigidBody : public Base {
   int index_ = -1;
 };
 typedef std::shared_ptr<RigidBody> RigidBodyPtr;
-typedef RigidBodyPtr ControlledBodyPtr;
+
+// ---------------------------------------------------------------------------------------------- joints, articulated body
+struct DynamicBodyd { enum GeneralizedCoordinateType { eEuler, eSpatial }; };
+// Joint.h / Ravelin::Jointd: one-DoF joints of a fixed-base tree.  set_location(point, inboard, outboard) and set_axis(axis)
+// take GLOBAL-frame values at the links' construction poses, as example/sims-in-code/pendulum.cpp:85-103 uses them
+// (set_location before set_axis).
+class Joint : public Base {
+ public:
+  std::string joint_id;
+  Ravelin::VectorNd q = Ravelin::VectorNd(1, 0.0), qd = Ravelin::VectorNd(1, 0.0);    // position / velocity of the CURRENT env (see RCArticulatedBody)
+  virtual int type() const = 0;
+  unsigned num_dof() const { return 1; }
+  unsigned get_coord_index() const { return (unsigned)coord_; }
+  void set_location(const Ravelin::Vector3d& p, RigidBodyPtr inboard, RigidBodyPtr outboard) { loc_ = p; in_ = inboard; out_ = outboard; }
+  void set_axis(const Ravelin::Vector3d& a) { axis_ = a; }
+  RigidBodyPtr get_inboard_link() const { return in_; }
+  RigidBodyPtr get_outboard_link() const { return out_; }
+
+ private:
+  friend class RCArticulatedBody;
+  friend class TimeSteppingSimulator;
+  Ravelin::Vector3d loc_, axis_ = Ravelin::Vector3d(0, 0, 1);
+  RigidBodyPtr in_, out_;
+  int coord_ = -1;
+};
+class RevoluteJoint : public Joint { public: int type() const override { return B200MOBY_JOINT_REVOLUTE; } };
+class PrismaticJoint : public Joint { public: int type() const override { return B200MOBY_JOINT_PRISMATIC; } };
+typedef std::shared_ptr<Joint> JointPtr;
+
+// RCArticulatedBody (RCArticulatedBody.h:43; dynamics in Ravelin's RCArticulatedBodyd): fixed-base tree of one-DoF joints.
+// Generalized coordinates are the joint positions in joint order (get_coord_index); with several envs the accessors
+// refer to the env selected by TimeSteppingSimulator (env 0 outside controller callbacks).
+class RCArticulatedBody : public ControlledBody {
+ public:
+  enum ForwardDynamicsAlgorithmType { eFeatherstone, eCRB };
+  ForwardDynamicsAlgorithmType algorithm_type = eCRB;                      // RCArticulatedBody.cpp:60 default
+  void set_links_and_joints(const std::vector<RigidBodyPtr>& links, const std::vector<JointPtr>& joints);
+  const std::vector<RigidBodyPtr>& get_links() const { return links_; }
+  const std::vector<JointPtr>& get_joints() const { return joints_; }
+  void set_floating_base(bool f) { if (f) throw std::runtime_error("floating bases are outside the accelerated path (SURVEY.md 8f #4)"); }
+  bool is_floating_base() const { return false; }
+  std::list<RecurrentForcePtr>& get_recurrent_forces() { return forces_; }
+  unsigned num_generalized_coordinates(DynamicBodyd::GeneralizedCoordinateType) const { return (unsigned)joints_.size(); }
+  void get_generalized_coordinates_euler(Ravelin::VectorNd& q);
+  void get_generalized_velocity(DynamicBodyd::GeneralizedCoordinateType, Ravelin::VectorNd& qd);
+  void set_generalized_coordinates_euler(const Ravelin::VectorNd& q);
+  void set_generalized_velocity(DynamicBodyd::GeneralizedCoordinateType, const Ravelin::VectorNd& qd);
+
+ private:
+  friend class TimeSteppingSimulator;
+  std::vector<RigidBodyPtr> links_;        // link 0 = the base; parent before child
+  std::vector<JointPtr> joints_;           // joint k = inboard joint of link k + 1
+  std::vector<int> parent_;
+  std::list<RecurrentForcePtr> forces_;
+  TimeSteppingSimulator* sim_ = nullptr;
+  int first_body_ = -1;
+};
+typedef std::shared_ptr<RCArticulatedBody> RCArticulatedBodyPtr;
+
+// UnilateralConstraint (UnilateralConstraint.h): the contact fields the constraint callbacks and get_rigid_constraints() expose
+struct UnilateralConstraint {
+  enum UnilateralConstraintType { eNone, eContact, eLimit };
+  UnilateralConstraintType constraint_type = eContact;
+  Ravelin::Vector3d contact_point, contact_normal, contact_tan1, contact_tan2;
+  CollisionGeometryPtr contact_geom1, contact_geom2;
+  double signed_violation = 0.0;
+};
 
 class ContactParameters : public Base {           // defaults: ContactParameters.cpp:21-28
  public:
@@ -268,16 +344,50 @@ class TimeSteppingSimulator : public Base {
   ConstraintStabilization cstab;
   std::map<std::pair<BasePtr, BasePtr>, std::shared_ptr<ContactParameters> > contact_params;
   void (*post_step_callback_fn)(TimeSteppingSimulator*) = nullptr;           // Simulator.h:80
+  // ConstraintSimulator.h:51-68.  Both are called once per step() with the contacts of the state the step ended in (found
+  // again on the device and copied to the host: a slow path); the list is informational -- edits do not feed back into the
+  // solve, which has already run on the device.
+  void (*constraint_callback_fn)(std::vector<UnilateralConstraint>&, std::shared_ptr<void>) = nullptr;
+  void (*constraint_post_callback_fn)(const std::vector<UnilateralConstraint>&, std::shared_ptr<void>) = nullptr;
+  std::shared_ptr<void> constraint_callback_data, constraint_post_callback_data;
   void (*post_mini_step_callback_fn)(TimeSteppingSimulator*) = nullptr;      // ConstraintSimulator.h:55; see step()
   int impact_model = B200MOBY_MODEL_QP;                          // default build; B200MOBY_MODEL_AP == -DUSE_AP_MODEL
   int device = 0;
 
   void add_dynamic_body(ControlledBodyPtr body) {
     if (h_) throw std::logic_error("add_dynamic_body after the first step");
-    body->sim_ = this; body->index_ = (int)bodies_.size();
-    bodies_.push_back(body);
+    dyn_bodies_.push_back(body);
+    if (RigidBodyPtr rb = std::dynamic_pointer_cast<RigidBody>(body)) { rb->sim_ = this; rb->index_ = (int)bodies_.size(); bodies_.push_back(rb); return; }
+    RCArticulatedBodyPtr ab = std::dynamic_pointer_cast<RCArticulatedBody>(body);
+    if (!ab) throw std::invalid_argument("add_dynamic_body: RigidBody or RCArticulatedBody");
+    if (rc_) throw std::runtime_error("one RCArticulatedBody per simulator on the accelerated path");
+    if (ab->links_.empty()) throw std::logic_error("set_links_and_joints first");
+    rc_ = ab; ab->sim_ = this; ab->first_body_ = (int)bodies_.size();
+    for (const RigidBodyPtr& l : ab->links_) { l->sim_ = this; l->index_ = (int)bodies_.size(); bodies_.push_back(l); }
   }
-  const std::vector<ControlledBodyPtr>& get_dynamic_bodies() const { return bodies_; }
+  const std::vector<ControlledBodyPtr>& get_dynamic_bodies() const { return dyn_bodies_; }
+  // ConstraintSimulator::get_rigid_constraints: the contacts of env `env` at the current state
+  std::vector<UnilateralConstraint> get_rigid_constraints(int env = 0) {
+    if (!h_) compile();
+    const int cap = 64, ne = n_envs_, nb = (int)bodies_.size();
+    std::vector<int> count(ne), pair((size_t)cap * ne);
+    std::vector<double> pt((size_t)cap * 3 * ne), nr(pt.size()), t1(pt.size()), t2(pt.size()), dist((size_t)cap * ne);
+    b200_check(b200moby_find_contacts_host(h_, cap, count.data(), pt.data(), nr.data(), t1.data(), t2.data(), pair.data(), dist.data()), "b200moby_find_contacts_host");
+    std::vector<UnilateralConstraint> out;
+    for (int i = 0; i < count[env] && i < cap; i++) {
+      UnilateralConstraint c;
+      for (int k = 0; k < 3; k++) {
+        const size_t o = ((size_t)i * 3 + k) * ne + env;
+        c.contact_point[k] = pt[o]; c.contact_normal[k] = nr[o]; c.contact_tan1[k] = t1[o]; c.contact_tan2[k] = t2[o];
+      }
+      const int p = pair[(size_t)i * ne + env], b1 = p / nb, b2 = p % nb;
+      if (!bodies_[b1]->geometries.empty()) c.contact_geom1 = bodies_[b1]->geometries.front();
+      if (!bodies_[b2]->geometries.empty()) c.contact_geom2 = bodies_[b2]->geometries.front();
+      c.signed_violation = dist[(size_t)i * ne + env];
+      out.push_back(c);
+    }
+    return out;
+  }
   void add_contact_parameters(std::shared_ptr<ContactParameters> cp) { contact_params[cp->objects] = cp; }
 
   // --- batch extension: n independent copies of the scene; per-env perturbations through RigidBody::set_pose(p, env) ---
@@ -293,8 +403,14 @@ class TimeSteppingSimulator : public Base {
   // mini-step host callbacks would serialise the batch, so the reference's per-mini-step granularity is not kept.
   double step(double dt) {
     if (!h_) compile();
+    run_controllers(dt);
     b200_check(b200moby_step(h_, dt, 1, nullptr), "b200moby_step");
-    dirty_ = true;
+    dirty_ = true; jdirty_ = true;
+    if (constraint_callback_fn || constraint_post_callback_fn) {
+      std::vector<UnilateralConstraint> c = get_rigid_constraints(0);
+      if (constraint_callback_fn) constraint_callback_fn(c, constraint_callback_data);
+      if (constraint_post_callback_fn) constraint_post_callback_fn(c, constraint_post_callback_data);
+    }
     if (post_mini_step_callback_fn) post_mini_step_callback_fn(this);
     current_time += dt;                                           // every env advances by exactly dt per step()
     if (post_step_callback_fn) post_step_callback_fn(this);
@@ -303,8 +419,9 @@ class TimeSteppingSimulator : public Base {
   // n steps without returning to the host in between (no callbacks)
   void step_n(double dt, int n) {
     if (!h_) compile();
+    if (rc_ && rc_->controller) throw std::logic_error("step_n: a controller callback needs the host every step; use step()");
     b200_check(b200moby_step(h_, dt, n, nullptr), "b200moby_step");
-    dirty_ = true;
+    dirty_ = true; jdirty_ = true;
     current_time += dt * n;
   }
   b200moby_counters counters() {
@@ -342,6 +459,45 @@ class TimeSteppingSimulator : public Base {
   void push_state() {
     if (h_) { b200_check(b200moby_set_state(h_, q_.data(), v_.data()), "b200moby_set_state"); dirty_ = true; }
   }
+  // joint state of the articulated body, host copy [dof][env]
+  friend class RCArticulatedBody;
+  int ndof() const { return rc_ ? (int)rc_->joints_.size() : 0; }
+  void sync_joints() {
+    if (!rc_) return;
+    const size_t n = (size_t)ndof() * n_envs_;
+    if (jq_.size() != n) { jq_.assign(n, 0.0); jqd_.assign(n, 0.0); for (int k = 0; k < ndof(); k++) for (int e = 0; e < n_envs_; e++) { jq_[(size_t)k * n_envs_ + e] = rc_->joints_[k]->q[0]; jqd_[(size_t)k * n_envs_ + e] = rc_->joints_[k]->qd[0]; } }
+    if (h_ && jdirty_) { b200_check(b200moby_get_joint_state(h_, jq_.data(), jqd_.data()), "b200moby_get_joint_state"); jdirty_ = false; }
+    for (int k = 0; k < ndof(); k++) {
+      const double qk = jq_[(size_t)k * n_envs_ + cur_env_], qdk = jqd_[(size_t)k * n_envs_ + cur_env_];
+      rc_->joints_[k]->q[0] = qk + ctrl_dt_ * qdk; rc_->joints_[k]->qd[0] = qdk;
+    }
+  }
+  void push_joints() {
+    if (h_) { b200_check(b200moby_set_joint_state(h_, jq_.data(), jqd_.data()), "b200moby_set_joint_state"); dirty_ = true; }
+  }
+  // Simulator.cpp:339-348: the controller of every body, at current_time, before the forward dynamics.  One host call per
+  // env (the accessors of the body refer to that env during the call); its generalized forces go to the device.  The
+  // reference calls it inside the mini-step AFTER the position half of the semi-implicit Euler step
+  // (TimeSteppingSimulator.cpp:155-192): it sees q(t) + h qd(t) and qd(t).  The callback here runs before the device step,
+  // so the joint positions it reads are advanced by dt * qd on the host -- exact whenever the step is one mini-step.
+  void run_controllers(double dt) {
+    for (const RigidBodyPtr& b : bodies_) if (b->controller) throw std::runtime_error("controllers on free rigid bodies are outside the accelerated path");
+    if (!rc_ || !rc_->controller) return;
+    const int nd = ndof();
+    std::vector<double> tau((size_t)nd * n_envs_, 0.0);
+    Ravelin::VectorNd u;
+    ctrl_dt_ = dt;
+    for (int e = 0; e < n_envs_; e++) {
+      cur_env_ = e;
+      sync_joints();
+      u.assign(nd, 0.0);
+      Ravelin::VectorNd& r = rc_->controller(rc_, u, current_time, rc_->controller_arg);
+      for (int k = 0; k < nd && k < (int)r.size(); k++) tau[(size_t)k * n_envs_ + e] = r[k];
+    }
+    cur_env_ = 0; ctrl_dt_ = 0.0;
+    sync_joints();
+    b200_check(b200moby_set_joint_forces(h_, tau.data()), "b200moby_set_joint_forces");
+  }
   // object graph -> b200moby_scene_desc (what XMLReader::read + the simulator's containers hold in the reference)
   void compile() {
     if (cstab.eps != 1.4901161193847656e-08) throw std::runtime_error("cstab.eps: only the default sqrt(eps) (ConstraintStabilization.cpp:59) is on the accelerated path");
@@ -353,6 +509,8 @@ class TimeSteppingSimulator : public Base {
     std::vector<double> mu_c((size_t)nb * nb * ne, 0.0), mu_v(mu_c), eps(mu_c), comp(mu_c);
     b200moby_scene_desc d; memset(&d, 0, sizeof(d));
     d.gravity[0] = d.gravity[1] = d.gravity[2] = 0.0;
+    if (rc_) for (const RecurrentForcePtr& f : rc_->forces_)
+      if (const GravityForce* g = dynamic_cast<const GravityForce*>(f.get())) for (int k = 0; k < 3; k++) d.gravity[k] = g->gravity[k];
     for (int b = 0; b < nb; b++) {
       const RigidBody& rb = *bodies_[b];
       PrimitivePtr prim;
@@ -387,11 +545,54 @@ class TimeSteppingSimulator : public Base {
     d.contact_dist_thresh = contact_dist_thresh; d.min_step_size = min_step_size; d.min_step_size_env = nullptr;
     d.impact_model = impact_model;
     d.stabilization_max_iterations = cstab.max_iterations > 0x7fffffffu ? -1 : (int)cstab.max_iterations;   // UINT_MAX (the default) = no limit
+    // the articulated body: tree and joint frames from the links' construction poses and the joints' global location / axis
+    b200moby_rc_desc rd; memset(&rd, 0, sizeof(rd));
+    std::vector<int> parent, jtype; std::vector<double> axis, locp, locc, relq;
+    if (rc_) {
+      const int nl = (int)rc_->links_.size();
+      parent.assign(nl, 0); jtype.assign(nl, B200MOBY_JOINT_REVOLUTE); axis.assign(3 * nl, 0.0); locp.assign(3 * nl, 0.0); locc.assign(3 * nl, 0.0); relq.assign(4 * nl, 0.0);
+      relq[3] = 1.0; axis[2] = 1.0;
+      for (int i = 1; i < nl; i++) {
+        const Joint& J = *rc_->joints_[i - 1];
+        const Ravelin::Pose3d& Pi = rc_->links_[rc_->parent_[i]]->pose0_; const Ravelin::Pose3d& Po = rc_->links_[i]->pose0_;
+        parent[i] = rc_->parent_[i]; jtype[i] = J.type();
+        double Ri[9], Ro[9]; quat_to_R(Pi.q, Ri); quat_to_R(Po.q, Ro);
+        double an = std::sqrt(J.axis_[0] * J.axis_[0] + J.axis_[1] * J.axis_[1] + J.axis_[2] * J.axis_[2]);
+        if (!(an > 0.0)) throw std::runtime_error("joint '" + J.id + "': zero axis");
+        for (int r = 0; r < 3; r++) {
+          double a = 0, lp = 0, lc = 0;
+          for (int k = 0; k < 3; k++) { a += Ro[k * 3 + r] * J.axis_[k] / an; lp += Ri[k * 3 + r] * (J.loc_[k] - Pi.x[k]); lc += Ro[k * 3 + r] * (J.loc_[k] - Po.x[k]); }
+          axis[3 * i + r] = a; locp[3 * i + r] = lp; locc[3 * i + r] = lc;                 // R^T (.)
+        }
+        // conj(q_in) * q_out
+        const Ravelin::Quatd a(-Pi.q.x, -Pi.q.y, -Pi.q.z, Pi.q.w), b = Po.q;
+        relq[4 * i] = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y; relq[4 * i + 1] = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+        relq[4 * i + 2] = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w; relq[4 * i + 3] = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+      }
+      rd.n_links = nl; rd.first_body = rc_->first_body_;
+      rd.parent = parent.data(); rd.joint_type = jtype.data(); rd.joint_axis = axis.data(); rd.loc_parent = locp.data(); rd.loc_child = locc.data(); rd.rel_quat = relq.data();
+      rd.fdyn_algorithm = rc_->algorithm_type == RCArticulatedBody::eCRB ? B200MOBY_FDYN_CRB : B200MOBY_FDYN_FSAB;
+      d.rc = &rd;
+      for (int e = 0; e < ne; e++) enabled[(size_t)rc_->first_body_ * ne + e] = 0;           // the base is welded to the world
+    }
     b200_check(b200moby_create(&d, device, &h_), "b200moby_create");
     push_state();
+    if (rc_) { jdirty_ = false; sync_joints(); push_joints(); }
+  }
+  static void quat_to_R(const Ravelin::Quatd& q, double* R) {      // row-major
+    const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), x = q.x / n, y = q.y / n, z = q.z / n, w = q.w / n;
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
   }
 
-  std::vector<ControlledBodyPtr> bodies_;
+  std::vector<RigidBodyPtr> bodies_;            // every single body in scene order (the articulated body's links included)
+  std::vector<ControlledBodyPtr> dyn_bodies_;   // what add_dynamic_body received
+  RCArticulatedBodyPtr rc_;
+  std::vector<double> jq_, jqd_;
+  bool jdirty_ = false;
+  int cur_env_ = 0;
+  double ctrl_dt_ = 0.0;
   int n_envs_ = 1;
   b200moby_handle h_ = nullptr;
   std::vector<double> q_, v_;
@@ -432,6 +633,61 @@ inline Ravelin::SVelocityd RigidBody::get_velocity(int env) const {
   return out;
 }
 
+inline void RCArticulatedBody::set_links_and_joints(const std::vector<RigidBodyPtr>& links, const std::vector<JointPtr>& joints) {
+  if (links.size() != joints.size() + 1) throw std::invalid_argument("set_links_and_joints: a tree has one joint per non-base link");
+  // base = the link that is no joint's outboard; then breadth-first so that parents precede children
+  RigidBodyPtr base;
+  for (const RigidBodyPtr& l : links) { bool out = false; for (const JointPtr& j : joints) out = out || j->out_ == l; if (!out) { if (base) throw std::invalid_argument("two roots"); base = l; } }
+  if (!base) throw std::invalid_argument("no base link (kinematic loop?)");
+  links_.assign(1, base); joints_.clear(); parent_.assign(1, 0);
+  for (size_t i = 0; i < links_.size(); i++)
+    for (const JointPtr& j : joints)
+      if (j->in_ == links_[i]) { j->coord_ = (int)joints_.size(); joints_.push_back(j); links_.push_back(j->out_); parent_.push_back((int)i); }
+  if (links_.size() != links.size()) throw std::invalid_argument("set_links_and_joints: links not connected to the base");
+  for (const JointPtr& j : joints_) if (j->joint_id.empty()) j->joint_id = j->id;
+  for (const RigidBodyPtr& l : links_) if (l->body_id.empty()) l->body_id = l->id;
+}
+inline void RCArticulatedBody::get_generalized_coordinates_euler(Ravelin::VectorNd& q) {
+  if (sim_) sim_->sync_joints();
+  q.resize(joints_.size());
+  for (size_t k = 0; k < joints_.size(); k++) q[k] = joints_[k]->q[0];
+}
+inline void RCArticulatedBody::get_generalized_velocity(DynamicBodyd::GeneralizedCoordinateType, Ravelin::VectorNd& qd) {
+  if (sim_) sim_->sync_joints();
+  qd.resize(joints_.size());
+  for (size_t k = 0; k < joints_.size(); k++) qd[k] = joints_[k]->qd[0];
+}
+inline void RCArticulatedBody::set_generalized_coordinates_euler(const Ravelin::VectorNd& q) {
+  if (q.size() != joints_.size()) throw std::invalid_argument("set_generalized_coordinates_euler: one value per joint (fixed base)");
+  if (sim_) sim_->sync_joints();
+  for (size_t k = 0; k < joints_.size(); k++) joints_[k]->q[0] = q[k];
+  if (sim_ && !sim_->jq_.empty()) {                      // before the first step: every env starts from it; afterwards: the current env
+    for (size_t k = 0; k < joints_.size(); k++)
+      for (int e = 0; e < sim_->n_envs_; e++) if (!sim_->h_ || e == sim_->cur_env_) sim_->jq_[k * sim_->n_envs_ + e] = q[k];
+    sim_->push_joints();
+  }
+}
+inline void RCArticulatedBody::set_generalized_velocity(DynamicBodyd::GeneralizedCoordinateType, const Ravelin::VectorNd& qd) {
+  if (qd.size() != joints_.size()) throw std::invalid_argument("set_generalized_velocity: one value per joint (fixed base)");
+  if (sim_) sim_->sync_joints();
+  for (size_t k = 0; k < joints_.size(); k++) joints_[k]->qd[0] = qd[k];
+  if (sim_ && !sim_->jqd_.empty()) {
+    for (size_t k = 0; k < joints_.size(); k++)
+      for (int e = 0; e < sim_->n_envs_; e++) if (!sim_->h_ || e == sim_->cur_env_) sim_->jqd_[k * sim_->n_envs_ + e] = qd[k];
+    sim_->push_joints();
+  }
+}
+
+typedef TimeSteppingSimulator Simulator;      // example/sims-in-code/pendulum.cpp steps a plain Simulator: the same path without collision geometry
+
 }  // namespace Moby
+
+#ifndef B200MOBY_NO_RAVELIN_STANDINS
+namespace Ravelin {
+typedef Moby::Joint Jointd;
+typedef Moby::RigidBody RigidBodyd;
+typedef Moby::DynamicBodyd DynamicBodyd;
+}
+#endif
 
 #endif  // B200MOBY_HPP

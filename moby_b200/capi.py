@@ -67,7 +67,7 @@ SYMBOLS = [
     "b200moby_lcp_lemke_batched", "b200moby_lcp_fast_batched", "b200moby_lcp_lemke_regularized_batched",
     "b200moby_lcp_fast_regularized_batched", "b200moby_lcp_lemke_host", "b200moby_lcp_fast_host", "b200moby_lcp_solve_host",
     "b200moby_selftest_div",
-    "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_delassus_batched",
+    "b200moby_fwd_dyn_batched", "b200moby_find_contacts_batched", "b200moby_find_contacts_host", "b200moby_delassus_batched",
     "b200moby_set_joint_state", "b200moby_get_joint_state", "b200moby_set_joint_state_dev", "b200moby_get_joint_state_dev",
     "b200moby_set_joint_forces", "b200moby_rc_fwd_dyn_batched", "b200moby_rc_inertia_batched",
 ]
@@ -115,6 +115,7 @@ def lib():
     L.b200moby_selftest_div.argtypes = [C.c_int, dp, dp, dp, dp, vp]
     L.b200moby_fwd_dyn_batched.argtypes = [C.c_void_p, dp, dp, C.c_double, vp]
     L.b200moby_find_contacts_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, ip, dp, dp, dp, dp, ip, dp, vp]
+    L.b200moby_find_contacts_host.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, dp, dp, ip, dp]
     L.b200moby_delassus_batched.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, ip, vp]
     L.b200moby_set_joint_state.argtypes = [C.c_void_p, dp, dp]
     L.b200moby_get_joint_state.argtypes = [C.c_void_p, dp, dp]

@@ -863,6 +863,29 @@ b200moby_status b200moby_find_contacts_batched(b200moby_handle h, const double* 
   o.cap = cap; o.count = count; o.point = point; o.normal = normal; o.tan1 = tan1; o.tan2 = tan2; o.pair = pair; o.dist = dist;
   return run_stage(h, STAGE_CONTACTS, q, v, o, stream);
 }
+// Host-buffer form for callers without device memory of their own (the C++ facade's get_rigid_constraints): the contacts of
+// the simulator's CURRENT state.  Synchronous; temporary device buffers per call -- a documented slow path.
+b200moby_status b200moby_find_contacts_host(b200moby_handle h, int cap, int* count, double* point, double* normal, double* tan1, double* tan2,
+                                            int* pair, double* dist) {
+  if (!h || !count || !point || !normal || !tan1 || !tan2 || !pair || !dist || cap <= 0) return b2m_fail(B200MOBY_ERR_INVALID, "null output");
+  B2M_CUDA(cudaSetDevice(h->device));
+  const size_t ne = (size_t)h->n_envs, nv = (size_t)cap * 3 * ne;
+  int* d_i = nullptr; double* d_d = nullptr;
+  B2M_CUDA(cudaMalloc((void**)&d_i, sizeof(int) * (ne + (size_t)cap * ne)));
+  if (cudaMalloc((void**)&d_d, sizeof(double) * (4 * nv + (size_t)cap * ne)) != cudaSuccess) { cudaFree(d_i); return b2m_fail(B200MOBY_ERR_CUDA, "out of device memory"); }
+  b200moby_status st = b200moby_find_contacts_batched(h, h->P.q, h->P.v, cap, d_i, d_d, d_d + nv, d_d + 2 * nv, d_d + 3 * nv, d_i + ne, d_d + 4 * nv, nullptr);
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (st == B200MOBY_OK && ce == cudaSuccess) {
+    cudaMemcpy(count, d_i, sizeof(int) * ne, cudaMemcpyDeviceToHost); cudaMemcpy(pair, d_i + ne, sizeof(int) * cap * ne, cudaMemcpyDeviceToHost);
+    cudaMemcpy(point, d_d, sizeof(double) * nv, cudaMemcpyDeviceToHost); cudaMemcpy(normal, d_d + nv, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    cudaMemcpy(tan1, d_d + 2 * nv, sizeof(double) * nv, cudaMemcpyDeviceToHost); cudaMemcpy(tan2, d_d + 3 * nv, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    ce = cudaMemcpy(dist, d_d + 4 * nv, sizeof(double) * cap * ne, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_i); cudaFree(d_d);
+  if (st != B200MOBY_OK) return st;
+  if (ce != cudaSuccess) return b2m_fail(B200MOBY_ERR_CUDA, "%s", cudaGetErrorString(ce));
+  return B200MOBY_OK;
+}
 b200moby_status b200moby_delassus_batched(b200moby_handle h, const double* q, const double* v, int nmax, double* MM, double* qq,
                                           int* n, void* stream) {
   if (!MM || !qq || !n || nmax <= 0) return b2m_fail(B200MOBY_ERR_INVALID, "null output");

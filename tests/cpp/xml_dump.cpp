@@ -13,7 +13,7 @@ int main(int argc, char** argv) {
     printf("sim %s min_step_size %.17g contact_dist_thresh %.17g stabilization %u\n", sim->id.c_str(), sim->min_step_size, sim->contact_dist_thresh, sim->cstab.max_iterations);
     const auto& bodies = sim->get_dynamic_bodies();
     for (size_t i = 0; i < bodies.size(); i++) {
-      Moby::RigidBody& rb = *bodies[i];
+      Moby::RigidBody& rb = *std::dynamic_pointer_cast<Moby::RigidBody>(bodies[i]);     // as Moby programs do (coldet-plugin.cpp:30-35)
       Moby::PrimitivePtr p = rb.geometries.empty() ? Moby::PrimitivePtr() : rb.geometries.front()->get_geometry();
       const Ravelin::Pose3d ps = rb.get_pose(0);
       const Ravelin::SVelocityd v = rb.get_velocity(0);

@@ -115,3 +115,87 @@ def test_cpp_xml_reader_inline_scene_and_errors(sitting_box, tmp_path):
     broken.write_text("<XML><MOBY><Box id='b' xlen='1'></MOBY></XML>")
     rc, out, err = _dump(sitting_box, str(broken))
     assert rc == 1 and "XML parse error" in err
+
+
+# ---- articulated bodies, controller callback, constraint callback, extern "C" init plugin ----
+def test_pendulum_and_plugin_driver_build_and_refuse_without_gpu(sitting_box):
+    """example/sims-in-code/pendulum.cpp and a controller plugin shaped like example/ur10/controller.cpp compile against the
+    facade; without a GPU both programs stop at b200moby_create."""
+    import torch
+    for exe in ("pendulum", "plugin_driver", "libctrl_plugin.so"):
+        assert os.path.exists(os.path.join(CPP, exe)), exe
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([os.path.join(CPP, "pendulum"), "10", "5"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+    r = subprocess.run([os.path.join(CPP, "plugin_driver"), os.path.join(CPP, "libctrl_plugin.so"), "10", "5"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def _arm2_scene(n_envs=1, controller=True):
+    """The scene tests/cpp/plugin_driver.cpp builds through the facade, built with the Python mirror."""
+    from moby_b200 import scenes
+    s = scenes.SceneBatch(n_envs, 5)
+    s.gravity = (0.0, 0.0, -9.81)
+    m, dx, dy, dz = 1.0, 0.5, 0.05, 0.05
+    for b, cx in enumerate((0.0, 0.25, 0.75)):
+        s.mass[b, :] = m
+        s.inertia[b, 0, :], s.inertia[b, 1, :], s.inertia[b, 2, :] = m * (dy * dy + dz * dz) / 12, m * (dx * dx + dz * dz) / 12, m * (dx * dx + dy * dy) / 12
+        s.q[b, 0, :], s.q[b, 2, :] = cx, 1.0
+    rc = scenes.ArticulatedBody(s, 0, 3, fdyn=scenes.FDYN_CRB)
+    rc.set_joint(1, 0, scenes.JOINT_REVOLUTE, (0, 1, 0), (0.0, 0, 0), (-0.25, 0, 0))
+    rc.set_joint(2, 1, scenes.JOINT_REVOLUTE, (0, 1, 0), (0.25, 0, 0), (-0.25, 0, 0))
+    if controller:
+        rc.set_controller(kp=[30.0, 10.0], kv=[6.0, 2.0], amp=[0.5, 0.3], freq=[1.0, 2.0])
+    rc.jqd[0, :], rc.jqd[1, :] = 0.5, 0.3
+    s.set_sphere(3, 0.1, mass=1.0)
+    s.q[3, 0, :], s.q[3, 2, :] = 2.0, 0.1
+    h = np.sqrt(0.5)
+    s.set_plane(4, quat=(h, 0, 0, h))
+    for i in range(5):
+        for j in range(i + 1, 5):
+            s.set_contact(i, j)
+    return s
+
+
+@pytest.mark.gpu
+def test_plugin_controller_matches_builtin_pd_law(sitting_box):
+    """The plugin's controller (host callback every step -> b200moby_set_joint_forces) against the same PD law evaluated on
+    the device (rc.set_controller): joint trajectories agree to 1e-9; the constraint callback saw the ball's contact every step."""
+    from moby_b200 import TimeSteppingSimulator
+    r = subprocess.run([os.path.join(CPP, "plugin_driver"), os.path.join(CPP, "libctrl_plugin.so"), "300", "100"], capture_output=True, text=True, check=True)
+    rows = [[float(x) for x in l.split()] for l in r.stdout.splitlines() if l and not l.startswith("#")]
+    meta = [l.split() for l in r.stdout.splitlines() if l.startswith("#")][0]
+    assert int(meta[2]) == 300 and int(meta[4]) >= 1
+    sim = TimeSteppingSimulator(_arm2_scene())
+    for k, row in enumerate(rows):
+        sim.step(1e-3, 100)
+        jq, jqd = sim.get_joint_state()
+        q, _ = sim.get_state()
+        got = np.array([jq[0, 0], jq[1, 0], jqd[0, 0], jqd[1, 0], q[3, 2, 0]])
+        assert abs(row[0] - (k + 1) * 0.1) < 1e-12
+        assert np.allclose(got, row[1:6], rtol=0, atol=1e-9), (got, row[1:6])
+    assert abs(rows[-1][1]) > 1e-3            # the arm did move
+
+
+@pytest.mark.gpu
+def test_facade_pendulum_matches_python_mirror(sitting_box):
+    from moby_b200 import TimeSteppingSimulator, scenes
+    r = subprocess.run([os.path.join(CPP, "pendulum"), "400", "200", "2"], capture_output=True, text=True, check=True)
+    rows = [[float(x) for x in l.split()] for l in r.stdout.splitlines() if l]
+    s = scenes.SceneBatch(1, 2)
+    s.gravity = (0.0, 0.0, -9.8)
+    s.mass[:, :] = 1.0
+    s.inertia[0, :, :] = 1.0 * (0.01 + 0.01) / 12
+    s.inertia[1, 0, :] = s.inertia[1, 2, :] = (3 * 0.025 ** 2 + 1.0) / 12.0
+    s.inertia[1, 1, :] = 0.5 * 0.025 ** 2
+    s.q[1, 1, :] = -0.5
+    rc = scenes.ArticulatedBody(s, 0, 2, fdyn=scenes.FDYN_CRB)
+    rc.set_joint(1, 0, scenes.JOINT_REVOLUTE, (1, 0, 0), (0, 0, 0), (0, 0.5, 0))
+    s.stabilization_max_iterations = -1
+    sim = TimeSteppingSimulator(s)
+    for row in rows:
+        sim.step(1e-3, 200)
+        q, _ = sim.get_state()
+        jq, jqd = sim.get_joint_state()
+        assert np.allclose(q[1, :, 0], row[1:8], rtol=0, atol=1e-12) and abs(jq[0, 0] - row[8]) < 1e-12 and abs(jqd[0, 0] - row[9]) < 1e-12
