@@ -22,6 +22,8 @@ import time
 
 import numpy as np
 
+# one hardware queue per stream of a step (main, hard queue, one per LCP class; twice that for the mix): set before CUDA starts
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT]
 
@@ -231,7 +233,7 @@ def _secondary(args, W, scenes, rank_seed, local_rank, flush, stream):
         t = _device_timed(sim, DT, steps, 3, flush, stream)
         out["stabilization_off"] = {"value": ne * steps / t, "unit": "env-steps/s", "ms_per_step": 1e3 * t / steps, "steps": steps, "n_gpus": 1,
                                     "note": "same workload and seed on rank 0's GPU with constraint-stabilization-max-iterations=0 (the configuration of round 1's numbers)"}
-        del sim
+        sim.close()
     if not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_api as O
@@ -632,6 +634,9 @@ def main():
                                   "flops": "SURVEY 8(d): sum pivots*2n(n+1) + F_delassus + F_apply per solve + F_fd + F_narrow per mini-step, all from recorded counts"}},
         }
         if not args.no_secondary and len(names) == 1:
+            torch.cuda.synchronize()
+            for ps in part_sims:
+                ps.close()                   # one live simulator per GPU at a time: the secondary runs get the same schedule as the headline
             out["secondary"] = _secondary(args, W, scenes, 0xB200 + rank, local_rank, flush, stream)
         out["stabilization"] = {"iterations_per_env_step": r_cnt["stab_iterations"] / max(r_cnt["env_steps"], 1),
                                 "lcp_solves_per_env_step": r_cnt["stab_lcp_solves"] / max(r_cnt["env_steps"], 1),

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
         } else if (finished) e = -3;
         else {
           long long t_now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-          if (t_now - t_begin > 30000000ll) e = -3;        // 30 ms: never spin on a producer that cannot run
+          if (t_now - t_begin > 4000000ll) e = -3;         // 4 ms: never spin for long on a producer that cannot run
         }
       }
       e = __shfl_sync(0xffffffffu, e, 0);

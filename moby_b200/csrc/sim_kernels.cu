@@ -2,6 +2,7 @@
 // b200moby_step replaces TimeSteppingSimulator::step (Moby src/TimeSteppingSimulator.cpp:52-111) for a batch of
 // independent envs: one warp per env, the whole mini-step loop (narrowphase, conservative advancement, forward
 // dynamics, assembly, LCP solve, impulses) runs out of shared memory; HBM sees the state and the warm start only.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +26,11 @@ struct ClassPlan {
   size_t gstride = 0;
 };
 
+// live handles per device: the hard-queue launch waits for work from launches on other streams (k_impact_warp.cu), which is only
+// safe while no other handle's launches can sit between them in a hardware queue (with more streams than
+// CUDA_DEVICE_MAX_CONNECTIONS, streams share queues and a launch can be stuck behind another handle's blocked one)
+static std::atomic<int> g_live_handles[64];
+
 struct b200moby_sim {
   int device = 0;
   int n_envs = 0, nb = 0, cmax = 0, nmax = 0, npmax = 0;
@@ -44,7 +50,7 @@ struct b200moby_sim {
   // one step captured as a CUDA graph (b200moby_step): ~25 launches, memsets and the stream fork / join of a step become
   // one cudaGraphLaunch.  Captured on an internal stream; re-captured when dt or anything in SimParams changes.
   cudaGraphExec_t graph_exec = nullptr; cudaStream_t graph_stream = nullptr;
-  SimParams graph_P; double graph_dt = 0.0; long long graph_launches = 0; bool graph_on = true; int graph_captures = 0;
+  SimParams graph_P; double graph_dt = 0.0; bool graph_feed = false; long long graph_launches = 0; bool graph_on = true; int graph_captures = 0;
   int* feed_ctr = nullptr;   // [B2M_ROUNDS_MAX] class launches completed in the round (k_impact_warp.cu: the hard-queue launch takes their stragglers)
   bool all_thread_classes = false;
   LadderPool pool;           // task pool of the Lemke ladder (lcp_device.cuh) for the hard-queue / straggler launches; ctl == nullptr: off
@@ -398,6 +404,11 @@ b200moby_status launch_stabilize(b200moby_sim* h, cudaStream_t s) {
   return timed_launch(h, 4 + ncls, b2m_k_stabilize_warp(), dim3(h->stab_grid), dim3(128), a, 0, s);
 }
 
+bool launch_feeds(const b200moby_sim* h) {
+  return h->feed_ctr && h->concurrent && h->classes.size() > 1 && h->all_thread_classes && h->straggler.threads == 32 && h->P.hard_cost > 0 &&
+         g_live_handles[h->device & 63].load() == 1;
+}
+
 // One TimeSteppingSimulator::step for every env: advance, then per round the impact classes, stragglers and the
 // next advance; the finish kernel takes whatever the rounds left over.  All launches are asynchronous on `s`.
 b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
@@ -407,7 +418,7 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
   B2M_CUDA(cudaMemsetAsync(P.qctl, 0, sizeof(int) * 2 * B2M_ROUNDS_MAX * (B2M_SLOTS + 1), s));
   // the hard-queue launch also takes the stragglers of the classes running next to it (k_impact_warp.cu): only when every
   // class is a thread-per-env launch (no shared memory: they are sure to be resident beside it) on concurrent streams
-  const bool feed = h->feed_ctr && h->concurrent && h->classes.size() > 1 && h->all_thread_classes && h->straggler.threads == 32 && P.hard_cost > 0;
+  const bool feed = launch_feeds(h);
   if (feed) {
     B2M_CUDA(cudaMemsetAsync(h->feed_ctr, 0, sizeof(int) * B2M_ROUNDS_MAX, s));
     for (int r = 0; r < h->rounds; r++) B2M_CUDA(cudaMemsetAsync(q_list(P, r, B2M_SLOT_STRAGGLER), 0xff, sizeof(int) * h->n_envs, s));
@@ -476,6 +487,7 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   int cmax = 0, nmax = 0, npmax = 0;
   if (const char* err = b2m_scene_bounds(d, cmax, nmax, npmax)) return b2m_fail(B200MOBY_ERR_INVALID, "%s", err);
   b200moby_sim* h = new b200moby_sim;
+  g_live_handles[device & 63]++;
   h->device = device; h->n_envs = ne; h->nb = nb; h->cmax = std::max(cmax, 1); h->nmax = std::max(nmax, 1); h->npmax = std::max(npmax, 1);
   SimParams& P = h->P;
   memset(&P, 0, sizeof(P));
@@ -566,6 +578,7 @@ b200moby_status b200moby_destroy(b200moby_handle h) {
   for (auto& pe : h->kev_pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto& pe : h->kev_free) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (void* p : h->allocs) cudaFree(p);
+  g_live_handles[h->device & 63]--;
   delete h;
   return B200MOBY_OK;
 }
@@ -689,7 +702,7 @@ b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* s
     return B200MOBY_OK;
   }
   if (h->graph_on && !h->ktiming) {
-    if (!h->graph_exec || h->graph_dt != dt || memcmp(&h->graph_P, &h->P, sizeof(SimParams)) != 0) {
+    if (!h->graph_exec || h->graph_dt != dt || h->graph_feed != launch_feeds(h) || memcmp(&h->graph_P, &h->P, sizeof(SimParams)) != 0) {
       if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
       if (!h->graph_stream) B2M_CUDA(cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
       const long long l0 = h->launches;
@@ -704,7 +717,7 @@ b200moby_status b200moby_step(b200moby_handle h, double dt, int n_steps, void* s
         const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) { cudaGetLastError(); h->graph_exec = nullptr; h->graph_on = false; }
-        else { h->graph_P = h->P; h->graph_dt = dt; h->graph_captures++; }
+        else { h->graph_P = h->P; h->graph_dt = dt; h->graph_feed = launch_feeds(h); h->graph_captures++; }
       }
     }
     if (h->graph_exec) {

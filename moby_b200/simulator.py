@@ -28,6 +28,10 @@ class TimeSteppingSimulator:
             self.set_joint_state(self.rc.jq, self.rc.jqd)
         self.steps_taken = 0
 
+    def close(self):
+        """Destroy the device-side simulator now (b200moby_destroy); the object is unusable afterwards."""
+        self.__del__()
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
