@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
 #include "friction_table.h"
 #include "host_util.h"
 #include "sim_kernel_util.cuh"
@@ -404,6 +405,10 @@ b200moby_status launch_stabilize(b200moby_sim* h, cudaStream_t s) {
   return timed_launch(h, 4 + ncls, b2m_k_stabilize_warp(), dim3(h->stab_grid), dim3(128), a, 0, s);
 }
 
+// NVTX range per phase of a step (the equivalent of the reference's FILE_LOG sections), on the enqueuing
+// host thread; with graphs the ranges mark the capture, plain launches (B200MOBY_GRAPH=0) mark every step
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+
 bool launch_feeds(const b200moby_sim* h) {
   return h->feed_ctr && h->concurrent && h->classes.size() > 1 && h->all_thread_classes && h->straggler.threads == 32 && h->P.hard_cost > 0 &&
          g_live_handles[h->device & 63].load() == 1;
@@ -423,7 +428,9 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
     B2M_CUDA(cudaMemsetAsync(h->feed_ctr, 0, sizeof(int) * B2M_ROUNDS_MAX, s));
     for (int r = 0; r < h->rounds; r++) B2M_CUDA(cudaMemsetAsync(q_list(P, r, B2M_SLOT_STRAGGLER), 0xff, sizeof(int) * h->n_envs, s));
   }
+  NvtxRange step_range("b200moby step");
   for (int r = 0; r < h->rounds; r++) {
+    NvtxRange round_range(r == 0 ? "round 0: advance + impact" : "round n: advance + impact");
     { SimParams Pa = P; Pa.kslot = 0;
       void* a[] = {&Pa, &dt, &r, &h->adv_wpb};
       if (h->adv_thread >= 0) {
@@ -468,7 +475,8 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
       Pf.gscratch = h->finblock.gscratch; Pf.gstride = h->finblock.gstride;
       if ((st = timed_launch(h, 2 + ncls, b2m_k_finish_block256(), dim3(h->finblock.grid), dim3(256), a, h->finblock.shmem, s)) != B200MOBY_OK) return st;
     } else if ((st = timed_launch(h, 2 + ncls, b2m_k_finish(), dim3(h->fin_grid), dim3(32), a, h->shmem, s)) != B200MOBY_OK) return st; }
-  if ((st = launch_stabilize(h, s)) != B200MOBY_OK) return st;
+  { NvtxRange stab_range("constraint stabilization");
+    if ((st = launch_stabilize(h, s)) != B200MOBY_OK) return st; }
   B2M_CUDA(cudaGetLastError());
   return B200MOBY_OK;
 }
