@@ -21,9 +21,13 @@ __device__ __forceinline__ void stabilize_env(const G& g, const SimParams& P, in
   g.sync();
 }
 
-// P.nmax == P.cmax here (the host passes the stabilization view of the parameters)
+// P.nmax == P.cmax here (the host passes the stabilization view of the parameters).
+// Two launches per step.  mode 0 (select): every env evaluates its pairwise distances once and, if some pair is closer than
+// eps, puts itself on `queue`.  mode 1 (process): the queued envs are stabilized, 32 per warp.  With one launch over all
+// envs a warp of 32 consecutive envs holds on average five that need the LCP and the line search (17 % of configs[1]) and
+// runs as long as the slowest of them: compaction cuts the warps that walk the expensive path sixfold (2.2 -> ~1 ms per step).
 template <int ND, int NI>
-__global__ void __launch_bounds__(128) stabilize_thread_kernel(SimParams P) {
+__global__ void __launch_bounds__(128) stabilize_thread_kernel(SimParams P, int mode, int* queue, int* count) {
   double wd[ND];
   int wi[NI];
   const EnvDims D = env_dims(P);
@@ -34,7 +38,15 @@ __global__ void __launch_bounds__(128) stabilize_thread_kernel(SimParams P) {
   unsigned long long lc[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
   unsigned long long envs = 0;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_envs; e += gridDim.x * blockDim.x) { stabilize_env(g, P, e, m, s, lc); envs++; }
+  if (mode == 0) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_envs; e += gridDim.x * blockDim.x) {
+      env_load(g, P, e, m);
+      if (stab_eval(g, m, s.uC) < P.stab_eps) queue[atomicAdd(count, 1)] = e;          // the test env_stabilize starts with (:187-197)
+    }
+    return;
+  }
+  const int n = queue ? *count : P.n_envs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { stabilize_env(g, P, queue ? queue[i] : i, m, s, lc); envs++; }
   for (int k = 0; k < CNT_COUNT; k++) {
     unsigned long long v = lc[k];
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o); v = (k == CNT_MAX_N) ? (u > v ? u : v) : v + u; }
@@ -45,7 +57,7 @@ __global__ void __launch_bounds__(128) stabilize_thread_kernel(SimParams P) {
 }
 
 // warp per env, working set in the warp's slice of P.gscratch (gstride doubles per warp; ints follow the doubles)
-__global__ void __launch_bounds__(128) stabilize_warp_kernel(SimParams P, size_t nd_env, size_t nd_all) {
+__global__ void __launch_bounds__(128) stabilize_warp_kernel(SimParams P, size_t nd_env, size_t nd_all, int* queue, int* count) {
   const EnvDims D = env_dims(P);
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   double* base = P.gscratch + (size_t)w * P.gstride;
@@ -57,7 +69,8 @@ __global__ void __launch_bounds__(128) stabilize_warp_kernel(SimParams P, size_t
   unsigned long long lc[CNT_COUNT];
   for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
   unsigned long long envs = 0;
-  for (int e = w; e < P.n_envs; e += nw) { stabilize_env(g, P, e, m, s, lc); envs++; }
+  const int n = queue ? *count : P.n_envs;                       // queue: the envs the select launch found (thread-per-env select, warp-per-env work)
+  for (int i = w; i < n; i += nw) { stabilize_env(g, P, queue ? queue[i] : i, m, s, lc); envs++; }
   if (g.tid == 0) commit_counters(P, lc, envs);
 }
 

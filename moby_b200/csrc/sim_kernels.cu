@@ -52,6 +52,7 @@ struct b200moby_sim {
   // one cudaGraphLaunch.  Captured on an internal stream; re-captured when dt or anything in SimParams changes.
   cudaGraphExec_t graph_exec = nullptr; cudaStream_t graph_stream = nullptr;
   SimParams graph_P; double graph_dt = 0.0; bool graph_feed = false; long long graph_launches = 0; bool graph_on = true; int graph_captures = 0;
+  int* stab_queue = nullptr; // [n_envs + 1] envs selected for stabilization this step, then their count (k_stabilize.cu)
   int* feed_ctr = nullptr;   // [B2M_ROUNDS_MAX] class launches completed in the round (k_impact_warp.cu: the hard-queue launch takes their stragglers)
   bool all_thread_classes = false;
   LadderPool pool;           // task pool of the Lemke ladder (lcp_device.cuh) for the hard-queue / straggler launches; ctl == nullptr: off
@@ -351,6 +352,16 @@ b200moby_status plan_launch(b200moby_sim* h) {
       B2M_CUDA(cudaMalloc((void**)&h->stab_scratch, h->stab_stride * (size_t)h->stab_grid * 4 * sizeof(double)));
       h->allocs.push_back(h->stab_scratch);
     }
+    if (h->stab_variant >= 0 && env_int("B200MOBY_STAB_SELECT", 1) != 0) {
+      b200moby_status s4;
+      if ((s4 = dev_zero(h, (size_t)ne + 1, &h->stab_queue)) != B200MOBY_OK) return s4;
+      if (env_int("B200MOBY_STAB_PROCESS_WARP", 0) != 0) {
+        h->stab_grid = std::max(1, std::min((ne + 3) / 4, sms * 8));
+        h->stab_stride = h->stab_nd_all + (ni + xi + 1) / 2;
+        B2M_CUDA(cudaMalloc((void**)&h->stab_scratch, h->stab_stride * (size_t)h->stab_grid * 4 * sizeof(double)));
+        h->allocs.push_back(h->stab_scratch);
+      }
+    }
   }
   return B200MOBY_OK;
 }
@@ -396,12 +407,27 @@ b200moby_status launch_stabilize(b200moby_sim* h, cudaStream_t s) {
   const int ncls = (int)h->classes.size();
   SimParams Ps = h->P; Ps.nmax = Ps.cmax; Ps.kslot = 4 + ncls;
   if (h->stab_variant >= 0) {
-    void* a[] = {&Ps};
     const int blocks = std::max(1, std::min((h->n_envs + 127) / 128, h->sms * 16));
+    int mode = 1; int* queue = nullptr; int* count = nullptr;
+    if (h->stab_queue) {                                     // select, then stabilize the selected envs only (k_stabilize.cu)
+      mode = 0; queue = h->stab_queue; count = h->stab_queue + h->n_envs;
+      B2M_CUDA(cudaMemsetAsync(count, 0, sizeof(int), s));
+      void* a0[] = {&Ps, &mode, &queue, &count};
+      b200moby_status st = timed_launch(h, 4 + ncls, b2m_k_stabilize_thread(h->stab_variant), dim3(blocks), dim3(128), a0, 0, s);
+      if (st != B200MOBY_OK) return st;
+      mode = 1;
+    }
+    if (queue && h->stab_scratch) {                          // selected envs by warps (B200MOBY_STAB_PROCESS_WARP=1)
+      Ps.gscratch = h->stab_scratch; Ps.gstride = h->stab_stride;
+      void* aw[] = {&Ps, &h->stab_nd_env, &h->stab_nd_all, &queue, &count};
+      return timed_launch(h, 4 + ncls, b2m_k_stabilize_warp(), dim3(h->stab_grid), dim3(128), aw, 0, s);
+    }
+    void* a[] = {&Ps, &mode, &queue, &count};
     return timed_launch(h, 4 + ncls, b2m_k_stabilize_thread(h->stab_variant), dim3(blocks), dim3(128), a, 0, s);
   }
   Ps.gscratch = h->stab_scratch; Ps.gstride = h->stab_stride;
-  void* a[] = {&Ps, &h->stab_nd_env, &h->stab_nd_all};
+  int* queue = nullptr; int* count = nullptr;
+  void* a[] = {&Ps, &h->stab_nd_env, &h->stab_nd_all, &queue, &count};
   return timed_launch(h, 4 + ncls, b2m_k_stabilize_warp(), dim3(h->stab_grid), dim3(128), a, 0, s);
 }
 

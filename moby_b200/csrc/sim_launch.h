@@ -25,5 +25,5 @@ const void* b2m_k_rc_refresh();           // (SimParams P)
 #define B2M_STAB_NI0 192
 #define B2M_STAB_ND1 3072
 #define B2M_STAB_NI1 512
-const void* b2m_k_stabilize_thread(int variant);   // (SimParams P) with P.nmax = P.cmax
-const void* b2m_k_stabilize_warp();       // (SimParams P, size_t env_doubles, size_t all_doubles): working set in P.gscratch
+const void* b2m_k_stabilize_thread(int variant);   // (SimParams P, int mode, int* queue, int* count) with P.nmax = P.cmax; mode 0: select envs into queue, 1: stabilize the queued envs (queue == nullptr: all)
+const void* b2m_k_stabilize_warp();               // (SimParams P, size_t nd_env, size_t nd_all, int* queue, int* count): queue == nullptr: every env
