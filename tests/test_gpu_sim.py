@@ -297,10 +297,11 @@ def test_ladder_task_pool_gives_the_sequential_results(torch_cuda):
     assert res[0][0]["lemke_calls"] > res[0][0]["lcp_solves"] // 50 and res[0][0]["lemke_calls"] > 20000       # ladders beyond rung 0 were run
 
 
-@pytest.mark.parametrize("knob", ["B200MOBY_GRAPH", "B200MOBY_FEED"])
+@pytest.mark.parametrize("knob", ["B200MOBY_GRAPH", "B200MOBY_FEED", "B200MOBY_STAB_SELECT"])
 def test_schedule_knobs_do_not_change_results(torch_cuda, knob):
-    """One step as a CUDA graph (re-captured when dt changes) against plain launches, and the hard-queue launch taking the
-    classes' stragglers as they arrive against a straggler launch of its own: scheduling only -- states and every counter equal."""
+    """One step as a CUDA graph (re-captured when dt changes) against plain launches; the hard-queue launch taking the
+    classes' stragglers as they arrive against a straggler launch of its own; stabilization over the selected envs against
+    over all of them: none may change a state or a counter."""
     import os
     from moby_b200 import TimeSteppingSimulator
     sc = scenes.small_lcp_batch(8192, seed=0xB200)
