@@ -193,6 +193,12 @@ class PlanePrimitive : public Primitive {         // half-space y <= 0 of the bo
  public:
   PlanePrimitive() { shape = B200MOBY_SHAPE_PLANE; }
 };
+// The rimless wheel of example/rimless-wheel: in the reference a CollisionGeometry WITHOUT a primitive whose distance and
+// contacts come from the collision-detection plugin (coldet-plugin.cpp:86-137,222-310; params.h:4-6); here a shape of its own.
+class RimlessWheelPrimitive : public Primitive {
+ public:
+  RimlessWheelPrimitive(double R = 1.0, double W = 0.0, unsigned n_spokes = 6) { shape = B200MOBY_SHAPE_WHEEL; dims[0] = R; dims[1] = W; dims[2] = (double)n_spokes; }
+};
 
 class CollisionGeometry : public Base {
  public:
@@ -389,6 +395,7 @@ class TimeSteppingSimulator : public Base {
     return out;
   }
   void add_contact_parameters(std::shared_ptr<ContactParameters> cp) { contact_params[cp->objects] = cp; }
+  std::vector<std::pair<BasePtr, BasePtr> > disabled_pairs;       // <DisabledPair> (ConstraintSimulator.cpp:585-611): never checked
 
   // --- batch extension: n independent copies of the scene; per-env perturbations through RigidBody::set_pose(p, env) ---
   void replicate(int n_envs) {
@@ -534,6 +541,8 @@ class TimeSteppingSimulator : public Base {
           if ((a == bodies_[i].get() && b == bodies_[j].get()) || (a == bodies_[j].get() && b == bodies_[i].get())) cp = *kv.second;
         }
         if (cp.NK < 4) cp.NK = 4;                                   // ContactParameters.cpp:132-136
+        for (const auto& dp : disabled_pairs)
+          if ((dp.first.get() == bodies_[i].get() && dp.second.get() == bodies_[j].get()) || (dp.first.get() == bodies_[j].get() && dp.second.get() == bodies_[i].get())) cp.NK = 0;
         for (int e = 0; e < ne; e++) {
           const size_t o = ((size_t)i * nb + j) * ne + e;
           mu_c[o] = cp.mu_coulomb; mu_v[o] = cp.mu_viscous; eps[o] = cp.epsilon; comp[o] = cp.compliance; NK[o] = (int)cp.NK;

@@ -155,6 +155,15 @@ class XMLReader {
         for (int k = 0; k < 3; k++) g->gravity[k] = a[k];
         id_map[g->id] = g;
       } }
+    // collision-detection plugin of the simulator (XMLReader.cpp:334-388, ConstraintSimulator.cpp:562-572): only the one the
+    // accelerated path has a built-in equivalent for -- the rimless wheel's, which finds its bodies by the ids WHEEL / GROUND
+    std::string coldet_plugin;
+    { std::vector<const XMLTree*> sv; moby.find_all("TimeSteppingSimulator", sv);
+      if (sv.size() == 1 && sv[0]->get_attrib("collision-detection-plugin")) {
+        std::vector<const XMLTree*> pv; moby.find_all("CollisionDetectionPlugin", pv);
+        for (const XMLTree* pn : pv) if (pn->get_attrib("id") && *pn->get_attrib("id") == *sv[0]->get_attrib("collision-detection-plugin") && pn->get_attrib("plugin")) coldet_plugin = *pn->get_attrib("plugin");
+        if (coldet_plugin != "librimless-wheel-coldet-plugin.so") throw std::runtime_error("collision-detection-plugin '" + coldet_plugin + "': no built-in equivalent on the accelerated path");
+      } }
     // rigid bodies
     { std::vector<const XMLTree*> v; moby.find_all("RigidBody", v);
       for (const XMLTree* n : v) {
@@ -170,6 +179,7 @@ class XMLReader {
           for (const char* k : {"relative-origin", "relative-rpy", "relative-quat"}) if (cg[0]->get_attrib(k)) throw std::runtime_error("body '" + rb->id + "': CollisionGeometry offsets are not supported");
           const std::string pid = cg[0]->get_attrib("primitive-id") ? *cg[0]->get_attrib("primitive-id") : "";
           PrimitivePtr p = std::dynamic_pointer_cast<Primitive>(lookup(id_map, pid));
+          if (!p && pid.empty() && !coldet_plugin.empty() && rb->id == "WHEEL") { p.reset(new RimlessWheelPrimitive(1.0, 0.0, 6)); prim_pose[pid] = Ravelin::Pose3d(); }   // params.h:4-6
           if (!p) throw std::runtime_error("body '" + rb->id + "': primitive '" + pid + "' is not a Box / Sphere / Plane of this file");
           const Ravelin::Pose3d& pp = prim_pose[pid];
           if (p->shape == B200MOBY_SHAPE_PLANE) {
@@ -190,9 +200,15 @@ class XMLReader {
           if (!p || p->shape == B200MOBY_SHAPE_PLANE) throw std::runtime_error("body '" + rb->id + "': InertiaFromPrimitive needs a Box or Sphere of this file");
           if (p->get_mass() <= 0.0 && !has_mass_spec(moby, pid)) p->set_density(1.0);
           J = p->get_inertia();
-        } else if (enabled) throw std::runtime_error("body '" + rb->id + "': an enabled body needs InertiaFromPrimitive (explicit inertia matrices are not read yet)");
+        } else if (enabled && !(n->get_attrib("inertia") && n->get_attrib("mass"))) throw std::runtime_error("body '" + rb->id + "': an enabled body needs InertiaFromPrimitive or both mass and inertia attributes");
         if (n->get_attrib("mass")) J.m = num(*n, "mass", J.m);                     // RigidBody.cpp:182-188: J.m only
-        if (n->get_attrib("inertia")) throw std::runtime_error("body '" + rb->id + "': explicit inertia matrices are not read yet");
+        if (n->get_attrib("inertia")) {                                            // RigidBody.cpp:191-197: rows separated by ';'
+          std::string t = *n->get_attrib("inertia");
+          for (char& c : t) if (c == ';') c = ' ';
+          const std::vector<double> a = numbers(t);
+          if (a.size() != 9 || a[1] != 0.0 || a[2] != 0.0 || a[3] != 0.0 || a[5] != 0.0 || a[6] != 0.0 || a[7] != 0.0) throw std::runtime_error("body '" + rb->id + "': the body frame must be the principal frame (diagonal inertia matrix)");
+          J.J[0] = a[0]; J.J[1] = a[4]; J.J[2] = a[8];
+        }
         rb->set_inertia(J);
         Ravelin::SVelocityd vel;
         if (n->get_attrib("linear-velocity")) { const std::vector<double> a = vec(*n, "linear-velocity", 3); for (int k = 0; k < 3; k++) vel.linear[k] = a[k]; }
@@ -238,7 +254,11 @@ class XMLReader {
       sim->add_contact_parameters(c);
       id_map[c->id] = c;
     }
-    if (!sn.child_nodes("DisabledPair").empty()) throw std::runtime_error("<DisabledPair> is not supported by the C++ facade yet (use the Python loader)");
+    for (const XMLTree* dp : sn.child_nodes("DisabledPair")) {
+      const std::string a = dp->get_attrib("object1-id") ? *dp->get_attrib("object1-id") : "", b = dp->get_attrib("object2-id") ? *dp->get_attrib("object2-id") : "";
+      BasePtr oa = lookup(id_map, a), ob = lookup(id_map, b);
+      if (oa && ob && a != b) sim->disabled_pairs.push_back(std::make_pair(oa, ob));
+    }
     id_map[sim->id] = sim;
     return id_map;
   }
