@@ -607,7 +607,7 @@ def main():
             "config": {"workload": WORKLOAD, "envs_per_gpu": ne, "dt": DT, "preroll_steps": args.preroll, "seed": "0xB200+rank",
                        "min_step_size": ("boxes 1e-3 (test/box.xml), balls sqrt(eps) (bouncing-ball.xml)" if args.min_step == "scene" else "sqrt(eps) everywhere") if args.workload == "small" else scene.min_step_size,
                        "impact_model": "QP-as-LCP (default build); no-slip model for islands with mu >= 100", "stabilization": _stab_text(args),
-                       "l2": "flushed between timed steps (256 MiB write outside the events)", "launch": "one CUDA graph per step (cudaGraphLaunch)", "parallelism": f"envs sharded x{world}"},
+                       "l2": "flushed between timed steps (256 MiB write outside the events)", "launch": "one CUDA graph per step (cudaGraphLaunch) for two-round plans such as configs[1]; plain stream launches for the four-round plans of scenes with large LCPs (UR10, stacks)", "parallelism": f"envs sharded x{world}"},
             "lcp_solves_per_s": lcp_solves / t_dev,
             "mini_steps_per_step": mini_steps / max(env_steps, 1.0), "lcp_solves_per_env_step": lcp_solves / max(env_steps, 1.0),
             "pivots_per_solve": pivots / max(lcp_solves, 1.0), "lemke_calls": lemke_calls, "lcp_fast_calls": fast_calls,

@@ -582,7 +582,10 @@ b200moby_status b200moby_create(const b200moby_scene_desc* d, int device, b200mo
   }
   TRY(plan_launch(h));
   h->concurrent = env_int("B200MOBY_CONCURRENT", 1) != 0;
-  h->graph_on = env_int("B200MOBY_GRAPH", 1) != 0;
+  // default: graph for the two-round plans (configs[1]: neutral on the device, 13x less host work per step); the four-round
+  // plans of scenes with large LCPs are ~50 mostly empty launches per step and ran 10 % slower as graph nodes than as plain
+  // stream launches (UR10: 3.5 against 3.2 ms per step, tools/ur10_phases.py)
+  h->graph_on = env_int("B200MOBY_GRAPH", h->rounds <= 2 ? 1 : 0) != 0;
   if (h->concurrent) {
     h->side.resize(h->classes.size()); h->side_done.resize(h->classes.size());
     for (size_t c = 0; c < h->classes.size(); c++) { h->side[c] = nullptr; h->side_done[c] = nullptr; }
