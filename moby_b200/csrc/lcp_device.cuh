@@ -418,6 +418,16 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
   if (!(mq < 0.0)) { if (pivots_out) *pivots_out = 0; if (log_len) *log_len = 0; g.sync(); return LCP_OK; }   // :737-758
 
   // initial tableau: B = -I  =>  B^-1 M[:,j] = -M[:,j];  cover column B^-1 u = -u with u_i = [q_i < 0]   (:696-698,776-785)
+  if (G::size == 32 && ldm == n) {                                         // a warp walks M linearly (coalesced), keeping (row, column) by increments: no integer division
+    int r = g.tid % n, c = g.tid / n;
+    const int dr = 32 % n, dc = 32 / n;
+    for (int e = g.tid; e < n * n; e += 32) {
+      const double v = M[e];
+      T[e] = -((r == c) ? v + lambda : v);
+      r += dr; c += dc;
+      if (r >= n) { r -= n; c++; }
+    }
+  } else
   for (int e = g.tid; e < n * n; e += G::size) { const int c = e / n, r = e - c * n; T[e] = -m_at(M, ldm, r, c, lambda); }
   for (int i = g.tid; i < n; i += G::size) {
     const double qi = q[i];

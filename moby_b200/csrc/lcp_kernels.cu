@@ -82,7 +82,17 @@ __global__ void __launch_bounds__(256) lcp_warp_kernel(LcpArgs a, int warps_per_
   double* sm_d = (double*)smem + (size_t)w * warp_d;
   int* sm_i = (int*)((double*)smem + (size_t)warps_per_block * warp_d) + (size_t)w * warp_i;
   WarpGroup g(nullptr);
-  for (int b = blockIdx.x * warps_per_block + w; b < a.batch; b += gridDim.x * warps_per_block) solve_one(g, a, b, sm_d, sm_i);
+  const int stride = gridDim.x * warps_per_block;
+  for (int b = blockIdx.x * warps_per_block + w; b < a.batch; b += stride) {
+    // the next problem of this warp into L2 while this one pivots (its M and q are read twice from global memory: norm, tableau)
+    if (b + stride < a.batch) {
+      const char* nm = (const char*)(a.M + (size_t)(b + stride) * a.n * a.n);
+      const size_t bytes = (size_t)a.n * a.n * sizeof(double);
+      for (size_t o = (size_t)g.tid * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(nm + o));
+      if (g.tid == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.q + (size_t)(b + stride) * a.n));
+    }
+    solve_one(g, a, b, sm_d, sm_i);
+  }
 }
 
 // one block per LCP, working set in global scratch (L2-resident), reductions through shared memory
