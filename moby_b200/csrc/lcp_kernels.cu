@@ -6,6 +6,7 @@
 // per-block global scratch that stays L2-resident.  Grids are persistent (148 SMs x resident blocks) and
 // stride over the batch.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../../include/b200moby.h"
 #include "host_util.h"
@@ -95,6 +96,18 @@ __global__ void __launch_bounds__(256) lcp_warp_kernel(LcpArgs a, int warps_per_
   }
 }
 
+// L lanes per LCP (n <= L): 32 / L problems per warp, each sub-group with its own slice of shared memory
+template <int L>
+__global__ void __launch_bounds__(256) lcp_subwarp_kernel(LcpArgs a, int warps_per_block, size_t grp_d, size_t grp_i) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int GPW = 32 / L;                                  // groups per warp
+  const int gib = (threadIdx.x >> 5) * GPW + ((threadIdx.x & 31) / L), groups_per_block = warps_per_block * GPW;
+  double* sm_d = (double*)smem + (size_t)gib * grp_d;
+  int* sm_i = (int*)((double*)smem + (size_t)groups_per_block * grp_d) + (size_t)gib * grp_i;
+  SubWarpGroup<L> g(nullptr);
+  for (int b = blockIdx.x * groups_per_block + gib; b < a.batch; b += gridDim.x * groups_per_block) solve_one(g, a, b, sm_d, sm_i);
+}
+
 // one block per LCP, working set in global scratch (L2-resident), reductions through shared memory
 __global__ void __launch_bounds__(256) lcp_block_kernel(LcpArgs a) {
   __shared__ double red[4 * 8 + 4];
@@ -125,13 +138,37 @@ b200moby_status launch(LcpArgs a, void* stream_) {
   const size_t wi = (work_ints(a.mode, a.n) + 3) & ~(size_t)3;
   const size_t per_warp = wd * sizeof(double) + wi * sizeof(int);
   const size_t MAXS = 227 * 1024;
+  const char* sub_env = getenv("B200MOBY_LCP_SUBWARP_NMAX");
+  const int sub_nmax = sub_env ? atoi(sub_env) : 8;
+  if (a.n <= sub_nmax && a.n <= 16 && a.log == nullptr) {        // several problems per warp (the logged variant keeps the warp loop the parity tests pin)
+    const int L = a.n <= 8 ? 8 : 16, gpw = 32 / L, wpb = 8;
+    const size_t shmem = per_warp * gpw * wpb;                  // per_warp is the working set of ONE problem
+    const void* k = L == 8 ? (const void*)lcp_subwarp_kernel<8> : (const void*)lcp_subwarp_kernel<16>;
+    B2M_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
+    int per_sm = 1;
+    B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, wpb * 32, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const int need = (a.batch + wpb * gpw - 1) / (wpb * gpw);
+    const int grid = std::min(need, sms * per_sm);
+    int wpb_ = wpb; size_t wd_ = wd, wi_ = wi;
+    void* args[] = {&a, &wpb_, &wd_, &wi_};
+    B2M_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(wpb * 32), args, shmem, stream));
+    B2M_CUDA(cudaGetLastError());
+    return B200MOBY_OK;
+  }
   if (per_warp <= MAXS) {
-    int wpb = (int)std::min<size_t>(8, MAXS / per_warp);
+    B2M_CUDA(cudaFuncSetAttribute(lcp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
+    // warps per block that put the most warps on an SM (shared memory and registers both limit the blocks: at n = 40 one block
+    // of 8 warps fits, but two of 7 do); ties: the wider block
+    int wpb = 1, per_sm = 1, best = 0;
+    for (int w = (int)std::min<size_t>(8, MAXS / per_warp); w >= 1; w--) {
+      int blocks = 0;
+      B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, lcp_warp_kernel, w * 32, per_warp * w));
+      if (blocks * w > best) { best = blocks * w; wpb = w; per_sm = blocks; }
+    }
     // do not launch blocks wider than the batch needs
     while (wpb > 1 && (size_t)(wpb - 1) * sms >= (size_t)a.batch) wpb--;
     const size_t shmem = per_warp * wpb;
-    B2M_CUDA(cudaFuncSetAttribute(lcp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXS));
-    int per_sm = 1;
     B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcp_warp_kernel, wpb * 32, shmem));
     if (per_sm < 1) per_sm = 1;
     const int need = (a.batch + wpb - 1) / wpb;

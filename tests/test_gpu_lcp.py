@@ -195,3 +195,31 @@ def test_lockstep_division_is_ieee_division(torch_cuda):
         same = (q.view(torch.int64) == qref.view(torch.int64)) | (q.isnan() & qref.isnan())
         assert bool(same.all()), (kind, x[~same][:4], y[~same][:4], q[~same][:4], qref[~same][:4])
         del x, y, q, qref, same
+
+
+@pytest.mark.parametrize("n,batch", [(2, 1000), (5, 777), (8, 4096)])
+def test_small_lcps_several_per_warp(torch_cuda, oracle, n, batch):
+    """n <= 8 without a pivot log: eight lanes per problem, four problems per warp (lcp_subwarp_kernel).  Same arithmetic as
+    the warp-per-problem kernels: z, status and pivot counts bit-identical to them, for
+    all four solver families, ragged batch sizes included; Lemke also against the oracle."""
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    M, q = random_batch(batch, n, seed=4000 + n)
+    Md, qd = _dev(torch, M), _dev(torch, q)
+    solver = LCP(log_cap=0)
+    for name in ("lcp_lemke", "lcp_fast", "lcp_lemke_regularized", "lcp_fast_regularized"):
+        a = getattr(solver, name)(Md, qd)
+        os.environ["B200MOBY_LCP_SUBWARP_NMAX"] = "0"            # the warp-per-problem kernel (read at every launch)
+        try:
+            b = getattr(solver, name)(Md, qd)
+        finally:
+            del os.environ["B200MOBY_LCP_SUBWARP_NMAX"]
+        za, sa, pa = (x.cpu().numpy() for x in a[:3])
+        zb, sb, pb = (x.cpu().numpy() for x in b[:3])
+        assert np.array_equal(sa, sb) and np.array_equal(pa, pb), name
+        okm = (sa == 0) | (sa == 1) | (sa >= 16)
+        assert np.array_equal(za[okm], zb[okm]), name
+    z = solver.lcp_lemke(Md, qd)[0].cpu().numpy()
+    for b in range(0, batch, max(1, batch // 64)):
+        ok, zo, _ = oracle.lcp_lemke(M[b], q[b])
+        assert ok and np.allclose(z[b], zo, rtol=0, atol=1e-9 * max(1.0, np.abs(zo).max()))
