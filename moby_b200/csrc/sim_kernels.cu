@@ -300,7 +300,7 @@ b200moby_status plan_launch(b200moby_sim* h) {
     if (env_int("B200MOBY_FEED", 1) != 0) { b200moby_status s3; if ((s3 = dev_zero(h, (size_t)B2M_ROUNDS_MAX, &h->feed_ctr)) != B200MOBY_OK) return s3; }
     h->thread_budget = env_int("B200MOBY_THREAD_BUDGET", 12);
     {   // per-class budget: base x (40 / n)^p, at most 8 x base (an iteration of a small LCP is cheap, so a small class can keep envs the n <= 40 class must hand on)
-      const double pw = env_int("B200MOBY_BUDGET_POW10", 0) / 10.0;
+      const double pw = env_int("B200MOBY_BUDGET_POW10", 15) / 10.0;   // measured on configs[1]: 0 -> 6.89, 1.0 -> 7.16, 1.5 -> 7.27, 2.5 -> 5.34 M env-steps/s
       for (size_t k = 0; k < h->classes.size(); k++) {
         const double f = h->classes[k].nmax < 40 ? std::pow(40.0 / h->classes[k].nmax, pw) : 1.0;
         h->P.class_budget[k] = h->classes[k].threads == 1 ? (int)std::min(8.0 * h->thread_budget, std::floor(h->thread_budget * f)) : 0;
