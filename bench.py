@@ -39,7 +39,7 @@ WORKLOADS = {
                    make=lambda sc, ne, seed: sc.box_stack(ne, 10, seed=seed)),
     "ur10": dict(name="example/ur10 arm (9-DoF RCArticulatedBody, CRB forward dynamics) + block + table, mu = 100 as ur10.xml:20 (no-slip impact model), "
                       "16,384 envs per GPU (BASELINE configs[3]; SURVEY 8d case 4)",
-                 envs=16384, dt=5e-4, preroll=100, bytes=2.0 * 8.0 * (9 + 9) + 208.0, cpu_sample=(256, 40), ref_sample=2048,
+                 envs=16384, dt=5e-4, preroll=300, bytes=2.0 * 8.0 * (9 + 9) + 208.0, cpu_sample=(256, 40), ref_sample=2048,   # 300 like configs[1]; the step time follows the arm's motion: 3.1-4.3 ms over windows of 20 steps (tools/ur10_phases.py)
                  make=lambda sc, ne, seed: sc.ur10(ne, seed=seed, mu=100.0)),
     "feeder": dict(name="parts-feeder-like (SURVEY 8d case 5 variant): prismatic shaker tray (RCArticulatedBody) + free box part, mu = 0.01, "
                         "16,384 envs per GPU (part of BASELINE configs[4])",
