@@ -552,6 +552,25 @@ template <class G>
 B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m) {
   const int nb = P.nb, ne = P.n_envs;
   m.cdt = P.contact_dist_thresh; m.wtab = P.fr_tab + B2M_WTAB_OFF;
+  if constexpr (G::size == 1) {
+    // one thread per env: all 22 words of a body are requested before the first is stored (the element-wise loops below made
+    // every global load wait for the local store before it -- ncu, UR10: 18 % of the thread-per-env impact launch sat here)
+    for (int b = 0; b < nb; b++) {
+      const size_t o = (size_t)b * ne + e;
+      const double* qb = P.q + (size_t)b * 7 * ne + e; const double* vb = P.v + (size_t)b * 6 * ne + e;
+      const double* db = P.dims + (size_t)b * 3 * ne + e; const double* jb = P.inertia + (size_t)b * 3 * ne + e;
+      const int sh = P.shape[o], en = P.enabled[o];
+      const double ms = P.mass[o];
+      const double q0 = qb[0], q1 = qb[ne], q2 = qb[2 * (size_t)ne], q3 = qb[3 * (size_t)ne], q4 = qb[4 * (size_t)ne], q5 = qb[5 * (size_t)ne], q6 = qb[6 * (size_t)ne];
+      const double v0 = vb[0], v1 = vb[ne], v2 = vb[2 * (size_t)ne], v3 = vb[3 * (size_t)ne], v4 = vb[4 * (size_t)ne], v5 = vb[5 * (size_t)ne];
+      const double d0 = db[0], d1 = db[ne], d2 = db[2 * (size_t)ne], j0 = jb[0], j1 = jb[ne], j2 = jb[2 * (size_t)ne];
+      m.bshape[b] = sh; m.ben[b] = en; m.bmass[b] = ms;
+      m.bdims[3 * b] = d0; m.bdims[3 * b + 1] = d1; m.bdims[3 * b + 2] = d2; m.bJ[3 * b] = j0; m.bJ[3 * b + 1] = j1; m.bJ[3 * b + 2] = j2;
+      m.bx[3 * b] = q0; m.bx[3 * b + 1] = q1; m.bx[3 * b + 2] = q2;
+      m.bq[4 * b] = q3; m.bq[4 * b + 1] = q4; m.bq[4 * b + 2] = q5; m.bq[4 * b + 3] = q6;
+      m.bvl[3 * b] = v0; m.bvl[3 * b + 1] = v1; m.bvl[3 * b + 2] = v2; m.bva[3 * b] = v3; m.bva[3 * b + 1] = v4; m.bva[3 * b + 2] = v5;
+    }
+  } else {
   for (int b = g.tid; b < nb; b += G::size) {
     m.bshape[b] = P.shape[(size_t)b * ne + e];
     m.ben[b] = P.enabled[(size_t)b * ne + e];
@@ -561,6 +580,7 @@ B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m
   for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; m.bx[k] = P.q[((size_t)b * 7 + c) * ne + e]; }
   for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; m.bq[k] = P.q[((size_t)b * 7 + 3 + c) * ne + e]; }
   for (int k = g.tid; k < 3 * nb; k += G::size) { const int b = k / 3, c = k - 3 * b; m.bvl[k] = P.v[((size_t)b * 6 + c) * ne + e]; m.bva[k] = P.v[((size_t)b * 6 + 3 + c) * ne + e]; }
+  }
   g.sync();
   // quaternions are stored normalised (b200moby_set_state does what set_generalized_coordinates_euler does)
   for (int b = g.tid; b < nb; b += G::size) quat_to_R(m.bq + 4 * b, m.bR + 9 * b);
@@ -581,6 +601,17 @@ B2M_DEV B2M_NOINL void env_load(const G& g, const SimParams& P, int e, EnvMem& m
     if (B2M_RC(P)) { m.ranc[0] = 0; for (int i = 1; i < P.rc_links; i++) m.ranc[i] = m.ranc[P.rc->parent[i]] | (1 << i); }
   }
   if (B2M_RC(P)) {
+    if constexpr (G::size == 1) {                                 // three joints (nine words) per batch: loads first
+      const int nd = P.rc_links - 1;
+      int k = 0;
+      for (; k + 3 <= nd; k += 3) {
+        const size_t o = (size_t)k * ne + e;
+        const double a0 = P.jq[o], a1 = P.jq[o + ne], a2 = P.jq[o + 2 * (size_t)ne], b0 = P.jqd[o], b1 = P.jqd[o + ne], b2 = P.jqd[o + 2 * (size_t)ne];
+        const double c0 = P.jtau[o], c1 = P.jtau[o + ne], c2 = P.jtau[o + 2 * (size_t)ne];
+        m.jq[k] = a0; m.jq[k + 1] = a1; m.jq[k + 2] = a2; m.jqd[k] = b0; m.jqd[k + 1] = b1; m.jqd[k + 2] = b2; m.jtau[k] = c0; m.jtau[k + 1] = c1; m.jtau[k + 2] = c2;
+      }
+      for (; k < nd; k++) { m.jq[k] = P.jq[(size_t)k * ne + e]; m.jqd[k] = P.jqd[(size_t)k * ne + e]; m.jtau[k] = P.jtau[(size_t)k * ne + e]; }
+    } else
     for (int k = g.tid; k < P.rc_links - 1; k += G::size) { m.jq[k] = P.jq[(size_t)k * ne + e]; m.jqd[k] = P.jqd[(size_t)k * ne + e]; m.jtau[k] = P.jtau[(size_t)k * ne + e]; }
     g.sync();
     rc_refresh(g, P, m);
@@ -608,6 +639,20 @@ B2M_DEV B2M_NOINL void env_store(const G& g, const SimParams& P, int e, const En
     }
     g.sync();
   }
+  if constexpr (G::size == 1) {                                  // per body: read the local words first, then the global stores back to back
+    for (int b = 0; b < nb; b++) {
+      if (!m.ben[b]) continue;
+      double* qb = P.q + (size_t)b * 7 * ne + e; double* vb = P.v + (size_t)b * 6 * ne + e;
+      if (what & ST_POS) {
+        const double q0 = m.bx[3 * b], q1 = m.bx[3 * b + 1], q2 = m.bx[3 * b + 2], q3 = m.bq[4 * b], q4 = m.bq[4 * b + 1], q5 = m.bq[4 * b + 2], q6 = m.bq[4 * b + 3];
+        qb[0] = q0; qb[ne] = q1; qb[2 * (size_t)ne] = q2; qb[3 * (size_t)ne] = q3; qb[4 * (size_t)ne] = q4; qb[5 * (size_t)ne] = q5; qb[6 * (size_t)ne] = q6;
+      }
+      if (what & ST_VEL) {
+        const double v0 = m.bvl[3 * b], v1 = m.bvl[3 * b + 1], v2 = m.bvl[3 * b + 2], v3 = m.bva[3 * b], v4 = m.bva[3 * b + 1], v5 = m.bva[3 * b + 2];
+        vb[0] = v0; vb[ne] = v1; vb[2 * (size_t)ne] = v2; vb[3 * (size_t)ne] = v3; vb[4 * (size_t)ne] = v4; vb[5 * (size_t)ne] = v5;
+      }
+    }
+  } else {
   for (int k = g.tid; k < 3 * nb; k += G::size) {
     const int b = k / 3, c = k - 3 * b;
     if (!m.ben[b]) continue;
@@ -615,6 +660,7 @@ B2M_DEV B2M_NOINL void env_store(const G& g, const SimParams& P, int e, const En
     if (what & ST_VEL) { P.v[((size_t)b * 6 + c) * ne + e] = m.bvl[k]; P.v[((size_t)b * 6 + 3 + c) * ne + e] = m.bva[k]; }
   }
   if (what & ST_POS) for (int k = g.tid; k < 4 * nb; k += G::size) { const int b = k / 4, c = k - 4 * b; if (m.ben[b]) P.q[((size_t)b * 7 + 3 + c) * ne + e] = m.bq[k]; }
+  }
   if ((what & ST_ZL) && m.zl && m.scal[S_ZLDIRTY]) {
     const int zn = m.scal[S_ZLN];
     for (int i = g.tid; i < zn; i += G::size) P.zlast[(size_t)i * ne + e] = m.zl[i];
@@ -821,6 +867,33 @@ B2M_DEV B2M_NOINL void inverse_spd_group(const G& g, double* A, int n, int lda, 
   for (int t = g.tid; t < n * n; t += G::size) { const int j = t / n, i = t - j * n; L[t] = A[(size_t)j * lda + i]; }
   g.sync();
   chol_factor_group(g, L, n);
+  if constexpr (G::size == 1) {                                  // one thread: three columns of the inverse per pass (three independent substitution chains)
+    int j = 0;
+    for (; j + 3 <= n; j += 3) {
+      double e0[B2M_MAX_LINKS], e1[B2M_MAX_LINKS], e2[B2M_MAX_LINKS];
+      for (int i = 0; i < n; i++) { e0[i] = (i == j) ? 1.0 : 0.0; e1[i] = (i == j + 1) ? 1.0 : 0.0; e2[i] = (i == j + 2) ? 1.0 : 0.0; }
+      for (int i = 0; i < n; i++) {
+        double s0 = e0[i], s1 = e1[i], s2 = e2[i];
+        for (int k = 0; k < i; k++) { const double l = L[(size_t)k * n + i]; s0 = fma(-l, e0[k], s0); s1 = fma(-l, e1[k], s1); s2 = fma(-l, e2[k], s2); }
+        const double d = L[(size_t)i * n + i];
+        e0[i] = s0 / d; e1[i] = s1 / d; e2[i] = s2 / d;
+      }
+      for (int i = n - 1; i >= 0; i--) {
+        double s0 = e0[i], s1 = e1[i], s2 = e2[i];
+        for (int k = i + 1; k < n; k++) { const double l = L[(size_t)i * n + k]; s0 = fma(-l, e0[k], s0); s1 = fma(-l, e1[k], s1); s2 = fma(-l, e2[k], s2); }
+        const double d = L[(size_t)i * n + i];
+        e0[i] = s0 / d; e1[i] = s1 / d; e2[i] = s2 / d;
+      }
+      for (int i = 0; i < n; i++) { A[(size_t)j * lda + i] = e0[i]; A[(size_t)(j + 1) * lda + i] = e1[i]; A[(size_t)(j + 2) * lda + i] = e2[i]; }
+    }
+    for (; j < n; j++) {
+      double e[B2M_MAX_LINKS];
+      for (int i = 0; i < n; i++) e[i] = (i == j) ? 1.0 : 0.0;
+      chol_solve1(L, n, e);
+      for (int i = 0; i < n; i++) A[(size_t)j * lda + i] = e[i];
+    }
+    return;
+  }
   for (int j = g.tid; j < n; j += G::size) {
     double e[B2M_MAX_LINKS];
     for (int i = 0; i < n; i++) e[i] = (i == j) ? 1.0 : 0.0;
@@ -925,6 +998,47 @@ B2M_DEV B2M_NOINL void compute_problem_data_dense(const G& g, const SimParams& P
   }
   g.sync();
   // X_CdT = (Cd X)^T, kept as rows: XJ[row][k] = sum_kk Jr[row][kk] X[kk][k]
+  if constexpr (G::size == 1) {
+    // one thread per env: the same dot products (same order of the terms), four at a time -- four independent fma chains and
+    // their loads in flight instead of one (ncu, UR10: these three loops were 19 % of the thread-per-env impact launch)
+    for (int row = 0; row < 3 * nc; row++) {
+      const double* jr = m.Jr + (size_t)row * ngc;
+      double* out = m.XJ + (size_t)row * ngc;
+      int k = 0;
+      for (; k + 4 <= ngc; k += 4) {
+        const double* x0 = m.Xb + (size_t)k * ngc; const double* x1 = x0 + ngc; const double* x2 = x1 + ngc; const double* x3 = x2 + ngc;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int kk = 0; kk < ngc; kk++) { const double a = jr[kk]; s0 = fma(a, x0[kk], s0); s1 = fma(a, x1[kk], s1); s2 = fma(a, x2[kk], s2); s3 = fma(a, x3[kk], s3); }
+        out[k] = s0; out[k + 1] = s1; out[k + 2] = s2; out[k + 3] = s3;
+      }
+      for (; k < ngc; k++) { double s0 = 0.0; for (int kk = 0; kk < ngc; kk++) s0 = fma(jr[kk], m.Xb[(size_t)k * ngc + kk], s0); out[k] = s0; }
+    }
+    for (int bk = 0; bk < 6; bk++) {
+      const int d1 = bk < 3 ? 0 : (bk < 5 ? 1 : 2), d2 = bk < 3 ? bk : (bk < 5 ? bk - 2 : 2);
+      for (int i = 0; i < nc; i++) {
+        const double* jr = m.Jr + ((size_t)d1 * nc + i) * ngc;
+        double* out = m.D + ((size_t)bk * nc + i) * nc;
+        int j = 0;
+        for (; j + 4 <= nc; j += 4) {
+          const double* x0 = m.XJ + ((size_t)d2 * nc + j) * ngc; const double* x1 = x0 + ngc; const double* x2 = x1 + ngc; const double* x3 = x2 + ngc;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          for (int k = 0; k < ngc; k++) { const double a = jr[k]; s0 = fma(a, x0[k], s0); s1 = fma(a, x1[k], s1); s2 = fma(a, x2[k], s2); s3 = fma(a, x3[k], s3); }
+          out[j] = s0; out[j + 1] = s1; out[j + 2] = s2; out[j + 3] = s3;
+        }
+        for (; j < nc; j++) { const double* xj = m.XJ + ((size_t)d2 * nc + j) * ngc; double s0 = 0.0; for (int k = 0; k < ngc; k++) s0 = fma(jr[k], xj[k], s0); out[j] = s0; }
+      }
+    }
+    {
+      int t = 0;
+      for (; t + 3 <= 3 * nc; t += 3) {
+        const double* j0 = m.Jr + (size_t)t * ngc; const double* j1 = j0 + ngc; const double* j2 = j1 + ngc;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < ngc; k++) { const double gk = m.gv[k]; s0 = fma(j0[k], gk, s0); s1 = fma(j1[k], gk, s1); s2 = fma(j2[k], gk, s2); }
+        m.Cv[t] = s0; m.Cv[t + 1] = s1; m.Cv[t + 2] = s2; m.imp[t] = 0.0; m.imp[t + 1] = 0.0; m.imp[t + 2] = 0.0;
+      }
+    }
+    return;
+  }
   for (int t = g.tid; t < 3 * nc * ngc; t += G::size) {
     const int k = t % ngc, row = t / ngc;
     const double* jr = m.Jr + (size_t)row * ngc;
