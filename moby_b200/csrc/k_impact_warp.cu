@@ -79,3 +79,36 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
 }
 
 const void* b2m_k_impact_warp() { return (const void*)impact_warp_kernel; }
+
+// ---- impact, L lanes per env (L = 8): 32 / L envs per warp, working sets in shared memory ----
+// For the small LCP classes (one or two contacts: n <= 24).  A thread per env walks these envs' few thousand instructions
+// alone, a warp per env leaves most lanes idle (7-15 active lanes per instruction in round 1's captures); eight lanes share
+// one env's loops and four envs share a warp's instruction stream.  The sub-groups of a warp are independent (every
+// collective carries the group's own lane mask, common.cuh: SubWarpGroup), so a long solve holds up its own eight lanes only.
+// Same device functions, same arithmetic per element: bit-identical to the other kernels.
+template <int L>
+__global__ void __launch_bounds__(256) impact_subwarp_kernel(SimParams P, double dt, int round, int slot, int wpb) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int GPW = 32 / L;
+  const int lane = threadIdx.x & 31, gib = (threadIdx.x >> 5) * GPW + lane / L;
+  EnvMem m;
+  env_mem_full(P, m, smem, gib, wpb * GPW);
+  SubWarpGroup<L> g(nullptr);
+  unsigned long long lc[CNT_COUNT], tot[CNT_COUNT];
+  for (int k = 0; k < CNT_COUNT; k++) tot[k] = 0;
+  unsigned long long envs = 0;
+  const int count = q_size(P, round, slot);
+  int* head = q_head(P, round, slot);
+  for (;;) {
+    int i = 0;
+    if (g.tid == 0) i = atomicAdd(head, 1);
+    i = __shfl_sync(g.mask, i, lane & ~(L - 1));
+    if (i >= count) break;
+    for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
+    EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
+    if (env_impact(g, P, q_at(P, round, slot, i), m, dt, round, lc, cx)) add_counters(tot, lc);
+    envs++;
+  }
+  if (g.tid == 0) commit_counters(P, tot, envs);
+}
+const void* b2m_k_impact_subwarp8() { return (const void*)impact_subwarp_kernel<8>; }

@@ -54,7 +54,7 @@ struct b200moby_sim {
   SimParams graph_P; double graph_dt = 0.0; bool graph_feed = false; long long graph_launches = 0; bool graph_on = true; int graph_captures = 0;
   int* stab_queue = nullptr; // [n_envs + 1] envs selected for stabilization this step, then their count (k_stabilize.cu)
   int* feed_ctr = nullptr;   // [B2M_ROUNDS_MAX] class launches completed in the round (k_impact_warp.cu: the hard-queue launch takes their stragglers)
-  bool all_thread_classes = false;
+  bool all_thread_classes = false, any_subwarp_class = false;
   LadderPool pool;           // task pool of the Lemke ladder (lcp_device.cuh) for the hard-queue / straggler launches; ctl == nullptr: off
   int pool_owners = 0;
   ClassPlan straggler;       // full-size kernel (warp per env while the scene's LCPs fit one, else a 256-thread block) for envs over their pivot budget and for the hard queue
@@ -280,6 +280,17 @@ b200moby_status plan_launch(b200moby_sim* h) {
           else if (nd <= B2M_THREAD_ND1 && ni <= B2M_THREAD_NI1) c.tvariant = 1;
         }
       }
+      if (c.tvariant >= 0 && c.nmax <= env_int("B200MOBY_SUBWARP_NMAX", 0) && !B2M_RC(h->P)) {   // small classes: eight lanes per env, four envs per warp (k_impact_warp.cu)
+        EnvDims Dc = env_dims(h->P); Dc.cmax = c.cmax; Dc.nmax = c.nmax;
+        const size_t ed = (env_doubles(Dc) + 1) & ~(size_t)1, ei = (env_ints(Dc) + 3) & ~(size_t)3, per = ed * sizeof(double) + ei * sizeof(int);
+        c.threads = 8; c.tvariant = -1; c.wpb = 1; c.shmem = per * 4;
+        if (c.shmem <= 100 * 1024) {
+          if ((st = plan_grid(b2m_k_impact_subwarp8(), 32, c.shmem, sms, (ne + 3) / 4, &c.grid)) != B200MOBY_OK) return st;
+          h->any_subwarp_class = true;
+          h->classes.push_back(c); continue;
+        }
+        c.threads = 32; c.tvariant = -1;                          // does not fit: fall through to the warp kernel
+      }
       if (c.tvariant >= 0) {
         const int lanes = std::max(1, std::min(32, env_int("B200MOBY_THREAD_LANES", 32)));
         h->P.thread_lanes = lanes;
@@ -294,16 +305,16 @@ b200moby_status plan_launch(b200moby_sim* h) {
       h->classes.push_back(c);
     }
     h->P.n_classes = (int)h->classes.size();
-    for (const ClassPlan& c : h->classes) if (c.threads == 1) h->any_thread_class = true;
+    for (const ClassPlan& c : h->classes) if (c.threads == 1 || c.threads == 8) h->any_thread_class = true;
     h->all_thread_classes = true;
-    for (const ClassPlan& c : h->classes) if (c.threads != 1) h->all_thread_classes = false;
+    for (const ClassPlan& c : h->classes) if (c.threads != 1 && c.threads != 8) h->all_thread_classes = false;   // thread- and sub-warp classes can run beside the hard queue (the latter in the shared memory it is made to leave)
     if (env_int("B200MOBY_FEED", 1) != 0) { b200moby_status s3; if ((s3 = dev_zero(h, (size_t)B2M_ROUNDS_MAX, &h->feed_ctr)) != B200MOBY_OK) return s3; }
     h->thread_budget = env_int("B200MOBY_THREAD_BUDGET", 12);
     {   // per-class budget: base x (40 / n)^p, at most 8 x base (an iteration of a small LCP is cheap, so a small class can keep envs the n <= 40 class must hand on)
       const double pw = env_int("B200MOBY_BUDGET_POW10", 15) / 10.0;   // measured on configs[1]: 0 -> 6.89, 1.0 -> 7.16, 1.5 -> 7.27, 2.5 -> 5.34 M env-steps/s
       for (size_t k = 0; k < h->classes.size(); k++) {
         const double f = h->classes[k].nmax < 40 ? std::pow(40.0 / h->classes[k].nmax, pw) : 1.0;
-        h->P.class_budget[k] = h->classes[k].threads == 1 ? (int)std::min(8.0 * h->thread_budget, std::floor(h->thread_budget * f)) : 0;
+        h->P.class_budget[k] = (h->classes[k].threads == 1 || h->classes[k].threads == 8) ? (int)std::min(8.0 * h->thread_budget, std::floor(h->thread_budget * f)) : 0;
       }
     }
     ClassPlan& sg = h->straggler;
@@ -312,7 +323,7 @@ b200moby_status plan_launch(b200moby_sim* h) {
     sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : (h->nmax <= 64 ? 32 : 128));   // n <= 64: the warp-owned pivot loops (lcp_device.cuh), no block barriers   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
     if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
     if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
-    { const int cap = env_int("B200MOBY_HARD_BLOCKS_PER_SM", 0);      // experiment knob: fewer resident warps of the hard-queue launch per SM (less contention for the shared-memory pipe)
+    { const int cap = env_int("B200MOBY_HARD_BLOCKS_PER_SM", h->any_subwarp_class ? 1 : 0);      // experiment knob: fewer resident warps of the hard-queue launch per SM (less contention for the shared-memory pipe)
       if (cap > 0 && sg.grid > sms * cap) sg.grid = sms * cap;
       if (env_int("B200MOBY_PLAN_DEBUG", 0)) fprintf(stderr, "[b200moby] hard/straggler plan: threads %d wpb %d grid %d (%d SMs) shmem %zu\n", sg.threads, sg.wpb, sg.grid, sms, sg.shmem); }
     // the Lemke ladder as a task pool: one job buffer per warp of the hard-queue / straggler launches
@@ -485,6 +496,11 @@ b200moby_status launch_step(b200moby_sim* h, double dt, cudaStream_t s) {
         Pc.pivot_budget = h->P.class_budget[c] > 0 ? h->P.class_budget[c] : h->thread_budget;
         void* a[] = {&Pc, &dt, &r, &slot};
         st = timed_launch(h, 1 + (int)c, b2m_k_impact_thread(cp.tvariant), dim3(cp.grid), dim3(128), a, 0, sc);
+      } else if (cp.threads == 8) {
+        Pc.pivot_budget = h->P.class_budget[c] > 0 ? h->P.class_budget[c] : h->thread_budget;
+        int wpb = cp.wpb;
+        void* a[] = {&Pc, &dt, &r, &slot, &wpb};
+        st = timed_launch(h, 1 + (int)c, b2m_k_impact_subwarp8(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
       } else {
         if (cp.threads != 32) Pc.pivot_budget = 0;
         st = launch_impact(h, 1 + (int)c, cp, Pc, dt, r, slot, false, sc);
@@ -852,7 +868,7 @@ b200moby_status b200moby_get_kernel_profile(b200moby_handle h, int enable, int r
     for (int k = 0; k < nk && k < B200MOBY_MAX_KERNELS; k++) {
       b200moby_kernel_stat& o = out->k[k];
       if (k == 0) snprintf(o.name, sizeof(o.name), "advance_kernel");
-      else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 1) snprintf(o.name, sizeof(o.name), "impact_thread_kernel[n<=%d]", c.nmax); else if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
+      else if (k <= ncls) { const ClassPlan& c = h->classes[k - 1]; if (c.threads == 1) snprintf(o.name, sizeof(o.name), "impact_thread_kernel[n<=%d]", c.nmax); else if (c.threads == 8) snprintf(o.name, sizeof(o.name), "impact_subwarp_kernel<8>[n<=%d]", c.nmax); else if (c.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[n<=%d]", c.nmax); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[n<=%d]", c.threads, c.nmax); o.lcp_nmax = c.nmax; o.threads_per_env = c.threads; }
       else if (k == ncls + 1 || k == ncls + 3) { if (h->straggler.threads == 32) snprintf(o.name, sizeof(o.name), "impact_warp_kernel[%s]", k == ncls + 1 ? "stragglers" : "hard queue"); else snprintf(o.name, sizeof(o.name), "impact_block_kernel<%d>[%s]", h->straggler.threads, k == ncls + 1 ? "stragglers" : "hard queue"); o.lcp_nmax = h->nmax; o.threads_per_env = h->straggler.threads; }
       else if (k == ncls + 4) { snprintf(o.name, sizeof(o.name), h->stab_variant >= 0 ? "stabilize_thread_kernel" : "stabilize_warp_kernel"); o.threads_per_env = h->stab_variant >= 0 ? 1 : 32; }
       else snprintf(o.name, sizeof(o.name), h->finblock.threads == 256 ? "finish_block_kernel<256>" : "finish_kernel");

@@ -12,6 +12,7 @@ const void* b2m_k_advance_thread(int cls); // (SimParams P, double dt, int round
 #define B2M_THREAD_NI1 384
 const void* b2m_k_impact_thread(int variant);   // (SimParams P, double dt, int round, int slot)
 const void* b2m_k_impact_warp();          // (SimParams P, double dt, int round, int slot, int wpb, LadderPool L, int feed_slot, int* feed_done, int feed_expect)
+const void* b2m_k_impact_subwarp8();       // (SimParams P, double dt, int round, int slot, int wpb): eight lanes per env, 4 * wpb envs per block
 const void* b2m_k_signal();               // (int* counter): one thread, counter += 1 (stream-ordered completion signal of a class launch)
 const void* b2m_k_impact_block64();
 const void* b2m_k_impact_block128();

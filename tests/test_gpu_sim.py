@@ -297,7 +297,7 @@ def test_ladder_task_pool_gives_the_sequential_results(torch_cuda):
     assert res[0][0]["lemke_calls"] > res[0][0]["lcp_solves"] // 50 and res[0][0]["lemke_calls"] > 20000       # ladders beyond rung 0 were run
 
 
-@pytest.mark.parametrize("knob", ["B200MOBY_GRAPH", "B200MOBY_FEED", "B200MOBY_STAB_SELECT"])
+@pytest.mark.parametrize("knob", ["B200MOBY_GRAPH", "B200MOBY_FEED", "B200MOBY_STAB_SELECT", "B200MOBY_SUBWARP_NMAX=24"])
 def test_schedule_knobs_do_not_change_results(torch_cuda, knob):
     """One step as a CUDA graph (re-captured when dt changes) against plain launches; the hard-queue launch taking the
     classes' stragglers as they arrive against a straggler launch of its own; stabilization over the selected envs against
@@ -307,7 +307,8 @@ def test_schedule_knobs_do_not_change_results(torch_cuda, knob):
     sc = scenes.small_lcp_batch(8192, seed=0xB200)
     sc.stabilization_max_iterations = -1
     res = []
-    for val in ("1", "0"):
+    knob, _, on = knob.partition("=")              # "NAME=value": value against 0 (the sub-warp impact classes: eight lanes per env for n <= 24)
+    for val in (on or "1", "0"):
         os.environ[knob] = val
         try:
             sim = TimeSteppingSimulator(sc)
