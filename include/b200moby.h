@@ -57,7 +57,11 @@ enum { B200MOBY_SHAPE_NONE = 0, B200MOBY_SHAPE_SPHERE = 1, B200MOBY_SHAPE_BOX = 
         * contacts and conservative-advancement step come from the collision-detection plugin (coldet-plugin.cpp:86-137,
         * 214-334; extern "C" factory() :340-346).  Built in as a shape: dims = (R, W, N_SPOKES) (params.h:4-6), spokes in the
         * body's x-z plane, checked against planes only. */
-       B200MOBY_SHAPE_WHEEL = 4 };
+       B200MOBY_SHAPE_WHEEL = 4,
+       /* example/contact-constrained-pendulum: a pin joint emulated by six frictionless contacts, again the work of a collision-detection
+        * plugin (contact-constrained-pendulum-coldet-plugin.cpp:60-110): PIN on the moving body (dims = the anchor point in its frame),
+        * PINWORLD on the fixed one (anchor = its origin). */
+       B200MOBY_SHAPE_PIN = 5, B200MOBY_SHAPE_PINWORLD = 6 };
 
 /* Impact models (ImpactConstraintHandler.cpp:122-146). */
 enum {

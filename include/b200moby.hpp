@@ -195,6 +195,17 @@ class PlanePrimitive : public Primitive {         // half-space y <= 0 of the bo
 };
 // The rimless wheel of example/rimless-wheel: in the reference a CollisionGeometry WITHOUT a primitive whose distance and
 // contacts come from the collision-detection plugin (coldet-plugin.cpp:86-137,222-310; params.h:4-6); here a shape of its own.
+// example/contact-constrained-pendulum: the pin joint its collision-detection plugin emulates with six frictionless contacts
+// (contact-constrained-pendulum-coldet-plugin.cpp:60-110).  PinPrimitive goes on the moving body (anchor point in its frame),
+// PinWorldPrimitive on the fixed one (anchor = its origin).
+class PinPrimitive : public Primitive {
+ public:
+  PinPrimitive(double ax = 0.0, double ay = 1.0, double az = 0.0) { shape = B200MOBY_SHAPE_PIN; dims[0] = ax; dims[1] = ay; dims[2] = az; }
+};
+class PinWorldPrimitive : public Primitive {
+ public:
+  PinWorldPrimitive() { shape = B200MOBY_SHAPE_PINWORLD; }
+};
 class RimlessWheelPrimitive : public Primitive {
  public:
   RimlessWheelPrimitive(double R = 1.0, double W = 0.0, unsigned n_spokes = 6) { shape = B200MOBY_SHAPE_WHEEL; dims[0] = R; dims[1] = W; dims[2] = (double)n_spokes; }

@@ -162,7 +162,7 @@ class XMLReader {
       if (sv.size() == 1 && sv[0]->get_attrib("collision-detection-plugin")) {
         std::vector<const XMLTree*> pv; moby.find_all("CollisionDetectionPlugin", pv);
         for (const XMLTree* pn : pv) if (pn->get_attrib("id") && *pn->get_attrib("id") == *sv[0]->get_attrib("collision-detection-plugin") && pn->get_attrib("plugin")) coldet_plugin = *pn->get_attrib("plugin");
-        if (coldet_plugin != "librimless-wheel-coldet-plugin.so") throw std::runtime_error("collision-detection-plugin '" + coldet_plugin + "': no built-in equivalent on the accelerated path");
+        if (coldet_plugin != "librimless-wheel-coldet-plugin.so" && coldet_plugin != "libcontact-constrained-pendulum-coldet-plugin.so") throw std::runtime_error("collision-detection-plugin '" + coldet_plugin + "': no built-in equivalent on the accelerated path");
       } }
     // rigid bodies
     { std::vector<const XMLTree*> v; moby.find_all("RigidBody", v);
@@ -179,7 +179,11 @@ class XMLReader {
           for (const char* k : {"relative-origin", "relative-rpy", "relative-quat"}) if (cg[0]->get_attrib(k)) throw std::runtime_error("body '" + rb->id + "': CollisionGeometry offsets are not supported");
           const std::string pid = cg[0]->get_attrib("primitive-id") ? *cg[0]->get_attrib("primitive-id") : "";
           PrimitivePtr p = std::dynamic_pointer_cast<Primitive>(lookup(id_map, pid));
-          if (!p && pid.empty() && !coldet_plugin.empty() && rb->id == "WHEEL") { p.reset(new RimlessWheelPrimitive(1.0, 0.0, 6)); prim_pose[pid] = Ravelin::Pose3d(); }   // params.h:4-6
+          if (!p && pid.empty() && coldet_plugin == "librimless-wheel-coldet-plugin.so" && rb->id == "WHEEL") { p.reset(new RimlessWheelPrimitive(1.0, 0.0, 6)); prim_pose[pid] = Ravelin::Pose3d(); }   // params.h:4-6
+          if (!p && pid.empty() && coldet_plugin == "libcontact-constrained-pendulum-coldet-plugin.so" && (rb->id == "l1" || rb->id == "world")) {   // contact-constrained-pendulum-coldet-plugin.cpp:21-37,60-75
+            if (rb->id == "l1") p.reset(new PinPrimitive(0.0, 1.0, 0.0)); else p.reset(new PinWorldPrimitive);
+            prim_pose[pid] = Ravelin::Pose3d();
+          }
           if (!p) throw std::runtime_error("body '" + rb->id + "': primitive '" + pid + "' is not a Box / Sphere / Plane of this file");
           const Ravelin::Pose3d& pp = prim_pose[pid];
           if (p->shape == B200MOBY_SHAPE_PLANE) {

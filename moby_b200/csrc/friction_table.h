@@ -55,7 +55,8 @@ inline void b2m_env_bounds(int nb, const int* shape, const int* enabled, const i
       if ((bi && pj) || (pi && bj)) cnt = 4;           // a non-degenerate box touches a plane with at most 4 vertices
       if (bi && bj) cnt = 8;
       if (pi && pj) cnt = 0;
-      if (shape[i] == 4 || shape[j] == 4) cnt = (pi || pj) ? 4 : 0;   // rimless wheel: spoke tips against a plane only (two tips, two sides when W > 0)
+      if (shape[i] == 4 || shape[j] == 4) cnt = (pi || pj) ? 4 : 0;
+      if (shape[i] >= 5 || shape[j] >= 5) cnt = ((shape[i] == 5 && shape[j] == 6) || (shape[i] == 6 && shape[j] == 5)) ? 6 : 0;   // pin joint as six contacts   // rimless wheel: spoke tips against a plane only (two tips, two sides when W > 0)
       cmax += cnt;
       nmax += cnt * (model == 1 ? 5 + (nk > 4 ? (nk + 4) / 4 : 1) : 6 + nk / 2);
     }

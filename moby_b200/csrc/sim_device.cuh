@@ -15,7 +15,8 @@
 namespace b2m {
 
 enum { SH_NONE = 0, SH_SPHERE = 1, SH_BOX = 2, SH_PLANE = 3,
-       SH_WHEEL = 4 };   // rimless wheel of example/rimless-wheel/coldet-plugin.cpp: dims = (R, W, N_SPOKES) (params.h:4-6); collides with planes only
+       SH_WHEEL = 4,
+       SH_PIN = 5, SH_PINWORLD = 6 };   // example/contact-constrained-pendulum: a pin joint as six frictionless contacts (its collision-detection plugin); dims of SH_PIN = the anchor point in the body frame   // rimless wheel of example/rimless-wheel/coldet-plugin.cpp: dims = (R, W, N_SPOKES) (params.h:4-6); collides with planes only
 enum { CNT_ENV_STEPS = 0, CNT_MINI_STEPS, CNT_LCP_SOLVES, CNT_FAST_CALLS, CNT_LEMKE_CALLS, CNT_PIVOTS, CNT_LCP_FAIL,
        CNT_IMPACT_TOL, CNT_CONTACTS, CNT_MAX_N, CNT_OVERFLOW, CNT_PIVOT_FLOPS, CNT_ASM_FLOPS, CNT_CA_ITERS, CNT_STAB_ITERS, CNT_STAB_SOLVES, CNT_STAB_LSFAIL, CNT_COUNT };
 #define B2M_NKMAX 64
@@ -321,6 +322,13 @@ B2M_HD B2M_NOINL inline double wheel_plane_signed_dist(const BodyRef& Wh, const 
 B2M_HD inline bool signed_dist(const BodyRef& A, const BodyRef& B, double& dist, V3& pA, V3& pB) {
   // coldet-plugin.cpp:324-334: both argument orders hand (pA, pB) to (pwheel, pground); with the pair the plugin queues,
   // (ground, wheel) (:70), the point reported for the ground is the wheel's and vice versa.  Literal.
+  // contact-constrained-pendulum-coldet-plugin.cpp:60-75,140-150: minus the distance from the link's anchor point to the world body's origin
+  if ((A.shape == SH_PIN && B.shape == SH_PINWORLD) || (A.shape == SH_PINWORLD && B.shape == SH_PIN)) {
+    const BodyRef& L = (A.shape == SH_PIN) ? A : B; const BodyRef& W = (A.shape == SH_PIN) ? B : A;
+    pA = to_global(L, V3(L.dims[0], L.dims[1], L.dims[2])); pB = ld3(W.x);
+    dist = -norm(to_local(W, pA));
+    return true;
+  }
   if (A.shape == SH_WHEEL && B.shape == SH_PLANE) { dist = wheel_plane_signed_dist(A, B, pA, pB); return true; }
   if (A.shape == SH_PLANE && B.shape == SH_WHEEL) { dist = wheel_plane_signed_dist(B, A, pA, pB); return true; }
   if (signed_dist_ordered(A, B, dist, pA, pB)) return true;
@@ -343,6 +351,19 @@ struct ContactOut { V3 p, n; int b1, b2; double dist; };
 B2M_HD B2M_NOINL inline int pair_contacts(const EnvMem& m, int ia, int ib, double TOL, ContactOut* out, int cap) {
   const BodyRef A = body_ref(m, ia), B = body_ref(m, ib);
   int cnt = 0;
+  if ((A.shape == SH_PIN && B.shape == SH_PINWORLD) || (A.shape == SH_PINWORLD && B.shape == SH_PIN)) {   // contact-constrained-pendulum-coldet-plugin.cpp:78-110
+    const int il = (A.shape == SH_PIN) ? ia : ib, iw = (A.shape == SH_PIN) ? ib : ia;
+    const BodyRef L = body_ref(m, il);
+    const V3 p = to_global(L, V3(L.dims[0], L.dims[1], L.dims[2]));
+    const V3 point = (p + V3(0, 0, 0)) * 0.5;                  // midpoint of the anchor point and the GLOBAL origin
+    for (int k = 0; k < 6; k++) {                              // normals +y -y +z -z +x -x; violation min(0, -p_k) for both normals of an axis
+      const int ax = k < 2 ? 1 : (k < 4 ? 2 : 0);
+      const double sg = (k & 1) ? -1.0 : 1.0, pk = ax == 0 ? p.x : (ax == 1 ? p.y : p.z);
+      if (cnt < cap) { out[cnt].p = point; out[cnt].n = V3(ax == 0 ? sg : 0.0, ax == 1 ? sg : 0.0, ax == 2 ? sg : 0.0); out[cnt].b1 = il; out[cnt].b2 = iw; out[cnt].dist = fmin(0.0, -pk); }
+      cnt++;
+    }
+    return cnt;
+  }
   if ((A.shape == SH_WHEEL && B.shape == SH_PLANE) || (A.shape == SH_PLANE && B.shape == SH_WHEEL)) {     // coldet-plugin.cpp:222-310
     const int iw = (A.shape == SH_WHEEL) ? ia : ib, ip = (A.shape == SH_WHEEL) ? ib : ia;
     const BodyRef Wh = body_ref(m, iw), P = body_ref(m, ip);
@@ -491,7 +512,7 @@ B2M_HD B2M_NOINL inline double pair_CA(const EnvMem& m, int p) {
       if (nc == 1 && fabs(contact_vel(m, con[0])) < B2M_NEAR_ZERO * 10) return B2M_INF;
     }
   }
-  if (pdist <= 0.0 && (A.shape == SH_WHEEL || B.shape == SH_WHEEL)) return B2M_INF;   // coldet-plugin.cpp:214-217 overrides calc_next_CA_Euler_step
+  if (pdist <= 0.0 && (A.shape == SH_WHEEL || B.shape == SH_WHEEL || A.shape == SH_PIN || B.shape == SH_PIN)) return B2M_INF;   // both plugins override calc_next_CA_Euler_step
   if (pdist <= 0.0) {                                                       // :189-190 -> :238-400
     const int nc = pair_contacts(m, ia, ib, B2M_NEAR_ZERO, con, 8);
     if (nc == 0) return B2M_INF;

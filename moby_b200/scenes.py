@@ -11,7 +11,7 @@ import numpy as np
 
 from .capi import RcDesc, SceneDesc
 
-SHAPE_NONE, SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE, SHAPE_WHEEL = 0, 1, 2, 3, 4
+SHAPE_NONE, SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE, SHAPE_WHEEL, SHAPE_PIN, SHAPE_PINWORLD = 0, 1, 2, 3, 4, 5, 6
 MODEL_QP, MODEL_AP = 0, 1
 JOINT_REVOLUTE, JOINT_PRISMATIC = 1, 2
 FDYN_FSAB, FDYN_CRB = 0, 1
@@ -249,6 +249,27 @@ def sphere_stack(n_envs=1):
     s.set_contact(0, 2, NK=4)
     s.set_contact(1, 3, NK=4)
     s.set_contact(2, 3, NK=4)
+    return s
+
+
+def contact_constrained_pendulum(n_envs=1, stabilization=25):
+    """example/contact-constrained-pendulum/contact-constrained-pendulum.xml: body l1 (sphere inertia r = 1.5811, mass 1) at
+    (1, 0, 0) turned 90 degrees about z, its point (0, 1, 0) held at the origin of the fixed body `world` by the six frictionless
+    contacts of the scene's collision-detection plugin; gravity -y; constraint-stabilization-max-iterations = 25."""
+    s = SceneBatch(n_envs, 2)
+    s.name = "contact-constrained-pendulum"
+    s.gravity = (0.0, -9.81, 0.0)
+    s.set_sphere(0, 1.5811, mass=1.0)
+    s.shape[0, :] = SHAPE_PIN
+    s.dims[0, 0, :], s.dims[0, 1, :], s.dims[0, 2, :] = 0.0, 1.0, 0.0
+    s.q[0, 0, :] = 1.0
+    qz = quat_from_rpy(0.0, 0.0, np.float64(1.57079632679490))
+    for k in range(4):
+        s.q[0, 3 + k, :] = qz[k]
+    s.shape[1, :] = SHAPE_PINWORLD
+    s.enabled[1, :] = 0
+    s.set_contact(0, 1, mu_coulomb=0.0, epsilon=0.0, NK=4)
+    s.stabilization_max_iterations = stabilization
     return s
 
 

@@ -34,7 +34,9 @@ _PRIMS = ("Box", "Sphere", "Plane")
 # Collision-detection plugins (XMLReader.cpp:334-388, ConstraintSimulator.cpp:562-572) the accelerated path has a built-in
 # equivalent for: plugin file name -> {body id: (shape setter arguments)}.  The rimless wheel's plugin finds its bodies by
 # the ids "WHEEL" and "GROUND" (coldet-plugin.cpp:29-36) and takes R, W, N_SPOKES from params.h:4-6.
-_COLDET_PLUGINS = {"librimless-wheel-coldet-plugin.so": {"WHEEL": dict(radius=1.0, width=0.0, n_spokes=6), "GROUND": None}}
+_COLDET_PLUGINS = {"librimless-wheel-coldet-plugin.so": {"WHEEL": dict(radius=1.0, width=0.0, n_spokes=6), "GROUND": None},
+                   # contact-constrained-pendulum-coldet-plugin.cpp:21-37,60-75: bodies "l1" (anchor point (0,1,0)) and "world"
+                   "libcontact-constrained-pendulum-coldet-plugin.so": {"l1": dict(pin=(0.0, 1.0, 0.0)), "world": dict(pinworld=True)}}
 _UNSUPPORTED_PRIMS = ("Cone", "Cylinder", "Torus", "Heightmap", "TriangleMesh", "Polyhedron", "CSG", "GaussianMixture")
 
 
@@ -137,7 +139,15 @@ def load_xml(source, n_envs=1):
                 raise ValueError(f"body {bid!r}: CollisionGeometry offsets are not supported")
             p = prims.get(cg.get("primitive-id"))
             if p is None and cg.get("primitive-id") is None and plugin_bodies.get(bid) is not None:
-                s.set_wheel(i, **plugin_bodies[bid])                 # geometry without a primitive: the plugin's own shape
+                spec = plugin_bodies[bid]                            # geometry without a primitive: the plugin's own shape
+                if "pin" in spec:
+                    s.shape[i, :] = scenes.SHAPE_PIN
+                    for k in range(3):
+                        s.dims[i, k, :] = spec["pin"][k]
+                elif "pinworld" in spec:
+                    s.shape[i, :] = scenes.SHAPE_PINWORLD
+                else:
+                    s.set_wheel(i, **spec)
                 cgs = []
             elif p is None:
                 raise ValueError(f"body {bid!r}: primitive {cg.get('primitive-id')!r} is not a Box / Sphere / Plane of this file")

@@ -190,6 +190,14 @@ static double wheel_plane_signed_dist(const Body& Wh, const Body& P, V3& pwheel,
 static bool signed_dist(const Body& A, const Body& B, double& dist, V3& pA, V3& pB) {
   // coldet-plugin.cpp:324-334: BOTH argument orders hand (pA, pB) to (pwheel, pground) -- with the pair the plugin
   // queues, (ground, wheel) (:70), the point reported for the ground is the wheel's and vice versa.  Literal.
+  // contact-constrained-pendulum-coldet-plugin.cpp:60-75,140-150: minus the distance between the link's anchor point and the world
+  // body's origin, never positive; both argument orders hand (pA, pB) to (point on l1, point on world)
+  if ((A.shape == SHAPE_PIN && B.shape == SHAPE_PINWORLD) || (A.shape == SHAPE_PINWORLD && B.shape == SHAPE_PIN)) {
+    const Body& L = (A.shape == SHAPE_PIN) ? A : B; const Body& W = (A.shape == SHAPE_PIN) ? B : A;
+    pA = to_global(L, V3(L.dims[0], L.dims[1], L.dims[2])); pB = W.x;
+    dist = -norm(to_local(W, pA));
+    return true;
+  }
   if (A.shape == SHAPE_WHEEL && B.shape == SHAPE_PLANE) { dist = wheel_plane_signed_dist(A, B, pA, pB); return true; }
   if (A.shape == SHAPE_PLANE && B.shape == SHAPE_WHEEL) { dist = wheel_plane_signed_dist(B, A, pA, pB); return true; }
   if (signed_dist_ordered(A, B, dist, pA, pB)) return true;
@@ -229,6 +237,21 @@ static Contact create_contact(int a, int b, const V3& point, const V3& normal, d
 // CCD.inl:3-82 dispatch and leaves
 void Sim::find_contacts(int ia, int ib, double TOL, std::vector<Contact>& out) const {
   const Body& A = bodies[ia]; const Body& B = bodies[ib];
+  // pin joint as contacts (contact-constrained-pendulum-coldet-plugin.cpp:78-110): six contacts at the midpoint of the anchor
+  // point and the GLOBAL origin, normals +y -y +z -z +x -x, signed violation min(0, -p_k) for both normals of an axis; TOL ignored
+  if ((A.shape == SHAPE_PIN && B.shape == SHAPE_PINWORLD) || (A.shape == SHAPE_PINWORLD && B.shape == SHAPE_PIN)) {
+    const int il = (A.shape == SHAPE_PIN) ? ia : ib, iw = (A.shape == SHAPE_PIN) ? ib : ia;
+    const Body& L = bodies[il];
+    const V3 p = to_global(L, V3(L.dims[0], L.dims[1], L.dims[2]));
+    const V3 point = (p + V3(0, 0, 0)) * 0.5;
+    const double pk[3] = {p.x, p.y, p.z};
+    static const int axis[6] = {1, 1, 2, 2, 0, 0}; static const double sgn[6] = {+1, -1, +1, -1, +1, -1};
+    for (int k = 0; k < 6; k++) {
+      V3 n(0, 0, 0); n[axis[k]] = sgn[k];
+      out.push_back(create_contact(il, iw, point, n, std::min(0.0, -pk[axis[k]])));
+    }
+    return;
+  }
   // rimless wheel / plane (coldet-plugin.cpp:222-310): one candidate per spoke tip (two when W > 0); the plugin ignores
   // the caller's TOL and tests `< sim->contact_dist_thresh` (:225,:270,:283)
   if ((A.shape == SHAPE_WHEEL && B.shape == SHAPE_PLANE) || (A.shape == SHAPE_PLANE && B.shape == SHAPE_WHEEL)) {
@@ -427,7 +450,7 @@ double Sim::calc_CA_Euler_step(const PairDist& pdi) const {
     }
   }
   // :169-235 generic
-  if (pdi.dist <= 0.0 && (A.shape == SHAPE_WHEEL || B.shape == SHAPE_WHEEL)) return INF;   // coldet-plugin.cpp:214-217 overrides calc_next_CA_Euler_step
+  if (pdi.dist <= 0.0 && (A.shape == SHAPE_WHEEL || B.shape == SHAPE_WHEEL || A.shape == SHAPE_PIN || B.shape == SHAPE_PIN)) return INF;   // both plugins override calc_next_CA_Euler_step (coldet-plugin.cpp:214-217, contact-constrained-pendulum-coldet-plugin.cpp:152-155)
   if (pdi.dist <= 0.0) {
     // :238-400 bodies in contact
     std::vector<Contact> contacts;

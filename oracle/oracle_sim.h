@@ -39,7 +39,10 @@ struct V3 {
 };
 
 enum Shape { SHAPE_NONE = 0, SHAPE_SPHERE = 1, SHAPE_BOX = 2, SHAPE_PLANE = 3,
-             SHAPE_WHEEL = 4 };   // rimless wheel of example/rimless-wheel/coldet-plugin.cpp: dims = (R, W, N_SPOKES), params.h:4-6; collides with planes only
+             SHAPE_WHEEL = 4,
+             // example/contact-constrained-pendulum: a pin joint emulated by six frictionless contacts (its collision-detection plugin):
+             // SHAPE_PIN on the moving body (dims = the anchor point in its frame), SHAPE_PINWORLD on the fixed one (anchor = its origin)
+             SHAPE_PIN = 5, SHAPE_PINWORLD = 6 };   // rimless wheel of example/rimless-wheel/coldet-plugin.cpp: dims = (R, W, N_SPOKES), params.h:4-6; collides with planes only
 enum Model { MODEL_QP = 0, MODEL_AP = 1 };
 
 struct Body {

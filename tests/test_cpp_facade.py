@@ -98,7 +98,7 @@ def _check_against_python_loader(sitting_box, path):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("rel", ["simple-contact/simplest.xml", "bouncing-ball/bouncing-ball.xml", "stacks/sphere-stack.xml", "stacks/stack.xml",
-                                 "rimless-wheel/wheel.xml"])
+                                 "rimless-wheel/wheel.xml", "contact-constrained-pendulum/contact-constrained-pendulum.xml"])
 def test_cpp_xml_reader_loads_reference_scenes(sitting_box, rel):
     _check_against_python_loader(sitting_box, os.path.join(REF, rel))
 
