@@ -246,6 +246,7 @@ def _secondary(args, W, scenes, rank_seed, local_rank, flush, stream):
         sim = TimeSteppingSimulator(sc, device=local_rank)
         sim.step(DT, s_d)
         q, v = sim.get_state()
+        sim.close()
         ob = O.OracleBatch(sc)
         ob.run(DT, s_d, threads=os.cpu_count() or 1)
         qo, vo = ob.get_state_soa()
@@ -255,6 +256,66 @@ def _secondary(args, W, scenes, rank_seed, local_rank, flush, stream):
                         "max_rel_err": float(err.max()), "median_rel_err": float(np.median(err)),
                         "note": "GPU vs oracle/ from the same initial state; envs above 1e-9 ran Lemke on a singular LCP whose pivot path "
                                 "differs between the tableau and the LU-per-pivot form (tests/parity_util.py, profiles/r02_lemke_path_sensitivity.json)"}
+    return out
+
+
+def _other_workloads(local_rank, flush, stream):
+    """Rank 0, after the headline: short device-timed runs of the other BASELINE configs on rank 0's GPU, so that the one JSON
+    line the driver records also carries them (each is a full bench line of its own under --workload)."""
+    import torch
+    from moby_b200 import TimeSteppingSimulator, scenes
+    out = {}
+    steps = 10
+    try:
+        W = WORKLOADS["ur10"]
+        sc = W["make"](scenes, W["envs"], 0xB200)
+        sc.stabilization_max_iterations = 0
+        sim = TimeSteppingSimulator(sc, device=local_rank)
+        sim.step(W["dt"], W["preroll"])
+        t = _device_timed(sim, W["dt"], steps, 3, flush, stream)
+        c = sim.counters()
+        out["ur10"] = {"value": W["envs"] * steps / t, "unit": "env-steps/s", "ms_per_step": 1e3 * t / steps, "envs_per_gpu": W["envs"], "steps": steps, "n_gpus": 1,
+                       "lcp_failures": c["lcp_failures"], "workload": W["name"]}
+        sim.close()
+        names = MIX["parts"]
+        sims = []
+        for nm in names:
+            sc = WORKLOADS[nm]["make"](scenes, MIX["envs"] // len(names), 0xB200)
+            sc.stabilization_max_iterations = -1
+            sims.append(TimeSteppingSimulator(sc, device=local_rank))
+        grp = SimGroup(sims, names)
+        grp.step(MIX["dt"], MIX["preroll"])
+        t = _device_timed(grp, MIX["dt"], steps, 3, flush, stream)
+        out["mix"] = {"value": MIX["envs"] * steps / t, "unit": "env-steps/s", "ms_per_step": 1e3 * t / steps, "envs_per_gpu": MIX["envs"], "steps": steps, "n_gpus": 1,
+                      "lcp_failures": grp.counters()["lcp_failures"], "workload": MIX["name"]}
+        for sm in sims:
+            sm.close()
+        # batched Lemke solver, n = 32, operands in HBM (bench.py --workload lcp)
+        from moby_b200 import capi, lcp as L
+        n, batch = 32, 131072
+        dev = torch.device("cuda", local_rank)
+        gen = torch.Generator(device=dev); gen.manual_seed(0xB200)
+        A = torch.randn(batch, n, n, dtype=torch.float64, device=dev, generator=gen)
+        Mc = (torch.bmm(A, A.transpose(1, 2)) / n + 1e-3 * torch.eye(n, dtype=torch.float64, device=dev)).transpose(-1, -2).contiguous()
+        del A
+        q = torch.randn(batch, n, dtype=torch.float64, device=dev, generator=gen)
+        z = torch.zeros_like(q); status = torch.zeros(batch, dtype=torch.int32, device=dev); pivots = torch.zeros_like(status)
+        solve = lambda: capi.check(capi.lib().b200moby_lcp_lemke_batched(batch, n, Mc.data_ptr(), q.data_ptr(), z.data_ptr(), -1.0, -1.0, status.data_ptr(),  # noqa: E731
+                                                                          pivots.data_ptr(), None, 0, L._stream_ptr(None)))
+        for _ in range(3):
+            solve()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            solve()
+        b.record(stream)
+        torch.cuda.synchronize()
+        t = a.elapsed_time(b) * 1e-3
+        out["lcp_n32"] = {"value": batch * steps / t, "unit": "LCP solves/s", "ms_per_launch": 1e3 * t / steps, "batch": batch, "n": n,
+                          "algorithmic_GBps": 8.0 * (n * n + 2 * n) * batch * steps / t / 1e9, "solved": int(((status == 0) | (status == 1)).sum().item())}
+    except Exception as ex:                       # the headline must not be lost to a side measurement
+        out["error"] = repr(ex)
     return out
 
 
@@ -638,6 +699,8 @@ def main():
             for ps in part_sims:
                 ps.close()                   # one live simulator per GPU at a time: the secondary runs get the same schedule as the headline
             out["secondary"] = _secondary(args, W, scenes, 0xB200 + rank, local_rank, flush, stream)
+            if args.workload == "small":
+                out["secondary"]["other_workloads"] = _other_workloads(local_rank, flush, stream)
         out["stabilization"] = {"iterations_per_env_step": r_cnt["stab_iterations"] / max(r_cnt["env_steps"], 1),
                                 "lcp_solves_per_env_step": r_cnt["stab_lcp_solves"] / max(r_cnt["env_steps"], 1),
                                 "line_search_failures": r_cnt["stab_line_search_failures"]}
