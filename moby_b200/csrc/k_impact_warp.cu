@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
   int* head = q_head(P, round, slot);
   LadderCtx C; C.pool = L; C.owner = blockIdx.x * wpb + w; C.wd = m.work; C.wi = m.iwork;
   for (int i = pull_warp(head); i < count; i = pull_warp(head)) {
-    if (L.ctl) while (ladder_help_one(L, m.work, m.iwork)) {}     // rungs of a running ladder are on some env's critical path: they go before the next env
+    if (L.ctl) while (ladder_help_one(g, L, m.work, m.iwork)) {}     // rungs of a running ladder are on some env's critical path: they go before the next env
     for (int k = 0; k < CNT_COUNT; k++) lc[k] = 0;
     EnvCtx cx; cx.limit = P.pivot_budget > 0; cx.budget = P.pivot_budget;
     if (L.ctl && !cx.limit) cx.ladder = &C;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
     volatile int* fdone = feed_done;
     long long t_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     for (;;) {
-      if (L.ctl && ladder_help_one(L, m.work, m.iwork)) continue;
+      if (L.ctl && ladder_help_one(g, L, m.work, m.iwork)) continue;
       int e = -2;                                        // -2: nothing to take now, -3: the producers are done and the queue is empty
       if (g.tid == 0) {
         const int finished = *fdone >= feed_expect;      // read BEFORE the count: a count read after it is final
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) impact_warp_kernel(SimParams P, double dt
     const int total_warps = gridDim.x * wpb;
     if (g.tid == 0) { __threadfence(); atomicAdd(L.ctl + 2, 1); }
     for (;;) {
-      if (ladder_help_one(L, m.work, m.iwork)) continue;
+      if (ladder_help_one(g, L, m.work, m.iwork)) continue;
       int done = 0;
       if (g.tid == 0) { volatile int* ctl = L.ctl; done = (ctl[2] >= total_warps && ctl[1] >= min(ctl[0], L.cap)) ? 1 : 0; }
       if (__shfl_sync(0xffffffffu, done, 0)) break;

@@ -114,11 +114,14 @@ B2M_HD inline size_t lemke_work_ints(int n) { return (size_t)3 * n + 1; }
 // B columns of the rank-one update for the two rows a lane owns: all loads, then the fmas, then the stores.  The pivot
 // row is not stored here (s0 / s1 exclude it): the lanes that formed r_c wrote it already.
 template <int B>
-static __device__ __forceinline__ void lemke_update_batch(double* q0, double* q1, const double* rvec, int c, int n, double nd0, double nd1, bool s0, bool s1) {
+static __device__ __forceinline__ void lemke_update_batch(double* q0, double* q1, const double* rvec, int c, int n, double nd0, double nd1, bool s0, bool s1, bool h1) {
   double rv[B], t0[B], t1[B];
   const int cn = c * n;
+  // h1: the lane has a second row (n > 32: lanes 0 .. n-33).  The others used to re-read their first row through the clamped
+  // index, a second 256-byte wavefront pair per column for nothing: predicated off, the second-row load is one 64-byte
+  // wavefront at n = 40 (the shared-memory pipe is what the pivot loop contends for)
 #pragma unroll
-  for (int k = 0; k < B; k++) { rv[k] = rvec[c + k]; t0[k] = q0[cn + k * n]; t1[k] = q1[cn + k * n]; }
+  for (int k = 0; k < B; k++) { rv[k] = rvec[c + k]; t0[k] = q0[cn + k * n]; t1[k] = h1 ? q1[cn + k * n] : 0.0; }
 #pragma unroll
   for (int k = 0; k < B; k++) { t0[k] = fma(nd0, rv[k], t0[k]); t1[k] = fma(nd1, rv[k], t1[k]); }
 #pragma unroll
@@ -194,16 +197,16 @@ static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* 
     const double nd0 = -d0, nd1 = -d1;
     if (N) {
 #pragma unroll
-      for (int c = 0; c + 8 <= N + 2; c += 8) lemke_update_batch<8>(q0, q1, rvec, c, N, nd0, nd1, s0, s1);
-      if ((N + 2) & 4) lemke_update_batch<4>(q0, q1, rvec, (N + 2) & ~7, N, nd0, nd1, s0, s1);
-      if ((N + 2) & 2) lemke_update_batch<2>(q0, q1, rvec, (N + 2) & ~3, N, nd0, nd1, s0, s1);
-      if ((N + 2) & 1) lemke_update_batch<1>(q0, q1, rvec, (N + 2) & ~1, N, nd0, nd1, s0, s1);
+      for (int c = 0; c + 8 <= N + 2; c += 8) lemke_update_batch<8>(q0, q1, rvec, c, N, nd0, nd1, s0, s1, h1);
+      if ((N + 2) & 4) lemke_update_batch<4>(q0, q1, rvec, (N + 2) & ~7, N, nd0, nd1, s0, s1, h1);
+      if ((N + 2) & 2) lemke_update_batch<2>(q0, q1, rvec, (N + 2) & ~3, N, nd0, nd1, s0, s1, h1);
+      if ((N + 2) & 1) lemke_update_batch<1>(q0, q1, rvec, (N + 2) & ~1, N, nd0, nd1, s0, s1, h1);
     } else {
       int c = 0;
-      for (; c + 8 <= NC; c += 8) lemke_update_batch<8>(q0, q1, rvec, c, n, nd0, nd1, s0, s1);   // straight-line batches
-      if (NC & 4) { lemke_update_batch<4>(q0, q1, rvec, c, n, nd0, nd1, s0, s1); c += 4; }
-      if (NC & 2) { lemke_update_batch<2>(q0, q1, rvec, c, n, nd0, nd1, s0, s1); c += 2; }
-      if (NC & 1) lemke_update_batch<1>(q0, q1, rvec, c, n, nd0, nd1, s0, s1);
+      for (; c + 8 <= NC; c += 8) lemke_update_batch<8>(q0, q1, rvec, c, n, nd0, nd1, s0, s1, h1);   // straight-line batches
+      if (NC & 4) { lemke_update_batch<4>(q0, q1, rvec, c, n, nd0, nd1, s0, s1, h1); c += 4; }
+      if (NC & 2) { lemke_update_batch<2>(q0, q1, rvec, c, n, nd0, nd1, s0, s1, h1); c += 2; }
+      if (NC & 1) lemke_update_batch<1>(q0, q1, rvec, c, n, nd0, nd1, s0, s1, h1);
     }
     __syncwarp();
     if (!first) piv++;
@@ -395,7 +398,7 @@ template <class G>
 B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
                            int* log, int log_cap, int* log_len, int* budget = nullptr, int* executed_out = nullptr, double offdiag = -1.0,
-                           const volatile int* cancel = nullptr) {      // cancel: warp-owned loop only (ladder task pool); a cancelled run returns LCP_DEFER
+                           const volatile int* cancel = nullptr) {      // cancel: ladder task pool; a cancelled run returns LCP_DEFER
   double* T = wd;
   double* dvec = T + (size_t)n * (n + 2);
   double* rvec = dvec + n;
@@ -467,7 +470,9 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
       // enters the second one as key -1 so that it wins whenever it passes (LCP.cpp:961-975)
       double theta = B2M_INF;
       for (int i = g.tid; i < n; i += G::size) { const double d = dvec[i]; if (d > PIV_TOL) theta = fmin(theta, (xcol[i] + zero_tol) / d); }
+      if (cancel && g.tid == 0 && *cancel) theta = -B2M_INF;               // ladder task pool: the owner has its answer; the flag rides on the reduction so that the whole group leaves together
       theta = g.min(theta);
+      if (theta == -B2M_INF) { status = LCP_DEFER; break; }
       if (theta == B2M_INF) { status = LCP_RAY; break; }
       int lo = 0x7fffffff;
       const int trow = -(where[t] + 1);
@@ -496,7 +501,24 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
       int i = g.tid % n, c = g.tid / n;
       const int di = G::size % n, dc = G::size / n;
       const int total = n * (n + 2);
-      for (int e = g.tid; e < total; e += G::size) {
+      int e = g.tid;
+      if constexpr (G::size > 32) {
+        // a block's tableau lives in L2 / HBM: eight entries per thread in flight (all loads of a batch ahead of its first
+        // store), else every entry waits out one L2 round trip on its own.  Same operation per entry: bit-identical.
+        constexpr int B = 8;
+        for (; e + (B - 1) * G::size < total; e += B * G::size) {
+          double tv[B], dv[B], rv[B]; bool pr[B];
+#pragma unroll
+          for (int k = 0; k < B; k++) {
+            tv[k] = T[e + k * G::size]; dv[k] = dvec[i]; rv[k] = rvec[c]; pr[k] = (i == r);
+            i += di; c += dc;
+            if (i >= n) { i -= n; c++; }
+          }
+#pragma unroll
+          for (int k = 0; k < B; k++) T[e + k * G::size] = pr[k] ? rv[k] : fma(-dv[k], rv[k], tv[k]);
+        }
+      }
+      for (; e < total; e += G::size) {
         T[e] = (i == r) ? rvec[c] : fma(-dvec[i], rvec[c], T[e]);
         i += di; c += dc;
         if (i >= n) { i -= n; c++; }
@@ -542,7 +564,7 @@ static __device__ __forceinline__ void lu_update_batch(double* q0, double* q1, c
   double rv[B], a0[B], a1[B];
   const int ck = c * k;
 #pragma unroll
-  for (int q = 0; q < B; q++) { rv[q] = pr[ck + q * k]; a0[q] = q0[ck + q * k]; a1[q] = q1[ck + q * k]; }
+  for (int q = 0; q < B; q++) { rv[q] = pr[ck + q * k]; a0[q] = q0[ck + q * k]; a1[q] = u1 ? q1[ck + q * k] : 0.0; }   // lanes without a live second row skip its load
 #pragma unroll
   for (int q = 0; q < B; q++) { a0[q] = fma(nl0, rv[q], a0[q]); a1[q] = fma(nl1, rv[q], a1[q]); }
 #pragma unroll
@@ -1100,12 +1122,12 @@ B2M_HD inline size_t ladder_job_doubles(int nmax) { return (size_t)nmax * nmax +
 B2M_HD inline size_t ladder_job_ints() { return LJ_HDR + LJ_RW * B2M_LADDER_MAX_RUNGS; }
 struct LadderCtx { LadderPool pool; int owner; double* wd; int* wi; long long* dbg = nullptr; };    // wd / wi: this warp's Lemke work area (shared memory)
 
-// takes one task from the list and runs it; false when there was none
-static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double* wd, int* wi) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+// takes one task from the list and runs it; false when there was none.  G: the warp (WarpGroup) or the block (BlockGroup)
+// that owns the work area wd / wi.
+template <class G>
+static __device__ __noinline__ bool ladder_help_one(const G& g, const LadderPool& L, double* wd, int* wi) {
   int v = 0, tg = 0, run = 0;
-  if (lane == 0) {
+  if (g.tid == 0) {
     volatile int* ctl = L.ctl;
     for (;;) {
       const int h = ctl[1], t = min(ctl[0], L.cap);
@@ -1123,7 +1145,7 @@ static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double*
       break;
     }
   }
-  v = __shfl_sync(FULL, v, 0); run = __shfl_sync(FULL, run, 0);
+  v = g.bcast(v); run = g.bcast(run);
   if (run == 0) return false;
   if (run == 2) return true;
   const int owner = (v >> 6) - 1, rung = v & 63;
@@ -1134,12 +1156,12 @@ static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double*
   const double* M = job; const double* q = job + (size_t)L.nmax * L.nmax;
   double* zr = job + (size_t)L.nmax * L.nmax + L.nmax + (size_t)rung * L.nmax;
   const double lambda = (rung == 0) ? 0.0 : pow10i(mo[LJ_MINEXP] + (rung - 1) * mo[LJ_STEPEXP]);
-  WarpGroup g(nullptr);
   int piv = 0, ex = 0;
   const int st = lemke_solve(g, n, M, n, q, lambda, jd[0], jd[1], zr, wd, wi, &piv, nullptr, 0, nullptr, nullptr, &ex, jd[3], (const volatile int*)(mo + LJ_CANCEL));
   const bool ok = (st == LCP_OK || st == LCP_TRIVIAL) && lcp_verify(g, n, M, n, q, lambda, zr, jd[2], rung > 0, wd + (size_t)n * (n + 2));
-  __syncwarp();
-  if (lane == 0) {
+  __threadfence();                                     // every thread's part of z before the ready flag
+  g.sync();
+  if (g.tid == 0) {
     int* r = mo + LJ_HDR + LJ_RW * rung;
     r[1] = st; r[2] = ok ? 1 : 0; r[3] = piv; r[4] = ex; r[6] = b2m_now_us();
     __threadfence();
@@ -1147,23 +1169,23 @@ static __device__ __noinline__ bool ladder_help_one(const LadderPool& L, double*
     __threadfence();
     atomicSub(mo + LJ_INFLIGHT, 1);
   }
-  __syncwarp();
+  g.sync();
   return true;
 }
 
-// lcp_lemke_regularized for the warp that owns the env (g: its WarpGroup): same results and statistics as the sequential form
-static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g, const LadderCtx& C, int n, const double* M, int ldm, const double* q, double piv_tol,
+// lcp_lemke_regularized for the warp / block that owns the env (g: its group): same results and statistics as the sequential form
+template <class G>
+static __device__ __noinline__ int lcp_lemke_regularized_pool(const G& g, const LadderCtx& C, int n, const double* M, int ldm, const double* q, double piv_tol,
                                                               double zero_tol, int min_exp, int step_exp, int max_exp, double* z, int* pivots_out, long long* stats) {
-  const unsigned FULL = 0xffffffffu;
   if (n == 0) { if (pivots_out) *pivots_out = 0; return LCP_OK; }
   const LadderPool& L = C.pool;
   const double offdiag = norm_inf_offdiag(g, n, M, ldm);
   const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf_with(g, n, M, ldm, 0.0, offdiag) * B2M_NEAR_ZERO;   // :369
   int total = 0, piv = 0, ex = 0;
-  // Rung 0 here, but only for B2M_LADDER_PROBE pivots: a solve that is going to succeed is over long before that
-  // (profiles/: < 60 pivots at n = 40); one that is still pivoting is very likely circling towards the cap, and then the
-  // whole ladder -- rung 0 included, started afresh -- goes to the task list at once instead of after 1,000 pivots.
-  int probe = B2M_LADDER_PROBE;
+  // Rung 0 here, but only for B2M_LADDER_PROBE pivots (2n for the large LCPs of a block): a solve that is going to succeed is
+  // over long before that (profiles/: < 60 pivots at n = 40); one that is still pivoting is very likely circling towards the
+  // cap, and then the whole ladder -- rung 0 included, started afresh -- goes to the task list at once instead of after 1,000 pivots.
+  int probe = (G::size == 32) ? B2M_LADDER_PROBE : max(B2M_LADDER_PROBE, 2 * n);
   int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, C.wd, C.wi, &piv, nullptr, 0, nullptr, &probe, &ex, offdiag);
   int first_rung = 1;
   if (st == LCP_DEFER) first_rung = 0;
@@ -1177,12 +1199,13 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
   }
   int n_rungs = 1;
   for (int rf = min_exp; rf < max_exp && n_rungs < B2M_LADDER_MAX_RUNGS; rf += step_exp) n_rungs++;
-  if (n_rungs == 1 && first_rung == 1) { if (pivots_out) *pivots_out = total; for (int i = g.tid; i < n; i += 32) z[i] = 0.0; g.sync(); return LCP_UNVERIFIED; }
-  // the job: wait until no task of this warp's previous request is running, then publish (M, q) and the rungs
+  if (n_rungs == 1 && first_rung == 1) { if (pivots_out) *pivots_out = total; for (int i = g.tid; i < n; i += G::size) z[i] = 0.0; g.sync(); return LCP_UNVERIFIED; }
+  // the job: wait until no task of this owner's previous request is running, then publish (M, q) and the rungs
   int* mo = L.meta + (size_t)C.owner * L.meta_stride;
   double* job = L.jobs + (size_t)C.owner * L.job_stride;
   double* jd = L.jobd + (size_t)C.owner * 4;
   int gen = 0;
+  g.sync();
   if (g.tid == 0) {
     while (((volatile int*)mo)[LJ_INFLIGHT] != 0) __nanosleep(100);
     gen = mo[LJ_GEN] + 1;
@@ -1192,8 +1215,8 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
     for (int k = first_rung; k < n_rungs; k++) mo[LJ_HDR + LJ_RW * k] = 0;
   }
   g.sync();
-  for (int e = g.tid; e < n * n; e += 32) { const int c = e / n, r = e - c * n; job[e] = M[(size_t)c * ldm + r]; }
-  for (int i = g.tid; i < n; i += 32) job[(size_t)L.nmax * L.nmax + i] = q[i];
+  for (int e = g.tid; e < n * n; e += G::size) { const int c = e / n, r = e - c * n; job[e] = M[(size_t)c * ldm + r]; }
+  for (int i = g.tid; i < n; i += G::size) job[(size_t)L.nmax * L.nmax + i] = q[i];
   __threadfence();
   g.sync();
   int posted = 0;
@@ -1211,7 +1234,7 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
       }
     }
   }
-  posted = __shfl_sync(FULL, posted, 0);
+  posted = g.bcast(posted);
   int result = LCP_UNVERIFIED;
   if (!posted) {                                          // task list full: the remaining rungs one after the other, as the generic wrapper does
     if (first_rung == 0) {
@@ -1236,9 +1259,9 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
     for (;;) {
       int ready = 0;
       if (g.tid == 0) ready = r[0];
-      ready = __shfl_sync(FULL, ready, 0);
+      ready = g.bcast(ready);
       if (ready == 1) break;
-      if (ready == 2 || !ladder_help_one(L, C.wd, C.wi)) __nanosleep(200);      // somebody is on it: wait; not taken yet: take tasks (maybe this one)
+      if (ready == 2 || !ladder_help_one(g, L, C.wd, C.wi)) __nanosleep(200);      // somebody is on it: wait; not taken yet: take tasks (maybe this one)
     }
     __threadfence();
     const int pk = r[3], ek = r[4], okk = r[2];
@@ -1253,15 +1276,16 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const WarpGroup& g
     if (stats && g.tid == 0) { stats[0]++; stats[1] += pk; stats[2] += ek; }
     if (okk) {
       const double* zr = job + (size_t)L.nmax * L.nmax + L.nmax + (size_t)k * L.nmax;
-      for (int i = g.tid; i < n; i += 32) z[i] = ((const volatile double*)zr)[i];
+      for (int i = g.tid; i < n; i += G::size) z[i] = ((const volatile double*)zr)[i];
       result = (k == 0) ? r[1] : LCP_REGULARIZED + (k - 1);
       if (k == 0) total = pk;                           // the wrapper reports the first solve's own count when it is accepted (:252-255)
       break;
     }
   }
+  g.sync();
   if (g.tid == 0) { ((volatile int*)mo)[LJ_CANCEL] = 1; __threadfence(); }
   if (pivots_out) *pivots_out = total;
-  if (result == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += 32) z[i] = 0.0; }
+  if (result == LCP_UNVERIFIED) { for (int i = g.tid; i < n; i += G::size) z[i] = 0.0; }
   g.sync();
   return result;
 }

@@ -1463,7 +1463,7 @@ B2M_DEV B2M_NOINL bool solve_qp(const G& g, const SimParams& P, int e, EnvMem& m
     stats[0] = stats[1] = stats[2] = 0;
     { B2M_PROF_T0(m);
 #ifdef __CUDACC__
-      if constexpr (G::size == 32) {
+      if constexpr (G::size >= 32) {
         if (cx.ladder) {
           LadderCtx LC = *(const LadderCtx*)cx.ladder;
           if (m.prof && P.tap_times) LC.dbg = m.dbg;

@@ -328,9 +328,11 @@ b200moby_status plan_launch(b200moby_sim* h) {
       if (env_int("B200MOBY_PLAN_DEBUG", 0)) fprintf(stderr, "[b200moby] hard/straggler plan: threads %d wpb %d grid %d (%d SMs) shmem %zu\n", sg.threads, sg.wpb, sg.grid, sms, sg.shmem); }
     // the Lemke ladder as a task pool: one job buffer per warp of the hard-queue / straggler launches
     memset(&h->pool, 0, sizeof(h->pool));
-    if (sg.threads == 32 && !sg.gscratch && h->nmax <= 64 && h->P.model == 0 && env_int("B200MOBY_LADDER", 1) != 0) {
+    // (warp per env, n <= 64) or one per block (n in the hundreds: 0.9 MB per block at n = 320)
+    const bool warp_pool = sg.threads == 32 && !sg.gscratch && h->nmax <= 64, block_pool = sg.threads != 32 && h->nmax > 64;
+    if ((warp_pool || block_pool) && h->P.model == 0 && env_int("B200MOBY_LADDER", 1) != 0) {
       LadderPool& L = h->pool;
-      h->pool_owners = sg.grid * sg.wpb;
+      h->pool_owners = sg.threads == 32 ? sg.grid * sg.wpb : sg.grid;
       L.nmax = h->nmax; L.cap = h->pool_owners * 64;
       L.job_stride = ladder_job_doubles(h->nmax); L.meta_stride = ladder_job_ints();
       b200moby_status s2;
@@ -411,7 +413,13 @@ b200moby_status launch_impact(b200moby_sim* h, int kslot, const ClassPlan& cp, S
     void* a[] = {&Pk, &dt, &r, &slot, &wpb, &L, &feed_slot, &feed_done, &feed_expect};
     return timed_launch(h, kslot, b2m_k_impact_warp(), dim3(cp.grid), dim3(cp.wpb * 32), a, cp.shmem, sc);
   }
-  void* a[] = {&Pk, &dt, &r, &slot};
+  LadderPool L; memset(&L, 0, sizeof(L));
+  if (pool && h->pool.ctl && h->straggler.threads == cp.threads && cp.grid <= h->pool_owners) {
+    L = h->pool;
+    B2M_CUDA(cudaMemsetAsync(L.ctl, 0, sizeof(int) * 4, sc));
+    B2M_CUDA(cudaMemsetAsync(L.tasks, 0, sizeof(int) * L.cap, sc));
+  }
+  void* a[] = {&Pk, &dt, &r, &slot, &L};
   return timed_launch(h, kslot, impact_block_ptr(cp.threads), dim3(cp.grid), dim3(cp.threads), a, cp.shmem, sc);
 }
 
