@@ -394,6 +394,35 @@ static __device__ __forceinline__ int lemke_loop_warp_n(int n, double* T, double
 // 1,024 envs x 300 steps of configs[1] the literal run left such "cycles" through rounding 1,268 pivots before the cap
 // (same final states, different pivot counts), while a bit-exact variant (recurrence of the tracked state AND of every
 // tableau entry's bits) never fired once.  So the solver is literal: it pivots until the reference would stop.
+#ifdef __CUDACC__
+// Rank-one update of a block-owned tableau that lives in global memory (L2): eight entries per thread in flight, all 24
+// loads of a batch ahead of its first fma / store.  The pointer is declared global to the compiler: with generic loads it
+// assumes shared-memory latency and interleaves each entry's fma with the next entry's loads, which serialises a batch into
+// eight L2 round trips (profiles/r02_ncu_stacks_block_hotspots.txt).  Same operation per entry: bit-identical.  Returns
+// the first entry index left for the caller's tail loop and advances (i, c) with it.
+template <int NT>
+static __device__ __forceinline__ int lemke_update_block_global(double* T, int n, int r, int e, int& i, int& c) {
+  __builtin_assume(__isGlobal(T));
+  const double* dvec = T + (size_t)n * (n + 2);
+  const double* rvec = dvec + n;
+  const int di = NT % n, dc = NT / n;
+  const int total = n * (n + 2);
+  constexpr int B = 8;
+  for (; e + (B - 1) * NT < total; e += B * NT) {
+    double tv[B], dv[B], rv[B]; bool pr[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+      tv[k] = T[e + k * NT]; dv[k] = dvec[i]; rv[k] = rvec[c]; pr[k] = (i == r);
+      i += di; c += dc;
+      if (i >= n) { i -= n; c++; }
+    }
+#pragma unroll
+    for (int k = 0; k < B; k++) T[e + k * NT] = pr[k] ? rv[k] : fma(-dv[k], rv[k], tv[k]);
+  }
+  return e;
+}
+#endif
+
 template <class G>
 B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, const double* q, double lambda,
                            double piv_tol, double zero_tol, double* z, double* wd, int* wi, int* pivots_out,
@@ -502,22 +531,11 @@ B2M_DEV B2M_NOINL int lemke_solve(const G& g, int n, const double* M, int ldm, c
       const int di = G::size % n, dc = G::size / n;
       const int total = n * (n + 2);
       int e = g.tid;
+#ifdef __CUDACC__
       if constexpr (G::size > 32) {
-        // a block's tableau lives in L2 / HBM: eight entries per thread in flight (all loads of a batch ahead of its first
-        // store), else every entry waits out one L2 round trip on its own.  Same operation per entry: bit-identical.
-        constexpr int B = 8;
-        for (; e + (B - 1) * G::size < total; e += B * G::size) {
-          double tv[B], dv[B], rv[B]; bool pr[B];
-#pragma unroll
-          for (int k = 0; k < B; k++) {
-            tv[k] = T[e + k * G::size]; dv[k] = dvec[i]; rv[k] = rvec[c]; pr[k] = (i == r);
-            i += di; c += dc;
-            if (i >= n) { i -= n; c++; }
-          }
-#pragma unroll
-          for (int k = 0; k < B; k++) T[e + k * G::size] = pr[k] ? rv[k] : fma(-dv[k], rv[k], tv[k]);
-        }
+        if (__isGlobal(T)) e = lemke_update_block_global<G::size>(T, n, r, e, i, c);     // n in the hundreds: the tableau is in global scratch (L2)
       }
+#endif
       for (; e < total; e += G::size) {
         T[e] = (i == r) ? rvec[c] : fma(-dvec[i], rvec[c], T[e]);
         i += di; c += dc;
@@ -705,6 +723,44 @@ B2M_DEV B2M_NOINL inline bool lu_solve_serial(int k, double* A, int lda, double*
   return true;
 }
 
+#ifdef __CUDACC__
+// Trailing update of column step j of a block-owned LU in global memory: A[c][i] -= l_i * A[c][j] for i, c > j, the (k - j - 1)^2
+// entries spread over all NT threads (column-major walk: coalesced), eight entries per thread in flight.  One row per thread
+// with a dependent column loop left most of the block idle and paid one L2 round trip per entry (the lcp_fast phase of the
+// n = 320 stacks: profiles/r02_stacks_profile_*).  Same fma per entry: bit-identical.
+template <int NT>
+static __device__ __forceinline__ void lu_trailing_update_block_global(double* A, int k, int j, int tid) {
+  __builtin_assume(__isGlobal(A));
+  const int m = k - j - 1;
+  if (m <= 0) return;
+  double* base = A + (size_t)(j + 1) * k + (j + 1);              // entry (ii, cc) at base[cc * k + ii]
+  const double* prow = A + (size_t)(j + 1) * k + j;              // pivot-row entry of column cc at prow[cc * k]
+  const double* lcol = A + (size_t)j * k + (j + 1);              // multiplier of row ii
+  int ii = tid % m, cc = tid / m;
+  const int di = NT % m, dc = NT / m;
+  const int total = m * m;
+  constexpr int B = 8;
+  int e = tid;
+  for (; e + (B - 1) * NT < total; e += B * NT) {
+    double a[B], l[B], pv[B]; int off[B];
+#pragma unroll
+    for (int q = 0; q < B; q++) {
+      off[q] = cc * k + ii; a[q] = base[off[q]]; l[q] = lcol[ii]; pv[q] = prow[cc * k];
+      ii += di; cc += dc;
+      if (ii >= m) { ii -= m; cc++; }
+    }
+#pragma unroll
+    for (int q = 0; q < B; q++) base[off[q]] = fma(-l[q], pv[q], a[q]);
+  }
+  for (; e < total; e += NT) {
+    const int o = cc * k + ii;
+    base[o] = fma(-lcol[ii], prow[cc * k], base[o]);
+    ii += di; cc += dc;
+    if (ii >= m) { ii -= m; cc++; }
+  }
+}
+#endif
+
 template <class G>
 B2M_DEV B2M_NOINL bool lu_solve(const G& g, int k, double* A, double* b) {
   if constexpr (G::size == 1) return lu_solve_serial(k, A, k, b);
@@ -723,6 +779,21 @@ B2M_DEV B2M_NOINL bool lu_solve(const G& g, int k, double* A, double* b) {
     g.sync();
     const double rinv = 1.0 / A[(size_t)j * k + j];
     const double bj = b[j];
+#ifdef __CUDACC__
+    if constexpr (G::size > 32) {
+      if (__isGlobal(A)) {                                      // a block's sub-system in global scratch (n in the hundreds): multipliers first, then the
+        for (int i = j + 1 + g.tid; i < k; i += G::size) {      // trailing block entry by entry over all threads instead of one row per thread
+          const double l = A[(size_t)j * k + i] * rinv;
+          A[(size_t)j * k + i] = l;
+          b[i] = fma(-l, bj, b[i]);
+        }
+        g.sync();
+        lu_trailing_update_block_global<G::size>(A, k, j, g.tid);
+        g.sync();
+        continue;
+      }
+    }
+#endif
     for (int i = j + 1 + g.tid; i < k; i += G::size) {
       const double l = A[(size_t)j * k + i] * rinv;
       A[(size_t)j * k + i] = l;
