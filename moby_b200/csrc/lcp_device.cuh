@@ -1253,10 +1253,10 @@ static __device__ __noinline__ int lcp_lemke_regularized_pool(const G& g, const 
   const double offdiag = norm_inf_offdiag(g, n, M, ldm);
   const double ZERO_TOL = (zero_tol > 0.0) ? zero_tol : n * norm_inf_with(g, n, M, ldm, 0.0, offdiag) * B2M_NEAR_ZERO;   // :369
   int total = 0, piv = 0, ex = 0;
-  // Rung 0 here, but only for B2M_LADDER_PROBE pivots (2n for the large LCPs of a block): a solve that is going to succeed is
+  // Rung 0 here, but only for B2M_LADDER_PROBE pivots: a solve that is going to succeed is
   // over long before that (profiles/: < 60 pivots at n = 40); one that is still pivoting is very likely circling towards the
   // cap, and then the whole ladder -- rung 0 included, started afresh -- goes to the task list at once instead of after 1,000 pivots.
-  int probe = (G::size == 32) ? B2M_LADDER_PROBE : max(B2M_LADDER_PROBE, 2 * n);
+  int probe = B2M_LADDER_PROBE;
   int st = lemke_solve(g, n, M, ldm, q, 0.0, piv_tol, zero_tol, z, C.wd, C.wi, &piv, nullptr, 0, nullptr, &probe, &ex, offdiag);
   int first_rung = 1;
   if (st == LCP_DEFER) first_rung = 0;

@@ -322,7 +322,10 @@ b200moby_status plan_launch(b200moby_sim* h) {
     // the worst env's chain takes 16 ms on a lone warp and 6.7 ms on a 256-thread block
     sg.nmax = h->nmax; sg.cmax = h->cmax; sg.threads = env_int("B200MOBY_STRAGGLER_THREADS", h->nmax > big_n ? 256 : (h->nmax <= 64 ? 32 : 128));   // n <= 64: the warp-owned pivot loops (lcp_device.cuh), no block barriers   // n = 320 stack LCPs: 2.0 s (256) against 4.3 s (128) per step of 256 envs
     if (sg.threads != 32 && sg.threads != 64 && sg.threads != 128) sg.threads = 256;
-    if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, ne)) != B200MOBY_OK) return st;
+    // block per env with the Lemke ladder's rungs as tasks (n in the hundreds): a full grid even for a small batch, the blocks
+    // without an env of their own take rungs
+    const int sg_work = (sg.threads != 32 && h->nmax > 64 && h->P.model == 0 && env_int("B200MOBY_LADDER", 1) != 0) ? std::max(ne, sms * 8) : ne;
+    if ((st = plan_memory(h, sg.threads == 32 ? b2m_k_impact_warp() : impact_block_ptr(sg.threads), sg, 4, sg_work)) != B200MOBY_OK) return st;
     { const int cap = env_int("B200MOBY_HARD_BLOCKS_PER_SM", h->any_subwarp_class ? 1 : 0);      // experiment knob: fewer resident warps of the hard-queue launch per SM (less contention for the shared-memory pipe)
       if (cap > 0 && sg.grid > sms * cap) sg.grid = sms * cap;
       if (env_int("B200MOBY_PLAN_DEBUG", 0)) fprintf(stderr, "[b200moby] hard/straggler plan: threads %d wpb %d grid %d (%d SMs) shmem %zu\n", sg.threads, sg.wpb, sg.grid, sms, sg.shmem); }
