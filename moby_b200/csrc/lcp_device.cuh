@@ -134,6 +134,7 @@ template <bool SH, int N>
 static __device__ __noinline__ int lemke_loop_warp(int n_rt, double* T, double* rvec, int* where, int* bas, double PIV_TOL, double zero_tol, int r,
                                                    int* log, int log_cap, int& nlog_io, int& piv_io, int& executed_io, int* budget, const volatile int* cancel) {
   if (SH) { __builtin_assume(__isShared(T)); __builtin_assume(__isShared(rvec)); __builtin_assume(__isShared(where)); __builtin_assume(__isShared(bas)); }
+  else { __builtin_assume(__isGlobal(T)); __builtin_assume(__isGlobal(rvec)); }     // global scratch: LDG / STG, scheduled for L2 latency (generic loads are scheduled as if shared)
   const int n = N ? N : n_rt;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -591,6 +592,7 @@ static __device__ __forceinline__ void lu_update_batch(double* q0, double* q1, c
 template <bool SH>
 static __device__ __noinline__ bool lu_solve_warp(int k, double* A, double* b) {
   if (SH) { __builtin_assume(__isShared(A)); __builtin_assume(__isShared(b)); }
+  else { __builtin_assume(__isGlobal(A)); }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int i0 = lane, i1 = lane + 32;
