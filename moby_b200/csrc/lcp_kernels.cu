@@ -11,6 +11,8 @@
 #include "../../include/b200moby.h"
 #include "host_util.h"
 #include "lcp_device.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 using namespace b2m;
 
@@ -117,6 +119,131 @@ __global__ void __launch_bounds__(256) lcp_block_kernel(LcpArgs a) {
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) solve_one(g, a, b, wd, wi);
 }
 
+// ---- Lemke for n in the hundreds: the tableau in the distributed shared memory of an 8-CTA cluster ----------------------
+// (SURVEY 7.4 option (i).)  At n = 320 the tableau is 0.82 MB: a block that keeps it in global scratch moves 1.64 MB through L2
+// per pivot (29 us alone, 110 us when every SM does it).  Here CTA k of a cluster owns the columns [k W, (k + 1) W) of the
+// column-major tableau in its own shared memory (W = ceil((n + 2) / 8): 105 KB at n = 320) and updates only those.  Per pivot
+// every CTA copies the entering column and the x column from their owners through DSMEM, then runs the ratio test and the basis
+// bookkeeping REDUNDANTLY on its private copies -- all CTAs reach the same pivot row without a cross-CTA reduction -- scales its
+// own slice of the pivot row and updates its own columns.  Two cluster barriers per pivot: after the remote reads (the owner
+// is about to overwrite the entering column) and after the update.  Same arithmetic per entry as lemke_solve: bit-identical
+// results, pivots and pivot log.
+#define B2M_CL 8
+__global__ void __launch_bounds__(256) lcp_cluster_kernel(LcpArgs a, int W) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red[4 * 8 + 4];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int n = a.n, t = 2 * n, tid = threadIdx.x;
+  BlockGroup<256> g(red);
+  double* Tl = (double*)smem;                       // own columns, column-major, n rows each
+  double* dvec = Tl + (size_t)W * n;
+  double* xl = dvec + n;                            // private copy of the x column
+  double* rl = xl + n;                              // own slice of the scaled pivot row
+  int* where = (int*)(rl + W);
+  int* bas = where + 2 * n + 1;
+  const int c0 = rank * W, c1 = min(c0 + W, n + 2), nown = max(c1 - c0, 0);
+  const int xo = (n + 1) / W, xc = (n + 1) - xo * W;            // owner and local index of the x column
+  const int n_clusters = gridDim.x / B2M_CL;
+  const int MAXITER = min(1000, 50 * n);
+  for (int b = blockIdx.x / B2M_CL; b < a.batch; b += n_clusters) {
+    const double* M = a.M + (size_t)b * n * n;
+    const double* q = a.q + (size_t)b * n;
+    double* z = a.z + (size_t)b * n;
+    int* logp = a.log ? a.log + (size_t)b * a.log_cap : nullptr;
+    int nlog = 0, piv = 0, status = LCP_OK;
+    const double nrm = norm_inf_with(g, n, M, n, 0.0, -1.0);
+    const double zero_tol = (a.zero_tol > 0.0) ? a.zero_tol : B2M_EPS * nrm * n;
+    const double PIV_TOL = (a.piv_tol > 0.0) ? a.piv_tol : B2M_EPS * n * fmax(1.0, nrm);
+    double mq = B2M_INF;
+    for (int i = tid; i < n; i += 256) mq = fmin(mq, q[i]);
+    mq = g.min(mq);
+    if (rank == 0) for (int i = tid; i < n; i += 256) z[i] = 0.0;
+    bool done = false;
+    if (mq > -zero_tol) { status = LCP_TRIVIAL; done = true; }
+    else if (!(mq < 0.0)) { status = LCP_OK; done = true; }
+    if (!done) {
+      for (int e = tid; e < nown * n; e += 256) {
+        const int cl = e / n, i = e - cl * n, c = c0 + cl;
+        double v;
+        if (c < n) { const double mv = M[(size_t)c * n + i]; v = -((c == i) ? mv + 0.0 : mv); }      // as m_at with lambda = 0 (the diagonal takes the addition)
+        else if (c == n) v = (q[i] < 0.0) ? -1.0 : 0.0;
+        else v = q[i];
+        Tl[e] = v;
+      }
+      for (int i = tid; i < n; i += 256) { xl[i] = q[i]; where[i] = i; where[n + i] = -(i + 1); bas[i] = n + i; }
+      if (tid == 0) where[t] = n;
+      __syncthreads();
+      int r; { double key = B2M_INF; int idx = 0x7fffffff;
+        for (int i = tid; i < n; i += 256) { const double x = xl[i]; if (x < key) { key = x; idx = i; } }
+        g.min_key_idx(key, idx); r = idx; }
+      int s = n, entering = t;
+      bool first = true;
+      cluster.sync();                                             // every CTA's columns are in place
+      for (;;) {
+        { const int so = s / W;
+          const double* src = cluster.map_shared_rank(Tl, so) + (size_t)(s - so * W) * n;
+          const double* xs = cluster.map_shared_rank(Tl, xo) + (size_t)xc * n;
+          for (int i = tid; i < n; i += 256) { dvec[i] = src[i]; xl[i] = xs[i]; } }
+        cluster.sync();                                           // remote reads done: the owners may overwrite these columns
+        if (!first) {
+          double theta = B2M_INF;
+          for (int i = tid; i < n; i += 256) { const double d = dvec[i]; if (d > PIV_TOL) theta = fmin(theta, (xl[i] + zero_tol) / d); }
+          theta = g.min(theta);
+          if (theta == B2M_INF) { status = LCP_RAY; break; }
+          int lo = 0x7fffffff;
+          const int trow = -(where[t] + 1);
+          for (int i = tid; i < n; i += 256) {
+            const double d = dvec[i];
+            if (d > PIV_TOL && xl[i] / d <= theta) { const int key = (i == trow) ? -1 : i; if (key < lo) lo = key; }
+          }
+          lo = g.min(lo);
+          if (lo == 0x7fffffff) { status = LCP_EMPTY_RATIO; break; }
+          r = (lo < 0) ? trow : lo;
+        }
+        const int leaving = bas[r];
+        const double p = dvec[r];
+        __syncthreads();
+        for (int cl = tid; cl < nown; cl += 256) { const int c = c0 + cl; rl[cl] = (c == s) ? 1.0 / p : Tl[(size_t)cl * n + r] / p; }
+        if (s >= c0 && s < c1) for (int i = tid; i < n; i += 256) Tl[(size_t)(s - c0) * n + i] = 0.0;
+        if (tid == 0) {
+          if (rank == 0 && logp && nlog < a.log_cap) logp[nlog] = leaving;
+          where[entering] = -(r + 1); where[leaving] = s; bas[r] = entering;
+        }
+        nlog++;
+        __syncthreads();
+        {
+          int i = tid % n, cl = tid / n;
+          const int di = 256 % n, dc = 256 / n;
+          const int total = nown * n;
+          for (int e = tid; e < total; e += 256) {
+            Tl[e] = (i == r) ? rl[cl] : fma(-dvec[i], rl[cl], Tl[e]);
+            i += di; cl += dc;
+            if (i >= n) { i -= n; cl++; }
+          }
+        }
+        cluster.sync();                                           // the update is visible to the next pivot's remote reads
+        if (!first) piv++;
+        first = false;
+        if (leaving == t) break;
+        if (piv >= MAXITER) { status = LCP_MAXITER; break; }
+        entering = (leaving < n) ? n + leaving : leaving - n;
+        s = where[entering];
+      }
+      if (status == LCP_OK && rank == xo) {
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) { const int bb = bas[i]; if (bb < n) z[bb] = Tl[(size_t)xc * n + i]; }
+      }
+    }
+    if (rank == 0 && tid == 0) {
+      a.status[b] = status;
+      if (a.pivots) a.pivots[b] = piv;
+      if (logp && nlog < a.log_cap) logp[nlog] = -1;
+    }
+    cluster.sync();                                               // nobody starts the next problem while a neighbour still reads this one
+  }
+}
+
 // self-test of b2m_divn (common.cuh): q = the lock-step division, qref = the compiler's `/`, four pairs per thread
 __global__ void div_selftest_kernel(int n, const double* x, const double* y, double* q, double* qref) {
   const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
@@ -126,6 +253,12 @@ __global__ void div_selftest_kernel(int n, const double* x, const double* y, dou
   b2m_divn<4>(xs, ys, qs);
   for (int k = 0; k < 4; k++) { q[i + k] = qs[k]; qref[i + k] = xs[k] / ys[k]; }
 }
+
+size_t cluster_smem(int n) {
+  const size_t W = (n + 2 + B2M_CL - 1) / B2M_CL;
+  return (W * n + 2 * (size_t)n + W) * sizeof(double) + ((size_t)3 * n + 2) * sizeof(int);
+}
+bool cluster_fits(int n) { return n >= 16 && cluster_smem(n) <= 227 * 1024 - 2048; }
 
 b200moby_status launch(LcpArgs a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -174,6 +307,22 @@ b200moby_status launch(LcpArgs a, void* stream_) {
     const int need = (a.batch + wpb - 1) / wpb;
     const int grid = std::min(need, sms * per_sm);
     lcp_warp_kernel<<<grid, wpb * 32, shmem, stream>>>(a, wpb, wd, wi);
+    B2M_CUDA(cudaGetLastError());
+  } else if (a.mode == MODE_LEMKE && cluster_fits(a.n) && !(getenv("B200MOBY_LCP_CLUSTER") && atoi(getenv("B200MOBY_LCP_CLUSTER")) == 0)) {
+    // tableau in the distributed shared memory of an 8-CTA cluster
+    int W = (a.n + 2 + B2M_CL - 1) / B2M_CL;
+    const size_t shmem = cluster_smem(a.n);
+    B2M_CUDA(cudaFuncSetAttribute(lcp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = B2M_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = shmem; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(B2M_CL);
+    int max_clusters = 0;
+    B2M_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, lcp_cluster_kernel, &cfg));
+    if (max_clusters < 1) max_clusters = 1;
+    cfg.gridDim = dim3(B2M_CL * std::min(a.batch, max_clusters));
+    B2M_CUDA(cudaLaunchKernelEx(&cfg, lcp_cluster_kernel, a, W));
     B2M_CUDA(cudaGetLastError());
   } else {
     const int grid = std::min(a.batch, sms * 2);

@@ -26,7 +26,7 @@ def _log_list(row):
     return row[:row.index(-1)] if -1 in row else row
 
 
-@pytest.mark.parametrize("n,batch", [(1, 8), (3, 64), (8, 256), (24, 128), (40, 128), (96, 48), (200, 6)])
+@pytest.mark.parametrize("n,batch", [(1, 8), (3, 64), (8, 256), (24, 128), (40, 128), (96, 48), (200, 6), (320, 3)])
 def test_lemke_matches_oracle(torch_cuda, oracle, n, batch):
     """Tableau Lemke vs the oracle's LU-per-pivot Lemke: same leaving-variable sequence on tie-free well-conditioned
     problems, z within 1e-9 relative."""
@@ -148,6 +148,31 @@ def test_host_forms_and_block_path(torch_cuda, oracle):
         assert ok == (st[b] in (0, 1)) and st[b] == info["status"] and piv[b] == info["pivots"]
         if ok:
             assert np.array_equal(z[b], zo)
+
+
+@pytest.mark.parametrize("n,batch", [(170, 5), (200, 40), (320, 50), (401, 3)])
+def test_cluster_tableau_matches_block_path(torch_cuda, n, batch):
+    """n in the hundreds: the Lemke tableau in the distributed shared memory of an 8-CTA cluster (lcp_cluster_kernel) against
+    the block-per-LCP kernel that keeps it in global scratch (B200MOBY_LCP_CLUSTER=0): z, status, pivot count and the whole
+    pivot log bit for bit; more problems than resident clusters, an n that is not a multiple of the cluster size, and
+    problems that end on a ray (q < 0 against a matrix with a zero row)."""
+    import os
+    torch = torch_cuda
+    from moby_b200.lcp import LCP
+    M, q = random_batch(batch, n, seed=77 + n)
+    M[1, 3, :] = 0.0; M[1, :, 3] = 0.0; q[1, 3] = -1.0            # no z can lift w_3 = q_3 < 0: the solve cannot succeed
+    cap = 50 * n + 8
+    res = []
+    for val in ("1", "0"):
+        os.environ["B200MOBY_LCP_CLUSTER"] = val
+        try:
+            z, st, piv, log = LCP(log_cap=cap).lcp_lemke(_dev(torch, M), _dev(torch, q))
+            res.append((z.cpu().numpy(), st.cpu().numpy(), piv.cpu().numpy(), log.cpu().numpy()))
+        finally:
+            del os.environ["B200MOBY_LCP_CLUSTER"]
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y)
+    assert res[0][1][1] not in (0, 1) and (res[0][1][[0, 2]] == 0).all()
 
 
 def test_empty_and_ragged(torch_cuda):
