@@ -35,7 +35,7 @@ WORKLOADS = {
                   envs=65536, dt=1e-3, preroll=300, bytes=208.0, cpu_sample=(512, 40), ref_sample=4096,
                   make=lambda sc, ne, seed: sc.small_lcp_batch(ne, seed=seed)),
     "stacks": dict(name="example/stacks: 10-box stack, 4,096 envs per GPU, LCP n = 320 (BASELINE configs[2]; SURVEY 8d case 3)",
-                   envs=4096, dt=1e-3, preroll=2, bytes=2080.0, cpu_sample=(2, 1), ref_sample=16,
+                   envs=4096, dt=1e-3, preroll=2, bytes=2080.0, cpu_sample=(2, 1), ref_sample=16, cpu_limit_s=60,
                    make=lambda sc, ne, seed: sc.box_stack(ne, 10, seed=seed)),
     "ur10": dict(name="example/ur10 arm (9-DoF RCArticulatedBody, CRB forward dynamics) + block + table, mu = 100 as ur10.xml:20 (no-slip impact model), "
                       "16,384 envs per GPU (BASELINE configs[3]; SURVEY 8d case 4)",
@@ -184,6 +184,29 @@ def _cpu_baseline(scene, q, v, joints, dt, n_envs, n_steps, threads):
     c = batch.run(dt, n_steps, threads=threads)
     el = time.perf_counter() - t0
     return c["env_steps"] / el, c["lcp_solves"] / el, el, c
+
+
+def _cpu_baseline_bounded(limit_s, *a):
+    """_cpu_baseline in a forked child with a wall-clock limit (the oracle is CPU-only code: the child never touches CUDA).
+    Degenerate n = 320 stack LCPs can cost the LU-per-pivot CPU solver minutes per env-step; past the limit the child is killed
+    (by its own PID) and the sample's rate is reported as an upper bound: (env-steps asked for) / limit."""
+    if not limit_s:
+        return _cpu_baseline(*a) + (False,)
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    qd = ctx.Queue()
+
+    def work():
+        qd.put(_cpu_baseline(*a))
+    pr = ctx.Process(target=work)
+    pr.start()
+    pr.join(limit_s)
+    if pr.is_alive():
+        pr.kill()
+        pr.join()
+        n_envs, n_steps = a[5], a[6]
+        return n_envs * n_steps / limit_s, float("nan"), float(limit_s), {}, True
+    return qd.get() + (False,)
 
 
 def _stab_iters(args):
@@ -708,12 +731,14 @@ def main():
             cores = os.cpu_count() or 1
             tot = {1: [0.0, 0.0, 0.0], cores: [0.0, 0.0, 0.0]}        # env-steps, LCP solves, seconds
             desc = []
+            bounded = False
             for nm, sc, n_i, ((q0, v0), j0) in zip(names, part_scenes, sizes, state0):
                 n_cpu, s_cpu = WORKLOADS[nm]["cpu_sample"]
                 n_cpu = min(n_cpu, n_i)
                 for thr, n_s in ((1, n_cpu), (cores, min(n_cpu * 4, n_i))):
-                    val, lps, el, _ = _cpu_baseline(sc, q0, v0, j0, DT, n_s, s_cpu, thr)
-                    tot[thr][0] += val * el; tot[thr][1] += lps * el; tot[thr][2] += el
+                    val, lps, el, _, capped = _cpu_baseline_bounded(WORKLOADS[nm].get("cpu_limit_s"), sc, q0, v0, j0, DT, n_s, s_cpu, thr)
+                    bounded = bounded or capped
+                    tot[thr][0] += val * el; tot[thr][1] += (0.0 if capped else lps * el); tot[thr][2] += el
                 desc.append(f"first {n_cpu} {nm} envs" if len(names) > 1 else f"first {n_cpu} envs")
             out["cpu_baseline"] = {"value": tot[1][0] / tot[1][2], "unit": "env-steps/s", "cores": 1, "kind": "port",
                                    "sample": f"{' + '.join(desc)} of rank 0's batch from the same pre-rolled state, {s_cpu} steps, "
@@ -721,6 +746,8 @@ def main():
                                    "lcp_solves_per_s": tot[1][1] / tot[1][2],
                                    "all_cores": {"value": tot[cores][0] / tot[cores][2], "cores": cores,
                                                  "sample": f"4x the envs, {s_cpu} steps ({tot[cores][2]:.1f} s)"}}
+            if bounded:
+                out["cpu_baseline"]["upper_bound"] = "a sample hit its wall-clock limit and was stopped: its rate enters as (env-steps asked for) / limit, so the values are upper bounds"
         guard.emit(out)
     if world > 1:
         dist.destroy_process_group()
