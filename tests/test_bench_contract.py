@@ -38,3 +38,17 @@ def test_gpu_arm_has_no_cpu_fallback():
         return
     r = _run("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_cpu_sample_wall_clock_limit(monkeypatch):
+    """The stacks workload's CPU sample can take the LU-per-pivot oracle minutes per env-step: bench.py runs it in a forked
+    child with a limit, kills that child by its PID and reports (env-steps asked for) / limit as an upper bound."""
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "_cpu_baseline", lambda *a: (time.sleep(a[0]) or (7.0, 3.0, a[0], {"env_steps": 8})))
+    assert bench._cpu_baseline_bounded(5, 0.05, 0, 0, 0, 0, 4, 2, 1) == (7.0, 3.0, 0.05, {"env_steps": 8}, False)
+    val, lps, el, c, capped = bench._cpu_baseline_bounded(0.5, 30.0, 0, 0, 0, 0, 4, 2, 1)
+    assert capped and val == 4 * 2 / 0.5 and el == 0.5 and c == {}
+    assert bench._cpu_baseline_bounded(None, 0.01, 0, 0, 0, 0, 4, 2, 1)[4] is False
+    assert bench.WORKLOADS["stacks"]["cpu_limit_s"] > 0 and "cpu_limit_s" not in bench.WORKLOADS["small"]
