@@ -212,14 +212,21 @@ __global__ void __launch_bounds__(256) lcp_cluster_kernel(LcpArgs a, int W) {
         }
         nlog++;
         __syncthreads();
-        {
-          int i = tid % n, cl = tid / n;
-          const int di = 256 % n, dc = 256 / n;
-          const int total = nown * n;
-          for (int e = tid; e < total; e += 256) {
-            Tl[e] = (i == r) ? rl[cl] : fma(-dvec[i], rl[cl], Tl[e]);
-            i += di; cl += dc;
-            if (i >= n) { i -= n; cl++; }
+        {                                                         // a warp per column, lanes down the rows: no index arithmetic per entry, the pivot-row entry is read once per column
+          const int lane = tid & 31;
+          for (int cl = tid >> 5; cl < nown; cl += 8) {
+            const double rv = rl[cl];
+            double* col = Tl + (size_t)cl * n;
+            int i = lane;
+            for (; i + 96 < n; i += 128) {
+              const double a0 = col[i], a1 = col[i + 32], a2 = col[i + 64], a3 = col[i + 96];
+              const double d0 = dvec[i], d1 = dvec[i + 32], d2 = dvec[i + 64], d3 = dvec[i + 96];
+              col[i] = (i == r) ? rv : fma(-d0, rv, a0);
+              col[i + 32] = (i + 32 == r) ? rv : fma(-d1, rv, a1);
+              col[i + 64] = (i + 64 == r) ? rv : fma(-d2, rv, a2);
+              col[i + 96] = (i + 96 == r) ? rv : fma(-d3, rv, a3);
+            }
+            for (; i < n; i += 32) col[i] = (i == r) ? rv : fma(-dvec[i], rv, col[i]);
           }
         }
         cluster.sync();                                           // the update is visible to the next pivot's remote reads
