@@ -19,7 +19,7 @@ def load(name):
     return np.array(rows)
 
 
-for name, every in (("sitting-box.dat", 200), ("sphere-stack.dat", 50), ("rimless-wheel.dat", 50), ("contact-constrained-pendulum.dat", 50)):
+for name, every in (("sitting-box.dat", 200), ("sphere-stack.dat", 10), ("rimless-wheel.dat", 50), ("contact-constrained-pendulum.dat", 50)):
     a = load(name)
     idx = sorted(set(list(range(0, 6)) + list(range(0, len(a), every)) + [len(a) - 1]))
     np.savetxt(os.path.join(OUT, "regress_" + name.replace(".dat", ".txt").replace("-", "_")), a[idx], fmt="%.6g",
